@@ -1,0 +1,190 @@
+"""Pins for the oracle.  The reference ships no golden vectors and PyG cannot be
+installed here ("parity unpinned", oracle/__init__.py), so the oracle is pinned by
+hand-computed known answers and by an independent dense-adjacency formulation."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle.buckgnn_oracle import (OracleBuckGNN, OracleGraphNetBlock, OracleSAGEConv, aggregate,
+                                   global_mean_pool, randomize_bn_stats, scatter_max, scatter_mean)
+from buckgnn_b200.synth import make_batch
+
+# 5 nodes, 2 graphs: graph 0 = {0,1,2} with hub 2; graph 1 = {3,4}, node 4 isolated (no in-edges)
+EI = torch.tensor([[0, 1, 2, 2, 0, 3],    # src
+                   [2, 2, 0, 1, 1, 3]])   # dst   (self loop on 3)
+X = torch.tensor([[1., 2.], [3., 4.], [5., 6.], [7., 8.], [9., 10.]])
+BATCH = torch.tensor([0, 0, 0, 1, 1])
+
+
+def test_kat_aggregations_by_hand():
+    # in-neighbours: 0<-{2}; 1<-{2,0}; 2<-{0,1}; 3<-{3}; 4<-{}
+    mean = torch.tensor([[5., 6.], [3., 4.], [2., 3.], [7., 8.], [0., 0.]])
+    add = torch.tensor([[5., 6.], [6., 8.], [4., 6.], [7., 8.], [0., 0.]])
+    mx = torch.tensor([[5., 6.], [5., 6.], [3., 4.], [7., 8.], [0., 0.]])
+    assert torch.equal(aggregate(X, EI, "mean"), mean)
+    assert torch.equal(aggregate(X, EI, "add"), add)
+    assert torch.equal(aggregate(X, EI, "sum"), add)
+    assert torch.equal(aggregate(X, EI, "max"), mx)
+
+
+def test_kat_max_negative_and_isolated():
+    src = torch.tensor([[-3.], [-1.], [-2.]])
+    out = scatter_max(src, torch.tensor([0, 0, 2]), 4)
+    assert out.flatten().tolist() == [-1., 0., -2., 0.]      # untouched rows stay 0, not -inf
+
+
+def test_kat_pooling_by_hand():
+    assert torch.equal(global_mean_pool(X, BATCH), torch.tensor([[3., 4.], [8., 9.]]))
+    assert torch.equal(global_mean_pool(X, None), torch.tensor([[5., 6.]]))
+    # dim_size larger than max index: empty rows are 0 (count clamped to 1)
+    assert torch.equal(scatter_mean(X, BATCH, 3)[2], torch.zeros(2))
+
+
+def test_kat_sage_conv_by_hand():
+    conv = OracleSAGEConv(2, 2, normalize=True, aggr="mean")
+    with torch.no_grad():
+        conv.lin_l.weight.copy_(torch.tensor([[1., 0.], [0., 2.]]))
+        conv.lin_l.bias.copy_(torch.tensor([0.5, -0.5]))
+        conv.lin_r.weight.copy_(torch.tensor([[0., 1.], [1., 0.]]))
+    out = conv(X, EI)
+    # node 1: agg=[3,4] -> lin_l=[3.5, 7.5]; lin_r(x1=[3,4])=[4,3]; sum=[7.5,10.5]; /norm
+    v = torch.tensor([7.5, 10.5]); assert torch.allclose(out[1], v / v.norm())
+    # node 4 (isolated): agg=0 -> lin_l = bias; lin_r(x4=[9,10])=[10,9]; sum=[10.5, 8.5]
+    v = torch.tensor([10.5, 8.5]); assert torch.allclose(out[4], v / v.norm())
+    assert "lin_r.bias" not in dict(conv.named_parameters())
+
+
+@pytest.mark.parametrize("aggr", ["mean", "add", "max"])
+def test_sage_conv_vs_dense_adjacency(aggr):
+    torch.manual_seed(1)
+    b = make_batch(2, nx=6, ny=5)
+    n = b.num_nodes
+    x = torch.randn(n, 8, dtype=torch.float64)
+    conv = OracleSAGEConv(8, 8, aggr=aggr).double()
+    A = torch.zeros(n, n, dtype=torch.float64)
+    A.index_put_((b.edge_index[1], b.edge_index[0]), torch.ones(b.num_edges, dtype=torch.float64), accumulate=True)
+    if aggr == "mean":
+        agg = (A @ x) / A.sum(1, keepdim=True).clamp(min=1)
+    elif aggr == "add":
+        agg = A @ x
+    else:
+        agg = torch.stack([x[A[i] > 0].max(0).values if (A[i] > 0).any() else torch.zeros(8, dtype=torch.float64)
+                           for i in range(n)])
+    want = F.normalize(agg @ conv.lin_l.weight.T + conv.lin_l.bias + x @ conv.lin_r.weight.T, dim=-1)
+    assert torch.allclose(conv(x, b.edge_index), want, atol=1e-12)
+
+
+def test_graphnet_block_vs_loop():
+    torch.manual_seed(2)
+    h = 4
+    blk = OracleGraphNetBlock(h).double()
+    x = torch.randn(5, h, dtype=torch.float64); e = torch.randn(6, h, dtype=torch.float64)
+    xo, eo = blk(x, EI, e)
+    row, col = EI
+    e_new = torch.stack([blk.edge_mlp(torch.cat([x[row[k]], x[col[k]], e[k]])) for k in range(6)])
+    msg = torch.stack([blk.node_mlp_phi(torch.cat([x[col[k]], e_new[k]])) for k in range(6)])
+    agg = torch.zeros(5, h, dtype=torch.float64)
+    for i in range(5):                       # aggregates on row = edge_index[0]
+        ks = [k for k in range(6) if row[k] == i]
+        if ks:
+            agg[i] = msg[ks].mean(0)
+    xg = blk.node_mlp_gamma(torch.cat([x, agg], 1))
+    assert torch.allclose(eo, e_new) and torch.allclose(xo, xg + blk.node_mlp_beta(xg))
+
+
+def _manifest(model):
+    return {k: tuple(v.shape) for k, v in model.state_dict().items()}
+
+
+def test_state_dict_manifest_graphsage_mean_512():
+    """SURVEY.md 8b key/shape manifest (reference registration order Models/BuckGNN.py:68-187)."""
+    m = _manifest(OracleBuckGNN(16, 5, 512, 6, "mean", model_name="GraphSage_meanAggr"))
+    want = {}
+    for name, dims in (("node_encoder", [(64, 16), (128, 64), (512, 128)]),
+                       ("edge_encoder", [(64, 5), (128, 64), (512, 128)]),
+                       ("decoder", [(128, 512), (64, 128), (1, 64)])):
+        for idx, d in zip((0, 2, 4), dims):
+            want[f"{name}.{idx}.weight"] = d
+            want[f"{name}.{idx}.bias"] = (d[0],)
+    for i in range(6):
+        want[f"sage_blocks_mean.{i}.lin_l.weight"] = (512, 512)
+        want[f"sage_blocks_mean.{i}.lin_l.bias"] = (512,)
+        want[f"sage_blocks_mean.{i}.lin_r.weight"] = (512, 512)
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            want[f"batch_norms.{i}.{k}"] = (512,)
+        want[f"batch_norms.{i}.num_batches_tracked"] = ()
+        want[f"sage_mlps.{i}.weight"] = (512, 512)
+        want[f"sage_mlps.{i}.bias"] = (512,)
+    for k in ("weight", "bias", "running_mean", "running_var"):
+        want[f"batch_norm.{k}"] = (512,)
+    want["batch_norm.num_batches_tracked"] = ()
+    want["pooling_mpl.mlp.0.weight"] = (512, 512)
+    want["pooling_mpl.mlp.0.bias"] = (512,)
+    assert m == want
+
+
+def test_forward_shapes_and_skip_rule():
+    torch.manual_seed(0)
+    b = make_batch(3, nx=6, ny=5)
+    m = OracleBuckGNN(16, 5, 256, 4, "mean", model_name="GraphSage_meanAggr").eval()
+    randomize_bn_stats(m)
+    with torch.no_grad():
+        pred, bb = m(b.x, b.edge_index, b.edge_attr, b.batch)
+        assert pred.shape == (3,) and bb is b.batch
+        one = make_batch(1, nx=6, ny=5)
+        p1, b1 = m(one.x, one.edge_index, one.edge_attr, None)
+        assert p1.dim() == 0 and b1 is None                 # .squeeze() -> 0-dim when G == 1
+        p1b, _ = m(one.x, one.edge_index, one.edge_attr, one.batch)
+        assert torch.allclose(p1, p1b, atol=1e-6)
+        # explicit re-statement of Models/BuckGNN.py:445-458, 515-516
+        x = m.node_encoder(b.x)
+        for i in range(4):
+            xp = x
+            x = torch.relu(m.batch_norms[i](m.sage_blocks_mean[i](x, b.edge_index)))
+            if 0 < i < 3:
+                x = x + xp
+        want = m.decoder(global_mean_pool(x, b.batch)).squeeze()
+        assert torch.allclose(pred, want, atol=1e-7)
+
+
+def test_graphs_are_independent():
+    """Block-diagonal batches: a graph's prediction does not depend on its batch mates
+    (the property multi-GPU graph sharding relies on)."""
+    torch.manual_seed(0)
+    m = OracleBuckGNN(16, 5, 256, 3, "mean", model_name="GraphSage_meanAggr").double().eval()
+    randomize_bn_stats(m)
+    b = make_batch(4, nx=7, ny=6)
+    solo = make_batch(1, first_index=2, nx=7, ny=6)
+    with torch.no_grad():
+        p, _ = m(b.x.double(), b.edge_index, b.edge_attr.double(), b.batch)
+        s, _ = m(solo.x.double(), solo.edge_index, solo.edge_attr.double(), solo.batch)
+    assert torch.allclose(p[2], s, atol=1e-12)
+
+
+@pytest.mark.parametrize("pool", ["mean", "mean_no_super", "supernode_only", "supernode_with_pooling", "mlp",
+                                  "mlp_no_super"])
+def test_pooling_variants_shapes(pool):
+    torch.manual_seed(0)
+    b = make_batch(3, nx=5, ny=5)
+    m = OracleBuckGNN(16, 5, 256, 2, pool, model_name="GraphSage_meanAggr").eval()
+    with torch.no_grad():
+        pred, _ = m(b.x, b.edge_index, b.edge_attr, b.batch)
+    assert pred.shape == (3,)
+
+
+def test_default_model_name_is_encoder_pool_decoder_only():
+    torch.manual_seed(0)
+    b = make_batch(2, nx=5, ny=5)
+    m = OracleBuckGNN(16, 5, 256, 6, "mean").eval()          # "GraphSAGE_MLP": matches no branch
+    with torch.no_grad():
+        pred, _ = m(b.x, b.edge_index, b.edge_attr, b.batch)
+        want = m.decoder(global_mean_pool(m.node_encoder(b.x), b.batch)).squeeze()
+    assert torch.equal(pred, want)
+
+
+def test_unknown_pooling_raises():
+    b = make_batch(1, nx=4, ny=4)
+    m = OracleBuckGNN(16, 5, 256, 1, "hybrid", model_name="GraphSage_meanAggr").eval()
+    with pytest.raises(ValueError, match="Unknown pooling layer"):
+        m(b.x, b.edge_index, b.edge_attr, b.batch)
