@@ -1,0 +1,185 @@
+"""ctypes binding of libbuckgnn_b200.so (include/buckgnn_b200.h).
+
+Pointers cross as plain integers (`tensor.data_ptr()`), sizes as int64, the CUDA
+stream as its integer handle.  A non-zero status raises `BuckGNNError` carrying
+bg_last_error().  If the library has not been built, loading raises -- there is no
+CPU or eager-PyTorch fallback for the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from .build import LIB_PATH
+
+BG_BF16, BG_F32 = 0, 1
+BG_AGGR_MEAN, BG_AGGR_SUM, BG_AGGR_MAX = 0, 1, 2
+BG_GEMM_BF16, BG_GEMM_TF32 = 0, 1
+BG_BIG_ROW_THRESHOLD = 64
+BG_MAX_GEMM_SEGMENTS = 6
+ABI_VERSION = 1
+
+AGGR_CODES = {"mean": BG_AGGR_MEAN, "sum": BG_AGGR_SUM, "add": BG_AGGR_SUM, "max": BG_AGGR_MAX}
+
+# every symbol include/buckgnn_b200.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "bg_abi_version", "bg_last_error", "bg_device_check", "bg_watchdog_info_host",
+    "bg_csr_max_big_rows", "bg_csr_workspace_bytes", "bg_csr_build",
+    "bg_batch_info", "bg_graph_ptr_build", "bg_encoder_front",
+    "bg_aggregate_workspace_bytes", "bg_sage_aggregate", "bg_gemm512",
+    "bg_pool_workspace_bytes", "bg_pool_head", "bg_cast_f32_to_bf16", "bg_split_tf32",
+)
+
+
+class BuckGNNError(RuntimeError):
+    def __init__(self, status: int, where: str, message: str):
+        super().__init__(f"{where} failed with status {status}: {message}")
+        self.status = status
+
+
+class GemmSegment(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("lda", C.c_int64), ("b", C.c_void_p), ("ldb", C.c_int64),
+                ("k", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("bias", C.c_void_p), ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
+                ("residual", C.c_void_p), ("ldr", C.c_int64), ("normalize", C.c_int32), ("relu", C.c_int32)]
+
+
+_lib = None
+_lock = threading.Lock()
+_P, _I64, _I32, _SZP = C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_size_t)
+
+_SIGNATURES = {
+    "bg_abi_version": (C.c_int, []),
+    "bg_last_error": (C.c_char_p, []),
+    "bg_device_check": (C.c_int, []),
+    "bg_watchdog_info_host": (C.c_int, [C.POINTER(C.c_uint32)]),
+    "bg_csr_max_big_rows": (_I64, [_I64]),
+    "bg_csr_workspace_bytes": (C.c_int, [_I64, _I64, _SZP]),
+    "bg_csr_build": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "bg_batch_info": (C.c_int, [_P, _I64, _P, _P]),
+    "bg_graph_ptr_build": (C.c_int, [_P, _I64, _I64, _P, _P]),
+    "bg_encoder_front": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "bg_aggregate_workspace_bytes": (C.c_int, [_I32, _SZP]),
+    "bg_sage_aggregate": (C.c_int, [_P, _P, C.c_int, _I64, _P, _P, _P, _I32, C.c_int, _P, C.c_size_t, _P]),
+    "bg_gemm512": (C.c_int, [C.POINTER(GemmSegment), _I32, _I64, C.c_int, C.POINTER(Epilogue), _P, C.c_int,
+                             _I64, C.c_int, _P]),
+    "bg_pool_workspace_bytes": (C.c_int, [_I64, _SZP]),
+    "bg_pool_head": (C.c_int, [_P, C.c_int, _I64, _P, _I64, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P,
+                               C.c_size_t, _P]),
+    "bg_cast_f32_to_bf16": (C.c_int, [_P, _P, _I64, _P]),
+    "bg_split_tf32": (C.c_int, [_P, _P, _P, _I64, _P]),
+}
+
+
+def library_path() -> str:
+    return LIB_PATH
+
+
+def load():
+    """dlopen the in-tree library (once).  Raises if it is missing or has the wrong ABI."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise BuckGNNError(-100, "load", f"{LIB_PATH} not built: run `python -m buckgnn_b200.build` "
+                               "(the BuckGNN hot path has no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.bg_abi_version() != ABI_VERSION:
+            raise BuckGNNError(-101, "load", f"ABI version mismatch: library {lib.bg_abi_version()}, binding {ABI_VERSION}")
+        _lib = lib
+        return lib
+
+
+def last_error() -> str:
+    return load().bg_last_error().decode("utf-8", "replace")
+
+
+def _check(status: int, where: str) -> None:
+    if status != 0:
+        raise BuckGNNError(status, where, last_error())
+
+
+def device_check() -> None:
+    _check(load().bg_device_check(), "bg_device_check")
+
+
+def watchdog_info():
+    buf = (C.c_uint32 * 4)()
+    _check(load().bg_watchdog_info_host(buf), "bg_watchdog_info_host")
+    return list(buf)
+
+
+def csr_max_big_rows(n_edges: int) -> int:
+    return int(load().bg_csr_max_big_rows(n_edges))
+
+
+def _query(fn_name: str, *args) -> int:
+    out = C.c_size_t(0)
+    _check(getattr(load(), fn_name)(*args, C.byref(out)), fn_name)
+    return int(out.value)
+
+
+def csr_workspace_bytes(n_nodes: int, n_edges: int) -> int:
+    return _query("bg_csr_workspace_bytes", n_nodes, n_edges)
+
+
+def aggregate_workspace_bytes(n_big: int) -> int:
+    return _query("bg_aggregate_workspace_bytes", n_big)
+
+
+def pool_workspace_bytes(n_graphs: int) -> int:
+    return _query("bg_pool_workspace_bytes", n_graphs)
+
+
+def csr_build(edge_index, n_edges, n_nodes, key_row, rowptr, col, perm, big_rows, info, ws, ws_bytes, stream):
+    _check(load().bg_csr_build(edge_index, n_edges, n_nodes, key_row, rowptr, col, perm, big_rows, info,
+                               ws, ws_bytes, stream), "bg_csr_build")
+
+
+def batch_info(batch, n_nodes, info, stream):
+    _check(load().bg_batch_info(batch, n_nodes, info, stream), "bg_batch_info")
+
+
+def graph_ptr_build(batch, n_nodes, n_graphs, graph_ptr, stream):
+    _check(load().bg_graph_ptr_build(batch, n_nodes, n_graphs, graph_ptr, stream), "bg_graph_ptr_build")
+
+
+def encoder_front(x, n_nodes, n_features, w1, b1, w2, b2, out, out_dtype, stream):
+    _check(load().bg_encoder_front(x, n_nodes, n_features, w1, b1, w2, b2, out, out_dtype, stream),
+           "bg_encoder_front")
+
+
+def sage_aggregate(x, out, dtype, n_nodes, rowptr, col, big_rows, n_big, aggr, ws, ws_bytes, stream):
+    _check(load().bg_sage_aggregate(x, out, dtype, n_nodes, rowptr, col, big_rows, n_big, aggr, ws, ws_bytes,
+                                    stream), "bg_sage_aggregate")
+
+
+def gemm512(segments, m, mode, out, out_dtype, ldo, stream, *, bias=None, bn_scale=None, bn_shift=None,
+            residual=None, ldr=0, normalize=False, relu=False, cta_group=2):
+    """segments: list of (a_ptr, lda, b_ptr, ldb, k)."""
+    n = len(segments)
+    arr = (GemmSegment * n)(*[GemmSegment(a, lda, b, ldb, k, 0) for (a, lda, b, ldb, k) in segments])
+    epi = Epilogue(bias, bn_scale, bn_shift, residual, ldr, int(bool(normalize)), int(bool(relu)))
+    _check(load().bg_gemm512(arr, n, m, mode, C.byref(epi), out, out_dtype, ldo, cta_group, stream), "bg_gemm512")
+
+
+def pool_head(x, dtype, n_nodes, graph_ptr, n_graphs, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out,
+              ws, ws_bytes, stream):
+    _check(load().bg_pool_head(x, dtype, n_nodes, graph_ptr, n_graphs, w1, b1, w2, b2, w3, b3, out_dim, pred,
+                               pooled_out, ws, ws_bytes, stream), "bg_pool_head")
+
+
+def cast_f32_to_bf16(src, dst, n, stream):
+    _check(load().bg_cast_f32_to_bf16(src, dst, n, stream), "bg_cast_f32_to_bf16")
+
+
+def split_tf32(src, hi, lo, n, stream):
+    _check(load().bg_split_tf32(src, hi, lo, n, stream), "bg_split_tf32")

@@ -1,0 +1,198 @@
+// K2: neighbourhood aggregation over the CSR of K1 (mean / sum / max), 512 columns.
+//
+// Replaces `x.index_select(0, src)` + `scatter_add_` + `/ clamp(count, 1)` inside
+// PyG SAGEConv.propagate (reference call sites Models/BuckGNN.py:342,393,434,449,463).
+// HBM/L2-bandwidth bound: every source row is read once from HBM (re-reads by the
+// ~6 rows that share it hit L2/L1), the aggregate row is written once.
+//
+//  * normal rows: one warp per row; a lane owns 16 of the 512 columns and reads
+//    them with 128-bit loads, so one warp-wide load instruction covers 512
+//    contiguous bytes of a source row; neighbour indices are fetched 32 at a time
+//    and broadcast by shuffle; 4 neighbours are in flight per lane.  fp32
+//    accumulation in CSR order = ascending edge id (deterministic).
+//  * hub rows (degree > 64: the super node, degree = graph size): split into
+//    kHubSlices slices, one CTA per (hub, slice) writes an fp32 partial; the last
+//    CTA to finish a hub (atomic ticket) reduces the partials in slice order and
+//    writes the row -- no warp ever walks a 4k-32k neighbour list alone, and the
+//    result does not depend on scheduling.
+#pragma once
+#include "common.cuh"
+
+namespace bg {
+
+constexpr int kHubSlices = 16;
+constexpr int kAggWarpsPerBlock = 8;
+
+template <int kAggr> BG_DEVINL float agg_init() { return kAggr == BG_AGGR_MAX ? -INFINITY : 0.f; }
+template <int kAggr> BG_DEVINL float agg_op(float a, float b) {
+  if constexpr (kAggr == BG_AGGR_MAX) return fmaxf(a, b); else return a + b;
+}
+
+// ---- per-lane row fragments: 16 values of one 512-wide row -------------------------------
+// bf16: two 16-byte chunks at columns [8*lane, +8) and [256 + 8*lane, +8)
+// f32 : four 16-byte chunks at columns [4*lane + 128*j, +4), j = 0..3
+template <typename T> struct RowFrag;
+
+template <> struct RowFrag<__nv_bfloat16> {
+  uint4 q[2];
+  BG_DEVINL void load(const __nv_bfloat16* row, int lane) {
+    const uint4* p = reinterpret_cast<const uint4*>(row);
+    q[0] = ldg_v4(p + lane);
+    q[1] = ldg_v4(p + 32 + lane);
+  }
+  template <int kAggr> BG_DEVINL void accumulate(float (&acc)[16]) const {
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(q);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[2 * i] = agg_op<kAggr>(acc[2 * i], bf16_lo(u[i]));
+      acc[2 * i + 1] = agg_op<kAggr>(acc[2 * i + 1], bf16_hi(u[i]));
+    }
+  }
+  static BG_DEVINL void store(__nv_bfloat16* row, int lane, const float (&v)[16]) {
+    uint4 a, b;
+    a.x = pack_bf16(v[0], v[1]);  a.y = pack_bf16(v[2], v[3]);  a.z = pack_bf16(v[4], v[5]);  a.w = pack_bf16(v[6], v[7]);
+    b.x = pack_bf16(v[8], v[9]);  b.y = pack_bf16(v[10], v[11]); b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
+    uint4* p = reinterpret_cast<uint4*>(row);
+    stg_v4(p + lane, a);
+    stg_v4(p + 32 + lane, b);
+  }
+  // column of accumulator slot i for this lane
+  static BG_DEVINL int col_of(int lane, int i) { return (i < 8) ? (8 * lane + i) : (256 + 8 * lane + (i - 8)); }
+};
+
+template <> struct RowFrag<float> {
+  uint4 q[4];
+  BG_DEVINL void load(const float* row, int lane) {
+    const uint4* p = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = ldg_v4(p + 32 * j + lane);
+  }
+  template <int kAggr> BG_DEVINL void accumulate(float (&acc)[16]) const {
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(q);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = agg_op<kAggr>(acc[i], __uint_as_float(u[i]));
+  }
+  static BG_DEVINL void store(float* row, int lane, const float (&v)[16]) {
+    uint4* p = reinterpret_cast<uint4*>(row);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 a;
+      a.x = __float_as_uint(v[4 * j]); a.y = __float_as_uint(v[4 * j + 1]);
+      a.z = __float_as_uint(v[4 * j + 2]); a.w = __float_as_uint(v[4 * j + 3]);
+      stg_v4(p + 32 * j + lane, a);
+    }
+  }
+  static BG_DEVINL int col_of(int lane, int i) { return 128 * (i >> 2) + 4 * lane + (i & 3); }
+};
+
+// accumulate rows col[beg..end) of x into acc, in order
+template <typename T, int kAggr>
+BG_DEVINL void gather_range(const T* __restrict__ x, const int32_t* __restrict__ col, int32_t beg, int32_t end,
+                            int lane, float (&acc)[16]) {
+  for (int32_t base = beg; base < end; base += 32) {
+    const int32_t cnt = min(32, end - base);
+    const int32_t my = (lane < cnt) ? col[base + lane] : 0;
+    int32_t j = 0;
+    for (; j + 4 <= cnt; j += 4) {
+      RowFrag<T> f0, f1, f2, f3;
+      f0.load(x + (size_t)__shfl_sync(0xffffffffu, my, j) * kHidden, lane);
+      f1.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 1) * kHidden, lane);
+      f2.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 2) * kHidden, lane);
+      f3.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 3) * kHidden, lane);
+      f0.template accumulate<kAggr>(acc);
+      f1.template accumulate<kAggr>(acc);
+      f2.template accumulate<kAggr>(acc);
+      f3.template accumulate<kAggr>(acc);
+    }
+    for (; j < cnt; ++j) {
+      RowFrag<T> f;
+      f.load(x + (size_t)__shfl_sync(0xffffffffu, my, j) * kHidden, lane);
+      f.template accumulate<kAggr>(acc);
+    }
+  }
+}
+
+template <int kAggr> BG_DEVINL void agg_finalize(float (&acc)[16], int32_t deg) {
+  if constexpr (kAggr == BG_AGGR_MEAN) {
+    const float d = (float)max(deg, 1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = acc[i] / d;     // true division, as `sum / count` does
+  } else if constexpr (kAggr == BG_AGGR_MAX) {
+    if (deg == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    }
+  }
+}
+
+template <typename T, int kAggr>
+__global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
+k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N,
+                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * kAggWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * kAggWarpsPerBlock;
+  for (int64_t r = warp; r < N; r += n_warps) {
+    const int32_t beg = rowptr[r], end = rowptr[r + 1];
+    if (end - beg > kBigRowThreshold) continue;             // hub rows: k_aggregate_hubs
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = agg_init<kAggr>();
+    gather_range<T, kAggr>(x, col, beg, end, lane, acc);
+    agg_finalize<kAggr>(acc, end - beg);
+    RowFrag<T>::store(out + (size_t)r * kHidden, lane, acc);
+  }
+}
+
+// grid = n_big * kHubSlices CTAs of 8 warps; partial [n_big][kHubSlices][512] f32; ticket [n_big] (zeroed)
+template <typename T, int kAggr>
+__global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
+k_aggregate_hubs(const T* __restrict__ x, T* __restrict__ out,
+                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                 const int32_t* __restrict__ big_rows, int32_t n_big,
+                 float* __restrict__ partial, int32_t* __restrict__ ticket) {
+  __shared__ float red[kAggWarpsPerBlock][kHidden];
+  __shared__ int32_t is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int32_t hub = blockIdx.x / kHubSlices, slice = blockIdx.x % kHubSlices;
+  if (hub >= n_big) return;
+  const int32_t r = big_rows[hub];
+  const int32_t beg = rowptr[r], deg = rowptr[r + 1] - beg;
+  // slice -> contiguous neighbour range; warp -> contiguous sub-range (order-preserving split)
+  const int32_t s_beg = beg + (int32_t)((int64_t)deg * slice / kHubSlices);
+  const int32_t s_end = beg + (int32_t)((int64_t)deg * (slice + 1) / kHubSlices);
+  const int32_t s_len = s_end - s_beg;
+  const int32_t w_beg = s_beg + (int32_t)((int64_t)s_len * warp / kAggWarpsPerBlock);
+  const int32_t w_end = s_beg + (int32_t)((int64_t)s_len * (warp + 1) / kAggWarpsPerBlock);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = agg_init<kAggr>();
+  gather_range<T, kAggr>(x, col, w_beg, w_end, lane, acc);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) red[warp][RowFrag<T>::col_of(lane, i)] = acc[i];
+  __syncthreads();
+  float* my_partial = partial + ((size_t)hub * kHubSlices + slice) * kHidden;
+  for (int c = threadIdx.x; c < kHidden; c += blockDim.x) {
+    float v = red[0][c];
+#pragma unroll
+    for (int w = 1; w < kAggWarpsPerBlock; ++w) v = agg_op<kAggr>(v, red[w][c]);
+    my_partial[c] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(&ticket[hub], 1) == kHubSlices - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float* hp = partial + (size_t)hub * kHubSlices * kHidden;
+  T* orow = out + (size_t)r * kHidden;
+  for (int c = threadIdx.x; c < kHidden; c += blockDim.x) {
+    float v = __ldcg(hp + c);
+    for (int s = 1; s < kHubSlices; ++s) v = agg_op<kAggr>(v, __ldcg(hp + (size_t)s * kHidden + c));
+    if constexpr (kAggr == BG_AGGR_MEAN) v = v / (float)max(deg, 1);
+    if constexpr (sizeof(T) == 2) orow[c] = __float2bfloat16_rn(v); else orow[c] = v;
+  }
+  if (threadIdx.x == 0) ticket[hub] = 0;    // leave the ticket ready for the next launch
+}
+
+}  // namespace bg

@@ -1,0 +1,355 @@
+// C-ABI entry points of libbuckgnn_b200.so (declared in include/buckgnn_b200.h).
+// Unity build: the kernels live in the .cuh files included here.
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "csr_build.cuh"
+#include "aggregate.cuh"
+#include "encoder.cuh"
+#include "gemm_tc.cuh"
+#include "pool_head.cuh"
+
+namespace bg {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_cuda_error(cudaError_t e, const char* what, const char* file, int line) {
+  snprintf(g_last_error, sizeof(g_last_error), "CUDA error %d (%s) at %s:%d: %s", (int)e,
+           cudaGetErrorString(e), file, line, what);
+}
+static int fail(int code, const char* msg) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s", msg);
+  return code;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+PFN_tensorMapEncodeTiled get_tensor_map_encoder() {
+  static PFN_tensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tensorMapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__global__ void k_cast_f32_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void k_split_tf32(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = src[i];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+static inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
+  int64_t b = ceil_div64(n > 0 ? n : 1, threads);
+  return (unsigned)(b < max_blocks ? b : max_blocks);
+}
+
+template <typename T>
+static int aggregate_dispatch(const T* x, T* out, int64_t N, const int32_t* rowptr, const int32_t* col,
+                              const int32_t* big_rows, int32_t n_big, int aggr, float* partial, int32_t* ticket,
+                              cudaStream_t stream) {
+  const unsigned grid = (unsigned)min64(ceil_div64(N, kAggWarpsPerBlock), (int64_t)sm_count() * 32);
+  const unsigned hub_grid = (unsigned)n_big * kHubSlices;
+#define BG_AGG_CASE(A)                                                                                       \
+  case A:                                                                                                    \
+    k_aggregate_rows<T, A><<<grid, kAggWarpsPerBlock * 32, 0, stream>>>(x, out, N, rowptr, col);             \
+    if (n_big > 0)                                                                                           \
+      k_aggregate_hubs<T, A><<<hub_grid, kAggWarpsPerBlock * 32, 0, stream>>>(x, out, rowptr, col, big_rows, \
+                                                                              n_big, partial, ticket);      \
+    break;
+  switch (aggr) {
+    BG_AGG_CASE(BG_AGGR_MEAN)
+    BG_AGG_CASE(BG_AGGR_SUM)
+    BG_AGG_CASE(BG_AGGR_MAX)
+    default: return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad aggr");
+  }
+#undef BG_AGG_CASE
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+
+}  // namespace bg
+
+using namespace bg;
+
+extern "C" {
+
+int bg_abi_version(void) { return BG_ABI_VERSION; }
+const char* bg_last_error(void) { return g_last_error; }
+
+int bg_device_check(void) {
+  int dev = 0;
+  BG_CUDA_OK(cudaGetDevice(&dev));
+  int major = 0;
+  BG_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(BG_ERR_DEVICE, "buckgnn_b200 kernels are built for sm_100a only");
+  return BG_OK;
+}
+
+int bg_watchdog_info_host(uint32_t* out4_host) {
+  if (!out4_host) return fail(BG_ERR_INVALID, "null output");
+  BG_CUDA_OK(cudaMemcpyFromSymbol(out4_host, g_watchdog_info, 16));
+  return BG_OK;
+}
+
+// ------------------------------------------------------------------ K1
+int64_t bg_csr_max_big_rows(int64_t n_edges) { return n_edges / (BG_BIG_ROW_THRESHOLD + 1) + 1; }
+
+int bg_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, size_t* bytes_host) {
+  if (!bytes_host || n_nodes < 0 || n_edges < 0) return fail(BG_ERR_INVALID, "bg_csr_workspace_bytes: bad argument");
+  *bytes_host = csr_workspace_layout(nullptr, n_nodes).bytes;
+  return BG_OK;
+}
+
+int bg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int key_row,
+                 int32_t* rowptr, int32_t* col, int32_t* perm, int32_t* big_rows, int32_t* info,
+                 void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (E < 0 || N < 0 || E >= 0x7fffffffLL || N >= 0x7fffffffLL) return fail(BG_ERR_INVALID, "bg_csr_build: sizes out of range");
+  if (key_row != 0 && key_row != 1) return fail(BG_ERR_INVALID, "bg_csr_build: key_row must be 0 or 1");
+  if (!rowptr || !info || !workspace || (E > 0 && (!edge_index || !col || !perm || !big_rows)))
+    return fail(BG_ERR_INVALID, "bg_csr_build: null pointer");
+  CsrWorkspace w = csr_workspace_layout(workspace, N);
+  if (workspace_bytes < w.bytes) return fail(BG_ERR_WORKSPACE, "bg_csr_build: workspace too small");
+  const int64_t* key = edge_index + (size_t)key_row * E;
+  const int64_t* other = edge_index + (size_t)(1 - key_row) * E;
+  const int max_big = (int)bg_csr_max_big_rows(E);
+  const int sms = sm_count();
+  BG_CUDA_OK(cudaMemsetAsync(w.deg, 0, sizeof(int32_t) * (size_t)(N + 1), stream));
+  BG_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t) * 2, stream));
+  BG_CUDA_OK(cudaMemsetAsync(rowptr, 0, sizeof(int32_t), stream));           // covers N == 0
+  if (N == 0) return BG_OK;
+  if (E > 0) {
+    k_csr_hist<<<grid_for(E, 256, sms * 16), 256, 0, stream>>>(key, E, N, w.deg, info);
+    BG_LAUNCH_OK();
+  }
+  k_scan_block_sums<<<w.n_scan_blocks, 1024, 0, stream>>>(w.deg, N, w.block_sums);
+  BG_LAUNCH_OK();
+  k_scan_of_sums<<<1, 1024, 0, stream>>>(w.block_sums, w.n_scan_blocks);
+  BG_LAUNCH_OK();
+  k_scan_apply<<<w.n_scan_blocks, 1024, 0, stream>>>(w.deg, N, w.block_sums, rowptr, w.cursor, big_rows, info, max_big);
+  BG_LAUNCH_OK();
+  if (E > 0) {
+    k_csr_fill<<<grid_for(E, 256, sms * 16), 256, 0, stream>>>(key, E, N, w.cursor, perm);
+    BG_LAUNCH_OK();
+    k_csr_sort_small<<<(unsigned)ceil_div64(N, 256), 256, 0, stream>>>(rowptr, N, other, perm, col);
+    BG_LAUNCH_OK();
+    static bool attr_set = false;
+    const int sort_smem = kSortSmemElems * (int)sizeof(int32_t);
+    if (!attr_set) {
+      BG_CUDA_OK(cudaFuncSetAttribute(k_csr_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, sort_smem));
+      attr_set = true;
+    }
+    k_csr_sort_big<<<sms, 1024, sort_smem, stream>>>(rowptr, big_rows, info, max_big, other, perm, col);
+    BG_LAUNCH_OK();
+  }
+  return BG_OK;
+}
+
+int bg_batch_info(const int64_t* batch, int64_t N, int32_t* info, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!info || N < 0 || (N > 0 && !batch)) return fail(BG_ERR_INVALID, "bg_batch_info: bad argument");
+  BG_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t) * 2, stream));
+  if (N == 0) return BG_OK;
+  k_batch_info<<<grid_for(N, 256, sm_count() * 8), 256, 0, stream>>>(batch, N, info);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_graph_ptr_build(const int64_t* batch, int64_t N, int64_t G, int32_t* graph_ptr, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!graph_ptr || N < 0 || G < 0 || (N > 0 && !batch)) return fail(BG_ERR_INVALID, "bg_graph_ptr_build: bad argument");
+  k_graph_ptr<<<grid_for(N + 1, 256, sm_count() * 8), 256, 0, stream>>>(batch, N, G, graph_ptr);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+// ------------------------------------------------------------------ K5 front
+int bg_encoder_front(const float* x, int64_t N, int32_t F, const float* w1, const float* b1,
+                     const float* w2, const float* b2, void* out, int out_dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N < 0 || F <= 0 || F > kEncMaxF) return fail(BG_ERR_UNSUPPORTED, "bg_encoder_front: need 0 < n_features <= 32");
+  if (N == 0) return BG_OK;
+  if (!x || !w1 || !b1 || !w2 || !b2 || !out || !aligned16(out)) return fail(BG_ERR_INVALID, "bg_encoder_front: bad pointer");
+  const int smem = (int)sizeof(EncoderSmem);
+  const unsigned grid = (unsigned)min64(ceil_div64(N, kEncRows), (int64_t)sm_count() * 3);
+  if (out_dtype == BG_BF16) {
+    static bool set = false;
+    if (!set) { BG_CUDA_OK(cudaFuncSetAttribute(k_encoder_front<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+    k_encoder_front<__nv_bfloat16><<<grid, kEncThreads, smem, stream>>>(x, N, F, w1, b1, w2, b2, static_cast<__nv_bfloat16*>(out));
+  } else if (out_dtype == BG_F32) {
+    static bool set = false;
+    if (!set) { BG_CUDA_OK(cudaFuncSetAttribute(k_encoder_front<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+    k_encoder_front<float><<<grid, kEncThreads, smem, stream>>>(x, N, F, w1, b1, w2, b2, static_cast<float*>(out));
+  } else {
+    return fail(BG_ERR_INVALID, "bg_encoder_front: bad out_dtype");
+  }
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+// ------------------------------------------------------------------ K2
+int bg_aggregate_workspace_bytes(int32_t n_big, size_t* bytes_host) {
+  if (!bytes_host || n_big < 0) return fail(BG_ERR_INVALID, "bg_aggregate_workspace_bytes: bad argument");
+  *bytes_host = (size_t)n_big * kHubSlices * kHidden * sizeof(float) + (size_t)n_big * sizeof(int32_t) + 256;
+  return BG_OK;
+}
+
+int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t N, const int32_t* rowptr, const int32_t* col,
+                      const int32_t* big_rows, int32_t n_big, int aggr, void* workspace, size_t workspace_bytes,
+                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N < 0 || n_big < 0) return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad size");
+  if (N == 0) return BG_OK;
+  if (!x || !out || !rowptr || !aligned16(x) || !aligned16(out)) return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad pointer");
+  float* partial = nullptr;
+  int32_t* ticket = nullptr;
+  if (n_big > 0) {
+    size_t need = 0;
+    bg_aggregate_workspace_bytes(n_big, &need);
+    if (!workspace || workspace_bytes < need || !big_rows) return fail(BG_ERR_WORKSPACE, "bg_sage_aggregate: workspace too small");
+    partial = static_cast<float*>(workspace);
+    ticket = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + (size_t)n_big * kHubSlices * kHidden * sizeof(float));
+    BG_CUDA_OK(cudaMemsetAsync(ticket, 0, sizeof(int32_t) * (size_t)n_big, stream));
+  }
+  if (dtype == BG_BF16)
+    return aggregate_dispatch(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, rowptr, col,
+                              big_rows, n_big, aggr, partial, ticket, stream);
+  if (dtype == BG_F32)
+    return aggregate_dispatch(static_cast<const float*>(x), static_cast<float*>(out), N, rowptr, col, big_rows, n_big,
+                              aggr, partial, ticket, stream);
+  return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad dtype");
+}
+
+// ------------------------------------------------------------------ K3
+int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int mode, const bg_epilogue* epi,
+               void* out, int out_dtype, int64_t ldo, int cta_group, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!segs || n_seg < 1 || n_seg > BG_MAX_GEMM_SEGMENTS) return fail(BG_ERR_INVALID, "bg_gemm512: bad segment count");
+  if (m < 0 || m >= 0x7fffffffLL) return fail(BG_ERR_INVALID, "bg_gemm512: bad m");
+  if (m == 0) return BG_OK;
+  if (mode != BG_GEMM_BF16 && mode != BG_GEMM_TF32) return fail(BG_ERR_INVALID, "bg_gemm512: bad mode");
+  if (out_dtype != BG_BF16 && out_dtype != BG_F32) return fail(BG_ERR_INVALID, "bg_gemm512: bad out_dtype");
+  if (cta_group != 1 && cta_group != 2) return fail(BG_ERR_INVALID, "bg_gemm512: cta_group must be 1 or 2");
+  const bool tf32 = mode == BG_GEMM_TF32;
+  const int esz = tf32 ? 4 : 2, osz = out_dtype == BG_F32 ? 4 : 2;
+  const int kblk = kStageKBytes / esz;
+  if (!out || !aligned16(out) || (ldo * osz) % 16 != 0 || ldo < kHidden) return fail(BG_ERR_INVALID, "bg_gemm512: bad out/ldo");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  for (int s = 0; s < n_seg; ++s) {
+    const bg_gemm_segment& g = segs[s];
+    if (!g.a || !g.b || g.k <= 0 || g.k % kblk != 0) return fail(BG_ERR_UNSUPPORTED, "bg_gemm512: k must be a positive multiple of 64 (bf16) / 32 (tf32)");
+    if (!aligned16(g.a) || !aligned16(g.b) || (g.lda * esz) % 16 != 0 || (g.ldb * esz) % 16 != 0 || g.lda < g.k || g.ldb < g.k)
+      return fail(BG_ERR_INVALID, "bg_gemm512: operand alignment / leading dimension");
+    int rc = make_operand_map(&p.seg[s].a, g.a, m, g.k, g.lda, tf32);
+    if (rc == BG_OK) rc = make_operand_map(&p.seg[s].b, g.b, kHidden, g.k, g.ldb, tf32);
+    if (rc != BG_OK) return fail(rc, "bg_gemm512: cuTensorMapEncodeTiled failed");
+    p.kblocks[s] = g.k / kblk;
+  }
+  p.n_seg = n_seg;
+  p.k_elems_per_block = kblk;
+  p.n_tiles = (int32_t)ceil_div64(m, kTileM * cta_group);
+  p.m = m;
+  if (epi) {
+    if (epi->residual && (!aligned16(epi->residual) || (epi->ldr * osz) % 16 != 0 || epi->ldr < kHidden))
+      return fail(BG_ERR_INVALID, "bg_gemm512: bad residual/ldr");
+    if (epi->bn_scale && !epi->bn_shift) return fail(BG_ERR_INVALID, "bg_gemm512: bn_scale without bn_shift");
+    p.bias = epi->bias; p.bn_scale = epi->bn_scale; p.bn_shift = epi->bn_shift;
+    p.residual = epi->residual; p.ldr = epi->ldr; p.normalize = epi->normalize; p.relu = epi->relu;
+  }
+  p.out = out; p.ldo = ldo;
+  const int key = (cta_group == 2 ? 4 : 0) | (tf32 ? 2 : 0) | (out_dtype == BG_F32 ? 1 : 0);
+  switch (key) {
+    case 0: return launch_gemm512<1, false, __nv_bfloat16>(p, stream);
+    case 1: return launch_gemm512<1, false, float>(p, stream);
+    case 2: return launch_gemm512<1, true, __nv_bfloat16>(p, stream);
+    case 3: return launch_gemm512<1, true, float>(p, stream);
+    case 4: return launch_gemm512<2, false, __nv_bfloat16>(p, stream);
+    case 5: return launch_gemm512<2, false, float>(p, stream);
+    case 6: return launch_gemm512<2, true, __nv_bfloat16>(p, stream);
+    default: return launch_gemm512<2, true, float>(p, stream);
+  }
+}
+
+// ------------------------------------------------------------------ K4
+int bg_pool_workspace_bytes(int64_t G, size_t* bytes_host) {
+  if (!bytes_host || G < 0) return fail(BG_ERR_INVALID, "bg_pool_workspace_bytes: bad argument");
+  *bytes_host = (size_t)G * kPoolSlices * kHidden * sizeof(float) + 256;
+  return BG_OK;
+}
+
+int bg_pool_head(const void* x, int dtype, int64_t N, const int32_t* graph_ptr, int64_t G,
+                 const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
+                 int32_t out_dim, float* pred, float* pooled_out, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (G < 0 || N < 0 || G > 65535LL * 1024) return fail(BG_ERR_INVALID, "bg_pool_head: bad size");
+  if (G == 0) return BG_OK;
+  if (out_dim < 1 || out_dim > 64) return fail(BG_ERR_UNSUPPORTED, "bg_pool_head: out_dim must be in [1,64]");
+  if (!graph_ptr || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !pred || (N > 0 && (!x || !aligned16(x))) || !aligned16(w1))
+    return fail(BG_ERR_INVALID, "bg_pool_head: bad pointer");
+  size_t need = 0;
+  bg_pool_workspace_bytes(G, &need);
+  if (!workspace || workspace_bytes < need) return fail(BG_ERR_WORKSPACE, "bg_pool_head: workspace too small");
+  float* partial = static_cast<float*>(workspace);
+  dim3 grid((unsigned)G, kPoolSlices);
+  if (dtype == BG_BF16)
+    k_pool_partial<__nv_bfloat16><<<grid, kPoolWarps * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), graph_ptr, partial);
+  else if (dtype == BG_F32)
+    k_pool_partial<float><<<grid, kPoolWarps * 32, 0, stream>>>(static_cast<const float*>(x), graph_ptr, partial);
+  else
+    return fail(BG_ERR_INVALID, "bg_pool_head: bad dtype");
+  BG_LAUNCH_OK();
+  k_pool_head<<<(unsigned)G, 128, 0, stream>>>(partial, graph_ptr, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+// ------------------------------------------------------------------ helpers
+int bg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n < 0 || (n > 0 && (!src || !dst))) return fail(BG_ERR_INVALID, "bg_cast_f32_to_bf16: bad argument");
+  if (n == 0) return BG_OK;
+  k_cast_f32_bf16<<<grid_for(n, 256, sm_count() * 8), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n < 0 || (n > 0 && (!src || !hi || !lo))) return fail(BG_ERR_INVALID, "bg_split_tf32: bad argument");
+  if (n == 0) return BG_OK;
+  k_split_tf32<<<grid_for(n, 256, sm_count() * 8), 256, 0, stream>>>(src, hi, lo, n);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+"""The BuckGNN forward as a sequence of C-ABI calls on the current CUDA stream.
+
+torch is used here for device memory (caching allocator), streams and nothing else:
+every arithmetic step of the hot path is one of the hand-written kernels behind
+include/buckgnn_b200.h.  There is no fallback: a CPU tensor or a missing library
+raises.
+
+Reference path restated (Models/BuckGNN.py):
+  :323      node_encoder            -> bg_encoder_front + bg_gemm512 (128 -> 512)
+  :445-458  GraphSAGE layer loop    -> per layer bg_sage_aggregate + bg_gemm512 with the
+                                       fused bias / L2-normalize / BN / ReLU / skip epilogue
+  :274,515  global_mean_pool+decoder-> bg_pool_head
+The CSR (bg_csr_build) and graph offsets (bg_graph_ptr_build) are rebuilt from the raw
+`edge_index` / `batch` on every call unless the caller opts into `cache_index`.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import capi
+
+PRECISIONS = ("bf16", "tf32", "fp32")   # fp32 = 3xTF32 split ("fp32-GEMM mode")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"buckgnn_b200: `{name}` must be a CUDA tensor (got {t.device}); the hot path has "
+                           "no CPU implementation")
+
+
+@dataclass
+class GraphIndex:
+    """CSR of the batch keyed by target node + per-graph node offsets (all int32, on device)."""
+    n_nodes: int
+    n_edges: int
+    rowptr: torch.Tensor
+    col: torch.Tensor
+    perm: torch.Tensor
+    big_rows: torch.Tensor
+    n_big: int
+    graph_ptr: torch.Tensor
+    n_graphs: int
+
+
+def build_graph_index(edge_index: torch.Tensor, batch: Optional[torch.Tensor], n_nodes: int,
+                      key_row: int = 1) -> GraphIndex:
+    """K1.  One small device->host read (4 ints: error flag, hub-row count, graph count,
+    sortedness) -- the same kind of sync PyG's `batch.max()+1` does."""
+    _require_cuda(edge_index, "edge_index")
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError("edge_index must be an int64 tensor of shape [2, E]")
+    edge_index = edge_index.contiguous()
+    dev = edge_index.device
+    E = edge_index.shape[1]
+    N = int(n_nodes)
+    s = _stream()
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr = torch.empty(N + 1, **i32)
+    col = torch.empty(max(E, 1), **i32)
+    perm = torch.empty(max(E, 1), **i32)
+    big_rows = torch.empty(capi.csr_max_big_rows(E), **i32)
+    info = torch.zeros(4, **i32)
+    ws_bytes = capi.csr_workspace_bytes(N, E)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    capi.csr_build(edge_index.data_ptr(), E, N, key_row, rowptr.data_ptr(), col.data_ptr(), perm.data_ptr(),
+                   big_rows.data_ptr(), info.data_ptr(), ws.data_ptr(), ws_bytes, s)
+    if batch is not None:
+        _require_cuda(batch, "batch")
+        if batch.dtype != torch.int64 or batch.dim() != 1 or batch.shape[0] != N:
+            raise ValueError("batch must be an int64 tensor of shape [N]")
+        batch = batch.contiguous()
+        capi.batch_info(batch.data_ptr(), N, info[2:].data_ptr(), s)
+    host = info.cpu().tolist()                       # the one sync of the forward
+    if host[0] & 1:
+        raise IndexError("edge_index contains node ids outside [0, num_nodes)")
+    n_big = host[1]
+    if batch is None:
+        n_graphs = 1
+        graph_ptr = torch.tensor([0, N], **i32)
+    else:
+        if host[3]:
+            raise ValueError("buckgnn_b200 needs a sorted, non-negative `batch` vector (PyG DataLoader order)")
+        n_graphs = host[2] if N > 0 else 0
+        graph_ptr = torch.empty(n_graphs + 1, **i32)
+        capi.graph_ptr_build(batch.data_ptr(), N, n_graphs, graph_ptr.data_ptr(), s)
+    return GraphIndex(N, E, rowptr, col, perm, big_rows, n_big, graph_ptr, n_graphs)
+
+
+# ----------------------------------------------------------------------------- packed weights
+@dataclass
+class LinearPack:
+    """A weight [512, K] (nn.Linear layout) in the operand format of one precision mode."""
+    k: int
+    parts: Tuple[torch.Tensor, ...]     # bf16: (w,)  tf32: (w,)  fp32: (w_hi, w_lo)
+
+
+def pack_linear(weight: torch.Tensor, precision: str) -> LinearPack:
+    w = weight.detach().to(torch.float32).contiguous()
+    k = w.shape[1]
+    s = _stream()
+    if precision == "bf16":
+        out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+        capi.cast_f32_to_bf16(w.data_ptr(), out.data_ptr(), w.numel(), s)
+        return LinearPack(k, (out,))
+    if precision == "tf32":
+        return LinearPack(k, (w.clone(),))
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    capi.split_tf32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), s)
+    return LinearPack(k, (hi, lo))
+
+
+@dataclass
+class SageLayerPack:
+    lin_l: LinearPack
+    lin_r: LinearPack
+    bias: torch.Tensor                   # f32 [512]
+    bn_scale: Optional[torch.Tensor]     # f32 [512]  gamma / sqrt(var + eps)
+    bn_shift: Optional[torch.Tensor]     # f32 [512]  beta - mean * scale
+
+
+def fold_batchnorm(bn: torch.nn.BatchNorm1d) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Eval-mode BatchNorm1d as one multiply-add per column (Models/BuckGNN.py:451)."""
+    scale = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)).contiguous()
+    shift = (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).contiguous()
+    return scale, shift
+
+
+class Activation:
+    """An [N, 512] (or [N, K]) activation in the operand format of a precision mode."""
+
+    def __init__(self, n: int, width: int, precision: str, device):
+        self.precision = precision
+        self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.code = capi.BG_BF16 if precision == "bf16" else capi.BG_F32
+        self.data = torch.empty((n, width), dtype=self.dtype, device=device)
+        self.hi = self.lo = None
+        if precision == "fp32":
+            self.hi = torch.empty_like(self.data)
+            self.lo = torch.empty_like(self.data)
+
+    def refresh_split(self):
+        if self.precision == "fp32":
+            capi.split_tf32(self.data.data_ptr(), self.hi.data_ptr(), self.lo.data_ptr(), self.data.numel(), _stream())
+
+
+def _segments(act: Activation, w: LinearPack):
+    """K-segments of act . w^T for the mode: 1 (bf16/tf32) or 3 (3xTF32: hi*hi + hi*lo + lo*hi)."""
+    k = w.k
+    ld = act.data.shape[1]
+    if act.precision != "fp32":
+        return [(act.data.data_ptr(), ld, w.parts[0].data_ptr(), k, k)]
+    w_hi, w_lo = w.parts
+    return [(act.hi.data_ptr(), ld, w_hi.data_ptr(), k, k),
+            (act.hi.data_ptr(), ld, w_lo.data_ptr(), k, k),
+            (act.lo.data_ptr(), ld, w_hi.data_ptr(), k, k)]
+
+
+def gemm512(segs, m: int, precision: str, out: Activation, *, cta_group: int = 2, **epi) -> None:
+    mode = capi.BG_GEMM_BF16 if precision == "bf16" else capi.BG_GEMM_TF32
+    capi.gemm512(segs, m, mode, out.data.data_ptr(), out.code, out.data.shape[1], _stream(),
+                 cta_group=cta_group, **epi)
+    out.refresh_split()
+
+
+def aggregate(x: Activation, out: Activation, idx: GraphIndex, aggr: str) -> None:
+    ws_bytes = capi.aggregate_workspace_bytes(idx.n_big)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.data.device)
+    capi.sage_aggregate(x.data.data_ptr(), out.data.data_ptr(), x.code, idx.n_nodes, idx.rowptr.data_ptr(),
+                        idx.col.data_ptr(), idx.big_rows.data_ptr(), idx.n_big, capi.AGGR_CODES[aggr],
+                        ws.data_ptr(), ws_bytes, _stream())
+    out.refresh_split()
+
+
+def encoder_forward(x: torch.Tensor, enc_w: Dict[str, torch.Tensor], w3: LinearPack, precision: str,
+                    out: Activation, cta_group: int) -> None:
+    """node_encoder (Models/BuckGNN.py:68-74): two fp32 CUDA-core layers, then 128->512 on tcgen05."""
+    n, f = x.shape
+    h = Activation(n, 128, precision, x.device)
+    capi.encoder_front(x.data_ptr(), n, f, enc_w["w1"].data_ptr(), enc_w["b1"].data_ptr(), enc_w["w2"].data_ptr(),
+                       enc_w["b2"].data_ptr(), h.data.data_ptr(), h.code, _stream())
+    h.refresh_split()
+    gemm512(_segments(h, w3), n, precision, out, cta_group=cta_group, bias=enc_w["b3"].data_ptr())
+
+
+def sage_layer(x: Activation, agg: Activation, out: Activation, idx: GraphIndex, layer: SageLayerPack, *,
+               aggr: str, normalize: bool, relu: bool, residual: bool, cta_group: int) -> None:
+    """One reference layer iteration (Models/BuckGNN.py:447-457) = aggregate + fused update GEMM."""
+    aggregate(x, agg, idx, aggr)
+    segs = _segments(agg, layer.lin_l) + _segments(x, layer.lin_r)
+    gemm512(segs, idx.n_nodes, x.precision, out, cta_group=cta_group,
+            bias=layer.bias.data_ptr(), bn_scale=_p(layer.bn_scale), bn_shift=_p(layer.bn_shift),
+            residual=x.data.data_ptr() if residual else None, ldr=x.data.shape[1],
+            normalize=normalize, relu=relu)
+
+
+def pool_head(x: Activation, idx: GraphIndex, dec: Dict[str, torch.Tensor], out_dim: int,
+              want_pooled: bool = False):
+    """global_mean_pool + decoder (Models/BuckGNN.py:274, 515-516)."""
+    dev = x.data.device
+    g = idx.n_graphs
+    pred = torch.empty((g, out_dim), dtype=torch.float32, device=dev)
+    pooled = torch.empty((g, 512), dtype=torch.float32, device=dev) if want_pooled else None
+    ws_bytes = capi.pool_workspace_bytes(g)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    capi.pool_head(x.data.data_ptr(), x.code, idx.n_nodes, idx.graph_ptr.data_ptr(), g,
+                   dec["w1"].data_ptr(), dec["b1"].data_ptr(), dec["w2"].data_ptr(), dec["b2"].data_ptr(),
+                   dec["w3"].data_ptr(), dec["b3"].data_ptr(), out_dim, pred.data_ptr(), _p(pooled),
+                   ws.data_ptr(), ws_bytes, _stream())
+    return pred, pooled

@@ -1,0 +1,245 @@
+"""`BuckGNN` with the reference's module contract, running on the sm_100a kernels.
+
+Mirrors `Models/BuckGNN.py` of the reference:
+  * constructor arguments, attribute names and parameter registration order
+    (`:10-244`) -> identical `state_dict()` keys and shapes, so checkpoints written
+    by `TRAIN_FINAL.py:394-410` load with `strict=True`;
+  * `forward(x, edge_index, edge_attr, batch=None, mask=None)` -> `(pred, batch)`
+    (`:311`, `:516`); `pred` is `[G]` after `.squeeze()` (0-dim when G == 1), the
+    second element is the caller's `batch` object unchanged;
+  * errors: `ValueError("Unknown pooling layer: ...")` (`:307`) and
+    `ValueError("Unknown prediction type: ...")` (`:526`).
+
+The forward never touches PyG / torch_scatter / ATen math: it is the kernel sequence
+in `engine.py`.  CPU tensors raise -- there is no fallback path.
+
+Extra, non-reference keyword: `precision` in {"bf16", "tf32", "fp32"} selects how the
+tensor-core GEMMs read their operands (fp32 = 3xTF32 split, the "fp32-GEMM mode").
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import engine
+from .engine import Activation, LinearPack, SageLayerPack
+
+_SAGE_LISTS = {  # model_name -> (ModuleList attribute, aggr)      reference :120-180
+    "GraphSage_sumAggr": ("sage_blocks_sum", "sum"),
+    "GraphSage_addAggr": ("sage_blocks_add", "add"),
+    "GraphSage_meanAggr": ("sage_blocks_mean", "mean"),
+    "GraphSage_maxAggr": ("sage_blocks_max", "max"),
+}
+
+
+class SAGEConv(nn.Module):
+    """Parameter container with PyG SAGEConv's names: lin_l.{weight,bias}, lin_r.weight."""
+
+    def __init__(self, in_channels: int, out_channels: int, normalize: bool = True, aggr: str = "mean"):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.normalize, self.aggr = normalize, aggr
+        self.lin_l = nn.Linear(in_channels, out_channels, bias=True)
+        self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+
+    def forward(self, *a, **k):  # pragma: no cover - the layer only runs fused inside BuckGNN.forward
+        raise RuntimeError("buckgnn_b200.SAGEConv holds parameters only; it runs fused inside BuckGNN.forward")
+
+
+def _mlp2(i, h, o):
+    return nn.Sequential(nn.Linear(i, h), nn.ReLU(), nn.Linear(h, o))
+
+
+class GraphNetBlock(nn.Module):
+    """Parameter container for the reference's EA-GNN block (`:528-550`)."""
+
+    def __init__(self, hidden_channels: int):
+        super().__init__()
+        h = hidden_channels
+        self.edge_mlp = _mlp2(3 * h, h, h)
+        self.node_mlp_phi = _mlp2(2 * h, h, h)
+        self.node_mlp_gamma = _mlp2(2 * h, h, h)
+        self.node_mlp_beta = _mlp2(h, h, h)
+
+
+class MLPPooling(nn.Module):
+    """Parameter container for the reference's `MLPPooling` (`:568-576`)."""
+
+    def __init__(self, in_channels, hidden_channels, out_channels):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(in_channels, hidden_channels), nn.ReLU())
+
+
+def _output_dim(prediction_type, use_z_coord, use_rotations):
+    if prediction_type == "buckling":
+        return 1
+    if prediction_type == "static_disp":
+        return {(True, True): 6, (True, False): 3, (False, True): 4, (False, False): 2}[
+            (bool(use_z_coord), bool(use_rotations))]
+    if prediction_type == "static_stress":
+        return 3
+    if prediction_type == "mode_shape":
+        return 6 if use_rotations else 3
+    raise NameError("output_dim")          # the reference leaves output_dim unbound here (:20-38)
+
+
+class BuckGNN(nn.Module):
+    def __init__(self, num_node_features, num_edge_features, hidden_channels=128,
+                 num_layers=6, pooling_layer="mean", prediction_type="buckling",
+                 use_z_coord=False, use_rotations=False, dropout_rate=0.1,
+                 model_name="GraphSAGE_MLP", *, precision: str = "bf16", cta_group: int = 2,
+                 cache_index: bool = False):
+        super().__init__()
+        if precision not in engine.PRECISIONS:
+            raise ValueError(f"precision must be one of {engine.PRECISIONS}")
+        self.hidden_channels = hidden_channels
+        self.prediction_type = prediction_type
+        self.pooling_layer = pooling_layer
+        self.num_layers = num_layers
+        self.model_name = model_name
+        self.precision = precision
+        self.cta_group = cta_group
+        self.cache_index = cache_index
+        self.output_dim = output_dim = _output_dim(prediction_type, use_z_coord, use_rotations)
+        h = hidden_channels
+        cat_dec = pooling_layer == "supernode_with_pooling" and prediction_type == "buckling"
+        if h <= 128:
+            self.node_encoder = _mlp2(num_node_features, 64, h)
+            self.edge_encoder = _mlp2(num_edge_features, 64, h)
+            self.decoder = _mlp2(2 * h if cat_dec else h, 64, output_dim)
+        elif h >= 256:
+            self.node_encoder = nn.Sequential(nn.Linear(num_node_features, 64), nn.ReLU(),
+                                              nn.Linear(64, 128), nn.ReLU(), nn.Linear(128, h))
+            self.edge_encoder = nn.Sequential(nn.Linear(num_edge_features, 64), nn.ReLU(),
+                                              nn.Linear(64, 128), nn.ReLU(), nn.Linear(128, h))
+            self.decoder = nn.Sequential(nn.Linear(2 * h if cat_dec else h, 128), nn.ReLU(),
+                                         nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, output_dim))
+        if model_name == "EA_GNN_Shared":
+            self.shared_gn_block = GraphNetBlock(h)
+        if model_name == "EA_GNN":
+            self.gn_blocks = nn.ModuleList([GraphNetBlock(h) for _ in range(num_layers)])
+        if model_name == "GraphSage_addAggr_Shared":
+            self.shared_graphsage_block = SAGEConv(h, h, normalize=True, aggr="add")
+        if model_name in _SAGE_LISTS:
+            attr, aggr = _SAGE_LISTS[model_name]
+            blocks, bns, mlps = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+            setattr(self, attr, blocks)
+            self.batch_norms = bns
+            self.sage_mlps = mlps
+            for _ in range(num_layers):
+                blocks.append(SAGEConv(h, h, normalize=True, aggr=aggr))
+                bns.append(nn.BatchNorm1d(h))
+                mlps.append(nn.Linear(h, h))
+        self.batch_norm = nn.BatchNorm1d(h)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(p=dropout_rate)
+        self.pooling_mpl = MLPPooling(h, h, h)
+        self._packs: Dict[str, object] = {}
+        self._pack_sig = None
+        self._index_cache = None
+
+    # ------------------------------------------------------------------ weight packing
+    def _signature(self):
+        return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
+            tuple((b.data_ptr(), b._version) for b in self.buffers())
+
+    def _sage_layers(self):
+        if self.model_name in _SAGE_LISTS:
+            convs = getattr(self, _SAGE_LISTS[self.model_name][0])
+            return [(c, bn) for c, bn in zip(convs, self.batch_norms)]
+        if self.model_name == "GraphSage_addAggr_Shared":
+            return [(self.shared_graphsage_block, None)] * self.num_layers
+        return []
+
+    def _packed(self):
+        """Operand-format copies of the weights, rebuilt when any parameter/buffer changes."""
+        sig = self._signature()
+        if self._pack_sig == sig:
+            return self._packs
+        prec = self.precision
+        f32 = lambda t: t.detach().float().contiguous()
+        enc = self.node_encoder
+        packs = {"enc": {"w1": f32(enc[0].weight), "b1": f32(enc[0].bias), "w2": f32(enc[2].weight),
+                         "b2": f32(enc[2].bias), "b3": f32(enc[4].bias)},
+                 "enc_w3": engine.pack_linear(enc[4].weight, prec)}
+        dec = self.decoder
+        packs["dec"] = {"w1": f32(dec[0].weight), "b1": f32(dec[0].bias), "w2": f32(dec[2].weight),
+                        "b2": f32(dec[2].bias), "w3": f32(dec[4].weight), "b3": f32(dec[4].bias)}
+        layers, seen = [], {}
+        for conv, bn in self._sage_layers():
+            if id(conv) not in seen:
+                scale, shift = engine.fold_batchnorm(bn) if bn is not None else (None, None)
+                seen[id(conv)] = SageLayerPack(engine.pack_linear(conv.lin_l.weight, prec),
+                                               engine.pack_linear(conv.lin_r.weight, prec),
+                                               f32(conv.lin_l.bias), scale, shift)
+            layers.append(seen[id(conv)])
+        packs["layers"] = layers
+        self._packs, self._pack_sig = packs, sig
+        return packs
+
+    # ------------------------------------------------------------------ forward
+    def _check_supported(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("buckgnn_b200.BuckGNN runs on CUDA (sm_100a) tensors only; there is no CPU path")
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("buckgnn_b200: the training step (backward kernels + BN batch statistics) "
+                                      "is not built yet; call model.eval() under torch.no_grad()")
+        if self.hidden_channels != 512:
+            raise NotImplementedError("buckgnn_b200: the tcgen05 path is built for hidden_channels=512")
+        if self.model_name in ("EA_GNN", "EA_GNN_Shared", "GraphSAGE_SAG", "EAGNN_SAG"):
+            raise NotImplementedError(f"buckgnn_b200: model_name={self.model_name!r} is not built yet")
+        if self.model_name in ("GraphSage_MLP", "GraphSage_addAggr_woBatchNorm", "GraphSage_sumAggr_woBatchNorm"):
+            # the reference constructs the module lists these branches use only under other names
+            raise AttributeError(f"'BuckGNN' object has no module list for model_name={self.model_name!r} "
+                                 "(same failure as the reference, Models/BuckGNN.py:404-429,472-492)")
+
+    def forward(self, x, edge_index, edge_attr, batch=None, mask=None):
+        self._check_supported(x)
+        if self.prediction_type != "buckling":
+            if "static" in self.prediction_type or "mode_shape" in self.prediction_type:
+                raise NotImplementedError("buckgnn_b200: node-level heads are not built yet")
+            raise ValueError(f"Unknown prediction type: {self.prediction_type}")
+        if self.pooling_layer != "mean":
+            if self.pooling_layer in ("mean_no_super", "supernode_only", "supernode_with_pooling", "mlp",
+                                      "mlp_no_super"):
+                raise NotImplementedError(f"buckgnn_b200: pooling_layer={self.pooling_layer!r} is not built yet")
+            if self.pooling_layer == "hybrid":
+                raise AttributeError("'BuckGNN' object has no attribute 'hybrid_pooling'")   # reference :188,276
+            raise ValueError(f"Unknown pooling layer: {self.pooling_layer}")
+        with torch.no_grad():
+            pred = self._forward_cuda(x, edge_index, batch)
+        return pred.squeeze(), batch
+
+    def _graph_index(self, edge_index, batch, n):
+        if self.cache_index:
+            key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape),
+                   None if batch is None else (batch.data_ptr(), batch._version), n)
+            if self._index_cache is not None and self._index_cache[0] == key:
+                return self._index_cache[1]
+            idx = engine.build_graph_index(edge_index, batch, n)
+            self._index_cache = (key, idx)
+            return idx
+        return engine.build_graph_index(edge_index, batch, n)
+
+    def _forward_cuda(self, x, edge_index, batch):
+        packs = self._packed()
+        prec, cg = self.precision, self.cta_group
+        x = x.detach().to(torch.float32).contiguous()
+        n = x.shape[0]
+        idx = self._graph_index(edge_index, batch, n)
+        cur = Activation(n, 512, prec, x.device)
+        engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg)          # reference :323
+        layers = packs["layers"]
+        if layers:
+            nxt = Activation(n, 512, prec, x.device)
+            agg = Activation(n, 512, prec, x.device)
+            aggr = self._sage_layers()[0][0].aggr
+            L = len(layers)
+            for i, layer in enumerate(layers):                                            # reference :445-458
+                engine.sage_layer(cur, agg, nxt, idx, layer, aggr=aggr, normalize=True, relu=True,
+                                  residual=(0 < i < L - 1), cta_group=cg)
+                cur, nxt = nxt, cur
+        pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim)               # reference :515-516
+        return pred

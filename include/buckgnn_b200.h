@@ -1,0 +1,177 @@
+/* buckgnn_b200 -- C ABI of the B200-native BuckGNN forward hot path.
+ *
+ * The reference (omerkurt-okt/buck-gnn) is pure Python: its hot path,
+ * `BuckGNN.forward` (Models/BuckGNN.py:311-526), bottoms out in torch_geometric /
+ * torch_scatter library kernels.  It has no FFI of its own, so the boundary a
+ * maintainer binds is the set of operators that forward calls; each entry point
+ * below names the reference call site it replaces.  The Python host
+ * (buckgnn_b200/capi.py, ctypes) is the only caller; INTEGRATION.md shows the
+ * binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *    buffers are borrowed for the duration of the call, never retained;
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *    all work is enqueued on it, nothing synchronises unless stated;
+ *  - return value: BG_OK (0) or a negative bg_status; bg_last_error() gives the
+ *    text of the last failure on the calling thread.  Nothing throws;
+ *  - no allocation happens inside: workspace sizes are queried first so the host
+ *    framework (torch's caching allocator) owns all memory;
+ *  - matrices are row-major; `ld*` are leading dimensions in ELEMENTS.
+ *  - the library is compiled for sm_100a only; bg_device_check() says whether the
+ *    current device can run it.  There is no CPU fallback.
+ */
+#ifndef BUCKGNN_B200_H_
+#define BUCKGNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BG_ABI_VERSION 1
+
+typedef enum bg_status {
+  BG_OK = 0,
+  BG_ERR_INVALID = -1,      /* bad argument (null pointer, size, alignment, enum) */
+  BG_ERR_CUDA = -2,         /* a CUDA runtime/driver call failed; see bg_last_error() */
+  BG_ERR_WORKSPACE = -3,    /* workspace too small */
+  BG_ERR_UNSUPPORTED = -4,  /* shape / mode outside what the kernels are built for */
+  BG_ERR_DEVICE = -5        /* current device is not sm_100 */
+} bg_status;
+
+typedef enum bg_dtype { BG_BF16 = 0, BG_F32 = 1 } bg_dtype;
+
+/* SAGEConv(aggr=...) values used by the reference (Models/BuckGNN.py:118,130,145,160,175);
+ * 'add' and 'sum' are the same reduction. */
+typedef enum bg_aggr { BG_AGGR_MEAN = 0, BG_AGGR_SUM = 1, BG_AGGR_MAX = 2 } bg_aggr;
+
+/* how the tensor-core GEMM reads its operands */
+typedef enum bg_gemm_mode {
+  BG_GEMM_BF16 = 0,   /* bf16 operands, fp32 accumulate (tcgen05 kind::f16)            */
+  BG_GEMM_TF32 = 1    /* fp32 operands read as tf32, fp32 accumulate (kind::tf32);
+                         with hi/lo split operands this is the "fp32-GEMM" (3xTF32) mode */
+} bg_gemm_mode;
+
+int bg_abi_version(void);
+const char* bg_last_error(void);
+/* BG_OK if the current CUDA device is compute capability 10.x */
+int bg_device_check(void);
+/* info about the last barrier watchdog trip (debugging aid): 4 words copied to host */
+int bg_watchdog_info_host(uint32_t* out4_host);
+
+/* ------------------------------------------------------------------ K1: CSR build
+ * Replaces the implicit gather/scatter indexing inside PyG's
+ * `SAGEConv.propagate` (called at Models/BuckGNN.py:342,393,434,449,463) and
+ * torch_scatter `scatter_mean(messages, row, ...)` (Models/BuckGNN.py:561).
+ *
+ * Stable counting sort of the E edges by key row (key_row = 1: by target
+ * edge_index[1], the SAGEConv direction; key_row = 0: by edge_index[0], the
+ * GraphNetBlock direction):
+ *    perm   == argsort(key, stable)            [E]   int32
+ *    rowptr == concat(0, cumsum(bincount(key, N)))  [N+1] int32
+ *    col[i] == other_row[perm[i]]              [E]   int32
+ * bit-exact.  Rows whose degree exceeds BG_BIG_ROW_THRESHOLD (the super-node hub
+ * rows) are additionally listed in big_rows (unordered), their count in info[1].
+ *    info[0] : bit 0 set if any index was outside [0, N)   (such edges are dropped)
+ *    info[1] : number of big rows
+ * big_rows must hold bg_csr_max_big_rows(E) entries.  E, N < 2^31.
+ */
+#define BG_BIG_ROW_THRESHOLD 64
+int64_t bg_csr_max_big_rows(int64_t n_edges);
+int bg_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, size_t* bytes_host);
+int bg_csr_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int key_row,
+                 int32_t* rowptr, int32_t* col, int32_t* perm, int32_t* big_rows, int32_t* info,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Graph offsets from the PyG `batch` vector; replaces the index handling inside
+ * `global_mean_pool(x, batch)` (Models/BuckGNN.py:274).
+ * bg_batch_info:  info[0] = batch[N-1] + 1 (= batch.max()+1 for sorted batch),
+ *                 info[1] = 1 if batch is not non-decreasing or has a negative id.
+ * bg_graph_ptr_build: graph_ptr[g] = first node index with batch >= g, g in [0, G];
+ *                 graph_ptr[G] = N.  Requires sorted batch (PyG DataLoader order). */
+int bg_batch_info(const int64_t* batch, int64_t n_nodes, int32_t* info, void* stream);
+int bg_graph_ptr_build(const int64_t* batch, int64_t n_nodes, int64_t n_graphs, int32_t* graph_ptr,
+                       void* stream);
+
+/* ------------------------------------------------------------------ K5: node encoder front
+ * First two Linear+ReLU of `node_encoder` (Models/BuckGNN.py:68-72, applied :323):
+ *    h = relu(relu(x W1^T + b1) W2^T + b2),  x [N,F] f32 -> h [N,128] (out_dtype)
+ * W1 [64,F], W2 [128,64] f32 row-major (out,in) as in nn.Linear.  F <= 32. */
+int bg_encoder_front(const float* x, int64_t n_nodes, int32_t n_features,
+                     const float* w1, const float* b1, const float* w2, const float* b2,
+                     void* out, int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------ K2: neighbourhood aggregation
+ * Replaces `x[src]` gather + `scatter_add_` + divide inside SAGEConv.propagate:
+ *    out[i] = reduce_{e: key(e)=i} x[col(e)]     mean: sum / max(deg,1); max: 0 if deg = 0
+ * x, out: [N,512] of `dtype` (bf16 or f32), accumulation in fp32 in CSR (stable) order.
+ * Big rows (info[1] of bg_csr_build, read back by the host) are split across CTAs;
+ * workspace from bg_aggregate_workspace_bytes(n_big). */
+int bg_aggregate_workspace_bytes(int32_t n_big, size_t* bytes_host);
+int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t n_nodes,
+                      const int32_t* rowptr, const int32_t* col,
+                      const int32_t* big_rows, int32_t n_big, int aggr,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ K3: tensor-core update GEMM
+ * out[m, 0:512] = epilogue( sum_s A_s[m, :] . B_s[:, :]^T )
+ * Each segment s contributes A_s [M, k_s] times B_s [512, k_s] (nn.Linear weight
+ * layout, K-major) -- the SAGE update is the two segments (agg, lin_l.weight),
+ * (x, lin_r.weight), i.e. the concatenated [lin_l | lin_r] GEMM with K = 1024.
+ * Replaces `lin_l(agg) + lin_r(x)`, `F.normalize`, `BatchNorm1d` (eval), `ReLU`
+ * and the skip connection (Models/BuckGNN.py:449-457 and PyG SAGEConv.forward).
+ * Epilogue order (each step optional):
+ *    v = acc + bias;  v /= max(||v||_2, 1e-12);  v = v*bn_scale + bn_shift;
+ *    v = max(v, 0);   v += residual[m, :]
+ * mode BG_GEMM_BF16: A, B bf16, k_s % 64 == 0.  BG_GEMM_TF32: A, B f32, k_s % 32 == 0.
+ * out/residual dtype = out_dtype.  All base pointers 16-byte aligned, ld* such that
+ * rows are 16-byte aligned.  cta_group: 1 or 2 (2 = tcgen05 cta_group::2 CTA pairs). */
+#define BG_MAX_GEMM_SEGMENTS 6
+typedef struct bg_gemm_segment {
+  const void* a; int64_t lda;
+  const void* b; int64_t ldb;
+  int32_t k; int32_t reserved;
+} bg_gemm_segment;
+
+typedef struct bg_epilogue {
+  const float* bias;      /* [512] or NULL */
+  const float* bn_scale;  /* [512] or NULL (then bn_shift ignored) */
+  const float* bn_shift;
+  const void* residual;   /* [M,512], ld = ldr, or NULL */
+  int64_t ldr;
+  int32_t normalize;      /* F.normalize(p=2, dim=-1, eps=1e-12) */
+  int32_t relu;
+} bg_epilogue;
+
+int bg_gemm512(const bg_gemm_segment* segments_host, int32_t n_segments, int64_t m, int mode,
+               const bg_epilogue* epilogue_host, void* out, int out_dtype, int64_t ldo,
+               int cta_group, void* stream);
+
+/* ------------------------------------------------------------------ K4: mean pool + regression head
+ * Replaces `global_mean_pool(x, batch)` + `decoder(pooled).squeeze()`
+ * (Models/BuckGNN.py:274, 515-516):
+ *    pooled[g] = sum_{i in graph g} x[i] / max(count_g, 1);   pred[g] = MLP(pooled[g])
+ * decoder = Linear(512,128) ReLU Linear(128,64) ReLU Linear(64,out_dim), f32 weights.
+ * x [N,512] of `dtype`; pred [G, out_dim] f32; pooled_out [G,512] f32 optional (NULL to skip).
+ * workspace from bg_pool_workspace_bytes(G). */
+int bg_pool_workspace_bytes(int64_t n_graphs, size_t* bytes_host);
+int bg_pool_head(const void* x, int dtype, int64_t n_nodes, const int32_t* graph_ptr, int64_t n_graphs,
+                 const float* w1, const float* b1, const float* w2, const float* b2,
+                 const float* w3, const float* b3, int32_t out_dim,
+                 float* pred, float* pooled_out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ helpers
+ * fp32 -> bf16 (round to nearest even) cast of a contiguous buffer (weight packing). */
+int bg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* hi/lo split for the 3xTF32 "fp32-GEMM" mode: hi = src with the low 13 mantissa bits
+ * cleared (exactly representable in tf32), lo = src - hi. */
+int bg_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BUCKGNN_B200_H_ */

@@ -267,14 +267,25 @@ class OracleBuckGNN(nn.Module):
         raise ValueError(f"Unknown prediction type: {self.prediction_type}")
 
 
-def randomize_bn_stats(model: nn.Module, seed: int = 1) -> None:
+def randomize_bn_stats(model: nn.Module, seed: int = 1, realistic: bool = False) -> None:
     """Give every BatchNorm non-trivial running stats and affine terms, so a wrong
-    BN fold cannot hide behind the 0/1 defaults."""
+    BN fold cannot hide behind the 0/1 defaults.
+
+    `realistic=True` uses the statistics a trained network would have after an
+    L2-normalised 512-wide layer (entries ~ 1/sqrt(512)): running_var ~ U(.5,1.5)/C,
+    running_mean ~ N(0, .3/sqrt(C)).  BN then rescales by ~sqrt(C), which makes the
+    prediction sensitive to the message passing (and to GEMM rounding) instead of
+    being dominated by the BN constants -- the honest setting for parity tests."""
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for m in model.modules():
             if isinstance(m, nn.BatchNorm1d):
-                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
-                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
-                m.weight.copy_(torch.rand(m.num_features, generator=g) + 0.5)
-                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                c = m.num_features
+                if realistic:
+                    m.running_mean.copy_(torch.randn(c, generator=g) * 0.3 / c ** 0.5)
+                    m.running_var.copy_((torch.rand(c, generator=g) + 0.5) / c)
+                else:
+                    m.running_mean.copy_(torch.randn(c, generator=g) * 0.1)
+                    m.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+                m.weight.copy_(torch.rand(c, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(c, generator=g) * 0.1)

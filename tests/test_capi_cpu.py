@@ -1,0 +1,88 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol the
+header declares; the module keeps the reference's contract; nothing falls back to CPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import __graft_entry__ as entry
+from buckgnn_b200 import capi
+from buckgnn_b200.model import BuckGNN
+from buckgnn_b200.synth import make_batch
+from oracle.buckgnn_oracle import OracleBuckGNN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    entry.build()
+    return capi.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "buckgnn_b200.h")).read()
+    declared = set(re.findall(r"\b(bg_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(capi.EXPORTED_SYMBOLS)
+    raw = ctypes.CDLL(capi.library_path())
+    for name in declared:
+        assert hasattr(raw, name), name
+    assert lib.bg_abi_version() == 1
+
+
+def test_size_queries_and_argument_errors_without_gpu(lib):
+    assert capi.csr_max_big_rows(650) == 11
+    assert capi.csr_workspace_bytes(1000, 5000) >= 2 * 4 * 1001
+    assert capi.aggregate_workspace_bytes(3) >= 3 * 16 * 512 * 4
+    assert capi.pool_workspace_bytes(4) >= 4 * 8 * 512 * 4
+    with pytest.raises(capi.BuckGNNError) as e:
+        capi.csr_workspace_bytes(-1, 0)
+    assert e.value.status == -1 and "bad argument" in str(e.value)
+    # bad enum / null pointers are rejected before any CUDA call
+    with pytest.raises(capi.BuckGNNError):
+        capi.gemm512([], 128, capi.BG_GEMM_BF16, 0, capi.BG_BF16, 512, None)
+    with pytest.raises(capi.BuckGNNError):
+        capi.csr_build(None, 10, 10, 7, None, None, None, None, None, None, 0, None)
+
+
+@pytest.mark.parametrize("name", ["GraphSage_meanAggr", "GraphSage_sumAggr", "GraphSage_addAggr",
+                                  "GraphSage_maxAggr", "GraphSage_addAggr_Shared", "EA_GNN", "EA_GNN_Shared",
+                                  "GraphSAGE_MLP"])
+@pytest.mark.parametrize("hidden", [128, 512])
+def test_state_dict_layout_matches_oracle_restatement(name, hidden):
+    kw = dict(num_node_features=16, num_edge_features=5, hidden_channels=hidden, num_layers=3,
+              pooling_layer="mean", model_name=name)
+    ours, ref = BuckGNN(**kw), OracleBuckGNN(**kw)
+    a, b = ours.state_dict(), ref.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+    ours.load_state_dict(b, strict=True)
+    assert all(torch.equal(ours.state_dict()[k], b[k]) for k in b)
+
+
+def test_reference_import_paths_and_positional_ctor():
+    from Models.BuckGNN import BuckGNN as A
+    from Models.EA_GNN import EdgeAugmentedGNN as B
+    assert A is B is BuckGNN
+    # INFERENCE.py:73-84 / TRAIN_FINAL.py:161-166 call order
+    m = A(16, 5, 512, 6, "mean", prediction_type="buckling", use_z_coord=False, use_rotations=False,
+          dropout_rate=0.1, model_name="GraphSage_meanAggr")
+    assert m.hidden_channels == 512 and m.num_layers == 6 and m.dropout.p == 0.1
+    assert [p.requires_grad for p in m.parameters()].count(False) == 0
+
+
+def test_cpu_tensors_fail_loudly_no_fallback():
+    b = make_batch(1, nx=4, ny=4)
+    m = BuckGNN(16, 5, 512, 2, "mean", model_name="GraphSage_meanAggr").eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        m(b.x, b.edge_index, b.edge_attr, b.batch)
+
+
+def test_product_code_never_imports_the_oracle():
+    for d in ("buckgnn_b200", "Models"):
+        for f in os.listdir(os.path.join(ROOT, d)):
+            if f.endswith(".py"):
+                src = open(os.path.join(ROOT, d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f

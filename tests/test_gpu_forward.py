@@ -1,0 +1,103 @@
+"""End-to-end parity of `BuckGNN.forward` on the B200 against the fp32 oracle.
+
+Tolerances are BASELINE.json's: rtol 1e-3 on the predicted eigenvalues for the
+bf16 / tf32 tensor-core modes, rtol 1e-4 for the fp32-GEMM (3xTF32) mode."""
+import pytest
+import torch
+
+from buckgnn_b200.model import BuckGNN
+from buckgnn_b200.synth import make_batch
+from oracle.buckgnn_oracle import OracleBuckGNN, randomize_bn_stats
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL = {"bf16": 1e-3, "tf32": 1e-3, "fp32": 1e-4}
+
+
+def _pair(model_name, precision, layers=6, seed=0, **kw):
+    torch.manual_seed(seed)
+    cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=layers,
+               pooling_layer="mean", model_name=model_name)
+    ref = OracleBuckGNN(**cfg).eval()
+    randomize_bn_stats(ref, realistic=True)
+    ours = BuckGNN(**cfg, precision=precision, **kw)
+    ours.load_state_dict(ref.state_dict())
+    return ref, ours.to(DEV).eval()
+
+
+def _run(ref, ours, b):
+    with torch.no_grad():
+        want, _ = ref(b.x, b.edge_index, b.edge_attr, b.batch)
+        bd = b.to(DEV)
+        got, bb = ours(bd.x, bd.edge_index, bd.edge_attr, bd.batch)
+    assert bb is bd.batch
+    return got.cpu(), want
+
+
+def _assert_rel(got, want, rtol):
+    rel = (got - want).abs() / want.abs().clamp(min=1e-3)
+    assert rel.max().item() < rtol, f"max rel err {rel.max().item():.3e} >= {rtol} (got {got}, want {want})"
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32", "fp32"])
+def test_graphsage_mean_6x512_matches_oracle(precision):
+    ref, ours = _pair("GraphSage_meanAggr", precision)
+    got, want = _run(ref, ours, make_batch(4, nx=24, ny=20))
+    assert got.shape == want.shape == (4,)
+    _assert_rel(got, want, RTOL[precision])
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_cta_group_variants_agree(cta_group):
+    ref, ours = _pair("GraphSage_meanAggr", "bf16", cta_group=cta_group)
+    got, want = _run(ref, ours, make_batch(3, nx=16, ny=16))
+    _assert_rel(got, want, 1e-3)
+
+
+@pytest.mark.parametrize("name", ["GraphSage_sumAggr", "GraphSage_addAggr", "GraphSage_maxAggr",
+                                  "GraphSage_addAggr_Shared", "GraphSAGE_MLP"])
+def test_other_graphsage_variants(name):
+    ref, ours = _pair(name, "tf32", layers=4)
+    got, want = _run(ref, ours, make_batch(3, nx=12, ny=10))
+    _assert_rel(got, want, 1e-3)
+
+
+def test_single_graph_batch_none_gives_0dim():
+    ref, ours = _pair("GraphSage_meanAggr", "tf32", layers=3)
+    b = make_batch(1, nx=10, ny=10)
+    with torch.no_grad():
+        want, _ = ref(b.x, b.edge_index, b.edge_attr, None)
+        got, bb = ours(b.x.to(DEV), b.edge_index.to(DEV), b.edge_attr.to(DEV), None)
+    assert bb is None and got.dim() == 0
+    _assert_rel(got.cpu(), want, 1e-3)
+
+
+def test_inputs_not_mutated_and_deterministic():
+    ref, ours = _pair("GraphSage_meanAggr", "bf16", layers=3)
+    b = make_batch(3, nx=10, ny=9).to(DEV)
+    snap = [t.clone() for t in (b.x, b.edge_index, b.edge_attr, b.batch)]
+    with torch.no_grad():
+        p1, _ = ours(b.x, b.edge_index, b.edge_attr, b.batch)
+        p2, _ = ours(b.x, b.edge_index, b.edge_attr, b.batch)
+    assert all(torch.equal(a, c) for a, c in zip(snap, (b.x, b.edge_index, b.edge_attr, b.batch)))
+    assert torch.equal(p1, p2)                 # no atomics on the float path -> bitwise repeatable
+
+
+def test_permuting_edges_changes_nothing_beyond_rounding():
+    ref, ours = _pair("GraphSage_meanAggr", "tf32", layers=3)
+    b = make_batch(2, nx=9, ny=9).to(DEV)
+    perm = torch.randperm(b.num_edges, device=DEV)
+    with torch.no_grad():
+        p1, _ = ours(b.x, b.edge_index, b.edge_attr, b.batch)
+        p2, _ = ours(b.x, b.edge_index[:, perm].contiguous(), b.edge_attr[perm], b.batch)
+    torch.testing.assert_close(p1, p2, rtol=1e-4, atol=1e-6)
+
+
+def test_weight_update_invalidates_packed_copies():
+    ref, ours = _pair("GraphSage_meanAggr", "tf32", layers=2)
+    b = make_batch(2, nx=8, ny=8).to(DEV)
+    with torch.no_grad():
+        p1, _ = ours(b.x, b.edge_index, b.edge_attr, b.batch)
+        ours.decoder[4].bias.add_(1.0)
+        p2, _ = ours(b.x, b.edge_index, b.edge_attr, b.batch)
+    torch.testing.assert_close(p2, p1 + 1.0, rtol=1e-5, atol=1e-5)

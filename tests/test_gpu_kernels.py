@@ -1,0 +1,211 @@
+"""Parity of each sm_100a kernel against the oracle, through the C ABI (needs a B200)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from buckgnn_b200 import capi, engine
+from buckgnn_b200.engine import Activation, build_graph_index
+from buckgnn_b200.synth import make_batch
+from oracle import buckgnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ----------------------------------------------------------------------------- K1
+def _csr_reference(edge_index, n, key_row):
+    key, other = edge_index[key_row], edge_index[1 - key_row]
+    perm = torch.sort(key, stable=True).indices
+    rowptr = torch.zeros(n + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(torch.bincount(key, minlength=n), 0)
+    return rowptr.int(), other[perm].int(), perm.int()
+
+
+def _random_multigraph(n, e, seed, hub=None):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    if hub is not None:                      # one row with a huge degree, like the super node
+        ei[1, ::3] = hub
+    return ei
+
+
+@pytest.mark.parametrize("key_row", [1, 0])
+@pytest.mark.parametrize("case", ["mesh", "random", "hub", "tiny", "empty_edges", "bighub"])
+def test_csr_build_bit_exact(case, key_row):
+    if case == "mesh":
+        b = make_batch(5, nx=17, ny=13); ei, n = b.edge_index, b.num_nodes
+    elif case == "random":
+        n = 5000; ei = _random_multigraph(n, 60000, 1)
+    elif case == "hub":
+        n = 3000; ei = _random_multigraph(n, 40000, 2, hub=1234)
+    elif case == "tiny":
+        n = 3; ei = torch.tensor([[0, 1, 2, 2], [2, 2, 0, 1]])
+    elif case == "empty_edges":
+        n = 10; ei = torch.zeros((2, 0), dtype=torch.int64)
+    else:                                     # degree above the shared-memory sort capacity (32768)
+        n = 200; ei = _random_multigraph(n, 150000, 3, hub=7)
+    idx = build_graph_index(ei.to(DEV), None, n, key_row=key_row)
+    rowptr, col, perm = _csr_reference(ei, n, key_row)
+    e = ei.shape[1]
+    assert torch.equal(idx.rowptr.cpu(), rowptr)
+    assert torch.equal(idx.perm.cpu()[:e], perm)
+    assert torch.equal(idx.col.cpu()[:e], col)
+    deg = rowptr[1:] - rowptr[:-1]
+    big = sorted(idx.big_rows.cpu()[:idx.n_big].tolist())
+    assert big == torch.nonzero(deg > capi.BG_BIG_ROW_THRESHOLD).flatten().tolist()
+
+
+def test_csr_build_rejects_out_of_range_ids():
+    ei = torch.tensor([[0, 1, 5], [1, 0, 1]]).to(DEV)
+    with pytest.raises(IndexError):
+        build_graph_index(ei, None, 3)
+
+
+def test_graph_ptr_bit_exact_and_unsorted_batch_rejected():
+    b = make_batch(7, nx=9, ny=8)
+    idx = build_graph_index(b.edge_index.to(DEV), b.batch.to(DEV), b.num_nodes)
+    assert idx.n_graphs == 7 and torch.equal(idx.graph_ptr.cpu().long(), b.ptr)
+    # a graph id that never occurs (empty graph in the middle) keeps offsets monotone
+    batch = torch.tensor([0, 0, 2, 2, 2, 3])
+    ei = torch.zeros((2, 0), dtype=torch.int64)
+    idx = build_graph_index(ei.to(DEV), batch.to(DEV), 6)
+    assert idx.graph_ptr.cpu().tolist() == [0, 2, 2, 5, 6]
+    with pytest.raises(ValueError):
+        build_graph_index(ei.to(DEV), torch.tensor([0, 1, 0, 1, 1, 1]).to(DEV), 6)
+
+
+# ----------------------------------------------------------------------------- K5 front
+@pytest.mark.parametrize("n,f", [(1, 16), (63, 16), (1000, 16), (4097, 7)])
+def test_encoder_front_matches_fp32(n, f):
+    torch.manual_seed(0)
+    x = torch.randn(n, f)
+    l1, l2 = torch.nn.Linear(f, 64), torch.nn.Linear(64, 128)
+    want = torch.relu(l2(torch.relu(l1(x)))).detach()
+    out = torch.empty(n, 128, device=DEV)
+    d = lambda t: t.detach().to(DEV).contiguous()
+    w1, b1, w2, b2, xd = d(l1.weight), d(l1.bias), d(l2.weight), d(l2.bias), d(x)
+    capi.encoder_front(xd.data_ptr(), n, f, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                       out.data_ptr(), capi.BG_F32, _stream())
+    torch.testing.assert_close(out.cpu(), want, rtol=1e-5, atol=1e-5)
+    outb = torch.empty(n, 128, device=DEV, dtype=torch.bfloat16)
+    capi.encoder_front(xd.data_ptr(), n, f, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                       outb.data_ptr(), capi.BG_BF16, _stream())
+    torch.testing.assert_close(outb.cpu().float(), want, rtol=8e-3, atol=1e-5)   # one bf16 rounding
+
+
+# ----------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("aggr", ["mean", "sum", "max"])
+def test_aggregate_matches_oracle(aggr, precision):
+    torch.manual_seed(1)
+    b = make_batch(3, nx=21, ny=17)            # hubs of degree 357 -> the split path
+    n = b.num_nodes
+    ei = torch.cat([b.edge_index, torch.tensor([[5, 5], [9, 9]])], 1)     # duplicate edge
+    ei = ei[:, ei[1] != 3]                                                  # node 3 isolated
+    x = torch.randn(n, 512)
+    if precision == "bf16":
+        x = x.bfloat16().float()
+    want = O.aggregate(x.double(), ei, aggr).float()
+    idx = build_graph_index(ei.to(DEV), None, n)
+    assert idx.n_big == 3
+    xa, oa = Activation(n, 512, precision, DEV), Activation(n, 512, precision, DEV)
+    xa.data.copy_(x)
+    engine.aggregate(xa, oa, idx, aggr)
+    got = oa.data.float().cpu()
+    if precision == "bf16":
+        torch.testing.assert_close(got, want, rtol=8e-3, atol=1e-6 if aggr != "sum" else 2e-2)
+    else:
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+    if aggr == "max":
+        assert got[3].abs().sum() == 0          # isolated node -> 0, not -inf
+
+
+# ----------------------------------------------------------------------------- K3
+def _gemm_case(m, precision, cta_group, full_epilogue, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    ks = [512, 512] if full_epilogue else [128]
+    dt = torch.bfloat16 if precision == "bf16" else torch.float32
+    As = [(torch.randn(m, k, generator=g) / k ** 0.5).to(dt) for k in ks]
+    Bs = [(torch.randn(512, k, generator=g)).to(dt) for k in ks]
+    bias = torch.randn(512, generator=g) * 0.1
+    acc = sum(a.double() @ b.double().T for a, b in zip(As, Bs)) + bias.double()
+    if full_epilogue:
+        scale = torch.rand(512, generator=g) * 20 + 5
+        shift = torch.randn(512, generator=g) * 0.1
+        res = torch.randn(m, 512, generator=g).to(dt)
+        want = torch.relu(F.normalize(acc, dim=-1) * scale.double() + shift.double()) + res.double()
+    else:
+        scale = shift = res = None
+        want = acc
+    dv = lambda t: None if t is None else t.to(DEV).contiguous()
+    Ad, Bd = [dv(a) for a in As], [dv(b) for b in Bs]
+    biasd, scaled, shiftd, resd = dv(bias), dv(scale), dv(shift), dv(res)
+    out = Activation(m, 512, precision, DEV)
+    segs = [(a.data_ptr(), k, b.data_ptr(), k, k) for a, b, k in zip(Ad, Bd, ks)]
+    engine.gemm512(segs, m, precision, out, cta_group=cta_group, bias=biasd.data_ptr(),
+                   bn_scale=engine._p(scaled), bn_shift=engine._p(shiftd), residual=engine._p(resd), ldr=512,
+                   normalize=full_epilogue, relu=full_epilogue)
+    torch.cuda.synchronize()
+    return out.data.float().cpu(), want.float()
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("m", [128, 300, 20000])
+def test_gemm_plain_bias(m, precision, cta_group):
+    got, want = _gemm_case(m, precision, cta_group, full_epilogue=False)
+    tol = dict(rtol=1e-2, atol=2e-2) if precision == "bf16" else dict(rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(got, want, **tol)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("m", [77, 40000])
+def test_gemm_sage_epilogue(m, precision, cta_group):
+    got, want = _gemm_case(m, precision, cta_group, full_epilogue=True, seed=3)
+    tol = dict(rtol=1e-2, atol=2e-2) if precision == "bf16" else dict(rtol=2e-3, atol=3e-3)
+    torch.testing.assert_close(got, want, **tol)
+
+
+def test_gemm_3xtf32_is_fp32_accurate():
+    """hi/lo split operands (bg_split_tf32) through the tf32 kernel: ~fp32 accuracy."""
+    g = torch.Generator().manual_seed(5)
+    m, k = 1000, 512
+    a, w = torch.randn(m, k, generator=g), torch.randn(512, k, generator=g) / k ** 0.5
+    want = (a.double() @ w.double().T).float()
+    act = Activation(m, k, "fp32", DEV)
+    act.data.copy_(a)
+    act.refresh_split()
+    pack = engine.pack_linear(w.to(DEV), "fp32")
+    out = Activation(m, 512, "fp32", DEV)
+    engine.gemm512(engine._segments(act, pack), m, "fp32", out)
+    torch.testing.assert_close(out.data.cpu(), want, rtol=2e-5, atol=2e-5)
+    assert torch.equal((act.hi + act.lo).cpu(), a)       # the split is exact
+
+
+# ----------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_pool_head_matches_oracle(precision):
+    torch.manual_seed(2)
+    b = make_batch(6, nx=11, ny=9)
+    n = b.num_nodes
+    x = torch.randn(n, 512)
+    if precision == "bf16":
+        x = x.bfloat16().float()
+    dec = torch.nn.Sequential(torch.nn.Linear(512, 128), torch.nn.ReLU(), torch.nn.Linear(128, 64),
+                              torch.nn.ReLU(), torch.nn.Linear(64, 1))
+    pooled_want = O.global_mean_pool(x, b.batch)
+    want = dec(pooled_want).detach()
+    idx = build_graph_index(b.edge_index.to(DEV), b.batch.to(DEV), n)
+    xa = Activation(n, 512, precision, DEV)
+    xa.data.copy_(x)
+    d = lambda t: t.detach().to(DEV).contiguous()
+    packs = {"w1": d(dec[0].weight), "b1": d(dec[0].bias), "w2": d(dec[2].weight), "b2": d(dec[2].bias),
+             "w3": d(dec[4].weight), "b3": d(dec[4].bias)}
+    pred, pooled = engine.pool_head(xa, idx, packs, 1, want_pooled=True)
+    torch.testing.assert_close(pooled.cpu(), pooled_want, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(pred.cpu(), want, rtol=1e-4, atol=1e-5)
