@@ -13,9 +13,8 @@ import threading
 
 from .build import LIB_PATH
 
-BG_BF16, BG_F32 = 0, 1
+BG_BF16, BG_F32, BG_F16 = 0, 1, 2
 BG_AGGR_MEAN, BG_AGGR_SUM, BG_AGGR_MAX = 0, 1, 2
-BG_GEMM_BF16, BG_GEMM_TF32 = 0, 1
 BG_BIG_ROW_THRESHOLD = 64
 BG_MAX_GEMM_SEGMENTS = 6
 ABI_VERSION = 1
@@ -28,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "bg_csr_max_big_rows", "bg_csr_workspace_bytes", "bg_csr_build",
     "bg_batch_info", "bg_graph_ptr_build", "bg_encoder_front",
     "bg_aggregate_workspace_bytes", "bg_sage_aggregate", "bg_gemm512",
-    "bg_pool_workspace_bytes", "bg_pool_head", "bg_cast_f32_to_bf16", "bg_split_tf32",
+    "bg_pool_workspace_bytes", "bg_pool_head", "bg_cast_f32", "bg_split_tf32",
 )
 
 
@@ -65,12 +64,12 @@ _SIGNATURES = {
     "bg_encoder_front": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, C.c_int, _P]),
     "bg_aggregate_workspace_bytes": (C.c_int, [_I32, _SZP]),
     "bg_sage_aggregate": (C.c_int, [_P, _P, C.c_int, _I64, _P, _P, _P, _I32, C.c_int, _P, C.c_size_t, _P]),
-    "bg_gemm512": (C.c_int, [C.POINTER(GemmSegment), _I32, _I64, C.c_int, C.POINTER(Epilogue), _P, C.c_int,
-                             _I64, C.c_int, _P]),
+    "bg_gemm512": (C.c_int, [C.POINTER(GemmSegment), _I32, _I64, C.c_int, C.c_int, C.POINTER(Epilogue), _P,
+                             C.c_int, _I64, C.c_int, _P]),
     "bg_pool_workspace_bytes": (C.c_int, [_I64, _SZP]),
     "bg_pool_head": (C.c_int, [_P, C.c_int, _I64, _P, _I64, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P,
                                C.c_size_t, _P]),
-    "bg_cast_f32_to_bf16": (C.c_int, [_P, _P, _I64, _P]),
+    "bg_cast_f32": (C.c_int, [_P, _P, C.c_int, _I64, _P]),
     "bg_split_tf32": (C.c_int, [_P, _P, _P, _I64, _P]),
 }
 
@@ -162,13 +161,14 @@ def sage_aggregate(x, out, dtype, n_nodes, rowptr, col, big_rows, n_big, aggr, w
                                     stream), "bg_sage_aggregate")
 
 
-def gemm512(segments, m, mode, out, out_dtype, ldo, stream, *, bias=None, bn_scale=None, bn_shift=None,
-            residual=None, ldr=0, normalize=False, relu=False, cta_group=2):
+def gemm512(segments, m, a_dtype, b_dtype, out, out_dtype, ldo, stream, *, bias=None, bn_scale=None,
+            bn_shift=None, residual=None, ldr=0, normalize=False, relu=False, cta_group=2):
     """segments: list of (a_ptr, lda, b_ptr, ldb, k)."""
     n = len(segments)
     arr = (GemmSegment * n)(*[GemmSegment(a, lda, b, ldb, k, 0) for (a, lda, b, ldb, k) in segments])
     epi = Epilogue(bias, bn_scale, bn_shift, residual, ldr, int(bool(normalize)), int(bool(relu)))
-    _check(load().bg_gemm512(arr, n, m, mode, C.byref(epi), out, out_dtype, ldo, cta_group, stream), "bg_gemm512")
+    _check(load().bg_gemm512(arr, n, m, a_dtype, b_dtype, C.byref(epi), out, out_dtype, ldo, cta_group, stream),
+           "bg_gemm512")
 
 
 def pool_head(x, dtype, n_nodes, graph_ptr, n_graphs, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out,
@@ -177,8 +177,8 @@ def pool_head(x, dtype, n_nodes, graph_ptr, n_graphs, w1, b1, w2, b2, w3, b3, ou
                                pooled_out, ws, ws_bytes, stream), "bg_pool_head")
 
 
-def cast_f32_to_bf16(src, dst, n, stream):
-    _check(load().bg_cast_f32_to_bf16(src, dst, n, stream), "bg_cast_f32_to_bf16")
+def cast_f32(src, dst, dst_dtype, n, stream):
+    _check(load().bg_cast_f32(src, dst, dst_dtype, n, stream), "bg_cast_f32")
 
 
 def split_tf32(src, hi, lo, n, stream):

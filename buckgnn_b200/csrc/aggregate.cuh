@@ -29,13 +29,13 @@ template <int kAggr> BG_DEVINL float agg_op(float a, float b) {
 }
 
 // ---- per-lane row fragments: 16 values of one 512-wide row -------------------------------
-// bf16: two 16-byte chunks at columns [8*lane, +8) and [256 + 8*lane, +8)
+// bf16/f16: two 16-byte chunks at columns [8*lane, +8) and [256 + 8*lane, +8)
 // f32 : four 16-byte chunks at columns [4*lane + 128*j, +4), j = 0..3
 template <typename T> struct RowFrag;
 
-template <> struct RowFrag<__nv_bfloat16> {
+template <typename T> struct RowFrag16 {
   uint4 q[2];
-  BG_DEVINL void load(const __nv_bfloat16* row, int lane) {
+  BG_DEVINL void load(const T* row, int lane) {
     const uint4* p = reinterpret_cast<const uint4*>(row);
     q[0] = ldg_v4(p + lane);
     q[1] = ldg_v4(p + 32 + lane);
@@ -44,14 +44,16 @@ template <> struct RowFrag<__nv_bfloat16> {
     const uint32_t* u = reinterpret_cast<const uint32_t*>(q);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      acc[2 * i] = agg_op<kAggr>(acc[2 * i], bf16_lo(u[i]));
-      acc[2 * i + 1] = agg_op<kAggr>(acc[2 * i + 1], bf16_hi(u[i]));
+      acc[2 * i] = agg_op<kAggr>(acc[2 * i], Pack16<T>::lo(u[i]));
+      acc[2 * i + 1] = agg_op<kAggr>(acc[2 * i + 1], Pack16<T>::hi(u[i]));
     }
   }
-  static BG_DEVINL void store(__nv_bfloat16* row, int lane, const float (&v)[16]) {
+  static BG_DEVINL void store(T* row, int lane, const float (&v)[16]) {
     uint4 a, b;
-    a.x = pack_bf16(v[0], v[1]);  a.y = pack_bf16(v[2], v[3]);  a.z = pack_bf16(v[4], v[5]);  a.w = pack_bf16(v[6], v[7]);
-    b.x = pack_bf16(v[8], v[9]);  b.y = pack_bf16(v[10], v[11]); b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
+    a.x = Pack16<T>::pack(v[0], v[1]);  a.y = Pack16<T>::pack(v[2], v[3]);
+    a.z = Pack16<T>::pack(v[4], v[5]);  a.w = Pack16<T>::pack(v[6], v[7]);
+    b.x = Pack16<T>::pack(v[8], v[9]);  b.y = Pack16<T>::pack(v[10], v[11]);
+    b.z = Pack16<T>::pack(v[12], v[13]); b.w = Pack16<T>::pack(v[14], v[15]);
     uint4* p = reinterpret_cast<uint4*>(row);
     stg_v4(p + lane, a);
     stg_v4(p + 32 + lane, b);
@@ -59,6 +61,8 @@ template <> struct RowFrag<__nv_bfloat16> {
   // column of accumulator slot i for this lane
   static BG_DEVINL int col_of(int lane, int i) { return (i < 8) ? (8 * lane + i) : (256 + 8 * lane + (i - 8)); }
 };
+template <> struct RowFrag<__nv_bfloat16> : RowFrag16<__nv_bfloat16> {};
+template <> struct RowFrag<__half> : RowFrag16<__half> {};
 
 template <> struct RowFrag<float> {
   uint4 q[4];
@@ -190,7 +194,7 @@ k_aggregate_hubs(const T* __restrict__ x, T* __restrict__ out,
     float v = __ldcg(hp + c);
     for (int s = 1; s < kHubSlices; ++s) v = agg_op<kAggr>(v, __ldcg(hp + (size_t)s * kHidden + c));
     if constexpr (kAggr == BG_AGGR_MEAN) v = v / (float)max(deg, 1);
-    if constexpr (sizeof(T) == 2) orow[c] = __float2bfloat16_rn(v); else orow[c] = v;
+    if constexpr (sizeof(T) == 2) orow[c] = Pack16<T>::one(v); else orow[c] = v;
   }
   if (threadIdx.x == 0) ticket[hub] = 0;    // leave the ticket ready for the next launch
 }

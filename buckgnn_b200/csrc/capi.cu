@@ -50,10 +50,11 @@ PFN_tensorMapEncodeTiled get_tensor_map_encoder() {
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-__global__ void k_cast_f32_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+template <typename T>
+__global__ void k_cast_f32_16(const float* __restrict__ src, T* __restrict__ dst, int64_t n) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    dst[i] = __float2bfloat16_rn(src[i]);
+    dst[i] = Pack16<T>::one(src[i]);
 }
 __global__ void k_split_tf32(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -148,7 +149,7 @@ int bg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int key_row,
   BG_CUDA_OK(cudaMemsetAsync(rowptr, 0, sizeof(int32_t), stream));           // covers N == 0
   if (N == 0) return BG_OK;
   if (E > 0) {
-    k_csr_hist<<<grid_for(E, 256, sms * 16), 256, 0, stream>>>(key, E, N, w.deg, info);
+    k_csr_hist<<<grid_for(E, 256, sms * 16), 256, 0, stream>>>(key, other, E, N, w.deg, info);
     BG_LAUNCH_OK();
   }
   k_scan_block_sums<<<w.n_scan_blocks, 1024, 0, stream>>>(w.deg, N, w.block_sums);
@@ -158,7 +159,7 @@ int bg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int key_row,
   k_scan_apply<<<w.n_scan_blocks, 1024, 0, stream>>>(w.deg, N, w.block_sums, rowptr, w.cursor, big_rows, info, max_big);
   BG_LAUNCH_OK();
   if (E > 0) {
-    k_csr_fill<<<grid_for(E, 256, sms * 16), 256, 0, stream>>>(key, E, N, w.cursor, perm);
+    k_csr_fill<<<grid_for(E, 256, sms * 16), 256, 0, stream>>>(key, other, E, N, w.cursor, perm);
     BG_LAUNCH_OK();
     k_csr_sort_small<<<(unsigned)ceil_div64(N, 256), 256, 0, stream>>>(rowptr, N, other, perm, col);
     BG_LAUNCH_OK();
@@ -201,17 +202,17 @@ int bg_encoder_front(const float* x, int64_t N, int32_t F, const float* w1, cons
   if (!x || !w1 || !b1 || !w2 || !b2 || !out || !aligned16(out)) return fail(BG_ERR_INVALID, "bg_encoder_front: bad pointer");
   const int smem = (int)sizeof(EncoderSmem);
   const unsigned grid = (unsigned)min64(ceil_div64(N, kEncRows), (int64_t)sm_count() * 3);
-  if (out_dtype == BG_BF16) {
-    static bool set = false;
-    if (!set) { BG_CUDA_OK(cudaFuncSetAttribute(k_encoder_front<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
-    k_encoder_front<__nv_bfloat16><<<grid, kEncThreads, smem, stream>>>(x, N, F, w1, b1, w2, b2, static_cast<__nv_bfloat16*>(out));
-  } else if (out_dtype == BG_F32) {
-    static bool set = false;
-    if (!set) { BG_CUDA_OK(cudaFuncSetAttribute(k_encoder_front<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
-    k_encoder_front<float><<<grid, kEncThreads, smem, stream>>>(x, N, F, w1, b1, w2, b2, static_cast<float*>(out));
-  } else {
-    return fail(BG_ERR_INVALID, "bg_encoder_front: bad out_dtype");
+#define BG_ENC_CASE(T)                                                                                         \
+  {                                                                                                            \
+    static bool set = false;                                                                                   \
+    if (!set) { BG_CUDA_OK(cudaFuncSetAttribute(k_encoder_front<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; } \
+    k_encoder_front<T><<<grid, kEncThreads, smem, stream>>>(x, N, F, w1, b1, w2, b2, static_cast<T*>(out));    \
   }
+  if (out_dtype == BG_BF16) BG_ENC_CASE(__nv_bfloat16)
+  else if (out_dtype == BG_F16) BG_ENC_CASE(__half)
+  else if (out_dtype == BG_F32) BG_ENC_CASE(float)
+  else return fail(BG_ERR_INVALID, "bg_encoder_front: bad out_dtype");
+#undef BG_ENC_CASE
   BG_LAUNCH_OK();
   return BG_OK;
 }
@@ -243,6 +244,9 @@ int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t N, const int3
   if (dtype == BG_BF16)
     return aggregate_dispatch(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, rowptr, col,
                               big_rows, n_big, aggr, partial, ticket, stream);
+  if (dtype == BG_F16)
+    return aggregate_dispatch(static_cast<const __half*>(x), static_cast<__half*>(out), N, rowptr, col,
+                              big_rows, n_big, aggr, partial, ticket, stream);
   if (dtype == BG_F32)
     return aggregate_dispatch(static_cast<const float*>(x), static_cast<float*>(out), N, rowptr, col, big_rows, n_big,
                               aggr, partial, ticket, stream);
@@ -250,16 +254,20 @@ int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t N, const int3
 }
 
 // ------------------------------------------------------------------ K3
-int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int mode, const bg_epilogue* epi,
-               void* out, int out_dtype, int64_t ldo, int cta_group, void* stream_) {
+static inline int umma_format_of(int dtype) { return dtype == BG_F16 ? 0 : (dtype == BG_BF16 ? 1 : (dtype == BG_F32 ? 2 : -1)); }
+
+int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtype, int b_dtype,
+               const bg_epilogue* epi, void* out, int out_dtype, int64_t ldo, int cta_group, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!segs || n_seg < 1 || n_seg > BG_MAX_GEMM_SEGMENTS) return fail(BG_ERR_INVALID, "bg_gemm512: bad segment count");
   if (m < 0 || m >= 0x7fffffffLL) return fail(BG_ERR_INVALID, "bg_gemm512: bad m");
   if (m == 0) return BG_OK;
-  if (mode != BG_GEMM_BF16 && mode != BG_GEMM_TF32) return fail(BG_ERR_INVALID, "bg_gemm512: bad mode");
-  if (out_dtype != BG_BF16 && out_dtype != BG_F32) return fail(BG_ERR_INVALID, "bg_gemm512: bad out_dtype");
+  const int a_fmt = umma_format_of(a_dtype), b_fmt = umma_format_of(b_dtype);
+  if (a_fmt < 0 || b_fmt < 0 || ((a_fmt == 2) != (b_fmt == 2)))
+    return fail(BG_ERR_INVALID, "bg_gemm512: operand dtypes must be both 16-bit (bf16/f16) or both f32");
+  if (umma_format_of(out_dtype) < 0) return fail(BG_ERR_INVALID, "bg_gemm512: bad out_dtype");
   if (cta_group != 1 && cta_group != 2) return fail(BG_ERR_INVALID, "bg_gemm512: cta_group must be 1 or 2");
-  const bool tf32 = mode == BG_GEMM_TF32;
+  const bool tf32 = a_fmt == 2;
   const int esz = tf32 ? 4 : 2, osz = out_dtype == BG_F32 ? 4 : 2;
   const int kblk = kStageKBytes / esz;
   if (!out || !aligned16(out) || (ldo * osz) % 16 != 0 || ldo < kHidden) return fail(BG_ERR_INVALID, "bg_gemm512: bad out/ldo");
@@ -267,16 +275,17 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int mode, 
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < n_seg; ++s) {
     const bg_gemm_segment& g = segs[s];
-    if (!g.a || !g.b || g.k <= 0 || g.k % kblk != 0) return fail(BG_ERR_UNSUPPORTED, "bg_gemm512: k must be a positive multiple of 64 (bf16) / 32 (tf32)");
+    if (!g.a || !g.b || g.k <= 0 || g.k % kblk != 0) return fail(BG_ERR_UNSUPPORTED, "bg_gemm512: k must be a positive multiple of 64 (16-bit) / 32 (tf32)");
     if (!aligned16(g.a) || !aligned16(g.b) || (g.lda * esz) % 16 != 0 || (g.ldb * esz) % 16 != 0 || g.lda < g.k || g.ldb < g.k)
       return fail(BG_ERR_INVALID, "bg_gemm512: operand alignment / leading dimension");
-    int rc = make_operand_map(&p.seg[s].a, g.a, m, g.k, g.lda, tf32);
-    if (rc == BG_OK) rc = make_operand_map(&p.seg[s].b, g.b, kHidden, g.k, g.ldb, tf32);
+    int rc = make_operand_map(&p.seg[s].a, g.a, m, g.k, g.lda, (uint32_t)a_fmt);
+    if (rc == BG_OK) rc = make_operand_map(&p.seg[s].b, g.b, kHidden, g.k, g.ldb, (uint32_t)b_fmt);
     if (rc != BG_OK) return fail(rc, "bg_gemm512: cuTensorMapEncodeTiled failed");
     p.kblocks[s] = g.k / kblk;
   }
   p.n_seg = n_seg;
   p.k_elems_per_block = kblk;
+  p.a_fmt = (uint32_t)a_fmt; p.b_fmt = (uint32_t)b_fmt;
   p.n_tiles = (int32_t)ceil_div64(m, kTileM * cta_group);
   p.m = m;
   if (epi) {
@@ -287,17 +296,13 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int mode, 
     p.residual = epi->residual; p.ldr = epi->ldr; p.normalize = epi->normalize; p.relu = epi->relu;
   }
   p.out = out; p.ldo = ldo;
-  const int key = (cta_group == 2 ? 4 : 0) | (tf32 ? 2 : 0) | (out_dtype == BG_F32 ? 1 : 0);
-  switch (key) {
-    case 0: return launch_gemm512<1, false, __nv_bfloat16>(p, stream);
-    case 1: return launch_gemm512<1, false, float>(p, stream);
-    case 2: return launch_gemm512<1, true, __nv_bfloat16>(p, stream);
-    case 3: return launch_gemm512<1, true, float>(p, stream);
-    case 4: return launch_gemm512<2, false, __nv_bfloat16>(p, stream);
-    case 5: return launch_gemm512<2, false, float>(p, stream);
-    case 6: return launch_gemm512<2, true, __nv_bfloat16>(p, stream);
-    default: return launch_gemm512<2, true, float>(p, stream);
-  }
+#define BG_GEMM_OUT(CG, TF)                                                              \
+  (out_dtype == BG_BF16 ? launch_gemm512<CG, TF, __nv_bfloat16>(p, stream)               \
+   : out_dtype == BG_F16 ? launch_gemm512<CG, TF, __half>(p, stream)                     \
+                         : launch_gemm512<CG, TF, float>(p, stream))
+  if (cta_group == 1) return tf32 ? BG_GEMM_OUT(1, true) : BG_GEMM_OUT(1, false);
+  return tf32 ? BG_GEMM_OUT(2, true) : BG_GEMM_OUT(2, false);
+#undef BG_GEMM_OUT
 }
 
 // ------------------------------------------------------------------ K4
@@ -323,6 +328,8 @@ int bg_pool_head(const void* x, int dtype, int64_t N, const int32_t* graph_ptr, 
   dim3 grid((unsigned)G, kPoolSlices);
   if (dtype == BG_BF16)
     k_pool_partial<__nv_bfloat16><<<grid, kPoolWarps * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), graph_ptr, partial);
+  else if (dtype == BG_F16)
+    k_pool_partial<__half><<<grid, kPoolWarps * 32, 0, stream>>>(static_cast<const __half*>(x), graph_ptr, partial);
   else if (dtype == BG_F32)
     k_pool_partial<float><<<grid, kPoolWarps * 32, 0, stream>>>(static_cast<const float*>(x), graph_ptr, partial);
   else
@@ -334,11 +341,14 @@ int bg_pool_head(const void* x, int dtype, int64_t N, const int32_t* graph_ptr, 
 }
 
 // ------------------------------------------------------------------ helpers
-int bg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream_) {
+int bg_cast_f32(const float* src, void* dst, int dst_dtype, int64_t n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (n < 0 || (n > 0 && (!src || !dst))) return fail(BG_ERR_INVALID, "bg_cast_f32_to_bf16: bad argument");
+  if (n < 0 || (n > 0 && (!src || !dst))) return fail(BG_ERR_INVALID, "bg_cast_f32: bad argument");
+  if (dst_dtype != BG_BF16 && dst_dtype != BG_F16) return fail(BG_ERR_INVALID, "bg_cast_f32: dst_dtype must be bf16 or f16");
   if (n == 0) return BG_OK;
-  k_cast_f32_bf16<<<grid_for(n, 256, sm_count() * 8), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  const unsigned grid = grid_for(n, 256, sm_count() * 8);
+  if (dst_dtype == BG_BF16) k_cast_f32_16<__nv_bfloat16><<<grid, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  else k_cast_f32_16<__half><<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), n);
   BG_LAUNCH_OK();
   return BG_OK;
 }

@@ -8,6 +8,7 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "../../include/buckgnn_b200.h"
@@ -74,6 +75,25 @@ BG_DEVINL uint32_t pack_bf16(float a, float b) {   // a -> low half, b -> high h
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+
+BG_DEVINL uint32_t pack_f16(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// 16-bit storage formats: unpack a pair / pack a pair / scalar convert
+template <typename T> struct Pack16;
+template <> struct Pack16<__nv_bfloat16> {
+  static BG_DEVINL float lo(uint32_t u) { return bf16_lo(u); }
+  static BG_DEVINL float hi(uint32_t u) { return bf16_hi(u); }
+  static BG_DEVINL uint32_t pack(float a, float b) { return pack_bf16(a, b); }
+  static BG_DEVINL __nv_bfloat16 one(float a) { return __float2bfloat16_rn(a); }
+};
+template <> struct Pack16<__half> {
+  static BG_DEVINL float lo(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu))); }
+  static BG_DEVINL float hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
+  static BG_DEVINL uint32_t pack(float a, float b) { return pack_f16(a, b); }
+  static BG_DEVINL __half one(float a) { return __float2half_rn(a); }
+};
 
 // ------------------------------------------------------------------ watchdog
 // Barrier waits are bounded: after ~2^31 cycles (about a second) the kernel records
@@ -232,9 +252,9 @@ BG_DEVINL uint64_t umma_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor: fp32 accumulate, A/B both K-major, format 1 = bf16, 2 = tf32
-__host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t m, uint32_t n) {
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// instruction descriptor: fp32 accumulate, A/B both K-major; operand format 0 = f16, 1 = bf16, 2 = tf32
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t a_fmt, uint32_t b_fmt, uint32_t m, uint32_t n) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 }  // namespace bg

@@ -21,13 +21,16 @@ namespace bg {
 constexpr int kScanItemsPerBlock = 4096;   // 1024 threads x 4
 constexpr int kSortSmemElems = 32768;      // hub rows up to this degree sort in shared memory
 
-__global__ void k_csr_hist(const int64_t* __restrict__ key, int64_t E, int64_t N,
+// an edge with either endpoint outside [0, N) is dropped and flagged (info bit 0)
+BG_DEVINL bool edge_ok(int64_t k, int64_t o, int64_t N) { return k >= 0 && k < N && o >= 0 && o < N; }
+
+__global__ void k_csr_hist(const int64_t* __restrict__ key, const int64_t* __restrict__ other, int64_t E, int64_t N,
                            int32_t* __restrict__ deg, int32_t* __restrict__ info) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   bool bad = false;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
     int64_t k = key[e];
-    if (k < 0 || k >= N) { bad = true; continue; }
+    if (!edge_ok(k, other[e], N)) { bad = true; continue; }
     atomicAdd(&deg[k], 1);
   }
   if (bad) atomicOr(&info[0], 1);
@@ -118,12 +121,12 @@ __global__ void __launch_bounds__(1024) k_scan_apply(const int32_t* __restrict__
   }
 }
 
-__global__ void k_csr_fill(const int64_t* __restrict__ key, int64_t E, int64_t N,
+__global__ void k_csr_fill(const int64_t* __restrict__ key, const int64_t* __restrict__ other, int64_t E, int64_t N,
                            int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
     int64_t k = key[e];
-    if (k < 0 || k >= N) continue;
+    if (!edge_ok(k, other[e], N)) continue;
     int32_t pos = atomicAdd(&cursor[k], 1);
     perm[pos] = (int32_t)e;
   }

@@ -99,8 +99,8 @@ k_encoder_front(const float* __restrict__ x, int64_t N, int F,
         for (int b = 0; b < 8; ++b) v[b] = fmaxf(acc[a][b], 0.f);
         if constexpr (sizeof(TOut) == 2) {
           uint4 q;
-          q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]);
-          q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+          q.x = Pack16<TOut>::pack(v[0], v[1]); q.y = Pack16<TOut>::pack(v[2], v[3]);
+          q.z = Pack16<TOut>::pack(v[4], v[5]); q.w = Pack16<TOut>::pack(v[6], v[7]);
           stg_v4(out + m * kEncH2 + tx * 8, q);
         } else {
           uint4 q0, q1;

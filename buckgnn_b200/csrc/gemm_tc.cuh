@@ -45,7 +45,8 @@ struct alignas(64) GemmParams {
   GemmSeg seg[BG_MAX_GEMM_SEGMENTS];
   int32_t kblocks[BG_MAX_GEMM_SEGMENTS];
   int32_t n_seg;
-  int32_t k_elems_per_block;        // 64 (bf16) or 32 (tf32)
+  int32_t k_elems_per_block;        // 64 (16-bit operands) or 32 (tf32)
+  uint32_t a_fmt, b_fmt;            // UMMA operand formats: 0 f16, 1 bf16, 2 tf32
   int32_t n_tiles;                  // row tiles of 128*cg rows
   int32_t normalize, relu;
   int64_t m;
@@ -145,7 +146,7 @@ k_gemm512(const __grid_constant__ GemmParams p) {
   } else if (warp == 1) {
     // ================================================================ MMA issuer (leader CTA)
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc(kTf32 ? 2u : 1u, kTileM * kCg, 256);
+      const uint32_t idesc = umma_idesc(p.a_fmt, p.b_fmt, kTileM * kCg, 256);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = tile0; tile < p.n_tiles; tile += tile_stride, ++it) {
         mbar_wait(tmem_empty_bar, (it & 1u) ^ 1u, kTagTmemEmpty);   // epilogue drained the accumulator
@@ -229,7 +230,7 @@ k_gemm512(const __grid_constant__ GemmParams p) {
           const uint32_t* ru = reinterpret_cast<const uint32_t*>(res);
           if constexpr (sizeof(TOut) == 2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { v[2 * i] += bf16_lo(ru[i]); v[2 * i + 1] += bf16_hi(ru[i]); }
+            for (int i = 0; i < 16; ++i) { v[2 * i] += Pack16<TOut>::lo(ru[i]); v[2 * i + 1] += Pack16<TOut>::hi(ru[i]); }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(ru[i]);
@@ -241,8 +242,8 @@ k_gemm512(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
-              o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+              o.x = Pack16<TOut>::pack(v[8 * j], v[8 * j + 1]); o.y = Pack16<TOut>::pack(v[8 * j + 2], v[8 * j + 3]);
+              o.z = Pack16<TOut>::pack(v[8 * j + 4], v[8 * j + 5]); o.w = Pack16<TOut>::pack(v[8 * j + 6], v[8 * j + 7]);
               stg_v4(dst + j, o);
             }
           } else {
@@ -277,16 +278,20 @@ typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, 
 PFN_tensorMapEncodeTiled get_tensor_map_encoder();
 
 // [rows, k] row-major matrix, box = 128 rows x 128 bytes of K, 128B swizzle, zero fill out of bounds
+// fmt: UMMA operand format (0 f16, 1 bf16, 2 tf32/f32)
 static inline int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t k, int64_t ld,
-                                   bool tf32) {
+                                   uint32_t fmt) {
   PFN_tensorMapEncodeTiled enc = get_tensor_map_encoder();
   if (!enc) return BG_ERR_CUDA;
+  const bool tf32 = fmt == 2;
   const int esz = tf32 ? 4 : 2;
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                      : (fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
   cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
   cuuint32_t box[2] = {(cuuint32_t)(kStageKBytes / esz), 128u};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  CUresult r = enc(map, dt, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

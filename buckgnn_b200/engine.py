@@ -22,11 +22,80 @@ import torch
 
 from . import capi
 
-PRECISIONS = ("bf16", "tf32", "fp32")   # fp32 = 3xTF32 split ("fp32-GEMM mode")
+# precision mode -> (activation storage, weight storage) of the tensor-core GEMMs
+#   mixed : bf16 activations (fp32-like range) x fp16 weights (11-bit significand).  The
+#           weight rounding is the error that does NOT average out over nodes, so this is
+#           ~8x more accurate than bf16 x bf16 at the same cost; the default.
+#   fp16  : fp16 x fp16 (most accurate 16-bit mode; activations must stay < 65504)
+#   bf16  : bf16 x bf16
+#   tf32  : fp32 storage, operands read as tf32
+#   fp32  : fp32 storage, hi/lo split operands, 3 tf32 products per term ("fp32-GEMM mode")
+_TORCH = {capi.BG_BF16: torch.bfloat16, capi.BG_F16: torch.float16, capi.BG_F32: torch.float32}
+PRECISION_FORMATS = {
+    "mixed": (capi.BG_BF16, capi.BG_F16),
+    "fp16": (capi.BG_F16, capi.BG_F16),
+    "bf16": (capi.BG_BF16, capi.BG_BF16),
+    "tf32": (capi.BG_F32, capi.BG_F32),
+    "fp32": (capi.BG_F32, capi.BG_F32),
+}
+PRECISIONS = tuple(PRECISION_FORMATS)
 
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+class _KernelTimers:
+    """Optional CUDA-event brackets around each kernel class, recorded on the launching
+    stream (bench.py turns them on for its timed region; off by default = zero cost)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.spans = []
+
+    def enable(self):
+        self.enabled, self.spans = True, []
+
+    def disable(self):
+        self.enabled, self.spans = False, []
+
+    class _Span:
+        def __init__(self, owner, name):
+            self.owner, self.name = owner, name
+
+        def __enter__(self):
+            if self.owner.enabled:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+            return self
+
+        def __exit__(self, *a):
+            if self.owner.enabled:
+                self.e1.record()
+                self.owner.spans.append((self.name, self.e0, self.e1))
+
+    def span(self, name):
+        return self._Span(self, name)
+
+    def summary(self):
+        """{name: (total_ms, calls)} -- synchronises."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.spans:
+            ms, n = out.get(name, (0.0, 0))
+            out[name] = (ms + e0.elapsed_time(e1), n + 1)
+        return out
+
+
+TIMERS = _KernelTimers()
+
+
+def LAUNCHES_PER_FORWARD(num_layers: int) -> int:
+    """Kernels of ours launched by one GraphSAGE forward: CSR build 7 (hist, 3 scan, fill,
+    2 sorts) + batch_info + graph_ptr + encoder 2 + per layer (aggregate rows + hubs + GEMM)
+    + pool 2.  (memsets and the 16-byte info read-back are not counted.)"""
+    return 7 + 2 + 2 + 3 * num_layers + 2
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -73,8 +142,9 @@ def build_graph_index(edge_index: torch.Tensor, batch: Optional[torch.Tensor], n
     info = torch.zeros(4, **i32)
     ws_bytes = capi.csr_workspace_bytes(N, E)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    capi.csr_build(edge_index.data_ptr(), E, N, key_row, rowptr.data_ptr(), col.data_ptr(), perm.data_ptr(),
-                   big_rows.data_ptr(), info.data_ptr(), ws.data_ptr(), ws_bytes, s)
+    with TIMERS.span("csr_build"):
+        capi.csr_build(edge_index.data_ptr(), E, N, key_row, rowptr.data_ptr(), col.data_ptr(), perm.data_ptr(),
+                       big_rows.data_ptr(), info.data_ptr(), ws.data_ptr(), ws_bytes, s)
     if batch is not None:
         _require_cuda(batch, "batch")
         if batch.dtype != torch.int64 or batch.dim() != 1 or batch.shape[0] != N:
@@ -102,22 +172,24 @@ def build_graph_index(edge_index: torch.Tensor, batch: Optional[torch.Tensor], n
 class LinearPack:
     """A weight [512, K] (nn.Linear layout) in the operand format of one precision mode."""
     k: int
-    parts: Tuple[torch.Tensor, ...]     # bf16: (w,)  tf32: (w,)  fp32: (w_hi, w_lo)
+    parts: Tuple[torch.Tensor, ...]     # 16-bit / tf32: (w,)   fp32: (w_hi, w_lo)
+    code: int = capi.BG_F32             # bg_dtype of the parts
 
 
 def pack_linear(weight: torch.Tensor, precision: str) -> LinearPack:
     w = weight.detach().to(torch.float32).contiguous()
     k = w.shape[1]
     s = _stream()
-    if precision == "bf16":
-        out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
-        capi.cast_f32_to_bf16(w.data_ptr(), out.data_ptr(), w.numel(), s)
-        return LinearPack(k, (out,))
+    code = PRECISION_FORMATS[precision][1]
+    if code != capi.BG_F32:
+        out = torch.empty(w.shape, dtype=_TORCH[code], device=w.device)
+        capi.cast_f32(w.data_ptr(), out.data_ptr(), code, w.numel(), s)
+        return LinearPack(k, (out,), code)
     if precision == "tf32":
-        return LinearPack(k, (w.clone(),))
+        return LinearPack(k, (w.clone(),), code)
     hi, lo = torch.empty_like(w), torch.empty_like(w)
     capi.split_tf32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), s)
-    return LinearPack(k, (hi, lo))
+    return LinearPack(k, (hi, lo), code)
 
 
 @dataclass
@@ -141,8 +213,8 @@ class Activation:
 
     def __init__(self, n: int, width: int, precision: str, device):
         self.precision = precision
-        self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
-        self.code = capi.BG_BF16 if precision == "bf16" else capi.BG_F32
+        self.code = PRECISION_FORMATS[precision][0]
+        self.dtype = _TORCH[self.code]
         self.data = torch.empty((n, width), dtype=self.dtype, device=device)
         self.hi = self.lo = None
         if precision == "fp32":
@@ -155,7 +227,7 @@ class Activation:
 
 
 def _segments(act: Activation, w: LinearPack):
-    """K-segments of act . w^T for the mode: 1 (bf16/tf32) or 3 (3xTF32: hi*hi + hi*lo + lo*hi)."""
+    """K-segments of act . w^T for the mode: 1, or 3 for fp32 (3xTF32: hi*hi + hi*lo + lo*hi)."""
     k = w.k
     ld = act.data.shape[1]
     if act.precision != "fp32":
@@ -167,8 +239,8 @@ def _segments(act: Activation, w: LinearPack):
 
 
 def gemm512(segs, m: int, precision: str, out: Activation, *, cta_group: int = 2, **epi) -> None:
-    mode = capi.BG_GEMM_BF16 if precision == "bf16" else capi.BG_GEMM_TF32
-    capi.gemm512(segs, m, mode, out.data.data_ptr(), out.code, out.data.shape[1], _stream(),
+    a_code, b_code = PRECISION_FORMATS[precision]
+    capi.gemm512(segs, m, a_code, b_code, out.data.data_ptr(), out.code, out.data.shape[1], _stream(),
                  cta_group=cta_group, **epi)
     out.refresh_split()
 
@@ -176,9 +248,10 @@ def gemm512(segs, m: int, precision: str, out: Activation, *, cta_group: int = 2
 def aggregate(x: Activation, out: Activation, idx: GraphIndex, aggr: str) -> None:
     ws_bytes = capi.aggregate_workspace_bytes(idx.n_big)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.data.device)
-    capi.sage_aggregate(x.data.data_ptr(), out.data.data_ptr(), x.code, idx.n_nodes, idx.rowptr.data_ptr(),
-                        idx.col.data_ptr(), idx.big_rows.data_ptr(), idx.n_big, capi.AGGR_CODES[aggr],
-                        ws.data_ptr(), ws_bytes, _stream())
+    with TIMERS.span("aggregate"):
+        capi.sage_aggregate(x.data.data_ptr(), out.data.data_ptr(), x.code, idx.n_nodes, idx.rowptr.data_ptr(),
+                            idx.col.data_ptr(), idx.big_rows.data_ptr(), idx.n_big, capi.AGGR_CODES[aggr],
+                            ws.data_ptr(), ws_bytes, _stream())
     out.refresh_split()
 
 
@@ -187,10 +260,12 @@ def encoder_forward(x: torch.Tensor, enc_w: Dict[str, torch.Tensor], w3: LinearP
     """node_encoder (Models/BuckGNN.py:68-74): two fp32 CUDA-core layers, then 128->512 on tcgen05."""
     n, f = x.shape
     h = Activation(n, 128, precision, x.device)
-    capi.encoder_front(x.data_ptr(), n, f, enc_w["w1"].data_ptr(), enc_w["b1"].data_ptr(), enc_w["w2"].data_ptr(),
-                       enc_w["b2"].data_ptr(), h.data.data_ptr(), h.code, _stream())
+    with TIMERS.span("encoder_front"):
+        capi.encoder_front(x.data_ptr(), n, f, enc_w["w1"].data_ptr(), enc_w["b1"].data_ptr(),
+                           enc_w["w2"].data_ptr(), enc_w["b2"].data_ptr(), h.data.data_ptr(), h.code, _stream())
     h.refresh_split()
-    gemm512(_segments(h, w3), n, precision, out, cta_group=cta_group, bias=enc_w["b3"].data_ptr())
+    with TIMERS.span("encoder_gemm"):
+        gemm512(_segments(h, w3), n, precision, out, cta_group=cta_group, bias=enc_w["b3"].data_ptr())
 
 
 def sage_layer(x: Activation, agg: Activation, out: Activation, idx: GraphIndex, layer: SageLayerPack, *,
@@ -198,10 +273,11 @@ def sage_layer(x: Activation, agg: Activation, out: Activation, idx: GraphIndex,
     """One reference layer iteration (Models/BuckGNN.py:447-457) = aggregate + fused update GEMM."""
     aggregate(x, agg, idx, aggr)
     segs = _segments(agg, layer.lin_l) + _segments(x, layer.lin_r)
-    gemm512(segs, idx.n_nodes, x.precision, out, cta_group=cta_group,
-            bias=layer.bias.data_ptr(), bn_scale=_p(layer.bn_scale), bn_shift=_p(layer.bn_shift),
-            residual=x.data.data_ptr() if residual else None, ldr=x.data.shape[1],
-            normalize=normalize, relu=relu)
+    with TIMERS.span("sage_update"):
+        gemm512(segs, idx.n_nodes, x.precision, out, cta_group=cta_group,
+                bias=layer.bias.data_ptr(), bn_scale=_p(layer.bn_scale), bn_shift=_p(layer.bn_shift),
+                residual=x.data.data_ptr() if residual else None, ldr=x.data.shape[1],
+                normalize=normalize, relu=relu)
 
 
 def pool_head(x: Activation, idx: GraphIndex, dec: Dict[str, torch.Tensor], out_dim: int,
@@ -213,8 +289,9 @@ def pool_head(x: Activation, idx: GraphIndex, dec: Dict[str, torch.Tensor], out_
     pooled = torch.empty((g, 512), dtype=torch.float32, device=dev) if want_pooled else None
     ws_bytes = capi.pool_workspace_bytes(g)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    capi.pool_head(x.data.data_ptr(), x.code, idx.n_nodes, idx.graph_ptr.data_ptr(), g,
-                   dec["w1"].data_ptr(), dec["b1"].data_ptr(), dec["w2"].data_ptr(), dec["b2"].data_ptr(),
-                   dec["w3"].data_ptr(), dec["b3"].data_ptr(), out_dim, pred.data_ptr(), _p(pooled),
-                   ws.data_ptr(), ws_bytes, _stream())
+    with TIMERS.span("pool_head"):
+        capi.pool_head(x.data.data_ptr(), x.code, idx.n_nodes, idx.graph_ptr.data_ptr(), g,
+                       dec["w1"].data_ptr(), dec["b1"].data_ptr(), dec["w2"].data_ptr(), dec["b2"].data_ptr(),
+                       dec["w3"].data_ptr(), dec["b3"].data_ptr(), out_dim, pred.data_ptr(), _p(pooled),
+                       ws.data_ptr(), ws_bytes, _stream())
     return pred, pooled

@@ -13,8 +13,9 @@ Mirrors `Models/BuckGNN.py` of the reference:
 The forward never touches PyG / torch_scatter / ATen math: it is the kernel sequence
 in `engine.py`.  CPU tensors raise -- there is no fallback path.
 
-Extra, non-reference keyword: `precision` in {"bf16", "tf32", "fp32"} selects how the
-tensor-core GEMMs read their operands (fp32 = 3xTF32 split, the "fp32-GEMM mode").
+Extra, non-reference keyword: `precision` in {"mixed", "fp16", "bf16", "tf32", "fp32"}
+selects how the tensor-core GEMMs read their operands (engine.PRECISION_FORMATS; fp32 =
+3xTF32 split, the "fp32-GEMM mode").
 """
 from __future__ import annotations
 
@@ -89,7 +90,7 @@ class BuckGNN(nn.Module):
     def __init__(self, num_node_features, num_edge_features, hidden_channels=128,
                  num_layers=6, pooling_layer="mean", prediction_type="buckling",
                  use_z_coord=False, use_rotations=False, dropout_rate=0.1,
-                 model_name="GraphSAGE_MLP", *, precision: str = "bf16", cta_group: int = 2,
+                 model_name="GraphSAGE_MLP", *, precision: str = "mixed", cta_group: int = 2,
                  cache_index: bool = False):
         super().__init__()
         if precision not in engine.PRECISIONS:

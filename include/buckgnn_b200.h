@@ -42,18 +42,11 @@ typedef enum bg_status {
   BG_ERR_DEVICE = -5        /* current device is not sm_100 */
 } bg_status;
 
-typedef enum bg_dtype { BG_BF16 = 0, BG_F32 = 1 } bg_dtype;
+typedef enum bg_dtype { BG_BF16 = 0, BG_F32 = 1, BG_F16 = 2 } bg_dtype;
 
 /* SAGEConv(aggr=...) values used by the reference (Models/BuckGNN.py:118,130,145,160,175);
  * 'add' and 'sum' are the same reduction. */
 typedef enum bg_aggr { BG_AGGR_MEAN = 0, BG_AGGR_SUM = 1, BG_AGGR_MAX = 2 } bg_aggr;
-
-/* how the tensor-core GEMM reads its operands */
-typedef enum bg_gemm_mode {
-  BG_GEMM_BF16 = 0,   /* bf16 operands, fp32 accumulate (tcgen05 kind::f16)            */
-  BG_GEMM_TF32 = 1    /* fp32 operands read as tf32, fp32 accumulate (kind::tf32);
-                         with hi/lo split operands this is the "fp32-GEMM" (3xTF32) mode */
-} bg_gemm_mode;
 
 int bg_abi_version(void);
 const char* bg_last_error(void);
@@ -107,7 +100,7 @@ int bg_encoder_front(const float* x, int64_t n_nodes, int32_t n_features,
 /* ------------------------------------------------------------------ K2: neighbourhood aggregation
  * Replaces `x[src]` gather + `scatter_add_` + divide inside SAGEConv.propagate:
  *    out[i] = reduce_{e: key(e)=i} x[col(e)]     mean: sum / max(deg,1); max: 0 if deg = 0
- * x, out: [N,512] of `dtype` (bf16 or f32), accumulation in fp32 in CSR (stable) order.
+ * x, out: [N,512] of `dtype` (bf16, f16 or f32), accumulation in fp32 in CSR (stable) order.
  * Big rows (info[1] of bg_csr_build, read back by the host) are split across CTAs;
  * workspace from bg_aggregate_workspace_bytes(n_big). */
 int bg_aggregate_workspace_bytes(int32_t n_big, size_t* bytes_host);
@@ -126,8 +119,11 @@ int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t n_nodes,
  * Epilogue order (each step optional):
  *    v = acc + bias;  v /= max(||v||_2, 1e-12);  v = v*bn_scale + bn_shift;
  *    v = max(v, 0);   v += residual[m, :]
- * mode BG_GEMM_BF16: A, B bf16, k_s % 64 == 0.  BG_GEMM_TF32: A, B f32, k_s % 32 == 0.
- * out/residual dtype = out_dtype.  All base pointers 16-byte aligned, ld* such that
+ * Operand formats: a_dtype / b_dtype in {BG_BF16, BG_F16} (tcgen05 kind::f16; the two may
+ * differ, e.g. bf16 activations x fp16 weights; k_s % 64 == 0) or both BG_F32 (read as
+ * tf32, kind::tf32; k_s % 32 == 0 -- with hi/lo split operands from bg_split_tf32 this
+ * is the 3xTF32 "fp32-GEMM" mode).  fp32 accumulation in TMEM always.
+ * out/residual dtype = out_dtype (any bg_dtype).  All base pointers 16-byte aligned, ld* such that
  * rows are 16-byte aligned.  cta_group: 1 or 2 (2 = tcgen05 cta_group::2 CTA pairs). */
 #define BG_MAX_GEMM_SEGMENTS 6
 typedef struct bg_gemm_segment {
@@ -146,9 +142,9 @@ typedef struct bg_epilogue {
   int32_t relu;
 } bg_epilogue;
 
-int bg_gemm512(const bg_gemm_segment* segments_host, int32_t n_segments, int64_t m, int mode,
-               const bg_epilogue* epilogue_host, void* out, int out_dtype, int64_t ldo,
-               int cta_group, void* stream);
+int bg_gemm512(const bg_gemm_segment* segments_host, int32_t n_segments, int64_t m,
+               int a_dtype, int b_dtype, const bg_epilogue* epilogue_host,
+               void* out, int out_dtype, int64_t ldo, int cta_group, void* stream);
 
 /* ------------------------------------------------------------------ K4: mean pool + regression head
  * Replaces `global_mean_pool(x, batch)` + `decoder(pooled).squeeze()`
@@ -165,8 +161,8 @@ int bg_pool_head(const void* x, int dtype, int64_t n_nodes, const int32_t* graph
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ helpers
- * fp32 -> bf16 (round to nearest even) cast of a contiguous buffer (weight packing). */
-int bg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+ * fp32 -> bf16 / f16 (round to nearest even) cast of a contiguous buffer (weight packing). */
+int bg_cast_f32(const float* src, void* dst, int dst_dtype, int64_t n, void* stream);
 /* hi/lo split for the 3xTF32 "fp32-GEMM" mode: hi = src with the low 13 mantissa bits
  * cleared (exactly representable in tf32), lo = src - hi. */
 int bg_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream);

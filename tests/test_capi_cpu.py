@@ -42,7 +42,7 @@ def test_size_queries_and_argument_errors_without_gpu(lib):
     assert e.value.status == -1 and "bad argument" in str(e.value)
     # bad enum / null pointers are rejected before any CUDA call
     with pytest.raises(capi.BuckGNNError):
-        capi.gemm512([], 128, capi.BG_GEMM_BF16, 0, capi.BG_BF16, 512, None)
+        capi.gemm512([], 128, capi.BG_BF16, capi.BG_BF16, 0, capi.BG_BF16, 512, None)
     with pytest.raises(capi.BuckGNNError):
         capi.csr_build(None, 10, 10, 7, None, None, None, None, None, None, 0, None)
 

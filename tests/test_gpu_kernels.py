@@ -91,14 +91,15 @@ def test_encoder_front_matches_fp32(n, f):
     capi.encoder_front(xd.data_ptr(), n, f, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
                        out.data_ptr(), capi.BG_F32, _stream())
     torch.testing.assert_close(out.cpu(), want, rtol=1e-5, atol=1e-5)
-    outb = torch.empty(n, 128, device=DEV, dtype=torch.bfloat16)
-    capi.encoder_front(xd.data_ptr(), n, f, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
-                       outb.data_ptr(), capi.BG_BF16, _stream())
-    torch.testing.assert_close(outb.cpu().float(), want, rtol=8e-3, atol=1e-5)   # one bf16 rounding
+    for code, dt, rtol in ((capi.BG_BF16, torch.bfloat16, 8e-3), (capi.BG_F16, torch.float16, 1e-3)):
+        outb = torch.empty(n, 128, device=DEV, dtype=dt)
+        capi.encoder_front(xd.data_ptr(), n, f, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                           outb.data_ptr(), code, _stream())
+        torch.testing.assert_close(outb.cpu().float(), want, rtol=rtol, atol=1e-5)   # one 16-bit rounding
 
 
 # ----------------------------------------------------------------------------- K2
-@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
 @pytest.mark.parametrize("aggr", ["mean", "sum", "max"])
 def test_aggregate_matches_oracle(aggr, precision):
     torch.manual_seed(1)
@@ -107,8 +108,7 @@ def test_aggregate_matches_oracle(aggr, precision):
     ei = torch.cat([b.edge_index, torch.tensor([[5, 5], [9, 9]])], 1)     # duplicate edge
     ei = ei[:, ei[1] != 3]                                                  # node 3 isolated
     x = torch.randn(n, 512)
-    if precision == "bf16":
-        x = x.bfloat16().float()
+    x = x.to(engine._TORCH[engine.PRECISION_FORMATS[precision][0]]).float()
     want = O.aggregate(x.double(), ei, aggr).float()
     idx = build_graph_index(ei.to(DEV), None, n)
     assert idx.n_big == 3
@@ -118,6 +118,8 @@ def test_aggregate_matches_oracle(aggr, precision):
     got = oa.data.float().cpu()
     if precision == "bf16":
         torch.testing.assert_close(got, want, rtol=8e-3, atol=1e-6 if aggr != "sum" else 2e-2)
+    elif precision == "fp16":
+        torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-6 if aggr != "sum" else 3e-3)
     else:
         torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
     if aggr == "max":
@@ -128,9 +130,10 @@ def test_aggregate_matches_oracle(aggr, precision):
 def _gemm_case(m, precision, cta_group, full_epilogue, seed=0):
     g = torch.Generator().manual_seed(seed)
     ks = [512, 512] if full_epilogue else [128]
-    dt = torch.bfloat16 if precision == "bf16" else torch.float32
-    As = [(torch.randn(m, k, generator=g) / k ** 0.5).to(dt) for k in ks]
-    Bs = [(torch.randn(512, k, generator=g)).to(dt) for k in ks]
+    a_dt, b_dt = (engine._TORCH[c] for c in engine.PRECISION_FORMATS[precision])
+    dt = a_dt
+    As = [(torch.randn(m, k, generator=g) / k ** 0.5).to(a_dt) for k in ks]
+    Bs = [(torch.randn(512, k, generator=g)).to(b_dt) for k in ks]
     bias = torch.randn(512, generator=g) * 0.1
     acc = sum(a.double() @ b.double().T for a, b in zip(As, Bs)) + bias.double()
     if full_epilogue:
@@ -153,21 +156,24 @@ def _gemm_case(m, precision, cta_group, full_epilogue, seed=0):
     return out.data.float().cpu(), want.float()
 
 
+_TOL16 = {"bf16": dict(rtol=1e-2, atol=2e-2), "mixed": dict(rtol=1e-2, atol=2e-2), "fp16": dict(rtol=2e-3, atol=3e-3)}
+
+
 @pytest.mark.parametrize("cta_group", [1, 2])
-@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("precision", ["bf16", "mixed", "fp16", "tf32"])
 @pytest.mark.parametrize("m", [128, 300, 20000])
 def test_gemm_plain_bias(m, precision, cta_group):
     got, want = _gemm_case(m, precision, cta_group, full_epilogue=False)
-    tol = dict(rtol=1e-2, atol=2e-2) if precision == "bf16" else dict(rtol=2e-3, atol=2e-3)
+    tol = _TOL16.get(precision, dict(rtol=2e-3, atol=2e-3))
     torch.testing.assert_close(got, want, **tol)
 
 
 @pytest.mark.parametrize("cta_group", [1, 2])
-@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("precision", ["bf16", "mixed", "fp16", "tf32"])
 @pytest.mark.parametrize("m", [77, 40000])
 def test_gemm_sage_epilogue(m, precision, cta_group):
     got, want = _gemm_case(m, precision, cta_group, full_epilogue=True, seed=3)
-    tol = dict(rtol=1e-2, atol=2e-2) if precision == "bf16" else dict(rtol=2e-3, atol=3e-3)
+    tol = _TOL16.get(precision, dict(rtol=2e-3, atol=3e-3))
     torch.testing.assert_close(got, want, **tol)
 
 
@@ -188,14 +194,13 @@ def test_gemm_3xtf32_is_fp32_accurate():
 
 
 # ----------------------------------------------------------------------------- K4
-@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
 def test_pool_head_matches_oracle(precision):
     torch.manual_seed(2)
     b = make_batch(6, nx=11, ny=9)
     n = b.num_nodes
     x = torch.randn(n, 512)
-    if precision == "bf16":
-        x = x.bfloat16().float()
+    x = x.to(engine._TORCH[engine.PRECISION_FORMATS[precision][0]]).float()
     dec = torch.nn.Sequential(torch.nn.Linear(512, 128), torch.nn.ReLU(), torch.nn.Linear(128, 64),
                               torch.nn.ReLU(), torch.nn.Linear(64, 1))
     pooled_want = O.global_mean_pool(x, b.batch)

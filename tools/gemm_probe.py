@@ -9,7 +9,7 @@ DEV = "cuda:0"
 
 
 def run(m, k, precision, cg, pattern):
-    dt = torch.bfloat16 if precision == "bf16" else torch.float32
+    a_dt, b_dt = (engine._TORCH[c] for c in engine.PRECISION_FORMATS[precision])
     g = torch.Generator().manual_seed(0)
     if pattern == "ones":
         a = torch.ones(m, k); b = torch.ones(512, k)
@@ -21,7 +21,7 @@ def run(m, k, precision, cg, pattern):
         a = torch.zeros(m, k); a[torch.arange(m), torch.arange(m) % k] = 1; b = torch.randn(512, k, generator=g)
     else:
         a = torch.randn(m, k, generator=g); b = torch.randn(512, k, generator=g)
-    a, b = a.to(dt), b.to(dt)
+    a, b = a.to(a_dt), b.to(b_dt)
     want = (a.double() @ b.double().T).float()
     ad, bd = a.to(DEV).contiguous(), b.to(DEV).contiguous()
     out = Activation(m, 512, precision, DEV)
@@ -49,8 +49,8 @@ if __name__ == "__main__":
     cgs = [int(c) for c in (sys.argv[1] if len(sys.argv) > 1 else "1,2").split(",")]
     ok = True
     for cg in cgs:
-        for precision in ("bf16", "tf32"):
-            k = 128 if precision == "bf16" else 64
+        for precision in ("bf16", "mixed", "fp16", "tf32"):
+            k = 64 if precision == "tf32" else 128
             for pattern in ("ones", "rowid", "colid", "kdelta", "rand"):
                 ok &= run(256, k, precision, cg, pattern)
             ok &= run(1000, 512, precision, cg, "rand")

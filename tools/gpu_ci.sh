@@ -13,3 +13,4 @@ run t_gemm python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "gemm"
 run t_pool python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "pool"
 run t_fwd python -m pytest tests/test_gpu_forward.py -q -m gpu
 run smoke python __graft_entry__.py --smoke
+run bench python bench.py --steps 10 --warmup 3
