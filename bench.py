@@ -249,7 +249,7 @@ def run_b200(args):
         line = {
             "metric": "graphs/sec", "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"mixed": "bf16", "fp16": "f16", "bf16": "bf16", "tf32": "tf32",
+            "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "tf32": "tf32",
                                            "fp32": "f32"}[args.precision],
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "graphs_per_gpu": G, "nodes_per_gpu": N, "edges_per_gpu": E,
@@ -278,7 +278,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="mixed")
+    ap.add_argument("--precision", default="fp16")
     ap.add_argument("--cta-group", type=int, default=2)
     ap.add_argument("--graphs", type=int, default=GRAPHS_PER_RANK)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -263,8 +263,8 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
   if (m < 0 || m >= 0x7fffffffLL) return fail(BG_ERR_INVALID, "bg_gemm512: bad m");
   if (m == 0) return BG_OK;
   const int a_fmt = umma_format_of(a_dtype), b_fmt = umma_format_of(b_dtype);
-  if (a_fmt < 0 || b_fmt < 0 || ((a_fmt == 2) != (b_fmt == 2)))
-    return fail(BG_ERR_INVALID, "bg_gemm512: operand dtypes must be both 16-bit (bf16/f16) or both f32");
+  if (a_fmt < 0 || b_fmt < 0 || a_fmt != b_fmt)
+    return fail(BG_ERR_INVALID, "bg_gemm512: a_dtype and b_dtype must be the same (bf16, f16 or f32)");
   if (umma_format_of(out_dtype) < 0) return fail(BG_ERR_INVALID, "bg_gemm512: bad out_dtype");
   if (cta_group != 1 && cta_group != 2) return fail(BG_ERR_INVALID, "bg_gemm512: cta_group must be 1 or 2");
   const bool tf32 = a_fmt == 2;

@@ -23,22 +23,28 @@ import torch
 from . import capi
 
 # precision mode -> (activation storage, weight storage) of the tensor-core GEMMs
-#   mixed : bf16 activations (fp32-like range) x fp16 weights (11-bit significand).  The
-#           weight rounding is the error that does NOT average out over nodes, so this is
-#           ~8x more accurate than bf16 x bf16 at the same cost; the default.
-#   fp16  : fp16 x fp16 (most accurate 16-bit mode; activations must stay < 65504)
-#   bf16  : bf16 x bf16
-#   tf32  : fp32 storage, operands read as tf32
+#   fp16  : fp16 x fp16, fp32 accumulate.  11-bit significands: the rounding of the SHARED
+#           weights (the error that does not average out over nodes) is 8x smaller than
+#           with bf16, at the same cost.  Activations must stay below 65504, which the
+#           L2-normalise + BN of every layer guarantees for mean / max aggregation.
+#   bf16  : bf16 x bf16 (fp32-like range, ~1e-3 systematic error on the prediction)
+#   tf32  : fp32 storage, operands read as tf32 (default for sum/add aggregation, whose
+#           hub rows sum thousands of terms and can leave the fp16 range)
 #   fp32  : fp32 storage, hi/lo split operands, 3 tf32 products per term ("fp32-GEMM mode")
+# (tcgen05 kind::f16 rejects A = bf16 with B = fp16 -- illegal instruction on sm_100a --
+#  so there is no mixed mode.)
 _TORCH = {capi.BG_BF16: torch.bfloat16, capi.BG_F16: torch.float16, capi.BG_F32: torch.float32}
 PRECISION_FORMATS = {
-    "mixed": (capi.BG_BF16, capi.BG_F16),
     "fp16": (capi.BG_F16, capi.BG_F16),
     "bf16": (capi.BG_BF16, capi.BG_BF16),
     "tf32": (capi.BG_F32, capi.BG_F32),
     "fp32": (capi.BG_F32, capi.BG_F32),
 }
 PRECISIONS = tuple(PRECISION_FORMATS)
+
+
+def default_precision(aggr: str) -> str:
+    return "fp16" if aggr in ("mean", "max") else "tf32"
 
 
 def _stream() -> int:

@@ -13,9 +13,10 @@ Mirrors `Models/BuckGNN.py` of the reference:
 The forward never touches PyG / torch_scatter / ATen math: it is the kernel sequence
 in `engine.py`.  CPU tensors raise -- there is no fallback path.
 
-Extra, non-reference keyword: `precision` in {"mixed", "fp16", "bf16", "tf32", "fp32"}
+Extra, non-reference keyword: `precision` in {"auto", "fp16", "bf16", "tf32", "fp32"}
 selects how the tensor-core GEMMs read their operands (engine.PRECISION_FORMATS; fp32 =
-3xTF32 split, the "fp32-GEMM mode").
+3xTF32 split, the "fp32-GEMM mode"; "auto" = fp16 for mean/max aggregation, tf32 for
+sum/add whose hub rows can leave the fp16 range).
 """
 from __future__ import annotations
 
@@ -90,11 +91,15 @@ class BuckGNN(nn.Module):
     def __init__(self, num_node_features, num_edge_features, hidden_channels=128,
                  num_layers=6, pooling_layer="mean", prediction_type="buckling",
                  use_z_coord=False, use_rotations=False, dropout_rate=0.1,
-                 model_name="GraphSAGE_MLP", *, precision: str = "mixed", cta_group: int = 2,
+                 model_name="GraphSAGE_MLP", *, precision: str = "auto", cta_group: int = 2,
                  cache_index: bool = False):
         super().__init__()
+        if precision == "auto":
+            aggr = _SAGE_LISTS[model_name][1] if model_name in _SAGE_LISTS else (
+                "add" if model_name == "GraphSage_addAggr_Shared" else "mean")
+            precision = engine.default_precision(aggr)
         if precision not in engine.PRECISIONS:
-            raise ValueError(f"precision must be one of {engine.PRECISIONS}")
+            raise ValueError(f"precision must be \"auto\" or one of {engine.PRECISIONS}")
         self.hidden_channels = hidden_channels
         self.prediction_type = prediction_type
         self.pooling_layer = pooling_layer

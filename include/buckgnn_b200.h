@@ -119,8 +119,8 @@ int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t n_nodes,
  * Epilogue order (each step optional):
  *    v = acc + bias;  v /= max(||v||_2, 1e-12);  v = v*bn_scale + bn_shift;
  *    v = max(v, 0);   v += residual[m, :]
- * Operand formats: a_dtype / b_dtype in {BG_BF16, BG_F16} (tcgen05 kind::f16; the two may
- * differ, e.g. bf16 activations x fp16 weights; k_s % 64 == 0) or both BG_F32 (read as
+ * Operand formats: a_dtype == b_dtype in {BG_BF16, BG_F16} (tcgen05 kind::f16, k_s % 64 == 0;
+ * the hardware rejects bf16 x fp16 mixes) or both BG_F32 (read as
  * tf32, kind::tf32; k_s % 32 == 0 -- with hi/lo split operands from bg_split_tf32 this
  * is the 3xTF32 "fp32-GEMM" mode).  fp32 accumulation in TMEM always.
  * out/residual dtype = out_dtype (any bg_dtype).  All base pointers 16-byte aligned, ld* such that

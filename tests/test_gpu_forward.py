@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 # bf16 x bf16 is kept as a mode but is NOT held to 1e-3: rounding the shared weights to 8
 # bits gives a systematic ~1e-3 shift that does not average out over nodes.
-RTOL = {"mixed": 1e-3, "fp16": 1e-3, "bf16": 3e-3, "tf32": 1e-3, "fp32": 1e-4}
+RTOL = {"fp16": 1e-3, "bf16": 3e-3, "tf32": 1e-3, "fp32": 1e-4}
 
 
 def _pair(model_name, precision, layers=6, seed=0, **kw):
@@ -41,7 +41,7 @@ def _assert_rel(got, want, rtol):
     assert rel.max().item() < rtol, f"max rel err {rel.max().item():.3e} >= {rtol} (got {got}, want {want})"
 
 
-@pytest.mark.parametrize("precision", ["mixed", "fp16", "bf16", "tf32", "fp32"])
+@pytest.mark.parametrize("precision", ["fp16", "bf16", "tf32", "fp32"])
 def test_graphsage_mean_6x512_matches_oracle(precision):
     ref, ours = _pair("GraphSage_meanAggr", precision)
     got, want = _run(ref, ours, make_batch(4, nx=24, ny=20))
@@ -51,7 +51,7 @@ def test_graphsage_mean_6x512_matches_oracle(precision):
 
 @pytest.mark.parametrize("cta_group", [1, 2])
 def test_cta_group_variants_agree(cta_group):
-    ref, ours = _pair("GraphSage_meanAggr", "mixed", cta_group=cta_group)
+    ref, ours = _pair("GraphSage_meanAggr", "fp16", cta_group=cta_group)
     got, want = _run(ref, ours, make_batch(3, nx=16, ny=16))
     _assert_rel(got, want, 1e-3)
 
@@ -75,7 +75,7 @@ def test_single_graph_batch_none_gives_0dim():
 
 
 def test_inputs_not_mutated_and_deterministic():
-    ref, ours = _pair("GraphSage_meanAggr", "mixed", layers=3)
+    ref, ours = _pair("GraphSage_meanAggr", "fp16", layers=3)
     b = make_batch(3, nx=10, ny=9).to(DEV)
     snap = [t.clone() for t in (b.x, b.edge_index, b.edge_attr, b.batch)]
     with torch.no_grad():

@@ -49,7 +49,7 @@ if __name__ == "__main__":
     cgs = [int(c) for c in (sys.argv[1] if len(sys.argv) > 1 else "1,2").split(",")]
     ok = True
     for cg in cgs:
-        for precision in ("bf16", "mixed", "fp16", "tf32"):
+        for precision in ("bf16", "fp16", "tf32"):
             k = 64 if precision == "tf32" else 128
             for pattern in ("ones", "rowid", "colid", "kdelta", "rand"):
                 ok &= run(256, k, precision, cg, pattern)
