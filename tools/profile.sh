@@ -1,0 +1,11 @@
+#!/bin/bash
+# ncu evidence for the bench command (run under gpurun, 1 GPU). Outputs under gpurun_out/.
+mkdir -p gpurun_out
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+$CMD > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+echo "launch list exit $?"
+$CMD > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"k_gemm512|k_aggregate_rows|k_encoder_front" -s 12 -c 6 -o gpurun_out/prof_top -f $CMD > gpurun_out/ncu_full.log 2>&1
+echo "full capture exit $?"
+tail -3 gpurun_out/ncu_full.log
