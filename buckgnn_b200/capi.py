@@ -43,7 +43,7 @@ class GemmSegment(C.Structure):
 
 
 class Epilogue(C.Structure):
-    _fields_ = [("bias", C.c_void_p), ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
+    _fields_ = [("bias_host", C.c_void_p), ("bn_scale_host", C.c_void_p), ("bn_shift_host", C.c_void_p),
                 ("residual", C.c_void_p), ("ldr", C.c_int64), ("normalize", C.c_int32), ("relu", C.c_int32)]
 
 
@@ -163,7 +163,7 @@ def sage_aggregate(x, out, dtype, n_nodes, rowptr, col, big_rows, n_big, aggr, w
 
 def gemm512(segments, m, a_dtype, b_dtype, out, out_dtype, ldo, stream, *, bias=None, bn_scale=None,
             bn_shift=None, residual=None, ldr=0, normalize=False, relu=False, cta_group=2):
-    """segments: list of (a_ptr, lda, b_ptr, ldb, k)."""
+    """segments: list of (a_ptr, lda, b_ptr, ldb, k); bias / bn_scale / bn_shift are HOST pointers."""
     n = len(segments)
     arr = (GemmSegment * n)(*[GemmSegment(a, lda, b, ldb, k, 0) for (a, lda, b, ldb, k) in segments])
     epi = Epilogue(bias, bn_scale, bn_shift, residual, ldr, int(bool(normalize)), int(bool(relu)))

@@ -5,7 +5,8 @@
 // HBM/L2-bandwidth bound: every source row is read once from HBM (re-reads by the
 // ~6 rows that share it hit L2/L1), the aggregate row is written once.
 //
-//  * normal rows: one warp per row; a lane owns 16 of the 512 columns and reads
+//  * normal rows: one warp per row, each SM walking a contiguous band of rows so the
+//    mesh's neighbour reuse is served by L1; a lane owns 16 of the 512 columns and reads
 //    them with 128-bit loads, so one warp-wide load instruction covers 512
 //    contiguous bytes of a source row; neighbour indices are fetched 32 at a time
 //    and broadcast by shuffle; 4 neighbours are in flight per lane.  fp32
@@ -21,7 +22,9 @@
 namespace bg {
 
 constexpr int kHubSlices = 16;
-constexpr int kAggWarpsPerBlock = 8;
+constexpr int kAggWarpsPerBlock = 8;       // hub kernel
+// row kernel: one CTA per SM; 32 warps for 16-bit rows (64 regs/thread), 16 warps for fp32 rows
+template <typename T> constexpr int agg_row_threads() { return sizeof(T) == 2 ? 1024 : 512; }
 
 template <int kAggr> BG_DEVINL float agg_init() { return kAggr == BG_AGGR_MAX ? -INFINITY : 0.f; }
 template <int kAggr> BG_DEVINL float agg_op(float a, float b) {
@@ -129,14 +132,19 @@ template <int kAggr> BG_DEVINL void agg_finalize(float (&acc)[16], int32_t deg) 
   }
 }
 
+// One persistent 32-warp CTA per SM owns a CONTIGUOUS band of rows and walks it in order,
+// 32 rows at a time.  Mesh neighbours of row i are i+-1 and i+-nx, so the band's reuse
+// window (~2*nx+32 rows of 1 KB) stays in the SM's L1: a source row is fetched from L2
+// once and hit ~3 more times, instead of every gather going to L2.
 template <typename T, int kAggr>
-__global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
+__global__ void __launch_bounds__(agg_row_threads<T>(), 1)
 k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N,
                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t)blockIdx.x * kAggWarpsPerBlock + (threadIdx.x >> 5);
-  const int64_t n_warps = (int64_t)gridDim.x * kAggWarpsPerBlock;
-  for (int64_t r = warp; r < N; r += n_warps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t band = (N + gridDim.x - 1) / gridDim.x;
+  const int64_t r_beg = (int64_t)blockIdx.x * band;
+  const int64_t r_end = min(N, r_beg + band);
+  for (int64_t r = r_beg + warp; r < r_end; r += agg_row_threads<T>() / 32) {
     const int32_t beg = rowptr[r], end = rowptr[r + 1];
     if (end - beg > kBigRowThreshold) continue;             // hub rows: k_aggregate_hubs
     float acc[16];

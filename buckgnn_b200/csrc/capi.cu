@@ -76,11 +76,11 @@ template <typename T>
 static int aggregate_dispatch(const T* x, T* out, int64_t N, const int32_t* rowptr, const int32_t* col,
                               const int32_t* big_rows, int32_t n_big, int aggr, float* partial, int32_t* ticket,
                               cudaStream_t stream) {
-  const unsigned grid = (unsigned)min64(ceil_div64(N, kAggWarpsPerBlock), (int64_t)sm_count() * 32);
+  const unsigned grid = (unsigned)min64(ceil_div64(N, agg_row_threads<T>() / 32), (int64_t)sm_count());
   const unsigned hub_grid = (unsigned)n_big * kHubSlices;
 #define BG_AGG_CASE(A)                                                                                       \
   case A:                                                                                                    \
-    k_aggregate_rows<T, A><<<grid, kAggWarpsPerBlock * 32, 0, stream>>>(x, out, N, rowptr, col);             \
+    k_aggregate_rows<T, A><<<grid, agg_row_threads<T>(), 0, stream>>>(x, out, N, rowptr, col);                     \
     if (n_big > 0)                                                                                           \
       k_aggregate_hubs<T, A><<<hub_grid, kAggWarpsPerBlock * 32, 0, stream>>>(x, out, rowptr, col, big_rows, \
                                                                               n_big, partial, ticket);      \
@@ -266,7 +266,7 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
   if (a_fmt < 0 || b_fmt < 0 || a_fmt != b_fmt)
     return fail(BG_ERR_INVALID, "bg_gemm512: a_dtype and b_dtype must be the same (bf16, f16 or f32)");
   if (umma_format_of(out_dtype) < 0) return fail(BG_ERR_INVALID, "bg_gemm512: bad out_dtype");
-  if (cta_group != 1 && cta_group != 2) return fail(BG_ERR_INVALID, "bg_gemm512: cta_group must be 1 or 2");
+  if (cta_group != 2) return fail(BG_ERR_UNSUPPORTED, "bg_gemm512: only cta_group = 2 is built");
   const bool tf32 = a_fmt == 2;
   const int esz = tf32 ? 4 : 2, osz = out_dtype == BG_F32 ? 4 : 2;
   const int kblk = kStageKBytes / esz;
@@ -288,19 +288,30 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
   p.a_fmt = (uint32_t)a_fmt; p.b_fmt = (uint32_t)b_fmt;
   p.n_tiles = (int32_t)ceil_div64(m, kTileM * cta_group);
   p.m = m;
+  for (int i = 0; i < kHidden; ++i) { p.bias[i] = 0.f; p.scale[i] = 1.f; p.shift[i] = 0.f; }
+  const uint32_t o_fmt = (uint32_t)umma_format_of(out_dtype);
   if (epi) {
     if (epi->residual && (!aligned16(epi->residual) || (epi->ldr * osz) % 16 != 0 || epi->ldr < kHidden))
       return fail(BG_ERR_INVALID, "bg_gemm512: bad residual/ldr");
-    if (epi->bn_scale && !epi->bn_shift) return fail(BG_ERR_INVALID, "bg_gemm512: bn_scale without bn_shift");
-    p.bias = epi->bias; p.bn_scale = epi->bn_scale; p.bn_shift = epi->bn_shift;
-    p.residual = epi->residual; p.ldr = epi->ldr; p.normalize = epi->normalize; p.relu = epi->relu;
+    if (epi->bn_scale_host && !epi->bn_shift_host) return fail(BG_ERR_INVALID, "bg_gemm512: bn_scale without bn_shift");
+    if (epi->bias_host) memcpy(p.bias, epi->bias_host, sizeof(float) * kHidden);
+    if (epi->bn_scale_host) {
+      memcpy(p.scale, epi->bn_scale_host, sizeof(float) * kHidden);
+      memcpy(p.shift, epi->bn_shift_host, sizeof(float) * kHidden);
+    }
+    p.normalize = epi->normalize; p.relu = epi->relu;
+    if (epi->residual) {
+      p.has_res = 1;
+      if (make_operand_map(&p.res_map, epi->residual, m, kHidden, epi->ldr, o_fmt) != BG_OK)
+        return fail(BG_ERR_CUDA, "bg_gemm512: cuTensorMapEncodeTiled (residual) failed");
+    }
   }
-  p.out = out; p.ldo = ldo;
+  if (make_operand_map(&p.out_map, out, m, kHidden, ldo, o_fmt) != BG_OK)
+    return fail(BG_ERR_CUDA, "bg_gemm512: cuTensorMapEncodeTiled (out) failed");
 #define BG_GEMM_OUT(CG, TF)                                                              \
   (out_dtype == BG_BF16 ? launch_gemm512<CG, TF, __nv_bfloat16>(p, stream)               \
    : out_dtype == BG_F16 ? launch_gemm512<CG, TF, __half>(p, stream)                     \
                          : launch_gemm512<CG, TF, float>(p, stream))
-  if (cta_group == 1) return tf32 ? BG_GEMM_OUT(1, true) : BG_GEMM_OUT(1, false);
   return tf32 ? BG_GEMM_OUT(2, true) : BG_GEMM_OUT(2, false);
 #undef BG_GEMM_OUT
 }

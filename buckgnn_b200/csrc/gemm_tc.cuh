@@ -8,17 +8,27 @@
 // reference layer loop (Models/BuckGNN.py:449-457 + PyG SAGEConv.forward).  The same
 // kernel runs the encoder's 128 -> 512 Linear (:73) as a one-segment GEMM.
 //
-// Structure (one persistent CTA per SM, or one CTA pair per SM pair with cta_group::2):
-//   warp 0    TMA producer: A tile 128 x 128 B and the B (weight) rows of this CTA
-//             into a ring of 128B-swizzled K-major stages
-//   warp 1    allocates TMEM; one elected lane issues tcgen05.mma (M = 128*cg, N = 256,
-//             two N halves -> all 512 output columns of a row tile live in TMEM)
-//   warps 2-5 epilogue: one TMEM lane (= output row) per thread; pass 1 sums squares
-//             of the whole 512-wide row (L2-normalize needs the full row, which is why
-//             the tile spans all 512 columns = all 512 TMEM columns), pass 2 applies
-//             bias / normalize / BN / ReLU / skip and stores.
-// Tensor-core bound: 2*M*K*512 flops per tile row block; algorithmic bytes per row
-// = (K_total + 512 [+512 residual]) * elem_size.
+// One persistent CTA pair per SM pair (tcgen05 cta_group::2), 12 warps per CTA:
+//   warp 0     TMA producer: this CTA's 128 activation rows x 128 B of K and its 256 of
+//              the 512 weight rows into a ring of 128B-swizzled K-major stages
+//   warp 1     allocates TMEM; in the leader CTA one elected lane issues tcgen05.mma
+//              (M = 256 over the pair, N = 256, two N halves -> the 512 fp32 columns of
+//              TMEM hold one full output row per lane: L2-normalize needs the whole row)
+//   warps 2-3  idle (register donors)
+//   warps 4-11 epilogue, two groups of 4 warps = two 256-column halves; one TMEM lane
+//              (= output row) per thread.
+//              16-bit output: ONE pass over TMEM adds the bias, accumulates the row's sum
+//              of squares and stashes the row as packed 16-bit pairs in 128 registers;
+//              TMEM is released right after, so the next tile's MMAs overlap pass 2, which
+//              applies normalize / BN / ReLU / skip from the stash.
+//              fp32 output (tf32 / 3xTF32 modes): two passes over TMEM (no stash).
+//              Either way the result goes through 128B-swizzled staging tiles in shared
+//              memory and leaves with TMA stores; the skip-connection rows arrive the
+//              same way (TMA load into the staging tile, added in place) -- no
+//              row-strided global accesses.
+// setmaxnreg moves registers from warps 0-3 (40) to the epilogue warps (232).
+// Tensor-core bound: 2*K*512 flops per row; algorithmic bytes per row
+// = (K_total + 512 [+512 skip]) * elem_size.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -28,55 +38,75 @@ namespace bg {
 constexpr int kTileM = 128;                       // rows per CTA
 constexpr int kStageKBytes = 128;                 // one 128B swizzle row of K per stage
 constexpr int kATileBytes = kTileM * kStageKBytes;        // 16 KB
-constexpr int kGemmThreads = 192;
-constexpr int kEpiParamBytes = 3 * kHidden * 4;   // bias, bn_scale, bn_shift staged in smem
+constexpr int kGemmThreads = 384;                 // 12 warps
+constexpr int kEpiFirstWarp = 4;
+constexpr int kEpiSlotBytes = kTileM * 128;       // staging tile: 128 rows x 128 B
+constexpr int kEpiSlots = 4;                      // 2 per column-half group
 
 template <int kCg> struct GemmCfg {
   static constexpr int kBRows = kHidden / kCg;                  // weight rows held by one CTA
   static constexpr int kBTileBytes = kBRows * kStageKBytes;     // 64 KB / 32 KB
   static constexpr int kStageBytes = kATileBytes + kBTileBytes; // 80 KB / 48 KB
-  static constexpr int kStages = (kCg == 1) ? 2 : 4;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiParamBytes + 256;
+  static constexpr int kStages = (kCg == 1) ? 2 : 3;
+  static constexpr int kMiscBytes = 2048 + 256;                 // row sum-of-squares exchange + barriers
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiSlots * kEpiSlotBytes + kMiscBytes;
 };
 
 struct alignas(64) GemmSeg { CUtensorMap a; CUtensorMap b; };
 
 struct alignas(64) GemmParams {
   GemmSeg seg[BG_MAX_GEMM_SEGMENTS];
+  CUtensorMap out_map;              // [M, 512] out, box 128 rows x 128 B, 128B swizzle
+  CUtensorMap res_map;              // same geometry over the residual (valid iff has_res)
   int32_t kblocks[BG_MAX_GEMM_SEGMENTS];
   int32_t n_seg;
   int32_t k_elems_per_block;        // 64 (16-bit operands) or 32 (tf32)
   uint32_t a_fmt, b_fmt;            // UMMA operand formats: 0 f16, 1 bf16, 2 tf32
   int32_t n_tiles;                  // row tiles of 128*cg rows
-  int32_t normalize, relu;
+  int32_t normalize, relu, has_res;
   int64_t m;
-  const float* bias;
-  const float* bn_scale;
-  const float* bn_shift;
-  const void* residual;
-  int64_t ldr;
-  void* out;
-  int64_t ldo;
+  float bias[kHidden];              // epilogue vectors by value -> constant bank, broadcast reads
+  float scale[kHidden];             // 1 when there is no BN
+  float shift[kHidden];             // 0 when there is no BN
 };
 
-enum : uint32_t { kTagEmpty = 1, kTagFull = 2, kTagTmemEmpty = 3, kTagTmemFull = 4 };
+enum : uint32_t { kTagEmpty = 1, kTagFull = 2, kTagTmemEmpty = 3, kTagTmemFull = 4, kTagRes = 5 };
+
+BG_DEVINL void named_bar_sync(uint32_t id, uint32_t threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+BG_DEVINL uint4 lds_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+BG_DEVINL void sts_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <int kRegs> BG_DEVINL void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> BG_DEVINL void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
 template <int kCg, bool kTf32, typename TOut>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm512(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<kCg>;
   constexpr int kStages = Cfg::kStages;
+  constexpr bool kOut16 = sizeof(TOut) == 2;
+  constexpr int kChunkCols = 128 / (int)sizeof(TOut);           // columns per 128-byte staging row: 64 / 32
+  constexpr int kChunks = 256 / kChunkCols;                     // staging chunks per 256-column group: 4 / 8
   extern __shared__ uint8_t gemm_smem_raw[];
   const uint32_t smem_base = (smem_u32(gemm_smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B wants 1024 B
   uint8_t* smem_gen = gemm_smem_raw + (smem_base - smem_u32(gemm_smem_raw));
   const uint32_t stages_u32 = smem_base;
-  float* epi_params = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes);
-  const uint32_t bars_u32 = stages_u32 + kStages * Cfg::kStageBytes + kEpiParamBytes;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + kEpiParamBytes + 192);
+  const uint32_t slots_u32 = stages_u32 + kStages * Cfg::kStageBytes;
+  float* ss_smem = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes + kEpiSlots * kEpiSlotBytes);
+  const uint32_t bars_u32 = slots_u32 + kEpiSlots * kEpiSlotBytes + 2048;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + kEpiSlots * kEpiSlotBytes + 2048 + 192);
   auto full_bar = [&](int s) { return bars_u32 + 8u * s; };
   auto empty_bar = [&](int s) { return bars_u32 + 8u * (kStages + s); };
   const uint32_t tmem_full_bar = bars_u32 + 8u * (2 * kStages);
   const uint32_t tmem_empty_bar = bars_u32 + 8u * (2 * kStages + 1);
+  auto res_bar = [&](int g, int s) { return bars_u32 + 8u * (2 * kStages + 2 + g * 2 + s); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,20 +115,18 @@ k_gemm512(const __grid_constant__ GemmParams p) {
   const int tile_stride = (kCg == 2) ? (gridDim.x >> 1) : gridDim.x;
 
   // ---- one-time setup
-  for (int i = threadIdx.x; i < kHidden; i += kGemmThreads) {
-    epi_params[i] = p.bias ? p.bias[i] : 0.f;
-    epi_params[kHidden + i] = p.bn_scale ? p.bn_scale[i] : 1.f;
-    epi_params[2 * kHidden + i] = p.bn_scale ? p.bn_shift[i] : 0.f;
-  }
   if (warp == 0 && elect_one()) {
     for (int s = 0; s < p.n_seg; ++s) { tma_prefetch_desc(&p.seg[s].a); tma_prefetch_desc(&p.seg[s].b); }
+    tma_prefetch_desc(&p.out_map);
+    if (p.has_res) tma_prefetch_desc(&p.res_map);
   }
   if (kCg == 2) cluster_sync();                // both CTAs resident before the paired TMEM alloc
   if (warp == 1) {
     if (elect_one()) {
       for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), kCg); mbar_init(empty_bar(s), 1); }
       mbar_init(tmem_full_bar, 1);
-      mbar_init(tmem_empty_bar, kCg * 128);
+      mbar_init(tmem_empty_bar, kCg * 256);
+      for (int i = 0; i < 4; ++i) mbar_init(res_bar(i >> 1, i & 1), 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -109,43 +137,44 @@ k_gemm512(const __grid_constant__ GemmParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  if (warp == 0) {
-    // ================================================================ TMA producer
-    if (elect_one()) {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = tile0; tile < p.n_tiles; tile += tile_stride) {
-        const int32_t row0 = tile * (kTileM * kCg) + (int32_t)rank * kTileM;
-        for (int s = 0; s < p.n_seg; ++s) {
-          const void* map_a = &p.seg[s].a;
-          const void* map_b = &p.seg[s].b;
-          for (int kb = 0; kb < p.kblocks[s]; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u, kTagEmpty);
-            const uint32_t sa = stages_u32 + stage * Cfg::kStageBytes;
-            const uint32_t sb = sa + kATileBytes;
-            const int32_t k0 = kb * p.k_elems_per_block;
-            if constexpr (kCg == 1) {
-              mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-              tma_load_2d(sa, map_a, full_bar(stage), k0, row0);
+  if (warp < kEpiFirstWarp) {
+    setmaxnreg_dec<40>();
+    if (warp == 0) {
+      // ================================================================ TMA producer
+      if (elect_one()) {
+        uint32_t stage = 0, phase = 0;
+        for (int tile = tile0; tile < p.n_tiles; tile += tile_stride) {
+          const int32_t row0 = tile * (kTileM * kCg) + (int32_t)rank * kTileM;
+          for (int s = 0; s < p.n_seg; ++s) {
+            const void* map_a = &p.seg[s].a;
+            const void* map_b = &p.seg[s].b;
+            for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u, kTagEmpty);
+              const uint32_t sa = stages_u32 + stage * Cfg::kStageBytes;
+              const uint32_t sb = sa + kATileBytes;
+              const int32_t k0 = kb * p.k_elems_per_block;
+              if constexpr (kCg == 1) {
+                mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                tma_load_2d(sa, map_a, full_bar(stage), k0, row0);
 #pragma unroll
-              for (int j = 0; j < Cfg::kBRows / 128; ++j)
-                tma_load_2d(sb + j * 16384, map_b, full_bar(stage), k0, j * 128);
-            } else {
-              if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-              else mbar_arrive_cluster(full_bar(stage), 0);
-              tma_load_2d_cg2(sa, map_a, full_bar(stage), k0, row0);
+                for (int j = 0; j < Cfg::kBRows / 128; ++j)
+                  tma_load_2d(sb + j * 16384, map_b, full_bar(stage), k0, j * 128);
+              } else {
+                if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+                else mbar_arrive_cluster(full_bar(stage), 0);
+                tma_load_2d_cg2(sa, map_a, full_bar(stage), k0, row0);
 #pragma unroll
-              for (int j = 0; j < Cfg::kBRows / 128; ++j)      // N half j: weight rows j*256 + rank*128
-                tma_load_2d_cg2(sb + j * 16384, map_b, full_bar(stage), k0, j * 256 + (int32_t)rank * 128);
+                for (int j = 0; j < Cfg::kBRows / 128; ++j)      // N half j: weight rows j*256 + rank*128
+                  tma_load_2d_cg2(sb + j * 16384, map_b, full_bar(stage), k0, j * 256 + (int32_t)rank * 128);
+              }
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ================================================================ MMA issuer (leader CTA)
-    if (rank == 0) {
+      __syncwarp();
+    } else if (warp == 1 && rank == 0) {
+      // ================================================================ MMA issuer (leader CTA)
       const uint32_t idesc = umma_idesc(p.a_fmt, p.b_fmt, kTileM * kCg, 256);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = tile0; tile < p.n_tiles; tile += tile_stride, ++it) {
@@ -178,90 +207,140 @@ k_gemm512(const __grid_constant__ GemmParams p) {
           }
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
-    // ================================================================ epilogue warps 2..5
+    // ================================================================ epilogue warps 4..11
+    setmaxnreg_inc<232>();
     const int q = warp & 3;                                     // TMEM lane quarter this warp may read
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float* sbias = epi_params;
-    const float* sscale = epi_params + kHidden;
-    const float* sshift = epi_params + 2 * kHidden;
-    const bool has_bn = p.bn_scale != nullptr;
-    uint32_t it = 0;
+    const int g = (warp - kEpiFirstWarp) >> 2;                  // column half: [g*256, g*256+256)
+    const int row = q * 32 + lane;                              // row within the CTA's 128-row tile
+    const int cb = g * 256;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cb;
+    const bool leader = (warp == kEpiFirstWarp + 4 * g) && (lane == 0);   // issues this group's TMA traffic
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t grp_bar = 2 + g;
+    uint32_t it = 0, seq = 0;                                   // tiles done; staging chunks done (this group)
     for (int tile = tile0; tile < p.n_tiles; tile += tile_stride, ++it) {
-      const int64_t m = (int64_t)tile * (kTileM * kCg) + rank * kTileM + q * 32 + lane;
-      const bool valid = m < p.m;
+      const int32_t row0 = tile * (kTileM * kCg) + (int32_t)rank * kTileM;
+      if (leader) {
+        tma_store_wait_read<0>();                               // previous tile's stores have left their slots
+        if (p.has_res) {
+          const uint32_t s0 = seq & 1u;
+          mbar_arrive_expect_tx(res_bar(g, s0), kEpiSlotBytes);
+          tma_load_2d(slots_u32 + (g * 2 + s0) * kEpiSlotBytes, &p.res_map, res_bar(g, s0), cb, row0);
+        }
+      }
       mbar_wait(tmem_full_bar, it & 1u, kTagTmemFull);
       tc_fence_after();
+
+      // ---- pass 1: row sum of squares of (acc + bias); 16-bit output also stashes the row
+      [[maybe_unused]] uint32_t stash[kOut16 ? 128 : 1];
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = __uint_as_float(r[2 * i]) + p.bias[cb + c * 32 + 2 * i];
+          const float b = __uint_as_float(r[2 * i + 1]) + p.bias[cb + c * 32 + 2 * i + 1];
+          ss = fmaf(a, a, ss);
+          ss = fmaf(b, b, ss);
+          if constexpr (kOut16) stash[c * 16 + i] = Pack16<TOut>::pack(a, b);
+        }
+      }
+      if constexpr (kOut16) {                                   // accumulator fully read: release TMEM now
+        tc_fence_before();
+        if (kCg == 1 || rank == 0) mbar_arrive(tmem_empty_bar);
+        else mbar_arrive_cluster(tmem_empty_bar, 0);
+      }
       float inv = 1.f;
       if (p.normalize) {
-        float ss = 0.f;
-        for (int c0 = 0; c0 < kHidden; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c0, r);
+        float* ssb = ss_smem + (it & 1u) * 256;
+        ssb[g * 128 + row] = ss;
+        named_bar_sync(1, 256);
+        inv = 1.f / fmaxf(sqrtf(ssb[row] + ssb[128 + row]), 1e-12f);
+      }
+
+      // ---- pass 2: normalize / BN / ReLU / skip, staged through swizzled smem, TMA store
+#pragma unroll
+      for (int ch = 0; ch < kChunks; ++ch, ++seq) {
+        const uint32_t s = seq & 1u;
+        const uint32_t slot = slots_u32 + (g * 2 + s) * kEpiSlotBytes;
+        const int col0 = cb + ch * kChunkCols;
+        if (leader) {
+          if (ch > 0) tma_store_wait_read<0>();                 // the other slot is free again
+          if (p.has_res && ch + 1 < kChunks) {                  // prefetch the next chunk's skip rows into it
+            const uint32_t s1 = s ^ 1u;
+            mbar_arrive_expect_tx(res_bar(g, s1), kEpiSlotBytes);
+            tma_load_2d(slots_u32 + (g * 2 + s1) * kEpiSlotBytes, &p.res_map, res_bar(g, s1),
+                        col0 + kChunkCols, row0);
+          }
+        }
+        if (p.has_res) mbar_wait(res_bar(g, s), (seq >> 1) & 1u, kTagRes);
+        [[maybe_unused]] uint32_t r[32];
+        if constexpr (!kOut16) {
+          tmem_ld_32x32(taddr + ch * 32, r);
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { float v = __uint_as_float(r[i]) + sbias[c0 + i]; ss = fmaf(v, v, ss); }
         }
-        inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-      }
-      TOut* orow = reinterpret_cast<TOut*>(p.out) + m * p.ldo;
-      const TOut* rrow = p.residual ? reinterpret_cast<const TOut*>(p.residual) + m * p.ldr : nullptr;
-      for (int c0 = 0; c0 < kHidden; c0 += 32) {
-        constexpr int kVec = 32 * sizeof(TOut) / 16;             // 16-byte vectors per 32 columns
-        uint4 res[kVec];
-        if (rrow && valid) {
 #pragma unroll
-          for (int j = 0; j < kVec; ++j) res[j] = ldg_nc_v4(reinterpret_cast<const uint4*>(rrow + c0) + j);
-        }
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c0, r);
-        tmem_ld_wait();
-        float v[32];
+        for (int j = 0; j < 8; ++j) {                           // 16-byte pieces of this thread's 128-byte row
+          const uint32_t addr = slot + row_off + (((uint32_t)j ^ sw) << 4);
+          constexpr int kPer = 16 / (int)sizeof(TOut);          // 8 or 4 columns per piece
+          float v[kPer];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = (__uint_as_float(r[i]) + sbias[c0 + i]) * inv;
-          if (has_bn) t = fmaf(t, sscale[c0 + i], sshift[c0 + i]);
-          if (p.relu) t = fmaxf(t, 0.f);
-          v[i] = t;
-        }
-        if (rrow && valid) {
-          const uint32_t* ru = reinterpret_cast<const uint32_t*>(res);
-          if constexpr (sizeof(TOut) == 2) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { v[2 * i] += Pack16<TOut>::lo(ru[i]); v[2 * i + 1] += Pack16<TOut>::hi(ru[i]); }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(ru[i]);
-          }
-        }
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + c0);
-          if constexpr (sizeof(TOut) == 2) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = Pack16<TOut>::pack(v[8 * j], v[8 * j + 1]); o.y = Pack16<TOut>::pack(v[8 * j + 2], v[8 * j + 3]);
-              o.z = Pack16<TOut>::pack(v[8 * j + 4], v[8 * j + 5]); o.w = Pack16<TOut>::pack(v[8 * j + 6], v[8 * j + 7]);
-              stg_v4(dst + j, o);
+          for (int e = 0; e < kPer; ++e) {
+            const int c = col0 + j * kPer + e;
+            float a;
+            if constexpr (kOut16) {
+              const uint32_t u = stash[ch * 32 + j * 4 + (e >> 1)];
+              a = (e & 1) ? Pack16<TOut>::hi(u) : Pack16<TOut>::lo(u);
+            } else {
+              a = __uint_as_float(r[j * 4 + e]) + p.bias[c];
             }
-          } else {
+            a = fmaf(a * inv, p.scale[c], p.shift[c]);
+            if (p.relu) a = fmaxf(a, 0.f);
+            v[e] = a;
+          }
+          if (p.has_res) {
+            const uint4 rr = lds_v4(addr);
+            const uint32_t ru[4] = {rr.x, rr.y, rr.z, rr.w};
+            if constexpr (kOut16) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint4 o;
-              o.x = __float_as_uint(v[4 * j]); o.y = __float_as_uint(v[4 * j + 1]);
-              o.z = __float_as_uint(v[4 * j + 2]); o.w = __float_as_uint(v[4 * j + 3]);
-              stg_v4(dst + j, o);
+              for (int e = 0; e < 4; ++e) { v[2 * e] += Pack16<TOut>::lo(ru[e]); v[2 * e + 1] += Pack16<TOut>::hi(ru[e]); }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] += __uint_as_float(ru[e]);
             }
           }
+          uint4 o;
+          if constexpr (kOut16) {
+            o.x = Pack16<TOut>::pack(v[0], v[1]); o.y = Pack16<TOut>::pack(v[2], v[3]);
+            o.z = Pack16<TOut>::pack(v[4], v[5]); o.w = Pack16<TOut>::pack(v[6], v[7]);
+          } else {
+            o.x = __float_as_uint(v[0]); o.y = __float_as_uint(v[1]); o.z = __float_as_uint(v[2]); o.w = __float_as_uint(v[3]);
+          }
+          sts_v4(addr, o);
+        }
+        if constexpr (!kOut16) {
+          if (ch == kChunks - 1) {                              // last TMEM read of the tile
+            tc_fence_before();
+            if (kCg == 1 || rank == 0) mbar_arrive(tmem_empty_bar);
+            else mbar_arrive_cluster(tmem_empty_bar, 0);
+          }
+        }
+        fence_proxy_async_smem();                               // generic-proxy writes -> visible to the TMA store
+        named_bar_sync(grp_bar, 128);
+        if (leader) {
+          tma_store_2d(&p.out_map, slot, col0, row0);
+          tma_store_commit();
         }
       }
-      // accumulator fully read: hand TMEM back to the MMA warp of the leader CTA
-      tc_fence_before();
-      if (kCg == 1 || rank == 0) mbar_arrive(tmem_empty_bar);
-      else mbar_arrive_cluster(tmem_empty_bar, 0);
     }
+    if (leader) tma_store_wait<0>();                            // all stores complete before the CTA exits
   }
 
   // ---- teardown
@@ -278,6 +357,7 @@ typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, 
 PFN_tensorMapEncodeTiled get_tensor_map_encoder();
 
 // [rows, k] row-major matrix, box = 128 rows x 128 bytes of K, 128B swizzle, zero fill out of bounds
+// (the same geometry serves the operand tiles and the epilogue's out / residual staging tiles)
 // fmt: UMMA operand format (0 f16, 1 bf16, 2 tf32/f32)
 static inline int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t k, int64_t ld,
                                    uint32_t fmt) {

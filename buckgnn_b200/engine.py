@@ -202,16 +202,21 @@ def pack_linear(weight: torch.Tensor, precision: str) -> LinearPack:
 class SageLayerPack:
     lin_l: LinearPack
     lin_r: LinearPack
-    bias: torch.Tensor                   # f32 [512]
-    bn_scale: Optional[torch.Tensor]     # f32 [512]  gamma / sqrt(var + eps)
-    bn_shift: Optional[torch.Tensor]     # f32 [512]  beta - mean * scale
+    bias: torch.Tensor                   # f32 [512], HOST (travels in the kernel parameters)
+    bn_scale: Optional[torch.Tensor]     # f32 [512], HOST   gamma / sqrt(var + eps)
+    bn_shift: Optional[torch.Tensor]     # f32 [512], HOST   beta - mean * scale
 
 
 def fold_batchnorm(bn: torch.nn.BatchNorm1d) -> Tuple[torch.Tensor, torch.Tensor]:
     """Eval-mode BatchNorm1d as one multiply-add per column (Models/BuckGNN.py:451)."""
-    scale = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)).contiguous()
-    shift = (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).contiguous()
-    return scale, shift
+    scale = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps))
+    shift = (bn.bias.detach().float() - bn.running_mean.detach().float() * scale)
+    return scale.cpu().contiguous(), shift.cpu().contiguous()
+
+
+def host_vector(t: torch.Tensor) -> torch.Tensor:
+    """fp32 host copy of a [512] epilogue vector (bias / BN scale / BN shift)."""
+    return t.detach().float().cpu().contiguous()
 
 
 class Activation:
@@ -271,7 +276,7 @@ def encoder_forward(x: torch.Tensor, enc_w: Dict[str, torch.Tensor], w3: LinearP
                            enc_w["w2"].data_ptr(), enc_w["b2"].data_ptr(), h.data.data_ptr(), h.code, _stream())
     h.refresh_split()
     with TIMERS.span("encoder_gemm"):
-        gemm512(_segments(h, w3), n, precision, out, cta_group=cta_group, bias=enc_w["b3"].data_ptr())
+        gemm512(_segments(h, w3), n, precision, out, cta_group=cta_group, bias=enc_w["b3_host"].data_ptr())
 
 
 def sage_layer(x: Activation, agg: Activation, out: Activation, idx: GraphIndex, layer: SageLayerPack, *,

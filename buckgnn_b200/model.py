@@ -168,7 +168,7 @@ class BuckGNN(nn.Module):
         f32 = lambda t: t.detach().float().contiguous()
         enc = self.node_encoder
         packs = {"enc": {"w1": f32(enc[0].weight), "b1": f32(enc[0].bias), "w2": f32(enc[2].weight),
-                         "b2": f32(enc[2].bias), "b3": f32(enc[4].bias)},
+                         "b2": f32(enc[2].bias), "b3_host": engine.host_vector(enc[4].bias)},
                  "enc_w3": engine.pack_linear(enc[4].weight, prec)}
         dec = self.decoder
         packs["dec"] = {"w1": f32(dec[0].weight), "b1": f32(dec[0].bias), "w2": f32(dec[2].weight),
@@ -179,7 +179,7 @@ class BuckGNN(nn.Module):
                 scale, shift = engine.fold_batchnorm(bn) if bn is not None else (None, None)
                 seen[id(conv)] = SageLayerPack(engine.pack_linear(conv.lin_l.weight, prec),
                                                engine.pack_linear(conv.lin_r.weight, prec),
-                                               f32(conv.lin_l.bias), scale, shift)
+                                               engine.host_vector(conv.lin_l.bias), scale, shift)
             layers.append(seen[id(conv)])
         packs["layers"] = layers
         self._packs, self._pack_sig = packs, sig

@@ -124,7 +124,7 @@ int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t n_nodes,
  * tf32, kind::tf32; k_s % 32 == 0 -- with hi/lo split operands from bg_split_tf32 this
  * is the 3xTF32 "fp32-GEMM" mode).  fp32 accumulation in TMEM always.
  * out/residual dtype = out_dtype (any bg_dtype).  All base pointers 16-byte aligned, ld* such that
- * rows are 16-byte aligned.  cta_group: 1 or 2 (2 = tcgen05 cta_group::2 CTA pairs). */
+ * rows are 16-byte aligned.  cta_group must be 2 (tcgen05 cta_group::2 CTA pairs). */
 #define BG_MAX_GEMM_SEGMENTS 6
 typedef struct bg_gemm_segment {
   const void* a; int64_t lda;
@@ -133,12 +133,12 @@ typedef struct bg_gemm_segment {
 } bg_gemm_segment;
 
 typedef struct bg_epilogue {
-  const float* bias;      /* [512] or NULL */
-  const float* bn_scale;  /* [512] or NULL (then bn_shift ignored) */
-  const float* bn_shift;
-  const void* residual;   /* [M,512], ld = ldr, or NULL */
+  const float* bias_host;      /* [512] HOST pointers: the vectors travel in the kernel   */
+  const float* bn_scale_host;  /* parameters (constant bank); NULL = absent                */
+  const float* bn_shift_host;  /* required iff bn_scale_host is given                      */
+  const void* residual;        /* DEVICE [M,512], ld = ldr, dtype = out_dtype, or NULL     */
   int64_t ldr;
-  int32_t normalize;      /* F.normalize(p=2, dim=-1, eps=1e-12) */
+  int32_t normalize;           /* F.normalize(p=2, dim=-1, eps=1e-12) */
   int32_t relu;
 } bg_epilogue;
 

@@ -146,7 +146,9 @@ def _gemm_case(m, precision, cta_group, full_epilogue, seed=0):
         want = acc
     dv = lambda t: None if t is None else t.to(DEV).contiguous()
     Ad, Bd = [dv(a) for a in As], [dv(b) for b in Bs]
-    biasd, scaled, shiftd, resd = dv(bias), dv(scale), dv(shift), dv(res)
+    resd = dv(res)
+    hv = lambda t: None if t is None else t.float().contiguous()
+    biasd, scaled, shiftd = hv(bias), hv(scale), hv(shift)          # epilogue vectors are HOST pointers
     out = Activation(m, 512, precision, DEV)
     segs = [(a.data_ptr(), k, b.data_ptr(), k, k) for a, b, k in zip(Ad, Bd, ks)]
     engine.gemm512(segs, m, precision, out, cta_group=cta_group, bias=biasd.data_ptr(),
@@ -159,7 +161,7 @@ def _gemm_case(m, precision, cta_group, full_epilogue, seed=0):
 _TOL16 = {"bf16": dict(rtol=1e-2, atol=2e-2), "fp16": dict(rtol=2e-3, atol=3e-3)}
 
 
-@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("cta_group", [2])
 @pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
 @pytest.mark.parametrize("m", [128, 300, 20000])
 def test_gemm_plain_bias(m, precision, cta_group):
@@ -168,7 +170,7 @@ def test_gemm_plain_bias(m, precision, cta_group):
     torch.testing.assert_close(got, want, **tol)
 
 
-@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("cta_group", [2])
 @pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
 @pytest.mark.parametrize("m", [77, 40000])
 def test_gemm_sage_epilogue(m, precision, cta_group):

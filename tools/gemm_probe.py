@@ -46,7 +46,7 @@ def run(m, k, precision, cg, pattern):
 
 if __name__ == "__main__":
     capi.device_check()
-    cgs = [int(c) for c in (sys.argv[1] if len(sys.argv) > 1 else "1,2").split(",")]
+    cgs = [int(c) for c in (sys.argv[1] if len(sys.argv) > 1 else "2").split(",")]
     ok = True
     for cg in cgs:
         for precision in ("bf16", "fp16", "tf32"):

@@ -4,7 +4,6 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 run() { name=$1; shift; echo "=== $name"; timeout 600 "$@" > gpurun_out/$name.log 2>&1; echo "exit $?" | tee -a gpurun_out/$name.log; tail -n 25 gpurun_out/$name.log; }
-run probe_cg1 python tools/gemm_probe.py 1
 run probe_cg2 python tools/gemm_probe.py 2
 run t_csr python -m pytest tests/test_gpu_kernels.py -q -x -m gpu -k "csr or graph_ptr"
 run t_enc python -m pytest tests/test_gpu_kernels.py -q -x -m gpu -k "encoder"
