@@ -24,7 +24,7 @@ namespace bg {
 constexpr int kHubSlices = 16;
 constexpr int kAggWarpsPerBlock = 8;       // hub kernel
 // row kernel: one CTA per SM; 32 warps for 16-bit rows (64 regs/thread), 16 warps for fp32 rows
-template <typename T> constexpr int agg_row_threads() { return sizeof(T) == 2 ? 1024 : 512; }
+template <typename T> __host__ __device__ constexpr int agg_row_threads() { return sizeof(T) == 2 ? 1024 : 512; }
 
 template <int kAggr> BG_DEVINL float agg_init() { return kAggr == BG_AGGR_MAX ? -INFINITY : 0.f; }
 template <int kAggr> BG_DEVINL float agg_op(float a, float b) {
@@ -47,8 +47,12 @@ template <typename T> struct RowFrag16 {
     const uint32_t* u = reinterpret_cast<const uint32_t*>(q);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      acc[2 * i] = agg_op<kAggr>(acc[2 * i], Pack16<T>::lo(u[i]));
-      acc[2 * i + 1] = agg_op<kAggr>(acc[2 * i + 1], Pack16<T>::hi(u[i]));
+      if constexpr (kAggr == BG_AGGR_MAX) {
+        acc[2 * i] = fmaxf(acc[2 * i], Pack16<T>::lo(u[i]));
+        acc[2 * i + 1] = fmaxf(acc[2 * i + 1], Pack16<T>::hi(u[i]));
+      } else {
+        Pack16<T>::add2(acc[2 * i], acc[2 * i + 1], u[i]);      // fp32 += 16-bit, one FHADD each
+      }
     }
   }
   static BG_DEVINL void store(T* row, int lane, const float (&v)[16]) {
@@ -119,11 +123,17 @@ BG_DEVINL void gather_range(const T* __restrict__ x, const int32_t* __restrict__
   }
 }
 
-template <int kAggr> BG_DEVINL void agg_finalize(float (&acc)[16], int32_t deg) {
+template <int kAggr, bool kExactDiv> BG_DEVINL void agg_finalize(float (&acc)[16], int32_t deg) {
   if constexpr (kAggr == BG_AGGR_MEAN) {
     const float d = (float)max(deg, 1);
+    if constexpr (kExactDiv) {                            // fp32 rows: true division, as `sum / count` does
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = acc[i] / d;     // true division, as `sum / count` does
+      for (int i = 0; i < 16; ++i) acc[i] = acc[i] / d;
+    } else {                                              // 16-bit rows: the 1-ulp difference is below the output rounding
+      const float rd = 1.f / d;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] *= rd;
+    }
   } else if constexpr (kAggr == BG_AGGR_MAX) {
     if (deg == 0) {
 #pragma unroll
@@ -151,7 +161,7 @@ k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N,
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = agg_init<kAggr>();
     gather_range<T, kAggr>(x, col, beg, end, lane, acc);
-    agg_finalize<kAggr>(acc, end - beg);
+    agg_finalize<kAggr, sizeof(T) == 4>(acc, end - beg);
     RowFrag<T>::store(out + (size_t)r * kHidden, lane, acc);
   }
 }

@@ -80,17 +80,27 @@ BG_DEVINL uint32_t pack_f16(float a, float b) {
   __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-// 16-bit storage formats: unpack a pair / pack a pair / scalar convert
+// 16-bit storage formats: unpack a pair / pack a pair / scalar convert / fp32 += 16-bit pair.
+// add2 uses sm_100's mixed-precision add (add.rn.f32.{f16,bf16} -> one FHADD per element, the
+// 16-bit half selected for free), so fp32 accumulation of 16-bit rows needs no conversions.
 template <typename T> struct Pack16;
 template <> struct Pack16<__nv_bfloat16> {
   static BG_DEVINL float lo(uint32_t u) { return bf16_lo(u); }
   static BG_DEVINL float hi(uint32_t u) { return bf16_hi(u); }
+  static BG_DEVINL void add2(float& a0, float& a1, uint32_t u) {
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\t"
+        "add.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t}" : "+f"(a0), "+f"(a1) : "r"(u));
+  }
   static BG_DEVINL uint32_t pack(float a, float b) { return pack_bf16(a, b); }
   static BG_DEVINL __nv_bfloat16 one(float a) { return __float2bfloat16_rn(a); }
 };
 template <> struct Pack16<__half> {
   static BG_DEVINL float lo(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu))); }
   static BG_DEVINL float hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
+  static BG_DEVINL void add2(float& a0, float& a1, uint32_t u) {
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\t"
+        "add.rn.f32.f16 %0, lo, %0;\n\tadd.rn.f32.f16 %1, hi, %1;\n\t}" : "+f"(a0), "+f"(a1) : "r"(u));
+  }
   static BG_DEVINL uint32_t pack(float a, float b) { return pack_f16(a, b); }
   static BG_DEVINL __half one(float a) { return __float2half_rn(a); }
 };

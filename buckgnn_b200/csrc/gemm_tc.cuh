@@ -310,7 +310,7 @@ k_gemm512(const __grid_constant__ GemmParams p) {
             const uint32_t ru[4] = {rr.x, rr.y, rr.z, rr.w};
             if constexpr (kOut16) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { v[2 * e] += Pack16<TOut>::lo(ru[e]); v[2 * e + 1] += Pack16<TOut>::hi(ru[e]); }
+              for (int e = 0; e < 4; ++e) Pack16<TOut>::add2(v[2 * e], v[2 * e + 1], ru[e]);
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) v[e] += __uint_as_float(ru[e]);
