@@ -27,20 +27,21 @@ def is_stale() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/capi.cu (a unity build including the .cuh kernels) -> lib/libbuckgnn_b200.so."""
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB_PATH) -> str:
+    """Compile csrc/capi.cu (a unity build including the .cuh kernels) -> lib/libbuckgnn_b200.so.
+    `defines` / `out` build instrumented variants (e.g. -DBG_PROFILE) next to it."""
+    if not force and not is_stale() and out == LIB_PATH:
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH, os.path.join(CSRC, "capi.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines] + \
+          ["-o", out, os.path.join(CSRC, "capi.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

@@ -11,7 +11,10 @@ import ctypes as C
 import os
 import threading
 
-from .build import LIB_PATH
+from .build import LIB_PATH as _DEFAULT_LIB_PATH
+
+# BG_LIB_PATH selects an instrumented build of the same ABI (tools/gemm_bench.py); default = the product library
+LIB_PATH = os.environ.get("BG_LIB_PATH", _DEFAULT_LIB_PATH)
 
 BG_BF16, BG_F32, BG_F16 = 0, 1, 2
 BG_AGGR_MEAN, BG_AGGR_SUM, BG_AGGR_MAX = 0, 1, 2

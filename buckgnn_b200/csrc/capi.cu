@@ -115,6 +115,14 @@ int bg_device_check(void) {
   return BG_OK;
 }
 
+#ifdef BG_PROFILE
+// profiling build only: copy the per-CTA role cycle counters of the last bg_gemm512 to the host
+int bg_gemm_prof_host(unsigned long long* out, int n) {
+  BG_CUDA_OK(cudaMemcpyFromSymbol(out, g_gemm_prof, sizeof(unsigned long long) * (size_t)n));
+  return BG_OK;
+}
+#endif
+
 int bg_watchdog_info_host(uint32_t* out4_host) {
   if (!out4_host) return fail(BG_ERR_INVALID, "null output");
   BG_CUDA_OK(cudaMemcpyFromSymbol(out4_host, g_watchdog_info, 16));

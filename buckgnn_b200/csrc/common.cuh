@@ -95,8 +95,16 @@ template <> struct Pack16<__nv_bfloat16> {
   static BG_DEVINL __nv_bfloat16 one(float a) { return __float2bfloat16_rn(a); }
 };
 template <> struct Pack16<__half> {
-  static BG_DEVINL float lo(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu))); }
-  static BG_DEVINL float hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
+  static BG_DEVINL float lo(uint32_t u) {
+    float f;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(f) : "r"(u));
+    return f;
+  }
+  static BG_DEVINL float hi(uint32_t u) {
+    float f;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(f) : "r"(u));
+    return f;
+  }
   static BG_DEVINL void add2(float& a0, float& a1, uint32_t u) {
     asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\t"
         "add.rn.f32.f16 %0, lo, %0;\n\tadd.rn.f32.f16 %1, hi, %1;\n\t}" : "+f"(a0), "+f"(a1) : "r"(u));

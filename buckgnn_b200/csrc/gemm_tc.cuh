@@ -14,7 +14,8 @@
 //   warp 1     allocates TMEM; in the leader CTA one elected lane issues tcgen05.mma
 //              (M = 256 over the pair, N = 256, two N halves -> the 512 fp32 columns of
 //              TMEM hold one full output row per lane: L2-normalize needs the whole row)
-//   warps 2-3  idle (register donors)
+//   warps 2-3  staging-ring drivers, one per column half: issue the epilogue's TMA stores
+//              and skip-row loads so the math warps never wait on the TMA engine
 //   warps 4-11 epilogue, two groups of 4 warps = two 256-column halves; one TMEM lane
 //              (= output row) per thread.
 //              16-bit output: ONE pass over TMEM adds the bias, accumulates the row's sum
@@ -70,7 +71,23 @@ struct alignas(64) GemmParams {
   float shift[kHidden];             // 0 when there is no BN
 };
 
-enum : uint32_t { kTagEmpty = 1, kTagFull = 2, kTagTmemEmpty = 3, kTagTmemFull = 4, kTagRes = 5 };
+// Optional role-level cycle accounting (build with -DBG_PROFILE, see tools/gemm_bench.py):
+// per CTA: [0] producer wait-empty, [1] mma wait-full, [2] mma wait-tmem-empty, [3] mma total,
+// [4] epi wait-tmem-full, [5] epi pass 1, [6] epi pass 2, [7] epi total
+#ifdef BG_PROFILE
+__device__ unsigned long long g_gemm_prof[296 * 8];
+#define BG_PROF_DECL long long _pt0 = 0, _pacc_a = 0, _pacc_b = 0, _pacc_c = 0; const long long _pstart = clock64();
+#define BG_PROF_T0() _pt0 = clock64()
+#define BG_PROF_ADD(acc) acc += clock64() - _pt0
+#define BG_PROF_STORE(slot, v) g_gemm_prof[blockIdx.x * 8 + (slot)] = (unsigned long long)(v)
+#else
+#define BG_PROF_DECL
+#define BG_PROF_T0()
+#define BG_PROF_ADD(acc)
+#define BG_PROF_STORE(slot, v)
+#endif
+
+enum : uint32_t { kTagEmpty = 1, kTagFull = 2, kTagTmemEmpty = 3, kTagTmemFull = 4, kTagEpiReady = 5, kTagEpiFull = 6 };
 
 BG_DEVINL void named_bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -85,6 +102,161 @@ BG_DEVINL void sts_v4(uint32_t addr, uint4 v) {
 }
 template <int kRegs> BG_DEVINL void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs> BG_DEVINL void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
+// staging-ring barriers: per column-half group g and slot s
+BG_DEVINL uint32_t epi_ready_bar(uint32_t base, int g, uint32_t s) { return base + 8u * (uint32_t)(g * 2 + s); }
+BG_DEVINL uint32_t epi_full_bar(uint32_t base, int g, uint32_t s) { return base + 8u * (uint32_t)(4 + g * 2 + s); }
+
+struct EpiCtx {
+  uint32_t tmem_base, slots_u32, ring_bars;
+  float* ss_smem;
+  uint32_t tmem_full_bar, tmem_empty_bar, rank;
+  int tile0, tile_stride;
+};
+
+// TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns
+BG_DEVINL void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+
+// One column-half group (4 warps = 128 TMEM lanes = 128 output rows, 256 columns starting at
+// kG*256).  kG is a template parameter so every bias / scale / shift access is a constant-bank
+// operand with an immediate offset.
+template <int kCg, typename TOut, int kG>
+BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
+  constexpr bool kOut16 = sizeof(TOut) == 2;
+  constexpr int kChunkCols = 128 / (int)sizeof(TOut);           // columns per 128-byte staging row: 64 / 32
+  constexpr int kChunks = 256 / kChunkCols;                     // 4 / 8
+  constexpr int cb = kG * 256;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;                                       // TMEM lane quarter this warp may read
+  const int row = q * 32 + lane;                                // row within the CTA's 128-row tile
+  const uint32_t taddr = cx.tmem_base + ((uint32_t)(q * 32) << 16) + cb;
+  const uint32_t row_off = (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)(row & 7);
+  uint32_t it = 0, seq = 0;                                     // tiles done; staging chunks done (this group)
+  BG_PROF_DECL
+  for (int tile = cx.tile0; tile < p.n_tiles; tile += cx.tile_stride, ++it) {
+    BG_PROF_T0();
+    mbar_wait(cx.tmem_full_bar, it & 1u, kTagTmemFull);
+    BG_PROF_ADD(_pacc_a);
+    tc_fence_after();
+    BG_PROF_T0();
+
+    // ---- pass 1: row sum of squares of (acc + bias); 16-bit output also stashes the row.
+    // TMEM loads are double-buffered (16 columns each) so their latency hides behind the math.
+    [[maybe_unused]] uint32_t stash[kOut16 ? 128 : 1];
+    float ss = 0.f;
+    {
+      uint32_t ra[16], rb[16];
+      auto consume = [&](const uint32_t (&r)[16], int c16) {    // c16: index of the 16-column block
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = __uint_as_float(r[2 * i]) + p.bias[cb + c16 * 16 + 2 * i];
+          const float b = __uint_as_float(r[2 * i + 1]) + p.bias[cb + c16 * 16 + 2 * i + 1];
+          ss = fmaf(a, a, ss);
+          ss = fmaf(b, b, ss);
+          if constexpr (kOut16) stash[c16 * 8 + i] = Pack16<TOut>::pack(a, b);
+        }
+      };
+      if (kOut16 || p.normalize) {
+        tmem_ld_32x16(taddr, ra);
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x16(taddr + (c + 1) * 16, rb);
+          consume(ra, c);
+          tmem_ld_wait();
+          if (c + 2 < 16) tmem_ld_32x16(taddr + (c + 2) * 16, ra);
+          consume(rb, c + 1);
+        }
+      }
+    }
+    if constexpr (kOut16) {                                     // accumulator fully read: release TMEM now
+      tc_fence_before();
+      if (kCg == 1 || cx.rank == 0) mbar_arrive(cx.tmem_empty_bar);
+      else mbar_arrive_cluster(cx.tmem_empty_bar, 0);
+    }
+    float inv = 1.f;
+    if (p.normalize) {
+      float* ssb = cx.ss_smem + (it & 1u) * 256;
+      ssb[kG * 128 + row] = ss;
+      named_bar_sync(1, 256);
+      inv = 1.f / fmaxf(sqrtf(ssb[row] + ssb[128 + row]), 1e-12f);
+    }
+    BG_PROF_ADD(_pacc_b);
+    BG_PROF_T0();
+
+    // ---- pass 2: normalize / BN / ReLU / skip into the swizzled staging ring
+#pragma unroll
+    for (int ch = 0; ch < kChunks; ++ch, ++seq) {
+      const uint32_t sl = seq & 1u;
+      const uint32_t slot = cx.slots_u32 + (kG * 2 + sl) * kEpiSlotBytes;
+      constexpr int kPer = 16 / (int)sizeof(TOut);              // 8 or 4 columns per 16-byte piece
+      [[maybe_unused]] uint32_t r[32];
+      if constexpr (!kOut16) {
+        tmem_ld_32x32(taddr + ch * 32, r);
+        tmem_ld_wait();
+        if (ch == kChunks - 1) {                                // last TMEM read of the tile
+          tc_fence_before();
+          if (kCg == 1 || cx.rank == 0) mbar_arrive(cx.tmem_empty_bar);
+          else mbar_arrive_cluster(cx.tmem_empty_bar, 0);
+        }
+      }
+      mbar_wait(epi_ready_bar(cx.ring_bars, kG, sl), (seq >> 1) & 1u, kTagEpiReady);   // tile free / skip rows landed
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {                             // 16-byte pieces of this thread's 128-byte row
+        const uint32_t addr = slot + row_off + (((uint32_t)j ^ sw) << 4);
+        float v[kPer];
+#pragma unroll
+        for (int e = 0; e < kPer; ++e) {
+          const int c = cb + ch * kChunkCols + j * kPer + e;    // compile-time constant
+          float a;
+          if constexpr (kOut16) {
+            const uint32_t u = stash[ch * 32 + j * 4 + (e >> 1)];
+            a = (e & 1) ? Pack16<TOut>::hi(u) : Pack16<TOut>::lo(u);
+          } else {
+            a = __uint_as_float(r[j * 4 + e]) + p.bias[c];
+          }
+          a = fmaf(a * inv, p.scale[c], p.shift[c]);
+          if (p.relu) a = fmaxf(a, 0.f);
+          v[e] = a;
+        }
+        if (p.has_res) {
+          const uint4 rr = lds_v4(addr);
+          const uint32_t ru[4] = {rr.x, rr.y, rr.z, rr.w};
+          if constexpr (kOut16) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) Pack16<TOut>::add2(v[2 * e], v[2 * e + 1], ru[e]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] += __uint_as_float(ru[e]);
+          }
+        }
+        uint4 o;
+        if constexpr (kOut16) {
+          o.x = Pack16<TOut>::pack(v[0], v[1]); o.y = Pack16<TOut>::pack(v[2], v[3]);
+          o.z = Pack16<TOut>::pack(v[4], v[5]); o.w = Pack16<TOut>::pack(v[6], v[7]);
+        } else {
+          o.x = __float_as_uint(v[0]); o.y = __float_as_uint(v[1]); o.z = __float_as_uint(v[2]); o.w = __float_as_uint(v[3]);
+        }
+        sts_v4(addr, o);
+      }
+      fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA store
+      mbar_arrive(epi_full_bar(cx.ring_bars, kG, sl));          // 128 arrivals hand the tile to the ring driver
+    }
+    BG_PROF_ADD(_pacc_c);
+  }
+#ifdef BG_PROFILE
+  if (threadIdx.x == kEpiFirstWarp * 32) {
+    BG_PROF_STORE(4, _pacc_a); BG_PROF_STORE(5, _pacc_b); BG_PROF_STORE(6, _pacc_c); BG_PROF_STORE(7, clock64() - _pstart);
+  }
+#endif
+}
 
 template <int kCg, bool kTf32, typename TOut>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -106,7 +278,6 @@ k_gemm512(const __grid_constant__ GemmParams p) {
   auto empty_bar = [&](int s) { return bars_u32 + 8u * (kStages + s); };
   const uint32_t tmem_full_bar = bars_u32 + 8u * (2 * kStages);
   const uint32_t tmem_empty_bar = bars_u32 + 8u * (2 * kStages + 1);
-  auto res_bar = [&](int g, int s) { return bars_u32 + 8u * (2 * kStages + 2 + g * 2 + s); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -126,7 +297,10 @@ k_gemm512(const __grid_constant__ GemmParams p) {
       for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), kCg); mbar_init(empty_bar(s), 1); }
       mbar_init(tmem_full_bar, 1);
       mbar_init(tmem_empty_bar, kCg * 256);
-      for (int i = 0; i < 4; ++i) mbar_init(res_bar(i >> 1, i & 1), 1);
+      for (int i = 0; i < 4; ++i) {
+        mbar_init(epi_ready_bar(bars_u32 + 8u * (2 * kStages + 2), i >> 1, i & 1), 1);
+        mbar_init(epi_full_bar(bars_u32 + 8u * (2 * kStages + 2), i >> 1, i & 1), 128);
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -142,6 +316,7 @@ k_gemm512(const __grid_constant__ GemmParams p) {
     if (warp == 0) {
       // ================================================================ TMA producer
       if (elect_one()) {
+        BG_PROF_DECL
         uint32_t stage = 0, phase = 0;
         for (int tile = tile0; tile < p.n_tiles; tile += tile_stride) {
           const int32_t row0 = tile * (kTileM * kCg) + (int32_t)rank * kTileM;
@@ -149,7 +324,9 @@ k_gemm512(const __grid_constant__ GemmParams p) {
             const void* map_a = &p.seg[s].a;
             const void* map_b = &p.seg[s].b;
             for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+              BG_PROF_T0();
               mbar_wait(empty_bar(stage), phase ^ 1u, kTagEmpty);
+              BG_PROF_ADD(_pacc_a);
               const uint32_t sa = stages_u32 + stage * Cfg::kStageBytes;
               const uint32_t sb = sa + kATileBytes;
               const int32_t k0 = kb * p.k_elems_per_block;
@@ -171,20 +348,26 @@ k_gemm512(const __grid_constant__ GemmParams p) {
             }
           }
         }
+        BG_PROF_STORE(0, _pacc_a);
       }
       __syncwarp();
     } else if (warp == 1 && rank == 0) {
       // ================================================================ MMA issuer (leader CTA)
       const uint32_t idesc = umma_idesc(p.a_fmt, p.b_fmt, kTileM * kCg, 256);
+      BG_PROF_DECL
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = tile0; tile < p.n_tiles; tile += tile_stride, ++it) {
+        BG_PROF_T0();
         mbar_wait(tmem_empty_bar, (it & 1u) ^ 1u, kTagTmemEmpty);   // epilogue drained the accumulator
+        BG_PROF_ADD(_pacc_b);
         tc_fence_after();
         uint32_t first = 1;
         for (int s = 0; s < p.n_seg; ++s) {
           const int nkb = p.kblocks[s];
           for (int kb = 0; kb < nkb; ++kb) {
+            BG_PROF_T0();
             mbar_wait(full_bar(stage), phase, kTagFull);
+            BG_PROF_ADD(_pacc_a);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t sa = stages_u32 + stage * Cfg::kStageBytes;
@@ -207,140 +390,63 @@ k_gemm512(const __grid_constant__ GemmParams p) {
           }
         }
       }
+#ifdef BG_PROFILE
+      if (lane == 0) { BG_PROF_STORE(1, _pacc_a); BG_PROF_STORE(2, _pacc_b); BG_PROF_STORE(3, clock64() - _pstart); }
+#endif
+      __syncwarp();
+    } else if (warp >= 2) {
+      // ================================================================ staging-ring drivers (one per column half)
+      // Own all TMA traffic of the epilogue: store a staging tile once its 128 rows are
+      // written, and as soon as that store has left the tile, refill it for the chunk two
+      // ahead (skip-connection rows by TMA load, or just hand it back).
+      if (elect_one()) {
+        const int g = warp - 2;
+        constexpr int kChunkCols = 128 / (int)sizeof(TOut);
+        constexpr int kChunks = 256 / kChunkCols;
+        const uint32_t rb = bars_u32 + 8u * (2 * kStages + 2);
+        const int my_tiles = (p.n_tiles - tile0 + tile_stride - 1) / tile_stride;
+        const int total = my_tiles * kChunks;
+        auto coords = [&](int n, int32_t& col0, int32_t& row0) {
+          const int tile = tile0 + (n / kChunks) * tile_stride;
+          col0 = g * 256 + (n % kChunks) * kChunkCols;
+          row0 = tile * (kTileM * kCg) + (int32_t)rank * kTileM;
+        };
+        auto prepare = [&](int n) {                           // make slot n&1 ready for chunk n
+          const uint32_t sl = (uint32_t)n & 1u;
+          const uint32_t bar = epi_ready_bar(rb, g, sl);
+          if (p.has_res) {
+            int32_t c0, r0;
+            coords(n, c0, r0);
+            mbar_arrive_expect_tx(bar, kEpiSlotBytes);
+            tma_load_2d(slots_u32 + (g * 2 + sl) * kEpiSlotBytes, &p.res_map, bar, c0, r0);
+          } else {
+            mbar_arrive(bar);
+          }
+        };
+        for (int n = 0; n < 2 && n < total; ++n) prepare(n);
+        for (int n = 0; n < total; ++n) {
+          const uint32_t sl = (uint32_t)n & 1u;
+          mbar_wait(epi_full_bar(rb, g, sl), ((uint32_t)n >> 1) & 1u, kTagEpiFull);
+          int32_t c0, r0;
+          coords(n, c0, r0);
+          tma_store_2d(&p.out_map, slots_u32 + (g * 2 + sl) * kEpiSlotBytes, c0, r0);
+          tma_store_commit();
+          if (n + 2 < total) {
+            tma_store_wait_read<0>();                         // the store has left the tile
+            prepare(n + 2);
+          }
+        }
+        tma_store_wait<0>();                                  // all rows written before the CTA exits
+      }
       __syncwarp();
     }
   } else {
     // ================================================================ epilogue warps 4..11
     setmaxnreg_inc<232>();
-    const int q = warp & 3;                                     // TMEM lane quarter this warp may read
-    const int g = (warp - kEpiFirstWarp) >> 2;                  // column half: [g*256, g*256+256)
-    const int row = q * 32 + lane;                              // row within the CTA's 128-row tile
-    const int cb = g * 256;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cb;
-    const bool leader = (warp == kEpiFirstWarp + 4 * g) && (lane == 0);   // issues this group's TMA traffic
-    const uint32_t row_off = (uint32_t)row * 128u;
-    const uint32_t sw = (uint32_t)(row & 7);
-    const uint32_t grp_bar = 2 + g;
-    uint32_t it = 0, seq = 0;                                   // tiles done; staging chunks done (this group)
-    for (int tile = tile0; tile < p.n_tiles; tile += tile_stride, ++it) {
-      const int32_t row0 = tile * (kTileM * kCg) + (int32_t)rank * kTileM;
-      if (leader) {
-        tma_store_wait_read<0>();                               // previous tile's stores have left their slots
-        if (p.has_res) {
-          const uint32_t s0 = seq & 1u;
-          mbar_arrive_expect_tx(res_bar(g, s0), kEpiSlotBytes);
-          tma_load_2d(slots_u32 + (g * 2 + s0) * kEpiSlotBytes, &p.res_map, res_bar(g, s0), cb, row0);
-        }
-      }
-      mbar_wait(tmem_full_bar, it & 1u, kTagTmemFull);
-      tc_fence_after();
-
-      // ---- pass 1: row sum of squares of (acc + bias); 16-bit output also stashes the row
-      [[maybe_unused]] uint32_t stash[kOut16 ? 128 : 1];
-      float ss = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float a = __uint_as_float(r[2 * i]) + p.bias[cb + c * 32 + 2 * i];
-          const float b = __uint_as_float(r[2 * i + 1]) + p.bias[cb + c * 32 + 2 * i + 1];
-          ss = fmaf(a, a, ss);
-          ss = fmaf(b, b, ss);
-          if constexpr (kOut16) stash[c * 16 + i] = Pack16<TOut>::pack(a, b);
-        }
-      }
-      if constexpr (kOut16) {                                   // accumulator fully read: release TMEM now
-        tc_fence_before();
-        if (kCg == 1 || rank == 0) mbar_arrive(tmem_empty_bar);
-        else mbar_arrive_cluster(tmem_empty_bar, 0);
-      }
-      float inv = 1.f;
-      if (p.normalize) {
-        float* ssb = ss_smem + (it & 1u) * 256;
-        ssb[g * 128 + row] = ss;
-        named_bar_sync(1, 256);
-        inv = 1.f / fmaxf(sqrtf(ssb[row] + ssb[128 + row]), 1e-12f);
-      }
-
-      // ---- pass 2: normalize / BN / ReLU / skip, staged through swizzled smem, TMA store
-#pragma unroll
-      for (int ch = 0; ch < kChunks; ++ch, ++seq) {
-        const uint32_t s = seq & 1u;
-        const uint32_t slot = slots_u32 + (g * 2 + s) * kEpiSlotBytes;
-        const int col0 = cb + ch * kChunkCols;
-        if (leader) {
-          if (ch > 0) tma_store_wait_read<0>();                 // the other slot is free again
-          if (p.has_res && ch + 1 < kChunks) {                  // prefetch the next chunk's skip rows into it
-            const uint32_t s1 = s ^ 1u;
-            mbar_arrive_expect_tx(res_bar(g, s1), kEpiSlotBytes);
-            tma_load_2d(slots_u32 + (g * 2 + s1) * kEpiSlotBytes, &p.res_map, res_bar(g, s1),
-                        col0 + kChunkCols, row0);
-          }
-        }
-        if (p.has_res) mbar_wait(res_bar(g, s), (seq >> 1) & 1u, kTagRes);
-        [[maybe_unused]] uint32_t r[32];
-        if constexpr (!kOut16) {
-          tmem_ld_32x32(taddr + ch * 32, r);
-          tmem_ld_wait();
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {                           // 16-byte pieces of this thread's 128-byte row
-          const uint32_t addr = slot + row_off + (((uint32_t)j ^ sw) << 4);
-          constexpr int kPer = 16 / (int)sizeof(TOut);          // 8 or 4 columns per piece
-          float v[kPer];
-#pragma unroll
-          for (int e = 0; e < kPer; ++e) {
-            const int c = col0 + j * kPer + e;
-            float a;
-            if constexpr (kOut16) {
-              const uint32_t u = stash[ch * 32 + j * 4 + (e >> 1)];
-              a = (e & 1) ? Pack16<TOut>::hi(u) : Pack16<TOut>::lo(u);
-            } else {
-              a = __uint_as_float(r[j * 4 + e]) + p.bias[c];
-            }
-            a = fmaf(a * inv, p.scale[c], p.shift[c]);
-            if (p.relu) a = fmaxf(a, 0.f);
-            v[e] = a;
-          }
-          if (p.has_res) {
-            const uint4 rr = lds_v4(addr);
-            const uint32_t ru[4] = {rr.x, rr.y, rr.z, rr.w};
-            if constexpr (kOut16) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) Pack16<TOut>::add2(v[2 * e], v[2 * e + 1], ru[e]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] += __uint_as_float(ru[e]);
-            }
-          }
-          uint4 o;
-          if constexpr (kOut16) {
-            o.x = Pack16<TOut>::pack(v[0], v[1]); o.y = Pack16<TOut>::pack(v[2], v[3]);
-            o.z = Pack16<TOut>::pack(v[4], v[5]); o.w = Pack16<TOut>::pack(v[6], v[7]);
-          } else {
-            o.x = __float_as_uint(v[0]); o.y = __float_as_uint(v[1]); o.z = __float_as_uint(v[2]); o.w = __float_as_uint(v[3]);
-          }
-          sts_v4(addr, o);
-        }
-        if constexpr (!kOut16) {
-          if (ch == kChunks - 1) {                              // last TMEM read of the tile
-            tc_fence_before();
-            if (kCg == 1 || rank == 0) mbar_arrive(tmem_empty_bar);
-            else mbar_arrive_cluster(tmem_empty_bar, 0);
-          }
-        }
-        fence_proxy_async_smem();                               // generic-proxy writes -> visible to the TMA store
-        named_bar_sync(grp_bar, 128);
-        if (leader) {
-          tma_store_2d(&p.out_map, slot, col0, row0);
-          tma_store_commit();
-        }
-      }
-    }
-    if (leader) tma_store_wait<0>();                            // all stores complete before the CTA exits
+    const EpiCtx cx{tmem_base, slots_u32, bars_u32 + 8u * (2 * kStages + 2), ss_smem, tmem_full_bar, tmem_empty_bar,
+                    rank, tile0, tile_stride};
+    if (warp < kEpiFirstWarp + 4) epilogue_group<kCg, TOut, 0>(p, cx);
+    else epilogue_group<kCg, TOut, 1>(p, cx);
   }
 
   // ---- teardown
