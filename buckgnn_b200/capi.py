@@ -70,8 +70,8 @@ _SIGNATURES = {
     "bg_gemm512": (C.c_int, [C.POINTER(GemmSegment), _I32, _I64, C.c_int, C.c_int, C.POINTER(Epilogue), _P,
                              C.c_int, _I64, C.c_int, _P]),
     "bg_pool_workspace_bytes": (C.c_int, [_I64, _SZP]),
-    "bg_pool_head": (C.c_int, [_P, C.c_int, _I64, _P, _I64, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P,
-                               C.c_size_t, _P]),
+    "bg_pool_head": (C.c_int, [_P, C.c_int, _I64, _P, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P,
+                               _P, C.c_size_t, _P]),
     "bg_cast_f32": (C.c_int, [_P, _P, C.c_int, _I64, _P]),
     "bg_split_tf32": (C.c_int, [_P, _P, _P, _I64, _P]),
 }
@@ -174,10 +174,14 @@ def gemm512(segments, m, a_dtype, b_dtype, out, out_dtype, ldo, stream, *, bias=
            "bg_gemm512")
 
 
-def pool_head(x, dtype, n_nodes, graph_ptr, n_graphs, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out,
-              ws, ws_bytes, stream):
-    _check(load().bg_pool_head(x, dtype, n_nodes, graph_ptr, n_graphs, w1, b1, w2, b2, w3, b3, out_dim, pred,
-                               pooled_out, ws, ws_bytes, stream), "bg_pool_head")
+POOL_MODES = {"mean": 0, "mlp": 0, "mean_no_super": 1, "mlp_no_super": 1, "supernode_only": 2,
+              "supernode_with_pooling": 3}
+
+
+def pool_head(x, dtype, n_nodes, graph_ptr, n_graphs, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim,
+              pred, pooled_out, ws, ws_bytes, stream):
+    _check(load().bg_pool_head(x, dtype, n_nodes, graph_ptr, n_graphs, pool_mode, pre_w, pre_b, w1, b1, w2, b2,
+                               w3, b3, out_dim, pred, pooled_out, ws, ws_bytes, stream), "bg_pool_head")
 
 
 def cast_f32(src, dst, dst_dtype, n, stream):

@@ -97,6 +97,19 @@ static int aggregate_dispatch(const T* x, T* out, int64_t N, const int32_t* rowp
 }
 
 
+template <typename T>
+static void pool_launch(const T* x, const int32_t* graph_ptr, int64_t G, int mode, const float* pre_w, const float* pre_b,
+                        const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                        const float* b3, int out_dim, float* pred, float* pooled_out, float* partial, cudaStream_t stream) {
+  if (mode != BG_POOL_SUPERNODE_ONLY) {
+    dim3 grid((unsigned)G, kPoolSlices);
+    const int exclude_last = (mode == BG_POOL_MEAN_NO_SUPER || mode == BG_POOL_SUPERNODE_WITH_POOLING) ? 1 : 0;
+    k_pool_partial<T><<<grid, kPoolWarps * 32, 0, stream>>>(x, graph_ptr, partial, exclude_last);
+  }
+  k_pool_head<T><<<(unsigned)G, 128, 0, stream>>>(x, partial, graph_ptr, mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3,
+                                                   out_dim, pred, pooled_out);
+}
+
 }  // namespace bg
 
 using namespace bg;
@@ -331,30 +344,31 @@ int bg_pool_workspace_bytes(int64_t G, size_t* bytes_host) {
   return BG_OK;
 }
 
-int bg_pool_head(const void* x, int dtype, int64_t N, const int32_t* graph_ptr, int64_t G,
+int bg_pool_head(const void* x, int dtype, int64_t N, const int32_t* graph_ptr, int64_t G, int pool_mode,
+                 const float* pre_w, const float* pre_b,
                  const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
                  int32_t out_dim, float* pred, float* pooled_out, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (G < 0 || N < 0 || G > 65535LL * 1024) return fail(BG_ERR_INVALID, "bg_pool_head: bad size");
   if (G == 0) return BG_OK;
   if (out_dim < 1 || out_dim > 64) return fail(BG_ERR_UNSUPPORTED, "bg_pool_head: out_dim must be in [1,64]");
+  if (pool_mode < BG_POOL_MEAN || pool_mode > BG_POOL_SUPERNODE_WITH_POOLING) return fail(BG_ERR_INVALID, "bg_pool_head: bad pool_mode");
+  if ((pre_w != nullptr) != (pre_b != nullptr) || (pre_w && pool_mode > BG_POOL_MEAN_NO_SUPER) || (pre_w && !aligned16(pre_w)))
+    return fail(BG_ERR_INVALID, "bg_pool_head: pooling MLP needs both pre_w and pre_b and a mean pooling mode");
   if (!graph_ptr || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !pred || (N > 0 && (!x || !aligned16(x))) || !aligned16(w1))
     return fail(BG_ERR_INVALID, "bg_pool_head: bad pointer");
   size_t need = 0;
   bg_pool_workspace_bytes(G, &need);
   if (!workspace || workspace_bytes < need) return fail(BG_ERR_WORKSPACE, "bg_pool_head: workspace too small");
   float* partial = static_cast<float*>(workspace);
-  dim3 grid((unsigned)G, kPoolSlices);
   if (dtype == BG_BF16)
-    k_pool_partial<__nv_bfloat16><<<grid, kPoolWarps * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), graph_ptr, partial);
+    pool_launch(static_cast<const __nv_bfloat16*>(x), graph_ptr, G, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, partial, stream);
   else if (dtype == BG_F16)
-    k_pool_partial<__half><<<grid, kPoolWarps * 32, 0, stream>>>(static_cast<const __half*>(x), graph_ptr, partial);
+    pool_launch(static_cast<const __half*>(x), graph_ptr, G, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, partial, stream);
   else if (dtype == BG_F32)
-    k_pool_partial<float><<<grid, kPoolWarps * 32, 0, stream>>>(static_cast<const float*>(x), graph_ptr, partial);
+    pool_launch(static_cast<const float*>(x), graph_ptr, G, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, partial, stream);
   else
     return fail(BG_ERR_INVALID, "bg_pool_head: bad dtype");
-  BG_LAUNCH_OK();
-  k_pool_head<<<(unsigned)G, 128, 0, stream>>>(partial, graph_ptr, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out);
   BG_LAUNCH_OK();
   return BG_OK;
 }

@@ -18,13 +18,19 @@ namespace bg {
 constexpr int kPoolSlices = 8;
 constexpr int kPoolWarps = 8;
 
+// pooling variants of the reference's get_pooling_layer (Models/BuckGNN.py:246-307); the
+// super node is the LAST node of each graph (:252, :256-266)
+enum : int { kPoolMean = BG_POOL_MEAN, kPoolMeanNoSuper = BG_POOL_MEAN_NO_SUPER,
+             kPoolSuperOnly = BG_POOL_SUPERNODE_ONLY, kPoolSuperWithPooling = BG_POOL_SUPERNODE_WITH_POOLING };
+
 template <typename T>
 __global__ void __launch_bounds__(kPoolWarps * 32)
-k_pool_partial(const T* __restrict__ x, const int32_t* __restrict__ graph_ptr, float* __restrict__ partial) {
+k_pool_partial(const T* __restrict__ x, const int32_t* __restrict__ graph_ptr, float* __restrict__ partial,
+               int exclude_last) {
   __shared__ float red[kPoolWarps][kHidden];
   const int g = blockIdx.x, slice = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int32_t beg = graph_ptr[g], cnt = graph_ptr[g + 1] - beg;
+  const int32_t beg = graph_ptr[g], cnt = max(graph_ptr[g + 1] - beg - (exclude_last ? 1 : 0), 0);
   const int32_t s_beg = beg + (int32_t)((int64_t)cnt * slice / kPoolSlices);
   const int32_t s_end = beg + (int32_t)((int64_t)cnt * (slice + 1) / kPoolSlices);
   float acc[16];
@@ -55,34 +61,68 @@ k_pool_partial(const T* __restrict__ x, const int32_t* __restrict__ graph_ptr, f
   }
 }
 
+template <typename T> BG_DEVINL float load_as_float(const T* p) {
+  if constexpr (sizeof(T) == 4) return *p; else return (float)*p;
+}
+
+// one CTA per graph: pooled feature (512 or 1024 wide) -> optional MLPPooling Linear+ReLU
+// (Models/BuckGNN.py:568-581) -> decoder Linear(in,128) ReLU Linear(128,64) ReLU Linear(64,out)
+template <typename T>
 __global__ void __launch_bounds__(128)
-k_pool_head(const float* __restrict__ partial, const int32_t* __restrict__ graph_ptr,
+k_pool_head(const T* __restrict__ x, const float* __restrict__ partial, const int32_t* __restrict__ graph_ptr,
+            int mode, const float* __restrict__ pre_w, const float* __restrict__ pre_b,
             const float* __restrict__ w1, const float* __restrict__ b1,
             const float* __restrict__ w2, const float* __restrict__ b2,
             const float* __restrict__ w3, const float* __restrict__ b3, int out_dim,
             float* __restrict__ pred, float* __restrict__ pooled_out) {
-  __shared__ float pooled[kHidden];
+  __shared__ float feat[2 * kHidden];
+  __shared__ float tmp[kHidden];
   __shared__ float h1[128];
   __shared__ float h2[64];
   const int g = blockIdx.x, t = threadIdx.x;
-  const float cnt = (float)max(graph_ptr[g + 1] - graph_ptr[g], 1);
-  for (int c = t; c < kHidden; c += 128) {
-    const float* pp = partial + (size_t)g * kPoolSlices * kHidden + c;
-    float v = pp[0];
+  const int32_t n_g = graph_ptr[g + 1] - graph_ptr[g];
+  const bool no_super = (mode == kPoolMeanNoSuper || mode == kPoolSuperWithPooling);
+  const int in_dim = (mode == kPoolSuperWithPooling) ? 2 * kHidden : kHidden;
+  if (mode != kPoolSuperOnly) {
+    const float cnt = (float)max(n_g - (no_super ? 1 : 0), 1);
+    for (int c = t; c < kHidden; c += 128) {
+      const float* pp = partial + (size_t)g * kPoolSlices * kHidden + c;
+      float v = pp[0];
 #pragma unroll
-    for (int s = 1; s < kPoolSlices; ++s) v += pp[(size_t)s * kHidden];
-    v = v / cnt;
-    pooled[c] = v;
-    if (pooled_out) pooled_out[(size_t)g * kHidden + c] = v;
+      for (int s = 1; s < kPoolSlices; ++s) v += pp[(size_t)s * kHidden];
+      feat[c] = v / cnt;
+    }
+  }
+  if (mode == kPoolSuperOnly || mode == kPoolSuperWithPooling) {
+    const int off = (mode == kPoolSuperOnly) ? 0 : kHidden;
+    const T* srow = x + (size_t)(graph_ptr[g + 1] - 1) * kHidden;
+    for (int c = t; c < kHidden; c += 128) feat[off + c] = (n_g > 0) ? load_as_float(srow + c) : 0.f;
   }
   __syncthreads();
-  {  // 512 -> 128: one output per thread, 4 independent partial sums
-    const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)t * kHidden);
+  if (pre_w) {                                   // pooling_mpl: relu(Linear(512,512)(mean))
+    for (int o = t; o < kHidden; o += 128) {
+      const float4* wr = reinterpret_cast<const float4*>(pre_w + (size_t)o * kHidden);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int k = 0; k < kHidden / 4; ++k) {
+        const float4 w = __ldg(wr + k);
+        a0 = fmaf(w.x, feat[4 * k], a0); a1 = fmaf(w.y, feat[4 * k + 1], a1);
+        a2 = fmaf(w.z, feat[4 * k + 2], a2); a3 = fmaf(w.w, feat[4 * k + 3], a3);
+      }
+      tmp[o] = fmaxf((a0 + a1) + (a2 + a3) + pre_b[o], 0.f);
+    }
+    __syncthreads();
+    for (int c = t; c < kHidden; c += 128) feat[c] = tmp[c];
+    __syncthreads();
+  }
+  if (pooled_out)
+    for (int c = t; c < in_dim; c += 128) pooled_out[(size_t)g * in_dim + c] = feat[c];
+  {  // in_dim -> 128: one output per thread, 4 independent partial sums
+    const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)t * in_dim);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int k = 0; k < kHidden / 4; ++k) {
+    for (int k = 0; k < in_dim / 4; ++k) {
       const float4 w = __ldg(wr + k);
-      a0 = fmaf(w.x, pooled[4 * k], a0); a1 = fmaf(w.y, pooled[4 * k + 1], a1);
-      a2 = fmaf(w.z, pooled[4 * k + 2], a2); a3 = fmaf(w.w, pooled[4 * k + 3], a3);
+      a0 = fmaf(w.x, feat[4 * k], a0); a1 = fmaf(w.y, feat[4 * k + 1], a1);
+      a2 = fmaf(w.z, feat[4 * k + 2], a2); a3 = fmaf(w.w, feat[4 * k + 3], a3);
     }
     h1[t] = fmaxf((a0 + a1) + (a2 + a3) + b1[t], 0.f);
   }

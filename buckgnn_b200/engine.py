@@ -292,16 +292,19 @@ def sage_layer(x: Activation, agg: Activation, out: Activation, idx: GraphIndex,
 
 
 def pool_head(x: Activation, idx: GraphIndex, dec: Dict[str, torch.Tensor], out_dim: int,
-              want_pooled: bool = False):
-    """global_mean_pool + decoder (Models/BuckGNN.py:274, 515-516)."""
+              want_pooled: bool = False, pooling: str = "mean", pre: Optional[Dict[str, torch.Tensor]] = None):
+    """get_pooling_layer + decoder (Models/BuckGNN.py:246-307, 515-516)."""
     dev = x.data.device
     g = idx.n_graphs
+    mode = capi.POOL_MODES[pooling]
+    in_dim = 1024 if pooling == "supernode_with_pooling" else 512
     pred = torch.empty((g, out_dim), dtype=torch.float32, device=dev)
-    pooled = torch.empty((g, 512), dtype=torch.float32, device=dev) if want_pooled else None
+    pooled = torch.empty((g, in_dim), dtype=torch.float32, device=dev) if want_pooled else None
     ws_bytes = capi.pool_workspace_bytes(g)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with TIMERS.span("pool_head"):
-        capi.pool_head(x.data.data_ptr(), x.code, idx.n_nodes, idx.graph_ptr.data_ptr(), g,
+        capi.pool_head(x.data.data_ptr(), x.code, idx.n_nodes, idx.graph_ptr.data_ptr(), g, mode,
+                       _p(pre["w"]) if pre else None, _p(pre["b"]) if pre else None,
                        dec["w1"].data_ptr(), dec["b1"].data_ptr(), dec["w2"].data_ptr(), dec["b2"].data_ptr(),
                        dec["w3"].data_ptr(), dec["b3"].data_ptr(), out_dim, pred.data_ptr(), _p(pooled),
                        ws.data_ptr(), ws_bytes, _stream())

@@ -173,6 +173,8 @@ class BuckGNN(nn.Module):
         dec = self.decoder
         packs["dec"] = {"w1": f32(dec[0].weight), "b1": f32(dec[0].bias), "w2": f32(dec[2].weight),
                         "b2": f32(dec[2].bias), "w3": f32(dec[4].weight), "b3": f32(dec[4].bias)}
+        mpl = self.pooling_mpl.mlp[0]
+        packs["pool_mlp"] = {"w": f32(mpl.weight), "b": f32(mpl.bias)}
         layers, seen = [], {}
         for conv, bn in self._sage_layers():
             if id(conv) not in seen:
@@ -207,10 +209,8 @@ class BuckGNN(nn.Module):
             if "static" in self.prediction_type or "mode_shape" in self.prediction_type:
                 raise NotImplementedError("buckgnn_b200: node-level heads are not built yet")
             raise ValueError(f"Unknown prediction type: {self.prediction_type}")
-        if self.pooling_layer != "mean":
-            if self.pooling_layer in ("mean_no_super", "supernode_only", "supernode_with_pooling", "mlp",
+        if self.pooling_layer not in ("mean", "mean_no_super", "supernode_only", "supernode_with_pooling", "mlp",
                                       "mlp_no_super"):
-                raise NotImplementedError(f"buckgnn_b200: pooling_layer={self.pooling_layer!r} is not built yet")
             if self.pooling_layer == "hybrid":
                 raise AttributeError("'BuckGNN' object has no attribute 'hybrid_pooling'")   # reference :188,276
             raise ValueError(f"Unknown pooling layer: {self.pooling_layer}")
@@ -247,5 +247,7 @@ class BuckGNN(nn.Module):
                 engine.sage_layer(cur, agg, nxt, idx, layer, aggr=aggr, normalize=True, relu=True,
                                   residual=(0 < i < L - 1), cta_group=cg)
                 cur, nxt = nxt, cur
-        pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim)               # reference :515-516
+        pre = packs["pool_mlp"] if self.pooling_layer in ("mlp", "mlp_no_super") else None
+        pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim, pooling=self.pooling_layer,
+                                   pre=pre)                                                # reference :515-516
         return pred

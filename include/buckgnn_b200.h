@@ -146,15 +146,23 @@ int bg_gemm512(const bg_gemm_segment* segments_host, int32_t n_segments, int64_t
                int a_dtype, int b_dtype, const bg_epilogue* epilogue_host,
                void* out, int out_dtype, int64_t ldo, int cta_group, void* stream);
 
-/* ------------------------------------------------------------------ K4: mean pool + regression head
- * Replaces `global_mean_pool(x, batch)` + `decoder(pooled).squeeze()`
- * (Models/BuckGNN.py:274, 515-516):
- *    pooled[g] = sum_{i in graph g} x[i] / max(count_g, 1);   pred[g] = MLP(pooled[g])
- * decoder = Linear(512,128) ReLU Linear(128,64) ReLU Linear(64,out_dim), f32 weights.
- * x [N,512] of `dtype`; pred [G, out_dim] f32; pooled_out [G,512] f32 optional (NULL to skip).
+/* ------------------------------------------------------------------ K4: pooling + regression head
+ * Replaces `get_pooling_layer` + `decoder(pooled).squeeze()` (Models/BuckGNN.py:246-307, 515-516):
+ *    BG_POOL_MEAN                   pooled[g] = sum_{i in g} x[i] / max(count_g, 1)          (:274)
+ *    BG_POOL_MEAN_NO_SUPER          same over all nodes but the graph's last (super) node    (:277-282)
+ *    BG_POOL_SUPERNODE_ONLY         pooled[g] = x[last node of g]                            (:283-284)
+ *    BG_POOL_SUPERNODE_WITH_POOLING cat[mean_no_super, super]  (1024 wide)                   (:285-293)
+ * pre_w/pre_b [512,512]/[512] non-NULL: the `MLPPooling` Linear+ReLU on the mean (:294-305, 568-581);
+ * allowed with the two mean modes only.  Then decoder Linear(in,128) ReLU Linear(128,64) ReLU
+ * Linear(64,out_dim), in = 1024 for SUPERNODE_WITH_POOLING else 512; all weights f32, nn.Linear layout.
+ * x [N,512] of `dtype`; pred [G,out_dim] f32; pooled_out [G,in] f32 optional (NULL to skip).
  * workspace from bg_pool_workspace_bytes(G). */
+typedef enum bg_pool_mode {
+  BG_POOL_MEAN = 0, BG_POOL_MEAN_NO_SUPER = 1, BG_POOL_SUPERNODE_ONLY = 2, BG_POOL_SUPERNODE_WITH_POOLING = 3
+} bg_pool_mode;
 int bg_pool_workspace_bytes(int64_t n_graphs, size_t* bytes_host);
 int bg_pool_head(const void* x, int dtype, int64_t n_nodes, const int32_t* graph_ptr, int64_t n_graphs,
+                 int pool_mode, const float* pre_w, const float* pre_b,
                  const float* w1, const float* b1, const float* w2, const float* b2,
                  const float* w3, const float* b3, int32_t out_dim,
                  float* pred, float* pooled_out,

@@ -66,6 +66,29 @@ def test_other_graphsage_variants(name):
     _assert_rel(got, want, 1e-3)
 
 
+@pytest.mark.parametrize("pool", ["mean_no_super", "supernode_only", "supernode_with_pooling", "mlp",
+                                  "mlp_no_super"])
+def test_pooling_variants(pool):
+    """reference get_pooling_layer variants (Models/BuckGNN.py:246-307)"""
+    torch.manual_seed(1)
+    cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=3,
+               pooling_layer=pool, model_name="GraphSage_meanAggr")
+    ref = OracleBuckGNN(**cfg).eval()
+    randomize_bn_stats(ref, realistic=True)
+    ours = BuckGNN(**cfg, precision="tf32")
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV).eval()
+    got, want = _run(ref, ours, make_batch(3, nx=11, ny=9))
+    assert got.shape == want.shape == (3,)
+    _assert_rel(got, want, 1e-3)
+    one = make_batch(1, nx=8, ny=7)
+    with torch.no_grad():
+        w1, _ = ref(one.x, one.edge_index, one.edge_attr, None)
+        g1, _ = ours(one.x.to(DEV), one.edge_index.to(DEV), one.edge_attr.to(DEV), None)
+    assert g1.dim() == 0
+    _assert_rel(g1.cpu(), w1, 1e-3)
+
+
 def test_single_graph_batch_none_gives_0dim():
     ref, ours = _pair("GraphSage_meanAggr", "tf32", layers=3)
     b = make_batch(1, nx=10, ny=10)

@@ -216,3 +216,10 @@ def test_pool_head_matches_oracle(precision):
     pred, pooled = engine.pool_head(xa, idx, packs, 1, want_pooled=True)
     torch.testing.assert_close(pooled.cpu(), pooled_want, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(pred.cpu(), want, rtol=1e-4, atol=1e-5)
+    # super-node variants: the last node of each graph
+    last = b.ptr[1:] - 1
+    keep = torch.ones(n, dtype=torch.bool); keep[last] = False
+    _, pooled = engine.pool_head(xa, idx, packs, 1, want_pooled=True, pooling="supernode_only")
+    torch.testing.assert_close(pooled.cpu(), x[last], rtol=0, atol=0)
+    _, pooled = engine.pool_head(xa, idx, packs, 1, want_pooled=True, pooling="mean_no_super")
+    torch.testing.assert_close(pooled.cpu(), O.global_mean_pool(x[keep], b.batch[keep]), rtol=1e-5, atol=1e-6)
