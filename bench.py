@@ -211,6 +211,12 @@ def run_b200(args):
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps    # host wall clock: includes every copy and sync
     barrier()
+    # diagnostic: same loop without the H2D copies (resident batch, pred.cpu() every step)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fwd(resident).cpu()
+    sync_only_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    barrier()
 
     # ---- max over ranks
     if world > 1:
@@ -257,6 +263,7 @@ def run_b200(args):
                        "parity_rel_err_vs_oracle_sample": rel_err},
             "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(out.numel() * out.element_size()),
+                    "ms_per_step_without_h2d": sync_only_ms,
                     "how": "pinned host batch -> DevicePrefetcher (H2D of step i+1 on a copy stream during "
                            "step i) -> model(...) -> pred.cpu(); host wall clock over the timed steps"},
             "gpu_launches": engine.LAUNCHES_PER_FORWARD(L) * args.steps,

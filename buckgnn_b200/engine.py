@@ -128,49 +128,85 @@ class GraphIndex:
     n_graphs: int
 
 
+_INFO_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+class PendingGraphIndex:
+    """K1 in flight.  `begin_graph_index` enqueues the CSR build (and the `batch` scan) on the
+    current stream and starts reading the 4 result words (error flag, hub-row count, graph count,
+    sortedness) back on a side stream; `finish()` blocks only on that read -- kernels the caller
+    enqueued in between (the node encoder) keep the GPU busy meanwhile.  This is the one
+    host<->device sync of a forward, the same kind PyG's `batch.max()+1` does."""
+
+    def __init__(self, edge_index, batch, n_nodes, key_row):
+        _require_cuda(edge_index, "edge_index")
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise ValueError("edge_index must be an int64 tensor of shape [2, E]")
+        self.edge_index = edge_index.contiguous()
+        dev = edge_index.device
+        self.E, self.N = edge_index.shape[1], int(n_nodes)
+        E, N = self.E, self.N
+        s = _stream()
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.rowptr = torch.empty(N + 1, **i32)
+        self.col = torch.empty(max(E, 1), **i32)
+        self.perm = torch.empty(max(E, 1), **i32)
+        self.big_rows = torch.empty(capi.csr_max_big_rows(E), **i32)
+        self.info = torch.zeros(4, **i32)
+        ws_bytes = capi.csr_workspace_bytes(N, E)
+        self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with TIMERS.span("csr_build"):
+            capi.csr_build(self.edge_index.data_ptr(), E, N, key_row, self.rowptr.data_ptr(), self.col.data_ptr(),
+                           self.perm.data_ptr(), self.big_rows.data_ptr(), self.info.data_ptr(),
+                           self._ws.data_ptr(), ws_bytes, s)
+        self.batch = None
+        if batch is not None:
+            _require_cuda(batch, "batch")
+            if batch.dtype != torch.int64 or batch.dim() != 1 or batch.shape[0] != N:
+                raise ValueError("batch must be an int64 tensor of shape [N]")
+            self.batch = batch.contiguous()
+            capi.batch_info(self.batch.data_ptr(), N, self.info[2:].data_ptr(), s)
+        ready = torch.cuda.Event()
+        ready.record()
+        side = _INFO_STREAMS.get(dev.index)
+        if side is None:
+            side = _INFO_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+        self._host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+        self._done = torch.cuda.Event()
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            self._host.copy_(self.info, non_blocking=True)
+            self._done.record(side)
+
+    def finish(self) -> "GraphIndex":
+        self._done.synchronize()                      # the one sync of the forward
+        host = self._host.tolist()
+        N, E = self.N, self.E
+        i32 = dict(dtype=torch.int32, device=self.edge_index.device)
+        if host[0] & 1:
+            raise IndexError("edge_index contains node ids outside [0, num_nodes)")
+        n_big = host[1]
+        if self.batch is None:
+            n_graphs = 1
+            graph_ptr = torch.tensor([0, N], **i32)
+        else:
+            if host[3]:
+                raise ValueError("buckgnn_b200 needs a sorted, non-negative `batch` vector (PyG DataLoader order)")
+            n_graphs = host[2] if N > 0 else 0
+            graph_ptr = torch.empty(n_graphs + 1, **i32)
+            capi.graph_ptr_build(self.batch.data_ptr(), N, n_graphs, graph_ptr.data_ptr(), _stream())
+        return GraphIndex(N, E, self.rowptr, self.col, self.perm, self.big_rows, n_big, graph_ptr, n_graphs)
+
+
+def begin_graph_index(edge_index: torch.Tensor, batch: Optional[torch.Tensor], n_nodes: int,
+                      key_row: int = 1) -> PendingGraphIndex:
+    return PendingGraphIndex(edge_index, batch, n_nodes, key_row)
+
+
 def build_graph_index(edge_index: torch.Tensor, batch: Optional[torch.Tensor], n_nodes: int,
                       key_row: int = 1) -> GraphIndex:
-    """K1.  One small device->host read (4 ints: error flag, hub-row count, graph count,
-    sortedness) -- the same kind of sync PyG's `batch.max()+1` does."""
-    _require_cuda(edge_index, "edge_index")
-    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
-        raise ValueError("edge_index must be an int64 tensor of shape [2, E]")
-    edge_index = edge_index.contiguous()
-    dev = edge_index.device
-    E = edge_index.shape[1]
-    N = int(n_nodes)
-    s = _stream()
-    i32 = dict(dtype=torch.int32, device=dev)
-    rowptr = torch.empty(N + 1, **i32)
-    col = torch.empty(max(E, 1), **i32)
-    perm = torch.empty(max(E, 1), **i32)
-    big_rows = torch.empty(capi.csr_max_big_rows(E), **i32)
-    info = torch.zeros(4, **i32)
-    ws_bytes = capi.csr_workspace_bytes(N, E)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    with TIMERS.span("csr_build"):
-        capi.csr_build(edge_index.data_ptr(), E, N, key_row, rowptr.data_ptr(), col.data_ptr(), perm.data_ptr(),
-                       big_rows.data_ptr(), info.data_ptr(), ws.data_ptr(), ws_bytes, s)
-    if batch is not None:
-        _require_cuda(batch, "batch")
-        if batch.dtype != torch.int64 or batch.dim() != 1 or batch.shape[0] != N:
-            raise ValueError("batch must be an int64 tensor of shape [N]")
-        batch = batch.contiguous()
-        capi.batch_info(batch.data_ptr(), N, info[2:].data_ptr(), s)
-    host = info.cpu().tolist()                       # the one sync of the forward
-    if host[0] & 1:
-        raise IndexError("edge_index contains node ids outside [0, num_nodes)")
-    n_big = host[1]
-    if batch is None:
-        n_graphs = 1
-        graph_ptr = torch.tensor([0, N], **i32)
-    else:
-        if host[3]:
-            raise ValueError("buckgnn_b200 needs a sorted, non-negative `batch` vector (PyG DataLoader order)")
-        n_graphs = host[2] if N > 0 else 0
-        graph_ptr = torch.empty(n_graphs + 1, **i32)
-        capi.graph_ptr_build(batch.data_ptr(), N, n_graphs, graph_ptr.data_ptr(), s)
-    return GraphIndex(N, E, rowptr, col, perm, big_rows, n_big, graph_ptr, n_graphs)
+    """K1, blocking form."""
+    return begin_graph_index(edge_index, batch, n_nodes, key_row).finish()
 
 
 # ----------------------------------------------------------------------------- packed weights

@@ -218,25 +218,35 @@ class BuckGNN(nn.Module):
             pred = self._forward_cuda(x, edge_index, batch)
         return pred.squeeze(), batch
 
-    def _graph_index(self, edge_index, batch, n):
+    def _begin_graph_index(self, edge_index, batch, n):
+        """Returns an object with .finish() -> GraphIndex (cached index when cache_index is on)."""
         if self.cache_index:
             key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape),
                    None if batch is None else (batch.data_ptr(), batch._version), n)
             if self._index_cache is not None and self._index_cache[0] == key:
-                return self._index_cache[1]
-            idx = engine.build_graph_index(edge_index, batch, n)
-            self._index_cache = (key, idx)
-            return idx
-        return engine.build_graph_index(edge_index, batch, n)
+                cached = self._index_cache[1]
+                return type("Cached", (), {"finish": staticmethod(lambda: cached)})
+            pending = engine.begin_graph_index(edge_index, batch, n)
+            outer = self
+
+            class _Fill:
+                @staticmethod
+                def finish():
+                    idx = pending.finish()
+                    outer._index_cache = (key, idx)
+                    return idx
+            return _Fill
+        return engine.begin_graph_index(edge_index, batch, n)
 
     def _forward_cuda(self, x, edge_index, batch):
         packs = self._packed()
         prec, cg = self.precision, self.cta_group
         x = x.detach().to(torch.float32).contiguous()
         n = x.shape[0]
-        idx = self._graph_index(edge_index, batch, n)
+        pending = self._begin_graph_index(edge_index, batch, n)       # K1 enqueued, result read-back in flight
         cur = Activation(n, 512, prec, x.device)
         engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg)          # reference :323
+        idx = pending.finish()                                        # host sync hidden behind the encoder
         layers = packs["layers"]
         if layers:
             nxt = Activation(n, 512, prec, x.device)
