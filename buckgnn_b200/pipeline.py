@@ -29,6 +29,8 @@ class DevicePrefetcher:
         self.slots = [None, None]
         self.copied = [torch.cuda.Event(), torch.cuda.Event()]
         self.released = [torch.cuda.Event(), torch.cuda.Event()]
+        self.copy_events = []          # (start, stop) per staged batch when `time_copies` is set
+        self.time_copies = False
 
     def _stage(self, host: PlateBatch, k: int) -> PlateBatch:
         slot = self.slots[k]
@@ -41,8 +43,15 @@ class DevicePrefetcher:
                                   host.num_graphs)
                 self.slots[k] = slot
             slot.num_graphs = host.num_graphs
+            if self.time_copies:
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record(self.copy_stream)
             for f in fields:
                 getattr(slot, f).copy_(getattr(host, f), non_blocking=True)
+            if self.time_copies:
+                t1 = torch.cuda.Event(enable_timing=True)
+                t1.record(self.copy_stream)
+                self.copy_events.append((t0, t1))
             self.copied[k].record(self.copy_stream)
         return slot
 
