@@ -66,6 +66,27 @@ __global__ void k_split_tf32(const float* __restrict__ src, float* __restrict__ 
   }
 }
 
+// warp per row: the row's CSR slots get the row id; every slot also gets its own index
+__global__ void k_expand_rowptr(const int32_t* __restrict__ rowptr, int64_t n_rows, int32_t* __restrict__ row_of,
+                                int32_t* __restrict__ iota) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n_rows; r += n_warps) {
+    const int32_t b = rowptr[r], e = rowptr[r + 1];
+    for (int32_t i = b + lane; i < e; i += 32) { row_of[i] = (int32_t)r; iota[i] = i; }
+  }
+}
+
+template <typename T>
+__global__ void k_add(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c, T* __restrict__ out, int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = (float)a[i] + (float)b[i];
+    if (c) v += (float)c[i];
+    if constexpr (sizeof(T) == 2) out[i] = Pack16<T>::one(v); else out[i] = v;
+  }
+}
+
 static inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
   int64_t b = ceil_div64(n > 0 ? n : 1, threads);
@@ -216,7 +237,7 @@ int bg_graph_ptr_build(const int64_t* batch, int64_t N, int64_t G, int32_t* grap
 
 // ------------------------------------------------------------------ K5 front
 int bg_encoder_front(const float* x, int64_t N, int32_t F, const float* w1, const float* b1,
-                     const float* w2, const float* b2, void* out, int out_dtype, void* stream_) {
+                     const float* w2, const float* b2, const int32_t* row_gather, void* out, int out_dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (N < 0 || F <= 0 || F > kEncMaxF) return fail(BG_ERR_UNSUPPORTED, "bg_encoder_front: need 0 < n_features <= 32");
   if (N == 0) return BG_OK;
@@ -227,7 +248,7 @@ int bg_encoder_front(const float* x, int64_t N, int32_t F, const float* w1, cons
   {                                                                                                            \
     static bool set = false;                                                                                   \
     if (!set) { BG_CUDA_OK(cudaFuncSetAttribute(k_encoder_front<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; } \
-    k_encoder_front<T><<<grid, kEncThreads, smem, stream>>>(x, N, F, w1, b1, w2, b2, static_cast<T*>(out));    \
+    k_encoder_front<T><<<grid, kEncThreads, smem, stream>>>(x, N, F, w1, b1, w2, b2, row_gather, static_cast<T*>(out)); \
   }
   if (out_dtype == BG_BF16) BG_ENC_CASE(__nv_bfloat16)
   else if (out_dtype == BG_F16) BG_ENC_CASE(__half)
@@ -309,7 +330,7 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
   p.a_fmt = (uint32_t)a_fmt; p.b_fmt = (uint32_t)b_fmt;
   p.n_tiles = (int32_t)ceil_div64(m, kTileM * cta_group);
   p.m = m;
-  for (int i = 0; i < kHidden; ++i) { p.bias[i] = 0.f; p.scale[i] = 1.f; p.shift[i] = 0.f; }
+  for (int i = 0; i < kHidden; ++i) { p.bias[i] = 0.f; p.bias2[i] = 0.f; p.scale[i] = 1.f; p.shift[i] = 0.f; }
   const uint32_t o_fmt = (uint32_t)umma_format_of(out_dtype);
   if (epi) {
     if (epi->residual && (!aligned16(epi->residual) || (epi->ldr * osz) % 16 != 0 || epi->ldr < kHidden))
@@ -321,6 +342,21 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
       memcpy(p.shift, epi->bn_shift_host, sizeof(float) * kHidden);
     }
     p.normalize = epi->normalize; p.relu = epi->relu;
+    if (epi->bias2_host) {
+      if (!epi->gate_rowptr) return fail(BG_ERR_INVALID, "bg_gemm512: bias2 needs gate_rowptr");
+      memcpy(p.bias2, epi->bias2_host, sizeof(float) * kHidden);
+      p.gate_rowptr = epi->gate_rowptr;
+    }
+    for (int k = 0; k < 2; ++k) {
+      if (!epi->gather[k]) break;
+      if (!epi->gather_idx[k] || !aligned16(epi->gather[k]) || (epi->gather_ld * osz) % 16 != 0 || epi->gather_ld < kHidden)
+        return fail(BG_ERR_INVALID, "bg_gemm512: bad gather operand");
+      p.gather[k] = epi->gather[k]; p.gidx[k] = epi->gather_idx[k];
+      p.n_gather = k + 1;
+    }
+    p.gather_ld = epi->gather_ld;
+    if (p.n_gather > 0 && (epi->normalize || epi->residual))
+      return fail(BG_ERR_UNSUPPORTED, "bg_gemm512: gathered addends cannot be combined with normalize or residual");
     if (epi->residual) {
       p.has_res = 1;
       if (make_operand_map(&p.res_map, epi->residual, m, kHidden, epi->ldr, o_fmt) != BG_OK)
@@ -369,6 +405,30 @@ int bg_pool_head(const void* x, int dtype, int64_t N, const int32_t* graph_ptr, 
     pool_launch(static_cast<const float*>(x), graph_ptr, G, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, partial, stream);
   else
     return fail(BG_ERR_INVALID, "bg_pool_head: bad dtype");
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+// ------------------------------------------------------------------ EA-GNN helpers
+int bg_expand_rowptr(const int32_t* rowptr, int64_t n_rows, int64_t n_entries, int32_t* row_of, int32_t* iota, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_rows < 0 || n_entries < 0 || (n_rows > 0 && !rowptr) || (n_entries > 0 && (!row_of || !iota)))
+    return fail(BG_ERR_INVALID, "bg_expand_rowptr: bad argument");
+  if (n_rows == 0 || n_entries == 0) return BG_OK;
+  k_expand_rowptr<<<grid_for(n_rows * 32, 256, sm_count() * 32), 256, 0, stream>>>(rowptr, n_rows, row_of, iota);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_add(const void* a, const void* b, const void* c, void* out, int dtype, int64_t n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n < 0 || (n > 0 && (!a || !b || !out))) return fail(BG_ERR_INVALID, "bg_add: bad argument");
+  if (n == 0) return BG_OK;
+  const unsigned grid = grid_for(n, 256, sm_count() * 16);
+  if (dtype == BG_BF16) k_add<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<const __nv_bfloat16*>(c), static_cast<__nv_bfloat16*>(out), n);
+  else if (dtype == BG_F16) k_add<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<const __half*>(c), static_cast<__half*>(out), n);
+  else if (dtype == BG_F32) k_add<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(a), static_cast<const float*>(b), static_cast<const float*>(c), static_cast<float*>(out), n);
+  else return fail(BG_ERR_INVALID, "bg_add: bad dtype");
   BG_LAUNCH_OK();
   return BG_OK;
 }

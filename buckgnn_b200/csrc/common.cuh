@@ -93,6 +93,10 @@ template <> struct Pack16<__nv_bfloat16> {
   }
   static BG_DEVINL uint32_t pack(float a, float b) { return pack_bf16(a, b); }
   static BG_DEVINL __nv_bfloat16 one(float a) { return __float2bfloat16_rn(a); }
+  static BG_DEVINL uint32_t hadd2(uint32_t a, uint32_t b) {          // packed pair + packed pair
+    __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
 };
 template <> struct Pack16<__half> {
   static BG_DEVINL float lo(uint32_t u) {
@@ -111,6 +115,10 @@ template <> struct Pack16<__half> {
   }
   static BG_DEVINL uint32_t pack(float a, float b) { return pack_f16(a, b); }
   static BG_DEVINL __half one(float a) { return __float2half_rn(a); }
+  static BG_DEVINL uint32_t hadd2(uint32_t a, uint32_t b) {
+    __half2 r = __hadd2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
 };
 
 // ------------------------------------------------------------------ watchdog

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(kEncThreads)
 k_encoder_front(const float* __restrict__ x, int64_t N, int F,
                 const float* __restrict__ w1, const float* __restrict__ b1,
                 const float* __restrict__ w2, const float* __restrict__ b2,
-                TOut* __restrict__ out) {
+                const int32_t* __restrict__ row_gather, TOut* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char enc_smem_raw[];
   EncoderSmem& s = *reinterpret_cast<EncoderSmem*>(enc_smem_raw);
   const int tid = threadIdx.x;
@@ -48,7 +48,12 @@ k_encoder_front(const float* __restrict__ x, int64_t N, int F,
     // stage x tile transposed: xt[k][m]
     for (int i = tid; i < kEncRows * F; i += kEncThreads) {
       int m = i / F, k = i % F;
-      s.xt[k][m] = (m0 + m < N) ? x[(m0 + m) * F + k] : 0.f;
+      float val = 0.f;
+      if (m0 + m < N) {
+        const int64_t src = row_gather ? (int64_t)row_gather[m0 + m] : (m0 + m);
+        val = x[src * F + k];
+      }
+      s.xt[k][m] = val;
     }
     __syncthreads();
     {  // layer 1: thread -> rows ty*4..+4, cols tx*4..+4

@@ -65,8 +65,14 @@ struct alignas(64) GemmParams {
   uint32_t a_fmt, b_fmt;            // UMMA operand formats: 0 f16, 1 bf16, 2 tf32
   int32_t n_tiles;                  // row tiles of 128*cg rows
   int32_t normalize, relu, has_res;
+  int32_t n_gather;                 // 0..2 gathered pre-activation addends: v += G_k[gidx_k[m], :]
   int64_t m;
+  const void* gather[2];            // [*, 512] row-major matrices of the output dtype, ld = gather_ld
+  const int32_t* gidx[2];           // [M] row index into gather[k]
+  int64_t gather_ld;
+  const int32_t* gate_rowptr;       // optional CSR rowptr [M+1]: bias2 is added only to rows with >= 1 entry
   float bias[kHidden];              // epilogue vectors by value -> constant bank, broadcast reads
+  float bias2[kHidden];             // gated bias (0 when unused)
   float scale[kHidden];             // 1 when there is no BN
   float shift[kHidden];             // 0 when there is no BN
 };
@@ -141,6 +147,13 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
   uint32_t it = 0, seq = 0;                                     // tiles done; staging chunks done (this group)
   BG_PROF_DECL
   for (int tile = cx.tile0; tile < p.n_tiles; tile += cx.tile_stride, ++it) {
+    const int64_t m_row = (int64_t)tile * (kTileM * kCg) + (int64_t)cx.rank * kTileM + row;
+    const bool row_valid = m_row < p.m;
+    float gate = 0.f;
+    if (p.gate_rowptr && row_valid) gate = (p.gate_rowptr[m_row + 1] > p.gate_rowptr[m_row]) ? 1.f : 0.f;
+    int32_t gi0 = 0, gi1 = 0;
+    if (p.n_gather > 0 && row_valid) gi0 = p.gidx[0][m_row];
+    if (p.n_gather > 1 && row_valid) gi1 = p.gidx[1][m_row];
     BG_PROF_T0();
     mbar_wait(cx.tmem_full_bar, it & 1u, kTagTmemFull);
     BG_PROF_ADD(_pacc_a);
@@ -156,8 +169,8 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
       auto consume = [&](const uint32_t (&r)[16], int c16) {    // c16: index of the 16-column block
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float a = __uint_as_float(r[2 * i]) + p.bias[cb + c16 * 16 + 2 * i];
-          const float b = __uint_as_float(r[2 * i + 1]) + p.bias[cb + c16 * 16 + 2 * i + 1];
+          const float a = __uint_as_float(r[2 * i]) + fmaf(gate, p.bias2[cb + c16 * 16 + 2 * i], p.bias[cb + c16 * 16 + 2 * i]);
+          const float b = __uint_as_float(r[2 * i + 1]) + fmaf(gate, p.bias2[cb + c16 * 16 + 2 * i + 1], p.bias[cb + c16 * 16 + 2 * i + 1]);
           ss = fmaf(a, a, ss);
           ss = fmaf(b, b, ss);
           if constexpr (kOut16) stash[c16 * 8 + i] = Pack16<TOut>::pack(a, b);
@@ -208,6 +221,45 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
         }
       }
       mbar_wait(epi_ready_bar(cx.ring_bars, kG, sl), (seq >> 1) & 1u, kTagEpiReady);   // tile free / skip rows landed
+      if (p.n_gather > 0) {
+        // software gather: this warp fetches the 128-byte chunk of G_k[gidx_k[row]] for its own 32 rows with
+        // coalesced loads (8 lanes per row) and parks the sum in the staging tile, swizzled like a TMA tile
+        const int r4 = lane >> 3, piece = lane & 7;
+        const size_t col_off = (size_t)(cb + ch * kChunkCols) * sizeof(TOut) + (size_t)piece * 16;
+        const size_t ldb = (size_t)p.gather_ld * sizeof(TOut);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint4 g0[4], g1[4];
+#pragma unroll
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int rr = (half * 4 + t4) * 4 + r4;
+            const int32_t n0 = __shfl_sync(0xffffffffu, gi0, rr);
+            g0[t4] = ldg_v4(reinterpret_cast<const char*>(p.gather[0]) + (size_t)n0 * ldb + col_off);
+            if (p.n_gather > 1) {
+              const int32_t n1 = __shfl_sync(0xffffffffu, gi1, rr);
+              g1[t4] = ldg_v4(reinterpret_cast<const char*>(p.gather[1]) + (size_t)n1 * ldb + col_off);
+            }
+          }
+#pragma unroll
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int rr = q * 32 + (half * 4 + t4) * 4 + r4;
+            uint4 o = g0[t4];
+            if (p.n_gather > 1) {
+              if constexpr (kOut16) {
+                o.x = Pack16<TOut>::hadd2(o.x, g1[t4].x); o.y = Pack16<TOut>::hadd2(o.y, g1[t4].y);
+                o.z = Pack16<TOut>::hadd2(o.z, g1[t4].z); o.w = Pack16<TOut>::hadd2(o.w, g1[t4].w);
+              } else {
+                o.x = __float_as_uint(__uint_as_float(o.x) + __uint_as_float(g1[t4].x));
+                o.y = __float_as_uint(__uint_as_float(o.y) + __uint_as_float(g1[t4].y));
+                o.z = __float_as_uint(__uint_as_float(o.z) + __uint_as_float(g1[t4].z));
+                o.w = __float_as_uint(__uint_as_float(o.w) + __uint_as_float(g1[t4].w));
+              }
+            }
+            sts_v4(slot + (uint32_t)rr * 128u + (((uint32_t)piece ^ (uint32_t)(rr & 7)) << 4), o);
+          }
+        }
+        __syncwarp();
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {                             // 16-byte pieces of this thread's 128-byte row
         const uint32_t addr = slot + row_off + (((uint32_t)j ^ sw) << 4);
@@ -220,9 +272,25 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
             const uint32_t u = stash[ch * 32 + j * 4 + (e >> 1)];
             a = (e & 1) ? Pack16<TOut>::hi(u) : Pack16<TOut>::lo(u);
           } else {
-            a = __uint_as_float(r[j * 4 + e]) + p.bias[c];
+            a = __uint_as_float(r[j * 4 + e]) + fmaf(gate, p.bias2[c], p.bias[c]);
           }
-          a = fmaf(a * inv, p.scale[c], p.shift[c]);
+          v[e] = a;
+        }
+        if (p.n_gather > 0) {                                   // gathered pre-activation addends, staged in the tile
+          const uint4 gg = lds_v4(addr);
+          const uint32_t gu[4] = {gg.x, gg.y, gg.z, gg.w};
+          if constexpr (kOut16) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) Pack16<TOut>::add2(v[2 * e], v[2 * e + 1], gu[e]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] += __uint_as_float(gu[e]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < kPer; ++e) {
+          const int c = cb + ch * kChunkCols + j * kPer + e;
+          float a = fmaf(v[e] * inv, p.scale[c], p.shift[c]);
           if (p.relu) a = fmaxf(a, 0.f);
           v[e] = a;
         }

@@ -303,13 +303,16 @@ def aggregate(x: Activation, out: Activation, idx: GraphIndex, aggr: str) -> Non
 
 
 def encoder_forward(x: torch.Tensor, enc_w: Dict[str, torch.Tensor], w3: LinearPack, precision: str,
-                    out: Activation, cta_group: int) -> None:
-    """node_encoder (Models/BuckGNN.py:68-74): two fp32 CUDA-core layers, then 128->512 on tcgen05."""
-    n, f = x.shape
+                    out: Activation, cta_group: int, row_gather: Optional[torch.Tensor] = None) -> None:
+    """node_encoder / edge_encoder (Models/BuckGNN.py:68-82): two fp32 CUDA-core layers, then 128->512 on
+    tcgen05.  `row_gather` [n] int32 reads input row row_gather[i] for output row i."""
+    f = x.shape[1]
+    n = x.shape[0] if row_gather is None else row_gather.shape[0]
     h = Activation(n, 128, precision, x.device)
     with TIMERS.span("encoder_front"):
         capi.encoder_front(x.data_ptr(), n, f, enc_w["w1"].data_ptr(), enc_w["b1"].data_ptr(),
-                           enc_w["w2"].data_ptr(), enc_w["b2"].data_ptr(), h.data.data_ptr(), h.code, _stream())
+                           enc_w["w2"].data_ptr(), enc_w["b2"].data_ptr(), h.data.data_ptr(), h.code, _stream(),
+                           row_gather=_p(row_gather))
     h.refresh_split()
     with TIMERS.span("encoder_gemm"):
         gemm512(_segments(h, w3), n, precision, out, cta_group=cta_group, bias=enc_w["b3_host"].data_ptr())
@@ -345,3 +348,126 @@ def pool_head(x: Activation, idx: GraphIndex, dec: Dict[str, torch.Tensor], out_
                        dec["w3"].data_ptr(), dec["b3"].data_ptr(), out_dim, pred.data_ptr(), _p(pooled),
                        ws.data_ptr(), ws_bytes, _stream())
     return pred, pooled
+
+
+# ----------------------------------------------------------------------------- EA-GNN (GraphNetBlock)
+@dataclass
+class GNBlockPack:
+    """Operand-format weights of one reference `GraphNetBlock` (Models/BuckGNN.py:528-566), split and
+    composed so that concatenations never materialise and two Linears fold away:
+
+      edge_mlp L1   cat[x[row], x[col], e] W1^T  =  (x W1a^T)[row] + (x W1b^T)[col] + e W1c^T
+      phi L1        cat[x[col], e1] Wp1^T with e1 = h_e W2^T + b2
+                    =  (x Wp1a^T)[col] + h_e (Wp1b W2)^T + (Wp1b b2 + bp1)          (edge_mlp L2 folded in)
+      scatter_mean then phi L2 then gamma L1 (all linear in between):
+                    cat[x, agg] Wg1^T = x Wg1a^T + mean(h_m) (Wg1b Wp2)^T + gate (Wg1b bp2) + bg1
+    """
+    w1a: LinearPack; w1b: LinearPack; w1c: LinearPack; b1: torch.Tensor
+    w2: LinearPack; b2: torch.Tensor
+    wp1a: LinearPack; w3c: LinearPack; b3c: torch.Tensor
+    wg1a: LinearPack; wgc: LinearPack; bg1: torch.Tensor; bg2c: torch.Tensor
+    wg2: LinearPack; bg2: torch.Tensor
+    wb1: LinearPack; bb1: torch.Tensor
+    wb2: LinearPack; bb2: torch.Tensor
+
+
+def pack_gnblock(blk, precision: str) -> GNBlockPack:
+    h = 512
+    dev = blk.edge_mlp[0].weight.device
+    d64 = lambda t: t.detach().to(torch.float64).cpu()
+    W1, b1 = d64(blk.edge_mlp[0].weight), d64(blk.edge_mlp[0].bias)
+    W2, b2 = d64(blk.edge_mlp[2].weight), d64(blk.edge_mlp[2].bias)
+    Wp1, bp1 = d64(blk.node_mlp_phi[0].weight), d64(blk.node_mlp_phi[0].bias)
+    Wp2, bp2 = d64(blk.node_mlp_phi[2].weight), d64(blk.node_mlp_phi[2].bias)
+    Wg1, bg1 = d64(blk.node_mlp_gamma[0].weight), d64(blk.node_mlp_gamma[0].bias)
+    Wg2, bg2 = d64(blk.node_mlp_gamma[2].weight), d64(blk.node_mlp_gamma[2].bias)
+    Wb1, bb1 = d64(blk.node_mlp_beta[0].weight), d64(blk.node_mlp_beta[0].bias)
+    Wb2, bb2 = d64(blk.node_mlp_beta[2].weight), d64(blk.node_mlp_beta[2].bias)
+    lp = lambda w: pack_linear(w.to(torch.float32).to(dev), precision)
+    hv = lambda b: b.to(torch.float32).contiguous()
+    Wp1b, Wg1b = Wp1[:, h:], Wg1[:, h:]
+    return GNBlockPack(
+        w1a=lp(W1[:, :h]), w1b=lp(W1[:, h:2 * h]), w1c=lp(W1[:, 2 * h:]), b1=hv(b1),
+        w2=lp(W2), b2=hv(b2),
+        wp1a=lp(Wp1[:, :h]), w3c=lp(Wp1b @ W2), b3c=hv(Wp1b @ b2 + bp1),
+        wg1a=lp(Wg1[:, :h]), wgc=lp(Wg1b @ Wp2), bg1=hv(bg1), bg2c=hv(Wg1b @ bp2),
+        wg2=lp(Wg2), bg2=hv(bg2), wb1=lp(Wb1), bb1=hv(bb1), wb2=lp(Wb2), bb2=hv(bb2))
+
+
+@dataclass
+class EdgeIndexExtras:
+    row_of: torch.Tensor     # [E] int32: key node of CSR slot i
+    iota: torch.Tensor       # [E] int32: 0..E-1
+
+
+def edge_extras(idx: GraphIndex) -> EdgeIndexExtras:
+    dev = idx.rowptr.device
+    e = max(idx.n_edges, 1)
+    row_of = torch.empty(e, dtype=torch.int32, device=dev)
+    iota = torch.empty(e, dtype=torch.int32, device=dev)
+    capi.expand_rowptr(idx.rowptr.data_ptr(), idx.n_nodes, idx.n_edges, row_of.data_ptr(), iota.data_ptr(), _stream())
+    return EdgeIndexExtras(row_of, iota)
+
+
+def add_into(out: Activation, a: Activation, b: Activation) -> None:
+    capi.add(a.data.data_ptr(), b.data.data_ptr(), None, out.data.data_ptr(), out.code, out.data.numel(), _stream())
+    out.refresh_split()
+
+
+class GNBlockBuffers:
+    """Scratch activations of the EA-GNN layer loop (allocated once per forward)."""
+
+    def __init__(self, n: int, e: int, precision: str, device):
+        mk = lambda rows: Activation(rows, 512, precision, device)
+        self.P, self.Q, self.R, self.mh, self.g1, self.xg, self.t, self.s, self.x_alt = (mk(n) for _ in range(9))
+        self.he, self.hm, self.e_alt = (mk(max(e, 1)) for _ in range(3))
+
+
+def gnblock_layer(x: Activation, e: Activation, buf: GNBlockBuffers, idx: GraphIndex, ex: EdgeIndexExtras,
+                  w: GNBlockPack, *, skip: bool, need_edges_out: bool, cta_group: int = 2):
+    """One iteration of the EA-GNN loop (Models/BuckGNN.py:378-387): returns (x_next, e_next).
+    Edge tensors live in CSR order keyed by `row = edge_index[0]` (idx built with key_row=0), so
+    scatter_mean(messages, row) is a segmented mean over contiguous slots."""
+    prec, n, ne = x.precision, idx.n_nodes, idx.n_edges
+    hp = lambda t: t.data_ptr()
+    G = lambda out, segs, m, **kw: gemm512(segs, m, prec, out, cta_group=cta_group, **kw)
+    with TIMERS.span("gn_node_gemms"):
+        G(buf.P, _segments(x, w.w1a), n)
+        G(buf.Q, _segments(x, w.w1b), n)
+        G(buf.R, _segments(x, w.wp1a), n)
+    with TIMERS.span("gn_edge_gemms"):
+        # edge_mlp layer 1 (+ReLU): h_e
+        G(buf.he, _segments(e, w.w1c), ne, bias=hp(w.b1), relu=True,
+          gather=[(buf.P.data.data_ptr(), ex.row_of.data_ptr()), (buf.Q.data.data_ptr(), idx.col.data_ptr())])
+        # edge_mlp layer 2 (+ wrapper skip): the next layer's edge features
+        e_next = None
+        if need_edges_out:
+            e_next = buf.e_alt
+            G(e_next, _segments(buf.he, w.w2), ne, bias=hp(w.b2),
+              residual=e.data.data_ptr() if skip else None, ldr=512)
+        # phi layer 1 (+ReLU) on e1 = h_e W2^T + b2, folded
+        G(buf.hm, _segments(buf.he, w.w3c), ne, bias=hp(w.b3c), relu=True,
+          gather=[(buf.R.data.data_ptr(), idx.col.data_ptr())])
+    # scatter_mean over row (phi layer 2 is folded into gamma layer 1)
+    ws_bytes = capi.aggregate_workspace_bytes(idx.n_big)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.data.device)
+    with TIMERS.span("gn_segment_mean"):
+        capi.sage_aggregate(buf.hm.data.data_ptr(), buf.mh.data.data_ptr(), buf.hm.code, n, idx.rowptr.data_ptr(),
+                            ex.iota.data_ptr(), idx.big_rows.data_ptr(), idx.n_big, capi.BG_AGGR_MEAN,
+                            ws.data_ptr(), ws_bytes, _stream())
+    buf.mh.refresh_split()
+    with TIMERS.span("gn_node_gemms"):
+        G(buf.g1, _segments(x, w.wg1a) + _segments(buf.mh, w.wgc), n, bias=hp(w.bg1), bias2=hp(w.bg2c),
+          gate_rowptr=idx.rowptr.data_ptr(), relu=True)
+        G(buf.xg, _segments(buf.g1, w.wg2), n, bias=hp(w.bg2))
+        G(buf.t, _segments(buf.xg, w.wb1), n, bias=hp(w.bb1), relu=True)
+        res = buf.xg
+        if skip:                                   # x_next = xg + beta(xg) + x_prev
+            add_into(buf.s, buf.xg, x)
+            res = buf.s
+        G(buf.x_alt, _segments(buf.t, w.wb2), n, bias=hp(w.bb2), residual=res.data.data_ptr(), ldr=512)
+    x_next = buf.x_alt
+    buf.x_alt = x                                  # ping-pong
+    if e_next is not None:
+        buf.e_alt = e
+    return x_next, e_next

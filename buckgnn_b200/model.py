@@ -184,6 +184,16 @@ class BuckGNN(nn.Module):
                                                engine.host_vector(conv.lin_l.bias), scale, shift)
             layers.append(seen[id(conv)])
         packs["layers"] = layers
+        if self.model_name in ("EA_GNN", "EA_GNN_Shared"):
+            ee = self.edge_encoder
+            packs["edge_enc"] = {"w1": f32(ee[0].weight), "b1": f32(ee[0].bias), "w2": f32(ee[2].weight),
+                                 "b2": f32(ee[2].bias), "b3_host": engine.host_vector(ee[4].bias)}
+            packs["edge_enc_w3"] = engine.pack_linear(ee[4].weight, prec)
+            if self.model_name == "EA_GNN_Shared":
+                shared = engine.pack_gnblock(self.shared_gn_block, prec)
+                packs["gn"] = [shared] * self.num_layers
+            else:
+                packs["gn"] = [engine.pack_gnblock(b, prec) for b in self.gn_blocks]
         self._packs, self._pack_sig = packs, sig
         return packs
 
@@ -196,8 +206,8 @@ class BuckGNN(nn.Module):
                                       "is not built yet; call model.eval() under torch.no_grad()")
         if self.hidden_channels != 512:
             raise NotImplementedError("buckgnn_b200: the tcgen05 path is built for hidden_channels=512")
-        if self.model_name in ("EA_GNN", "EA_GNN_Shared", "GraphSAGE_SAG", "EAGNN_SAG"):
-            raise NotImplementedError(f"buckgnn_b200: model_name={self.model_name!r} is not built yet")
+        if self.model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):
+            raise NotImplementedError(f"buckgnn_b200: model_name={self.model_name!r} (SAGPooling) is out of scope")
         if self.model_name in ("GraphSage_MLP", "GraphSage_addAggr_woBatchNorm", "GraphSage_sumAggr_woBatchNorm"):
             # the reference constructs the module lists these branches use only under other names
             raise AttributeError(f"'BuckGNN' object has no module list for model_name={self.model_name!r} "
@@ -215,7 +225,10 @@ class BuckGNN(nn.Module):
                 raise AttributeError("'BuckGNN' object has no attribute 'hybrid_pooling'")   # reference :188,276
             raise ValueError(f"Unknown pooling layer: {self.pooling_layer}")
         with torch.no_grad():
-            pred = self._forward_cuda(x, edge_index, batch)
+            if self.model_name in ("EA_GNN", "EA_GNN_Shared"):
+                pred = self._forward_cuda_eagnn(x, edge_index, edge_attr, batch)
+            else:
+                pred = self._forward_cuda(x, edge_index, batch)
         return pred.squeeze(), batch
 
     def _begin_graph_index(self, edge_index, batch, n):
@@ -237,6 +250,37 @@ class BuckGNN(nn.Module):
                     return idx
             return _Fill
         return engine.begin_graph_index(edge_index, batch, n)
+
+    def _forward_cuda_eagnn(self, x, edge_index, edge_attr, batch):
+        """EA-GNN / "CustomGNN" path (reference :326-336, :375-387, GraphNetBlock :528-566)."""
+        packs = self._packed()
+        prec, cg = self.precision, self.cta_group
+        x = x.detach().to(torch.float32).contiguous()
+        if not edge_attr.is_cuda:
+            raise RuntimeError("buckgnn_b200: `edge_attr` must be a CUDA tensor")
+        edge_attr = edge_attr.detach().to(torch.float32).contiguous()
+        n = x.shape[0]
+        # GraphNetBlock aggregates on row = edge_index[0] (:553,561) -> CSR keyed by row 0
+        pending = engine.begin_graph_index(edge_index, batch, n, key_row=0)
+        cur = Activation(n, 512, prec, x.device)
+        engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg)                 # :323
+        idx = pending.finish()
+        ne = idx.n_edges
+        ex = engine.edge_extras(idx)
+        e = Activation(max(ne, 1), 512, prec, x.device)
+        if ne > 0:                                   # edge_encoder on edge_attr in CSR order (:327, :376)
+            engine.encoder_forward(edge_attr, packs["edge_enc"], packs["edge_enc_w3"], prec, e, cg,
+                                   row_gather=idx.perm[:ne])
+        buf = engine.GNBlockBuffers(n, ne, prec, x.device)
+        L = self.num_layers
+        for i, w in enumerate(packs["gn"]):
+            cur, e_next = engine.gnblock_layer(cur, e, buf, idx, ex, w, skip=(0 < i < L - 1),
+                                               need_edges_out=(i < L - 1), cta_group=cg)
+            if e_next is not None:
+                e = e_next
+        pre = packs["pool_mlp"] if self.pooling_layer in ("mlp", "mlp_no_super") else None
+        pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim, pooling=self.pooling_layer, pre=pre)
+        return pred
 
     def _forward_cuda(self, x, edge_index, batch):
         packs = self._packed()

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 1
+#define BG_ABI_VERSION 2
 
 typedef enum bg_status {
   BG_OK = 0,
@@ -92,10 +92,12 @@ int bg_graph_ptr_build(const int64_t* batch, int64_t n_nodes, int64_t n_graphs, 
 /* ------------------------------------------------------------------ K5: node encoder front
  * First two Linear+ReLU of `node_encoder` (Models/BuckGNN.py:68-72, applied :323):
  *    h = relu(relu(x W1^T + b1) W2^T + b2),  x [N,F] f32 -> h [N,128] (out_dtype)
- * W1 [64,F], W2 [128,64] f32 row-major (out,in) as in nn.Linear.  F <= 32. */
+ * W1 [64,F], W2 [128,64] f32 row-major (out,in) as in nn.Linear.  F <= 32.
+ * row_gather (optional, DEVICE [N] int32): output row i is computed from input row row_gather[i]
+ * (the edge encoder reads `edge_attr` through the CSR permutation this way). */
 int bg_encoder_front(const float* x, int64_t n_nodes, int32_t n_features,
                      const float* w1, const float* b1, const float* w2, const float* b2,
-                     void* out, int out_dtype, void* stream);
+                     const int32_t* row_gather, void* out, int out_dtype, void* stream);
 
 /* ------------------------------------------------------------------ K2: neighbourhood aggregation
  * Replaces `x[src]` gather + `scatter_add_` + divide inside SAGEConv.propagate:
@@ -117,8 +119,14 @@ int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t n_nodes,
  * Replaces `lin_l(agg) + lin_r(x)`, `F.normalize`, `BatchNorm1d` (eval), `ReLU`
  * and the skip connection (Models/BuckGNN.py:449-457 and PyG SAGEConv.forward).
  * Epilogue order (each step optional):
- *    v = acc + bias;  v /= max(||v||_2, 1e-12);  v = v*bn_scale + bn_shift;
- *    v = max(v, 0);   v += residual[m, :]
+ *    v = acc + bias + gate[m]*bias2;   v += G0[gidx0[m], :] + G1[gidx1[m], :];
+ *    v /= max(||v||_2, 1e-12);  v = v*bn_scale + bn_shift;  v = max(v, 0);  v += residual[m, :]
+ * The gathered addends serve the EA-GNN block (Models/BuckGNN.py:556-560), where
+ * cat[x[row], x[col], e] W^T is evaluated as (x W_a^T)[row] + (x W_b^T)[col] + e W_c^T: the two
+ * node-level products are gathered per edge inside the epilogue of the edge-level GEMM.
+ * gate[m] = 1 if gate_rowptr[m+1] > gate_rowptr[m] else 0 (a bias that only applies to rows
+ * whose segment is non-empty, i.e. scatter_mean's empty-row = 0 after folding a Linear through it).
+ * normalize cannot be combined with gathered addends, nor gathered addends with residual.
  * Operand formats: a_dtype == b_dtype in {BG_BF16, BG_F16} (tcgen05 kind::f16, k_s % 64 == 0;
  * the hardware rejects bf16 x fp16 mixes) or both BG_F32 (read as
  * tf32, kind::tf32; k_s % 32 == 0 -- with hi/lo split operands from bg_split_tf32 this
@@ -140,6 +148,11 @@ typedef struct bg_epilogue {
   int64_t ldr;
   int32_t normalize;           /* F.normalize(p=2, dim=-1, eps=1e-12) */
   int32_t relu;
+  const float* bias2_host;     /* [512] HOST, gated second bias, or NULL                   */
+  const int32_t* gate_rowptr;  /* DEVICE [M+1] CSR offsets defining gate[m], or NULL       */
+  const void* gather[2];       /* DEVICE [*,512] matrices of out_dtype (ld = gather_ld), NULL = absent */
+  const int32_t* gather_idx[2];/* DEVICE [M] row index into gather[k]                      */
+  int64_t gather_ld;
 } bg_epilogue;
 
 int bg_gemm512(const bg_gemm_segment* segments_host, int32_t n_segments, int64_t m,
@@ -167,6 +180,16 @@ int bg_pool_head(const void* x, int dtype, int64_t n_nodes, const int32_t* graph
                  const float* w3, const float* b3, int32_t out_dim,
                  float* pred, float* pooled_out,
                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ EA-GNN helpers
+ * bg_expand_rowptr: row_of[i] = r with rowptr[r] <= i < rowptr[r+1], iota[i] = i   (i < E)
+ *   (row ids of the CSR slots, and the identity "col" that turns bg_sage_aggregate into the
+ *   segmented mean torch_scatter.scatter_mean(messages, row) needs once edges are in CSR order).
+ * bg_add: out = a + b (+ c) elementwise over n values of `dtype`, fp32 math (skip connections
+ *   of the EA-GNN wrapper, Models/BuckGNN.py:382-384). */
+int bg_expand_rowptr(const int32_t* rowptr, int64_t n_rows, int64_t n_entries, int32_t* row_of, int32_t* iota,
+                     void* stream);
+int bg_add(const void* a, const void* b, const void* c_or_null, void* out, int dtype, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------ helpers
  * fp32 -> bf16 / f16 (round to nearest even) cast of a contiguous buffer (weight packing). */

@@ -142,3 +142,38 @@ def test_weight_update_invalidates_packed_copies():
         ours.decoder[4].bias.add_(1.0)
         p2, _ = ours(b.x, b.edge_index, b.edge_attr, b.batch)
     torch.testing.assert_close(p2, p1 + 1.0, rtol=1e-5, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------- EA-GNN ("CustomGNN")
+@pytest.mark.parametrize("name", ["EA_GNN", "EA_GNN_Shared"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_eagnn_matches_oracle(name, precision):
+    """GraphNetBlock path (Models/BuckGNN.py:375-387, 528-566) on stiffened plates with virtual edges."""
+    torch.manual_seed(3)
+    cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=4,
+               pooling_layer="mean", model_name=name)
+    ref = OracleBuckGNN(**cfg).eval()
+    ours = BuckGNN(**cfg, precision=precision)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV).eval()
+    b = make_batch(3, nx=10, ny=8, stiffened=True)
+    got, want = _run(ref, ours, b)
+    assert got.shape == (3,)
+    _assert_rel(got, want, 1e-4 if precision == "fp32" else 2e-3)
+
+
+def test_eagnn_directed_graph_with_isolated_sources():
+    """nodes that never appear in edge_index[0] have an empty scatter_mean segment (agg = 0, no phi bias)"""
+    torch.manual_seed(4)
+    cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=3,
+               pooling_layer="mean", model_name="EA_GNN")
+    ref = OracleBuckGNN(**cfg).eval()
+    ours = BuckGNN(**cfg, precision="fp32")
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV).eval()
+    b = make_batch(2, nx=7, ny=6)
+    keep = b.edge_index[0] % 3 != 0                    # every third node loses all its out-edges
+    b.edge_index = b.edge_index[:, keep].contiguous()
+    b.edge_attr = b.edge_attr[keep].contiguous()
+    got, want = _run(ref, ours, b)
+    _assert_rel(got, want, 1e-4)
