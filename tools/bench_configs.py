@@ -1,0 +1,88 @@
+"""Throughput of the other BASELINE.json configs on one B200 (not the headline bench line):
+  cfg3  stiffened-plate EA-GNN ("CustomGNN"), batch 128, fp16 operands / fp32 accumulate
+  cfg5  GraphSAGE 6x512 on stiffened plates with mesh sizes scaled 1x..8x (hub degree = graph size)
+Prints one JSON line per case."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from buckgnn_b200 import capi, engine
+from buckgnn_b200.model import BuckGNN
+from buckgnn_b200.synth import make_batch
+from oracle.buckgnn_oracle import OracleBuckGNN, randomize_bn_stats
+
+DEV = "cuda:0"
+
+
+def timed(model, b, steps=5, warmup=2):
+    with torch.no_grad():
+        for _ in range(warmup):
+            model(b.x, b.edge_index, b.edge_attr, b.batch)
+        torch.cuda.synchronize()
+        engine.TIMERS.enable()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            pred, _ = model(b.x, b.edge_index, b.edge_attr, b.batch)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    k = {n: v[0] / steps for n, v in engine.TIMERS.summary().items()}
+    engine.TIMERS.disable()
+    return ms, k, pred
+
+
+def parity(cfg, precision, sample, **kw):
+    torch.manual_seed(0)
+    ref = OracleBuckGNN(**cfg).eval()
+    randomize_bn_stats(ref, realistic=True)
+    ours = BuckGNN(**cfg, precision=precision, **kw)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV).eval()
+    with torch.no_grad():
+        want, _ = ref(sample.x, sample.edge_index, sample.edge_attr, sample.batch)
+        s = sample.to(DEV)
+        got, _ = ours(s.x, s.edge_index, s.edge_attr, s.batch)
+    err = ((got.cpu() - want).abs() / want.abs().clamp(min=1e-3)).max().item()
+    return ours, err
+
+
+def main():
+    capi.device_check()
+    which = sys.argv[1:] or ["cfg3", "cfg5"]
+    if "cfg3" in which:
+        cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=6,
+                   pooling_layer="mean", model_name="EA_GNN")
+        model, err = parity(cfg, "fp16", make_batch(2, nx=20, ny=16, stiffened=True))
+        b = make_batch(128, stiffened=True).to(DEV)
+        ms, k, _ = timed(model, b)
+        n, e = b.num_nodes, b.num_edges
+        flops = 6 * (3 * e + 8 * n) * 2.0 * 512 * 512 - 2.0 * e * 512 * 512     # last layer skips edge_mlp L2
+        print(json.dumps({"config": "cfg3: EA_GNN 6x512, batch 128 stiffened plates (CBAR sides+diagonals, 13.33% virtual "
+                                    "edges, super node)", "graphs": 128, "nodes": n, "edges": e, "precision": "fp16",
+                          "ms_per_forward": ms, "graphs_per_s": 128 / (ms * 1e-3), "gemm_tflops_as_executed": flops / ms / 1e9,
+                          "kernel_ms": k, "parity_rel_err_sample": err}), flush=True)
+        del model, b
+        torch.cuda.empty_cache()
+    if "cfg5" in which:
+        cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=6,
+                   pooling_layer="mean", model_name="GraphSage_meanAggr")
+        model, err = parity(cfg, "fp16", make_batch(2, nx=20, ny=16, stiffened=True))
+        for scale, graphs in ((1.0, 128), (2 ** 0.5, 64), (2.0, 32), (2 * 2 ** 0.5, 16)):
+            b = make_batch(graphs, stiffened=True, scale=scale).to(DEV)
+            ms, k, _ = timed(model, b)
+            print(json.dumps({"config": f"cfg5: GraphSage_meanAggr 6x512 on stiffened plates, linear mesh scale {scale:.3f} "
+                                        f"(node count x{scale * scale:.0f})", "graphs": graphs, "nodes": b.num_nodes,
+                              "edges": b.num_edges, "max_hub_degree": int((b.ptr[1:] - b.ptr[:-1]).max()) - 1,
+                              "ms_per_forward": ms, "graphs_per_s": graphs / (ms * 1e-3),
+                              "nodes_per_s": b.num_nodes / (ms * 1e-3), "kernel_ms": k,
+                              "parity_rel_err_sample": err}), flush=True)
+            del b
+            torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
