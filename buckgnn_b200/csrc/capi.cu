@@ -331,7 +331,6 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
   p.n_tiles = (int32_t)ceil_div64(m, kTileM * cta_group);
   p.m = m;
   for (int i = 0; i < kHidden; ++i) { p.bias[i] = 0.f; p.bias2[i] = 0.f; p.scale[i] = 1.f; p.shift[i] = 0.f; }
-  const uint32_t o_fmt = (uint32_t)umma_format_of(out_dtype);
   if (epi) {
     if (epi->residual && (!aligned16(epi->residual) || (epi->ldr * osz) % 16 != 0 || epi->ldr < kHidden))
       return fail(BG_ERR_INVALID, "bg_gemm512: bad residual/ldr");
@@ -357,14 +356,9 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
     p.gather_ld = epi->gather_ld;
     if (p.n_gather > 0 && (epi->normalize || epi->residual))
       return fail(BG_ERR_UNSUPPORTED, "bg_gemm512: gathered addends cannot be combined with normalize or residual");
-    if (epi->residual) {
-      p.has_res = 1;
-      if (make_operand_map(&p.res_map, epi->residual, m, kHidden, epi->ldr, o_fmt) != BG_OK)
-        return fail(BG_ERR_CUDA, "bg_gemm512: cuTensorMapEncodeTiled (residual) failed");
-    }
+    p.residual = epi->residual; p.ldr = epi->ldr;
   }
-  if (make_operand_map(&p.out_map, out, m, kHidden, ldo, o_fmt) != BG_OK)
-    return fail(BG_ERR_CUDA, "bg_gemm512: cuTensorMapEncodeTiled (out) failed");
+  p.out = out; p.ldo = ldo;
 #define BG_GEMM_OUT(CG, TF)                                                              \
   (out_dtype == BG_BF16 ? launch_gemm512<CG, TF, __nv_bfloat16>(p, stream)               \
    : out_dtype == BG_F16 ? launch_gemm512<CG, TF, __half>(p, stream)                     \

@@ -99,16 +99,8 @@ template <> struct Pack16<__nv_bfloat16> {
   }
 };
 template <> struct Pack16<__half> {
-  static BG_DEVINL float lo(uint32_t u) {
-    float f;
-    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(f) : "r"(u));
-    return f;
-  }
-  static BG_DEVINL float hi(uint32_t u) {
-    float f;
-    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(f) : "r"(u));
-    return f;
-  }
+  static BG_DEVINL float lo(uint32_t u) { return __low2float(*reinterpret_cast<const __half2*>(&u)); }
+  static BG_DEVINL float hi(uint32_t u) { return __high2float(*reinterpret_cast<const __half2*>(&u)); }
   static BG_DEVINL void add2(float& a0, float& a1, uint32_t u) {
     asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\t"
         "add.rn.f32.f16 %0, lo, %0;\n\tadd.rn.f32.f16 %1, hi, %1;\n\t}" : "+f"(a0), "+f"(a1) : "r"(u));

@@ -6,29 +6,31 @@
 // the concatenated [lin_l | lin_r] GEMM with K = 1024 -- replaces `lin_l(agg) +
 // lin_r(x)`, `F.normalize`, eval `BatchNorm1d`, `ReLU` and the skip connection of the
 // reference layer loop (Models/BuckGNN.py:449-457 + PyG SAGEConv.forward).  The same
-// kernel runs the encoder's 128 -> 512 Linear (:73) as a one-segment GEMM.
+// kernel runs the encoders' 128 -> 512 Linear (:73, :81) and every Linear of the EA-GNN
+// block (:528-566), whose gathered operands arrive as epilogue addends.
 //
 // One persistent CTA pair per SM pair (tcgen05 cta_group::2), 12 warps per CTA:
 //   warp 0     TMA producer: this CTA's 128 activation rows x 128 B of K and its 256 of
-//              the 512 weight rows into a ring of 128B-swizzled K-major stages
+//              the 512 weight rows into a 4-stage ring of 128B-swizzled K-major tiles
 //   warp 1     allocates TMEM; in the leader CTA one elected lane issues tcgen05.mma
 //              (M = 256 over the pair, N = 256, two N halves -> the 512 fp32 columns of
 //              TMEM hold one full output row per lane: L2-normalize needs the whole row)
-//   warps 2-3  staging-ring drivers, one per column half: issue the epilogue's TMA stores
-//              and skip-row loads so the math warps never wait on the TMA engine
+//   warps 2-3  idle (register donors: setmaxnreg 40 for warps 0-3, 232 for the epilogue)
 //   warps 4-11 epilogue, two groups of 4 warps = two 256-column halves; one TMEM lane
 //              (= output row) per thread.
-//              16-bit output: ONE pass over TMEM adds the bias, accumulates the row's sum
-//              of squares and stashes the row as packed 16-bit pairs in 128 registers;
-//              TMEM is released right after, so the next tile's MMAs overlap pass 2, which
-//              applies normalize / BN / ReLU / skip from the stash.
+//              16-bit output: ONE pass over TMEM (double-buffered tcgen05.ld) adds the bias,
+//              accumulates the row's sum of squares and stashes the row as packed 16-bit
+//              pairs in 128 registers; TMEM is released right after, so the next tile's
+//              MMAs overlap pass 2, which applies normalize / BN / ReLU / skip from the stash.
 //              fp32 output (tf32 / 3xTF32 modes): two passes over TMEM (no stash).
-//              Either way the result goes through 128B-swizzled staging tiles in shared
-//              memory and leaves with TMA stores; the skip-connection rows arrive the
-//              same way (TMA load into the staging tile, added in place) -- no
-//              row-strided global accesses.
-// setmaxnreg moves registers from warps 0-3 (40) to the epilogue warps (232).
-// Tensor-core bound: 2*K*512 flops per row; algorithmic bytes per row
+//              Global I/O of pass 2 is warp-cooperative and coalesced: a warp moves 128-byte
+//              row chunks with 8 lanes per row (4 full lines per instruction) between
+//              global memory and a 4 KB swizzled staging tile of its own, where each thread
+//              picks up / drops its row.  Skip rows and gathered addends are prefetched one
+//              chunk ahead.  (An earlier version staged whole 128-row tiles for TMA stores;
+//              the store-read latency of the 2-deep ring, ~3k cycles, made every K <= 512
+//              GEMM epilogue-bound -- profiles/r01_gemm_role_cycles_v3.txt.)
+// Tensor-core bound for K = 1024: 2*K*512 flops per row; algorithmic bytes per row
 // = (K_total + 512 [+512 skip]) * elem_size.
 #pragma once
 #include <cuda.h>
@@ -41,32 +43,34 @@ constexpr int kStageKBytes = 128;                 // one 128B swizzle row of K p
 constexpr int kATileBytes = kTileM * kStageKBytes;        // 16 KB
 constexpr int kGemmThreads = 384;                 // 12 warps
 constexpr int kEpiFirstWarp = 4;
-constexpr int kEpiSlotBytes = kTileM * 128;       // staging tile: 128 rows x 128 B
-constexpr int kEpiSlots = 4;                      // 2 per column-half group
+constexpr int kEpiWarps = 8;
+constexpr int kEpiStageBytes = 32 * 128;          // per-warp staging tile: 32 rows x 128 B
 
 template <int kCg> struct GemmCfg {
   static constexpr int kBRows = kHidden / kCg;                  // weight rows held by one CTA
   static constexpr int kBTileBytes = kBRows * kStageKBytes;     // 64 KB / 32 KB
   static constexpr int kStageBytes = kATileBytes + kBTileBytes; // 80 KB / 48 KB
-  static constexpr int kStages = (kCg == 1) ? 2 : 3;
+  static constexpr int kStages = (kCg == 1) ? 2 : 4;
   static constexpr int kMiscBytes = 2048 + 256;                 // row sum-of-squares exchange + barriers
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiSlots * kEpiSlotBytes + kMiscBytes;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kMiscBytes;
 };
 
 struct alignas(64) GemmSeg { CUtensorMap a; CUtensorMap b; };
 
 struct alignas(64) GemmParams {
   GemmSeg seg[BG_MAX_GEMM_SEGMENTS];
-  CUtensorMap out_map;              // [M, 512] out, box 128 rows x 128 B, 128B swizzle
-  CUtensorMap res_map;              // same geometry over the residual (valid iff has_res)
   int32_t kblocks[BG_MAX_GEMM_SEGMENTS];
   int32_t n_seg;
   int32_t k_elems_per_block;        // 64 (16-bit operands) or 32 (tf32)
   uint32_t a_fmt, b_fmt;            // UMMA operand formats: 0 f16, 1 bf16, 2 tf32
   int32_t n_tiles;                  // row tiles of 128*cg rows
-  int32_t normalize, relu, has_res;
+  int32_t normalize, relu;
   int32_t n_gather;                 // 0..2 gathered pre-activation addends: v += G_k[gidx_k[m], :]
   int64_t m;
+  void* out;                        // [M, 512] of the output dtype, leading dimension ldo (elements)
+  int64_t ldo;
+  const void* residual;             // [M, 512] skip rows of the output dtype (ld = ldr), or null
+  int64_t ldr;
   const void* gather[2];            // [*, 512] row-major matrices of the output dtype, ld = gather_ld
   const int32_t* gidx[2];           // [M] row index into gather[k]
   int64_t gather_ld;
@@ -93,7 +97,7 @@ __device__ unsigned long long g_gemm_prof[296 * 8];
 #define BG_PROF_STORE(slot, v)
 #endif
 
-enum : uint32_t { kTagEmpty = 1, kTagFull = 2, kTagTmemEmpty = 3, kTagTmemFull = 4, kTagEpiReady = 5, kTagEpiFull = 6 };
+enum : uint32_t { kTagEmpty = 1, kTagFull = 2, kTagTmemEmpty = 3, kTagTmemFull = 4 };
 
 BG_DEVINL void named_bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -109,12 +113,8 @@ BG_DEVINL void sts_v4(uint32_t addr, uint4 v) {
 template <int kRegs> BG_DEVINL void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs> BG_DEVINL void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
-// staging-ring barriers: per column-half group g and slot s
-BG_DEVINL uint32_t epi_ready_bar(uint32_t base, int g, uint32_t s) { return base + 8u * (uint32_t)(g * 2 + s); }
-BG_DEVINL uint32_t epi_full_bar(uint32_t base, int g, uint32_t s) { return base + 8u * (uint32_t)(4 + g * 2 + s); }
-
 struct EpiCtx {
-  uint32_t tmem_base, slots_u32, ring_bars;
+  uint32_t tmem_base, stage_u32;    // stage_u32: this warp's 4 KB staging tile
   float* ss_smem;
   uint32_t tmem_full_bar, tmem_empty_bar, rank;
   int tile0, tile_stride;
@@ -129,31 +129,62 @@ BG_DEVINL void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr) : "memory");
 }
 
+// 16 B from global memory that is read exactly once (skip rows): bypass L1
+BG_DEVINL uint4 ldg_stream_v4(const void* p) { return ldg_nc_v4(p); }
+
 // One column-half group (4 warps = 128 TMEM lanes = 128 output rows, 256 columns starting at
 // kG*256).  kG is a template parameter so every bias / scale / shift access is a constant-bank
 // operand with an immediate offset.
 template <int kCg, typename TOut, int kG>
 BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
   constexpr bool kOut16 = sizeof(TOut) == 2;
-  constexpr int kChunkCols = 128 / (int)sizeof(TOut);           // columns per 128-byte staging row: 64 / 32
+  constexpr int kChunkCols = 128 / (int)sizeof(TOut);           // columns per 128-byte row chunk: 64 / 32
   constexpr int kChunks = 256 / kChunkCols;                     // 4 / 8
+  constexpr int kPer = 16 / (int)sizeof(TOut);                  // 8 or 4 columns per 16-byte piece
   constexpr int cb = kG * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;                                       // TMEM lane quarter this warp may read
-  const int row = q * 32 + lane;                                // row within the CTA's 128-row tile
+  const int row = q * 32 + lane;                                // this thread's row within the CTA's 128-row tile
   const uint32_t taddr = cx.tmem_base + ((uint32_t)(q * 32) << 16) + cb;
-  const uint32_t row_off = (uint32_t)row * 128u;
-  const uint32_t sw = (uint32_t)(row & 7);
-  uint32_t it = 0, seq = 0;                                     // tiles done; staging chunks done (this group)
+  // per-thread view of the staging tile (own row) and cooperative view (8 lanes per row, 4 rows per pass)
+  const uint32_t my_row_off = cx.stage_u32 + (uint32_t)lane * 128u;
+  const uint32_t my_sw = (uint32_t)(lane & 7);
+  const int r4 = lane >> 3, piece = lane & 7;
+  const bool has_res = p.residual != nullptr;
+  const size_t out_esz = sizeof(TOut);
+  uint32_t it = 0;
   BG_PROF_DECL
   for (int tile = cx.tile0; tile < p.n_tiles; tile += cx.tile_stride, ++it) {
-    const int64_t m_row = (int64_t)tile * (kTileM * kCg) + (int64_t)cx.rank * kTileM + row;
+    const int64_t warp_row0 = (int64_t)tile * (kTileM * kCg) + (int64_t)cx.rank * kTileM + q * 32;
+    const int64_t m_row = warp_row0 + lane;
     const bool row_valid = m_row < p.m;
     float gate = 0.f;
     if (p.gate_rowptr && row_valid) gate = (p.gate_rowptr[m_row + 1] > p.gate_rowptr[m_row]) ? 1.f : 0.f;
     int32_t gi0 = 0, gi1 = 0;
     if (p.n_gather > 0 && row_valid) gi0 = p.gidx[0][m_row];
     if (p.n_gather > 1 && row_valid) gi1 = p.gidx[1][m_row];
+
+    // cooperative fetch of one 128-byte chunk of "addend" rows (skip rows, or the first gathered matrix)
+    // for this warp's 32 rows: pass t covers rows 4t..4t+3, 8 lanes x 16 B per row
+    uint4 pre[8];
+    auto fetch_chunk = [&](int ch) {
+      const size_t col_off = (size_t)(cb + ch * kChunkCols) * out_esz + (size_t)piece * 16;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int rr = t * 4 + r4;
+        if (has_res) {
+          const int64_t gr = warp_row0 + rr;
+          pre[t] = (gr < p.m) ? ldg_stream_v4(reinterpret_cast<const char*>(p.residual) + (size_t)gr * p.ldr * out_esz + col_off)
+                              : make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          const int32_t n0 = __shfl_sync(0xffffffffu, gi0, rr);
+          pre[t] = ldg_v4(reinterpret_cast<const char*>(p.gather[0]) + (size_t)n0 * p.gather_ld * out_esz + col_off);
+        }
+      }
+    };
+    const bool has_addend = has_res || p.n_gather > 0;
+    if (has_addend) fetch_chunk(0);                             // in flight while we wait for the MMAs
+
     BG_PROF_T0();
     mbar_wait(cx.tmem_full_bar, it & 1u, kTagTmemFull);
     BG_PROF_ADD(_pacc_a);
@@ -204,12 +235,36 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
     BG_PROF_ADD(_pacc_b);
     BG_PROF_T0();
 
-    // ---- pass 2: normalize / BN / ReLU / skip into the swizzled staging ring
+    // ---- pass 2: normalize / BN / ReLU / skip, 128-byte row chunks through the warp's staging tile
 #pragma unroll
-    for (int ch = 0; ch < kChunks; ++ch, ++seq) {
-      const uint32_t sl = seq & 1u;
-      const uint32_t slot = cx.slots_u32 + (kG * 2 + sl) * kEpiSlotBytes;
-      constexpr int kPer = 16 / (int)sizeof(TOut);              // 8 or 4 columns per 16-byte piece
+    for (int ch = 0; ch < kChunks; ++ch) {
+      const size_t col_off = (size_t)(cb + ch * kChunkCols) * out_esz + (size_t)piece * 16;
+      if (has_addend) {
+        // park the prefetched addend rows (second gathered matrix added on the way) in the staging tile
+        if (p.n_gather > 1) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int32_t n1 = __shfl_sync(0xffffffffu, gi1, t * 4 + r4);
+            const uint4 g1 = ldg_v4(reinterpret_cast<const char*>(p.gather[1]) + (size_t)n1 * p.gather_ld * out_esz + col_off);
+            if constexpr (kOut16) {
+              pre[t].x = Pack16<TOut>::hadd2(pre[t].x, g1.x); pre[t].y = Pack16<TOut>::hadd2(pre[t].y, g1.y);
+              pre[t].z = Pack16<TOut>::hadd2(pre[t].z, g1.z); pre[t].w = Pack16<TOut>::hadd2(pre[t].w, g1.w);
+            } else {
+              pre[t].x = __float_as_uint(__uint_as_float(pre[t].x) + __uint_as_float(g1.x));
+              pre[t].y = __float_as_uint(__uint_as_float(pre[t].y) + __uint_as_float(g1.y));
+              pre[t].z = __float_as_uint(__uint_as_float(pre[t].z) + __uint_as_float(g1.z));
+              pre[t].w = __float_as_uint(__uint_as_float(pre[t].w) + __uint_as_float(g1.w));
+            }
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int rr = t * 4 + r4;
+          sts_v4(cx.stage_u32 + (uint32_t)rr * 128u + (((uint32_t)piece ^ (uint32_t)(rr & 7)) << 4), pre[t]);
+        }
+        __syncwarp();
+        if (ch + 1 < kChunks) fetch_chunk(ch + 1);              // next chunk's addends fly during the math below
+      }
       [[maybe_unused]] uint32_t r[32];
       if constexpr (!kOut16) {
         tmem_ld_32x32(taddr + ch * 32, r);
@@ -220,71 +275,30 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
           else mbar_arrive_cluster(cx.tmem_empty_bar, 0);
         }
       }
-      mbar_wait(epi_ready_bar(cx.ring_bars, kG, sl), (seq >> 1) & 1u, kTagEpiReady);   // tile free / skip rows landed
-      if (p.n_gather > 0) {
-        // software gather: this warp fetches the 128-byte chunk of G_k[gidx_k[row]] for its own 32 rows with
-        // coalesced loads (8 lanes per row) and parks the sum in the staging tile, swizzled like a TMA tile
-        const int r4 = lane >> 3, piece = lane & 7;
-        const size_t col_off = (size_t)(cb + ch * kChunkCols) * sizeof(TOut) + (size_t)piece * 16;
-        const size_t ldb = (size_t)p.gather_ld * sizeof(TOut);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint4 g0[4], g1[4];
-#pragma unroll
-          for (int t4 = 0; t4 < 4; ++t4) {
-            const int rr = (half * 4 + t4) * 4 + r4;
-            const int32_t n0 = __shfl_sync(0xffffffffu, gi0, rr);
-            g0[t4] = ldg_v4(reinterpret_cast<const char*>(p.gather[0]) + (size_t)n0 * ldb + col_off);
-            if (p.n_gather > 1) {
-              const int32_t n1 = __shfl_sync(0xffffffffu, gi1, rr);
-              g1[t4] = ldg_v4(reinterpret_cast<const char*>(p.gather[1]) + (size_t)n1 * ldb + col_off);
-            }
-          }
-#pragma unroll
-          for (int t4 = 0; t4 < 4; ++t4) {
-            const int rr = q * 32 + (half * 4 + t4) * 4 + r4;
-            uint4 o = g0[t4];
-            if (p.n_gather > 1) {
-              if constexpr (kOut16) {
-                o.x = Pack16<TOut>::hadd2(o.x, g1[t4].x); o.y = Pack16<TOut>::hadd2(o.y, g1[t4].y);
-                o.z = Pack16<TOut>::hadd2(o.z, g1[t4].z); o.w = Pack16<TOut>::hadd2(o.w, g1[t4].w);
-              } else {
-                o.x = __float_as_uint(__uint_as_float(o.x) + __uint_as_float(g1[t4].x));
-                o.y = __float_as_uint(__uint_as_float(o.y) + __uint_as_float(g1[t4].y));
-                o.z = __float_as_uint(__uint_as_float(o.z) + __uint_as_float(g1[t4].z));
-                o.w = __float_as_uint(__uint_as_float(o.w) + __uint_as_float(g1[t4].w));
-              }
-            }
-            sts_v4(slot + (uint32_t)rr * 128u + (((uint32_t)piece ^ (uint32_t)(rr & 7)) << 4), o);
-          }
-        }
-        __syncwarp();
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {                             // 16-byte pieces of this thread's 128-byte row
-        const uint32_t addr = slot + row_off + (((uint32_t)j ^ sw) << 4);
+      for (int j = 0; j < 8; ++j) {                             // 16-byte pieces of this thread's 128-byte row chunk
+        const uint32_t addr = my_row_off + (((uint32_t)j ^ my_sw) << 4);
         float v[kPer];
 #pragma unroll
         for (int e = 0; e < kPer; ++e) {
           const int c = cb + ch * kChunkCols + j * kPer + e;    // compile-time constant
-          float a;
           if constexpr (kOut16) {
             const uint32_t u = stash[ch * 32 + j * 4 + (e >> 1)];
-            a = (e & 1) ? Pack16<TOut>::hi(u) : Pack16<TOut>::lo(u);
+            v[e] = (e & 1) ? Pack16<TOut>::hi(u) : Pack16<TOut>::lo(u);
           } else {
-            a = __uint_as_float(r[j * 4 + e]) + fmaf(gate, p.bias2[c], p.bias[c]);
+            v[e] = __uint_as_float(r[j * 4 + e]) + fmaf(gate, p.bias2[c], p.bias[c]);
           }
-          v[e] = a;
         }
-        if (p.n_gather > 0) {                                   // gathered pre-activation addends, staged in the tile
-          const uint4 gg = lds_v4(addr);
-          const uint32_t gu[4] = {gg.x, gg.y, gg.z, gg.w};
+        uint4 ad = make_uint4(0u, 0u, 0u, 0u);
+        if (has_addend) ad = lds_v4(addr);
+        const uint32_t au[4] = {ad.x, ad.y, ad.z, ad.w};
+        if (p.n_gather > 0) {                                   // gathered addends enter before the activation
           if constexpr (kOut16) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) Pack16<TOut>::add2(v[2 * e], v[2 * e + 1], gu[e]);
+            for (int e = 0; e < 4; ++e) Pack16<TOut>::add2(v[2 * e], v[2 * e + 1], au[e]);
           } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] += __uint_as_float(gu[e]);
+            for (int e = 0; e < 4; ++e) v[e] += __uint_as_float(au[e]);
           }
         }
 #pragma unroll
@@ -294,15 +308,13 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
           if (p.relu) a = fmaxf(a, 0.f);
           v[e] = a;
         }
-        if (p.has_res) {
-          const uint4 rr = lds_v4(addr);
-          const uint32_t ru[4] = {rr.x, rr.y, rr.z, rr.w};
+        if (has_res) {                                          // skip rows enter after it
           if constexpr (kOut16) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) Pack16<TOut>::add2(v[2 * e], v[2 * e + 1], ru[e]);
+            for (int e = 0; e < 4; ++e) Pack16<TOut>::add2(v[2 * e], v[2 * e + 1], au[e]);
           } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] += __uint_as_float(ru[e]);
+            for (int e = 0; e < 4; ++e) v[e] += __uint_as_float(au[e]);
           }
         }
         uint4 o;
@@ -314,8 +326,16 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
         }
         sts_v4(addr, o);
       }
-      fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA store
-      mbar_arrive(epi_full_bar(cx.ring_bars, kG, sl));          // 128 arrivals hand the tile to the ring driver
+      __syncwarp();
+      // coalesced store: 4 rows x 128 B per instruction
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int rr = t * 4 + r4;
+        const int64_t gr = warp_row0 + rr;
+        const uint4 o = lds_v4(cx.stage_u32 + (uint32_t)rr * 128u + (((uint32_t)piece ^ (uint32_t)(rr & 7)) << 4));
+        if (gr < p.m) stg_v4(reinterpret_cast<char*>(p.out) + (size_t)gr * p.ldo * out_esz + col_off, o);
+      }
+      __syncwarp();
     }
     BG_PROF_ADD(_pacc_c);
   }
@@ -331,17 +351,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm512(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<kCg>;
   constexpr int kStages = Cfg::kStages;
-  constexpr bool kOut16 = sizeof(TOut) == 2;
-  constexpr int kChunkCols = 128 / (int)sizeof(TOut);           // columns per 128-byte staging row: 64 / 32
-  constexpr int kChunks = 256 / kChunkCols;                     // staging chunks per 256-column group: 4 / 8
   extern __shared__ uint8_t gemm_smem_raw[];
   const uint32_t smem_base = (smem_u32(gemm_smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B wants 1024 B
   uint8_t* smem_gen = gemm_smem_raw + (smem_base - smem_u32(gemm_smem_raw));
   const uint32_t stages_u32 = smem_base;
-  const uint32_t slots_u32 = stages_u32 + kStages * Cfg::kStageBytes;
-  float* ss_smem = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes + kEpiSlots * kEpiSlotBytes);
-  const uint32_t bars_u32 = slots_u32 + kEpiSlots * kEpiSlotBytes + 2048;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + kEpiSlots * kEpiSlotBytes + 2048 + 192);
+  const uint32_t epi_u32 = stages_u32 + kStages * Cfg::kStageBytes;
+  constexpr int kEpiBytes = kEpiWarps * kEpiStageBytes;
+  float* ss_smem = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes + kEpiBytes);
+  const uint32_t bars_u32 = epi_u32 + kEpiBytes + 2048;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + kEpiBytes + 2048 + 192);
   auto full_bar = [&](int s) { return bars_u32 + 8u * s; };
   auto empty_bar = [&](int s) { return bars_u32 + 8u * (kStages + s); };
   const uint32_t tmem_full_bar = bars_u32 + 8u * (2 * kStages);
@@ -356,8 +374,6 @@ k_gemm512(const __grid_constant__ GemmParams p) {
   // ---- one-time setup
   if (warp == 0 && elect_one()) {
     for (int s = 0; s < p.n_seg; ++s) { tma_prefetch_desc(&p.seg[s].a); tma_prefetch_desc(&p.seg[s].b); }
-    tma_prefetch_desc(&p.out_map);
-    if (p.has_res) tma_prefetch_desc(&p.res_map);
   }
   if (kCg == 2) cluster_sync();                // both CTAs resident before the paired TMEM alloc
   if (warp == 1) {
@@ -365,10 +381,6 @@ k_gemm512(const __grid_constant__ GemmParams p) {
       for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), kCg); mbar_init(empty_bar(s), 1); }
       mbar_init(tmem_full_bar, 1);
       mbar_init(tmem_empty_bar, kCg * 256);
-      for (int i = 0; i < 4; ++i) {
-        mbar_init(epi_ready_bar(bars_u32 + 8u * (2 * kStages + 2), i >> 1, i & 1), 1);
-        mbar_init(epi_full_bar(bars_u32 + 8u * (2 * kStages + 2), i >> 1, i & 1), 128);
-      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -462,57 +474,12 @@ k_gemm512(const __grid_constant__ GemmParams p) {
       if (lane == 0) { BG_PROF_STORE(1, _pacc_a); BG_PROF_STORE(2, _pacc_b); BG_PROF_STORE(3, clock64() - _pstart); }
 #endif
       __syncwarp();
-    } else if (warp >= 2) {
-      // ================================================================ staging-ring drivers (one per column half)
-      // Own all TMA traffic of the epilogue: store a staging tile once its 128 rows are
-      // written, and as soon as that store has left the tile, refill it for the chunk two
-      // ahead (skip-connection rows by TMA load, or just hand it back).
-      if (elect_one()) {
-        const int g = warp - 2;
-        constexpr int kChunkCols = 128 / (int)sizeof(TOut);
-        constexpr int kChunks = 256 / kChunkCols;
-        const uint32_t rb = bars_u32 + 8u * (2 * kStages + 2);
-        const int my_tiles = (p.n_tiles - tile0 + tile_stride - 1) / tile_stride;
-        const int total = my_tiles * kChunks;
-        auto coords = [&](int n, int32_t& col0, int32_t& row0) {
-          const int tile = tile0 + (n / kChunks) * tile_stride;
-          col0 = g * 256 + (n % kChunks) * kChunkCols;
-          row0 = tile * (kTileM * kCg) + (int32_t)rank * kTileM;
-        };
-        auto prepare = [&](int n) {                           // make slot n&1 ready for chunk n
-          const uint32_t sl = (uint32_t)n & 1u;
-          const uint32_t bar = epi_ready_bar(rb, g, sl);
-          if (p.has_res) {
-            int32_t c0, r0;
-            coords(n, c0, r0);
-            mbar_arrive_expect_tx(bar, kEpiSlotBytes);
-            tma_load_2d(slots_u32 + (g * 2 + sl) * kEpiSlotBytes, &p.res_map, bar, c0, r0);
-          } else {
-            mbar_arrive(bar);
-          }
-        };
-        for (int n = 0; n < 2 && n < total; ++n) prepare(n);
-        for (int n = 0; n < total; ++n) {
-          const uint32_t sl = (uint32_t)n & 1u;
-          mbar_wait(epi_full_bar(rb, g, sl), ((uint32_t)n >> 1) & 1u, kTagEpiFull);
-          int32_t c0, r0;
-          coords(n, c0, r0);
-          tma_store_2d(&p.out_map, slots_u32 + (g * 2 + sl) * kEpiSlotBytes, c0, r0);
-          tma_store_commit();
-          if (n + 2 < total) {
-            tma_store_wait_read<0>();                         // the store has left the tile
-            prepare(n + 2);
-          }
-        }
-        tma_store_wait<0>();                                  // all rows written before the CTA exits
-      }
-      __syncwarp();
     }
   } else {
     // ================================================================ epilogue warps 4..11
     setmaxnreg_inc<232>();
-    const EpiCtx cx{tmem_base, slots_u32, bars_u32 + 8u * (2 * kStages + 2), ss_smem, tmem_full_bar, tmem_empty_bar,
-                    rank, tile0, tile_stride};
+    const EpiCtx cx{tmem_base, epi_u32 + (uint32_t)(warp - kEpiFirstWarp) * kEpiStageBytes, ss_smem,
+                    tmem_full_bar, tmem_empty_bar, rank, tile0, tile_stride};
     if (warp < kEpiFirstWarp + 4) epilogue_group<kCg, TOut, 0>(p, cx);
     else epilogue_group<kCg, TOut, 1>(p, cx);
   }
