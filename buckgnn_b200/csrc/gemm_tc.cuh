@@ -51,9 +51,12 @@ template <int kCg> struct GemmCfg {
   static constexpr int kBTileBytes = kBRows * kStageKBytes;     // 64 KB / 32 KB
   static constexpr int kStageBytes = kATileBytes + kBTileBytes; // 80 KB / 48 KB
   static constexpr int kStages = (kCg == 1) ? 2 : 4;
-  static constexpr int kMiscBytes = 2048 + 256;                 // row sum-of-squares exchange + barriers
+  static constexpr int kMiscBytes = 128;                        // mbarriers + TMEM address slot
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kMiscBytes;
 };
+
+static_assert(GemmCfg<2>::kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory a CTA may have");
+static_assert((2 * GemmCfg<2>::kStages + 2) * 8 <= 96, "mbarriers overlap the TMEM address slot");
 
 struct alignas(64) GemmSeg { CUtensorMap a; CUtensorMap b; };
 
@@ -115,7 +118,8 @@ template <int kRegs> BG_DEVINL void setmaxnreg_dec() { asm volatile("setmaxnreg.
 
 struct EpiCtx {
   uint32_t tmem_base, stage_u32;    // stage_u32: this warp's 4 KB staging tile
-  float* ss_smem;
+  float* my_tile;                   // generic pointers to this warp's tile and to the tile of the warp that owns
+  const float* partner_tile;        // the other 256 columns of the same rows (row sum-of-squares exchange)
   uint32_t tmem_full_bar, tmem_empty_bar, rank;
   int tile0, tile_stride;
 };
@@ -226,11 +230,11 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
       else mbar_arrive_cluster(cx.tmem_empty_bar, 0);
     }
     float inv = 1.f;
-    if (p.normalize) {
-      float* ssb = cx.ss_smem + (it & 1u) * 256;
-      ssb[kG * 128 + row] = ss;
+    if (p.normalize) {                                          // exchange through the (idle) staging tiles
+      cx.my_tile[lane] = ss;
       named_bar_sync(1, 256);
-      inv = 1.f / fmaxf(sqrtf(ssb[row] + ssb[128 + row]), 1e-12f);
+      inv = 1.f / fmaxf(sqrtf(ss + cx.partner_tile[lane]), 1e-12f);
+      named_bar_sync(1, 256);                                   // partner has read before pass 2 reuses the tile
     }
     BG_PROF_ADD(_pacc_b);
     BG_PROF_T0();
@@ -357,9 +361,9 @@ k_gemm512(const __grid_constant__ GemmParams p) {
   const uint32_t stages_u32 = smem_base;
   const uint32_t epi_u32 = stages_u32 + kStages * Cfg::kStageBytes;
   constexpr int kEpiBytes = kEpiWarps * kEpiStageBytes;
-  float* ss_smem = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes + kEpiBytes);
-  const uint32_t bars_u32 = epi_u32 + kEpiBytes + 2048;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + kEpiBytes + 2048 + 192);
+  uint8_t* epi_gen = smem_gen + kStages * Cfg::kStageBytes;
+  const uint32_t bars_u32 = epi_u32 + kEpiBytes;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_gen + kEpiBytes + 96);
   auto full_bar = [&](int s) { return bars_u32 + 8u * s; };
   auto empty_bar = [&](int s) { return bars_u32 + 8u * (kStages + s); };
   const uint32_t tmem_full_bar = bars_u32 + 8u * (2 * kStages);
@@ -478,7 +482,10 @@ k_gemm512(const __grid_constant__ GemmParams p) {
   } else {
     // ================================================================ epilogue warps 4..11
     setmaxnreg_inc<232>();
-    const EpiCtx cx{tmem_base, epi_u32 + (uint32_t)(warp - kEpiFirstWarp) * kEpiStageBytes, ss_smem,
+    const int ew = warp - kEpiFirstWarp;
+    const EpiCtx cx{tmem_base, epi_u32 + (uint32_t)ew * kEpiStageBytes,
+                    reinterpret_cast<float*>(epi_gen + ew * kEpiStageBytes),
+                    reinterpret_cast<const float*>(epi_gen + (ew ^ 4) * kEpiStageBytes),
                     tmem_full_bar, tmem_empty_bar, rank, tile0, tile_stride};
     if (warp < kEpiFirstWarp + 4) epilogue_group<kCg, TOut, 0>(p, cx);
     else epilogue_group<kCg, TOut, 1>(p, cx);
