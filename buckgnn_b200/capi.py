@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("BG_LIB_PATH", _DEFAULT_LIB_PATH)
 BG_BF16, BG_F32, BG_F16 = 0, 1, 2
 BG_AGGR_MEAN, BG_AGGR_SUM, BG_AGGR_MAX = 0, 1, 2
 BG_BIG_ROW_THRESHOLD = 64
-BG_MAX_GEMM_SEGMENTS = 6
+BG_MAX_GEMM_SEGMENTS = 8
 ABI_VERSION = 2
 
 AGGR_CODES = {"mean": BG_AGGR_MEAN, "sum": BG_AGGR_SUM, "add": BG_AGGR_SUM, "max": BG_AGGR_MAX}
@@ -49,7 +49,7 @@ class GemmSegment(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [("bias_host", C.c_void_p), ("bn_scale_host", C.c_void_p), ("bn_shift_host", C.c_void_p),
                 ("residual", C.c_void_p), ("ldr", C.c_int64), ("normalize", C.c_int32), ("relu", C.c_int32),
-                ("bias2_host", C.c_void_p), ("gate_rowptr", C.c_void_p), ("gather", C.c_void_p * 2),
+                ("gather", C.c_void_p * 2),
                 ("gather_idx", C.c_void_p * 2), ("gather_ld", C.c_int64)]
 
 
@@ -68,7 +68,7 @@ _SIGNATURES = {
     "bg_batch_info": (C.c_int, [_P, _I64, _P, _P]),
     "bg_graph_ptr_build": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "bg_encoder_front": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
-    "bg_expand_rowptr": (C.c_int, [_P, _I64, _I64, _P, _P, _P]),
+    "bg_expand_rowptr": (C.c_int, [_P, _I64, _I64, _P, _P, _P, C.c_int, _P]),
     "bg_add": (C.c_int, [_P, _P, _P, _P, C.c_int, _I64, _P]),
     "bg_aggregate_workspace_bytes": (C.c_int, [_I32, _SZP]),
     "bg_sage_aggregate": (C.c_int, [_P, _P, C.c_int, _I64, _P, _P, _P, _I32, C.c_int, _P, C.c_size_t, _P]),
@@ -164,8 +164,9 @@ def encoder_front(x, n_nodes, n_features, w1, b1, w2, b2, out, out_dtype, stream
            "bg_encoder_front")
 
 
-def expand_rowptr(rowptr, n_rows, n_entries, row_of, iota, stream):
-    _check(load().bg_expand_rowptr(rowptr, n_rows, n_entries, row_of, iota, stream), "bg_expand_rowptr")
+def expand_rowptr(rowptr, n_rows, n_entries, row_of, iota, nonempty, nonempty_dtype, stream):
+    _check(load().bg_expand_rowptr(rowptr, n_rows, n_entries, row_of, iota, nonempty, nonempty_dtype, stream),
+           "bg_expand_rowptr")
 
 
 def add(a, b, c, out, dtype, n, stream):
@@ -179,15 +180,15 @@ def sage_aggregate(x, out, dtype, n_nodes, rowptr, col, big_rows, n_big, aggr, w
 
 def gemm512(segments, m, a_dtype, b_dtype, out, out_dtype, ldo, stream, *, bias=None, bn_scale=None,
             bn_shift=None, residual=None, ldr=0, normalize=False, relu=False, cta_group=2,
-            bias2=None, gate_rowptr=None, gather=(), gather_ld=512):
-    """segments: list of (a_ptr, lda, b_ptr, ldb, k); bias / bias2 / bn_scale / bn_shift are HOST pointers;
+            gather=(), gather_ld=512):
+    """segments: list of (a_ptr, lda, b_ptr, ldb, k); bias / bn_scale / bn_shift are HOST pointers;
     gather: up to two (matrix_ptr, index_ptr) pairs of gathered pre-activation addends."""
     n = len(segments)
     arr = (GemmSegment * n)(*[GemmSegment(a, lda, b, ldb, k, 0) for (a, lda, b, ldb, k) in segments])
     gm = (C.c_void_p * 2)(*([g[0] for g in gather] + [None] * (2 - len(gather))))
     gi = (C.c_void_p * 2)(*([g[1] for g in gather] + [None] * (2 - len(gather))))
     epi = Epilogue(bias, bn_scale, bn_shift, residual, ldr, int(bool(normalize)), int(bool(relu)),
-                   bias2, gate_rowptr, gm, gi, gather_ld)
+                   gm, gi, gather_ld)
     _check(load().bg_gemm512(arr, n, m, a_dtype, b_dtype, C.byref(epi), out, out_dtype, ldo, cta_group, stream),
            "bg_gemm512")
 

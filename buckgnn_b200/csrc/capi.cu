@@ -66,14 +66,21 @@ __global__ void k_split_tf32(const float* __restrict__ src, float* __restrict__ 
   }
 }
 
-// warp per row: the row's CSR slots get the row id; every slot also gets its own index
+// warp per row: the row's CSR slots get the row id; every slot also gets its own index; optionally
+// nonempty[r, 0:64] = [1 if the row has entries else 0, 0, 0, ...]  (a K = 64 GEMM operand)
+template <typename T>
 __global__ void k_expand_rowptr(const int32_t* __restrict__ rowptr, int64_t n_rows, int32_t* __restrict__ row_of,
-                                int32_t* __restrict__ iota) {
+                                int32_t* __restrict__ iota, T* __restrict__ nonempty) {
   const int lane = threadIdx.x & 31;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n_rows; r += n_warps) {
     const int32_t b = rowptr[r], e = rowptr[r + 1];
     for (int32_t i = b + lane; i < e; i += 32) { row_of[i] = (int32_t)r; iota[i] = i; }
+    if (nonempty) {
+      const float v0 = (lane == 0 && e > b) ? 1.f : 0.f;
+      if constexpr (sizeof(T) == 2) { nonempty[r * 64 + lane] = Pack16<T>::one(v0); nonempty[r * 64 + 32 + lane] = Pack16<T>::one(0.f); }
+      else { nonempty[r * 64 + lane] = v0; nonempty[r * 64 + 32 + lane] = 0.f; }
+    }
   }
 }
 
@@ -330,7 +337,7 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
   p.a_fmt = (uint32_t)a_fmt; p.b_fmt = (uint32_t)b_fmt;
   p.n_tiles = (int32_t)ceil_div64(m, kTileM * cta_group);
   p.m = m;
-  for (int i = 0; i < kHidden; ++i) { p.bias[i] = 0.f; p.bias2[i] = 0.f; p.scale[i] = 1.f; p.shift[i] = 0.f; }
+  for (int i = 0; i < kHidden; ++i) { p.bias[i] = 0.f; p.scale[i] = 1.f; p.shift[i] = 0.f; }
   if (epi) {
     if (epi->residual && (!aligned16(epi->residual) || (epi->ldr * osz) % 16 != 0 || epi->ldr < kHidden))
       return fail(BG_ERR_INVALID, "bg_gemm512: bad residual/ldr");
@@ -341,11 +348,6 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
       memcpy(p.shift, epi->bn_shift_host, sizeof(float) * kHidden);
     }
     p.normalize = epi->normalize; p.relu = epi->relu;
-    if (epi->bias2_host) {
-      if (!epi->gate_rowptr) return fail(BG_ERR_INVALID, "bg_gemm512: bias2 needs gate_rowptr");
-      memcpy(p.bias2, epi->bias2_host, sizeof(float) * kHidden);
-      p.gate_rowptr = epi->gate_rowptr;
-    }
     for (int k = 0; k < 2; ++k) {
       if (!epi->gather[k]) break;
       if (!epi->gather_idx[k] || !aligned16(epi->gather[k]) || (epi->gather_ld * osz) % 16 != 0 || epi->gather_ld < kHidden)
@@ -359,11 +361,13 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
     p.residual = epi->residual; p.ldr = epi->ldr;
   }
   p.out = out; p.ldo = ldo;
-#define BG_GEMM_OUT(CG, TF)                                                              \
-  (out_dtype == BG_BF16 ? launch_gemm512<CG, TF, __nv_bfloat16>(p, stream)               \
-   : out_dtype == BG_F16 ? launch_gemm512<CG, TF, __half>(p, stream)                     \
-                         : launch_gemm512<CG, TF, float>(p, stream))
-  return tf32 ? BG_GEMM_OUT(2, true) : BG_GEMM_OUT(2, false);
+#define BG_GEMM_OUT(ADD)                                                                 \
+  (out_dtype == BG_BF16 ? launch_gemm512<2, __nv_bfloat16, ADD>(p, stream)               \
+   : out_dtype == BG_F16 ? launch_gemm512<2, __half, ADD>(p, stream)                     \
+                         : launch_gemm512<2, float, ADD>(p, stream))
+  if (p.n_gather > 0) return BG_GEMM_OUT(kAddGather);
+  if (p.residual) return BG_GEMM_OUT(kAddResidual);
+  return BG_GEMM_OUT(kAddNone);
 #undef BG_GEMM_OUT
 }
 
@@ -404,12 +408,18 @@ int bg_pool_head(const void* x, int dtype, int64_t N, const int32_t* graph_ptr, 
 }
 
 // ------------------------------------------------------------------ EA-GNN helpers
-int bg_expand_rowptr(const int32_t* rowptr, int64_t n_rows, int64_t n_entries, int32_t* row_of, int32_t* iota, void* stream_) {
+int bg_expand_rowptr(const int32_t* rowptr, int64_t n_rows, int64_t n_entries, int32_t* row_of, int32_t* iota,
+                     void* nonempty, int nonempty_dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_rows < 0 || n_entries < 0 || (n_rows > 0 && !rowptr) || (n_entries > 0 && (!row_of || !iota)))
     return fail(BG_ERR_INVALID, "bg_expand_rowptr: bad argument");
-  if (n_rows == 0 || n_entries == 0) return BG_OK;
-  k_expand_rowptr<<<grid_for(n_rows * 32, 256, sm_count() * 32), 256, 0, stream>>>(rowptr, n_rows, row_of, iota);
+  if (n_rows == 0) return BG_OK;
+  const unsigned grid = grid_for(n_rows * 32, 256, sm_count() * 32);
+  if (!nonempty) k_expand_rowptr<float><<<grid, 256, 0, stream>>>(rowptr, n_rows, row_of, iota, nullptr);
+  else if (nonempty_dtype == BG_BF16) k_expand_rowptr<__nv_bfloat16><<<grid, 256, 0, stream>>>(rowptr, n_rows, row_of, iota, static_cast<__nv_bfloat16*>(nonempty));
+  else if (nonempty_dtype == BG_F16) k_expand_rowptr<__half><<<grid, 256, 0, stream>>>(rowptr, n_rows, row_of, iota, static_cast<__half*>(nonempty));
+  else if (nonempty_dtype == BG_F32) k_expand_rowptr<float><<<grid, 256, 0, stream>>>(rowptr, n_rows, row_of, iota, static_cast<float*>(nonempty));
+  else return fail(BG_ERR_INVALID, "bg_expand_rowptr: bad dtype");
   BG_LAUNCH_OK();
   return BG_OK;
 }

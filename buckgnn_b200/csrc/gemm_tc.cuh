@@ -77,9 +77,7 @@ struct alignas(64) GemmParams {
   const void* gather[2];            // [*, 512] row-major matrices of the output dtype, ld = gather_ld
   const int32_t* gidx[2];           // [M] row index into gather[k]
   int64_t gather_ld;
-  const int32_t* gate_rowptr;       // optional CSR rowptr [M+1]: bias2 is added only to rows with >= 1 entry
   float bias[kHidden];              // epilogue vectors by value -> constant bank, broadcast reads
-  float bias2[kHidden];             // gated bias (0 when unused)
   float scale[kHidden];             // 1 when there is no BN
   float shift[kHidden];             // 0 when there is no BN
 };
@@ -133,61 +131,70 @@ BG_DEVINL void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr) : "memory");
 }
 
-// 16 B from global memory that is read exactly once (skip rows): bypass L1
-BG_DEVINL uint4 ldg_stream_v4(const void* p) { return ldg_nc_v4(p); }
+// what pass 2 adds to the accumulator besides bias / BN: nothing, skip rows after the activation, or
+// gathered rows before it.  A template parameter of the kernel: the epilogue is fully unrolled
+// straight-line code (the register stash forbids loops), and dead variants would only evict live
+// code from the instruction cache (v4 of this kernel, 13k SASS instructions, spent most issue slots
+// stalled on instruction fetch -- sm__icc_request_hit_rate 52 %).
+enum : int { kAddNone = 0, kAddResidual = 1, kAddGather = 2 };
 
-// One column-half group (4 warps = 128 TMEM lanes = 128 output rows, 256 columns starting at
-// kG*256).  kG is a template parameter so every bias / scale / shift access is a constant-bank
-// operand with an immediate offset.
-template <int kCg, typename TOut, int kG>
-BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
+// One epilogue warp: 32 TMEM lanes = 32 output rows, the 256 columns starting at g*256.
+// `g` is a run-time value (both column halves share ONE copy of the code); the per-column
+// vectors are read from the constant bank as float4 at g*256 + immediate.
+template <int kCg, typename TOut, int kAdd>
+BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g) {
   constexpr bool kOut16 = sizeof(TOut) == 2;
   constexpr int kChunkCols = 128 / (int)sizeof(TOut);           // columns per 128-byte row chunk: 64 / 32
   constexpr int kChunks = 256 / kChunkCols;                     // 4 / 8
   constexpr int kPer = 16 / (int)sizeof(TOut);                  // 8 or 4 columns per 16-byte piece
-  constexpr int cb = kG * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;                                       // TMEM lane quarter this warp may read
-  const int row = q * 32 + lane;                                // this thread's row within the CTA's 128-row tile
+  const int cb = g * 256;
   const uint32_t taddr = cx.tmem_base + ((uint32_t)(q * 32) << 16) + cb;
-  // per-thread view of the staging tile (own row) and cooperative view (8 lanes per row, 4 rows per pass)
-  const uint32_t my_row_off = cx.stage_u32 + (uint32_t)lane * 128u;
+  const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cb);
+  const float4* scale4 = reinterpret_cast<const float4*>(p.scale + cb);
+  const float4* shift4 = reinterpret_cast<const float4*>(p.shift + cb);
+  // per-thread view of the staging tile (own row = lane) and cooperative view (8 lanes per row, 4 rows per pass;
+  // the swizzle of row 4t + r4 only depends on the parity of t)
+  const uint32_t my_row = cx.stage_u32 + (uint32_t)lane * 128u;
   const uint32_t my_sw = (uint32_t)(lane & 7);
   const int r4 = lane >> 3, piece = lane & 7;
-  const bool has_res = p.residual != nullptr;
-  const size_t out_esz = sizeof(TOut);
+  const uint32_t coop_even = cx.stage_u32 + (uint32_t)r4 * 128u + (((uint32_t)piece ^ (uint32_t)r4) << 4);
+  const uint32_t coop_odd = cx.stage_u32 + (uint32_t)(4 + r4) * 128u + (((uint32_t)piece ^ (uint32_t)(4 + r4)) << 4);
+  constexpr size_t esz = sizeof(TOut);
+  const size_t out_row_bytes = (size_t)p.ldo * esz;
   uint32_t it = 0;
   BG_PROF_DECL
   for (int tile = cx.tile0; tile < p.n_tiles; tile += cx.tile_stride, ++it) {
     const int64_t warp_row0 = (int64_t)tile * (kTileM * kCg) + (int64_t)cx.rank * kTileM + q * 32;
     const int64_t m_row = warp_row0 + lane;
-    const bool row_valid = m_row < p.m;
-    float gate = 0.f;
-    if (p.gate_rowptr && row_valid) gate = (p.gate_rowptr[m_row + 1] > p.gate_rowptr[m_row]) ? 1.f : 0.f;
-    int32_t gi0 = 0, gi1 = 0;
-    if (p.n_gather > 0 && row_valid) gi0 = p.gidx[0][m_row];
-    if (p.n_gather > 1 && row_valid) gi1 = p.gidx[1][m_row];
-
-    // cooperative fetch of one 128-byte chunk of "addend" rows (skip rows, or the first gathered matrix)
-    // for this warp's 32 rows: pass t covers rows 4t..4t+3, 8 lanes x 16 B per row
-    uint4 pre[8];
-    auto fetch_chunk = [&](int ch) {
-      const size_t col_off = (size_t)(cb + ch * kChunkCols) * out_esz + (size_t)piece * 16;
+    const int rows_here = (int)min((int64_t)32, p.m - warp_row0);                 // <= 0: nothing to store
+    [[maybe_unused]] int32_t gi0 = 0, gi1 = 0;
+    if constexpr (kAdd == kAddGather) {
+      if (m_row < p.m) { gi0 = p.gidx[0][m_row]; if (p.n_gather > 1) gi1 = p.gidx[1][m_row]; }
+    }
+    // addend rows of one 128-byte chunk for this warp's 32 rows: pass t covers rows 4t..4t+3, 8 lanes x 16 B each
+    [[maybe_unused]] uint4 pre[kAdd == kAddNone ? 1 : 8];
+    [[maybe_unused]] const char* add_base = nullptr;
+    if constexpr (kAdd == kAddResidual)
+      add_base = reinterpret_cast<const char*>(p.residual) + (size_t)(warp_row0 + r4) * p.ldr * esz + (size_t)cb * esz + piece * 16;
+    if constexpr (kAdd == kAddGather)
+      add_base = reinterpret_cast<const char*>(p.gather[0]) + (size_t)cb * esz + piece * 16;
+    auto fetch = [&](int ch) {
+      if constexpr (kAdd == kAddResidual) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int rr = t * 4 + r4;
-        if (has_res) {
-          const int64_t gr = warp_row0 + rr;
-          pre[t] = (gr < p.m) ? ldg_stream_v4(reinterpret_cast<const char*>(p.residual) + (size_t)gr * p.ldr * out_esz + col_off)
-                              : make_uint4(0u, 0u, 0u, 0u);
-        } else {
-          const int32_t n0 = __shfl_sync(0xffffffffu, gi0, rr);
-          pre[t] = ldg_v4(reinterpret_cast<const char*>(p.gather[0]) + (size_t)n0 * p.gather_ld * out_esz + col_off);
+        for (int t = 0; t < 8; ++t)
+          pre[t] = (t * 4 + r4 < rows_here) ? ldg_nc_v4(add_base + (size_t)t * 4 * p.ldr * esz + ch * 128)
+                                            : make_uint4(0u, 0u, 0u, 0u);
+      } else if constexpr (kAdd == kAddGather) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int32_t n0 = __shfl_sync(0xffffffffu, gi0, t * 4 + r4);
+          pre[t] = ldg_v4(add_base + (size_t)n0 * p.gather_ld * esz + ch * 128);
         }
       }
     };
-    const bool has_addend = has_res || p.n_gather > 0;
-    if (has_addend) fetch_chunk(0);                             // in flight while we wait for the MMAs
+    fetch(0);                                                   // in flight while we wait for the MMAs
 
     BG_PROF_T0();
     mbar_wait(cx.tmem_full_bar, it & 1u, kTagTmemFull);
@@ -199,29 +206,30 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
     // TMEM loads are double-buffered (16 columns each) so their latency hides behind the math.
     [[maybe_unused]] uint32_t stash[kOut16 ? 128 : 1];
     float ss = 0.f;
-    {
+    if (kOut16 || p.normalize) {
       uint32_t ra[16], rb[16];
       auto consume = [&](const uint32_t (&r)[16], int c16) {    // c16: index of the 16-column block
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float a = __uint_as_float(r[2 * i]) + fmaf(gate, p.bias2[cb + c16 * 16 + 2 * i], p.bias[cb + c16 * 16 + 2 * i]);
-          const float b = __uint_as_float(r[2 * i + 1]) + fmaf(gate, p.bias2[cb + c16 * 16 + 2 * i + 1], p.bias[cb + c16 * 16 + 2 * i + 1]);
-          ss = fmaf(a, a, ss);
-          ss = fmaf(b, b, ss);
-          if constexpr (kOut16) stash[c16 * 8 + i] = Pack16<TOut>::pack(a, b);
+        for (int i = 0; i < 4; ++i) {
+          const float4 b = bias4[c16 * 4 + i];
+          const float v0 = __uint_as_float(r[4 * i]) + b.x, v1 = __uint_as_float(r[4 * i + 1]) + b.y;
+          const float v2 = __uint_as_float(r[4 * i + 2]) + b.z, v3 = __uint_as_float(r[4 * i + 3]) + b.w;
+          ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
+          if constexpr (kOut16) {
+            stash[c16 * 8 + 2 * i] = Pack16<TOut>::pack(v0, v1);
+            stash[c16 * 8 + 2 * i + 1] = Pack16<TOut>::pack(v2, v3);
+          }
         }
       };
-      if (kOut16 || p.normalize) {
-        tmem_ld_32x16(taddr, ra);
+      tmem_ld_32x16(taddr, ra);
 #pragma unroll
-        for (int c = 0; c < 16; c += 2) {
-          tmem_ld_wait();
-          tmem_ld_32x16(taddr + (c + 1) * 16, rb);
-          consume(ra, c);
-          tmem_ld_wait();
-          if (c + 2 < 16) tmem_ld_32x16(taddr + (c + 2) * 16, ra);
-          consume(rb, c + 1);
-        }
+      for (int c = 0; c < 16; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x16(taddr + (c + 1) * 16, rb);
+        consume(ra, c);
+        tmem_ld_wait();
+        if (c + 2 < 16) tmem_ld_32x16(taddr + (c + 2) * 16, ra);
+        consume(rb, c + 1);
       }
     }
     if constexpr (kOut16) {                                     // accumulator fully read: release TMEM now
@@ -239,35 +247,34 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
     BG_PROF_ADD(_pacc_b);
     BG_PROF_T0();
 
-    // ---- pass 2: normalize / BN / ReLU / skip, 128-byte row chunks through the warp's staging tile
+    // ---- pass 2: normalize / BN / ReLU / addends, 128-byte row chunks through the warp's staging tile
+    char* out_base = reinterpret_cast<char*>(p.out) + (size_t)(warp_row0 + r4) * out_row_bytes + (size_t)cb * esz + piece * 16;
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
-      const size_t col_off = (size_t)(cb + ch * kChunkCols) * out_esz + (size_t)piece * 16;
-      if (has_addend) {
-        // park the prefetched addend rows (second gathered matrix added on the way) in the staging tile
-        if (p.n_gather > 1) {
+      if constexpr (kAdd != kAddNone) {
+        if constexpr (kAdd == kAddGather) {
+          if (p.n_gather > 1) {                                 // second gathered matrix, summed on the way in
+            const char* g1_base = reinterpret_cast<const char*>(p.gather[1]) + (size_t)cb * esz + piece * 16 + ch * 128;
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int32_t n1 = __shfl_sync(0xffffffffu, gi1, t * 4 + r4);
-            const uint4 g1 = ldg_v4(reinterpret_cast<const char*>(p.gather[1]) + (size_t)n1 * p.gather_ld * out_esz + col_off);
-            if constexpr (kOut16) {
-              pre[t].x = Pack16<TOut>::hadd2(pre[t].x, g1.x); pre[t].y = Pack16<TOut>::hadd2(pre[t].y, g1.y);
-              pre[t].z = Pack16<TOut>::hadd2(pre[t].z, g1.z); pre[t].w = Pack16<TOut>::hadd2(pre[t].w, g1.w);
-            } else {
-              pre[t].x = __float_as_uint(__uint_as_float(pre[t].x) + __uint_as_float(g1.x));
-              pre[t].y = __float_as_uint(__uint_as_float(pre[t].y) + __uint_as_float(g1.y));
-              pre[t].z = __float_as_uint(__uint_as_float(pre[t].z) + __uint_as_float(g1.z));
-              pre[t].w = __float_as_uint(__uint_as_float(pre[t].w) + __uint_as_float(g1.w));
+            for (int t = 0; t < 8; ++t) {
+              const int32_t n1 = __shfl_sync(0xffffffffu, gi1, t * 4 + r4);
+              const uint4 g1 = ldg_v4(g1_base + (size_t)n1 * p.gather_ld * esz);
+              if constexpr (kOut16) {
+                pre[t].x = Pack16<TOut>::hadd2(pre[t].x, g1.x); pre[t].y = Pack16<TOut>::hadd2(pre[t].y, g1.y);
+                pre[t].z = Pack16<TOut>::hadd2(pre[t].z, g1.z); pre[t].w = Pack16<TOut>::hadd2(pre[t].w, g1.w);
+              } else {
+                pre[t].x = __float_as_uint(__uint_as_float(pre[t].x) + __uint_as_float(g1.x));
+                pre[t].y = __float_as_uint(__uint_as_float(pre[t].y) + __uint_as_float(g1.y));
+                pre[t].z = __float_as_uint(__uint_as_float(pre[t].z) + __uint_as_float(g1.z));
+                pre[t].w = __float_as_uint(__uint_as_float(pre[t].w) + __uint_as_float(g1.w));
+              }
             }
           }
         }
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int rr = t * 4 + r4;
-          sts_v4(cx.stage_u32 + (uint32_t)rr * 128u + (((uint32_t)piece ^ (uint32_t)(rr & 7)) << 4), pre[t]);
-        }
+        for (int t = 0; t < 8; ++t) sts_v4(((t & 1) ? coop_odd : coop_even) + (uint32_t)(t >> 1) * 1024u, pre[t]);
         __syncwarp();
-        if (ch + 1 < kChunks) fetch_chunk(ch + 1);              // next chunk's addends fly during the math below
+        if (ch + 1 < kChunks) fetch(ch + 1);                    // next chunk's addends fly during the math below
       }
       [[maybe_unused]] uint32_t r[32];
       if constexpr (!kOut16) {
@@ -281,22 +288,24 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {                             // 16-byte pieces of this thread's 128-byte row chunk
-        const uint32_t addr = my_row_off + (((uint32_t)j ^ my_sw) << 4);
+        const uint32_t addr = my_row + (((uint32_t)j ^ my_sw) << 4);
         float v[kPer];
+        if constexpr (kOut16) {
 #pragma unroll
-        for (int e = 0; e < kPer; ++e) {
-          const int c = cb + ch * kChunkCols + j * kPer + e;    // compile-time constant
-          if constexpr (kOut16) {
-            const uint32_t u = stash[ch * 32 + j * 4 + (e >> 1)];
-            v[e] = (e & 1) ? Pack16<TOut>::hi(u) : Pack16<TOut>::lo(u);
-          } else {
-            v[e] = __uint_as_float(r[j * 4 + e]) + fmaf(gate, p.bias2[c], p.bias[c]);
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t u = stash[ch * 32 + j * 4 + e];
+            v[2 * e] = Pack16<TOut>::lo(u);
+            v[2 * e + 1] = Pack16<TOut>::hi(u);
           }
+        } else {
+          const float4 b = bias4[ch * 8 + j];
+          v[0] = __uint_as_float(r[j * 4]) + b.x; v[1] = __uint_as_float(r[j * 4 + 1]) + b.y;
+          v[2] = __uint_as_float(r[j * 4 + 2]) + b.z; v[3] = __uint_as_float(r[j * 4 + 3]) + b.w;
         }
-        uint4 ad = make_uint4(0u, 0u, 0u, 0u);
-        if (has_addend) ad = lds_v4(addr);
-        const uint32_t au[4] = {ad.x, ad.y, ad.z, ad.w};
-        if (p.n_gather > 0) {                                   // gathered addends enter before the activation
+        [[maybe_unused]] uint4 ad;
+        if constexpr (kAdd != kAddNone) ad = lds_v4(addr);
+        if constexpr (kAdd == kAddGather) {                     // gathered addends enter before the activation
+          const uint32_t au[4] = {ad.x, ad.y, ad.z, ad.w};
           if constexpr (kOut16) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) Pack16<TOut>::add2(v[2 * e], v[2 * e + 1], au[e]);
@@ -306,13 +315,18 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
           }
         }
 #pragma unroll
-        for (int e = 0; e < kPer; ++e) {
-          const int c = cb + ch * kChunkCols + j * kPer + e;
-          float a = fmaf(v[e] * inv, p.scale[c], p.shift[c]);
-          if (p.relu) a = fmaxf(a, 0.f);
-          v[e] = a;
+        for (int e4 = 0; e4 < kPer / 4; ++e4) {
+          const float4 sc = scale4[(ch * kChunkCols + j * kPer) / 4 + e4];
+          const float4 sh = shift4[(ch * kChunkCols + j * kPer) / 4 + e4];
+          v[4 * e4] = fmaf(v[4 * e4] * inv, sc.x, sh.x); v[4 * e4 + 1] = fmaf(v[4 * e4 + 1] * inv, sc.y, sh.y);
+          v[4 * e4 + 2] = fmaf(v[4 * e4 + 2] * inv, sc.z, sh.z); v[4 * e4 + 3] = fmaf(v[4 * e4 + 3] * inv, sc.w, sh.w);
         }
-        if (has_res) {                                          // skip rows enter after it
+        if (p.relu) {
+#pragma unroll
+          for (int e = 0; e < kPer; ++e) v[e] = fmaxf(v[e], 0.f);
+        }
+        if constexpr (kAdd == kAddResidual) {                   // skip rows enter after it
+          const uint32_t au[4] = {ad.x, ad.y, ad.z, ad.w};
           if constexpr (kOut16) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) Pack16<TOut>::add2(v[2 * e], v[2 * e + 1], au[e]);
@@ -334,10 +348,8 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
       // coalesced store: 4 rows x 128 B per instruction
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
-        const int rr = t * 4 + r4;
-        const int64_t gr = warp_row0 + rr;
-        const uint4 o = lds_v4(cx.stage_u32 + (uint32_t)rr * 128u + (((uint32_t)piece ^ (uint32_t)(rr & 7)) << 4));
-        if (gr < p.m) stg_v4(reinterpret_cast<char*>(p.out) + (size_t)gr * p.ldo * out_esz + col_off, o);
+        const uint4 o = lds_v4(((t & 1) ? coop_odd : coop_even) + (uint32_t)(t >> 1) * 1024u);
+        if (t * 4 + r4 < rows_here) stg_v4(out_base + (size_t)t * 4 * out_row_bytes + ch * 128, o);
       }
       __syncwarp();
     }
@@ -350,7 +362,7 @@ BG_DEVINL void epilogue_group(const GemmParams& p, const EpiCtx& cx) {
 #endif
 }
 
-template <int kCg, bool kTf32, typename TOut>
+template <int kCg, typename TOut, int kAdd>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm512(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<kCg>;
@@ -438,6 +450,7 @@ k_gemm512(const __grid_constant__ GemmParams p) {
     } else if (warp == 1 && rank == 0) {
       // ================================================================ MMA issuer (leader CTA)
       const uint32_t idesc = umma_idesc(p.a_fmt, p.b_fmt, kTileM * kCg, 256);
+      const bool tf32 = p.a_fmt == 2;
       BG_PROF_DECL
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = tile0; tile < p.n_tiles; tile += tile_stride, ++it) {
@@ -462,7 +475,9 @@ k_gemm512(const __grid_constant__ GemmParams p) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   const uint64_t db = umma_smem_desc(sb + h * (Cfg::kBTileBytes / 2) + k * 32);
-                  umma<kCg, kTf32>(tmem_base + h * 256, da, db, idesc, (first && k == 0) ? 0u : 1u);
+                  const uint32_t acc = (first && k == 0) ? 0u : 1u;
+                  if (tf32) umma<kCg, true>(tmem_base + h * 256, da, db, idesc, acc);
+                  else umma<kCg, false>(tmem_base + h * 256, da, db, idesc, acc);
                 }
               }
               umma_commit<kCg>(empty_bar(stage));                   // smem slot reusable once these MMAs retire
@@ -487,8 +502,7 @@ k_gemm512(const __grid_constant__ GemmParams p) {
                     reinterpret_cast<float*>(epi_gen + ew * kEpiStageBytes),
                     reinterpret_cast<const float*>(epi_gen + (ew ^ 4) * kEpiStageBytes),
                     tmem_full_bar, tmem_empty_bar, rank, tile0, tile_stride};
-    if (warp < kEpiFirstWarp + 4) epilogue_group<kCg, TOut, 0>(p, cx);
-    else epilogue_group<kCg, TOut, 1>(p, cx);
+    epilogue_warp<kCg, TOut, kAdd>(p, cx, ew >> 2);
   }
 
   // ---- teardown
@@ -526,10 +540,10 @@ static inline int make_operand_map(CUtensorMap* map, const void* base, int64_t r
   return r == CUDA_SUCCESS ? BG_OK : BG_ERR_CUDA;
 }
 
-template <int kCg, bool kTf32, typename TOut>
+template <int kCg, typename TOut, int kAdd>
 static int launch_gemm512(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<kCg>;
-  auto kern = k_gemm512<kCg, kTf32, TOut>;
+  auto kern = k_gemm512<kCg, TOut, kAdd>;
   static bool attr_set = false;
   if (!attr_set) {
     BG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

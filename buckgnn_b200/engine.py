@@ -361,11 +361,13 @@ class GNBlockPack:
                     =  (x Wp1a^T)[col] + h_e (Wp1b W2)^T + (Wp1b b2 + bp1)          (edge_mlp L2 folded in)
       scatter_mean then phi L2 then gamma L1 (all linear in between):
                     cat[x, agg] Wg1^T = x Wg1a^T + mean(h_m) (Wg1b Wp2)^T + gate (Wg1b bp2) + bg1
+      where gate = 1 for rows with a non-empty scatter_mean segment: a third K = 64 segment whose A operand is
+      the indicator matrix from bg_expand_rowptr and whose weight has Wg1b bp2 in column 0.
     """
     w1a: LinearPack; w1b: LinearPack; w1c: LinearPack; b1: torch.Tensor
     w2: LinearPack; b2: torch.Tensor
     wp1a: LinearPack; w3c: LinearPack; b3c: torch.Tensor
-    wg1a: LinearPack; wgc: LinearPack; bg1: torch.Tensor; bg2c: torch.Tensor
+    wg1a: LinearPack; wgc: LinearPack; bg1: torch.Tensor; wgate: LinearPack
     wg2: LinearPack; bg2: torch.Tensor
     wb1: LinearPack; bb1: torch.Tensor
     wb2: LinearPack; bb2: torch.Tensor
@@ -390,7 +392,8 @@ def pack_gnblock(blk, precision: str) -> GNBlockPack:
         w1a=lp(W1[:, :h]), w1b=lp(W1[:, h:2 * h]), w1c=lp(W1[:, 2 * h:]), b1=hv(b1),
         w2=lp(W2), b2=hv(b2),
         wp1a=lp(Wp1[:, :h]), w3c=lp(Wp1b @ W2), b3c=hv(Wp1b @ b2 + bp1),
-        wg1a=lp(Wg1[:, :h]), wgc=lp(Wg1b @ Wp2), bg1=hv(bg1), bg2c=hv(Wg1b @ bp2),
+        wg1a=lp(Wg1[:, :h]), wgc=lp(Wg1b @ Wp2), bg1=hv(bg1),
+        wgate=lp(torch.cat([(Wg1b @ bp2)[:, None], torch.zeros(h, 63, dtype=torch.float64)], 1)),
         wg2=lp(Wg2), bg2=hv(bg2), wb1=lp(Wb1), bb1=hv(bb1), wb2=lp(Wb2), bb2=hv(bb2))
 
 
@@ -398,15 +401,19 @@ def pack_gnblock(blk, precision: str) -> GNBlockPack:
 class EdgeIndexExtras:
     row_of: torch.Tensor     # [E] int32: key node of CSR slot i
     iota: torch.Tensor       # [E] int32: 0..E-1
+    nonempty: "Activation"   # [N, 64]: column 0 = 1 where the node has >= 1 CSR slot
 
 
-def edge_extras(idx: GraphIndex) -> EdgeIndexExtras:
+def edge_extras(idx: GraphIndex, precision: str) -> EdgeIndexExtras:
     dev = idx.rowptr.device
     e = max(idx.n_edges, 1)
     row_of = torch.empty(e, dtype=torch.int32, device=dev)
     iota = torch.empty(e, dtype=torch.int32, device=dev)
-    capi.expand_rowptr(idx.rowptr.data_ptr(), idx.n_nodes, idx.n_edges, row_of.data_ptr(), iota.data_ptr(), _stream())
-    return EdgeIndexExtras(row_of, iota)
+    nonempty = Activation(idx.n_nodes, 64, precision, dev)
+    capi.expand_rowptr(idx.rowptr.data_ptr(), idx.n_nodes, idx.n_edges, row_of.data_ptr(), iota.data_ptr(),
+                       nonempty.data.data_ptr(), nonempty.code, _stream())
+    nonempty.refresh_split()
+    return EdgeIndexExtras(row_of, iota, nonempty)
 
 
 def add_into(out: Activation, a: Activation, b: Activation) -> None:
@@ -457,8 +464,8 @@ def gnblock_layer(x: Activation, e: Activation, buf: GNBlockBuffers, idx: GraphI
                             ws.data_ptr(), ws_bytes, _stream())
     buf.mh.refresh_split()
     with TIMERS.span("gn_node_gemms"):
-        G(buf.g1, _segments(x, w.wg1a) + _segments(buf.mh, w.wgc), n, bias=hp(w.bg1), bias2=hp(w.bg2c),
-          gate_rowptr=idx.rowptr.data_ptr(), relu=True)
+        gate_segs = _segments(ex.nonempty, w.wgate)[:2]      # the indicator is exact in tf32: its lo part is 0
+        G(buf.g1, _segments(x, w.wg1a) + _segments(buf.mh, w.wgc) + gate_segs, n, bias=hp(w.bg1), relu=True)
         G(buf.xg, _segments(buf.g1, w.wg2), n, bias=hp(w.bg2))
         G(buf.t, _segments(buf.xg, w.wb1), n, bias=hp(w.bb1), relu=True)
         res = buf.xg

@@ -266,7 +266,7 @@ class BuckGNN(nn.Module):
         engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg)                 # :323
         idx = pending.finish()
         ne = idx.n_edges
-        ex = engine.edge_extras(idx)
+        ex = engine.edge_extras(idx, prec)
         e = Activation(max(ne, 1), 512, prec, x.device)
         if ne > 0:                                   # edge_encoder on edge_attr in CSR order (:327, :376)
             engine.encoder_forward(edge_attr, packs["edge_enc"], packs["edge_enc_w3"], prec, e, cg,

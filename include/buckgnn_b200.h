@@ -119,13 +119,11 @@ int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t n_nodes,
  * Replaces `lin_l(agg) + lin_r(x)`, `F.normalize`, `BatchNorm1d` (eval), `ReLU`
  * and the skip connection (Models/BuckGNN.py:449-457 and PyG SAGEConv.forward).
  * Epilogue order (each step optional):
- *    v = acc + bias + gate[m]*bias2;   v += G0[gidx0[m], :] + G1[gidx1[m], :];
+ *    v = acc + bias;   v += G0[gidx0[m], :] + G1[gidx1[m], :];
  *    v /= max(||v||_2, 1e-12);  v = v*bn_scale + bn_shift;  v = max(v, 0);  v += residual[m, :]
  * The gathered addends serve the EA-GNN block (Models/BuckGNN.py:556-560), where
  * cat[x[row], x[col], e] W^T is evaluated as (x W_a^T)[row] + (x W_b^T)[col] + e W_c^T: the two
  * node-level products are gathered per edge inside the epilogue of the edge-level GEMM.
- * gate[m] = 1 if gate_rowptr[m+1] > gate_rowptr[m] else 0 (a bias that only applies to rows
- * whose segment is non-empty, i.e. scatter_mean's empty-row = 0 after folding a Linear through it).
  * normalize cannot be combined with gathered addends, nor gathered addends with residual.
  * Operand formats: a_dtype == b_dtype in {BG_BF16, BG_F16} (tcgen05 kind::f16, k_s % 64 == 0;
  * the hardware rejects bf16 x fp16 mixes) or both BG_F32 (read as
@@ -133,7 +131,7 @@ int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t n_nodes,
  * is the 3xTF32 "fp32-GEMM" mode).  fp32 accumulation in TMEM always.
  * out/residual dtype = out_dtype (any bg_dtype).  All base pointers 16-byte aligned, ld* such that
  * rows are 16-byte aligned.  cta_group must be 2 (tcgen05 cta_group::2 CTA pairs). */
-#define BG_MAX_GEMM_SEGMENTS 6
+#define BG_MAX_GEMM_SEGMENTS 8
 typedef struct bg_gemm_segment {
   const void* a; int64_t lda;
   const void* b; int64_t ldb;
@@ -148,8 +146,6 @@ typedef struct bg_epilogue {
   int64_t ldr;
   int32_t normalize;           /* F.normalize(p=2, dim=-1, eps=1e-12) */
   int32_t relu;
-  const float* bias2_host;     /* [512] HOST, gated second bias, or NULL                   */
-  const int32_t* gate_rowptr;  /* DEVICE [M+1] CSR offsets defining gate[m], or NULL       */
   const void* gather[2];       /* DEVICE [*,512] matrices of out_dtype (ld = gather_ld), NULL = absent */
   const int32_t* gather_idx[2];/* DEVICE [M] row index into gather[k]                      */
   int64_t gather_ld;
@@ -184,11 +180,14 @@ int bg_pool_head(const void* x, int dtype, int64_t n_nodes, const int32_t* graph
 /* ------------------------------------------------------------------ EA-GNN helpers
  * bg_expand_rowptr: row_of[i] = r with rowptr[r] <= i < rowptr[r+1], iota[i] = i   (i < E)
  *   (row ids of the CSR slots, and the identity "col" that turns bg_sage_aggregate into the
- *   segmented mean torch_scatter.scatter_mean(messages, row) needs once edges are in CSR order).
+ *   segmented mean torch_scatter.scatter_mean(messages, row) needs once edges are in CSR order);
+ *   nonempty (optional, [n_rows, 64] of nonempty_dtype): column 0 = 1 for rows with >= 1 entry, rest 0 --
+ *   a K = 64 GEMM segment that applies a bias only to rows whose scatter_mean segment is non-empty
+ *   (what remains of phi's second-layer bias after that Linear is folded through the mean).
  * bg_add: out = a + b (+ c) elementwise over n values of `dtype`, fp32 math (skip connections
  *   of the EA-GNN wrapper, Models/BuckGNN.py:382-384). */
 int bg_expand_rowptr(const int32_t* rowptr, int64_t n_rows, int64_t n_entries, int32_t* row_of, int32_t* iota,
-                     void* stream);
+                     void* nonempty, int nonempty_dtype, void* stream);
 int bg_add(const void* a, const void* b, const void* c_or_null, void* out, int dtype, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------ helpers
