@@ -50,7 +50,10 @@ template <int kCg> struct GemmCfg {
   static constexpr int kBRows = kHidden / kCg;                  // weight rows held by one CTA
   static constexpr int kBTileBytes = kBRows * kStageKBytes;     // 64 KB / 32 KB
   static constexpr int kStageBytes = kATileBytes + kBTileBytes; // 80 KB / 48 KB
-  static constexpr int kStages = (kCg == 1) ? 2 : 4;
+#ifndef BG_GEMM_STAGES
+#define BG_GEMM_STAGES 4
+#endif
+  static constexpr int kStages = (kCg == 1) ? 2 : BG_GEMM_STAGES;
   static constexpr int kMiscBytes = 128;                        // mbarriers + TMEM address slot
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kMiscBytes;
 };
