@@ -68,10 +68,10 @@ _SIGNATURES = {
     "bg_batch_info": (C.c_int, [_P, _I64, _P, _P]),
     "bg_graph_ptr_build": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "bg_encoder_front": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
-    "bg_expand_rowptr": (C.c_int, [_P, _I64, _I64, _P, _P, _P, C.c_int, _P]),
+    "bg_expand_rowptr": (C.c_int, [_P, _I64, _I64, _P, _P, _P, C.c_int, C.c_int, _P]),
     "bg_add": (C.c_int, [_P, _P, _P, _P, C.c_int, _I64, _P]),
     "bg_aggregate_workspace_bytes": (C.c_int, [_I32, _SZP]),
-    "bg_sage_aggregate": (C.c_int, [_P, _P, C.c_int, _I64, _P, _P, _P, _I32, C.c_int, _P, C.c_size_t, _P]),
+    "bg_sage_aggregate": (C.c_int, [_P, _P, C.c_int, _I64, _I32, _P, _P, _P, _I32, C.c_int, _P, C.c_size_t, _P]),
     "bg_gemm512": (C.c_int, [C.POINTER(GemmSegment), _I32, _I64, C.c_int, C.c_int, C.POINTER(Epilogue), _P,
                              C.c_int, _I64, C.c_int, _P]),
     "bg_pool_workspace_bytes": (C.c_int, [_I64, _SZP]),
@@ -164,17 +164,17 @@ def encoder_front(x, n_nodes, n_features, w1, b1, w2, b2, out, out_dtype, stream
            "bg_encoder_front")
 
 
-def expand_rowptr(rowptr, n_rows, n_entries, row_of, iota, nonempty, nonempty_dtype, stream):
-    _check(load().bg_expand_rowptr(rowptr, n_rows, n_entries, row_of, iota, nonempty, nonempty_dtype, stream),
-           "bg_expand_rowptr")
+def expand_rowptr(rowptr, n_rows, n_entries, row_of, iota, nonempty, nonempty_dtype, stream, as_count=False):
+    _check(load().bg_expand_rowptr(rowptr, n_rows, n_entries, row_of, iota, nonempty, nonempty_dtype,
+                                   int(bool(as_count)), stream), "bg_expand_rowptr")
 
 
 def add(a, b, c, out, dtype, n, stream):
     _check(load().bg_add(a, b, c, out, dtype, n, stream), "bg_add")
 
 
-def sage_aggregate(x, out, dtype, n_nodes, rowptr, col, big_rows, n_big, aggr, ws, ws_bytes, stream):
-    _check(load().bg_sage_aggregate(x, out, dtype, n_nodes, rowptr, col, big_rows, n_big, aggr, ws, ws_bytes,
+def sage_aggregate(x, out, dtype, n_nodes, rowptr, col, big_rows, n_big, aggr, ws, ws_bytes, stream, width=512):
+    _check(load().bg_sage_aggregate(x, out, dtype, n_nodes, width, rowptr, col, big_rows, n_big, aggr, ws, ws_bytes,
                                     stream), "bg_sage_aggregate")
 
 

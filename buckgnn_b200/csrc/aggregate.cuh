@@ -217,4 +217,160 @@ k_aggregate_hubs(const T* __restrict__ x, T* __restrict__ out,
   if (threadIdx.x == 0) ticket[hub] = 0;    // leave the ticket ready for the next launch
 }
 
+
+// ------------------------------------------------------------------ 128-column rows
+// The same aggregation over [N,128] rows (the node encoder's hidden layer): its last Linear is linear, so
+// mean/sum aggregation commutes with it and layer 0 can aggregate 128 instead of 512 columns
+// (engine.py: folded first layer).  A row is 256 B (16-bit: 16 lanes x 16 B, two rows per warp) or
+// 512 B (fp32: one row per warp).
+template <typename T> struct Narrow {
+  static constexpr int kCols = 128;
+  static constexpr int kLanes = kCols * (int)sizeof(T) / 16;   // lanes per row: 16 or 32
+  static constexpr int kVals = 16 / (int)sizeof(T);            // values per lane: 8 or 4
+  static constexpr int kRowsPerWarp = 32 / kLanes;
+};
+
+template <typename T, int kAggr>
+BG_DEVINL void narrow_accumulate(float (&acc)[Narrow<T>::kVals], const uint4& q) {
+  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+  if constexpr (sizeof(T) == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (kAggr == BG_AGGR_MAX) {
+        acc[2 * i] = fmaxf(acc[2 * i], Pack16<T>::lo(u[i]));
+        acc[2 * i + 1] = fmaxf(acc[2 * i + 1], Pack16<T>::hi(u[i]));
+      } else {
+        Pack16<T>::add2(acc[2 * i], acc[2 * i + 1], u[i]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = agg_op<kAggr>(acc[i], __uint_as_float(u[i]));
+  }
+}
+
+template <typename T> BG_DEVINL uint4 narrow_pack(const float (&v)[Narrow<T>::kVals]) {
+  uint4 o;
+  if constexpr (sizeof(T) == 2) {
+    o.x = Pack16<T>::pack(v[0], v[1]); o.y = Pack16<T>::pack(v[2], v[3]);
+    o.z = Pack16<T>::pack(v[4], v[5]); o.w = Pack16<T>::pack(v[6], v[7]);
+  } else {
+    o.x = __float_as_uint(v[0]); o.y = __float_as_uint(v[1]); o.z = __float_as_uint(v[2]); o.w = __float_as_uint(v[3]);
+  }
+  return o;
+}
+
+// accumulate rows col[beg..end) of the [*,128] matrix x; executed by one sub-warp of Narrow<T>::kLanes lanes
+template <typename T, int kAggr>
+BG_DEVINL void narrow_gather(const T* __restrict__ x, const int32_t* __restrict__ col, int32_t beg, int32_t end,
+                             int sl, uint32_t mask, float (&acc)[Narrow<T>::kVals]) {
+  constexpr int kLanes = Narrow<T>::kLanes;
+  const char* xb = reinterpret_cast<const char*>(x) + (size_t)sl * 16;
+  constexpr size_t kRowBytes = 128 * sizeof(T);
+  for (int32_t base = beg; base < end; base += kLanes) {
+    const int32_t cnt = min(kLanes, end - base);
+    const int32_t my = (sl < cnt) ? col[base + sl] : 0;
+    int32_t j = 0;
+    for (; j + 4 <= cnt; j += 4) {
+      const uint4 q0 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j, kLanes) * kRowBytes);
+      const uint4 q1 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 1, kLanes) * kRowBytes);
+      const uint4 q2 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 2, kLanes) * kRowBytes);
+      const uint4 q3 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 3, kLanes) * kRowBytes);
+      narrow_accumulate<T, kAggr>(acc, q0); narrow_accumulate<T, kAggr>(acc, q1);
+      narrow_accumulate<T, kAggr>(acc, q2); narrow_accumulate<T, kAggr>(acc, q3);
+    }
+    for (; j < cnt; ++j)
+      narrow_accumulate<T, kAggr>(acc, ldg_v4(xb + (size_t)__shfl_sync(mask, my, j, kLanes) * kRowBytes));
+  }
+}
+
+template <typename T, int kAggr>
+__global__ void __launch_bounds__(1024, 1)
+k_aggregate_rows128(const T* __restrict__ x, T* __restrict__ out, int64_t N,
+                    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col) {
+  using NW = Narrow<T>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / NW::kLanes, sl = lane % NW::kLanes;
+  const uint32_t mask = (NW::kLanes == 32) ? 0xffffffffu : (0xffffu << (16 * sub));
+  const int64_t band = (N + gridDim.x - 1) / gridDim.x;
+  const int64_t r_beg = (int64_t)blockIdx.x * band;
+  const int64_t r_end = min(N, r_beg + band);
+  constexpr int kRowsPerIter = 32 * NW::kRowsPerWarp;          // 32 warps per CTA
+  for (int64_t r = r_beg + warp * NW::kRowsPerWarp + sub; r < r_end; r += kRowsPerIter) {
+    const int32_t beg = rowptr[r], end = rowptr[r + 1];
+    if (end - beg > kBigRowThreshold) continue;
+    float acc[NW::kVals];
+#pragma unroll
+    for (int i = 0; i < NW::kVals; ++i) acc[i] = agg_init<kAggr>();
+    narrow_gather<T, kAggr>(x, col, beg, end, sl, mask, acc);
+    const int32_t deg = end - beg;
+    if constexpr (kAggr == BG_AGGR_MEAN) {
+      const float d = (float)max(deg, 1);
+#pragma unroll
+      for (int i = 0; i < NW::kVals; ++i) acc[i] = acc[i] / d;
+    } else if constexpr (kAggr == BG_AGGR_MAX) {
+      if (deg == 0) {
+#pragma unroll
+        for (int i = 0; i < NW::kVals; ++i) acc[i] = 0.f;
+      }
+    }
+    stg_v4(reinterpret_cast<char*>(out) + (size_t)r * 128 * sizeof(T) + (size_t)sl * 16, narrow_pack<T>(acc));
+  }
+}
+
+// hub rows of the 128-column aggregation: same slicing / ticket scheme as k_aggregate_hubs
+template <typename T, int kAggr>
+__global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
+k_aggregate_hubs128(const T* __restrict__ x, T* __restrict__ out,
+                    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                    const int32_t* __restrict__ big_rows, int32_t n_big,
+                    float* __restrict__ partial, int32_t* __restrict__ ticket) {
+  using NW = Narrow<T>;
+  __shared__ float red[kAggWarpsPerBlock * NW::kRowsPerWarp][128];
+  __shared__ int32_t is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / NW::kLanes, sl = lane % NW::kLanes;
+  const uint32_t mask = (NW::kLanes == 32) ? 0xffffffffu : (0xffffu << (16 * sub));
+  const int32_t hub = blockIdx.x / kHubSlices, slice = blockIdx.x % kHubSlices;
+  if (hub >= n_big) return;
+  const int32_t r = big_rows[hub];
+  const int32_t beg = rowptr[r], deg = rowptr[r + 1] - beg;
+  const int32_t s_beg = beg + (int32_t)((int64_t)deg * slice / kHubSlices);
+  const int32_t s_end = beg + (int32_t)((int64_t)deg * (slice + 1) / kHubSlices);
+  constexpr int kParts = kAggWarpsPerBlock * NW::kRowsPerWarp;      // sub-warps per CTA
+  const int part = warp * NW::kRowsPerWarp + sub;
+  const int32_t s_len = s_end - s_beg;
+  const int32_t w_beg = s_beg + (int32_t)((int64_t)s_len * part / kParts);
+  const int32_t w_end = s_beg + (int32_t)((int64_t)s_len * (part + 1) / kParts);
+  float acc[NW::kVals];
+#pragma unroll
+  for (int i = 0; i < NW::kVals; ++i) acc[i] = agg_init<kAggr>();
+  narrow_gather<T, kAggr>(x, col, w_beg, w_end, sl, mask, acc);
+#pragma unroll
+  for (int i = 0; i < NW::kVals; ++i) red[part][sl * NW::kVals + i] = acc[i];
+  __syncthreads();
+  float* my_partial = partial + ((size_t)hub * kHubSlices + slice) * 128;
+  for (int c = threadIdx.x; c < 128; c += blockDim.x) {
+    float v = red[0][c];
+#pragma unroll
+    for (int w = 1; w < kParts; ++w) v = agg_op<kAggr>(v, red[w][c]);
+    my_partial[c] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(&ticket[hub], 1) == kHubSlices - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float* hp = partial + (size_t)hub * kHubSlices * 128;
+  T* orow = out + (size_t)r * 128;
+  for (int c = threadIdx.x; c < 128; c += blockDim.x) {
+    float v = __ldcg(hp + c);
+    for (int s2 = 1; s2 < kHubSlices; ++s2) v = agg_op<kAggr>(v, __ldcg(hp + (size_t)s2 * 128 + c));
+    if constexpr (kAggr == BG_AGGR_MEAN) v = v / (float)max(deg, 1);
+    if constexpr (sizeof(T) == 2) orow[c] = Pack16<T>::one(v); else orow[c] = v;
+  }
+  if (threadIdx.x == 0) ticket[hub] = 0;
+}
+
 }  // namespace bg

@@ -70,14 +70,15 @@ __global__ void k_split_tf32(const float* __restrict__ src, float* __restrict__ 
 // nonempty[r, 0:64] = [1 if the row has entries else 0, 0, 0, ...]  (a K = 64 GEMM operand)
 template <typename T>
 __global__ void k_expand_rowptr(const int32_t* __restrict__ rowptr, int64_t n_rows, int32_t* __restrict__ row_of,
-                                int32_t* __restrict__ iota, T* __restrict__ nonempty) {
+                                int32_t* __restrict__ iota, T* __restrict__ nonempty, int as_count) {
   const int lane = threadIdx.x & 31;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n_rows; r += n_warps) {
     const int32_t b = rowptr[r], e = rowptr[r + 1];
-    for (int32_t i = b + lane; i < e; i += 32) { row_of[i] = (int32_t)r; iota[i] = i; }
+    if (row_of)
+      for (int32_t i = b + lane; i < e; i += 32) { row_of[i] = (int32_t)r; iota[i] = i; }
     if (nonempty) {
-      const float v0 = (lane == 0 && e > b) ? 1.f : 0.f;
+      const float v0 = (lane == 0 && e > b) ? (as_count ? (float)(e - b) : 1.f) : 0.f;
       if constexpr (sizeof(T) == 2) { nonempty[r * 64 + lane] = Pack16<T>::one(v0); nonempty[r * 64 + 32 + lane] = Pack16<T>::one(0.f); }
       else { nonempty[r * 64 + lane] = v0; nonempty[r * 64 + 32 + lane] = 0.f; }
     }
@@ -103,7 +104,27 @@ static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
 template <typename T>
 static int aggregate_dispatch(const T* x, T* out, int64_t N, const int32_t* rowptr, const int32_t* col,
                               const int32_t* big_rows, int32_t n_big, int aggr, float* partial, int32_t* ticket,
-                              cudaStream_t stream) {
+                              int width, cudaStream_t stream) {
+  if (width == 128) {
+    const unsigned grid128 = (unsigned)min64(ceil_div64(N, 32), (int64_t)sm_count());
+    const unsigned hub_grid128 = (unsigned)n_big * kHubSlices;
+#define BG_AGG128_CASE(A)                                                                                        \
+  case A:                                                                                                        \
+    k_aggregate_rows128<T, A><<<grid128, 1024, 0, stream>>>(x, out, N, rowptr, col);                             \
+    if (n_big > 0)                                                                                               \
+      k_aggregate_hubs128<T, A><<<hub_grid128, kAggWarpsPerBlock * 32, 0, stream>>>(x, out, rowptr, col,         \
+                                                                                    big_rows, n_big, partial, ticket); \
+    break;
+    switch (aggr) {
+      BG_AGG128_CASE(BG_AGGR_MEAN)
+      BG_AGG128_CASE(BG_AGGR_SUM)
+      BG_AGG128_CASE(BG_AGGR_MAX)
+      default: return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad aggr");
+    }
+#undef BG_AGG128_CASE
+    BG_LAUNCH_OK();
+    return BG_OK;
+  }
   const unsigned grid = (unsigned)min64(ceil_div64(N, agg_row_threads<T>() / 32), (int64_t)sm_count());
   const unsigned hub_grid = (unsigned)n_big * kHubSlices;
 #define BG_AGG_CASE(A)                                                                                       \
@@ -273,11 +294,12 @@ int bg_aggregate_workspace_bytes(int32_t n_big, size_t* bytes_host) {
   return BG_OK;
 }
 
-int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t N, const int32_t* rowptr, const int32_t* col,
-                      const int32_t* big_rows, int32_t n_big, int aggr, void* workspace, size_t workspace_bytes,
-                      void* stream_) {
+int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t N, int32_t width, const int32_t* rowptr,
+                      const int32_t* col, const int32_t* big_rows, int32_t n_big, int aggr, void* workspace,
+                      size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (N < 0 || n_big < 0) return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad size");
+  if (width != 512 && width != 128) return fail(BG_ERR_UNSUPPORTED, "bg_sage_aggregate: width must be 512 or 128");
   if (N == 0) return BG_OK;
   if (!x || !out || !rowptr || !aligned16(x) || !aligned16(out)) return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad pointer");
   float* partial = nullptr;
@@ -292,13 +314,13 @@ int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t N, const int3
   }
   if (dtype == BG_BF16)
     return aggregate_dispatch(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, rowptr, col,
-                              big_rows, n_big, aggr, partial, ticket, stream);
+                              big_rows, n_big, aggr, partial, ticket, width, stream);
   if (dtype == BG_F16)
     return aggregate_dispatch(static_cast<const __half*>(x), static_cast<__half*>(out), N, rowptr, col,
-                              big_rows, n_big, aggr, partial, ticket, stream);
+                              big_rows, n_big, aggr, partial, ticket, width, stream);
   if (dtype == BG_F32)
     return aggregate_dispatch(static_cast<const float*>(x), static_cast<float*>(out), N, rowptr, col, big_rows, n_big,
-                              aggr, partial, ticket, stream);
+                              aggr, partial, ticket, width, stream);
   return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad dtype");
 }
 
@@ -409,16 +431,16 @@ int bg_pool_head(const void* x, int dtype, int64_t N, const int32_t* graph_ptr, 
 
 // ------------------------------------------------------------------ EA-GNN helpers
 int bg_expand_rowptr(const int32_t* rowptr, int64_t n_rows, int64_t n_entries, int32_t* row_of, int32_t* iota,
-                     void* nonempty, int nonempty_dtype, void* stream_) {
+                     void* nonempty, int nonempty_dtype, int as_count, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (n_rows < 0 || n_entries < 0 || (n_rows > 0 && !rowptr) || (n_entries > 0 && (!row_of || !iota)))
+  if (n_rows < 0 || n_entries < 0 || (n_rows > 0 && !rowptr))
     return fail(BG_ERR_INVALID, "bg_expand_rowptr: bad argument");
   if (n_rows == 0) return BG_OK;
   const unsigned grid = grid_for(n_rows * 32, 256, sm_count() * 32);
-  if (!nonempty) k_expand_rowptr<float><<<grid, 256, 0, stream>>>(rowptr, n_rows, row_of, iota, nullptr);
-  else if (nonempty_dtype == BG_BF16) k_expand_rowptr<__nv_bfloat16><<<grid, 256, 0, stream>>>(rowptr, n_rows, row_of, iota, static_cast<__nv_bfloat16*>(nonempty));
-  else if (nonempty_dtype == BG_F16) k_expand_rowptr<__half><<<grid, 256, 0, stream>>>(rowptr, n_rows, row_of, iota, static_cast<__half*>(nonempty));
-  else if (nonempty_dtype == BG_F32) k_expand_rowptr<float><<<grid, 256, 0, stream>>>(rowptr, n_rows, row_of, iota, static_cast<float*>(nonempty));
+  if (!nonempty) k_expand_rowptr<float><<<grid, 256, 0, stream>>>(rowptr, n_rows, row_of, iota, nullptr, 0);
+  else if (nonempty_dtype == BG_BF16) k_expand_rowptr<__nv_bfloat16><<<grid, 256, 0, stream>>>(rowptr, n_rows, row_of, iota, static_cast<__nv_bfloat16*>(nonempty), as_count);
+  else if (nonempty_dtype == BG_F16) k_expand_rowptr<__half><<<grid, 256, 0, stream>>>(rowptr, n_rows, row_of, iota, static_cast<__half*>(nonempty), as_count);
+  else if (nonempty_dtype == BG_F32) k_expand_rowptr<float><<<grid, 256, 0, stream>>>(rowptr, n_rows, row_of, iota, static_cast<float*>(nonempty), as_count);
   else return fail(BG_ERR_INVALID, "bg_expand_rowptr: bad dtype");
   BG_LAUNCH_OK();
   return BG_OK;

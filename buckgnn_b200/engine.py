@@ -97,10 +97,11 @@ class _KernelTimers:
 TIMERS = _KernelTimers()
 
 
-def LAUNCHES_PER_FORWARD(num_layers: int) -> int:
+def LAUNCHES_PER_FORWARD(num_layers: int, folded: bool = True) -> int:
     """Kernels of ours launched by one GraphSAGE forward: CSR build 7 (hist, 3 scan, fill,
-    2 sorts) + batch_info + graph_ptr + encoder 2 + per layer (aggregate rows + hubs + GEMM)
-    + pool 2.  (memsets and the 16-byte info read-back are not counted.)"""
+    2 sorts) + batch_info + graph_ptr + encoder front 1 (+ encoder GEMM when layer 0 is not folded;
+    + row indicator when it is) + per layer (aggregate rows + hubs + GEMM) + pool 2.
+    (memsets and the 16-byte info read-back are not counted.)"""
     return 7 + 2 + 2 + 3 * num_layers + 2
 
 
@@ -293,19 +294,20 @@ def gemm512(segs, m: int, precision: str, out: Activation, *, cta_group: int = 2
 
 
 def aggregate(x: Activation, out: Activation, idx: GraphIndex, aggr: str) -> None:
+    """K2 over [N,512] rows, or [N,128] rows (the encoder hidden layer of the folded first layer)."""
+    width = x.data.shape[1]
     ws_bytes = capi.aggregate_workspace_bytes(idx.n_big)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.data.device)
-    with TIMERS.span("aggregate"):
+    with TIMERS.span("aggregate" if width == 512 else "aggregate128"):
         capi.sage_aggregate(x.data.data_ptr(), out.data.data_ptr(), x.code, idx.n_nodes, idx.rowptr.data_ptr(),
                             idx.col.data_ptr(), idx.big_rows.data_ptr(), idx.n_big, capi.AGGR_CODES[aggr],
-                            ws.data_ptr(), ws_bytes, _stream())
+                            ws.data_ptr(), ws_bytes, _stream(), width=width)
     out.refresh_split()
 
 
-def encoder_forward(x: torch.Tensor, enc_w: Dict[str, torch.Tensor], w3: LinearPack, precision: str,
-                    out: Activation, cta_group: int, row_gather: Optional[torch.Tensor] = None) -> None:
-    """node_encoder / edge_encoder (Models/BuckGNN.py:68-82): two fp32 CUDA-core layers, then 128->512 on
-    tcgen05.  `row_gather` [n] int32 reads input row row_gather[i] for output row i."""
+def encoder_hidden(x: torch.Tensor, enc_w: Dict[str, torch.Tensor], precision: str,
+                   row_gather: Optional[torch.Tensor] = None) -> "Activation":
+    """First two Linear+ReLU of an encoder -> [n,128] activation (K5 front)."""
     f = x.shape[1]
     n = x.shape[0] if row_gather is None else row_gather.shape[0]
     h = Activation(n, 128, precision, x.device)
@@ -314,6 +316,59 @@ def encoder_forward(x: torch.Tensor, enc_w: Dict[str, torch.Tensor], w3: LinearP
                            enc_w["w2"].data_ptr(), enc_w["b2"].data_ptr(), h.data.data_ptr(), h.code, _stream(),
                            row_gather=_p(row_gather))
     h.refresh_split()
+    return h
+
+
+@dataclass
+class FoldedLayer0Pack:
+    """SAGE layer 0 with the encoder's last Linear folded in (exact algebra; the encoder output
+    x0 = h W3^T + b3 is never materialised):
+        mean_j(x0_j) W_l^T + x0_i W_r^T + b_l
+      = mean_j(h_j) (W_l W3)^T + h_i (W_r W3)^T + [deg_i > 0] (W_l b3) + (W_r b3 + b_l)
+    (for sum/add aggregation the indicator is deg_i).  K = 128 + 128 + 64 instead of 1024, and the
+    aggregation moves 128 instead of 512 columns."""
+    wl3: LinearPack
+    wr3: LinearPack
+    wgate: LinearPack
+    bias: torch.Tensor                   # HOST f32 [512]
+    bn_scale: Optional[torch.Tensor]
+    bn_shift: Optional[torch.Tensor]
+    as_count: bool
+
+
+def pack_folded_layer0(enc_last: torch.nn.Linear, conv, bn, aggr: str, precision: str) -> FoldedLayer0Pack:
+    dev = conv.lin_l.weight.device
+    d64 = lambda t: t.detach().to(torch.float64).cpu()
+    W3, b3 = d64(enc_last.weight), d64(enc_last.bias)
+    Wl, bl, Wr = d64(conv.lin_l.weight), d64(conv.lin_l.bias), d64(conv.lin_r.weight)
+    lp = lambda w: pack_linear(w.to(torch.float32).to(dev), precision)
+    gate = torch.cat([(Wl @ b3)[:, None], torch.zeros(512, 63, dtype=torch.float64)], 1)
+    scale, shift = fold_batchnorm(bn) if bn is not None else (None, None)
+    return FoldedLayer0Pack(lp(Wl @ W3), lp(Wr @ W3), lp(gate), (Wr @ b3 + bl).to(torch.float32).contiguous(),
+                            scale, shift, aggr in ("sum", "add"))
+
+
+def sage_layer0_folded(h: "Activation", out: "Activation", idx: GraphIndex, w: FoldedLayer0Pack, *, aggr: str,
+                       normalize: bool, relu: bool, cta_group: int = 2) -> None:
+    n = idx.n_nodes
+    mh = Activation(n, 128, h.precision, h.data.device)
+    aggregate(h, mh, idx, aggr)
+    ind = Activation(n, 64, h.precision, h.data.device)
+    capi.expand_rowptr(idx.rowptr.data_ptr(), n, idx.n_edges, None, None, ind.data.data_ptr(), ind.code, _stream(),
+                       as_count=w.as_count)
+    ind.refresh_split()
+    segs = _segments(mh, w.wl3) + _segments(h, w.wr3) + _segments(ind, w.wgate)[:2]
+    with TIMERS.span("sage_update0"):
+        gemm512(segs, n, h.precision, out, cta_group=cta_group, bias=w.bias.data_ptr(), bn_scale=_p(w.bn_scale),
+                bn_shift=_p(w.bn_shift), normalize=normalize, relu=relu)
+
+
+def encoder_forward(x: torch.Tensor, enc_w: Dict[str, torch.Tensor], w3: LinearPack, precision: str,
+                    out: Activation, cta_group: int, row_gather: Optional[torch.Tensor] = None) -> None:
+    """node_encoder / edge_encoder (Models/BuckGNN.py:68-82): two fp32 CUDA-core layers, then 128->512 on
+    tcgen05.  `row_gather` [n] int32 reads input row row_gather[i] for output row i."""
+    h = encoder_hidden(x, enc_w, precision, row_gather)
+    n = h.data.shape[0]
     with TIMERS.span("encoder_gemm"):
         gemm512(_segments(h, w3), n, precision, out, cta_group=cta_group, bias=enc_w["b3_host"].data_ptr())
 

@@ -92,7 +92,7 @@ class BuckGNN(nn.Module):
                  num_layers=6, pooling_layer="mean", prediction_type="buckling",
                  use_z_coord=False, use_rotations=False, dropout_rate=0.1,
                  model_name="GraphSAGE_MLP", *, precision: str = "auto", cta_group: int = 2,
-                 cache_index: bool = False):
+                 cache_index: bool = False, fold_encoder: bool = True):
         super().__init__()
         if precision == "auto":
             aggr = _SAGE_LISTS[model_name][1] if model_name in _SAGE_LISTS else (
@@ -108,6 +108,7 @@ class BuckGNN(nn.Module):
         self.precision = precision
         self.cta_group = cta_group
         self.cache_index = cache_index
+        self.fold_encoder = fold_encoder      # fold node_encoder[4] into SAGE layer 0 (mean / sum / add aggregation)
         self.output_dim = output_dim = _output_dim(prediction_type, use_z_coord, use_rotations)
         h = hidden_channels
         cat_dec = pooling_layer == "supernode_with_pooling" and prediction_type == "buckling"
@@ -184,6 +185,11 @@ class BuckGNN(nn.Module):
                                                engine.host_vector(conv.lin_l.bias), scale, shift)
             layers.append(seen[id(conv)])
         packs["layers"] = layers
+        packs["layer0_folded"] = None
+        sl = self._sage_layers()
+        if self.fold_encoder and sl and sl[0][0].aggr != "max":
+            conv0, bn0 = sl[0]
+            packs["layer0_folded"] = engine.pack_folded_layer0(enc[4], conv0, bn0, conv0.aggr, prec)
         if self.model_name in ("EA_GNN", "EA_GNN_Shared"):
             ee = self.edge_encoder
             packs["edge_enc"] = {"w1": f32(ee[0].weight), "b1": f32(ee[0].bias), "w2": f32(ee[2].weight),
@@ -289,17 +295,25 @@ class BuckGNN(nn.Module):
         n = x.shape[0]
         pending = self._begin_graph_index(edge_index, batch, n)       # K1 enqueued, result read-back in flight
         cur = Activation(n, 512, prec, x.device)
-        engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg)          # reference :323
-        idx = pending.finish()                                        # host sync hidden behind the encoder
         layers = packs["layers"]
+        folded = packs["layer0_folded"]
+        if folded is not None:
+            h = engine.encoder_hidden(x, packs["enc"], prec)          # reference :323, first two Linears
+        else:
+            engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg)      # reference :323
+        idx = pending.finish()                                        # host sync hidden behind the encoder
         if layers:
             nxt = Activation(n, 512, prec, x.device)
             agg = Activation(n, 512, prec, x.device)
             aggr = self._sage_layers()[0][0].aggr
             L = len(layers)
             for i, layer in enumerate(layers):                                            # reference :445-458
-                engine.sage_layer(cur, agg, nxt, idx, layer, aggr=aggr, normalize=True, relu=True,
-                                  residual=(0 < i < L - 1), cta_group=cg)
+                if i == 0 and folded is not None:                     # encoder's last Linear folded into layer 0
+                    engine.sage_layer0_folded(h, nxt, idx, folded, aggr=aggr, normalize=True, relu=True,
+                                              cta_group=cg)
+                else:
+                    engine.sage_layer(cur, agg, nxt, idx, layer, aggr=aggr, normalize=True, relu=True,
+                                      residual=(0 < i < L - 1), cta_group=cg)
                 cur, nxt = nxt, cur
         pre = packs["pool_mlp"] if self.pooling_layer in ("mlp", "mlp_no_super") else None
         pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim, pooling=self.pooling_layer,

@@ -102,11 +102,12 @@ int bg_encoder_front(const float* x, int64_t n_nodes, int32_t n_features,
 /* ------------------------------------------------------------------ K2: neighbourhood aggregation
  * Replaces `x[src]` gather + `scatter_add_` + divide inside SAGEConv.propagate:
  *    out[i] = reduce_{e: key(e)=i} x[col(e)]     mean: sum / max(deg,1); max: 0 if deg = 0
- * x, out: [N,512] of `dtype` (bf16, f16 or f32), accumulation in fp32 in CSR (stable) order.
+ * x, out: [N,width] of `dtype` (bf16, f16 or f32), width 512 or 128 (the encoder's hidden layer, for the
+ * folded first layer); accumulation in fp32 in CSR (stable) order.
  * Big rows (info[1] of bg_csr_build, read back by the host) are split across CTAs;
  * workspace from bg_aggregate_workspace_bytes(n_big). */
 int bg_aggregate_workspace_bytes(int32_t n_big, size_t* bytes_host);
-int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t n_nodes,
+int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t n_nodes, int32_t width,
                       const int32_t* rowptr, const int32_t* col,
                       const int32_t* big_rows, int32_t n_big, int aggr,
                       void* workspace, size_t workspace_bytes, void* stream);
@@ -181,13 +182,15 @@ int bg_pool_head(const void* x, int dtype, int64_t n_nodes, const int32_t* graph
  * bg_expand_rowptr: row_of[i] = r with rowptr[r] <= i < rowptr[r+1], iota[i] = i   (i < E)
  *   (row ids of the CSR slots, and the identity "col" that turns bg_sage_aggregate into the
  *   segmented mean torch_scatter.scatter_mean(messages, row) needs once edges are in CSR order);
- *   nonempty (optional, [n_rows, 64] of nonempty_dtype): column 0 = 1 for rows with >= 1 entry, rest 0 --
+ *   row_of / iota may be NULL.
+ *   nonempty (optional, [n_rows, 64] of nonempty_dtype): column 0 = 1 for rows with >= 1 entry (or the
+ *   entry count when as_count != 0), rest 0 --
  *   a K = 64 GEMM segment that applies a bias only to rows whose scatter_mean segment is non-empty
  *   (what remains of phi's second-layer bias after that Linear is folded through the mean).
  * bg_add: out = a + b (+ c) elementwise over n values of `dtype`, fp32 math (skip connections
  *   of the EA-GNN wrapper, Models/BuckGNN.py:382-384). */
 int bg_expand_rowptr(const int32_t* rowptr, int64_t n_rows, int64_t n_entries, int32_t* row_of, int32_t* iota,
-                     void* nonempty, int nonempty_dtype, void* stream);
+                     void* nonempty, int nonempty_dtype, int as_count, void* stream);
 int bg_add(const void* a, const void* b, const void* c_or_null, void* out, int dtype, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------ helpers

@@ -49,6 +49,18 @@ def test_graphsage_mean_6x512_matches_oracle(precision):
     _assert_rel(got, want, RTOL[precision])
 
 
+@pytest.mark.parametrize("name", ["GraphSage_meanAggr", "GraphSage_sumAggr"])
+def test_unfolded_encoder_path_agrees_with_folded(name):
+    """fold_encoder=False materialises the encoder output and runs layer 0 like the others"""
+    ref, a = _pair(name, "fp32", layers=3)
+    _, b_ = _pair(name, "fp32", layers=3, fold_encoder=False)
+    batch = make_batch(3, nx=12, ny=9)
+    ga, want = _run(ref, a, batch)
+    gb, _ = _run(ref, b_, batch)
+    _assert_rel(ga, want, 1e-4)
+    _assert_rel(gb, want, 1e-4)
+
+
 def test_ragged_batch_with_tail_tiles():
     """graph sizes that leave partial 256-row tiles and one-row graphs' worth of tails"""
     ref, ours = _pair("GraphSage_meanAggr", "fp16")

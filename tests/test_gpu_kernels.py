@@ -126,6 +126,26 @@ def test_aggregate_matches_oracle(aggr, precision):
         assert got[3].abs().sum() == 0          # isolated node -> 0, not -inf
 
 
+@pytest.mark.parametrize("precision", ["fp16", "bf16", "tf32"])
+@pytest.mark.parametrize("aggr", ["mean", "sum", "max"])
+def test_aggregate_128_columns(aggr, precision):
+    torch.manual_seed(7)
+    b = make_batch(3, nx=19, ny=15)
+    n = b.num_nodes
+    ei = b.edge_index[:, b.edge_index[1] != 4]
+    x = torch.randn(n, 128).to(engine._TORCH[engine.PRECISION_FORMATS[precision][0]]).float()
+    want = O.aggregate(x.double(), ei, aggr).float()
+    idx = build_graph_index(ei.to(DEV), None, n)
+    xa, oa = Activation(n, 128, precision, DEV), Activation(n, 128, precision, DEV)
+    xa.data.copy_(x)
+    engine.aggregate(xa, oa, idx, aggr)
+    got = oa.data.float().cpu()
+    tol = {"bf16": dict(rtol=8e-3, atol=2e-2 if aggr == "sum" else 1e-6),
+           "fp16": dict(rtol=1e-3, atol=3e-3 if aggr == "sum" else 1e-6),
+           "tf32": dict(rtol=1e-5, atol=1e-5)}[precision]
+    torch.testing.assert_close(got, want, **tol)
+
+
 # ----------------------------------------------------------------------------- K3
 def _gemm_case(m, precision, cta_group, full_epilogue, seed=0):
     g = torch.Generator().manual_seed(seed)
