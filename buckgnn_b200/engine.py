@@ -102,6 +102,8 @@ def LAUNCHES_PER_FORWARD(num_layers: int, folded: bool = True) -> int:
     2 sorts) + batch_info + graph_ptr + encoder front 1 (+ encoder GEMM when layer 0 is not folded;
     + row indicator when it is) + per layer (aggregate rows + hubs + GEMM) + pool 2.
     (memsets and the 16-byte info read-back are not counted.)"""
+    if folded:
+        return 7 + 2 + 1 + 1 + 3 * num_layers + 2
     return 7 + 2 + 2 + 3 * num_layers + 2
 
 
