@@ -146,23 +146,67 @@ template <int kAggr, bool kExactDiv> BG_DEVINL void agg_finalize(float (&acc)[16
 // 32 rows at a time.  Mesh neighbours of row i are i+-1 and i+-nx, so the band's reuse
 // window (~2*nx+32 rows of 1 KB) stays in the SM's L1: a source row is fetched from L2
 // once and hit ~3 more times, instead of every gather going to L2.
+// gather the rows whose indices sit in `my` (lane j holds neighbour j, cnt <= 32 of them)
+template <typename T, int kAggr>
+BG_DEVINL void gather_indexed(const T* __restrict__ x, int32_t my, int32_t cnt, int lane, float (&acc)[16]) {
+  int32_t j = 0;
+  for (; j + 4 <= cnt; j += 4) {
+    RowFrag<T> f0, f1, f2, f3;
+    f0.load(x + (size_t)__shfl_sync(0xffffffffu, my, j) * kHidden, lane);
+    f1.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 1) * kHidden, lane);
+    f2.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 2) * kHidden, lane);
+    f3.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 3) * kHidden, lane);
+    f0.template accumulate<kAggr>(acc);
+    f1.template accumulate<kAggr>(acc);
+    f2.template accumulate<kAggr>(acc);
+    f3.template accumulate<kAggr>(acc);
+  }
+  for (; j < cnt; ++j) {
+    RowFrag<T> f;
+    f.load(x + (size_t)__shfl_sync(0xffffffffu, my, j) * kHidden, lane);
+    f.template accumulate<kAggr>(acc);
+  }
+}
+
+// One persistent CTA per SM owns a CONTIGUOUS band of rows and walks it in order, one warp per row.
+// Mesh neighbours of row i are i+-1 and i+-nx, so the band's reuse window (~2*nx+32 rows of 1 KB)
+// stays in the SM's L1: a source row is fetched from L2 once and hit ~3 more times.
+// A warp's rows form a dependent chain rowptr -> col -> x per row; it is software-pipelined two
+// rows deep (the next row's neighbour indices and the row-after-next's offsets are loaded while
+// the current row's feature rows are in flight), so one memory latency per row is exposed, not three.
 template <typename T, int kAggr>
 __global__ void __launch_bounds__(agg_row_threads<T>(), 1)
 k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N,
                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col) {
+  constexpr int kWarps = agg_row_threads<T>() / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t band = (N + gridDim.x - 1) / gridDim.x;
   const int64_t r_beg = (int64_t)blockIdx.x * band;
   const int64_t r_end = min(N, r_beg + band);
-  for (int64_t r = r_beg + warp; r < r_end; r += agg_row_threads<T>() / 32) {
-    const int32_t beg = rowptr[r], end = rowptr[r + 1];
-    if (end - beg > kBigRowThreshold) continue;             // hub rows: k_aggregate_hubs
-    float acc[16];
+  int64_t r = r_beg + warp;
+  int32_t beg = 0, end = 0, my = 0, nbeg = 0, nend = 0;
+  if (r < r_end) {
+    beg = rowptr[r]; end = rowptr[r + 1];
+    my = (lane < end - beg) ? col[beg + lane] : 0;
+  }
+  if (r + kWarps < r_end) { nbeg = rowptr[r + kWarps]; nend = rowptr[r + kWarps + 1]; }
+  for (; r < r_end; r += kWarps) {
+    // stage 2 of the pipeline: indices of the next row (its offsets arrived an iteration ago)
+    const int32_t nmy = (lane < nend - nbeg) ? col[nbeg + lane] : 0;
+    // stage 1: offsets of the row after next
+    int32_t n2beg = 0, n2end = 0;
+    if (r + 2 * kWarps < r_end) { n2beg = rowptr[r + 2 * kWarps]; n2end = rowptr[r + 2 * kWarps + 1]; }
+    const int32_t deg = end - beg;
+    if (deg <= kBigRowThreshold) {                          // hub rows: k_aggregate_hubs
+      float acc[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = agg_init<kAggr>();
-    gather_range<T, kAggr>(x, col, beg, end, lane, acc);
-    agg_finalize<kAggr, sizeof(T) == 4>(acc, end - beg);
-    RowFrag<T>::store(out + (size_t)r * kHidden, lane, acc);
+      for (int i = 0; i < 16; ++i) acc[i] = agg_init<kAggr>();
+      gather_indexed<T, kAggr>(x, my, min(deg, 32), lane, acc);
+      if (deg > 32) gather_range<T, kAggr>(x, col, beg + 32, end, lane, acc);
+      agg_finalize<kAggr, sizeof(T) == 4>(acc, deg);
+      RowFrag<T>::store(out + (size_t)r * kHidden, lane, acc);
+    }
+    beg = nbeg; end = nend; my = nmy; nbeg = n2beg; nend = n2end;
   }
 }
 
