@@ -59,3 +59,31 @@ def sharded_predict(graphs: Sequence[PlateGraph], forward: Callable, device, gro
         if p:
             out[torch.tensor(p, dtype=torch.long, device=device)] = gathered[r][:len(p)]
     return out
+
+
+def allreduce_gradients(params, group=None, average: bool = True) -> int:
+    """One flat all-reduce of the gradients a training step produced (config 4).
+
+    Parameters whose `.grad` is None are skipped on every rank -- `BuckGNN` registers modules the
+    selected `model_name` never uses (`sage_mlps`, `edge_encoder`, `pooling_mpl`, `batch_norm`;
+    reference Models/BuckGNN.py:164,184-187), which is why DDP would need
+    `find_unused_parameters=True`.  Ranks must agree on which parameters have gradients (same model,
+    same branch).  Gradients are flattened into one fp32 bucket (fp64 if every gradient is fp64) (about 13 MB for GraphSage_meanAggr
+    6x512), reduced with a single collective (NCCL over NVLink: latency-bound at this size) and
+    scattered back.  BatchNorm batch statistics stay rank-local, as a DDP port of the reference
+    would have them.  Returns the number of elements reduced."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    bucket_dtype = torch.float64 if all(g.dtype == torch.float64 for g in grads) else torch.float32
+    flat = torch.cat([g.reshape(-1).to(bucket_dtype) for g in grads])
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g).to(g.dtype))
+        off += n
+    return off

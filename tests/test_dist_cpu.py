@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from buckgnn_b200.dist import graph_cost, partition_graphs, sharded_predict
+from buckgnn_b200.dist import allreduce_gradients, graph_cost, partition_graphs, sharded_predict
 from buckgnn_b200.synth import make_plate_graph
 
 
@@ -60,3 +60,51 @@ def test_single_process_path():
     graphs = [make_plate_graph(i, nx=4, ny=4) for i in range(3)]
     out = sharded_predict(graphs, _fake_forward, "cpu")
     assert torch.allclose(out, torch.tensor([float(g.x.sum()) for g in graphs]), rtol=1e-6)
+
+
+def _grad_worker(rank, world, port, q):
+    """Data-parallel step on the CPU oracle: each rank backpropagates its shard, gradients are
+    all-reduced (mean) and must equal the single-process gradient of the mean loss over all graphs
+    (equal shard sizes, BN in eval mode so the statistics do not differ between the two runs)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.buckgnn_oracle import OracleBuckGNN
+    from buckgnn_b200.synth import collate
+    torch.manual_seed(0)
+    model = OracleBuckGNN(16, 5, 256, 2, "mean", model_name="GraphSage_meanAggr", dropout_rate=0.0).double().eval()
+    graphs = [make_plate_graph(i, nx=4, ny=3) for i in range(4)]
+    mine = collate(graphs[rank * 2:rank * 2 + 2])
+    pred, _ = model(mine.x.double(), mine.edge_index, mine.edge_attr.double(), mine.batch)
+    ((pred - mine.y.double()) ** 2).mean().backward()
+    n = allreduce_gradients(model.parameters())
+    unused = [k for k, p in model.named_parameters() if p.grad is None]
+    flat = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+    q.put((rank, n, sorted(set(k.split(".")[0] for k in unused)), flat.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world_size_2_matches_single_process():
+    from oracle.buckgnn_oracle import OracleBuckGNN
+    from buckgnn_b200.synth import collate
+    torch.manual_seed(0)
+    model = OracleBuckGNN(16, 5, 256, 2, "mean", model_name="GraphSage_meanAggr", dropout_rate=0.0).double().eval()
+    graphs = [make_plate_graph(i, nx=4, ny=3) for i in range(4)]
+    b = collate(graphs)
+    pred, _ = model(b.x.double(), b.edge_index, b.edge_attr.double(), b.batch)
+    ((pred - b.y.double()) ** 2).mean().backward()
+    want = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=180) for _ in range(2)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, n, unused, flat in got:
+        assert n == want.numel()
+        assert unused == ["batch_norm", "edge_encoder", "pooling_mpl", "sage_mlps"]   # never touched by this model_name
+        assert torch.allclose(torch.tensor(flat, dtype=torch.float64), want, rtol=1e-9, atol=1e-12)
