@@ -20,7 +20,7 @@ BG_BF16, BG_F32, BG_F16 = 0, 1, 2
 BG_AGGR_MEAN, BG_AGGR_SUM, BG_AGGR_MAX = 0, 1, 2
 BG_BIG_ROW_THRESHOLD = 64
 BG_MAX_GEMM_SEGMENTS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 AGGR_CODES = {"mean": BG_AGGR_MEAN, "sum": BG_AGGR_SUM, "add": BG_AGGR_SUM, "max": BG_AGGR_MAX}
 
@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     "bg_abi_version", "bg_last_error", "bg_device_check", "bg_watchdog_info_host",
     "bg_csr_max_big_rows", "bg_csr_workspace_bytes", "bg_csr_build",
     "bg_batch_info", "bg_graph_ptr_build", "bg_encoder_front",
-    "bg_aggregate_workspace_bytes", "bg_sage_aggregate", "bg_gemm512",
+    "bg_aggregate_workspace_bytes", "bg_hubfold_workspace_bytes", "bg_sage_aggregate", "bg_gemm512",
     "bg_pool_workspace_bytes", "bg_pool_head", "bg_cast_f32", "bg_split_tf32",
     "bg_expand_rowptr", "bg_add",
 )
@@ -64,14 +64,16 @@ _SIGNATURES = {
     "bg_watchdog_info_host": (C.c_int, [C.POINTER(C.c_uint32)]),
     "bg_csr_max_big_rows": (_I64, [_I64]),
     "bg_csr_workspace_bytes": (C.c_int, [_I64, _I64, _SZP]),
-    "bg_csr_build": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "bg_csr_build": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "bg_batch_info": (C.c_int, [_P, _I64, _P, _P]),
     "bg_graph_ptr_build": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "bg_encoder_front": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "bg_expand_rowptr": (C.c_int, [_P, _I64, _I64, _P, _P, _P, C.c_int, C.c_int, _P]),
     "bg_add": (C.c_int, [_P, _P, _P, _P, C.c_int, _I64, _P]),
     "bg_aggregate_workspace_bytes": (C.c_int, [_I32, _SZP]),
-    "bg_sage_aggregate": (C.c_int, [_P, _P, C.c_int, _I64, _I32, _P, _P, _P, _I32, C.c_int, _P, C.c_size_t, _P]),
+    "bg_hubfold_workspace_bytes": (C.c_int, [_I64, C.c_int, _I32, _I32, _SZP]),
+    "bg_sage_aggregate": (C.c_int, [_P, _P, C.c_int, _I64, _I32, _P, _P, _P, _I32, C.c_int, _P, _P, _I32, _P,
+                                    C.c_size_t, _P]),
     "bg_gemm512": (C.c_int, [C.POINTER(GemmSegment), _I32, _I64, C.c_int, C.c_int, C.POINTER(Epilogue), _P,
                              C.c_int, _I64, C.c_int, _P]),
     "bg_pool_workspace_bytes": (C.c_int, [_I64, _SZP]),
@@ -146,9 +148,11 @@ def pool_workspace_bytes(n_graphs: int) -> int:
     return _query("bg_pool_workspace_bytes", n_graphs)
 
 
-def csr_build(edge_index, n_edges, n_nodes, key_row, rowptr, col, perm, big_rows, info, ws, ws_bytes, stream):
+def csr_build(edge_index, n_edges, n_nodes, key_row, rowptr, col, perm, big_rows, info, ws, ws_bytes, stream,
+              hub_lo=None, hub_of_row=None):
+    """`info` holds 8 int32 words (see include/buckgnn_b200.h)."""
     _check(load().bg_csr_build(edge_index, n_edges, n_nodes, key_row, rowptr, col, perm, big_rows, info,
-                               ws, ws_bytes, stream), "bg_csr_build")
+                               hub_lo, hub_of_row, ws, ws_bytes, stream), "bg_csr_build")
 
 
 def batch_info(batch, n_nodes, info, stream):
@@ -173,9 +177,14 @@ def add(a, b, c, out, dtype, n, stream):
     _check(load().bg_add(a, b, c, out, dtype, n, stream), "bg_add")
 
 
-def sage_aggregate(x, out, dtype, n_nodes, rowptr, col, big_rows, n_big, aggr, ws, ws_bytes, stream, width=512):
-    _check(load().bg_sage_aggregate(x, out, dtype, n_nodes, width, rowptr, col, big_rows, n_big, aggr, ws, ws_bytes,
-                                    stream), "bg_sage_aggregate")
+def hubfold_workspace_bytes(n_nodes: int, dtype: int, n_big: int, hub_max_degree: int) -> int:
+    return _query("bg_hubfold_workspace_bytes", n_nodes, dtype, n_big, hub_max_degree)
+
+
+def sage_aggregate(x, out, dtype, n_nodes, rowptr, col, big_rows, n_big, aggr, ws, ws_bytes, stream, width=512,
+                   hub_lo=None, hub_of_row=None, hub_max_degree=0):
+    _check(load().bg_sage_aggregate(x, out, dtype, n_nodes, width, rowptr, col, big_rows, n_big, aggr,
+                                    hub_lo, hub_of_row, hub_max_degree, ws, ws_bytes, stream), "bg_sage_aggregate")
 
 
 def gemm512(segments, m, a_dtype, b_dtype, out, out_dtype, ldo, stream, *, bias=None, bn_scale=None,

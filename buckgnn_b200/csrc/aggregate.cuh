@@ -24,7 +24,12 @@ namespace bg {
 constexpr int kHubSlices = 16;
 constexpr int kAggWarpsPerBlock = 8;       // hub kernel
 // row kernel: one CTA per SM; 32 warps for 16-bit rows (64 regs/thread), 16 warps for fp32 rows
-template <typename T> __host__ __device__ constexpr int agg_row_threads() { return sizeof(T) == 2 ? 1024 : 512; }
+#ifndef BG_AGG_THREADS16
+#define BG_AGG_THREADS16 768
+#endif
+template <typename T> __host__ __device__ constexpr int agg_row_threads() { return sizeof(T) == 2 ? BG_AGG_THREADS16 : 512; }
+template <typename T> __host__ __device__ constexpr int agg_fold_threads() { return agg_row_threads<T>(); }
+
 
 template <int kAggr> BG_DEVINL float agg_init() { return kAggr == BG_AGGR_MAX ? -INFINITY : 0.f; }
 template <int kAggr> BG_DEVINL float agg_op(float a, float b) {
@@ -146,7 +151,9 @@ template <int kAggr, bool kExactDiv> BG_DEVINL void agg_finalize(float (&acc)[16
 // 32 rows at a time.  Mesh neighbours of row i are i+-1 and i+-nx, so the band's reuse
 // window (~2*nx+32 rows of 1 KB) stays in the SM's L1: a source row is fetched from L2
 // once and hit ~3 more times, instead of every gather going to L2.
-// gather the rows whose indices sit in `my` (lane j holds neighbour j, cnt <= 32 of them)
+// gather the rows whose indices sit in `my` (lane j holds neighbour j, cnt <= 32 of them), 4 rows in flight.
+// (A generic kBatch-wide version with predicated loads into a fragment array was 2x slower: ptxas kept the
+// array in local memory -- tools/agg_bench.py, profiles/r01_agg_variants.txt.)
 template <typename T, int kAggr>
 BG_DEVINL void gather_indexed(const T* __restrict__ x, int32_t my, int32_t cnt, int lane, float (&acc)[16]) {
   int32_t j = 0;
@@ -174,15 +181,77 @@ BG_DEVINL void gather_indexed(const T* __restrict__ x, int32_t my, int32_t cnt, 
 // A warp's rows form a dependent chain rowptr -> col -> x per row; it is software-pipelined two
 // rows deep (the next row's neighbour indices and the row-after-next's offsets are loaded while
 // the current row's feature rows are in flight), so one memory latency per row is exposed, not three.
-template <typename T, int kAggr>
-__global__ void __launch_bounds__(agg_row_threads<T>(), 1)
-k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N,
-                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col) {
-  constexpr int kWarps = agg_row_threads<T>() / 32;
+//
+// kFold (mean / sum only): "range hubs" (bg_csr_build: a hub row whose neighbours are exactly the
+// contiguous rows lo..lo+deg-1 -- the reference's super node) are folded into this pass.  kStream of
+// the CTA's warps do not gather: they stream the band's own rows once, in order, 4 rows in flight, and
+// add each row to a register partial of the hub whose range contains it; the partial is flushed to
+// hub_partial[hub][band - first band of the hub][stream warp] when the rows move on to another hub.
+// They run beside the gather warps over the same band, so their reads are served by (or fill) the
+// L1/L2 lines the gathers need anyway, and k_hub_finalize adds the partials in a fixed order.  The
+// separate hub kernel's second pass over all of x (1 GB of HBM reads per layer at cfg 2) disappears.
+struct HubFold {
+  const int32_t* hub_of_row;   // [N]  hub slot of the range containing row r, or -1
+  const int32_t* hub_lo;       // [n_big] first row of the hub's range
+  float* partial;              // [n_big][parts][kStream][512] f32, lane-major
+  int32_t parts;               // band slots per hub
+};
+#ifndef BG_AGG_STREAM_WARPS
+#define BG_AGG_STREAM_WARPS 4
+#endif
+
+template <typename T, int kAggr, bool kFold, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1)
+k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N, int64_t band,
+                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const HubFold hf) {
+  constexpr int kStream = kFold ? BG_AGG_STREAM_WARPS : 0;
+  constexpr int kWarps = kThreads / 32 - kStream;            // gather warps
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t band = (N + gridDim.x - 1) / gridDim.x;
   const int64_t r_beg = (int64_t)blockIdx.x * band;
   const int64_t r_end = min(N, r_beg + band);
+  if constexpr (kFold) {
+    if (warp >= kWarps) {
+      // ---------------------------------------------------------------- hub streaming warps
+      const int sw = warp - kWarps;
+      float acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+      int32_t cur_h = -1;
+      auto flush = [&]() {
+        if (cur_h >= 0) {
+          const int64_t slot = (int64_t)cur_h * hf.parts + ((int64_t)blockIdx.x - hf.hub_lo[cur_h] / band);
+          float4* dst = reinterpret_cast<float4*>(hf.partial) + (slot * kStream + sw) * 128 + lane;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j * 32] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+      };
+      auto take = [&](int32_t h, const RowFrag<T>& f) {
+        if (h != cur_h) { flush(); cur_h = h; }
+        if (h >= 0) f.template accumulate<BG_AGGR_SUM>(acc);
+      };
+      int64_t r = r_beg + sw;
+      for (; r + 3 * kStream < r_end; r += 4 * kStream) {
+        const int32_t h0 = hf.hub_of_row[r], h1 = hf.hub_of_row[r + kStream];
+        const int32_t h2 = hf.hub_of_row[r + 2 * kStream], h3 = hf.hub_of_row[r + 3 * kStream];
+        RowFrag<T> f0, f1, f2, f3;
+        f0.load(x + (size_t)r * kHidden, lane);
+        f1.load(x + (size_t)(r + kStream) * kHidden, lane);
+        f2.load(x + (size_t)(r + 2 * kStream) * kHidden, lane);
+        f3.load(x + (size_t)(r + 3 * kStream) * kHidden, lane);
+        take(h0, f0); take(h1, f1); take(h2, f2); take(h3, f3);
+      }
+      for (; r < r_end; r += kStream) {
+        const int32_t h0 = hf.hub_of_row[r];
+        RowFrag<T> f0;
+        f0.load(x + (size_t)r * kHidden, lane);
+        take(h0, f0);
+      }
+      flush();
+      return;
+    }
+  }
   int64_t r = r_beg + warp;
   int32_t beg = 0, end = 0, my = 0, nbeg = 0, nend = 0;
   if (r < r_end) {
@@ -197,7 +266,7 @@ k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N,
     int32_t n2beg = 0, n2end = 0;
     if (r + 2 * kWarps < r_end) { n2beg = rowptr[r + 2 * kWarps]; n2end = rowptr[r + 2 * kWarps + 1]; }
     const int32_t deg = end - beg;
-    if (deg <= kBigRowThreshold) {                          // hub rows: k_aggregate_hubs
+    if (deg <= kBigRowThreshold) {                          // hub rows: k_aggregate_hubs / k_hub_finalize
       float acc[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) acc[i] = agg_init<kAggr>();
@@ -207,6 +276,48 @@ k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N,
       RowFrag<T>::store(out + (size_t)r * kHidden, lane, acc);
     }
     beg = nbeg; end = nend; my = nmy; nbeg = n2beg; nend = n2end;
+  }
+}
+
+// One CTA of 128 threads per range hub: thread (j, lane) owns accumulator slots 4j..4j+3 of `lane`, adds the
+// per-(band, stream warp) partials of k_aggregate_rows<kFold> in (band, warp) order -- only the slots whose warp
+// actually had a row inside the hub's range were written -- and writes the hub's aggregate row.
+template <typename T, int kAggr>
+__global__ void __launch_bounds__(128)
+k_hub_finalize(T* __restrict__ out, int64_t N, int64_t band, const int32_t* __restrict__ rowptr,
+               const int32_t* __restrict__ big_rows, const HubFold hf) {
+  constexpr int kStream = BG_AGG_STREAM_WARPS;
+  const int32_t b = blockIdx.x;
+  const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t r = big_rows[b];
+  const int64_t deg = rowptr[r + 1] - rowptr[r];
+  const int64_t lo = hf.hub_lo[b], hi = lo + deg;
+  const int64_t c0 = lo / band, c1 = (hi - 1) / band;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t c = c0; c <= c1; ++c) {
+    const int64_t a = max(lo, c * band), e = min(min(hi, (c + 1) * band), N);
+    const float4* src = reinterpret_cast<const float4*>(hf.partial) + (((int64_t)b * hf.parts + (c - c0)) * kStream) * 128 + j * 32 + lane;
+#pragma unroll
+    for (int w = 0; w < kStream; ++w) {
+      // first row >= a that stream warp w of band c walks: rows c*band + w + kStream*k
+      const int64_t first = a + (((c * band + w - a) % kStream) + kStream) % kStream;
+      if (first < e) {
+        const float4 v = __ldcg(src + (int64_t)w * 128);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+  }
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+  if constexpr (kAggr == BG_AGGR_MEAN) {
+    const float d = (float)max(deg, (int64_t)1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = v[k] / d;
+  }
+  T* orow = out + (size_t)r * kHidden;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = RowFrag<T>::col_of(lane, 4 * j + k);
+    if constexpr (sizeof(T) == 2) orow[c] = Pack16<T>::one(v[k]); else orow[c] = v[k];
   }
 }
 

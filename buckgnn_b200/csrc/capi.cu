@@ -101,10 +101,17 @@ static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
   return (unsigned)(b < max_blocks ? b : max_blocks);
 }
 
+struct HubRangeArgs { const int32_t* hub_lo; const int32_t* hub_of_row; int32_t max_degree; float* partial; };
+
+template <typename T> static inline unsigned agg_grid(int64_t N) {
+  return (unsigned)min64(ceil_div64(N, agg_row_threads<T>() / 32), (int64_t)sm_count());
+}
+static inline int64_t hub_parts(int64_t band, int32_t max_degree) { return ceil_div64(max_degree > 0 ? max_degree : 1, band) + 1; }
+
 template <typename T>
 static int aggregate_dispatch(const T* x, T* out, int64_t N, const int32_t* rowptr, const int32_t* col,
                               const int32_t* big_rows, int32_t n_big, int aggr, float* partial, int32_t* ticket,
-                              int width, cudaStream_t stream) {
+                              int width, const HubRangeArgs& hr, cudaStream_t stream) {
   if (width == 128) {
     const unsigned grid128 = (unsigned)min64(ceil_div64(N, 32), (int64_t)sm_count());
     const unsigned hub_grid128 = (unsigned)n_big * kHubSlices;
@@ -125,11 +132,31 @@ static int aggregate_dispatch(const T* x, T* out, int64_t N, const int32_t* rowp
     BG_LAUNCH_OK();
     return BG_OK;
   }
-  const unsigned grid = (unsigned)min64(ceil_div64(N, agg_row_threads<T>() / 32), (int64_t)sm_count());
+  const unsigned grid = agg_grid<T>(N);
+  const int64_t band = ceil_div64(N, grid);
+  if (hr.hub_lo && n_big > 0) {                    // range hubs folded into the row pass
+    constexpr int kThreads = agg_fold_threads<T>();
+    HubFold hf{hr.hub_of_row, hr.hub_lo, hr.partial, (int32_t)hub_parts(band, hr.max_degree)};
+    constexpr int smem = 0;
+#define BG_AGGF_CASE(A)                                                                                              \
+  case A: {                                                                                                          \
+    k_aggregate_rows<T, A, true, kThreads><<<grid, kThreads, smem, stream>>>(x, out, N, band, rowptr, col, hf);      \
+    k_hub_finalize<T, A><<<(unsigned)n_big, 128, 0, stream>>>(out, N, band, rowptr, big_rows, hf);                   \
+  } break;
+    switch (aggr) {
+      BG_AGGF_CASE(BG_AGGR_MEAN)
+      BG_AGGF_CASE(BG_AGGR_SUM)
+      default: return fail(BG_ERR_UNSUPPORTED, "bg_sage_aggregate: range hubs fold into mean / sum aggregation only");
+    }
+#undef BG_AGGF_CASE
+    BG_LAUNCH_OK();
+    return BG_OK;
+  }
   const unsigned hub_grid = (unsigned)n_big * kHubSlices;
+  const HubFold none{nullptr, nullptr, nullptr, 0};
 #define BG_AGG_CASE(A)                                                                                       \
   case A:                                                                                                    \
-    k_aggregate_rows<T, A><<<grid, agg_row_threads<T>(), 0, stream>>>(x, out, N, rowptr, col);                     \
+    k_aggregate_rows<T, A, false, agg_row_threads<T>()><<<grid, agg_row_threads<T>(), 0, stream>>>(x, out, N, band, rowptr, col, none); \
     if (n_big > 0)                                                                                           \
       k_aggregate_hubs<T, A><<<hub_grid, kAggWarpsPerBlock * 32, 0, stream>>>(x, out, rowptr, col, big_rows, \
                                                                               n_big, partial, ticket);      \
@@ -202,6 +229,7 @@ int bg_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, size_t* bytes_host)
 
 int bg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int key_row,
                  int32_t* rowptr, int32_t* col, int32_t* perm, int32_t* big_rows, int32_t* info,
+                 int32_t* hub_lo, int32_t* hub_of_row,
                  void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (E < 0 || N < 0 || E >= 0x7fffffffLL || N >= 0x7fffffffLL) return fail(BG_ERR_INVALID, "bg_csr_build: sizes out of range");
@@ -215,8 +243,11 @@ int bg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int key_row,
   const int max_big = (int)bg_csr_max_big_rows(E);
   const int sms = sm_count();
   BG_CUDA_OK(cudaMemsetAsync(w.deg, 0, sizeof(int32_t) * (size_t)(N + 1), stream));
+  if ((hub_lo != nullptr) != (hub_of_row != nullptr)) return fail(BG_ERR_INVALID, "bg_csr_build: hub_lo and hub_of_row go together");
   BG_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t) * 2, stream));
+  BG_CUDA_OK(cudaMemsetAsync(info + 4, 0, sizeof(int32_t) * 2, stream));
   BG_CUDA_OK(cudaMemsetAsync(rowptr, 0, sizeof(int32_t), stream));           // covers N == 0
+  if (hub_of_row && N > 0) BG_CUDA_OK(cudaMemsetAsync(hub_of_row, 0xff, sizeof(int32_t) * (size_t)N, stream));
   if (N == 0) return BG_OK;
   if (E > 0) {
     k_csr_hist<<<grid_for(E, 256, sms * 16), 256, 0, stream>>>(key, other, E, N, w.deg, info);
@@ -239,7 +270,7 @@ int bg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int key_row,
       BG_CUDA_OK(cudaFuncSetAttribute(k_csr_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, sort_smem));
       attr_set = true;
     }
-    k_csr_sort_big<<<sms, 1024, sort_smem, stream>>>(rowptr, big_rows, info, max_big, other, perm, col);
+    k_csr_sort_big<<<sms, 1024, sort_smem, stream>>>(rowptr, big_rows, info, max_big, other, perm, col, hub_lo, hub_of_row);
     BG_LAUNCH_OK();
   }
   return BG_OK;
@@ -288,39 +319,62 @@ int bg_encoder_front(const float* x, int64_t N, int32_t F, const float* w1, cons
 }
 
 // ------------------------------------------------------------------ K2
+static size_t generic_hub_bytes(int32_t n_big) {
+  return (size_t)n_big * kHubSlices * kHidden * sizeof(float) + (size_t)n_big * sizeof(int32_t) + 256;
+}
 int bg_aggregate_workspace_bytes(int32_t n_big, size_t* bytes_host) {
   if (!bytes_host || n_big < 0) return fail(BG_ERR_INVALID, "bg_aggregate_workspace_bytes: bad argument");
-  *bytes_host = (size_t)n_big * kHubSlices * kHidden * sizeof(float) + (size_t)n_big * sizeof(int32_t) + 256;
+  *bytes_host = generic_hub_bytes(n_big);
+  return BG_OK;
+}
+
+static size_t hubfold_bytes(int64_t N, int dtype, int32_t n_big, int32_t max_degree) {
+  const unsigned grid = dtype == BG_F32 ? agg_grid<float>(N) : agg_grid<__half>(N);
+  const int64_t band = ceil_div64(N > 0 ? N : 1, grid);
+  return (size_t)n_big * (size_t)hub_parts(band, max_degree) * BG_AGG_STREAM_WARPS * kHidden * sizeof(float) + 256;
+}
+int bg_hubfold_workspace_bytes(int64_t N, int dtype, int32_t n_big, int32_t max_degree, size_t* bytes_host) {
+  if (!bytes_host || n_big < 0 || N < 0 || max_degree < 0) return fail(BG_ERR_INVALID, "bg_hubfold_workspace_bytes: bad argument");
+  const size_t a = generic_hub_bytes(n_big), b = hubfold_bytes(N, dtype, n_big, max_degree);
+  *bytes_host = a > b ? a : b;
   return BG_OK;
 }
 
 int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t N, int32_t width, const int32_t* rowptr,
-                      const int32_t* col, const int32_t* big_rows, int32_t n_big, int aggr, void* workspace,
-                      size_t workspace_bytes, void* stream_) {
+                      const int32_t* col, const int32_t* big_rows, int32_t n_big, int aggr,
+                      const int32_t* hub_lo, const int32_t* hub_of_row, int32_t hub_max_degree,
+                      void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (N < 0 || n_big < 0) return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad size");
   if (width != 512 && width != 128) return fail(BG_ERR_UNSUPPORTED, "bg_sage_aggregate: width must be 512 or 128");
   if (N == 0) return BG_OK;
   if (!x || !out || !rowptr || !aligned16(x) || !aligned16(out)) return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad pointer");
+  if ((hub_lo != nullptr) != (hub_of_row != nullptr)) return fail(BG_ERR_INVALID, "bg_sage_aggregate: hub_lo and hub_of_row go together");
   float* partial = nullptr;
   int32_t* ticket = nullptr;
+  HubRangeArgs hr{nullptr, nullptr, 0, nullptr};
   if (n_big > 0) {
-    size_t need = 0;
-    bg_aggregate_workspace_bytes(n_big, &need);
+    const bool fold = hub_lo != nullptr && width == 512;
+    size_t need = generic_hub_bytes(n_big);
+    if (fold) { const size_t f = hubfold_bytes(N, dtype, n_big, hub_max_degree); if (f > need) need = f; }
     if (!workspace || workspace_bytes < need || !big_rows) return fail(BG_ERR_WORKSPACE, "bg_sage_aggregate: workspace too small");
-    partial = static_cast<float*>(workspace);
-    ticket = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + (size_t)n_big * kHubSlices * kHidden * sizeof(float));
-    BG_CUDA_OK(cudaMemsetAsync(ticket, 0, sizeof(int32_t) * (size_t)n_big, stream));
+    if (fold) {
+      hr = HubRangeArgs{hub_lo, hub_of_row, hub_max_degree, static_cast<float*>(workspace)};
+    } else {
+      partial = static_cast<float*>(workspace);
+      ticket = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + (size_t)n_big * kHubSlices * kHidden * sizeof(float));
+      BG_CUDA_OK(cudaMemsetAsync(ticket, 0, sizeof(int32_t) * (size_t)n_big, stream));
+    }
   }
   if (dtype == BG_BF16)
     return aggregate_dispatch(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, rowptr, col,
-                              big_rows, n_big, aggr, partial, ticket, width, stream);
+                              big_rows, n_big, aggr, partial, ticket, width, hr, stream);
   if (dtype == BG_F16)
     return aggregate_dispatch(static_cast<const __half*>(x), static_cast<__half*>(out), N, rowptr, col,
-                              big_rows, n_big, aggr, partial, ticket, width, stream);
+                              big_rows, n_big, aggr, partial, ticket, width, hr, stream);
   if (dtype == BG_F32)
     return aggregate_dispatch(static_cast<const float*>(x), static_cast<float*>(out), N, rowptr, col, big_rows, n_big,
-                              aggr, partial, ticket, width, stream);
+                              aggr, partial, ticket, width, hr, stream);
   return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad dtype");
 }
 

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(1024) k_scan_apply(const int32_t* __restrict__
       if (d[i] > kBigRowThreshold) {
         int32_t slot = atomicAdd(&info[1], 1);
         if (slot < max_big) big_rows[slot] = (int32_t)(base + i);
+        atomicMax(&info[5], d[i]);
       }
       run += d[i];
       if (base + i == N - 1) rowptr[N] = run;
@@ -166,12 +167,36 @@ BG_DEVINL void bitonic_ascending(int32_t* a, int32_t n, int32_t P) {
   }
 }
 
+// A hub row whose sorted neighbour list is exactly lo, lo+1, ..., lo+n-1 (the super node: hub edges (i -> n)
+// for i = 0..n-1 in order, reference VirtualEdgeCreate.py:106-111) is a "range hub": its aggregate is a sum
+// over a contiguous band of rows, which the row kernel of the aggregation can accumulate as a by-product
+// instead of re-reading every row (aggregate.cuh).  hub_lo[b] = lo or -1; hub_of_row[j] = b for j in the range;
+// info[4] counts hubs that are not ranges or whose ranges overlap (then the generic hub kernel is used).
+BG_DEVINL void mark_range_hub(int32_t b, const int32_t* __restrict__ colseg, int32_t n,
+                              int32_t* __restrict__ hub_lo, int32_t* __restrict__ hub_of_row,
+                              int32_t* __restrict__ info) {
+  const int32_t lo = colseg[0];
+  int ok = 1;
+  for (int32_t i = threadIdx.x; i < n; i += blockDim.x) ok &= (colseg[i] == lo + i);
+  ok = __syncthreads_and(ok);
+  if (ok) {
+    int clash = 0;
+    for (int32_t i = threadIdx.x; i < n; i += blockDim.x) clash |= (atomicCAS(&hub_of_row[lo + i], -1, b) != -1);
+    if (clash) atomicAdd(&info[4], 1);
+  }
+  if (threadIdx.x == 0) {
+    hub_lo[b] = ok ? lo : -1;
+    if (!ok) atomicAdd(&info[4], 1);
+  }
+}
+
 // one CTA per hub row (grid-stride over the list): bitonic sort of its edge ids
 __global__ void __launch_bounds__(1024) k_csr_sort_big(const int32_t* __restrict__ rowptr,
                                                        const int32_t* __restrict__ big_rows,
-                                                       const int32_t* __restrict__ info, int32_t max_big,
+                                                       int32_t* __restrict__ info, int32_t max_big,
                                                        const int64_t* __restrict__ other,
-                                                       int32_t* __restrict__ perm, int32_t* __restrict__ col) {
+                                                       int32_t* __restrict__ perm, int32_t* __restrict__ col,
+                                                       int32_t* __restrict__ hub_lo, int32_t* __restrict__ hub_of_row) {
   extern __shared__ int32_t sbuf[];
   int32_t n_big = min(info[1], max_big);
   for (int32_t b = blockIdx.x; b < n_big; b += gridDim.x) {
@@ -194,6 +219,8 @@ __global__ void __launch_bounds__(1024) k_csr_sort_big(const int32_t* __restrict
       for (int32_t i = threadIdx.x; i < n; i += blockDim.x) col[s + i] = (int32_t)other[perm[s + i]];
       __syncthreads();
     }
+    if (hub_of_row) mark_range_hub(b, col + s, n, hub_lo, hub_of_row, info);
+    __syncthreads();
   }
 }
 

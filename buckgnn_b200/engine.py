@@ -129,6 +129,11 @@ class GraphIndex:
     n_big: int
     graph_ptr: torch.Tensor
     n_graphs: int
+    # "range hubs" (bg_csr_build): set when EVERY big row's neighbour list is a contiguous run of rows --
+    # the reference's super node -- so bg_sage_aggregate can fold the hub rows into its row pass
+    hub_lo: Optional[torch.Tensor] = None
+    hub_of_row: Optional[torch.Tensor] = None
+    hub_max_degree: int = 0
 
 
 _INFO_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
@@ -155,13 +160,16 @@ class PendingGraphIndex:
         self.col = torch.empty(max(E, 1), **i32)
         self.perm = torch.empty(max(E, 1), **i32)
         self.big_rows = torch.empty(capi.csr_max_big_rows(E), **i32)
-        self.info = torch.zeros(4, **i32)
+        self.hub_lo = torch.empty(capi.csr_max_big_rows(E), **i32)
+        self.hub_of_row = torch.empty(max(N, 1), **i32)
+        self.info = torch.zeros(8, **i32)
         ws_bytes = capi.csr_workspace_bytes(N, E)
         self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with TIMERS.span("csr_build"):
             capi.csr_build(self.edge_index.data_ptr(), E, N, key_row, self.rowptr.data_ptr(), self.col.data_ptr(),
                            self.perm.data_ptr(), self.big_rows.data_ptr(), self.info.data_ptr(),
-                           self._ws.data_ptr(), ws_bytes, s)
+                           self._ws.data_ptr(), ws_bytes, s, hub_lo=self.hub_lo.data_ptr(),
+                           hub_of_row=self.hub_of_row.data_ptr())
         self.batch = None
         if batch is not None:
             _require_cuda(batch, "batch")
@@ -174,7 +182,7 @@ class PendingGraphIndex:
         side = _INFO_STREAMS.get(dev.index)
         if side is None:
             side = _INFO_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
-        self._host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+        self._host = torch.empty(8, dtype=torch.int32, pin_memory=True)
         self._done = torch.cuda.Event()
         with torch.cuda.stream(side):
             side.wait_event(ready)
@@ -198,7 +206,10 @@ class PendingGraphIndex:
             n_graphs = host[2] if N > 0 else 0
             graph_ptr = torch.empty(n_graphs + 1, **i32)
             capi.graph_ptr_build(self.batch.data_ptr(), N, n_graphs, graph_ptr.data_ptr(), _stream())
-        return GraphIndex(N, E, self.rowptr, self.col, self.perm, self.big_rows, n_big, graph_ptr, n_graphs)
+        ranges = n_big > 0 and host[4] == 0
+        return GraphIndex(N, E, self.rowptr, self.col, self.perm, self.big_rows, n_big, graph_ptr, n_graphs,
+                          hub_lo=self.hub_lo if ranges else None, hub_of_row=self.hub_of_row if ranges else None,
+                          hub_max_degree=host[5] if ranges else 0)
 
 
 def begin_graph_index(edge_index: torch.Tensor, batch: Optional[torch.Tensor], n_nodes: int,
@@ -295,15 +306,24 @@ def gemm512(segs, m: int, precision: str, out: Activation, *, cta_group: int = 2
     out.refresh_split()
 
 
-def aggregate(x: Activation, out: Activation, idx: GraphIndex, aggr: str) -> None:
+def aggregate(x: Activation, out: Activation, idx: GraphIndex, aggr: str, fold_hubs: bool = True) -> None:
     """K2 over [N,512] rows, or [N,128] rows (the encoder hidden layer of the folded first layer)."""
     width = x.data.shape[1]
     ws_bytes = capi.aggregate_workspace_bytes(idx.n_big)
+    hub = {}
+    if fold_hubs and idx.hub_lo is not None and width == 512 and aggr != "max":
+        fold_bytes = capi.hubfold_workspace_bytes(idx.n_nodes, x.code, idx.n_big, idx.hub_max_degree)
+        # the per-(hub, band, warp) partials are written and read once: only worth it while they stay
+        # small next to the pass over x they replace (many tiny hubs -> generic hub kernel)
+        if fold_bytes <= x.data.numel() * x.data.element_size() // 4 + (1 << 20):
+            ws_bytes = fold_bytes
+            hub = dict(hub_lo=idx.hub_lo.data_ptr(), hub_of_row=idx.hub_of_row.data_ptr(),
+                       hub_max_degree=idx.hub_max_degree)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.data.device)
     with TIMERS.span("aggregate" if width == 512 else "aggregate128"):
         capi.sage_aggregate(x.data.data_ptr(), out.data.data_ptr(), x.code, idx.n_nodes, idx.rowptr.data_ptr(),
                             idx.col.data_ptr(), idx.big_rows.data_ptr(), idx.n_big, capi.AGGR_CODES[aggr],
-                            ws.data_ptr(), ws_bytes, _stream(), width=width)
+                            ws.data_ptr(), ws_bytes, _stream(), width=width, **hub)
     out.refresh_split()
 
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 2
+#define BG_ABI_VERSION 3
 
 typedef enum bg_status {
   BG_OK = 0,
@@ -70,13 +70,21 @@ int bg_watchdog_info_host(uint32_t* out4_host);
  * rows) are additionally listed in big_rows (unordered), their count in info[1].
  *    info[0] : bit 0 set if any index was outside [0, N)   (such edges are dropped)
  *    info[1] : number of big rows
+ *    info[4] : number of big rows that are NOT "range hubs" (see below) or whose ranges overlap
+ *    info[5] : largest big-row degree
+ * (info has 8 words; bg_batch_info conventionally writes words 2-3 of the same buffer.)
  * big_rows must hold bg_csr_max_big_rows(E) entries.  E, N < 2^31.
+ * hub_lo [bg_csr_max_big_rows(E)] and hub_of_row [N] (optional, both or neither): a big row whose
+ * sorted neighbour list is exactly lo, lo+1, ..., lo+deg-1 (the reference's super node) gets
+ * hub_lo[b] = lo and hub_of_row[j] = b for every j in that range, else hub_lo[b] = -1; rows in no
+ * range keep hub_of_row = -1.  bg_sage_aggregate uses this to fold hub rows into its row pass.
  */
 #define BG_BIG_ROW_THRESHOLD 64
 int64_t bg_csr_max_big_rows(int64_t n_edges);
 int bg_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, size_t* bytes_host);
 int bg_csr_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int key_row,
                  int32_t* rowptr, int32_t* col, int32_t* perm, int32_t* big_rows, int32_t* info,
+                 int32_t* hub_lo, int32_t* hub_of_row,
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* Graph offsets from the PyG `batch` vector; replaces the index handling inside
@@ -105,11 +113,20 @@ int bg_encoder_front(const float* x, int64_t n_nodes, int32_t n_features,
  * x, out: [N,width] of `dtype` (bf16, f16 or f32), width 512 or 128 (the encoder's hidden layer, for the
  * folded first layer); accumulation in fp32 in CSR (stable) order.
  * Big rows (info[1] of bg_csr_build, read back by the host) are split across CTAs;
- * workspace from bg_aggregate_workspace_bytes(n_big). */
+ * workspace from bg_aggregate_workspace_bytes(n_big).
+ * hub_lo / hub_of_row (optional, both or neither; from bg_csr_build, valid only when its info[4] == 0)
+ * with hub_max_degree = info[5]: every big row is a "range hub", and for width 512 and mean / sum
+ * aggregation the hub rows are folded into the row pass (each row is added to its hub's partial sum
+ * while it is in cache) instead of a second pass over x.  Workspace then from
+ * bg_hubfold_workspace_bytes.  Summation order of a hub row is then (band, warp, row) instead of
+ * CSR order; both are fixed, so results stay run-to-run deterministic. */
 int bg_aggregate_workspace_bytes(int32_t n_big, size_t* bytes_host);
+int bg_hubfold_workspace_bytes(int64_t n_nodes, int dtype, int32_t n_big, int32_t hub_max_degree,
+                               size_t* bytes_host);
 int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t n_nodes, int32_t width,
                       const int32_t* rowptr, const int32_t* col,
                       const int32_t* big_rows, int32_t n_big, int aggr,
+                      const int32_t* hub_lo, const int32_t* hub_of_row, int32_t hub_max_degree,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ K3: tensor-core update GEMM

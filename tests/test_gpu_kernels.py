@@ -59,6 +59,31 @@ def test_csr_build_bit_exact(case, key_row):
     assert big == torch.nonzero(deg > capi.BG_BIG_ROW_THRESHOLD).flatten().tolist()
 
 
+def test_csr_range_hubs():
+    """Super-node rows are recognised as range hubs (neighbours = one contiguous run of rows); a hub with
+    arbitrary neighbours switches the whole index back to the generic hub path."""
+    b = make_batch(4, nx=13, ny=11)
+    idx = build_graph_index(b.edge_index.to(DEV), b.batch.to(DEV), b.num_nodes)
+    assert idx.n_big == 4 and idx.hub_lo is not None and idx.hub_max_degree == 13 * 11
+    big = idx.big_rows.cpu()[:4].tolist()
+    lo = idx.hub_lo.cpu()[:4].tolist()
+    want = torch.full((b.num_nodes,), -1, dtype=torch.int32)
+    for slot, (r, l) in enumerate(zip(big, lo)):
+        g = int(b.batch[r])
+        assert r == int(b.ptr[g + 1]) - 1 and l == int(b.ptr[g])          # super node = last node of its graph
+        want[l:r] = slot
+    assert torch.equal(idx.hub_of_row.cpu()[:b.num_nodes], want)
+    ei = _random_multigraph(3000, 40000, 2, hub=1234)
+    idx = build_graph_index(ei.to(DEV), None, 3000)
+    assert idx.n_big >= 1 and idx.hub_lo is None
+    # two hubs over the same range overlap -> not foldable either
+    n = 200
+    src = torch.arange(100)
+    ei = torch.cat([torch.stack([src, torch.full_like(src, 150)]), torch.stack([src, torch.full_like(src, 151)])], 1)
+    idx = build_graph_index(ei.to(DEV), None, n)
+    assert idx.n_big == 2 and idx.hub_lo is None
+
+
 def test_csr_build_rejects_out_of_range_ids():
     ei = torch.tensor([[0, 1, 5], [1, 0, 1]]).to(DEV)
     with pytest.raises(IndexError):
@@ -99,11 +124,12 @@ def test_encoder_front_matches_fp32(n, f):
 
 
 # ----------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("fold", [True, False])
 @pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
 @pytest.mark.parametrize("aggr", ["mean", "sum", "max"])
-def test_aggregate_matches_oracle(aggr, precision):
+def test_aggregate_matches_oracle(aggr, precision, fold):
     torch.manual_seed(1)
-    b = make_batch(3, nx=21, ny=17)            # hubs of degree 357 -> the split path
+    b = make_batch(3, nx=21, ny=17)            # hubs of degree 357 -> the split path / the folded range-hub path
     n = b.num_nodes
     ei = torch.cat([b.edge_index, torch.tensor([[5, 5], [9, 9]])], 1)     # duplicate edge
     ei = ei[:, ei[1] != 3]                                                  # node 3 isolated
@@ -111,11 +137,15 @@ def test_aggregate_matches_oracle(aggr, precision):
     x = x.to(engine._TORCH[engine.PRECISION_FORMATS[precision][0]]).float()
     want = O.aggregate(x.double(), ei, aggr).float()
     idx = build_graph_index(ei.to(DEV), None, n)
-    assert idx.n_big == 3
+    assert idx.n_big == 3 and idx.hub_lo is not None
     xa, oa = Activation(n, 512, precision, DEV), Activation(n, 512, precision, DEV)
     xa.data.copy_(x)
-    engine.aggregate(xa, oa, idx, aggr)
+    engine.aggregate(xa, oa, idx, aggr, fold_hubs=fold)
     got = oa.data.float().cpu()
+    if fold:                                    # deterministic: a second launch is bit-identical
+        ob = Activation(n, 512, precision, DEV)
+        engine.aggregate(xa, ob, idx, aggr, fold_hubs=True)
+        assert torch.equal(ob.data, oa.data)
     if precision == "bf16":
         torch.testing.assert_close(got, want, rtol=8e-3, atol=1e-6 if aggr != "sum" else 2e-2)
     elif precision == "fp16":
@@ -144,6 +174,25 @@ def test_aggregate_128_columns(aggr, precision):
            "fp16": dict(rtol=1e-3, atol=3e-3 if aggr == "sum" else 1e-6),
            "tf32": dict(rtol=1e-5, atol=1e-5)}[precision]
     torch.testing.assert_close(got, want, **tol)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "tf32"])
+def test_aggregate_folded_hubs_across_bands(precision):
+    """Graphs larger and smaller than an SM's band of rows, mixed: hub ranges start and end inside bands."""
+    torch.manual_seed(3)
+    sizes = [(70, 64), (9, 9), (40, 33), (9, 8), (55, 61), (12, 9)] * 3
+    from buckgnn_b200.synth import make_plate_graph, collate
+    b = collate([make_plate_graph(i, nx=nx, ny=ny) for i, (nx, ny) in enumerate(sizes)])
+    n = b.num_nodes
+    x = torch.randn(n, 512).to(engine._TORCH[engine.PRECISION_FORMATS[precision][0]]).float()
+    want = O.aggregate(x.double(), b.edge_index, "mean").float()
+    idx = build_graph_index(b.edge_index.to(DEV), b.batch.to(DEV), n)
+    assert idx.hub_lo is not None and idx.n_big == len(sizes)
+    xa, oa = Activation(n, 512, precision, DEV), Activation(n, 512, precision, DEV)
+    xa.data.copy_(x)
+    engine.aggregate(xa, oa, idx, "mean")
+    tol = dict(rtol=1e-3, atol=2e-4) if precision == "fp16" else dict(rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(oa.data.float().cpu(), want, **tol)
 
 
 # ----------------------------------------------------------------------------- K3
