@@ -32,6 +32,9 @@ EXPORTED_SYMBOLS = (
     "bg_aggregate_workspace_bytes", "bg_hubfold_workspace_bytes", "bg_sage_aggregate", "bg_gemm512",
     "bg_pool_workspace_bytes", "bg_pool_head", "bg_cast_f32", "bg_split_tf32",
     "bg_expand_rowptr", "bg_add",
+    "bg_train_workspace_bytes", "bg_bn_batch_stats", "bg_bn_act_forward", "bg_sage_backward_rows",
+    "bg_transpose_chunks", "bg_reduce_partials", "bg_colsum_workspace_bytes", "bg_colsum", "bg_pool_backward",
+    "bg_sgemm_workspace_bytes", "bg_sgemm", "bg_dropout_mask",
 )
 
 
@@ -43,14 +46,14 @@ class BuckGNNError(RuntimeError):
 
 class GemmSegment(C.Structure):
     _fields_ = [("a", C.c_void_p), ("lda", C.c_int64), ("b", C.c_void_p), ("ldb", C.c_int64),
-                ("k", C.c_int32), ("reserved", C.c_int32)]
+                ("k", C.c_int32), ("b_groups", C.c_int32)]
 
 
 class Epilogue(C.Structure):
     _fields_ = [("bias_host", C.c_void_p), ("bn_scale_host", C.c_void_p), ("bn_shift_host", C.c_void_p),
                 ("residual", C.c_void_p), ("ldr", C.c_int64), ("normalize", C.c_int32), ("relu", C.c_int32),
                 ("gather", C.c_void_p * 2),
-                ("gather_idx", C.c_void_p * 2), ("gather_ld", C.c_int64)]
+                ("gather_idx", C.c_void_p * 2), ("gather_ld", C.c_int64), ("inv_norm_out", C.c_void_p)]
 
 
 _lib = None
@@ -81,6 +84,21 @@ _SIGNATURES = {
                                _P, C.c_size_t, _P]),
     "bg_cast_f32": (C.c_int, [_P, _P, C.c_int, _I64, _P]),
     "bg_split_tf32": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "bg_train_workspace_bytes": (C.c_int, [_I64, _SZP]),
+    "bg_bn_batch_stats": (C.c_int, [_P, C.c_int, _I64, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P,
+                                    _P, C.c_size_t, _P]),
+    "bg_bn_act_forward": (C.c_int, [_P, _P, _P, C.c_int, _I64, _P, _P, C.c_float, C.c_uint64, _P]),
+    "bg_sage_backward_rows": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _I64, _P, _P, _P, _P, C.c_float, C.c_uint64,
+                                        _P, _P, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
+    "bg_transpose_chunks": (C.c_int, [_P, C.c_int, _I64, _I32, _I64, _I32, _I64, _P, _P]),
+    "bg_reduce_partials": (C.c_int, [_P, _I32, _I64, _P, C.c_int, _P]),
+    "bg_colsum_workspace_bytes": (C.c_int, [_I64, _I32, _SZP]),
+    "bg_colsum": (C.c_int, [_P, C.c_int, _I64, _I32, _I64, _P, C.c_int, _P, C.c_size_t, _P]),
+    "bg_pool_backward": (C.c_int, [_P, _I64, _P, _I64, C.c_int, _I64, _P, C.c_int, _P]),
+    "bg_sgemm_workspace_bytes": (C.c_int, [_I64, _I64, _I64, _SZP]),
+    "bg_sgemm": (C.c_int, [_P, C.c_int, _I64, _I64, _P, C.c_int, _I64, _I64, _I64, _I64, _I64, _P, C.c_int, _P,
+                           C.c_int, _I64, _P, C.c_int, _I64, C.c_int, _P, C.c_size_t, _P]),
+    "bg_dropout_mask": (C.c_int, [C.c_uint64, C.c_float, _I64, _P, _P]),
 }
 
 
@@ -189,15 +207,15 @@ def sage_aggregate(x, out, dtype, n_nodes, rowptr, col, big_rows, n_big, aggr, w
 
 def gemm512(segments, m, a_dtype, b_dtype, out, out_dtype, ldo, stream, *, bias=None, bn_scale=None,
             bn_shift=None, residual=None, ldr=0, normalize=False, relu=False, cta_group=2,
-            gather=(), gather_ld=512):
+            gather=(), gather_ld=512, inv_norm_out=None, b_groups=0):
     """segments: list of (a_ptr, lda, b_ptr, ldb, k); bias / bn_scale / bn_shift are HOST pointers;
     gather: up to two (matrix_ptr, index_ptr) pairs of gathered pre-activation addends."""
     n = len(segments)
-    arr = (GemmSegment * n)(*[GemmSegment(a, lda, b, ldb, k, 0) for (a, lda, b, ldb, k) in segments])
+    arr = (GemmSegment * n)(*[GemmSegment(a, lda, b, ldb, k, b_groups) for (a, lda, b, ldb, k) in segments])
     gm = (C.c_void_p * 2)(*([g[0] for g in gather] + [None] * (2 - len(gather))))
     gi = (C.c_void_p * 2)(*([g[1] for g in gather] + [None] * (2 - len(gather))))
     epi = Epilogue(bias, bn_scale, bn_shift, residual, ldr, int(bool(normalize)), int(bool(relu)),
-                   gm, gi, gather_ld)
+                   gm, gi, gather_ld, inv_norm_out)
     _check(load().bg_gemm512(arr, n, m, a_dtype, b_dtype, C.byref(epi), out, out_dtype, ldo, cta_group, stream),
            "bg_gemm512")
 
@@ -218,3 +236,64 @@ def cast_f32(src, dst, dst_dtype, n, stream):
 
 def split_tf32(src, hi, lo, n, stream):
     _check(load().bg_split_tf32(src, hi, lo, n, stream), "bg_split_tf32")
+
+
+# ----------------------------------------------------------------------------- training step
+def train_workspace_bytes(n_rows: int) -> int:
+    return _query("bg_train_workspace_bytes", n_rows)
+
+
+def bn_batch_stats(u, dtype, n_rows, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked,
+                   a_out, shift_out, mean_out, invstd_out, ws, ws_bytes, stream):
+    _check(load().bg_bn_batch_stats(u, dtype, n_rows, gamma, beta, eps, momentum, running_mean, running_var,
+                                    num_batches_tracked, a_out, shift_out, mean_out, invstd_out, ws, ws_bytes,
+                                    stream), "bg_bn_batch_stats")
+
+
+def bn_act_forward(u, x_prev, y, dtype, n_rows, a, shift, dropout_p, seed, stream):
+    _check(load().bg_bn_act_forward(u, x_prev, y, dtype, n_rows, a, shift, dropout_p, seed, stream),
+           "bg_bn_act_forward")
+
+
+def sage_backward_rows(u, dy, dy2, inv_norm, rowptr, dtype, n_rows, a, shift, mean, invstd, dropout_p, seed,
+                       dgamma, dbeta, accumulate, dz, dz_scaled, g_out, ws, ws_bytes, stream):
+    _check(load().bg_sage_backward_rows(u, dy, dy2, inv_norm, rowptr, dtype, n_rows, a, shift, mean, invstd,
+                                        dropout_p, seed, dgamma, dbeta, int(bool(accumulate)), dz, dz_scaled, g_out,
+                                        ws, ws_bytes, stream), "bg_sage_backward_rows")
+
+
+def transpose_chunks(src, dtype, n_rows, n_cols, ld, n_chunks, chunk_k, out, stream):
+    _check(load().bg_transpose_chunks(src, dtype, n_rows, n_cols, ld, n_chunks, chunk_k, out, stream),
+           "bg_transpose_chunks")
+
+
+def reduce_partials(partial, n_chunks, n, out, accumulate, stream):
+    _check(load().bg_reduce_partials(partial, n_chunks, n, out, int(bool(accumulate)), stream), "bg_reduce_partials")
+
+
+def colsum_workspace_bytes(rows: int, cols: int) -> int:
+    return _query("bg_colsum_workspace_bytes", rows, cols)
+
+
+def colsum(src, dtype, rows, cols, ld, out, accumulate, ws, ws_bytes, stream):
+    _check(load().bg_colsum(src, dtype, rows, cols, ld, out, int(bool(accumulate)), ws, ws_bytes, stream), "bg_colsum")
+
+
+def pool_backward(dpooled, ldp, graph_ptr, n_graphs, pool_mode, n_nodes, dx, dtype, stream):
+    _check(load().bg_pool_backward(dpooled, ldp, graph_ptr, n_graphs, pool_mode, n_nodes, dx, dtype, stream),
+           "bg_pool_backward")
+
+
+def sgemm_workspace_bytes(m: int, n: int, k: int) -> int:
+    return _query("bg_sgemm_workspace_bytes", m, n, k)
+
+
+def sgemm(a, a_dtype, sam, sak, b, b_dtype, sbk, sbn, m, n, k, bias, relu, mask, mask_dtype, mask_ld, out,
+          out_dtype, ldo, accumulate, ws, ws_bytes, stream):
+    _check(load().bg_sgemm(a, a_dtype, sam, sak, b, b_dtype, sbk, sbn, m, n, k, bias, int(bool(relu)), mask,
+                           mask_dtype, mask_ld, out, out_dtype, ldo, int(bool(accumulate)), ws, ws_bytes, stream),
+           "bg_sgemm")
+
+
+def dropout_mask(seed, dropout_p, n_rows, keep, stream):
+    _check(load().bg_dropout_mask(seed, dropout_p, n_rows, keep, stream), "bg_dropout_mask")

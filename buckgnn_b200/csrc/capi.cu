@@ -9,6 +9,7 @@
 #include "encoder.cuh"
 #include "gemm_tc.cuh"
 #include "pool_head.cuh"
+#include "train.cuh"
 
 namespace bg {
 
@@ -403,12 +404,16 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
     if (!g.a || !g.b || g.k <= 0 || g.k % kblk != 0) return fail(BG_ERR_UNSUPPORTED, "bg_gemm512: k must be a positive multiple of 64 (16-bit) / 32 (tf32)");
     if (!aligned16(g.a) || !aligned16(g.b) || (g.lda * esz) % 16 != 0 || (g.ldb * esz) % 16 != 0 || g.lda < g.k || g.ldb < g.k)
       return fail(BG_ERR_INVALID, "bg_gemm512: operand alignment / leading dimension");
+    const int groups = g.b_groups > 1 ? g.b_groups : 1;
+    if (groups != (segs[0].b_groups > 1 ? segs[0].b_groups : 1)) return fail(BG_ERR_INVALID, "bg_gemm512: segments disagree on b_groups");
+    if (groups > 1 && m != (int64_t)groups * kHidden) return fail(BG_ERR_INVALID, "bg_gemm512: b_groups needs m == b_groups * 512");
     int rc = make_operand_map(&p.seg[s].a, g.a, m, g.k, g.lda, (uint32_t)a_fmt);
-    if (rc == BG_OK) rc = make_operand_map(&p.seg[s].b, g.b, kHidden, g.k, g.ldb, (uint32_t)b_fmt);
+    if (rc == BG_OK) rc = make_operand_map(&p.seg[s].b, g.b, (int64_t)groups * kHidden, g.k, g.ldb, (uint32_t)b_fmt);
     if (rc != BG_OK) return fail(rc, "bg_gemm512: cuTensorMapEncodeTiled failed");
     p.kblocks[s] = g.k / kblk;
   }
   p.n_seg = n_seg;
+  p.b_group_tiles = segs[0].b_groups > 1 ? kHidden / (kTileM * cta_group) : 0;
   p.k_elems_per_block = kblk;
   p.a_fmt = (uint32_t)a_fmt; p.b_fmt = (uint32_t)b_fmt;
   p.n_tiles = (int32_t)ceil_div64(m, kTileM * cta_group);
@@ -435,6 +440,8 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
     if (p.n_gather > 0 && (epi->normalize || epi->residual))
       return fail(BG_ERR_UNSUPPORTED, "bg_gemm512: gathered addends cannot be combined with normalize or residual");
     p.residual = epi->residual; p.ldr = epi->ldr;
+    if (epi->inv_norm_out && !epi->normalize) return fail(BG_ERR_INVALID, "bg_gemm512: inv_norm_out needs normalize");
+    p.inv_norm_out = epi->inv_norm_out;
   }
   p.out = out; p.ldo = ldo;
 #define BG_GEMM_OUT(ADD)                                                                 \
@@ -509,6 +516,213 @@ int bg_add(const void* a, const void* b, const void* c, void* out, int dtype, in
   else if (dtype == BG_F16) k_add<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<const __half*>(c), static_cast<__half*>(out), n);
   else if (dtype == BG_F32) k_add<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(a), static_cast<const float*>(b), static_cast<const float*>(c), static_cast<float*>(out), n);
   else return fail(BG_ERR_INVALID, "bg_add: bad dtype");
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+
+// ------------------------------------------------------------------ training step
+static inline int stat_grid(int64_t N) { return (int)min64(ceil_div64(N > 0 ? N : 1, kStatWarps), (int64_t)sm_count() * 2); }
+static inline DropArgs drop_args(float p, uint64_t seed) {
+  DropArgs d;
+  d.seed = seed; d.thr = dropout_threshold(p); d.inv_keep = d.thr ? 1.f / (1.f - p) : 1.f;
+  return d;
+}
+#define BG_BY_DTYPE(dtype, CALL)                                    \
+  if ((dtype) == BG_BF16) { using T = __nv_bfloat16; CALL; }       \
+  else if ((dtype) == BG_F16) { using T = __half; CALL; }          \
+  else if ((dtype) == BG_F32) { using T = float; CALL; }           \
+  else return fail(BG_ERR_INVALID, "bad dtype");
+
+int bg_train_workspace_bytes(int64_t N, size_t* bytes_host) {
+  if (!bytes_host || N < 0) return fail(BG_ERR_INVALID, "bg_train_workspace_bytes: bad argument");
+  *bytes_host = (size_t)stat_grid(N) * 2 * kHidden * sizeof(float) + 2 * kHidden * sizeof(float) + 256;
+  return BG_OK;
+}
+
+int bg_bn_batch_stats(const void* u, int dtype, int64_t N, const float* gamma, const float* beta, float eps,
+                      float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                      float* a_out, float* shift_out, float* mean_out, float* invstd_out,
+                      void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N <= 0) return fail(BG_ERR_INVALID, "bg_bn_batch_stats: needs at least one row");
+  if (!u || !aligned16(u) || !gamma || !beta || !a_out || !shift_out || !mean_out || !invstd_out)
+    return fail(BG_ERR_INVALID, "bg_bn_batch_stats: bad pointer");
+  if ((running_mean != nullptr) != (running_var != nullptr)) return fail(BG_ERR_INVALID, "bg_bn_batch_stats: running_mean and running_var go together");
+  size_t need = 0;
+  bg_train_workspace_bytes(N, &need);
+  if (!workspace || workspace_bytes < need) return fail(BG_ERR_WORKSPACE, "bg_bn_batch_stats: workspace too small");
+  float* partial = static_cast<float*>(workspace);
+  const int grid = stat_grid(N);
+  const DropArgs nodrop = drop_args(0.f, 0);
+  BG_BY_DTYPE(dtype, (k_col_stats<T, 0><<<grid, kStatWarps * 32, 0, stream>>>(static_cast<const T*>(u), nullptr, nullptr, N,
+                                                                          nullptr, nullptr, nodrop, partial)))
+  BG_LAUNCH_OK();
+  BnVectors out{a_out, shift_out, mean_out, invstd_out};
+  k_bn_fwd_finalize<<<1, kHidden, 0, stream>>>(partial, grid, N, gamma, beta, eps, momentum, running_mean, running_var,
+                                               reinterpret_cast<long long*>(num_batches_tracked), out);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_bn_act_forward(const void* u, const void* x_prev, void* y, int dtype, int64_t N, const float* a,
+                      const float* shift, float dropout_p, uint64_t seed, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N < 0 || !(dropout_p >= 0.f && dropout_p < 1.f)) return fail(BG_ERR_INVALID, "bg_bn_act_forward: bad size / dropout_p");
+  if (N == 0) return BG_OK;
+  if (!u || !y || !a || !shift || !aligned16(u) || !aligned16(y) || (x_prev && !aligned16(x_prev)))
+    return fail(BG_ERR_INVALID, "bg_bn_act_forward: bad pointer");
+  const unsigned grid = grid_for(N * 32, 256, sm_count() * 8);
+  const DropArgs d = drop_args(dropout_p, seed);
+  BG_BY_DTYPE(dtype, (k_bn_act_fwd<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(u), static_cast<const T*>(x_prev),
+                                                                static_cast<T*>(y), N, a, shift, d)))
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_sage_backward_rows(const void* u, const void* dy, const void* dy2, const float* inv_norm, const int32_t* rowptr,
+                          int dtype, int64_t N, const float* a, const float* shift, const float* mean,
+                          const float* invstd, float dropout_p, uint64_t seed, float* dgamma, float* dbeta,
+                          int accumulate, void* dz, void* dz_scaled, void* g_out,
+                          void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N <= 0) return fail(BG_ERR_INVALID, "bg_sage_backward_rows: needs at least one row");
+  if (!(dropout_p >= 0.f && dropout_p < 1.f)) return fail(BG_ERR_INVALID, "bg_sage_backward_rows: bad dropout_p");
+  if (!u || !dy || !dz || !a || !shift || !aligned16(u) || !aligned16(dy) || !aligned16(dz) || (dy2 && !aligned16(dy2)) ||
+      (dz_scaled && (!aligned16(dz_scaled) || !rowptr)) || (g_out && !aligned16(g_out)))
+    return fail(BG_ERR_INVALID, "bg_sage_backward_rows: bad pointer");
+  const bool bn = mean != nullptr;
+  if (bn && (!invstd || !dgamma || !dbeta)) return fail(BG_ERR_INVALID, "bg_sage_backward_rows: BatchNorm needs mean, invstd, dgamma, dbeta");
+  size_t need = 0;
+  bg_train_workspace_bytes(N, &need);
+  if (!workspace || workspace_bytes < need) return fail(BG_ERR_WORKSPACE, "bg_sage_backward_rows: workspace too small");
+  float* partial = static_cast<float*>(workspace);
+  const int grid = stat_grid(N);
+  float* k0 = partial + (size_t)grid * 2 * kHidden;
+  float* k1 = k0 + kHidden;
+  const DropArgs d = drop_args(dropout_p, seed);
+  if (bn) {
+    BG_BY_DTYPE(dtype, (k_col_stats<T, 1><<<grid, kStatWarps * 32, 0, stream>>>(static_cast<const T*>(u), static_cast<const T*>(dy),
+                                                                            static_cast<const T*>(dy2), N, a, shift, d, partial)))
+    BG_LAUNCH_OK();
+    BnVectors v{const_cast<float*>(a), const_cast<float*>(shift), const_cast<float*>(mean), const_cast<float*>(invstd)};
+    k_bn_bwd_finalize<<<1, kHidden, 0, stream>>>(partial, grid, N, v, dgamma, dbeta, accumulate, k0, k1);
+    BG_LAUNCH_OK();
+  } else {
+    BG_CUDA_OK(cudaMemsetAsync(k0, 0, 2 * kHidden * sizeof(float), stream));
+  }
+  const unsigned rgrid = grid_for(N * 32, 256, sm_count() * 8);
+  BG_BY_DTYPE(dtype, (k_sage_bwd_rows<T><<<rgrid, 256, 0, stream>>>(static_cast<const T*>(u), static_cast<const T*>(dy),
+                                                                    static_cast<const T*>(dy2), N, inv_norm, rowptr, a, shift, k0, k1, d,
+                                                                    static_cast<T*>(dz), static_cast<T*>(dz_scaled), static_cast<T*>(g_out))))
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_transpose_chunks(const void* in, int dtype, int64_t n_rows, int32_t n_cols, int64_t ld, int32_t n_chunks,
+                        int64_t chunk_k, void* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_rows < 0 || n_cols <= 0 || n_cols % 32 != 0 || n_chunks <= 0 || chunk_k <= 0 || chunk_k % 32 != 0 ||
+      (int64_t)n_chunks * chunk_k < n_rows || ld < n_cols)
+    return fail(BG_ERR_INVALID, "bg_transpose_chunks: bad shape (n_cols, chunk_k multiples of 32; n_chunks*chunk_k >= n_rows)");
+  if (!in || !out) return fail(BG_ERR_INVALID, "bg_transpose_chunks: bad pointer");
+  dim3 grid((unsigned)((int64_t)n_chunks * chunk_k / 32), (unsigned)(n_cols / 32)), block(32, 8);
+  BG_BY_DTYPE(dtype, (k_transpose_chunks<T><<<grid, block, 0, stream>>>(static_cast<const T*>(in), n_rows, n_cols, ld, chunk_k, static_cast<T*>(out))))
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_reduce_partials(const float* partial, int32_t n_chunks, int64_t n, float* out, int accumulate, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n < 0 || n_chunks <= 0 || (n > 0 && (!partial || !out))) return fail(BG_ERR_INVALID, "bg_reduce_partials: bad argument");
+  if (n == 0) return BG_OK;
+  k_reduce_partials<<<grid_for(n, 256, sm_count() * 8), 256, 0, stream>>>(partial, n_chunks, n, out, accumulate);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+static inline int colsum_chunks(int64_t rows) { return (int)min64(ceil_div64(rows > 0 ? rows : 1, 64), 128); }
+int bg_colsum_workspace_bytes(int64_t rows, int32_t cols, size_t* bytes_host) {
+  if (!bytes_host || rows < 0 || cols <= 0) return fail(BG_ERR_INVALID, "bg_colsum_workspace_bytes: bad argument");
+  *bytes_host = (size_t)colsum_chunks(rows) * cols * sizeof(float) + 256;
+  return BG_OK;
+}
+int bg_colsum(const void* in, int dtype, int64_t rows, int32_t cols, int64_t ld, float* out, int accumulate,
+              void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows < 0 || cols <= 0 || ld < cols || !out) return fail(BG_ERR_INVALID, "bg_colsum: bad argument");
+  if (umma_format_of(dtype) < 0) return fail(BG_ERR_INVALID, "bg_colsum: bad dtype");
+  if (rows == 0) { if (!accumulate) BG_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * cols, stream)); return BG_OK; }
+  size_t need = 0;
+  bg_colsum_workspace_bytes(rows, cols, &need);
+  if (!in || !workspace || workspace_bytes < need) return fail(BG_ERR_WORKSPACE, "bg_colsum: workspace too small");
+  const int chunks = colsum_chunks(rows);
+  float* partial = static_cast<float*>(workspace);
+  k_colsum_partial<<<dim3((unsigned)ceil_div64(cols, 32), (unsigned)chunks), dim3(32, 8), 0, stream>>>(in, dtype, rows, cols, ld, partial);
+  BG_LAUNCH_OK();
+  k_reduce_partials<<<grid_for(cols, 256, 8), 256, 0, stream>>>(partial, chunks, cols, out, accumulate);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_pool_backward(const float* dpooled, int64_t ldp, const int32_t* graph_ptr, int64_t G, int pool_mode, int64_t N,
+                     void* dx, int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N < 0 || G <= 0 || G >= 0x7fffffffLL || ldp < kHidden) return fail(BG_ERR_INVALID, "bg_pool_backward: bad size");
+  if (pool_mode < BG_POOL_MEAN || pool_mode > BG_POOL_SUPERNODE_ONLY) return fail(BG_ERR_UNSUPPORTED, "bg_pool_backward: pool_mode must be mean, mean_no_super or supernode_only");
+  if (N == 0) return BG_OK;
+  if (!dpooled || !graph_ptr || !dx || !aligned16(dx)) return fail(BG_ERR_INVALID, "bg_pool_backward: bad pointer");
+  const unsigned grid = grid_for(N * 32, 256, sm_count() * 8);
+  BG_BY_DTYPE(dtype, (k_pool_bwd<T><<<grid, 256, 0, stream>>>(dpooled, ldp, graph_ptr, (int)G, pool_mode, N, static_cast<T*>(dx))))
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+static inline int sgemm_splits(int64_t M, int64_t N, int64_t K) {
+  const int64_t tiles = ceil_div64(M, kSgTile) * ceil_div64(N, kSgTile);
+  int64_t s = ceil_div64((int64_t)sm_count() * 2, tiles);
+  const int64_t max_s = ceil_div64(K, 256);                 // at least 256 of K per split
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  if (s > 512) s = 512;
+  return (int)s;
+}
+int bg_sgemm_workspace_bytes(int64_t M, int64_t N, int64_t K, size_t* bytes_host) {
+  if (!bytes_host || M < 0 || N < 0 || K < 0) return fail(BG_ERR_INVALID, "bg_sgemm_workspace_bytes: bad argument");
+  *bytes_host = (size_t)sgemm_splits(M, N, K) * (size_t)M * (size_t)N * sizeof(float) + 256;
+  return BG_OK;
+}
+int bg_sgemm(const void* a, int a_dtype, int64_t sam, int64_t sak, const void* b, int b_dtype, int64_t sbk, int64_t sbn,
+             int64_t M, int64_t N, int64_t K, const float* bias, int relu, const void* mask, int mask_dtype,
+             int64_t mask_ld, void* out, int out_dtype, int64_t ldo, int accumulate,
+             void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (M < 0 || N < 0 || K < 0 || M >= 0x7fffffffLL || N > 65535LL * kSgTile) return fail(BG_ERR_INVALID, "bg_sgemm: bad size");
+  if (umma_format_of(a_dtype) < 0 || umma_format_of(b_dtype) < 0 || umma_format_of(out_dtype) < 0 ||
+      (mask && umma_format_of(mask_dtype) < 0))
+    return fail(BG_ERR_INVALID, "bg_sgemm: bad dtype");
+  if (M == 0 || N == 0) return BG_OK;
+  if ((K > 0 && (!a || !b)) || !out || ldo < N) return fail(BG_ERR_INVALID, "bg_sgemm: bad pointer / ldo");
+  size_t need = 0;
+  bg_sgemm_workspace_bytes(M, N, K, &need);
+  if (!workspace || workspace_bytes < need) return fail(BG_ERR_WORKSPACE, "bg_sgemm: workspace too small");
+  const int splits = sgemm_splits(M, N, K);
+  const int64_t k_per = ceil_div64(ceil_div64(K > 0 ? K : 1, splits), kSgK) * kSgK;
+  SgemmArgs g{a, b, a_dtype, b_dtype, sam, sak, sbk, sbn, M, N, K, k_per, static_cast<float*>(workspace)};
+  if (ceil_div64(M, kSgTile) > 65535) return fail(BG_ERR_UNSUPPORTED, "bg_sgemm: M too large for the grid");
+  k_sgemm<<<dim3((unsigned)ceil_div64(N, kSgTile), (unsigned)ceil_div64(M, kSgTile), (unsigned)splits), 256, 0, stream>>>(g);
+  BG_LAUNCH_OK();
+  SgemmEpilogue e{static_cast<const float*>(workspace), splits, M, N, bias, relu, mask, mask_dtype, mask_ld, out, out_dtype, ldo, accumulate};
+  k_sgemm_epilogue<<<grid_for(M * N, 256, sm_count() * 8), 256, 0, stream>>>(e);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_dropout_mask(uint64_t seed, float dropout_p, int64_t n_rows, uint8_t* keep, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_rows < 0 || (n_rows > 0 && !keep) || !(dropout_p >= 0.f && dropout_p < 1.f)) return fail(BG_ERR_INVALID, "bg_dropout_mask: bad argument");
+  if (n_rows == 0) return BG_OK;
+  k_dropout_mask<<<grid_for(n_rows * kHidden, 256, sm_count() * 8), 256, 0, stream>>>(seed, dropout_threshold(dropout_p), n_rows, keep);
   BG_LAUNCH_OK();
   return BG_OK;
 }

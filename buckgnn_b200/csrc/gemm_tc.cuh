@@ -80,6 +80,9 @@ struct alignas(64) GemmParams {
   const void* gather[2];            // [*, 512] row-major matrices of the output dtype, ld = gather_ld
   const int32_t* gidx[2];           // [M] row index into gather[k]
   int64_t gather_ld;
+  float* inv_norm_out;              // [M] f32 or null: 1 / max(|row|, eps) of normalized rows (saved for the backward pass)
+  int32_t b_group_tiles;            // 0: one B for all rows; t: row tile i multiplies B rows [(i / t) * 512, +512)
+  int32_t pad_;
   float bias[kHidden];              // epilogue vectors by value -> constant bank, broadcast reads
   float scale[kHidden];             // 1 when there is no BN
   float shift[kHidden];             // 0 when there is no BN
@@ -246,6 +249,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
       named_bar_sync(1, 256);
       inv = 1.f / fmaxf(sqrtf(ss + cx.partner_tile[lane]), 1e-12f);
       named_bar_sync(1, 256);                                   // partner has read before pass 2 reuses the tile
+      if (p.inv_norm_out != nullptr && g == 0 && m_row < p.m) p.inv_norm_out[m_row] = inv;
     }
     BG_PROF_ADD(_pacc_b);
     BG_PROF_T0();
@@ -419,6 +423,7 @@ k_gemm512(const __grid_constant__ GemmParams p) {
         uint32_t stage = 0, phase = 0;
         for (int tile = tile0; tile < p.n_tiles; tile += tile_stride) {
           const int32_t row0 = tile * (kTileM * kCg) + (int32_t)rank * kTileM;
+          const int32_t brow0 = p.b_group_tiles ? (tile / p.b_group_tiles) * kHidden : 0;   // split-K groups
           for (int s = 0; s < p.n_seg; ++s) {
             const void* map_a = &p.seg[s].a;
             const void* map_b = &p.seg[s].b;
@@ -434,14 +439,14 @@ k_gemm512(const __grid_constant__ GemmParams p) {
                 tma_load_2d(sa, map_a, full_bar(stage), k0, row0);
 #pragma unroll
                 for (int j = 0; j < Cfg::kBRows / 128; ++j)
-                  tma_load_2d(sb + j * 16384, map_b, full_bar(stage), k0, j * 128);
+                  tma_load_2d(sb + j * 16384, map_b, full_bar(stage), k0, brow0 + j * 128);
               } else {
                 if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
                 else mbar_arrive_cluster(full_bar(stage), 0);
                 tma_load_2d_cg2(sa, map_a, full_bar(stage), k0, row0);
 #pragma unroll
                 for (int j = 0; j < Cfg::kBRows / 128; ++j)      // N half j: weight rows j*256 + rank*128
-                  tma_load_2d_cg2(sb + j * 16384, map_b, full_bar(stage), k0, j * 256 + (int32_t)rank * 128);
+                  tma_load_2d_cg2(sb + j * 16384, map_b, full_bar(stage), k0, brow0 + j * 256 + (int32_t)rank * 128);
               }
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }

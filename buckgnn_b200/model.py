@@ -13,7 +13,12 @@ Mirrors `Models/BuckGNN.py` of the reference:
 The forward never touches PyG / torch_scatter / ATen math: it is the kernel sequence
 in `engine.py`.  CPU tensors raise -- there is no fallback path.
 
-Extra, non-reference keyword: `precision` in {"auto", "fp16", "bf16", "tf32", "fp32"}
+In train mode (`model.train()`, as TRAIN_FINAL.py:289 does) the forward uses batch statistics in
+BatchNorm1d, applies Dropout and is differentiable: `loss.backward()` runs the backward kernels
+(`train.py`) and leaves `.grad` on the parameters that model_name uses.
+
+Extra, non-reference keywords: `train_precision` in {"tf32", "bf16", "fp16"} (storage of the training
+step's activations and activation gradients; default tf32 = fp32 storage), and `precision` in {"auto", "fp16", "bf16", "tf32", "fp32"}
 selects how the tensor-core GEMMs read their operands (engine.PRECISION_FORMATS; fp32 =
 3xTF32 split, the "fp32-GEMM mode"; "auto" = fp16 for mean/max aggregation, tf32 for
 sum/add whose hub rows can leave the fp16 range).
@@ -92,7 +97,7 @@ class BuckGNN(nn.Module):
                  num_layers=6, pooling_layer="mean", prediction_type="buckling",
                  use_z_coord=False, use_rotations=False, dropout_rate=0.1,
                  model_name="GraphSAGE_MLP", *, precision: str = "auto", cta_group: int = 2,
-                 cache_index: bool = False, fold_encoder: bool = True):
+                 cache_index: bool = False, fold_encoder: bool = True, train_precision: str = "tf32"):
         super().__init__()
         if precision == "auto":
             aggr = _SAGE_LISTS[model_name][1] if model_name in _SAGE_LISTS else (
@@ -100,6 +105,9 @@ class BuckGNN(nn.Module):
             precision = engine.default_precision(aggr)
         if precision not in engine.PRECISIONS:
             raise ValueError(f"precision must be \"auto\" or one of {engine.PRECISIONS}")
+        if train_precision not in ("tf32", "bf16", "fp16"):
+            raise ValueError('train_precision must be one of "tf32", "bf16", "fp16"')
+        self.train_precision = train_precision          # storage of activations / their gradients in train mode
         self.hidden_channels = hidden_channels
         self.prediction_type = prediction_type
         self.pooling_layer = pooling_layer
@@ -207,9 +215,14 @@ class BuckGNN(nn.Module):
     def _check_supported(self, x):
         if not x.is_cuda:
             raise RuntimeError("buckgnn_b200.BuckGNN runs on CUDA (sm_100a) tensors only; there is no CPU path")
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("buckgnn_b200: the training step (backward kernels + BN batch statistics) "
-                                      "is not built yet; call model.eval() under torch.no_grad()")
+        if self.training:
+            if self.model_name not in _SAGE_LISTS and self.model_name != "GraphSage_addAggr_Shared":
+                raise NotImplementedError(f"buckgnn_b200: the training step is built for the GraphSAGE variants; "
+                                          f"model_name={self.model_name!r} runs in eval mode only")
+            if self.model_name == "GraphSage_maxAggr":
+                raise NotImplementedError("buckgnn_b200: training with max aggregation is not built")
+            if self.pooling_layer not in ("mean", "mean_no_super", "supernode_only"):
+                raise NotImplementedError(f"buckgnn_b200: training with pooling_layer={self.pooling_layer!r} is not built")
         if self.hidden_channels != 512:
             raise NotImplementedError("buckgnn_b200: the tcgen05 path is built for hidden_channels=512")
         if self.model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):
@@ -230,6 +243,9 @@ class BuckGNN(nn.Module):
             if self.pooling_layer == "hybrid":
                 raise AttributeError("'BuckGNN' object has no attribute 'hybrid_pooling'")   # reference :188,276
             raise ValueError(f"Unknown pooling layer: {self.pooling_layer}")
+        if self.training:       # train-mode BatchNorm / Dropout + autograd through the backward kernels (train.py)
+            from . import train
+            return train.forward_train(self, x, edge_index, batch).squeeze(), batch
         with torch.no_grad():
             if self.model_name in ("EA_GNN", "EA_GNN_Shared"):
                 pred = self._forward_cuda_eagnn(x, edge_index, edge_attr, batch)

@@ -1,0 +1,359 @@
+"""Training step of the GraphSAGE BuckGNN on the sm_100a kernels (BASELINE.json configs[3]).
+
+`TRAIN_FINAL.py:289-297` of the reference does `model.train(); pred, _ = model(...); loss.backward();
+optimizer.step()`.  In train mode `BuckGNN.forward` routes here: one `torch.autograd.Function` whose
+forward and backward are sequences of C-ABI calls (include/buckgnn_b200.h, "training step"); torch
+provides memory, streams and the autograd graph edge between `pred` and the parameters, nothing else.
+
+Per layer (Models/BuckGNN.py:447-458, train mode)
+    forward   agg = A x                                   bg_sage_aggregate            (saved)
+              u = normalize(agg Wl^T + b + x Wr^T)        bg_gemm512, inv_norm_out     (saved, with 1/|z|)
+              batch statistics of u -> a, shift           bg_bn_batch_stats (+ running stats, momentum)
+              y = dropout(relu(a u + shift) + x_prev)     bg_bn_act_forward (counter-based mask)
+    backward  dz, dgamma, dbeta                           bg_sage_backward_rows
+              dWl = dz^T agg, dWr = dz^T x                bg_transpose_chunks + bg_gemm512(b_groups) + bg_reduce_partials
+              db = colsum(dz)                             bg_colsum
+              dagg = (dz / deg) Wl                        bg_gemm512 on the transposed weight
+              dx = dz Wr + A^T dagg  (+ g on skip layers) bg_sage_aggregate over the CSR keyed by source + bg_gemm512
+The encoder's first two Linears, the decoder and their gradients run on `bg_sgemm` (fp32 CUDA cores).
+
+Precision: `train_precision` in {"tf32" (default; fp32 storage), "bf16", "fp16"}: activations, saved tensors and
+gradients of activations are stored in that format, weight gradients and all reductions are fp32.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import capi, engine
+from .engine import Activation, _p, _stream
+
+_GOLDEN = 0x9E3779B97F4A7C15
+_MASK64 = (1 << 64) - 1
+
+
+def layer_seed(seed: int, layer: int) -> int:
+    return (seed + (layer + 1) * _GOLDEN) & _MASK64
+
+
+def _f32(shape, dev):
+    return torch.empty(shape, dtype=torch.float32, device=dev)
+
+
+def _ws(nbytes, dev):
+    return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+
+
+def sgemm(a, a_code, sam, sak, b, b_code, sbk, sbn, m, n, k, out, out_code, ldo, *, bias=None, relu=False,
+          mask=None, mask_code=capi.BG_F32, mask_ld=0, accumulate=False):
+    """out[m,n] (+)= mask(relu(sum_k a[m*sam + k*sak] * b[k*sbk + n*sbn] + bias[n]))   (bg_sgemm)."""
+    nbytes = capi.sgemm_workspace_bytes(m, n, k)
+    ws = _ws(nbytes, out.device)
+    capi.sgemm(a.data_ptr(), a_code, sam, sak, b.data_ptr(), b_code, sbk, sbn, m, n, k, _p(bias), relu,
+               _p(mask), mask_code, mask_ld, out.data_ptr(), out_code, ldo, accumulate, ws.data_ptr(), nbytes, _stream())
+
+
+def colsum(src, code, rows, cols, ld, out, accumulate=False):
+    nbytes = capi.colsum_workspace_bytes(rows, cols)
+    ws = _ws(nbytes, out.device)
+    capi.colsum(src.data_ptr(), code, rows, cols, ld, out.data_ptr(), accumulate, ws.data_ptr(), nbytes, _stream())
+
+
+def split_k_layout(n_rows: int):
+    """(chunks, chunk_k) of the split over nodes for the weight-gradient GEMMs: one 512 x 512 product per CTA
+    pair of the 148-SM part when there is enough work, K per chunk a multiple of 64."""
+    chunks = max(1, min(37, -(-n_rows // 1024)))
+    chunk_k = -(-(-(-n_rows // chunks)) // 64) * 64
+    return chunks, chunk_k
+
+
+class ChunkedTranspose:
+    """[N, C] activation -> [chunks][C][chunk_k] (bg_transpose_chunks): node dimension contiguous."""
+
+    def __init__(self, act: torch.Tensor, code: int, n_rows: int, chunks: int, chunk_k: int):
+        cols = act.shape[1]
+        self.data = torch.empty((chunks * cols, chunk_k), dtype=act.dtype, device=act.device)
+        self.code, self.chunks, self.chunk_k, self.cols = code, chunks, chunk_k, cols
+        capi.transpose_chunks(act.data_ptr(), code, n_rows, cols, act.shape[1], chunks, chunk_k,
+                              self.data.data_ptr(), _stream())
+
+
+def weight_grad_512(dz_t: ChunkedTranspose, act_t: ChunkedTranspose, precision: str, out: torch.Tensor,
+                    accumulate: bool) -> None:
+    """out[o, i] (+)= sum_n dz[n, o] act[n, i]  -- `chunks` independent 512x512xchunk_k products on tcgen05
+    (fp32 partials), then a fixed-order sum over the chunks."""
+    s, kc = dz_t.chunks, dz_t.chunk_k
+    dev = out.device
+    partial = _f32((s * 512, 512), dev)
+    a_code, b_code = engine.PRECISION_FORMATS[precision]
+    with engine.TIMERS.span("train_wgrad_gemm"):
+        capi.gemm512([(dz_t.data.data_ptr(), kc, act_t.data.data_ptr(), kc, kc)], s * 512, a_code, b_code,
+                     partial.data_ptr(), capi.BG_F32, 512, _stream(), b_groups=s)
+    capi.reduce_partials(partial.data_ptr(), s, 512 * 512, out.data_ptr(), accumulate, _stream())
+
+
+def transposed_pack(weight: torch.Tensor, precision: str) -> engine.LinearPack:
+    """W^T in operand format: the B operand of dX = dZ W (rows = input features)."""
+    w = weight.detach().to(torch.float32).contiguous()
+    wt = torch.empty((w.shape[1], w.shape[0]), dtype=torch.float32, device=w.device)
+    capi.transpose_chunks(w.data_ptr(), capi.BG_F32, w.shape[0], w.shape[1], w.shape[1], 1, w.shape[0],
+                          wt.data_ptr(), _stream())
+    return engine.pack_linear(wt, precision)
+
+
+class _Saved:
+    pass
+
+
+class SageTrainFunction(torch.autograd.Function):
+    """pred = f(parameters); x / edge_index / batch are data (no gradient)."""
+
+    @staticmethod
+    def forward(ctx, model, x, edge_index, batch, seed, *params):
+        prec = model.train_precision
+        code = engine.PRECISION_FORMATS[prec][0]
+        dev = x.device
+        s = _stream()
+        x = x.detach().to(torch.float32).contiguous()
+        n, f = x.shape
+        convs = model._sage_layers()
+        L = len(convs)
+        aggr = convs[0][0].aggr
+        if aggr == "max":
+            raise NotImplementedError("buckgnn_b200: training with max aggregation is not built")
+        p_drop = float(model.dropout.p)
+        pending = engine.begin_graph_index(edge_index, batch, n)
+        # one read-back for all epilogue bias vectors of the step (they travel as kernel parameters)
+        enc = model.node_encoder
+        uniq_convs = []
+        for c, _ in convs:
+            if all(c is not q for q in uniq_convs):
+                uniq_convs.append(c)
+        biases = torch.stack([enc[4].bias.detach().float()] + [c.lin_l.bias.detach().float() for c in uniq_convs]).cpu()
+        bias_of = {id(c): biases[1 + k] for k, c in enumerate(uniq_convs)}
+
+        sv = _Saved()
+        sv.model, sv.prec, sv.code, sv.n, sv.f, sv.x, sv.seed, sv.p_drop, sv.aggr = model, prec, code, n, f, x, seed, p_drop, aggr
+        # ---- encoder (Models/BuckGNN.py:68-74, :323)
+        w1, b1 = enc[0].weight.detach().float().contiguous(), enc[0].bias.detach().float().contiguous()
+        w2, b2 = enc[2].weight.detach().float().contiguous(), enc[2].bias.detach().float().contiguous()
+        with engine.TIMERS.span("train_encoder"):
+            h1 = _f32((n, 64), dev)
+            sgemm(x, capi.BG_F32, f, 1, w1, capi.BG_F32, 1, f, n, 64, f, h1, capi.BG_F32, 64, bias=b1, relu=True)
+            h2 = Activation(n, 128, prec, dev)
+            sgemm(h1, capi.BG_F32, 64, 1, w2, capi.BG_F32, 1, 64, n, 128, 64, h2.data, code, 128, bias=b2, relu=True)
+            h2.refresh_split()
+            cur = Activation(n, 512, prec, dev)
+            engine.gemm512(engine._segments(h2, engine.pack_linear(enc[4].weight, prec)), n, prec, cur,
+                           bias=biases[0].data_ptr())
+        sv.h1, sv.h2 = h1, h2
+        idx = pending.finish()
+        sv.idx = idx
+        sv.edge_index = pending.edge_index
+        # ---- layers
+        packs = {}
+        sv.layers = []
+        ws_bytes = capi.train_workspace_bytes(n)
+        ws = _ws(ws_bytes, dev)
+        ones = torch.ones(512, dtype=torch.float32, device=dev)
+        zeros = torch.zeros(512, dtype=torch.float32, device=dev)
+        for i, (conv, bn) in enumerate(convs):
+            if id(conv) not in packs:
+                packs[id(conv)] = (engine.pack_linear(conv.lin_l.weight, prec), engine.pack_linear(conv.lin_r.weight, prec))
+            wl, wr = packs[id(conv)]
+            agg = Activation(n, 512, prec, dev)
+            engine.aggregate(cur, agg, idx, aggr)
+            u = Activation(n, 512, prec, dev)
+            inv_norm = _f32((n,), dev)
+            with engine.TIMERS.span("train_update_gemm"):
+                engine.gemm512(engine._segments(agg, wl) + engine._segments(cur, wr), n, prec, u,
+                               bias=bias_of[id(conv)].data_ptr(), normalize=True, inv_norm_out=inv_norm.data_ptr())
+            vec = None
+            if bn is not None:
+                vec = _f32((4, 512), dev)              # a, shift, mean, invstd
+                track = bn.track_running_stats and bn.running_mean is not None
+                momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+                with engine.TIMERS.span("train_bn_stats"):
+                    capi.bn_batch_stats(u.data.data_ptr(), code, n, bn.weight.detach().data_ptr(), bn.bias.detach().data_ptr(),
+                                        float(bn.eps), momentum, bn.running_mean.data_ptr() if track else None,
+                                        bn.running_var.data_ptr() if track else None,
+                                        bn.num_batches_tracked.data_ptr() if track else None,
+                                        vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(),
+                                        ws.data_ptr(), ws_bytes, s)
+                a_vec, shift_vec = vec[0], vec[1]
+            else:
+                a_vec, shift_vec = ones, zeros
+            residual = 0 < i < L - 1
+            y = Activation(n, 512, prec, dev)
+            with engine.TIMERS.span("train_bn_act"):
+                capi.bn_act_forward(u.data.data_ptr(), cur.data.data_ptr() if residual else None, y.data.data_ptr(), code, n,
+                                    a_vec.data_ptr(), shift_vec.data_ptr(), p_drop, layer_seed(seed, i), s)
+            y.refresh_split()
+            sv.layers.append((conv, bn, cur, agg, u, inv_norm, vec, residual))
+            cur = y
+        sv.ones, sv.zeros = ones, zeros
+        # ---- pooling + decoder (Models/BuckGNN.py:515-516)
+        dec = model.decoder
+        decw = {"w1": dec[0].weight.detach(), "b1": dec[0].bias.detach(), "w2": dec[2].weight.detach(),
+                "b2": dec[2].bias.detach(), "w3": dec[4].weight.detach(), "b3": dec[4].bias.detach()}
+        decw = {k: v.float().contiguous() for k, v in decw.items()}
+        pred, pooled = engine.pool_head(cur, idx, decw, model.output_dim, want_pooled=True, pooling=model.pooling_layer)
+        sv.decw, sv.pooled = decw, pooled
+        ctx.sv = sv
+        ctx.params = params
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        sv = ctx.sv
+        model, prec, code, n, f = sv.model, sv.prec, sv.code, sv.n, sv.f
+        dev = sv.x.device
+        s = _stream()
+        F32 = capi.BG_F32
+        dpred = dpred.detach().to(torch.float32).contiguous()
+        g_count, out_dim = sv.pooled.shape[0], model.output_dim
+        grads = {}
+
+        def gbuf(param):
+            t = grads.get(id(param))
+            fresh = t is None
+            if fresh:
+                t = grads[id(param)] = _f32(tuple(param.shape), dev)
+            return t, not fresh                      # (buffer, accumulate?)
+
+        # ---- decoder: recompute the two hidden layers, then backward (all [G, <=512]: bg_sgemm)
+        d = sv.decw
+        dec = model.decoder
+        with engine.TIMERS.span("train_head_bwd"):
+            h1d, h2d = _f32((g_count, 128), dev), _f32((g_count, 64), dev)
+            sgemm(sv.pooled, F32, 512, 1, d["w1"], F32, 1, 512, g_count, 128, 512, h1d, F32, 128, bias=d["b1"], relu=True)
+            sgemm(h1d, F32, 128, 1, d["w2"], F32, 1, 128, g_count, 64, 128, h2d, F32, 64, bias=d["b2"], relu=True)
+            dw3, _ = gbuf(dec[4].weight); db3, _ = gbuf(dec[4].bias)
+            sgemm(dpred, F32, 1, out_dim, h2d, F32, 64, 1, out_dim, 64, g_count, dw3, F32, 64)
+            colsum(dpred, F32, g_count, out_dim, out_dim, db3)
+            dh2d = _f32((g_count, 64), dev)
+            sgemm(dpred, F32, out_dim, 1, d["w3"], F32, 64, 1, g_count, 64, out_dim, dh2d, F32, 64, mask=h2d, mask_ld=64)
+            dw2, _ = gbuf(dec[2].weight); db2, _ = gbuf(dec[2].bias)
+            sgemm(dh2d, F32, 1, 64, h1d, F32, 128, 1, 64, 128, g_count, dw2, F32, 128)
+            colsum(dh2d, F32, g_count, 64, 64, db2)
+            dh1d = _f32((g_count, 128), dev)
+            sgemm(dh2d, F32, 64, 1, d["w2"], F32, 128, 1, g_count, 128, 64, dh1d, F32, 128, mask=h1d, mask_ld=128)
+            dw1, _ = gbuf(dec[0].weight); db1, _ = gbuf(dec[0].bias)
+            sgemm(dh1d, F32, 1, 128, sv.pooled, F32, 512, 1, 128, 512, g_count, dw1, F32, 512)
+            colsum(dh1d, F32, g_count, 128, 128, db1)
+            dpooled = _f32((g_count, 512), dev)
+            sgemm(dh1d, F32, 128, 1, d["w1"], F32, 512, 1, g_count, 512, 128, dpooled, F32, 512)
+            # ---- global_mean_pool backward
+            dcur = Activation(n, 512, prec, dev)
+            capi.pool_backward(dpooled.data_ptr(), 512, sv.idx.graph_ptr.data_ptr(), g_count,
+                               capi.POOL_MODES[model.pooling_layer], n, dcur.data.data_ptr(), code, s)
+        dy2: Optional[Activation] = None
+
+        # ---- message passing layers, last to first
+        idx = sv.idx
+        idx_t = engine.build_graph_index(sv.edge_index, None, n, key_row=0) if sv.layers else None   # A^T
+        chunks, chunk_k = split_k_layout(n)
+        ws_bytes = capi.train_workspace_bytes(n)
+        ws = _ws(ws_bytes, dev)
+        tpacks = {}
+        mean = sv.aggr == "mean"
+        L = len(sv.layers)
+        for i in range(L - 1, -1, -1):
+            conv, bn, x_in, agg, u, inv_norm, vec, residual = sv.layers[i]
+            dz = Activation(n, 512, prec, dev)
+            dzs = Activation(n, 512, prec, dev) if mean else dz
+            g = Activation(n, 512, prec, dev) if residual else None
+            if bn is not None:
+                dgam, acc_g = gbuf(bn.weight); dbet, _ = gbuf(bn.bias)
+                a_vec, shift_vec, mean_vec, invstd_vec = vec[0], vec[1], vec[2], vec[3]
+            else:
+                dgam = dbet = mean_vec = invstd_vec = None
+                acc_g = False
+                a_vec, shift_vec = sv.ones, sv.zeros
+            with engine.TIMERS.span("train_bwd_rows"):
+                capi.sage_backward_rows(u.data.data_ptr(), dcur.data.data_ptr(), None if dy2 is None else dy2.data.data_ptr(),
+                                        inv_norm.data_ptr(), idx.rowptr.data_ptr() if mean else None, code, n,
+                                        a_vec.data_ptr(), shift_vec.data_ptr(), _p(mean_vec), _p(invstd_vec), sv.p_drop,
+                                        layer_seed(sv.seed, i), _p(dgam), _p(dbet), acc_g, dz.data.data_ptr(),
+                                        dzs.data.data_ptr() if mean else None, None if g is None else g.data.data_ptr(),
+                                        ws.data_ptr(), ws_bytes, s)
+            dz.refresh_split()
+            if mean:
+                dzs.refresh_split()
+            # weight gradients: split-K over nodes on the tensor cores
+            with engine.TIMERS.span("train_wgrad"):
+                dz_t = ChunkedTranspose(dz.data, code, n, chunks, chunk_k)
+                dwl, acc_l = gbuf(conv.lin_l.weight)
+                weight_grad_512(dz_t, ChunkedTranspose(agg.data, code, n, chunks, chunk_k), prec, dwl, acc_l)
+                dwr, acc_r = gbuf(conv.lin_r.weight)
+                weight_grad_512(dz_t, ChunkedTranspose(x_in.data, code, n, chunks, chunk_k), prec, dwr, acc_r)
+                dbl, acc_b = gbuf(conv.lin_l.bias)
+                colsum(dz.data, code, n, 512, 512, dbl, accumulate=acc_b)
+                del dz_t
+            # input gradient: dx = dz Wr + A^T (dz/deg Wl)  (+ g, added by the next iteration through dy2)
+            if id(conv) not in tpacks:
+                tpacks[id(conv)] = (transposed_pack(conv.lin_l.weight, prec), transposed_pack(conv.lin_r.weight, prec))
+            wlt, wrt = tpacks[id(conv)]
+            dagg = Activation(n, 512, prec, dev)
+            with engine.TIMERS.span("train_dgrad_gemm"):
+                engine.gemm512(engine._segments(dzs, wlt), n, prec, dagg)
+            sbuf = Activation(n, 512, prec, dev)
+            engine.aggregate(dagg, sbuf, idx_t, "sum")
+            dx = Activation(n, 512, prec, dev)
+            with engine.TIMERS.span("train_dgrad_gemm"):
+                engine.gemm512(engine._segments(dz, wrt), n, prec, dx, residual=sbuf.data.data_ptr(), ldr=512)
+            dcur, dy2 = dx, g
+        # ---- encoder backward (dy2 is None here: layer 0 has no skip)
+        enc = model.node_encoder
+        dx0 = dcur.data
+        with engine.TIMERS.span("train_encoder_bwd"):
+            w3 = enc[4].weight.detach().float().contiguous()
+            w2 = enc[2].weight.detach().float().contiguous()
+            dw3e, _ = gbuf(enc[4].weight); db3e, _ = gbuf(enc[4].bias)
+            sgemm(dx0, code, 1, 512, sv.h2.data, code, 128, 1, 512, 128, n, dw3e, F32, 128)
+            colsum(dx0, code, n, 512, 512, db3e)
+            dh2 = _f32((n, 128), dev)
+            sgemm(dx0, code, 512, 1, w3, F32, 128, 1, n, 128, 512, dh2, F32, 128, mask=sv.h2.data, mask_code=code, mask_ld=128)
+            dw2e, _ = gbuf(enc[2].weight); db2e, _ = gbuf(enc[2].bias)
+            sgemm(dh2, F32, 1, 128, sv.h1, F32, 64, 1, 128, 64, n, dw2e, F32, 64)
+            colsum(dh2, F32, n, 128, 128, db2e)
+            dh1 = _f32((n, 64), dev)
+            sgemm(dh2, F32, 128, 1, w2, F32, 64, 1, n, 64, 128, dh1, F32, 64, mask=sv.h1, mask_ld=64)
+            dw1e, _ = gbuf(enc[0].weight); db1e, _ = gbuf(enc[0].bias)
+            sgemm(dh1, F32, 1, 64, sv.x, F32, f, 1, 64, f, n, dw1e, F32, f)
+            colsum(dh1, F32, n, 64, 64, db1e)
+        ctx.sv = None
+        out: List[Optional[torch.Tensor]] = []
+        for p_ in ctx.params:
+            t = grads.get(id(p_))
+            out.append(None if t is None else t.to(p_.dtype))
+        return (None, None, None, None, None, *out)
+
+
+def trainable_parameters(model) -> List[torch.nn.Parameter]:
+    """Parameters the GraphSAGE training step produces gradients for (the reference registers more
+    modules than a given `model_name` uses: Models/BuckGNN.py:164,184-187)."""
+    ps: List[torch.nn.Parameter] = []
+    seen = set()
+
+    def add(p):
+        if p is not None and id(p) not in seen:
+            seen.add(id(p)); ps.append(p)
+
+    for m in (model.node_encoder[0], model.node_encoder[2], model.node_encoder[4]):
+        add(m.weight); add(m.bias)
+    for conv, bn in model._sage_layers():
+        add(conv.lin_l.weight); add(conv.lin_l.bias); add(conv.lin_r.weight)
+        if bn is not None:
+            add(bn.weight); add(bn.bias)
+    for m in (model.decoder[0], model.decoder[2], model.decoder[4]):
+        add(m.weight); add(m.bias)
+    return ps
+
+
+def forward_train(model, x, edge_index, batch, seed: Optional[int] = None) -> torch.Tensor:
+    if seed is None:                                    # one draw from torch's generator per step, like nn.Dropout
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    params = trainable_parameters(model)
+    return SageTrainFunction.apply(model, x, edge_index, batch, seed, *params)

@@ -153,7 +153,10 @@ int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t n_nodes, int3
 typedef struct bg_gemm_segment {
   const void* a; int64_t lda;
   const void* b; int64_t ldb;
-  int32_t k; int32_t reserved;
+  int32_t k;
+  int32_t b_groups;            /* 0 / 1: B is [512, k].  g > 1 (split-K weight gradients): B is [g*512, k], A is   */
+                               /* [g*512, k] (m == g*512) and rows [i*512, +512) of A multiply rows [i*512, +512)  */
+                               /* of B -- g independent 512 x 512 products in one launch; same g in every segment. */
 } bg_gemm_segment;
 
 typedef struct bg_epilogue {
@@ -167,6 +170,8 @@ typedef struct bg_epilogue {
   const void* gather[2];       /* DEVICE [*,512] matrices of out_dtype (ld = gather_ld), NULL = absent */
   const int32_t* gather_idx[2];/* DEVICE [M] row index into gather[k]                      */
   int64_t gather_ld;
+  float* inv_norm_out;         /* DEVICE [M] f32 or NULL: with normalize, 1 / max(||v||_2, 1e-12) per row (the   */
+                               /* training forward saves it for the backward of F.normalize)                     */
 } bg_epilogue;
 
 int bg_gemm512(const bg_gemm_segment* segments_host, int32_t n_segments, int64_t m,
@@ -209,6 +214,66 @@ int bg_pool_head(const void* x, int dtype, int64_t n_nodes, const int32_t* graph
 int bg_expand_rowptr(const int32_t* rowptr, int64_t n_rows, int64_t n_entries, int32_t* row_of, int32_t* iota,
                      void* nonempty, int nonempty_dtype, int as_count, void* stream);
 int bg_add(const void* a, const void* b, const void* c_or_null, void* out, int dtype, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ training step
+ * What `loss.backward()` and train-mode BatchNorm1d / Dropout need around the forward kernels
+ * (TRAIN_FINAL.py:289-297 driving Models/BuckGNN.py:445-458 with model.train()).  Per GraphSAGE layer:
+ *   forward:  agg = bg_sage_aggregate(x);  u = bg_gemm512(normalize, inv_norm_out) -- no BN in the epilogue;
+ *             bg_bn_batch_stats(u) -> a, shift (+ running statistics);  y = bg_bn_act_forward(u, x_prev)
+ *   backward: bg_sage_backward_rows(u, dy) -> dz (+ dgamma, dbeta);  dagg = bg_gemm512(dz_scaled, Wl^T rows);
+ *             s = bg_sage_aggregate over the CSR keyed by SOURCE (A^T);  dx = bg_gemm512(dz, Wr^T rows) + s;
+ *             dWl = dz^T agg, dWr = dz^T x: bg_transpose_chunks + bg_gemm512(b_groups) + bg_reduce_partials.
+ * Every reduction is two-stage in a fixed order (no floating-point atomics).
+ *
+ * bg_bn_batch_stats: batch mean / biased variance of the N rows of u [N,512] (torch BatchNorm1d, train mode):
+ *   a = gamma / sqrt(var + eps), shift = beta - mean * a, mean, invstd = 1/sqrt(var + eps)   (f32 [512], device);
+ *   running_mean / running_var (nullable) updated with `momentum` (unbiased variance), *num_batches_tracked += 1.
+ * bg_bn_act_forward: y = dropout(relu(a * u + shift) + x_prev)   (Models/BuckGNN.py:451-458; x_prev nullable).
+ *   Dropout is counter-based: element (r, c) is kept iff hash(seed, r*512 + c) >= dropout_p * 2^32, kept values
+ *   are scaled by 1/(1-p); the backward pass regenerates the mask from the same seed.  Without BatchNorm
+ *   (GraphSage_addAggr_Shared) pass a = 1, shift = 0.
+ * bg_sage_backward_rows: g = dropout'(dy + dy2);  dv = g * [a*u + shift > 0];
+ *   dbeta (+)= sum_r dv;  dgamma (+)= sum_r dv * (u - mean) * invstd          (mean == NULL: no BatchNorm)
+ *   du = BatchNorm1d input gradient;  dz = inv_norm * (du - u * (u . du))       (F.normalize backward)
+ *   dz_scaled (nullable) = dz / max(deg, 1) with deg from rowptr (mean aggregation);  g_out (nullable) = g.
+ *   workspace from bg_train_workspace_bytes(N). */
+int bg_train_workspace_bytes(int64_t n_rows, size_t* bytes_host);
+int bg_bn_batch_stats(const void* u, int dtype, int64_t n_rows, const float* gamma, const float* beta, float eps,
+                      float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                      float* a_out, float* shift_out, float* mean_out, float* invstd_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int bg_bn_act_forward(const void* u, const void* x_prev, void* y, int dtype, int64_t n_rows, const float* a,
+                      const float* shift, float dropout_p, uint64_t seed, void* stream);
+int bg_sage_backward_rows(const void* u, const void* dy, const void* dy2, const float* inv_norm, const int32_t* rowptr,
+                          int dtype, int64_t n_rows, const float* a, const float* shift, const float* mean,
+                          const float* invstd, float dropout_p, uint64_t seed, float* dgamma, float* dbeta,
+                          int accumulate, void* dz, void* dz_scaled, void* g_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* Split-K operand layout for the weight gradients: out[s][c][j] = in[s*chunk_k + j][c] (0 beyond n_rows), i.e.
+ * n_chunks K-major [n_cols, chunk_k] matrices; n_cols and chunk_k multiples of 32, n_chunks*chunk_k >= n_rows.
+ * bg_reduce_partials: out[i] (+)= sum_s partial[s][i]. */
+int bg_transpose_chunks(const void* in, int dtype, int64_t n_rows, int32_t n_cols, int64_t ld, int32_t n_chunks,
+                        int64_t chunk_k, void* out, void* stream);
+int bg_reduce_partials(const float* partial, int32_t n_chunks, int64_t n, float* out, int accumulate, void* stream);
+/* out[c] (+)= sum_r in[r, c]  (bias gradients). */
+int bg_colsum_workspace_bytes(int64_t rows, int32_t cols, size_t* bytes_host);
+int bg_colsum(const void* in, int dtype, int64_t rows, int32_t cols, int64_t ld, float* out, int accumulate,
+              void* workspace, size_t workspace_bytes, void* stream);
+/* global_mean_pool backward (Models/BuckGNN.py:273-284): dx[r] = dpooled[graph(r)] * w(r); pool_mode in
+ * {BG_POOL_MEAN, BG_POOL_MEAN_NO_SUPER, BG_POOL_SUPERNODE_ONLY}; dpooled [G, >=512] f32 (ld = ldp). */
+int bg_pool_backward(const float* dpooled, int64_t ldp, const int32_t* graph_ptr, int64_t n_graphs, int pool_mode,
+                     int64_t n_nodes, void* dx, int dtype, void* stream);
+/* fp32 GEMM on the CUDA cores for the narrow layers (encoder 16->64->128, decoder 512->128->64->out and their
+ * gradients; ~2 % of a step's flops):  out[m,n] (+)= mask( relu( sum_k A(m,k) B(k,n) + bias[n] ) ),
+ * A(m,k) = a[m*sam + k*sak], B(k,n) = b[k*sbk + n*sbn] (any bg_dtype, element strides), mask (nullable):
+ * out = 0 where mask[m,n] <= 0 (ReLU backward).  Split-K, reduced in a fixed order. */
+int bg_sgemm_workspace_bytes(int64_t m, int64_t n, int64_t k, size_t* bytes_host);
+int bg_sgemm(const void* a, int a_dtype, int64_t sam, int64_t sak, const void* b, int b_dtype, int64_t sbk, int64_t sbn,
+             int64_t m, int64_t n, int64_t k, const float* bias, int relu, const void* mask, int mask_dtype,
+             int64_t mask_ld, void* out, int out_dtype, int64_t ldo, int accumulate,
+             void* workspace, size_t workspace_bytes, void* stream);
+/* keep[r*512 + c] = 1 if dropout keeps element (r, c) for (seed, dropout_p) -- lets a test apply the same mask. */
+int bg_dropout_mask(uint64_t seed, float dropout_p, int64_t n_rows, uint8_t* keep, void* stream);
 
 /* ------------------------------------------------------------------ helpers
  * fp32 -> bf16 / f16 (round to nearest even) cast of a contiguous buffer (weight packing). */

@@ -1,0 +1,337 @@
+"""Parity of the training step (BASELINE.json configs[3]) on the B200: each backward kernel against
+torch autograd of the same operator, and a whole `loss.backward()` of `BuckGNN` in train mode against
+autograd through the fp32 oracle (same weights, same batch, same dropout masks).
+
+Tolerances: a gradient tensor g passes when |g - g_ref|_2 / |g_ref|_2 is below 5e-3 (tf32 operands,
+fp32 storage) or 1e-1 (bf16 storage of activations and their gradients: 8-bit significands through
+2 x 4 layers), with the oracle using the ReLU masks of our forward (see _MaskedReLU)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from buckgnn_b200 import capi, engine, train
+from buckgnn_b200.engine import Activation, build_graph_index
+from buckgnn_b200.model import BuckGNN
+from buckgnn_b200.synth import make_batch
+from oracle.buckgnn_oracle import OracleBuckGNN, randomize_bn_stats
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GRAD_TOL = {"tf32": 5e-3, "bf16": 1e-1, "fp16": 2e-2}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rel(got, want):
+    return ((got.double() - want.double()).norm() / want.double().norm().clamp(min=1e-30)).item()
+
+
+def _act(t, precision):
+    a = Activation(t.shape[0], t.shape[1], precision, DEV)
+    a.data.copy_(t)
+    return a
+
+
+# ----------------------------------------------------------------------------- kernels
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_bn_batch_stats_and_running_update(precision):
+    torch.manual_seed(0)
+    n = 3001
+    dt = engine._TORCH[engine.PRECISION_FORMATS[precision][0]]
+    u = (torch.randn(n, 512) * 0.05 + 0.01).to(dt)
+    bn = torch.nn.BatchNorm1d(512)
+    randomize_bn_stats(bn, realistic=True)
+    ref = torch.nn.BatchNorm1d(512)
+    ref.load_state_dict(bn.state_dict())
+    want = ref.train()(u.float())
+    bn = bn.to(DEV)
+    ua = _act(u, precision)
+    vec = torch.empty(4, 512, device=DEV)
+    nb = capi.train_workspace_bytes(n)
+    ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    capi.bn_batch_stats(ua.data.data_ptr(), ua.code, n, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.eps, 0.1,
+                        bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(),
+                        vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(), ws.data_ptr(), nb, _stream())
+    got = u.float() * vec[0].cpu() + vec[1].cpu()
+    torch.testing.assert_close(got, want.detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(bn.running_mean.cpu(), ref.running_mean, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(bn.running_var.cpu(), ref.running_var, rtol=1e-5, atol=1e-9)
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == 1
+
+
+def test_dropout_mask_rate_and_forward_consistency():
+    n, p, seed = 2000, 0.1, 1234567891011
+    keep = torch.empty(n, 512, dtype=torch.uint8, device=DEV)
+    capi.dropout_mask(seed, p, n, keep.data_ptr(), _stream())
+    rate = 1.0 - keep.float().mean().item()
+    assert abs(rate - p) < 3e-3
+    keep2 = torch.empty_like(keep)
+    capi.dropout_mask(seed + 1, p, n, keep2.data_ptr(), _stream())
+    assert (keep != keep2).float().mean().item() > 0.1          # a different seed is a different mask
+    torch.manual_seed(1)
+    u, xp = torch.randn(n, 512), torch.randn(n, 512)
+    a, sh = torch.rand(512) + 0.5, torch.randn(512) * 0.1
+    ua, xa, ya = _act(u, "tf32"), _act(xp, "tf32"), Activation(n, 512, "tf32", DEV)
+    ad, sd = a.to(DEV), sh.to(DEV)
+    capi.bn_act_forward(ua.data.data_ptr(), xa.data.data_ptr(), ya.data.data_ptr(), ya.code, n, ad.data_ptr(),
+                        sd.data_ptr(), p, seed, _stream())
+    want = (torch.relu(u * a + sh) + xp) * keep.cpu().float() / (1 - p)
+    torch.testing.assert_close(ya.data.cpu(), want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("precision,with_bn,p", [("tf32", True, 0.0), ("tf32", True, 0.2), ("tf32", False, 0.0),
+                                                  ("bf16", True, 0.0)])
+def test_sage_backward_rows_matches_autograd(precision, with_bn, p):
+    """dz, dgamma, dbeta of  y = drop(relu(BN_train(z/|z|)) ) against torch autograd (fp64)."""
+    torch.manual_seed(2)
+    b = make_batch(2, nx=9, ny=7)
+    n = b.num_nodes
+    idx = build_graph_index(b.edge_index.to(DEV), None, n)
+    dt = engine._TORCH[engine.PRECISION_FORMATS[precision][0]]
+    code = engine.PRECISION_FORMATS[precision][0]
+    z = torch.randn(n, 512, dtype=torch.float64, requires_grad=True)
+    gamma = (torch.rand(512, dtype=torch.float64) + 0.5).requires_grad_()
+    beta = (torch.randn(512, dtype=torch.float64) * 0.1).requires_grad_()
+    seed = 99
+    keep = torch.empty(n, 512, dtype=torch.uint8, device=DEV)
+    capi.dropout_mask(seed, p, n, keep.data_ptr(), _stream())
+    keep = keep.cpu().double()
+    norm = z.norm(dim=1, keepdim=True)
+    u = z / norm
+    u_st = u.detach().to(dt)                      # what the forward stored
+    u_q = u + (u_st.double() - u).detach()        # straight-through: backward sees the stored values
+    if with_bn:
+        mean, var = u_q.mean(0), u_q.var(0, unbiased=False)
+        invstd = 1.0 / torch.sqrt(var + 1e-5)
+        v = (u_q - mean) * invstd * gamma + beta
+        a_vec, shift_vec = (gamma * invstd).detach(), (beta - mean * gamma * invstd).detach()
+    else:
+        v = u_q
+        a_vec, shift_vec = torch.ones(512, dtype=torch.float64), torch.zeros(512, dtype=torch.float64)
+    y = torch.relu(v) * keep / (1 - p)
+    dy = torch.randn(n, 512).to(dt)
+    y.backward(dy.double())
+    deg = (idx.rowptr[1:] - idx.rowptr[:-1]).cpu().clamp(min=1).double()
+    f32 = lambda t: t.detach().float().to(DEV).contiguous()
+    ua, dya = _act(u_st, precision), _act(dy, precision)
+    dz, dzs, g = (Activation(n, 512, precision, DEV) for _ in range(3))
+    dgam, dbet = torch.zeros(512, device=DEV), torch.zeros(512, device=DEV)
+    nb = capi.train_workspace_bytes(n)
+    ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    inv_norm = f32(1.0 / norm.flatten())
+    av, sv = f32(a_vec), f32(shift_vec)
+    mv, iv = (f32(mean), f32(invstd)) if with_bn else (None, None)
+    capi.sage_backward_rows(ua.data.data_ptr(), dya.data.data_ptr(), None, inv_norm.data_ptr(), idx.rowptr.data_ptr(), code, n,
+                            av.data_ptr(), sv.data_ptr(), engine._p(mv), engine._p(iv), p, seed,
+                            dgam.data_ptr() if with_bn else None, dbet.data_ptr() if with_bn else None, False,
+                            dz.data.data_ptr(), dzs.data.data_ptr(), g.data.data_ptr(), ws.data_ptr(), nb, _stream())
+    tol = 2e-2 if precision == "bf16" else 1e-4
+    assert _rel(dz.data.cpu(), z.grad) < tol
+    assert _rel(dzs.data.cpu(), z.grad / deg[:, None]) < tol
+    assert _rel(g.data.cpu(), dy.double() * keep / (1 - p)) < (1e-2 if precision == "bf16" else 1e-6)
+    if with_bn:
+        assert _rel(dgam.cpu(), gamma.grad) < tol and _rel(dbet.cpu(), beta.grad) < tol
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "fp16"])
+@pytest.mark.parametrize("n", [100, 5000, 70001])
+def test_weight_gradient_split_k(precision, n):
+    """dW[o, i] = sum_n dz[n, o] act[n, i] through transpose_chunks + bg_gemm512(b_groups) + reduce."""
+    torch.manual_seed(3)
+    dt = engine._TORCH[engine.PRECISION_FORMATS[precision][0]]
+    code = engine.PRECISION_FORMATS[precision][0]
+    dz = (torch.randn(n, 512) * 0.1).to(dt)
+    act = torch.randn(n, 512).to(dt)
+    want = dz.double().T @ act.double()
+    chunks, chunk_k = train.split_k_layout(n)
+    assert chunks * chunk_k >= n and chunk_k % 64 == 0
+    dzd, actd = dz.to(DEV), act.to(DEV)
+    out = torch.full((512, 512), 7.0, device=DEV)
+    dz_t = train.ChunkedTranspose(dzd, code, n, chunks, chunk_k)
+    act_t = train.ChunkedTranspose(actd, code, n, chunks, chunk_k)
+    # the layout itself is exact
+    ref_t = torch.zeros(chunks * chunk_k, 512, dtype=dt)
+    ref_t[:n] = dz
+    ref_t = ref_t.view(chunks, chunk_k, 512).permute(0, 2, 1).reshape(chunks * 512, chunk_k)
+    assert torch.equal(dz_t.data.cpu(), ref_t)
+    train.weight_grad_512(dz_t, act_t, precision, out, accumulate=False)
+    tol = {"tf32": 2e-3, "bf16": 1e-4, "fp16": 1e-4}[precision]      # 16-bit products are exact in fp32 accumulation
+    assert _rel(out.cpu(), want) < tol
+    train.weight_grad_512(dz_t, act_t, precision, out, accumulate=True)
+    assert _rel(out.cpu(), 2 * want) < tol
+
+
+def test_sgemm_colsum_pool_backward():
+    torch.manual_seed(4)
+    m, n, k = 333, 70, 1000
+    a, b = torch.randn(m, k), torch.randn(n, k)
+    bias, mask = torch.randn(n), torch.randn(m, n)
+    want = torch.relu(a @ b.T + bias) * (mask > 0)
+    ad, bd, biasd, maskd = a.to(DEV), b.to(DEV), bias.to(DEV), mask.to(DEV)
+    out = torch.empty(m, n, device=DEV)
+    train.sgemm(ad, capi.BG_F32, k, 1, bd, capi.BG_F32, 1, k, m, n, k, out, capi.BG_F32, n, bias=biasd, relu=True,
+                mask=maskd, mask_ld=n)
+    torch.testing.assert_close(out.cpu(), want, rtol=1e-4, atol=1e-4)
+    # transposed A (reduction over the leading dimension), bf16 operand, accumulate
+    at = torch.randn(k, m).to(torch.bfloat16)
+    out2 = torch.ones(m, n, device=DEV)
+    train.sgemm(at.to(DEV), capi.BG_BF16, 1, m, bd, capi.BG_F32, 1, k, m, n, k, out2, capi.BG_F32, n, accumulate=True)
+    torch.testing.assert_close(out2.cpu(), at.float().T @ b.T + 1, rtol=1e-4, atol=2e-3)
+    cs = torch.empty(n, device=DEV)
+    train.colsum(out, capi.BG_F32, m, n, n, cs)
+    torch.testing.assert_close(cs.cpu(), want.sum(0), rtol=1e-4, atol=1e-4)
+    # pool backward
+    bt = make_batch(5, nx=6, ny=5)
+    idx = build_graph_index(bt.edge_index.to(DEV), bt.batch.to(DEV), bt.num_nodes)
+    dp = torch.randn(5, 512)
+    x = torch.randn(bt.num_nodes, 512, requires_grad=True)
+    from oracle.buckgnn_oracle import global_mean_pool
+    (global_mean_pool(x, bt.batch) * dp).sum().backward()
+    dx = Activation(bt.num_nodes, 512, "tf32", DEV)
+    capi.pool_backward(dp.to(DEV).data_ptr(), 512, idx.graph_ptr.data_ptr(), 5, 0, bt.num_nodes, dx.data.data_ptr(), dx.code, _stream())
+    torch.testing.assert_close(dx.data.cpu(), x.grad, rtol=1e-6, atol=1e-8)
+
+
+def test_gemm_saves_inverse_norm():
+    torch.manual_seed(5)
+    m = 700
+    a, w = torch.randn(m, 512), torch.randn(512, 512) / 512 ** 0.5
+    act = _act(a, "tf32")
+    pack = engine.pack_linear(w.to(DEV), "tf32")
+    out = Activation(m, 512, "tf32", DEV)
+    inv = torch.empty(m, device=DEV)
+    engine.gemm512(engine._segments(act, pack), m, "tf32", out, normalize=True, inv_norm_out=inv.data_ptr())
+    z = a.double() @ w.double().T
+    torch.testing.assert_close(inv.cpu().double(), 1.0 / z.norm(dim=1), rtol=2e-3, atol=0)
+    torch.testing.assert_close(out.data.cpu().double(), F.normalize(z, dim=1), rtol=0, atol=2e-3)
+
+
+# ----------------------------------------------------------------------------- whole training step
+class _MaskedDropout(torch.nn.Module):
+    """Applies the masks our kernels used (bg_dropout_mask), in call order."""
+
+    def __init__(self, masks, p):
+        super().__init__()
+        self.masks, self.p, self.i = masks, p, 0
+
+    def forward(self, x):
+        m = self.masks[self.i]
+        self.i += 1
+        return x * m / (1 - self.p)
+
+
+class _MaskedReLU(torch.nn.Module):
+    """relu'(v) taken from OUR forward (call order = layer order).  A ReLU network's gradient is discontinuous in
+    its activations: the ~1e-3 relative difference between a tf32 forward and the fp32 oracle flips the sign of
+    ~1e-3 of the pre-activations, and each flip is a full-size error in that element's gradient (measured: 2-4 %
+    of the gradient norm with independent masks).  Sharing the masks removes that noise, so the comparison
+    checks the backward kernels and their wiring to rounding accuracy."""
+
+    def __init__(self, masks):
+        super().__init__()
+        self.masks, self.i = masks, 0
+
+    def forward(self, x):
+        m = self.masks[self.i]
+        self.i += 1
+        return x * m
+
+
+def _train_pair(model_name, precision, layers, p, pooling="mean"):
+    torch.manual_seed(0)
+    cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=layers,
+               pooling_layer=pooling, model_name=model_name, dropout_rate=p)
+    ref = OracleBuckGNN(**cfg)
+    randomize_bn_stats(ref, realistic=True)
+    ours = BuckGNN(**cfg, train_precision=precision)
+    ours.load_state_dict(ref.state_dict())
+    return ref.train(), ours.to(DEV).train()
+
+
+@pytest.mark.parametrize("model_name,precision,layers,p,pooling", [
+    ("GraphSage_meanAggr", "tf32", 6, 0.0, "mean"),
+    ("GraphSage_meanAggr", "tf32", 4, 0.1, "mean"),
+    ("GraphSage_meanAggr", "bf16", 4, 0.0, "mean"),
+    ("GraphSage_sumAggr", "tf32", 3, 0.0, "mean_no_super"),
+    ("GraphSage_addAggr_Shared", "tf32", 4, 0.0, "supernode_only"),
+])
+def test_training_step_gradients_match_oracle(model_name, precision, layers, p, pooling):
+    ref, ours = _train_pair(model_name, precision, layers, p, pooling)
+    b = make_batch(5, nx=14, ny=11)
+    n = b.num_nodes
+    seed = 424242
+    if p > 0:
+        masks = []
+        for i in range(layers):
+            keep = torch.empty(n, 512, dtype=torch.uint8, device=DEV)
+            capi.dropout_mask(train.layer_seed(seed, i), p, n, keep.data_ptr(), _stream())
+            masks.append(keep.cpu().float())
+        ref.dropout = _MaskedDropout(masks, p)
+    y = torch.randn(5)
+    with torch.no_grad():                                   # the oracle's own forward, own ReLU masks
+        import copy
+        want_free, _ = copy.deepcopy(ref)(b.x, b.edge_index, b.edge_attr, b.batch)
+    bd = b.to(DEV)
+    got_raw = train.forward_train(ours, bd.x, bd.edge_index, bd.batch, seed=seed)
+    got = got_raw.squeeze()
+    loss = F.mse_loss(got, y.to(DEV))
+    saved = got_raw.grad_fn.sv                              # u and the BatchNorm vectors of every layer
+    relu_masks = []
+    for (_, bn, _, _, u, _, vec, _) in saved.layers:
+        v = u.data.float() * (vec[0] if bn is not None else 1.0) + (vec[1] if bn is not None else 0.0)
+        relu_masks.append((v > 0).float().cpu())
+    loss.backward()
+    ref.relu = _MaskedReLU(relu_masks)
+    want, _ = ref(b.x, b.edge_index, b.edge_attr, b.batch)
+    F.mse_loss(want, y).backward()
+    fwd_tol = 2e-2 if precision == "bf16" else 2e-3
+    assert _rel(got.detach().cpu(), want_free) < fwd_tol
+    assert _rel(got.detach().cpu(), want.detach()) < fwd_tol
+    tol = GRAD_TOL[precision]
+    ref_p, our_p = dict(ref.named_parameters()), dict(ours.named_parameters())
+    checked, bad = 0, []
+    for name, rp in ref_p.items():
+        op = our_p[name]
+        if rp.grad is None:
+            assert op.grad is None, name                      # unused modules get no gradient on either side
+            continue
+        assert op.grad is not None, name
+        err = _rel(op.grad.cpu(), rp.grad)
+        scale_ok = rp.grad.norm().item() > 1e-12
+        if scale_ok and not err < tol:
+            bad.append(f"{name}: rel err {err:.3e} >= {tol}")
+        checked += 1
+    assert not bad, "\n".join(bad)
+    assert checked >= 10
+    # BatchNorm running statistics moved exactly as torch's do
+    for (k, rb), (_, ob) in zip(ref.named_buffers(), ours.named_buffers()):
+        if rb.dtype.is_floating_point:
+            assert _rel(ob.cpu(), rb) < (1e-2 if precision == "bf16" else 1e-3), k
+        else:
+            assert int(ob) == int(rb), k
+
+
+def test_training_step_is_deterministic_and_optimizer_runs():
+    _, ours = _train_pair("GraphSage_meanAggr", "tf32", 3, 0.1)
+    b = make_batch(4, nx=10, ny=9).to(DEV)
+    y = torch.randn(4, device=DEV)
+    grads = []
+    for _ in range(2):
+        ours.zero_grad(set_to_none=True)
+        pred = train.forward_train(ours, b.x, b.edge_index, b.batch, seed=7).squeeze()
+        F.mse_loss(pred, y).backward()
+        grads.append([p.grad.clone() for p in train.trainable_parameters(ours)])
+    assert all(torch.equal(a, c) for a, c in zip(*grads))
+    # the reference's loop: model(...) in train mode -> loss.backward() -> Adam step (TRAIN_FINAL.py:289-297)
+    opt = torch.optim.Adam(ours.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(5):
+        opt.zero_grad()
+        pred, bb = ours(b.x, b.edge_index, b.edge_attr, b.batch)
+        loss = F.mse_loss(pred, y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert bb is b.batch and losses[-1] < losses[0]
