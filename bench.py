@@ -39,6 +39,30 @@ def _peaks():
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def _traffic_from_profile(name_part: str, exclude: str = ""):
+    """Measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel whose name
+    contains `name_part`, averaged over the launches of the newest committed `ncu --set full` summary
+    (profiles/r*_ncu_full_summary.csv, written by tools/ncu_summary.py).  None if there is no capture."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.csv")), key=os.path.getmtime)
+    if not files:
+        return None
+    rows = list(csv.reader(open(files[-1])))
+    if len(rows) < 3:
+        return None
+    hdr, units = rows[0], rows[1]
+    try:
+        i_n, i_r, i_w = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    except ValueError:
+        return None
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    vals = [float(r[i_r]) * scale.get(units[i_r], 1.0) + float(r[i_w]) * scale.get(units[i_w], 1.0)
+            for r in rows[2:] if name_part in r[i_n] and not (exclude and exclude in r[i_n])]
+    return {"bytes_per_launch": sum(vals) / len(vals), "launches": len(vals),
+            "source": os.path.relpath(files[-1], ROOT)} if vals else None
+
+
 class ClockSampler:
     """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
@@ -242,14 +266,20 @@ def run_b200(args):
         if "aggregate" in kernel_ms:
             ms, calls = kernel_ms["aggregate"]
             a = agg_bytes / (ms / calls * 1e-3) / 1e9
+            tr = _traffic_from_profile("k_aggregate_rows<", exclude="rows128") if args.precision == "fp16" else None
             roofs["aggregate"] = {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                  "frac": a / peaks["hbm_gbs"], "traffic": None, "kernel": "k_aggregate_rows+hubs",
+                                  "frac": a / peaks["hbm_gbs"], "traffic": tr and tr["bytes_per_launch"],
+                                  "traffic_source": tr and tr["source"], "algorithmic_bytes": agg_bytes,
+                                  "kernel": "k_aggregate_rows (hub-streaming warps) + k_hub_finalize",
                                   "ms_per_launch": ms / calls, "share_of_step": ms / args.steps / step_ms}
         if "sage_update" in kernel_ms:
             ms, calls = kernel_ms["sage_update"]
             a = upd_flops / (ms / calls * 1e-3) / 1e12
+            tr = _traffic_from_profile("k_gemm512<2, __half, 1>") if args.precision == "fp16" else None
             roofs["sage_update"] = {"bound": "tensor", "achieved": a, "peak": tf_peak, "unit": "TFLOP/s",
-                                    "frac": a / tf_peak, "traffic": None, "kernel": "k_gemm512",
+                                    "frac": a / tf_peak, "traffic": tr and tr["bytes_per_launch"],
+                                    "traffic_source": tr and tr["source"], "algorithmic_flops": upd_flops,
+                                    "kernel": "k_gemm512",
                                     "ms_per_launch": ms / calls, "share_of_step": ms / args.steps / step_ms}
         dominant = max(roofs, key=lambda k: roofs[k]["share_of_step"]) if roofs else None
         cpu = None
