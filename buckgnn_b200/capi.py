@@ -28,7 +28,7 @@ AGGR_CODES = {"mean": BG_AGGR_MEAN, "sum": BG_AGGR_SUM, "add": BG_AGGR_SUM, "max
 EXPORTED_SYMBOLS = (
     "bg_abi_version", "bg_last_error", "bg_device_check", "bg_watchdog_info_host",
     "bg_csr_max_big_rows", "bg_csr_workspace_bytes", "bg_csr_build",
-    "bg_batch_info", "bg_graph_ptr_build", "bg_encoder_front",
+    "bg_batch_info", "bg_graph_ptr_build", "bg_publish_words", "bg_encoder_front",
     "bg_aggregate_workspace_bytes", "bg_hubfold_workspace_bytes", "bg_sage_aggregate", "bg_gemm512",
     "bg_pool_workspace_bytes", "bg_pool_head", "bg_cast_f32", "bg_split_tf32",
     "bg_expand_rowptr", "bg_add",
@@ -69,6 +69,7 @@ _SIGNATURES = {
     "bg_csr_workspace_bytes": (C.c_int, [_I64, _I64, _SZP]),
     "bg_csr_build": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "bg_batch_info": (C.c_int, [_P, _I64, _P, _P]),
+    "bg_publish_words": (C.c_int, [_P, _P, _I32, _P]),
     "bg_graph_ptr_build": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "bg_encoder_front": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "bg_expand_rowptr": (C.c_int, [_P, _I64, _I64, _P, _P, _P, C.c_int, C.c_int, _P]),
@@ -175,6 +176,10 @@ def csr_build(edge_index, n_edges, n_nodes, key_row, rowptr, col, perm, big_rows
 
 def batch_info(batch, n_nodes, info, stream):
     _check(load().bg_batch_info(batch, n_nodes, info, stream), "bg_batch_info")
+
+
+def publish_words(src, dst_host_mapped, n, stream):
+    _check(load().bg_publish_words(src, dst_host_mapped, n, stream), "bg_publish_words")
 
 
 def graph_ptr_build(batch, n_nodes, n_graphs, graph_ptr, stream):

@@ -96,6 +96,13 @@ __global__ void k_add(const T* __restrict__ a, const T* __restrict__ b, const T*
   }
 }
 
+// device words -> pinned (UVA-mapped) host memory, written by the SMs: a result read-back that needs no copy
+// engine (a cudaMemcpyAsync D2H can queue behind a large H2D transfer of the next batch)
+__global__ void k_publish_words(const int32_t* __restrict__ src, volatile int32_t* __restrict__ dst_host, int n) {
+  if ((int)threadIdx.x < n) dst_host[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+}
+
 static inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
   int64_t b = ceil_div64(n > 0 ? n : 1, threads);
@@ -291,6 +298,14 @@ int bg_graph_ptr_build(const int64_t* batch, int64_t N, int64_t G, int32_t* grap
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!graph_ptr || N < 0 || G < 0 || (N > 0 && !batch)) return fail(BG_ERR_INVALID, "bg_graph_ptr_build: bad argument");
   k_graph_ptr<<<grid_for(N + 1, 256, sm_count() * 8), 256, 0, stream>>>(batch, N, G, graph_ptr);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_publish_words(const int32_t* src, int32_t* dst_host_mapped, int32_t n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!src || !dst_host_mapped || n <= 0 || n > 256) return fail(BG_ERR_INVALID, "bg_publish_words: bad argument");
+  k_publish_words<<<1, 256, 0, stream>>>(src, dst_host_mapped, n);
   BG_LAUNCH_OK();
   return BG_OK;
 }

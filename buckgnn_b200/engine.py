@@ -99,12 +99,12 @@ TIMERS = _KernelTimers()
 
 def LAUNCHES_PER_FORWARD(num_layers: int, folded: bool = True) -> int:
     """Kernels of ours launched by one GraphSAGE forward: CSR build 7 (hist, 3 scan, fill,
-    2 sorts) + batch_info + graph_ptr + encoder front 1 (+ encoder GEMM when layer 0 is not folded;
+    2 sorts) + batch_info + publish_words + graph_ptr + encoder front 1 (+ encoder GEMM when layer 0 is not folded;
     + row indicator when it is) + per layer (aggregate rows + hubs + GEMM) + pool 2.
     (memsets and the 16-byte info read-back are not counted.)"""
     if folded:
-        return 7 + 2 + 1 + 1 + 3 * num_layers + 2
-    return 7 + 2 + 2 + 3 * num_layers + 2
+        return 7 + 3 + 1 + 1 + 3 * num_layers + 2
+    return 7 + 3 + 2 + 3 * num_layers + 2
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -136,14 +136,11 @@ class GraphIndex:
     hub_max_degree: int = 0
 
 
-_INFO_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
-
-
 class PendingGraphIndex:
     """K1 in flight.  `begin_graph_index` enqueues the CSR build (and the `batch` scan) on the
-    current stream and starts reading the 4 result words (error flag, hub-row count, graph count,
-    sortedness) back on a side stream; `finish()` blocks only on that read -- kernels the caller
-    enqueued in between (the node encoder) keep the GPU busy meanwhile.  This is the one
+    current stream and publishes the result words (error flag, hub-row count, graph count,
+    sortedness, hub ranges) to pinned host memory; `finish()` blocks only on the event behind that
+    -- kernels the caller enqueued in between (the node encoder) keep the GPU busy meanwhile.  This is the one
     host<->device sync of a forward, the same kind PyG's `batch.max()+1` does."""
 
     def __init__(self, edge_index, batch, n_nodes, key_row):
@@ -177,17 +174,12 @@ class PendingGraphIndex:
                 raise ValueError("batch must be an int64 tensor of shape [N]")
             self.batch = batch.contiguous()
             capi.batch_info(self.batch.data_ptr(), N, self.info[2:].data_ptr(), s)
-        ready = torch.cuda.Event()
-        ready.record()
-        side = _INFO_STREAMS.get(dev.index)
-        if side is None:
-            side = _INFO_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
-        self._host = torch.empty(8, dtype=torch.int32, pin_memory=True)
+        # result words -> pinned host memory by SM stores (bg_publish_words), then an event on THIS stream: no
+        # copy engine involved, so the read-back cannot queue behind the H2D transfer of the next batch
+        self._host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        capi.publish_words(self.info.data_ptr(), self._host.data_ptr(), 8, s)
         self._done = torch.cuda.Event()
-        with torch.cuda.stream(side):
-            side.wait_event(ready)
-            self._host.copy_(self.info, non_blocking=True)
-            self._done.record(side)
+        self._done.record()
 
     def finish(self) -> "GraphIndex":
         self._done.synchronize()                      # the one sync of the forward

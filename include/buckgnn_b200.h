@@ -94,6 +94,11 @@ int bg_csr_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, in
  * bg_graph_ptr_build: graph_ptr[g] = first node index with batch >= g, g in [0, G];
  *                 graph_ptr[G] = N.  Requires sorted batch (PyG DataLoader order). */
 int bg_batch_info(const int64_t* batch, int64_t n_nodes, int32_t* info, void* stream);
+/* Copies n <= 256 device words to PINNED host memory (UVA-mapped, e.g. torch pin_memory) with SM stores +
+ * a system fence: the host reads them after an event recorded behind this call.  Unlike a D2H memcpy it
+ * cannot queue on a copy engine behind the H2D transfer of the next batch (the forward's only host sync,
+ * PyG's `batch.max()+1` equivalent, stays off the PCIe copy queues). */
+int bg_publish_words(const int32_t* src, int32_t* dst_host_mapped, int32_t n, void* stream);
 int bg_graph_ptr_build(const int64_t* batch, int64_t n_nodes, int64_t n_graphs, int32_t* graph_ptr,
                        void* stream);
 
