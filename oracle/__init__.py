@@ -14,5 +14,6 @@ reference names them without versions; `lin_l`/`lin_r` naming implies PyG >= 1.6
 restates the published semantics of those operators at the reference's call sites
 (`Models/BuckGNN.py:114-176, 274, 449, 561`) and is cross-checked only against
 (i) hand-computed known-answer cases and (ii) an independent dense-adjacency
-formulation (`tests/test_oracle.py`).
+formulation (`tests/test_oracle.py`), and frozen by the golden fixtures of
+`tests/golden/` (generated from this oracle by `tests/golden/make_golden.py`).
 """

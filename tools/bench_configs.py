@@ -12,7 +12,6 @@ import torch
 from buckgnn_b200 import capi, engine
 from buckgnn_b200.model import BuckGNN
 from buckgnn_b200.synth import make_batch
-from oracle.buckgnn_oracle import OracleBuckGNN, randomize_bn_stats
 
 DEV = "cuda:0"
 
@@ -35,19 +34,21 @@ def timed(model, b, steps=5, warmup=2):
     return ms, k, pred
 
 
-def parity(cfg, precision, sample, **kw):
+def seeded_model(cfg, precision, **kw):
+    """Seeded weights with BatchNorm running statistics of a trained network's magnitude (parity of these
+    configurations against the oracle is tests/test_gpu_forward.py's job, not this tool's)."""
     torch.manual_seed(0)
-    ref = OracleBuckGNN(**cfg).eval()
-    randomize_bn_stats(ref, realistic=True)
-    ours = BuckGNN(**cfg, precision=precision, **kw)
-    ours.load_state_dict(ref.state_dict())
-    ours = ours.to(DEV).eval()
+    m = BuckGNN(**cfg, precision=precision, **kw)
+    g = torch.Generator().manual_seed(1)
     with torch.no_grad():
-        want, _ = ref(sample.x, sample.edge_index, sample.edge_attr, sample.batch)
-        s = sample.to(DEV)
-        got, _ = ours(s.x, s.edge_index, s.edge_attr, s.batch)
-    err = ((got.cpu() - want).abs() / want.abs().clamp(min=1e-3)).max().item()
-    return ours, err
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm1d):
+                c = mod.num_features
+                mod.running_mean.copy_(torch.randn(c, generator=g) * 0.3 / c ** 0.5)
+                mod.running_var.copy_((torch.rand(c, generator=g) + 0.5) / c)
+                mod.weight.copy_(torch.rand(c, generator=g) + 0.5)
+                mod.bias.copy_(torch.randn(c, generator=g) * 0.1)
+    return m.to(DEV).eval()
 
 
 def main():
@@ -56,7 +57,7 @@ def main():
     if "cfg3" in which:
         cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=6,
                    pooling_layer="mean", model_name="EA_GNN")
-        model, err = parity(cfg, "fp16", make_batch(2, nx=20, ny=16, stiffened=True))
+        model = seeded_model(cfg, "fp16")
         b = make_batch(128, stiffened=True).to(DEV)
         ms, k, _ = timed(model, b)
         n, e = b.num_nodes, b.num_edges
@@ -64,13 +65,13 @@ def main():
         print(json.dumps({"config": "cfg3: EA_GNN 6x512, batch 128 stiffened plates (CBAR sides+diagonals, 13.33% virtual "
                                     "edges, super node)", "graphs": 128, "nodes": n, "edges": e, "precision": "fp16",
                           "ms_per_forward": ms, "graphs_per_s": 128 / (ms * 1e-3), "gemm_tflops_as_executed": flops / ms / 1e9,
-                          "kernel_ms": k, "parity_rel_err_sample": err}), flush=True)
+                          "kernel_ms": k}), flush=True)
         del model, b
         torch.cuda.empty_cache()
     if "cfg5" in which:
         cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=6,
                    pooling_layer="mean", model_name="GraphSage_meanAggr")
-        model, err = parity(cfg, "fp16", make_batch(2, nx=20, ny=16, stiffened=True))
+        model = seeded_model(cfg, "fp16")
         for scale, graphs in ((1.0, 128), (2 ** 0.5, 64), (2.0, 32), (2 * 2 ** 0.5, 16)):
             b = make_batch(graphs, stiffened=True, scale=scale).to(DEV)
             ms, k, _ = timed(model, b)
@@ -78,8 +79,7 @@ def main():
                                         f"(node count x{scale * scale:.0f})", "graphs": graphs, "nodes": b.num_nodes,
                               "edges": b.num_edges, "max_hub_degree": int((b.ptr[1:] - b.ptr[:-1]).max()) - 1,
                               "ms_per_forward": ms, "graphs_per_s": graphs / (ms * 1e-3),
-                              "nodes_per_s": b.num_nodes / (ms * 1e-3), "kernel_ms": k,
-                              "parity_rel_err_sample": err}), flush=True)
+                              "nodes_per_s": b.num_nodes / (ms * 1e-3), "kernel_ms": k}), flush=True)
             del b
             torch.cuda.empty_cache()
 
