@@ -325,10 +325,19 @@ int bg_encoder_front(const float* x, int64_t N, int32_t F, const float* w1, cons
     if (!set) { BG_CUDA_OK(cudaFuncSetAttribute(k_encoder_front<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; } \
     k_encoder_front<T><<<grid, kEncThreads, smem, stream>>>(x, N, F, w1, b1, w2, b2, row_gather, static_cast<T*>(out)); \
   }
-  if (out_dtype == BG_BF16) BG_ENC_CASE(__nv_bfloat16)
-  else if (out_dtype == BG_F16) BG_ENC_CASE(__half)
+#define BG_ENC_MMA_CASE(T)                                                                                     \
+  {                                                                                                            \
+    const int msmem = (int)sizeof(EncoderMmaSmem);                                                             \
+    static bool set = false;                                                                                   \
+    if (!set) { BG_CUDA_OK(cudaFuncSetAttribute(k_encoder_front_mma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem)); set = true; } \
+    const unsigned mgrid = (unsigned)min64(ceil_div64(N, 16 * kEncMmaWarps), (int64_t)sm_count() * 2);        \
+    k_encoder_front_mma<T><<<mgrid, kEncMmaWarps * 32, msmem, stream>>>(x, N, F, w1, b1, w2, b2, row_gather, static_cast<T*>(out)); \
+  }
+  if (out_dtype == BG_BF16) BG_ENC_MMA_CASE(__nv_bfloat16)
+  else if (out_dtype == BG_F16) BG_ENC_MMA_CASE(__half)
   else if (out_dtype == BG_F32) BG_ENC_CASE(float)
   else return fail(BG_ERR_INVALID, "bg_encoder_front: bad out_dtype");
+#undef BG_ENC_MMA_CASE
 #undef BG_ENC_CASE
   BG_LAUNCH_OK();
   return BG_OK;

@@ -104,7 +104,7 @@ def test_graph_ptr_bit_exact_and_unsorted_batch_rejected():
 
 
 # ----------------------------------------------------------------------------- K5 front
-@pytest.mark.parametrize("n,f", [(1, 16), (63, 16), (1000, 16), (4097, 7)])
+@pytest.mark.parametrize("n,f", [(1, 16), (63, 16), (1000, 16), (4097, 7), (777, 5), (300, 20), (50, 32)])
 def test_encoder_front_matches_fp32(n, f):
     torch.manual_seed(0)
     x = torch.randn(n, f)
@@ -120,7 +120,9 @@ def test_encoder_front_matches_fp32(n, f):
         outb = torch.empty(n, 128, device=DEV, dtype=dt)
         capi.encoder_front(xd.data_ptr(), n, f, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
                            outb.data_ptr(), code, _stream())
-        torch.testing.assert_close(outb.cpu().float(), want, rtol=rtol, atol=1e-5)   # one 16-bit rounding
+        # 16-bit outputs come from the mma.sync kernel: x, W1, h1, W2 rounded to fp16 operands (fp32 accumulate)
+        torch.testing.assert_close(outb.cpu().float(), want, rtol=rtol, atol=2e-3)
+        assert ((outb.cpu().float() - want).norm() / want.norm()).item() < (4e-3 if dt == torch.bfloat16 else 1e-3)
 
 
 # ----------------------------------------------------------------------------- K2

@@ -1,0 +1,8 @@
+#!/bin/bash
+# Multi-GPU evidence on one box: gpurun --gpus N -- bash tools/gpu_multi.sh N
+N=${1:-2}
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+timeout 600 $TR tools/bench_train.py --steps 10 --warmup 3 > gpurun_out/train_${N}gpu.log 2>&1; echo "train exit $?"; grep '^{' gpurun_out/train_${N}gpu.log
+timeout 600 $TR tools/train_ddp_check.py > gpurun_out/ddp_check_${N}gpu.log 2>&1; echo "ddp check exit $?"; tail -3 gpurun_out/ddp_check_${N}gpu.log
+timeout 600 $TR bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/scale_${N}.log 2>&1; echo "bench exit $?"; grep '^{' gpurun_out/scale_${N}.log | cut -c1-400
