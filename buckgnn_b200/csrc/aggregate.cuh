@@ -151,7 +151,8 @@ template <int kAggr, bool kExactDiv> BG_DEVINL void agg_finalize(float (&acc)[16
 // 32 rows at a time.  Mesh neighbours of row i are i+-1 and i+-nx, so the band's reuse
 // window (~2*nx+32 rows of 1 KB) stays in the SM's L1: a source row is fetched from L2
 // once and hit ~3 more times, instead of every gather going to L2.
-// gather the rows whose indices sit in `my` (lane j holds neighbour j, cnt <= 32 of them), 4 rows in flight.
+// gather the rows whose indices sit in `my` (lane j holds neighbour j, cnt <= 32 of them), 4 rows in flight;
+// the last 1-3 rows are issued together as one more group (one exposed latency, not one per row).
 // (A generic kBatch-wide version with predicated loads into a fragment array was 2x slower: ptxas kept the
 // array in local memory -- tools/agg_bench.py, profiles/r01_agg_variants.txt.)
 template <typename T, int kAggr>
@@ -168,10 +169,25 @@ BG_DEVINL void gather_indexed(const T* __restrict__ x, int32_t my, int32_t cnt, 
     f2.template accumulate<kAggr>(acc);
     f3.template accumulate<kAggr>(acc);
   }
-  for (; j < cnt; ++j) {
-    RowFrag<T> f;
-    f.load(x + (size_t)__shfl_sync(0xffffffffu, my, j) * kHidden, lane);
-    f.template accumulate<kAggr>(acc);
+  const int32_t rem = cnt - j;
+  if (rem == 3) {
+    RowFrag<T> f0, f1, f2;
+    f0.load(x + (size_t)__shfl_sync(0xffffffffu, my, j) * kHidden, lane);
+    f1.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 1) * kHidden, lane);
+    f2.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 2) * kHidden, lane);
+    f0.template accumulate<kAggr>(acc);
+    f1.template accumulate<kAggr>(acc);
+    f2.template accumulate<kAggr>(acc);
+  } else if (rem == 2) {
+    RowFrag<T> f0, f1;
+    f0.load(x + (size_t)__shfl_sync(0xffffffffu, my, j) * kHidden, lane);
+    f1.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 1) * kHidden, lane);
+    f0.template accumulate<kAggr>(acc);
+    f1.template accumulate<kAggr>(acc);
+  } else if (rem == 1) {
+    RowFrag<T> f0;
+    f0.load(x + (size_t)__shfl_sync(0xffffffffu, my, j) * kHidden, lane);
+    f0.template accumulate<kAggr>(acc);
   }
 }
 
@@ -197,8 +213,25 @@ struct HubFold {
   int32_t parts;               // band slots per hub
 };
 #ifndef BG_AGG_STREAM_WARPS
-#define BG_AGG_STREAM_WARPS 4
+#define BG_AGG_STREAM_WARPS 2
 #endif
+#ifndef BG_AGG_STREAM_LEAD
+#define BG_AGG_STREAM_LEAD 96                // rows the hub stream may run ahead of the gather front
+#endif
+static_assert(BG_AGG_STREAM_LEAD >= 0, "a negative lead can starve the stream warps");
+constexpr int kStreamChunk = 8;              // rows per bulk copy
+constexpr int kStreamRing = 3;               // bulk copies in flight per stream warp
+constexpr int kStreamLead = BG_AGG_STREAM_LEAD;
+template <typename T> constexpr int agg_fold_smem() {
+  return 1024 + BG_AGG_STREAM_WARPS * kStreamRing * kStreamChunk * kHidden * (int)sizeof(T);
+}
+#ifndef BG_AGG_PF
+#define BG_AGG_PF 0                          // 0: no prefetch (default), 1: prefetch.global.L2, 2: prefetch.global.L1 -- both slower
+#endif
+template <int kLevel> BG_DEVINL void prefetch_line(const void* p) {
+  if constexpr (kLevel == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  else asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 template <typename T, int kAggr, bool kFold, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -209,9 +242,26 @@ k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N, int64_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t r_beg = (int64_t)blockIdx.x * band;
   const int64_t r_end = min(N, r_beg + band);
+  extern __shared__ __align__(128) unsigned char agg_smem[];
+  volatile int32_t* progress = reinterpret_cast<volatile int32_t*>(agg_smem);        // gather front (row offset in band)
   if constexpr (kFold) {
+    constexpr uint32_t kRowBytes = kHidden * (uint32_t)sizeof(T);
+    constexpr uint32_t kBufBytes = kStreamChunk * kRowBytes;
+    const uint32_t bars = smem_u32(agg_smem) + 64;                                   // [kStream][kStreamRing] mbarriers
+    unsigned char* bufs = agg_smem + 1024;                                           // [kStream][kStreamRing][kBufBytes]
+    if (threadIdx.x == 0) {
+      *progress = 0;
+      for (int i = 0; i < kStream * kStreamRing; ++i) mbar_init(bars + 8u * i, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
     if (warp >= kWarps) {
       // ---------------------------------------------------------------- hub streaming warps
+      // Chunks of kStreamChunk consecutive rows arrive by 1-D bulk copies (TMA) into a small ring: no registers
+      // are tied up by loads in flight.  The stream is throttled to kStreamLead rows ahead of the gather front
+      // (warp 0's row, published in shared memory): ~one mesh row ahead it is the stream that takes the HBM
+      // misses of the rows entering the gather window, and the gathers find them in L2; further ahead the lines
+      // are evicted again before they are used (measured: lead 96 -> 0.42 ms, 384 -> 0.52 ms, profiles/r01_agg_variants.txt).
       const int sw = warp - kWarps;
       float acc[16];
 #pragma unroll
@@ -227,44 +277,108 @@ k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N, int64_
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.f;
       };
-      auto take = [&](int32_t h, const RowFrag<T>& f) {
-        if (h != cur_h) { flush(); cur_h = h; }
-        if (h >= 0) f.template accumulate<BG_AGGR_SUM>(acc);
+      const int64_t n_rows = r_end - r_beg;
+      const int64_t n_chunks = (n_rows + kStreamChunk - 1) / kStreamChunk;
+      const uint32_t my_bars = bars + 8u * (uint32_t)(sw * kStreamRing);
+      unsigned char* my_bufs = bufs + (size_t)sw * kStreamRing * kBufBytes;
+      auto issue = [&](int64_t c, int slot) {                  // lane 0: chunk c -> ring slot
+        const int64_t row0 = r_beg + c * kStreamChunk;
+        const uint32_t bytes = (uint32_t)min((int64_t)kStreamChunk, r_end - row0) * kRowBytes;
+        while ((c * kStreamChunk) > (int64_t)*progress + kStreamLead) __nanosleep(256);
+        mbar_arrive_expect_tx(my_bars + 8u * slot, bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(my_bufs + (size_t)slot * kBufBytes)), "l"(x + (size_t)row0 * kHidden), "r"(bytes),
+                       "r"(my_bars + 8u * slot) : "memory");
       };
-      int64_t r = r_beg + sw;
-      for (; r + 3 * kStream < r_end; r += 4 * kStream) {
-        const int32_t h0 = hf.hub_of_row[r], h1 = hf.hub_of_row[r + kStream];
-        const int32_t h2 = hf.hub_of_row[r + 2 * kStream], h3 = hf.hub_of_row[r + 3 * kStream];
-        RowFrag<T> f0, f1, f2, f3;
-        f0.load(x + (size_t)r * kHidden, lane);
-        f1.load(x + (size_t)(r + kStream) * kHidden, lane);
-        f2.load(x + (size_t)(r + 2 * kStream) * kHidden, lane);
-        f3.load(x + (size_t)(r + 3 * kStream) * kHidden, lane);
-        take(h0, f0); take(h1, f1); take(h2, f2); take(h3, f3);
-      }
-      for (; r < r_end; r += kStream) {
-        const int32_t h0 = hf.hub_of_row[r];
-        RowFrag<T> f0;
-        f0.load(x + (size_t)r * kHidden, lane);
-        take(h0, f0);
+      if (lane == 0)
+        for (int k = 0; k < kStreamRing; ++k)
+          if (sw + (int64_t)k * kStream < n_chunks) issue(sw + (int64_t)k * kStream, k);
+      // hub ids of this warp's chunks, fetched two chunks ahead (each is a fresh 32-byte sector from HBM)
+      auto hub_ids = [&](int64_t c) -> int32_t {
+        const int64_t row = r_beg + c * kStreamChunk + lane;
+        return (c < n_chunks && lane < kStreamChunk && row < r_end) ? hf.hub_of_row[row] : -1;
+      };
+      int32_t h_cur = hub_ids(sw), h_nxt = hub_ids(sw + kStream);
+      int64_t it = 0;
+      for (int64_t c = sw; c < n_chunks; c += kStream, ++it) {
+        const int slot = (int)(it % kStreamRing);
+        const int64_t row0 = r_beg + c * kStreamChunk;
+        const int rows = (int)min((int64_t)kStreamChunk, r_end - row0);
+        const int32_t h_nxt2 = hub_ids(c + 2 * (int64_t)kStream);
+        const int32_t hmine = h_cur;
+        h_cur = h_nxt; h_nxt = h_nxt2;
+        mbar_wait(my_bars + 8u * slot, (uint32_t)(it / kStreamRing) & 1u, 77u);
+        const uint4* buf = reinterpret_cast<const uint4*>(my_bufs + (size_t)slot * kBufBytes);
+        constexpr int kQ = (int)(sizeof(RowFrag<T>) / sizeof(uint4));            // 16-byte pieces per lane per row
+        const bool uniform = rows == kStreamChunk && __all_sync(0xffffffffu, lane >= kStreamChunk || hmine == cur_h) && cur_h >= 0;
+        if (uniform) {                                  // whole chunk inside the current hub's range: 4 rows at a time
+#pragma unroll
+          for (int k0 = 0; k0 < kStreamChunk; k0 += 4) {
+            RowFrag<T> f[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+              for (int j = 0; j < kQ; ++j) f[k].q[j] = buf[(size_t)(k0 + k) * (kRowBytes / 16) + 32 * j + lane];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) f[k].template accumulate<BG_AGGR_SUM>(acc);
+          }
+        } else {
+          for (int k = 0; k < rows; ++k) {
+            const int32_t h = __shfl_sync(0xffffffffu, hmine, k);
+            if (h != cur_h) { flush(); cur_h = h; }
+            if (h >= 0) {
+              RowFrag<T> f;
+              const uint4* rp = buf + (size_t)k * (kRowBytes / 16);
+#pragma unroll
+              for (int j = 0; j < kQ; ++j) f.q[j] = rp[32 * j + lane];
+              f.template accumulate<BG_AGGR_SUM>(acc);
+            }
+          }
+        }
+        __syncwarp();
+        const int64_t nc = c + (int64_t)kStreamRing * kStream;
+        if (lane == 0 && nc < n_chunks) issue(nc, slot);
       }
       flush();
       return;
     }
   }
+  // Software pipeline over the warp's rows (stride kWarps), three deep: the row being gathered has its
+  // neighbour indices in `my`; the next row's indices (`nmy`) arrived an iteration ago and are used NOW to
+  // prefetch its neighbour rows into L2/L1 (one prefetch instruction covers 4 rows: lane l -> line l%8 of
+  // neighbour l/8), so the row's own gathers find them on chip; the row after that has its offsets, and its
+  // indices are requested now.  A gather is stalled on HBM latency ~60 % of the time without this
+  // (ncu long_scoreboard, profiles/r01_v6_*): only the ~1 of 5 loads that misses L1 goes to HBM, so the loads
+  // in flight cover too few HBM bytes.
   int64_t r = r_beg + warp;
-  int32_t beg = 0, end = 0, my = 0, nbeg = 0, nend = 0;
+  int32_t beg = 0, end = 0, my = 0, nbeg = 0, nend = 0, nmy = 0, n2beg = 0, n2end = 0;
   if (r < r_end) {
     beg = rowptr[r]; end = rowptr[r + 1];
     my = (lane < end - beg) ? col[beg + lane] : 0;
   }
-  if (r + kWarps < r_end) { nbeg = rowptr[r + kWarps]; nend = rowptr[r + kWarps + 1]; }
+  if (r + kWarps < r_end) {
+    nbeg = rowptr[r + kWarps]; nend = rowptr[r + kWarps + 1];
+    nmy = (lane < nend - nbeg) ? col[nbeg + lane] : 0;
+  }
+  if (r + 2 * kWarps < r_end) { n2beg = rowptr[r + 2 * kWarps]; n2end = rowptr[r + 2 * kWarps + 1]; }
   for (; r < r_end; r += kWarps) {
-    // stage 2 of the pipeline: indices of the next row (its offsets arrived an iteration ago)
-    const int32_t nmy = (lane < nend - nbeg) ? col[nbeg + lane] : 0;
-    // stage 1: offsets of the row after next
-    int32_t n2beg = 0, n2end = 0;
-    if (r + 2 * kWarps < r_end) { n2beg = rowptr[r + 2 * kWarps]; n2end = rowptr[r + 2 * kWarps + 1]; }
+    if constexpr (kFold) {
+      if (warp == 0 && lane == 0) *progress = (int32_t)(r - r_beg);
+    }
+#if BG_AGG_PF
+    {
+      const int32_t ndeg = min(nend - nbeg, 8);
+      const int32_t nb0 = __shfl_sync(0xffffffffu, nmy, lane >> 3);
+      const int32_t nb1 = __shfl_sync(0xffffffffu, nmy, 4 + (lane >> 3));
+      if ((lane >> 3) < ndeg) prefetch_line<BG_AGG_PF>(reinterpret_cast<const char*>(x + (size_t)nb0 * kHidden) + (lane & 7) * (kHidden * (int)sizeof(T) / 8));
+      if (4 + (lane >> 3) < ndeg) prefetch_line<BG_AGG_PF>(reinterpret_cast<const char*>(x + (size_t)nb1 * kHidden) + (lane & 7) * (kHidden * (int)sizeof(T) / 8));
+    }
+#endif
+    // stage 2: indices of the row after next (its offsets arrived an iteration ago)
+    const int32_t n2my = (lane < n2end - n2beg) ? col[n2beg + lane] : 0;
+    // stage 1: offsets of the row after that
+    int32_t n3beg = 0, n3end = 0;
+    if (r + 3 * kWarps < r_end) { n3beg = rowptr[r + 3 * kWarps]; n3end = rowptr[r + 3 * kWarps + 1]; }
     const int32_t deg = end - beg;
     if (deg <= kBigRowThreshold) {                          // hub rows: k_aggregate_hubs / k_hub_finalize
       float acc[16];
@@ -275,7 +389,10 @@ k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N, int64_
       agg_finalize<kAggr, sizeof(T) == 4>(acc, deg);
       RowFrag<T>::store(out + (size_t)r * kHidden, lane, acc);
     }
-    beg = nbeg; end = nend; my = nmy; nbeg = n2beg; nend = n2end;
+    beg = nbeg; end = nend; my = nmy; nbeg = n2beg; nend = n2end; nmy = n2my; n2beg = n3beg; n2end = n3end;
+  }
+  if constexpr (kFold) {
+    if (warp == 0 && lane == 0) *progress = 0x7fffffff - 2 * kStreamLead;     // band done: release the stream warps
   }
 }
 
@@ -297,11 +414,13 @@ k_hub_finalize(T* __restrict__ out, int64_t N, int64_t band, const int32_t* __re
   for (int64_t c = c0; c <= c1; ++c) {
     const int64_t a = max(lo, c * band), e = min(min(hi, (c + 1) * band), N);
     const float4* src = reinterpret_cast<const float4*>(hf.partial) + (((int64_t)b * hf.parts + (c - c0)) * kStream) * 128 + j * 32 + lane;
+    // stream warp w of band c owns the 8-row chunks q with q % kStream == w; it wrote a partial for this hub iff
+    // one of its chunks intersects [a, e)
+    const int64_t qa = (a - c * band) / kStreamChunk, qe = (e - 1 - c * band) / kStreamChunk;
 #pragma unroll
     for (int w = 0; w < kStream; ++w) {
-      // first row >= a that stream warp w of band c walks: rows c*band + w + kStream*k
-      const int64_t first = a + (((c * band + w - a) % kStream) + kStream) % kStream;
-      if (first < e) {
+      const int64_t q0 = qa + (((w - qa) % kStream) + kStream) % kStream;
+      if (q0 <= qe) {
         const float4 v = __ldcg(src + (int64_t)w * 128);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }

@@ -145,9 +145,11 @@ static int aggregate_dispatch(const T* x, T* out, int64_t N, const int32_t* rowp
   if (hr.hub_lo && n_big > 0) {                    // range hubs folded into the row pass
     constexpr int kThreads = agg_fold_threads<T>();
     HubFold hf{hr.hub_of_row, hr.hub_lo, hr.partial, (int32_t)hub_parts(band, hr.max_degree)};
-    constexpr int smem = 0;
+    constexpr int smem = agg_fold_smem<T>();
 #define BG_AGGF_CASE(A)                                                                                              \
   case A: {                                                                                                          \
+    static bool set = false;                                                                                         \
+    if (!set) { BG_CUDA_OK(cudaFuncSetAttribute(k_aggregate_rows<T, A, true, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; } \
     k_aggregate_rows<T, A, true, kThreads><<<grid, kThreads, smem, stream>>>(x, out, N, band, rowptr, col, hf);      \
     k_hub_finalize<T, A><<<(unsigned)n_big, 128, 0, stream>>>(out, N, band, rowptr, big_rows, hf);                   \
   } break;

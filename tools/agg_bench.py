@@ -7,14 +7,16 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 VARIANTS = {
-    "t768_s4": ["BG_AGG_THREADS16=768", "BG_AGG_STREAM_WARPS=4"],
-    "t768_s3": ["BG_AGG_THREADS16=768", "BG_AGG_STREAM_WARPS=3"],
-    "t768_s5": ["BG_AGG_THREADS16=768", "BG_AGG_STREAM_WARPS=5"],
-    "t640_s4": ["BG_AGG_THREADS16=640", "BG_AGG_STREAM_WARPS=4"],
-    "t640_s3": ["BG_AGG_THREADS16=640", "BG_AGG_STREAM_WARPS=3"],
-    "t896_s4": ["BG_AGG_THREADS16=896", "BG_AGG_STREAM_WARPS=4"],
-    "t896_s5": ["BG_AGG_THREADS16=896", "BG_AGG_STREAM_WARPS=5"],
-    "t512_s3": ["BG_AGG_THREADS16=512", "BG_AGG_STREAM_WARPS=3"],
+    "s2_l0": ["BG_AGG_STREAM_WARPS=2", "BG_AGG_STREAM_LEAD=0"],
+    "s2_l16": ["BG_AGG_STREAM_WARPS=2", "BG_AGG_STREAM_LEAD=16"],
+    "s2_l32": ["BG_AGG_STREAM_WARPS=2", "BG_AGG_STREAM_LEAD=32"],
+    "s2_l48": ["BG_AGG_STREAM_WARPS=2", "BG_AGG_STREAM_LEAD=48"],
+    "s2_l64": ["BG_AGG_STREAM_WARPS=2", "BG_AGG_STREAM_LEAD=64"],
+    "s2_l96": ["BG_AGG_STREAM_WARPS=2", "BG_AGG_STREAM_LEAD=96"],
+    "s1_l32": ["BG_AGG_STREAM_WARPS=1", "BG_AGG_STREAM_LEAD=32"],
+    "s1_l64": ["BG_AGG_STREAM_WARPS=1", "BG_AGG_STREAM_LEAD=64"],
+    "s3_l64": ["BG_AGG_STREAM_WARPS=3", "BG_AGG_STREAM_LEAD=64"],
+    "s2_lm64": ["BG_AGG_STREAM_WARPS=2", "BG_AGG_STREAM_LEAD=-64"],
 }
 
 
