@@ -558,6 +558,38 @@ BG_DEVINL void narrow_gather(const T* __restrict__ x, const int32_t* __restrict_
   }
 }
 
+// neighbours my[0..cnt) (one per sub-warp lane, cnt <= kLanes), 4 rows in flight, tail issued as one group
+template <typename T, int kAggr>
+BG_DEVINL void narrow_gather_indexed(const T* __restrict__ x, int32_t my, int32_t cnt, int sl, uint32_t mask,
+                                     float (&acc)[Narrow<T>::kVals]) {
+  constexpr int kLanes = Narrow<T>::kLanes;
+  const char* xb = reinterpret_cast<const char*>(x) + (size_t)sl * 16;
+  constexpr size_t kRowBytes = 128 * sizeof(T);
+  int32_t j = 0;
+  for (; j + 4 <= cnt; j += 4) {
+    const uint4 q0 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j, kLanes) * kRowBytes);
+    const uint4 q1 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 1, kLanes) * kRowBytes);
+    const uint4 q2 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 2, kLanes) * kRowBytes);
+    const uint4 q3 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 3, kLanes) * kRowBytes);
+    narrow_accumulate<T, kAggr>(acc, q0); narrow_accumulate<T, kAggr>(acc, q1);
+    narrow_accumulate<T, kAggr>(acc, q2); narrow_accumulate<T, kAggr>(acc, q3);
+  }
+  const int32_t rem = cnt - j;
+  if (rem == 3) {
+    const uint4 q0 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j, kLanes) * kRowBytes);
+    const uint4 q1 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 1, kLanes) * kRowBytes);
+    const uint4 q2 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 2, kLanes) * kRowBytes);
+    narrow_accumulate<T, kAggr>(acc, q0); narrow_accumulate<T, kAggr>(acc, q1); narrow_accumulate<T, kAggr>(acc, q2);
+  } else if (rem == 2) {
+    const uint4 q0 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j, kLanes) * kRowBytes);
+    const uint4 q1 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 1, kLanes) * kRowBytes);
+    narrow_accumulate<T, kAggr>(acc, q0); narrow_accumulate<T, kAggr>(acc, q1);
+  } else if (rem == 1) {
+    narrow_accumulate<T, kAggr>(acc, ldg_v4(xb + (size_t)__shfl_sync(mask, my, j, kLanes) * kRowBytes));
+  }
+}
+
+// Same band walk and two-deep index pipeline as k_aggregate_rows, one SUB-warp (16 or 32 lanes) per row.
 template <typename T, int kAggr>
 __global__ void __launch_bounds__(1024, 1)
 k_aggregate_rows128(const T* __restrict__ x, T* __restrict__ out, int64_t N,
@@ -569,26 +601,39 @@ k_aggregate_rows128(const T* __restrict__ x, T* __restrict__ out, int64_t N,
   const int64_t band = (N + gridDim.x - 1) / gridDim.x;
   const int64_t r_beg = (int64_t)blockIdx.x * band;
   const int64_t r_end = min(N, r_beg + band);
-  constexpr int kRowsPerIter = 32 * NW::kRowsPerWarp;          // 32 warps per CTA
-  for (int64_t r = r_beg + warp * NW::kRowsPerWarp + sub; r < r_end; r += kRowsPerIter) {
-    const int32_t beg = rowptr[r], end = rowptr[r + 1];
-    if (end - beg > kBigRowThreshold) continue;
-    float acc[NW::kVals];
-#pragma unroll
-    for (int i = 0; i < NW::kVals; ++i) acc[i] = agg_init<kAggr>();
-    narrow_gather<T, kAggr>(x, col, beg, end, sl, mask, acc);
+  constexpr int kStride = 32 * NW::kRowsPerWarp;               // rows per CTA iteration (32 warps)
+  int64_t r = r_beg + warp * NW::kRowsPerWarp + sub;
+  int32_t beg = 0, end = 0, my = 0, nbeg = 0, nend = 0;
+  if (r < r_end) {
+    beg = rowptr[r]; end = rowptr[r + 1];
+    my = (sl < end - beg) ? col[beg + sl] : 0;
+  }
+  if (r + kStride < r_end) { nbeg = rowptr[r + kStride]; nend = rowptr[r + kStride + 1]; }
+  // the two sub-warps of a warp may run out of rows at different iterations: shuffles use per-sub-warp masks
+  for (; r < r_end; r += kStride) {
+    const int32_t nmy = (sl < nend - nbeg) ? col[nbeg + sl] : 0;
+    int32_t n2beg = 0, n2end = 0;
+    if (r + 2 * kStride < r_end) { n2beg = rowptr[r + 2 * kStride]; n2end = rowptr[r + 2 * kStride + 1]; }
     const int32_t deg = end - beg;
-    if constexpr (kAggr == BG_AGGR_MEAN) {
-      const float d = (float)max(deg, 1);
+    if (deg <= kBigRowThreshold) {
+      float acc[NW::kVals];
 #pragma unroll
-      for (int i = 0; i < NW::kVals; ++i) acc[i] = acc[i] / d;
-    } else if constexpr (kAggr == BG_AGGR_MAX) {
-      if (deg == 0) {
+      for (int i = 0; i < NW::kVals; ++i) acc[i] = agg_init<kAggr>();
+      narrow_gather_indexed<T, kAggr>(x, my, min(deg, NW::kLanes), sl, mask, acc);
+      if (deg > NW::kLanes) narrow_gather<T, kAggr>(x, col, beg + NW::kLanes, end, sl, mask, acc);
+      if constexpr (kAggr == BG_AGGR_MEAN) {
+        const float d = (float)max(deg, 1);
 #pragma unroll
-        for (int i = 0; i < NW::kVals; ++i) acc[i] = 0.f;
+        for (int i = 0; i < NW::kVals; ++i) acc[i] = acc[i] / d;
+      } else if constexpr (kAggr == BG_AGGR_MAX) {
+        if (deg == 0) {
+#pragma unroll
+          for (int i = 0; i < NW::kVals; ++i) acc[i] = 0.f;
+        }
       }
+      stg_v4(reinterpret_cast<char*>(out) + (size_t)r * 128 * sizeof(T) + (size_t)sl * 16, narrow_pack<T>(acc));
     }
-    stg_v4(reinterpret_cast<char*>(out) + (size_t)r * 128 * sizeof(T) + (size_t)sl * 16, narrow_pack<T>(acc));
+    beg = nbeg; end = nend; my = nmy; nbeg = n2beg; nend = n2end;
   }
 }
 
