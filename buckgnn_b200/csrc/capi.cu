@@ -469,6 +469,12 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
     if (epi->inv_norm_out && !epi->normalize) return fail(BG_ERR_INVALID, "bg_gemm512: inv_norm_out needs normalize");
     p.inv_norm_out = epi->inv_norm_out;
   }
+  for (int i = 0; i < kHidden / 2; ++i) {
+    const __half2 sc = __floats2half2_rn(p.scale[2 * i], p.scale[2 * i + 1]);
+    const __half2 sh = __floats2half2_rn(p.shift[2 * i], p.shift[2 * i + 1]);
+    memcpy(&p.scale_h2[i], &sc, 4);
+    memcpy(&p.shift_h2[i], &sh, 4);
+  }
   p.out = out; p.ldo = ldo;
 #define BG_GEMM_OUT(ADD)                                                                 \
   (out_dtype == BG_BF16 ? launch_gemm512<2, __nv_bfloat16, ADD>(p, stream)               \

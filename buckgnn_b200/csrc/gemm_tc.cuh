@@ -86,6 +86,8 @@ struct alignas(64) GemmParams {
   float bias[kHidden];              // epilogue vectors by value -> constant bank, broadcast reads
   float scale[kHidden];             // 1 when there is no BN
   float shift[kHidden];             // 0 when there is no BN
+  uint32_t scale_h2[kHidden / 2];   // the same two vectors as packed fp16 pairs (fp16 outputs: pass 2 runs on
+  uint32_t shift_h2[kHidden / 2];   // HMUL2 / HFMA2 / HMNMX2 / HADD2, two columns per instruction)
 };
 
 // Optional role-level cycle accounting (build with -DBG_PROFILE, see tools/gemm_bench.py):
@@ -120,6 +122,9 @@ BG_DEVINL void sts_v4(uint32_t addr, uint4 v) {
 template <int kRegs> BG_DEVINL void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs> BG_DEVINL void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
+template <typename T> struct is_bf16 { static constexpr bool value = false; };
+template <> struct is_bf16<__nv_bfloat16> { static constexpr bool value = true; };
+
 struct EpiCtx {
   uint32_t tmem_base, stage_u32;    // stage_u32: this warp's 4 KB staging tile
   float* my_tile;                   // generic pointers to this warp's tile and to the tile of the warp that owns
@@ -150,6 +155,15 @@ enum : int { kAddNone = 0, kAddResidual = 1, kAddGather = 2 };
 template <int kCg, typename TOut, int kAdd>
 BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g) {
   constexpr bool kOut16 = sizeof(TOut) == 2;
+  // -DBG_GEMM_PACKED_EPILOGUE: pass 2 of fp16 outputs as packed half2 math.  Measured (r01): SAGE update
+  // 1.04 -> 1.00 ms, EA-GNN cfg 3 107.7 -> 98.4 ms, but the prediction error vs the fp32 oracle rises from
+  // 6e-5 to 2.8e-4 (u = v * inv and the BN scale are rounded to 11 bits before the affine step).  Off by
+  // default: 4 % is not worth a 5x smaller accuracy margin.
+#ifdef BG_GEMM_PACKED_EPILOGUE
+  constexpr bool kPacked = sizeof(TOut) == 2 && !is_bf16<TOut>::value;
+#else
+  constexpr bool kPacked = false;
+#endif
   constexpr int kChunkCols = 128 / (int)sizeof(TOut);           // columns per 128-byte row chunk: 64 / 32
   constexpr int kChunks = 256 / kChunkCols;                     // 4 / 8
   constexpr int kPer = 16 / (int)sizeof(TOut);                  // 8 or 4 columns per 16-byte piece
@@ -251,6 +265,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
       named_bar_sync(1, 256);                                   // partner has read before pass 2 reuses the tile
       if (p.inv_norm_out != nullptr && g == 0 && m_row < p.m) p.inv_norm_out[m_row] = inv;
     }
+    [[maybe_unused]] const __half2 inv2 = __float2half2_rn(inv);
     BG_PROF_ADD(_pacc_b);
     BG_PROF_T0();
 
@@ -293,6 +308,36 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
           else mbar_arrive_cluster(cx.tmem_empty_bar, 0);
         }
       }
+      if constexpr (kPacked) {
+        // fp16 output: the stash already holds the row as fp16 pairs, so normalize / BN / ReLU / addends run as
+        // packed half2 math -- 4 instructions per TWO columns instead of ~11 (unpack, FMUL, FFMA, FMNMX, FHADD,
+        // pack).  The epilogue warps are latency-bound (2 per scheduler, ~3.8 k dependent-ish instructions per
+        // tile), so the instruction count is what sets the tile rate of every K <= 1024 GEMM here.
+        const uint2* sc2 = reinterpret_cast<const uint2*>(p.scale_h2 + cb / 2 + ch * 32);
+        const uint2* sh2 = reinterpret_cast<const uint2*>(p.shift_h2 + cb / 2 + ch * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = my_row + (((uint32_t)j ^ my_sw) << 4);
+          [[maybe_unused]] uint4 ad;
+          if constexpr (kAdd != kAddNone) ad = lds_v4(addr);
+          const uint32_t au[4] = {kAdd != kAddNone ? ad.x : 0u, kAdd != kAddNone ? ad.y : 0u,
+                                  kAdd != kAddNone ? ad.z : 0u, kAdd != kAddNone ? ad.w : 0u};
+          const uint2 sca = sc2[2 * j], scb = sc2[2 * j + 1], sha = sh2[2 * j], shb = sh2[2 * j + 1];
+          const uint32_t scv[4] = {sca.x, sca.y, scb.x, scb.y}, shv[4] = {sha.x, sha.y, shb.x, shb.y};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __half2 v = *reinterpret_cast<const __half2*>(&stash[ch * 32 + j * 4 + e]);
+            if constexpr (kAdd == kAddGather) v = __hadd2(v, *reinterpret_cast<const __half2*>(&au[e]));
+            v = __hmul2(v, inv2);
+            v = __hfma2(v, *reinterpret_cast<const __half2*>(&scv[e]), *reinterpret_cast<const __half2*>(&shv[e]));
+            if (p.relu) v = __hmax2(v, __half2(__half(0.f), __half(0.f)));
+            if constexpr (kAdd == kAddResidual) v = __hadd2(v, *reinterpret_cast<const __half2*>(&au[e]));
+            o[e] = *reinterpret_cast<const uint32_t*>(&v);
+          }
+          sts_v4(addr, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+      } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {                             // 16-byte pieces of this thread's 128-byte row chunk
         const uint32_t addr = my_row + (((uint32_t)j ^ my_sw) << 4);
@@ -350,6 +395,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
           o.x = __float_as_uint(v[0]); o.y = __float_as_uint(v[1]); o.z = __float_as_uint(v[2]); o.w = __float_as_uint(v[3]);
         }
         sts_v4(addr, o);
+      }
       }
       __syncwarp();
       // coalesced store: 4 rows x 128 B per instruction
