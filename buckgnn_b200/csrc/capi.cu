@@ -476,13 +476,17 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
     memcpy(&p.shift_h2[i], &sh, 4);
   }
   p.out = out; p.ldo = ldo;
-#define BG_GEMM_OUT(ADD)                                                                 \
-  (out_dtype == BG_BF16 ? launch_gemm512<2, __nv_bfloat16, ADD>(p, stream)               \
-   : out_dtype == BG_F16 ? launch_gemm512<2, __half, ADD>(p, stream)                     \
-                         : launch_gemm512<2, float, ADD>(p, stream))
+  // "plain" epilogue: no normalize, no BatchNorm vectors -> the packed 16-bit pass 2 (exactly equivalent rounding)
+  const bool plain = !p.normalize && !(epi && epi->bn_scale_host) && out_dtype != BG_F32;
+#define BG_GEMM_OUT2(ADD, PLAIN)                                                               \
+  (out_dtype == BG_BF16 ? launch_gemm512<2, __nv_bfloat16, ADD, PLAIN>(p, stream)              \
+   : out_dtype == BG_F16 ? launch_gemm512<2, __half, ADD, PLAIN>(p, stream)                    \
+                         : launch_gemm512<2, float, ADD, false>(p, stream))
+#define BG_GEMM_OUT(ADD) (plain ? BG_GEMM_OUT2(ADD, true) : BG_GEMM_OUT2(ADD, false))
   if (p.n_gather > 0) return BG_GEMM_OUT(kAddGather);
   if (p.residual) return BG_GEMM_OUT(kAddResidual);
   return BG_GEMM_OUT(kAddNone);
+#undef BG_GEMM_OUT2
 #undef BG_GEMM_OUT
 }
 

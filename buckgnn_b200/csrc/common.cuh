@@ -97,6 +97,10 @@ template <> struct Pack16<__nv_bfloat16> {
     __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);
   }
+  static BG_DEVINL uint32_t relu2(uint32_t a) {                        // max(pair, 0)
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), __floats2bfloat162_rn(0.f, 0.f));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
 };
 template <> struct Pack16<__half> {
   static BG_DEVINL float lo(uint32_t u) { return __low2float(*reinterpret_cast<const __half2*>(&u)); }
@@ -109,6 +113,10 @@ template <> struct Pack16<__half> {
   static BG_DEVINL __half one(float a) { return __float2half_rn(a); }
   static BG_DEVINL uint32_t hadd2(uint32_t a, uint32_t b) {
     __half2 r = __hadd2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static BG_DEVINL uint32_t relu2(uint32_t a) {
+    __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), __floats2half2_rn(0.f, 0.f));
     return *reinterpret_cast<uint32_t*>(&r);
   }
 };

@@ -152,18 +152,23 @@ enum : int { kAddNone = 0, kAddResidual = 1, kAddGather = 2 };
 // One epilogue warp: 32 TMEM lanes = 32 output rows, the 256 columns starting at g*256.
 // `g` is a run-time value (both column halves share ONE copy of the code); the per-column
 // vectors are read from the constant bank as float4 at g*256 + immediate.
-template <int kCg, typename TOut, int kAdd>
+// kPlain: no L2-normalize and no BatchNorm scale/shift (every EA-GNN Linear, the encoders, the training step's
+// input-gradient GEMMs).  With a 16-bit output, pass 2 then is "stash (+ gathered rows) -> ReLU (+ skip rows)" on
+// packed pairs: HADD2 / HMNMX2 round exactly like the fp32 path does (the sum of two 16-bit values is exact in
+// fp32, so both round the exact sum once), at ~1.5 instead of ~6.5 instructions per column.
+template <int kCg, typename TOut, int kAdd, bool kPlain>
 BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g) {
   constexpr bool kOut16 = sizeof(TOut) == 2;
-  // -DBG_GEMM_PACKED_EPILOGUE: pass 2 of fp16 outputs as packed half2 math.  Measured (r01): SAGE update
-  // 1.04 -> 1.00 ms, EA-GNN cfg 3 107.7 -> 98.4 ms, but the prediction error vs the fp32 oracle rises from
-  // 6e-5 to 2.8e-4 (u = v * inv and the BN scale are rounded to 11 bits before the affine step).  Off by
-  // default: 4 % is not worth a 5x smaller accuracy margin.
+  // -DBG_GEMM_PACKED_EPILOGUE: pass 2 of fp16 outputs as packed half2 math also WITH normalize / BN.  Measured
+  // (r01): SAGE update 1.04 -> 1.00 ms, but the prediction error vs the fp32 oracle rises from 6e-5 to 2.8e-4
+  // (u = v * inv and the BN scale are rounded to 11 bits before the affine step).  Off by default: 4 % is not
+  // worth a 5x smaller accuracy margin.
 #ifdef BG_GEMM_PACKED_EPILOGUE
-  constexpr bool kPacked = sizeof(TOut) == 2 && !is_bf16<TOut>::value;
+  constexpr bool kPacked = sizeof(TOut) == 2 && !is_bf16<TOut>::value && !kPlain;
 #else
   constexpr bool kPacked = false;
 #endif
+  constexpr bool kPlainPacked = kPlain && kOut16;
   constexpr int kChunkCols = 128 / (int)sizeof(TOut);           // columns per 128-byte row chunk: 64 / 32
   constexpr int kChunks = 256 / kChunkCols;                     // 4 / 8
   constexpr int kPer = 16 / (int)sizeof(TOut);                  // 8 or 4 columns per 16-byte piece
@@ -308,7 +313,27 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
           else mbar_arrive_cluster(cx.tmem_empty_bar, 0);
         }
       }
-      if constexpr (kPacked) {
+      if constexpr (kPlainPacked) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = my_row + (((uint32_t)j ^ my_sw) << 4);
+          uint32_t o[4] = {stash[ch * 32 + j * 4], stash[ch * 32 + j * 4 + 1], stash[ch * 32 + j * 4 + 2], stash[ch * 32 + j * 4 + 3]};
+          if constexpr (kAdd != kAddNone) {
+            const uint4 ad = lds_v4(addr);
+            const uint32_t au[4] = {ad.x, ad.y, ad.z, ad.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if constexpr (kAdd == kAddGather) o[e] = Pack16<TOut>::hadd2(o[e], au[e]);      // addends before the activation
+              if (p.relu) o[e] = Pack16<TOut>::relu2(o[e]);
+              if constexpr (kAdd == kAddResidual) o[e] = Pack16<TOut>::hadd2(o[e], au[e]);    // skip rows after it
+            }
+          } else if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = Pack16<TOut>::relu2(o[e]);
+          }
+          sts_v4(addr, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+      } else if constexpr (kPacked) {
         // fp16 output: the stash already holds the row as fp16 pairs, so normalize / BN / ReLU / addends run as
         // packed half2 math -- 4 instructions per TWO columns instead of ~11 (unpack, FMUL, FFMA, FMNMX, FHADD,
         // pack).  The epilogue warps are latency-bound (2 per scheduler, ~3.8 k dependent-ish instructions per
@@ -415,7 +440,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
 #endif
 }
 
-template <int kCg, typename TOut, int kAdd>
+template <int kCg, typename TOut, int kAdd, bool kPlain>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm512(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<kCg>;
@@ -556,7 +581,7 @@ k_gemm512(const __grid_constant__ GemmParams p) {
                     reinterpret_cast<float*>(epi_gen + ew * kEpiStageBytes),
                     reinterpret_cast<const float*>(epi_gen + (ew ^ 4) * kEpiStageBytes),
                     tmem_full_bar, tmem_empty_bar, rank, tile0, tile_stride};
-    epilogue_warp<kCg, TOut, kAdd>(p, cx, ew >> 2);
+    epilogue_warp<kCg, TOut, kAdd, kPlain>(p, cx, ew >> 2);
   }
 
   // ---- teardown
@@ -594,10 +619,10 @@ static inline int make_operand_map(CUtensorMap* map, const void* base, int64_t r
   return r == CUDA_SUCCESS ? BG_OK : BG_ERR_CUDA;
 }
 
-template <int kCg, typename TOut, int kAdd>
+template <int kCg, typename TOut, int kAdd, bool kPlain>
 static int launch_gemm512(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<kCg>;
-  auto kern = k_gemm512<kCg, TOut, kAdd>;
+  auto kern = k_gemm512<kCg, TOut, kAdd, kPlain>;
   static bool attr_set = false;
   if (!attr_set) {
     BG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
