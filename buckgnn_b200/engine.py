@@ -419,6 +419,43 @@ def pool_head(x: Activation, idx: GraphIndex, dec: Dict[str, torch.Tensor], out_
     return pred, pooled
 
 
+def pack_node_head(decoder, precision: str) -> Dict[str, object]:
+    """Node-level heads (`decoder(x)` on every node, Models/BuckGNN.py:518-524): the first Linear (512 -> 128)
+    runs on the tensor-core GEMM with its weight zero-padded to 512 output rows; the two narrow Linears
+    (128 -> 64 -> out) run on bg_sgemm."""
+    w1 = decoder[0].weight.detach().float()
+    dev = w1.device
+    w1p = torch.zeros((512, w1.shape[1]), dtype=torch.float32, device=dev)
+    w1p[:w1.shape[0]] = w1
+    b1p = torch.zeros(512, dtype=torch.float32)
+    b1p[:w1.shape[0]] = decoder[0].bias.detach().float().cpu()
+    f32 = lambda t: t.detach().float().contiguous()
+    return {"w1": pack_linear(w1p, precision), "b1_host": b1p.contiguous(), "h1_width": w1.shape[0],
+            "w2": f32(decoder[2].weight), "b2": f32(decoder[2].bias), "w3": f32(decoder[4].weight), "b3": f32(decoder[4].bias)}
+
+
+def node_head(x: Activation, n: int, head: Dict[str, object], out_dim: int, cta_group: int = 2) -> torch.Tensor:
+    """decoder(x) for all n nodes -> [n, out_dim] f32."""
+    dev = x.data.device
+    s = _stream()
+    h1 = Activation(n, 512, x.precision, dev)
+    with TIMERS.span("node_head"):
+        gemm512(_segments(x, head["w1"]), n, x.precision, h1, cta_group=cta_group, bias=head["b1_host"].data_ptr(), relu=True)
+        k1 = head["h1_width"]
+        w2, w3 = head["w2"], head["w3"]
+        h2 = torch.empty((n, w2.shape[0]), dtype=torch.float32, device=dev)
+        out = torch.empty((n, out_dim), dtype=torch.float32, device=dev)
+        for (a, a_code, lda, wt, bias, relu, dst) in ((h1.data, h1.code, 512, w2, head["b2"], True, h2),
+                                                     (h2, capi.BG_F32, w2.shape[0], w3, head["b3"], False, out)):
+            m_, n_, k_ = n, wt.shape[0], wt.shape[1]
+            nb = capi.sgemm_workspace_bytes(m_, n_, k_)
+            ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+            capi.sgemm(a.data_ptr(), a_code, lda, 1, wt.data_ptr(), capi.BG_F32, 1, k_, m_, n_, k_, bias.data_ptr(), relu,
+                       None, capi.BG_F32, 0, dst.data_ptr(), capi.BG_F32, n_, False, ws.data_ptr(), nb, s)
+        assert k1 == w2.shape[1]
+    return out
+
+
 # ----------------------------------------------------------------------------- EA-GNN (GraphNetBlock)
 @dataclass
 class GNBlockPack:

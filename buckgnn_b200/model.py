@@ -182,6 +182,8 @@ class BuckGNN(nn.Module):
         dec = self.decoder
         packs["dec"] = {"w1": f32(dec[0].weight), "b1": f32(dec[0].bias), "w2": f32(dec[2].weight),
                         "b2": f32(dec[2].bias), "w3": f32(dec[4].weight), "b3": f32(dec[4].bias)}
+        if self.prediction_type != "buckling" and self.hidden_channels >= 256:
+            packs["node_head"] = engine.pack_node_head(dec, prec)
         mpl = self.pooling_mpl.mlp[0]
         packs["pool_mlp"] = {"w": f32(mpl.weight), "b": f32(mpl.bias)}
         layers, seen = [], {}
@@ -234,12 +236,13 @@ class BuckGNN(nn.Module):
 
     def forward(self, x, edge_index, edge_attr, batch=None, mask=None):
         self._check_supported(x)
-        if self.prediction_type != "buckling":
-            if "static" in self.prediction_type or "mode_shape" in self.prediction_type:
-                raise NotImplementedError("buckgnn_b200: node-level heads are not built yet")
+        node_level = "static" in self.prediction_type or "mode_shape" in self.prediction_type
+        if self.prediction_type != "buckling" and not node_level:
             raise ValueError(f"Unknown prediction type: {self.prediction_type}")
-        if self.pooling_layer not in ("mean", "mean_no_super", "supernode_only", "supernode_with_pooling", "mlp",
-                                      "mlp_no_super"):
+        if node_level and (self.training or self.hidden_channels < 256):
+            raise NotImplementedError("buckgnn_b200: node-level heads run in eval mode with the 3-layer decoder only")
+        if not node_level and self.pooling_layer not in ("mean", "mean_no_super", "supernode_only",
+                                                          "supernode_with_pooling", "mlp", "mlp_no_super"):
             if self.pooling_layer == "hybrid":
                 raise AttributeError("'BuckGNN' object has no attribute 'hybrid_pooling'")   # reference :188,276
             raise ValueError(f"Unknown pooling layer: {self.pooling_layer}")
@@ -248,9 +251,14 @@ class BuckGNN(nn.Module):
             return train.forward_train(self, x, edge_index, batch).squeeze(), batch
         with torch.no_grad():
             if self.model_name in ("EA_GNN", "EA_GNN_Shared"):
-                pred = self._forward_cuda_eagnn(x, edge_index, edge_attr, batch)
+                pred = self._forward_cuda_eagnn(x, edge_index, edge_attr, batch, node_level)
             else:
-                pred = self._forward_cuda(x, edge_index, batch)
+                pred = self._forward_cuda(x, edge_index, batch, node_level)
+        if node_level:                                       # reference :518-524
+            if "super" in self.pooling_layer:
+                is_real_node = x[:, -1] == 0                 # :315-320 (row selection of the [N, out] result)
+                return pred[is_real_node], (batch[is_real_node] if batch is not None else None)
+            return pred, batch
         return pred.squeeze(), batch
 
     def _begin_graph_index(self, edge_index, batch, n):
@@ -273,7 +281,7 @@ class BuckGNN(nn.Module):
             return _Fill
         return engine.begin_graph_index(edge_index, batch, n)
 
-    def _forward_cuda_eagnn(self, x, edge_index, edge_attr, batch):
+    def _forward_cuda_eagnn(self, x, edge_index, edge_attr, batch, node_level=False):
         """EA-GNN / "CustomGNN" path (reference :326-336, :375-387, GraphNetBlock :528-566)."""
         packs = self._packed()
         prec, cg = self.precision, self.cta_group
@@ -300,11 +308,13 @@ class BuckGNN(nn.Module):
                                                need_edges_out=(i < L - 1), cta_group=cg)
             if e_next is not None:
                 e = e_next
+        if node_level:
+            return engine.node_head(cur, n, packs["node_head"], self.output_dim, cg)
         pre = packs["pool_mlp"] if self.pooling_layer in ("mlp", "mlp_no_super") else None
         pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim, pooling=self.pooling_layer, pre=pre)
         return pred
 
-    def _forward_cuda(self, x, edge_index, batch):
+    def _forward_cuda(self, x, edge_index, batch, node_level=False):
         packs = self._packed()
         prec, cg = self.precision, self.cta_group
         x = x.detach().to(torch.float32).contiguous()
@@ -331,6 +341,8 @@ class BuckGNN(nn.Module):
                     engine.sage_layer(cur, agg, nxt, idx, layer, aggr=aggr, normalize=True, relu=True,
                                       residual=(0 < i < L - 1), cta_group=cg)
                 cur, nxt = nxt, cur
+        if node_level:
+            return engine.node_head(cur, n, packs["node_head"], self.output_dim, cg)     # reference :518-524
         pre = packs["pool_mlp"] if self.pooling_layer in ("mlp", "mlp_no_super") else None
         pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim, pooling=self.pooling_layer,
                                    pre=pre)                                                # reference :515-516

@@ -189,3 +189,34 @@ def test_eagnn_directed_graph_with_isolated_sources():
     b.edge_attr = b.edge_attr[keep].contiguous()
     got, want = _run(ref, ours, b)
     _assert_rel(got, want, 1e-4)
+
+
+@pytest.mark.parametrize("prediction_type,use_z,use_rot,pooling,model_name,precision", [
+    ("static_disp", False, False, "mean", "GraphSage_meanAggr", "fp16"),
+    ("static_disp", True, True, "supernode_only", "GraphSage_meanAggr", "tf32"),
+    ("static_stress", False, False, "mean", "GraphSage_sumAggr", "tf32"),
+    ("mode_shape", False, True, "mean_no_super", "EA_GNN", "fp16"),
+])
+def test_node_level_heads(prediction_type, use_z, use_rot, pooling, model_name, precision):
+    """decoder(x) on every node (reference :518-524); with a "super" pooling layer only the real nodes are
+    returned, together with their batch ids (:315-320)."""
+    torch.manual_seed(0)
+    cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=3, pooling_layer=pooling,
+               prediction_type=prediction_type, use_z_coord=use_z, use_rotations=use_rot, model_name=model_name)
+    ref = OracleBuckGNN(**cfg).eval()
+    randomize_bn_stats(ref, realistic=True)
+    ours = BuckGNN(**cfg, precision=precision)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV).eval()
+    b = make_batch(3, nx=11, ny=9, stiffened=(model_name == "EA_GNN"))
+    with torch.no_grad():
+        want, want_batch = ref(b.x, b.edge_index, b.edge_attr, b.batch)
+        bd = b.to(DEV)
+        got, got_batch = ours(bd.x, bd.edge_index, bd.edge_attr, bd.batch)
+    assert got.shape == want.shape and got.shape[1] == ours.output_dim
+    assert torch.equal(got_batch.cpu(), want_batch)
+    n_real = b.num_nodes - 3
+    assert got.shape[0] == (n_real if "super" in pooling else b.num_nodes)
+    err = ((got.cpu().double() - want.double()).norm() / want.double().norm()).item()
+    assert err < 2e-3, err
+    assert (got.cpu() - want).abs().max().item() < 2e-3 * want.abs().max().item() + 1e-4
