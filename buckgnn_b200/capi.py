@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "bg_expand_rowptr", "bg_add",
     "bg_train_workspace_bytes", "bg_bn_batch_stats", "bg_bn_act_forward", "bg_sage_backward_rows",
     "bg_transpose_chunks", "bg_reduce_partials", "bg_colsum_workspace_bytes", "bg_colsum", "bg_pool_backward",
-    "bg_sgemm_workspace_bytes", "bg_sgemm", "bg_dropout_mask",
+    "bg_sgemm_workspace_bytes", "bg_sgemm", "bg_eigen_loss", "bg_dropout_mask", "bg_collate_ptr", "bg_collate",
 )
 
 
@@ -100,6 +100,9 @@ _SIGNATURES = {
     "bg_sgemm": (C.c_int, [_P, C.c_int, _I64, _I64, _P, C.c_int, _I64, _I64, _I64, _I64, _I64, _P, C.c_int, _P,
                            C.c_int, _I64, _P, C.c_int, _I64, C.c_int, _P, C.c_size_t, _P]),
     "bg_dropout_mask": (C.c_int, [C.c_uint64, C.c_float, _I64, _P, _P]),
+    "bg_collate_ptr": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
+    "bg_collate": (C.c_int, [_P, _I32, _P, _I64, _P, _I32, _P, _P, _I64, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P]),
+    "bg_eigen_loss": (C.c_int, [_P, _P, _I64, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P]),
 }
 
 
@@ -302,3 +305,18 @@ def sgemm(a, a_dtype, sam, sak, b, b_dtype, sbk, sbn, m, n, k, bias, relu, mask,
 
 def dropout_mask(seed, dropout_p, n_rows, keep, stream):
     _check(load().bg_dropout_mask(seed, dropout_p, n_rows, keep, stream), "bg_dropout_mask")
+
+
+def eigen_loss(pred, y, n_graphs, scale, center, eps, out2, dpred, accum3, stream):
+    _check(load().bg_eigen_loss(pred, y, n_graphs, scale, center, eps, out2, dpred, accum3, stream), "bg_eigen_loss")
+
+
+def collate_ptr(sel, n_graphs, node_ptr, edge_ptr, out_node_ptr, out_edge_ptr, stream):
+    _check(load().bg_collate_ptr(sel, n_graphs, node_ptr, edge_ptr, out_node_ptr, out_edge_ptr, stream), "bg_collate_ptr")
+
+
+def collate(x_all, n_features, ei_all, e_all, ea_all, n_edge_features, y_all, sel, n_graphs, node_ptr, edge_ptr,
+            out_node_ptr, out_edge_ptr, n_out, e_out, x, edge_index, edge_attr, batch, y, stream):
+    _check(load().bg_collate(x_all, n_features, ei_all, e_all, ea_all, n_edge_features, y_all, sel, n_graphs, node_ptr,
+                             edge_ptr, out_node_ptr, out_edge_ptr, n_out, e_out, x, edge_index, edge_attr, batch, y,
+                             stream), "bg_collate")

@@ -754,6 +754,51 @@ int bg_sgemm(const void* a, int a_dtype, int64_t sam, int64_t sak, const void* b
   return BG_OK;
 }
 
+int bg_collate_ptr(const int64_t* sel, int64_t G, const int64_t* node_ptr, const int64_t* edge_ptr,
+                   int64_t* out_node_ptr, int64_t* out_edge_ptr, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (G < 0 || !out_node_ptr || !out_edge_ptr || (G > 0 && (!sel || !node_ptr || !edge_ptr)))
+    return fail(BG_ERR_INVALID, "bg_collate_ptr: bad argument");
+  k_collate_ptr<<<1, 1024, 0, stream>>>(sel, G, node_ptr, edge_ptr, out_node_ptr, out_edge_ptr);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_collate(const float* x_all, int32_t F, const int64_t* ei_all, int64_t E_all, const float* ea_all, int32_t Fe,
+               const float* y_all, const int64_t* sel, int64_t G, const int64_t* node_ptr, const int64_t* edge_ptr,
+               const int64_t* out_node_ptr, const int64_t* out_edge_ptr, int64_t n_out, int64_t e_out,
+               float* x, int64_t* edge_index, float* edge_attr, int64_t* batch, float* y, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (G <= 0 || F <= 0 || Fe < 0 || n_out < 0 || e_out < 0 || E_all < 0) return fail(BG_ERR_INVALID, "bg_collate: bad size");
+  if (!sel || !node_ptr || !edge_ptr || !out_node_ptr || !out_edge_ptr || (n_out > 0 && (!x_all || !x || !batch)) ||
+      (e_out > 0 && (!ei_all || !edge_index || (Fe > 0 && (!ea_all || !edge_attr)))))
+    return fail(BG_ERR_INVALID, "bg_collate: bad pointer");
+  const int sms = sm_count();
+  if (n_out > 0) {
+    k_collate_nodes<<<grid_for(n_out * F, 256, sms * 16), 256, 0, stream>>>(x_all, F, sel, G, node_ptr, out_node_ptr, x, batch);
+    BG_LAUNCH_OK();
+  }
+  if (e_out > 0) {
+    k_collate_edges<<<grid_for(e_out, 256, sms * 16), 256, 0, stream>>>(ei_all, E_all, ea_all, Fe, sel, G, edge_ptr, out_node_ptr,
+                                                                      out_edge_ptr, edge_index, edge_attr);
+    BG_LAUNCH_OK();
+  }
+  if (y_all && y) {
+    k_collate_y<<<(unsigned)ceil_div64(G, 256), 256, 0, stream>>>(y_all, sel, G, y);
+    BG_LAUNCH_OK();
+  }
+  return BG_OK;
+}
+
+int bg_eigen_loss(const float* pred, const float* y, int64_t G, float scale, float center, float eps,
+                  float* out2, float* dpred, float* accum3, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (G <= 0 || !pred || !y || !out2) return fail(BG_ERR_INVALID, "bg_eigen_loss: bad argument");
+  k_eigen_loss<<<1, 256, 0, stream>>>(pred, y, G, scale, center, eps, out2, dpred, accum3);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
 int bg_dropout_mask(uint64_t seed, float dropout_p, int64_t n_rows, uint8_t* keep, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_rows < 0 || (n_rows > 0 && !keep) || !(dropout_p >= 0.f && dropout_p < 1.f)) return fail(BG_ERR_INVALID, "bg_dropout_mask: bad argument");

@@ -435,6 +435,113 @@ __global__ void k_sgemm_epilogue(const SgemmEpilogue p) {
   }
 }
 
+// ------------------------------------------------------------------ device-side collate
+// PyG's DataLoader collate (Batch.from_data_list) for a dataset that lives in HBM in concatenated form:
+//   store: x_all [sum n, F], ei_all [2, sum e] (node ids LOCAL to their graph), ea_all [sum e, Fe], y_all [G_all],
+//          node_ptr / edge_ptr [G_all + 1] (int64)
+//   batch of graphs sel[0..G): out x / edge_index (+ node offset of the graph's slot) / edge_attr / batch / y / ptr.
+// k_collate_ptr: exclusive scans of the selected graphs' sizes (one CTA; G is at most a few thousand).
+__global__ void __launch_bounds__(1024)
+k_collate_ptr(const int64_t* __restrict__ sel, int64_t G, const int64_t* __restrict__ node_ptr,
+              const int64_t* __restrict__ edge_ptr, int64_t* __restrict__ out_node_ptr, int64_t* __restrict__ out_edge_ptr) {
+  __shared__ int64_t carry[2];
+  __shared__ int64_t buf[2][1024];
+  if (threadIdx.x == 0) { carry[0] = carry[1] = 0; out_node_ptr[0] = 0; out_edge_ptr[0] = 0; }
+  __syncthreads();
+  for (int64_t base = 0; base < G; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    int64_t n = 0, e = 0;
+    if (i < G) { const int64_t g = sel[i]; n = node_ptr[g + 1] - node_ptr[g]; e = edge_ptr[g + 1] - edge_ptr[g]; }
+    buf[0][threadIdx.x] = n; buf[1][threadIdx.x] = e;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {                 // Hillis-Steele inclusive scan
+      int64_t a = 0, b = 0;
+      if ((int)threadIdx.x >= off) { a = buf[0][threadIdx.x - off]; b = buf[1][threadIdx.x - off]; }
+      __syncthreads();
+      buf[0][threadIdx.x] += a; buf[1][threadIdx.x] += b;
+      __syncthreads();
+    }
+    if (i < G) { out_node_ptr[i + 1] = carry[0] + buf[0][threadIdx.x]; out_edge_ptr[i + 1] = carry[1] + buf[1][threadIdx.x]; }
+    __syncthreads();
+    if (threadIdx.x == 1023) { carry[0] += buf[0][1023]; carry[1] += buf[1][1023]; }
+    __syncthreads();
+  }
+}
+
+BG_DEVINL int64_t slot_of(const int64_t* __restrict__ ptr, int64_t G, int64_t i) {   // last g with ptr[g] <= i
+  int64_t lo = 0, hi = G;
+  while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (ptr[mid] <= i) lo = mid; else hi = mid; }
+  return lo;
+}
+
+// one thread per (row, float) of x / edge_attr; rows carry their slot's bookkeeping
+__global__ void k_collate_nodes(const float* __restrict__ x_all, int F, const int64_t* __restrict__ sel, int64_t G,
+                                const int64_t* __restrict__ node_ptr, const int64_t* __restrict__ out_node_ptr,
+                                float* __restrict__ x, int64_t* __restrict__ batch) {
+  const int64_t n_out = out_node_ptr[G];
+  const int64_t total = n_out * F, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / F; const int k = (int)(t % F);
+    const int64_t g = slot_of(out_node_ptr, G, i);
+    const int64_t src = node_ptr[sel[g]] + (i - out_node_ptr[g]);
+    x[t] = x_all[src * F + k];
+    if (k == 0) batch[i] = g;
+  }
+}
+
+__global__ void k_collate_edges(const int64_t* __restrict__ ei_all, int64_t E_all, const float* __restrict__ ea_all, int Fe,
+                                const int64_t* __restrict__ sel, int64_t G, const int64_t* __restrict__ edge_ptr,
+                                const int64_t* __restrict__ out_node_ptr, const int64_t* __restrict__ out_edge_ptr,
+                                int64_t* __restrict__ ei, float* __restrict__ ea) {
+  const int64_t e_out = out_edge_ptr[G];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < e_out; e += stride) {
+    const int64_t g = slot_of(out_edge_ptr, G, e);
+    const int64_t src = edge_ptr[sel[g]] + (e - out_edge_ptr[g]);
+    const int64_t off = out_node_ptr[g];
+    ei[e] = ei_all[src] + off;
+    ei[e_out + e] = ei_all[E_all + src] + off;
+    for (int k = 0; k < Fe; ++k) ea[e * Fe + k] = ea_all[src * Fe + k];
+  }
+}
+
+__global__ void k_collate_y(const float* __restrict__ y_all, const int64_t* __restrict__ sel, int64_t G, float* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < G) y[i] = y_all[sel[i]];
+}
+
+// ------------------------------------------------------------------ loss + metric epilogue (one CTA)
+// What TRAIN_FINAL.py:262-263 / :340-341 compute per batch with three host syncs and two scaler uploads:
+//   pd = pred * scale + center, td = y * scale + center          (Normalizer.denormalize_eigenvalue, :207-215)
+//   loss = mean(|pd - td| / (|td| + eps))                         (RelativeErrorLoss, Utils/Losses.py:755-761)
+//   mape = 100 * mean(|td - pd| / |td|)                           (MAPE_error, Dataset_Preparation/Metrics.py:4-12)
+//   dpred = d loss / d pred = sign(pd - td) * scale / ((|td| + eps) * G)
+// out[0] = loss, out[1] = mape; accum (nullable) [3] += {loss, mape, 1} so an epoch's running sums stay on the device.
+__global__ void __launch_bounds__(256)
+k_eigen_loss(const float* __restrict__ pred, const float* __restrict__ y, int64_t G, float scale, float center, float eps,
+             float* __restrict__ out, float* __restrict__ dpred, float* __restrict__ accum) {
+  __shared__ float red[2][256];
+  float l = 0.f, m = 0.f;
+  for (int64_t i = threadIdx.x; i < G; i += 256) {
+    const float pd = fmaf(pred[i], scale, center), td = fmaf(y[i], scale, center);
+    const float diff = pd - td, at = fabsf(td);
+    l += fabsf(diff) / (at + eps);
+    m += fabsf(diff) / at;
+    if (dpred) dpred[i] = (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) * scale / ((at + eps) * (float)G);
+  }
+  red[0][threadIdx.x] = l; red[1][threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) { red[0][threadIdx.x] += red[0][threadIdx.x + s]; red[1][threadIdx.x] += red[1][threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float loss = red[0][0] / (float)G, mape = 100.f * red[1][0] / (float)G;
+    out[0] = loss; out[1] = mape;
+    if (accum) { accum[0] += loss; accum[1] += mape; accum[2] += 1.f; }
+  }
+}
+
 // materialise the dropout keep mask of a layer (test hook: lets the oracle apply the same mask)
 __global__ void k_dropout_mask(uint64_t seed, uint32_t thr, int64_t n_rows, uint8_t* __restrict__ keep) {
   const int64_t total = n_rows * kHidden, stride = (int64_t)gridDim.x * blockDim.x;

@@ -277,6 +277,27 @@ int bg_sgemm(const void* a, int a_dtype, int64_t sam, int64_t sak, const void* b
              int64_t m, int64_t n, int64_t k, const float* bias, int relu, const void* mask, int mask_dtype,
              int64_t mask_ld, void* out, int out_dtype, int64_t ldo, int accumulate,
              void* workspace, size_t workspace_bytes, void* stream);
+/* Device-side collate: PyG `DataLoader` / `Batch.from_data_list` for a dataset kept in HBM in
+ * concatenated form -- x_all [sum n, F], ei_all [2, E_all] with node ids LOCAL to their graph (as
+ * GraphCreate.py:417-432 emits them), ea_all [E_all, Fe], y_all [G_all], node_ptr / edge_ptr [G_all+1] int64.
+ * bg_collate_ptr: out_node_ptr / out_edge_ptr [G+1] = exclusive scans of the sizes of the selected graphs sel[0..G).
+ * bg_collate (after the host has read n_out = out_node_ptr[G], e_out = out_edge_ptr[G] and allocated):
+ *   x [n_out, F], edge_index [2, e_out] (+ the slot's node offset), edge_attr [e_out, Fe], batch [n_out], y [G].
+ * An 80 k-graph inference set (~90 GB) fits the 180 GB of a B200: no host collate, no PCIe traffic per batch. */
+int bg_collate_ptr(const int64_t* sel, int64_t n_graphs, const int64_t* node_ptr, const int64_t* edge_ptr,
+                   int64_t* out_node_ptr, int64_t* out_edge_ptr, void* stream);
+int bg_collate(const float* x_all, int32_t n_features, const int64_t* ei_all, int64_t e_all, const float* ea_all,
+               int32_t n_edge_features, const float* y_all, const int64_t* sel, int64_t n_graphs,
+               const int64_t* node_ptr, const int64_t* edge_ptr, const int64_t* out_node_ptr,
+               const int64_t* out_edge_ptr, int64_t n_out, int64_t e_out,
+               float* x, int64_t* edge_index, float* edge_attr, int64_t* batch, float* y, void* stream);
+/* Loss + metric epilogue of the eigenvalue head, replacing per batch `criterion(normalizer.denormalize_eigenvalue(pred),
+ * normalizer.denormalize_eigenvalue(batch.y))` + `MAPE_error(pred, batch.y, "buckling", normalizer).item()`
+ * (TRAIN_FINAL.py:262-263, 340-341; Normalizer.py:207-215, Utils/Losses.py:755-761, Metrics.py:4-12):
+ *   pd = pred*scale + center, td = y*scale + center;  out2[0] = mean(|pd-td| / (|td|+eps));  out2[1] = 100*mean(|td-pd|/|td|)
+ *   dpred (nullable, [G]) = d out2[0] / d pred;  accum3 (nullable) += {loss, mape, 1} (epoch sums without host syncs). */
+int bg_eigen_loss(const float* pred, const float* y, int64_t n_graphs, float scale, float center, float eps,
+                  float* out2, float* dpred, float* accum3, void* stream);
 /* keep[r*512 + c] = 1 if dropout keeps element (r, c) for (seed, dropout_p) -- lets a test apply the same mask. */
 int bg_dropout_mask(uint64_t seed, float dropout_p, int64_t n_rows, uint8_t* keep, void* stream);
 

@@ -294,3 +294,25 @@ def test_pool_head_matches_oracle(precision):
     torch.testing.assert_close(pooled.cpu(), x[last], rtol=0, atol=0)
     _, pooled = engine.pool_head(xa, idx, packs, 1, want_pooled=True, pooling="mean_no_super")
     torch.testing.assert_close(pooled.cpu(), O.global_mean_pool(x[keep], b.batch[keep]), rtol=1e-5, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- device-side collate (row f1)
+def test_device_collate_is_bit_exact():
+    """DeviceGraphStore.batch == the host collate (PyG Batch.from_data_list layout), for an arbitrary selection
+    with repeats and out-of-order graphs."""
+    from buckgnn_b200.collate import DeviceGraphStore
+    from buckgnn_b200.synth import collate, make_plate_graph
+    graphs = [make_plate_graph(i, nx=5 + i % 4, ny=4 + i % 3, stiffened=(i % 2 == 1)) for i in range(9)]
+    store = DeviceGraphStore(graphs, DEV)
+    for sel in ([0, 1, 2, 3, 4, 5, 6, 7, 8], [7, 2, 2, 5], [3]):
+        want = collate([graphs[i] for i in sel])
+        got = store.batch(torch.tensor(sel))
+        assert got.num_graphs == len(sel)
+        for f in ("x", "edge_index", "edge_attr", "batch", "y", "ptr"):
+            assert torch.equal(getattr(got, f).cpu(), getattr(want, f)), f
+    # 1500 graphs: more than one scan block of bg_collate_ptr
+    sel = torch.arange(1500) % 9
+    got = store.batch(sel)
+    want = collate([graphs[int(i)] for i in sel])
+    assert torch.equal(got.edge_index.cpu(), want.edge_index) and torch.equal(got.ptr.cpu(), want.ptr)
+    assert torch.equal(got.batch.cpu(), want.batch) and torch.equal(got.x.cpu(), want.x)

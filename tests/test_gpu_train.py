@@ -335,3 +335,28 @@ def test_training_step_is_deterministic_and_optimizer_runs():
         opt.step()
         losses.append(loss.item())
     assert bb is b.batch and losses[-1] < losses[0]
+
+
+def test_fused_eigenvalue_loss_and_mape():
+    """bg_eigen_loss against the reference formulas restated in torch (Normalizer.py:207-215,
+    Utils/Losses.py:755-761, Dataset_Preparation/Metrics.py:4-12)."""
+    from buckgnn_b200.loss import EigenvalueRelativeLoss
+    torch.manual_seed(0)
+    g, scale, center, eps = 777, 3.7, 11.0, 1e-8
+    pred = torch.randn(g, requires_grad=True)
+    y = torch.randn(g)
+    pd, td = pred * scale + center, y * scale + center
+    want_loss = torch.mean(torch.abs(pd - td) / (torch.abs(td) + eps))
+    want_mape = torch.mean(torch.abs((td - pd) / td)) * 100
+    want_loss.backward()
+    crit = EigenvalueRelativeLoss(scale, center, eps)
+    pdev = pred.detach().to(DEV).requires_grad_()
+    for _ in range(2):                                  # two batches: the epoch sums accumulate on the device
+        loss = crit(pdev, y.to(DEV))
+    (loss * 2).backward()
+    torch.testing.assert_close(loss.detach().cpu(), want_loss.detach(), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(crit.last_mape.cpu(), want_mape.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(pdev.grad.cpu(), 2 * pred.grad, rtol=1e-5, atol=1e-9)
+    ml, mm = crit.epoch_means()
+    assert abs(ml - float(want_loss)) < 1e-5 and abs(mm - float(want_mape)) < 1e-3
+    assert crit.epoch_means() == (0.0, 0.0)
