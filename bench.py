@@ -45,7 +45,12 @@ def _traffic_from_profile(name_part: str, exclude: str = ""):
     (profiles/r*_ncu_full_summary.csv, written by tools/ncu_summary.py).  None if there is no capture."""
     import csv
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.csv")), key=os.path.getmtime)
+    import re
+
+    def version(path):                      # profiles/rNN_vMM_ncu_full_summary.csv -> (NN, MM)
+        m = re.search(r"r(\d+)_v(\d+)_ncu_full_summary", os.path.basename(path))
+        return (int(m.group(1)), int(m.group(2))) if m else (-1, -1)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.csv")), key=version)
     if not files:
         return None
     rows = list(csv.reader(open(files[-1])))

@@ -20,7 +20,7 @@ BG_BF16, BG_F32, BG_F16 = 0, 1, 2
 BG_AGGR_MEAN, BG_AGGR_SUM, BG_AGGR_MAX = 0, 1, 2
 BG_BIG_ROW_THRESHOLD = 64
 BG_MAX_GEMM_SEGMENTS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 AGGR_CODES = {"mean": BG_AGGR_MEAN, "sum": BG_AGGR_SUM, "add": BG_AGGR_SUM, "max": BG_AGGR_MAX}
 
@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = (
     "bg_pool_workspace_bytes", "bg_pool_head", "bg_cast_f32", "bg_split_tf32",
     "bg_expand_rowptr", "bg_add",
     "bg_train_workspace_bytes", "bg_bn_batch_stats", "bg_bn_act_forward", "bg_sage_backward_rows",
-    "bg_transpose_chunks", "bg_reduce_partials", "bg_colsum_workspace_bytes", "bg_colsum", "bg_pool_backward",
+    "bg_transpose_chunks", "bg_mask_narrow", "bg_reduce_partials", "bg_colsum_workspace_bytes", "bg_colsum", "bg_pool_backward",
     "bg_sgemm_workspace_bytes", "bg_sgemm", "bg_eigen_loss", "bg_dropout_mask", "bg_collate_ptr", "bg_collate",
 )
 
@@ -91,7 +91,8 @@ _SIGNATURES = {
     "bg_bn_act_forward": (C.c_int, [_P, _P, _P, C.c_int, _I64, _P, _P, C.c_float, C.c_uint64, _P]),
     "bg_sage_backward_rows": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _I64, _P, _P, _P, _P, C.c_float, C.c_uint64,
                                         _P, _P, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
-    "bg_transpose_chunks": (C.c_int, [_P, C.c_int, _I64, _I32, _I64, _I32, _I64, _P, _P]),
+    "bg_transpose_chunks": (C.c_int, [_P, C.c_int, _I64, _I32, _I64, _I32, _I64, _I32, _P, _P]),
+    "bg_mask_narrow": (C.c_int, [_P, C.c_int, _I64, _P, C.c_int, _I64, _I64, _I32, _P, _P]),
     "bg_reduce_partials": (C.c_int, [_P, _I32, _I64, _P, C.c_int, _P]),
     "bg_colsum_workspace_bytes": (C.c_int, [_I64, _I32, _SZP]),
     "bg_colsum": (C.c_int, [_P, C.c_int, _I64, _I32, _I64, _P, C.c_int, _P, C.c_size_t, _P]),
@@ -270,9 +271,13 @@ def sage_backward_rows(u, dy, dy2, inv_norm, rowptr, dtype, n_rows, a, shift, me
                                         ws, ws_bytes, stream), "bg_sage_backward_rows")
 
 
-def transpose_chunks(src, dtype, n_rows, n_cols, ld, n_chunks, chunk_k, out, stream):
-    _check(load().bg_transpose_chunks(src, dtype, n_rows, n_cols, ld, n_chunks, chunk_k, out, stream),
+def transpose_chunks(src, dtype, n_rows, n_cols, ld, n_chunks, chunk_k, out, stream, out_rows_per_chunk=0):
+    _check(load().bg_transpose_chunks(src, dtype, n_rows, n_cols, ld, n_chunks, chunk_k, out_rows_per_chunk, out, stream),
            "bg_transpose_chunks")
+
+
+def mask_narrow(src, src_dtype, ld_in, mask, mask_dtype, ld_mask, m, n_cols, out, stream):
+    _check(load().bg_mask_narrow(src, src_dtype, ld_in, mask, mask_dtype, ld_mask, m, n_cols, out, stream), "bg_mask_narrow")
 
 
 def reduce_partials(partial, n_chunks, n, out, accumulate, stream):

@@ -656,14 +656,27 @@ int bg_sage_backward_rows(const void* u, const void* dy, const void* dy2, const 
 }
 
 int bg_transpose_chunks(const void* in, int dtype, int64_t n_rows, int32_t n_cols, int64_t ld, int32_t n_chunks,
-                        int64_t chunk_k, void* out, void* stream_) {
+                        int64_t chunk_k, int32_t out_rows_per_chunk, void* out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (out_rows_per_chunk <= 0) out_rows_per_chunk = n_cols;
   if (n_rows < 0 || n_cols <= 0 || n_cols % 32 != 0 || n_chunks <= 0 || chunk_k <= 0 || chunk_k % 32 != 0 ||
-      (int64_t)n_chunks * chunk_k < n_rows || ld < n_cols)
+      (int64_t)n_chunks * chunk_k < n_rows || ld < n_cols || out_rows_per_chunk < n_cols)
     return fail(BG_ERR_INVALID, "bg_transpose_chunks: bad shape (n_cols, chunk_k multiples of 32; n_chunks*chunk_k >= n_rows)");
   if (!in || !out) return fail(BG_ERR_INVALID, "bg_transpose_chunks: bad pointer");
   dim3 grid((unsigned)((int64_t)n_chunks * chunk_k / 32), (unsigned)(n_cols / 32)), block(32, 8);
-  BG_BY_DTYPE(dtype, (k_transpose_chunks<T><<<grid, block, 0, stream>>>(static_cast<const T*>(in), n_rows, n_cols, ld, chunk_k, static_cast<T*>(out))))
+  BG_BY_DTYPE(dtype, (k_transpose_chunks<T><<<grid, block, 0, stream>>>(static_cast<const T*>(in), n_rows, n_cols, ld, chunk_k, out_rows_per_chunk, static_cast<T*>(out))))
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_mask_narrow(const void* in, int in_dtype, int64_t ld_in, const void* mask, int mask_dtype, int64_t ld_mask,
+                   int64_t M, int32_t n_cols, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (M < 0 || n_cols <= 0 || ld_in < n_cols || (mask && ld_mask < n_cols)) return fail(BG_ERR_INVALID, "bg_mask_narrow: bad shape");
+  if (umma_format_of(in_dtype) < 0 || (mask && umma_format_of(mask_dtype) < 0)) return fail(BG_ERR_INVALID, "bg_mask_narrow: bad dtype");
+  if (M == 0) return BG_OK;
+  if (!in || !out) return fail(BG_ERR_INVALID, "bg_mask_narrow: bad pointer");
+  k_mask_narrow<<<grid_for(M * n_cols, 256, sm_count() * 8), 256, 0, stream>>>(in, in_dtype, ld_in, mask, mask_dtype, ld_mask, M, n_cols, out);
   BG_LAUNCH_OK();
   return BG_OK;
 }

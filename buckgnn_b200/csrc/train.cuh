@@ -253,12 +253,15 @@ k_sage_bwd_rows(const T* __restrict__ u, const T* __restrict__ dy, const T* __re
 }
 
 // ------------------------------------------------------------------ split-K operand layout
-// in [n_rows, n_cols] (ld) -> out [n_chunks][n_cols][chunk_k]:  out[s][c][j] = in[s*chunk_k + j][c], 0 beyond n_rows.
+// in [n_rows, n_cols] (ld) -> out [n_chunks][out_rows >= n_cols][chunk_k]:  out[s][c][j] = in[s*chunk_k + j][c], 0 beyond
+// n_rows (rows c >= n_cols of a chunk are left untouched: the caller zero-fills them when it pads a narrow matrix
+// to the 512 rows the tensor-core GEMM multiplies).
 // The node dimension becomes the contiguous (K) dimension the tcgen05 operand tiles want; chunk s of the
 // split-K is a [n_cols, chunk_k] K-major matrix.   grid (ceil(n_chunks*chunk_k / 32), n_cols / 32), block (32, 8)
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_transpose_chunks(const T* __restrict__ in, int64_t n_rows, int n_cols, int64_t ld, int64_t chunk_k, T* __restrict__ out) {
+k_transpose_chunks(const T* __restrict__ in, int64_t n_rows, int n_cols, int64_t ld, int64_t chunk_k, int out_rows,
+                   T* __restrict__ out) {
   __shared__ T tile[32][33];
   const int64_t j0 = (int64_t)blockIdx.x * 32;       // global node index of the tile
   const int c0 = blockIdx.y * 32;
@@ -273,7 +276,7 @@ k_transpose_chunks(const T* __restrict__ in, int64_t n_rows, int n_cols, int64_t
     const int c = c0 + threadIdx.y + 8 * k;
     const int64_t j = j0 + threadIdx.x;              // chunk_k is a multiple of 32: a tile never straddles chunks
     const int64_t s = j / chunk_k, jj = j % chunk_k;
-    out[((size_t)s * n_cols + c) * chunk_k + jj] = tile[threadIdx.x][threadIdx.y + 8 * k];
+    out[((size_t)s * out_rows + c) * chunk_k + jj] = tile[threadIdx.x][threadIdx.y + 8 * k];
   }
 }
 
@@ -539,6 +542,17 @@ k_eigen_loss(const float* __restrict__ pred, const float* __restrict__ y, int64_
     const float loss = red[0][0] / (float)G, mape = 100.f * red[1][0] / (float)G;
     out[0] = loss; out[1] = mape;
     if (accum) { accum[0] += loss; accum[1] += mape; accum[2] += 1.f; }
+  }
+}
+
+// out[m, n] (f32, ld = n_cols) = in[m, n] * [mask[m, n] > 0]   -- ReLU backward while narrowing a padded GEMM output
+__global__ void k_mask_narrow(const void* __restrict__ in, int in_dtype, int64_t ld_in, const void* __restrict__ mask,
+                              int mask_dtype, int64_t ld_mask, int64_t M, int n_cols, float* __restrict__ out) {
+  const int64_t total = M * n_cols, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t m = i / n_cols; const int n = (int)(i % n_cols);
+    const float v = load_as_float(in, in_dtype, (size_t)(m * ld_in + n));
+    out[i] = (!mask || load_as_float(mask, mask_dtype, (size_t)(m * ld_mask + n)) > 0.f) ? v : 0.f;
   }
 }
 

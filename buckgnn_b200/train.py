@@ -71,12 +71,16 @@ def split_k_layout(n_rows: int):
 class ChunkedTranspose:
     """[N, C] activation -> [chunks][C][chunk_k] (bg_transpose_chunks): node dimension contiguous."""
 
-    def __init__(self, act: torch.Tensor, code: int, n_rows: int, chunks: int, chunk_k: int):
+    def __init__(self, act: torch.Tensor, code: int, n_rows: int, chunks: int, chunk_k: int, pad_rows: int = 0):
+        """pad_rows > cols: every chunk is padded with zero rows to `pad_rows` (a narrow matrix made the
+        512-row B operand of the split-K GEMM)."""
         cols = act.shape[1]
-        self.data = torch.empty((chunks * cols, chunk_k), dtype=act.dtype, device=act.device)
+        rows = max(cols, pad_rows)
+        alloc = torch.zeros if rows > cols else torch.empty
+        self.data = alloc((chunks * rows, chunk_k), dtype=act.dtype, device=act.device)
         self.code, self.chunks, self.chunk_k, self.cols = code, chunks, chunk_k, cols
         capi.transpose_chunks(act.data_ptr(), code, n_rows, cols, act.shape[1], chunks, chunk_k,
-                              self.data.data_ptr(), _stream())
+                              self.data.data_ptr(), _stream(), out_rows_per_chunk=rows)
 
 
 def weight_grad_512(dz_t: ChunkedTranspose, act_t: ChunkedTranspose, precision: str, out: torch.Tensor,
@@ -308,13 +312,23 @@ class SageTrainFunction(torch.autograd.Function):
         enc = model.node_encoder
         dx0 = dcur.data
         with engine.TIMERS.span("train_encoder_bwd"):
-            w3 = enc[4].weight.detach().float().contiguous()
+            w3 = enc[4].weight.detach().float().contiguous()          # [512, 128]
             w2 = enc[2].weight.detach().float().contiguous()
             dw3e, _ = gbuf(enc[4].weight); db3e, _ = gbuf(enc[4].bias)
-            sgemm(dx0, code, 1, 512, sv.h2.data, code, 128, 1, 512, 128, n, dw3e, F32, 128)
+            # dW3 = dx0^T h2 (reduction over nodes) on the split-K tensor-core path, h2 padded to 512 columns
+            chunks0, chunk_k0 = split_k_layout(n)
+            tmp = _f32((512, 512), dev)
+            weight_grad_512(ChunkedTranspose(dx0, code, n, chunks0, chunk_k0),
+                            ChunkedTranspose(sv.h2.data, code, n, chunks0, chunk_k0, pad_rows=512), prec, tmp, False)
+            dw3e.copy_(tmp[:, :128])
             colsum(dx0, code, n, 512, 512, db3e)
+            # dh2 = (dx0 W3) [h2 > 0]: W3^T zero-padded to 512 output rows on the tensor cores, then mask + narrow
+            w3t_pad = torch.zeros((512, 512), dtype=torch.float32, device=dev)
+            capi.transpose_chunks(w3.data_ptr(), F32, 512, 128, 128, 1, 512, w3t_pad.data_ptr(), s)
+            full = Activation(n, 512, prec, dev)
+            engine.gemm512(engine._segments(dcur, engine.pack_linear(w3t_pad, prec)), n, prec, full)
             dh2 = _f32((n, 128), dev)
-            sgemm(dx0, code, 512, 1, w3, F32, 128, 1, n, 128, 512, dh2, F32, 128, mask=sv.h2.data, mask_code=code, mask_ld=128)
+            capi.mask_narrow(full.data.data_ptr(), code, 512, sv.h2.data.data_ptr(), code, 128, n, 128, dh2.data_ptr(), s)
             dw2e, _ = gbuf(enc[2].weight); db2e, _ = gbuf(enc[2].bias)
             sgemm(dh2, F32, 1, 128, sv.h1, F32, 64, 1, 128, 64, n, dw2e, F32, 64)
             colsum(dh2, F32, n, 128, 128, db2e)

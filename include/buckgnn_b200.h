@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 3
+#define BG_ABI_VERSION 4
 
 typedef enum bg_status {
   BG_OK = 0,
@@ -256,9 +256,15 @@ int bg_sage_backward_rows(const void* u, const void* dy, const void* dy2, const 
                           void* workspace, size_t workspace_bytes, void* stream);
 /* Split-K operand layout for the weight gradients: out[s][c][j] = in[s*chunk_k + j][c] (0 beyond n_rows), i.e.
  * n_chunks K-major [n_cols, chunk_k] matrices; n_cols and chunk_k multiples of 32, n_chunks*chunk_k >= n_rows.
+ * out_rows_per_chunk (0 = n_cols) > n_cols places chunk s at row s*out_rows_per_chunk of out (a narrow matrix
+ * padded to 512 rows per chunk; the caller zero-fills out first).
  * bg_reduce_partials: out[i] (+)= sum_s partial[s][i]. */
 int bg_transpose_chunks(const void* in, int dtype, int64_t n_rows, int32_t n_cols, int64_t ld, int32_t n_chunks,
-                        int64_t chunk_k, void* out, void* stream);
+                        int64_t chunk_k, int32_t out_rows_per_chunk, void* out, void* stream);
+/* out[m, n] (f32, contiguous [M, n_cols]) = in[m, n] * [mask[m, n] > 0] (mask nullable): ReLU backward while
+ * narrowing the [M, 512] output of a zero-padded bg_gemm512 to its n_cols real columns (encoder gradients). */
+int bg_mask_narrow(const void* in, int in_dtype, int64_t ld_in, const void* mask, int mask_dtype, int64_t ld_mask,
+                   int64_t m, int32_t n_cols, float* out, void* stream);
 int bg_reduce_partials(const float* partial, int32_t n_chunks, int64_t n, float* out, int accumulate, void* stream);
 /* out[c] (+)= sum_r in[r, c]  (bias gradients). */
 int bg_colsum_workspace_bytes(int64_t rows, int32_t cols, size_t* bytes_host);
