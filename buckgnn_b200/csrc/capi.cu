@@ -255,7 +255,7 @@ int bg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int key_row,
   BG_CUDA_OK(cudaMemsetAsync(w.deg, 0, sizeof(int32_t) * (size_t)(N + 1), stream));
   if ((hub_lo != nullptr) != (hub_of_row != nullptr)) return fail(BG_ERR_INVALID, "bg_csr_build: hub_lo and hub_of_row go together");
   BG_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t) * 2, stream));
-  BG_CUDA_OK(cudaMemsetAsync(info + 4, 0, sizeof(int32_t) * 2, stream));
+  BG_CUDA_OK(cudaMemsetAsync(info + 4, 0, sizeof(int32_t) * 3, stream));
   BG_CUDA_OK(cudaMemsetAsync(rowptr, 0, sizeof(int32_t), stream));           // covers N == 0
   if (hub_of_row && N > 0) BG_CUDA_OK(cudaMemsetAsync(hub_of_row, 0xff, sizeof(int32_t) * (size_t)N, stream));
   if (N == 0) return BG_OK;

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(1024) k_scan_apply(const int32_t* __restrict__
         if (slot < max_big) big_rows[slot] = (int32_t)(base + i);
         atomicMax(&info[5], d[i]);
       }
+      if (d[i] == 0) atomicOr(&info[6], 1);               // some row has no entries (isolated node)
       run += d[i];
       if (base + i == N - 1) rowptr[N] = run;
     }

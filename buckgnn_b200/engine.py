@@ -102,8 +102,8 @@ def LAUNCHES_PER_FORWARD(num_layers: int, folded: bool = True) -> int:
     2 sorts) + batch_info + publish_words + graph_ptr + encoder front 1 (+ encoder GEMM when layer 0 is not folded;
     + row indicator when it is) + per layer (aggregate rows + hubs + GEMM) + pool 2.
     (memsets and the 16-byte info read-back are not counted.)"""
-    if folded:
-        return 7 + 3 + 1 + 1 + 3 * num_layers + 2
+    if folded:                          # (the row-indicator kernel is skipped when no node is isolated)
+        return 7 + 3 + 1 + 3 * num_layers + 2
     return 7 + 3 + 2 + 3 * num_layers + 2
 
 
@@ -134,6 +134,7 @@ class GraphIndex:
     hub_lo: Optional[torch.Tensor] = None
     hub_of_row: Optional[torch.Tensor] = None
     hub_max_degree: int = 0
+    has_empty_rows: bool = True          # some node has no CSR entries (bg_csr_build info[6])
 
 
 class PendingGraphIndex:
@@ -201,7 +202,7 @@ class PendingGraphIndex:
         ranges = n_big > 0 and host[4] == 0
         return GraphIndex(N, E, self.rowptr, self.col, self.perm, self.big_rows, n_big, graph_ptr, n_graphs,
                           hub_lo=self.hub_lo if ranges else None, hub_of_row=self.hub_of_row if ranges else None,
-                          hub_max_degree=host[5] if ranges else 0)
+                          hub_max_degree=host[5] if ranges else 0, has_empty_rows=bool(host[6]) or N == 0)
 
 
 def begin_graph_index(edge_index: torch.Tensor, batch: Optional[torch.Tensor], n_nodes: int,
@@ -348,6 +349,7 @@ class FoldedLayer0Pack:
     bn_scale: Optional[torch.Tensor]
     bn_shift: Optional[torch.Tensor]
     as_count: bool
+    bias_all_gated: Optional[torch.Tensor] = None   # HOST f32 [512]: bias + W_l b3, valid when every row's gate is 1
 
 
 def pack_folded_layer0(enc_last: torch.nn.Linear, conv, bn, aggr: str, precision: str) -> FoldedLayer0Pack:
@@ -359,7 +361,8 @@ def pack_folded_layer0(enc_last: torch.nn.Linear, conv, bn, aggr: str, precision
     gate = torch.cat([(Wl @ b3)[:, None], torch.zeros(512, 63, dtype=torch.float64)], 1)
     scale, shift = fold_batchnorm(bn) if bn is not None else (None, None)
     return FoldedLayer0Pack(lp(Wl @ W3), lp(Wr @ W3), lp(gate), (Wr @ b3 + bl).to(torch.float32).contiguous(),
-                            scale, shift, aggr in ("sum", "add"))
+                            scale, shift, aggr in ("sum", "add"),
+                            bias_all_gated=(Wr @ b3 + bl + Wl @ b3).to(torch.float32).contiguous())
 
 
 def sage_layer0_folded(h: "Activation", out: "Activation", idx: GraphIndex, w: FoldedLayer0Pack, *, aggr: str,
@@ -367,13 +370,18 @@ def sage_layer0_folded(h: "Activation", out: "Activation", idx: GraphIndex, w: F
     n = idx.n_nodes
     mh = Activation(n, 128, h.precision, h.data.device)
     aggregate(h, mh, idx, aggr)
-    ind = Activation(n, 64, h.precision, h.data.device)
-    capi.expand_rowptr(idx.rowptr.data_ptr(), n, idx.n_edges, None, None, ind.data.data_ptr(), ind.code, _stream(),
-                       as_count=w.as_count)
-    ind.refresh_split()
-    segs = _segments(mh, w.wl3) + _segments(h, w.wr3) + _segments(ind, w.wgate)[:2]
+    segs = _segments(mh, w.wl3) + _segments(h, w.wr3)
+    bias = w.bias
+    if not w.as_count and not idx.has_empty_rows:
+        bias = w.bias_all_gated          # mean aggregation, every node has a neighbour: the gate is 1 on every row
+    else:
+        ind = Activation(n, 64, h.precision, h.data.device)
+        capi.expand_rowptr(idx.rowptr.data_ptr(), n, idx.n_edges, None, None, ind.data.data_ptr(), ind.code, _stream(),
+                           as_count=w.as_count)
+        ind.refresh_split()
+        segs = segs + _segments(ind, w.wgate)[:2]
     with TIMERS.span("sage_update0"):
-        gemm512(segs, n, h.precision, out, cta_group=cta_group, bias=w.bias.data_ptr(), bn_scale=_p(w.bn_scale),
+        gemm512(segs, n, h.precision, out, cta_group=cta_group, bias=bias.data_ptr(), bn_scale=_p(w.bn_scale),
                 bn_shift=_p(w.bn_shift), normalize=normalize, relu=relu)
 
 

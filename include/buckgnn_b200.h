@@ -72,6 +72,7 @@ int bg_watchdog_info_host(uint32_t* out4_host);
  *    info[1] : number of big rows
  *    info[4] : number of big rows that are NOT "range hubs" (see below) or whose ranges overlap
  *    info[5] : largest big-row degree
+ *    info[6] : 1 if any row has no entries (a node without in-edges), else 0
  * (info has 8 words; bg_batch_info conventionally writes words 2-3 of the same buffer.)
  * big_rows must hold bg_csr_max_big_rows(E) entries.  E, N < 2^31.
  * hub_lo [bg_csr_max_big_rows(E)] and hub_of_row [N] (optional, both or neither): a big row whose

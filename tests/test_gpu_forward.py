@@ -220,3 +220,19 @@ def test_node_level_heads(prediction_type, use_z, use_rot, pooling, model_name, 
     err = ((got.cpu().double() - want.double()).norm() / want.double().norm()).item()
     assert err < 2e-3, err
     assert (got.cpu() - want).abs().max().item() < 2e-3 * want.abs().max().item() + 1e-4
+
+
+@pytest.mark.parametrize("name", ["GraphSage_meanAggr", "GraphSage_sumAggr"])
+def test_folded_layer0_with_isolated_nodes(name):
+    """Nodes without in-edges: the folded first layer must apply the encoder bias term W_l b3 only to rows with
+    neighbours (the row-indicator GEMM segment); without isolated nodes that segment is skipped and the term is
+    part of the bias."""
+    ref, ours = _pair(name, "fp32", layers=2)
+    from buckgnn_b200.synth import PlateBatch
+    b = make_batch(3, nx=10, ny=8)
+    keep = ~torch.isin(b.edge_index[1], torch.tensor([0, 17, 95, 200]))        # these nodes lose all in-edges
+    bi = PlateBatch(b.x, b.edge_index[:, keep].contiguous(), b.edge_attr[keep].contiguous(), b.batch, b.y, b.ptr, b.num_graphs)
+    got, want = _run(ref, ours, bi)
+    _assert_rel(got, want, 1e-4)
+    got2, want2 = _run(ref, ours, b)                                          # no isolated node: gate folded into the bias
+    _assert_rel(got2, want2, 1e-4)
