@@ -69,18 +69,21 @@ def _traffic_from_profile(name_part: str, exclude: str = ""):
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
+    """Samples nvidia-smi SM clocks / throttle reasons.  Started BEFORE the warm-up (nvidia-smi takes a while to
+    come up); `begin()` / `end()` bracket the timed region and only samples that arrived inside it are summarised
+    (if the region was shorter than the sampling period, the sample nearest to it is used and flagged)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
         "clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -88,9 +91,20 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def wait_ready(self, timeout: float = 5.0):
+        t = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t < timeout:
+            time.sleep(0.01)
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
@@ -101,9 +115,16 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
+        rows = self.rows
+        inside = [r for t, r in rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+        how = "inside the timed region"
+        if not inside and rows and self.t0 is not None:
+            mid = 0.5 * (self.t0 + (self.t1 or self.t0))
+            inside = [min(rows, key=lambda tr: abs(tr[0] - mid))[1]]
+            how = "nearest sample (timed region shorter than the sampling period)"
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
             except (ValueError, IndexError):
@@ -113,7 +134,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sampled": how}
 
 
 def _oracle_model():
@@ -207,17 +228,20 @@ def run_b200(args):
     rel_err = ((got - want).abs() / want.abs().clamp(min=1e-3)).max().item()
 
     # ---- device-resident timing (the `value`)
-    for _ in range(args.warmup):
-        fwd(resident)
-    barrier()
-    engine.TIMERS.enable()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
+        for _ in range(args.warmup):
+            fwd(resident)
+        clk.wait_ready()
+        barrier()
+        engine.TIMERS.enable()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clk.begin()
         ev0.record()
         for _ in range(args.steps):
             pred = fwd(resident)
         ev1.record()
         barrier()
+        clk.end()
     step_ms = ev0.elapsed_time(ev1) / args.steps
     kernel_ms = engine.TIMERS.summary()          # per kernel class: total ms, calls
     engine.TIMERS.disable()

@@ -132,6 +132,28 @@ struct BnVectors {          // [512] f32 each, device
   float* invstd;
 };
 
+// column c of the [n_parts][2][512] partials, summed in fp64 in a fixed order: eight interleaved chains (the loads of
+// one chain of ~300 would each wait for the previous add: 40 us per finalize kernel), combined at the end
+BG_DEVINL void sum_partials(const float* __restrict__ partial, int n_parts, int c, double& s1, double& s2) {
+  double a1[8], a2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a1[k] = a2[k] = 0.0;
+  int p = 0;
+  for (; p + 8 <= n_parts; p += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a1[k] += (double)partial[(size_t)(p + k) * 2 * kHidden + c];
+      a2[k] += (double)partial[(size_t)(p + k) * 2 * kHidden + kHidden + c];
+    }
+  }
+  for (int k = 0; p < n_parts; ++p, ++k) {
+    a1[k] += (double)partial[(size_t)p * 2 * kHidden + c];
+    a2[k] += (double)partial[(size_t)p * 2 * kHidden + kHidden + c];
+  }
+  s1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
+  s2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + ((a2[4] + a2[5]) + (a2[6] + a2[7]));
+}
+
 // 1 CTA x 512 threads.  Batch mean / biased variance -> a, shift, mean, invstd; running statistics updated
 // as torch.nn.BatchNorm1d does in train mode (momentum, unbiased variance) -- Models/BuckGNN.py:163,451.
 __global__ void __launch_bounds__(kHidden)
@@ -139,11 +161,8 @@ k_bn_fwd_finalize(const float* __restrict__ partial, int n_parts, int64_t N, con
                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
                   float* __restrict__ running_var, long long* __restrict__ num_batches_tracked, BnVectors out) {
   const int c = threadIdx.x;
-  double s1 = 0.0, s2 = 0.0;
-  for (int p = 0; p < n_parts; ++p) {
-    s1 += (double)partial[(size_t)p * 2 * kHidden + c];
-    s2 += (double)partial[(size_t)p * 2 * kHidden + kHidden + c];
-  }
+  double s1, s2;
+  sum_partials(partial, n_parts, c, s1, s2);
   const double mean = s1 / (double)N;
   double var = s2 / (double)N - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -168,11 +187,8 @@ k_bn_bwd_finalize(const float* __restrict__ partial, int n_parts, int64_t N, con
                   float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                   float* __restrict__ k0, float* __restrict__ k1) {
   const int c = threadIdx.x;
-  double s1 = 0.0, s2 = 0.0;
-  for (int p = 0; p < n_parts; ++p) {
-    s1 += (double)partial[(size_t)p * 2 * kHidden + c];
-    s2 += (double)partial[(size_t)p * 2 * kHidden + kHidden + c];
-  }
+  double s1, s2;
+  sum_partials(partial, n_parts, c, s1, s2);
   const double mean = bn.mean[c], invstd = bn.invstd[c], av = bn.a[c];
   const double dg = invstd * (s2 - mean * s1);
   if (accumulate) { dgamma[c] += (float)dg; dbeta[c] += (float)s1; }

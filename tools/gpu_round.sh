@@ -8,4 +8,12 @@ run smoke python __graft_entry__.py --smoke
 run bench python bench.py --steps 10 --warmup 3
 run bench_train python tools/bench_train.py --steps 10 --warmup 3
 run bench_train_bf16 python tools/bench_train.py --steps 10 --warmup 3 --precision bf16
-if [ "$1" != "noprof" ]; then bash tools/profile.sh; fi
+TAILN=3 run bench_configs python tools/bench_configs.py
+if [ "$1" != "noprof" ]; then
+  bash tools/profile.sh
+  # launch list of training steps (cfg 4): two steps after three warm-up steps, skipping the warm-up launches
+  TRAIN="python tools/bench_train.py --steps 2 --warmup 3"
+  $TRAIN > gpurun_out/train_plain.log 2>&1 &&
+  ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 700 --csv --log-file gpurun_out/train_launches.csv $TRAIN > gpurun_out/ncu_train.log 2>&1
+  echo "train launch list exit $?"
+fi

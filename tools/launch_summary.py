@@ -21,7 +21,9 @@ def main(path):
         seq.append((re.sub(r"\(.*", "", d["Kernel Name"])[:60], val))
     starts = [i for i, (n, _) in enumerate(seq) if "k_csr_hist" in n]
     print(f"launches captured: {len(seq)}; forwards seen: {len(starts)}")
-    if len(starts) < 2:
+    if "--all" in sys.argv:                      # everything captured (e.g. whole training steps)
+        fwd = seq
+    elif len(starts) < 2:
         fwd = seq[starts[-1]:] if starts else seq
     else:
         fwd = seq[starts[-2]:starts[-1]]
@@ -34,7 +36,7 @@ def main(path):
     print(f"{'kernel':62s} {'n':>3s} {'ms':>9s} {'share':>7s}")
     for n, (v, c) in agg.items():
         print(f"{n:62s} {c:3d} {v:9.3f} {100 * v / tot:6.1f}%")
-    print(f"{'one forward, sum of kernel durations':62s} {len(fwd):3d} {tot:9.3f}")
+    print(f"{'sum of kernel durations':62s} {len(fwd):3d} {tot:9.3f}")
 
 
 if __name__ == "__main__":
