@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     "bg_csr_max_big_rows", "bg_csr_workspace_bytes", "bg_csr_build",
     "bg_batch_info", "bg_graph_ptr_build", "bg_publish_words", "bg_encoder_front",
     "bg_aggregate_workspace_bytes", "bg_hubfold_workspace_bytes", "bg_sage_aggregate", "bg_gemm512",
-    "bg_pool_workspace_bytes", "bg_pool_head", "bg_cast_f32", "bg_split_tf32",
+    "bg_wgrad512", "bg_pool_workspace_bytes", "bg_pool_head", "bg_cast_f32", "bg_split_tf32",
     "bg_expand_rowptr", "bg_add",
     "bg_train_workspace_bytes", "bg_bn_batch_stats", "bg_bn_act_forward", "bg_sage_backward_rows",
     "bg_transpose_chunks", "bg_mask_narrow", "bg_reduce_partials", "bg_colsum_workspace_bytes", "bg_colsum", "bg_pool_backward",
@@ -80,6 +80,7 @@ _SIGNATURES = {
                                     C.c_size_t, _P]),
     "bg_gemm512": (C.c_int, [C.POINTER(GemmSegment), _I32, _I64, C.c_int, C.c_int, C.POINTER(Epilogue), _P,
                              C.c_int, _I64, C.c_int, _P]),
+    "bg_wgrad512": (C.c_int, [_P, _I64, _P, _I32, _I64, C.c_int, _I64, _I32, _I64, _P, _P]),
     "bg_pool_workspace_bytes": (C.c_int, [_I64, _SZP]),
     "bg_pool_head": (C.c_int, [_P, C.c_int, _I64, _P, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P,
                                _P, C.c_size_t, _P]),
@@ -325,3 +326,8 @@ def collate(x_all, n_features, ei_all, e_all, ea_all, n_edge_features, y_all, se
     _check(load().bg_collate(x_all, n_features, ei_all, e_all, ea_all, n_edge_features, y_all, sel, n_graphs, node_ptr,
                              edge_ptr, out_node_ptr, out_edge_ptr, n_out, e_out, x, edge_index, edge_attr, batch, y,
                              stream), "bg_collate")
+
+
+def wgrad512(dz, ld_dz, act, act_cols, ld_act, dtype, n_rows, n_chunks, chunk_k, partial, stream):
+    _check(load().bg_wgrad512(dz, ld_dz, act, act_cols, ld_act, dtype, n_rows, n_chunks, chunk_k, partial, stream),
+           "bg_wgrad512")

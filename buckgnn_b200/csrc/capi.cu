@@ -490,6 +490,40 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
 #undef BG_GEMM_OUT
 }
 
+int bg_wgrad512(const void* dz, int64_t ld_dz, const void* act, int32_t act_cols, int64_t ld_act, int dtype, int64_t n_rows,
+                int32_t n_chunks, int64_t chunk_k, float* partial, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int fmt = umma_format_of(dtype);
+  if (fmt != 0 && fmt != 1)
+    return fail(BG_ERR_UNSUPPORTED, "bg_wgrad512: bf16 / f16 operands only (tf32 MN-major operands need the 32-byte-atom "
+                                    "swizzle; use bg_transpose_chunks + bg_gemm512 for f32)");
+  if (act_cols <= 0 || act_cols > kHidden || act_cols % 8 != 0) return fail(BG_ERR_INVALID, "bg_wgrad512: act_cols must be a multiple of 8 in (0, 512]");
+  const int esz = fmt == 2 ? 4 : 2;
+  const int kblk = kStageKBytes / esz;                     // nodes per pipeline stage: 64 (16-bit) / 32 (tf32)
+  if (n_rows <= 0 || n_chunks <= 0 || chunk_k <= 0 || chunk_k % kblk != 0 || (int64_t)n_chunks * chunk_k < n_rows ||
+      (int64_t)n_chunks * chunk_k >= 0x7fffffffLL)
+    return fail(BG_ERR_INVALID, "bg_wgrad512: chunk_k must be a multiple of 64 (16-bit) / 32 (tf32) and n_chunks*chunk_k >= n_rows");
+  if (!dz || !act || !partial || !aligned16(dz) || !aligned16(act) || !aligned16(partial) || ld_dz < kHidden ||
+      ld_act < act_cols || (ld_dz * esz) % 16 != 0 || (ld_act * esz) % 16 != 0)
+    return fail(BG_ERR_INVALID, "bg_wgrad512: bad pointer / leading dimension");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = make_mn_operand_map(&p.seg[0].a, dz, n_rows, kHidden, ld_dz, (uint32_t)fmt, kblk);
+  if (rc == BG_OK) rc = make_mn_operand_map(&p.seg[0].b, act, n_rows, act_cols, ld_act, (uint32_t)fmt, kblk);
+  if (rc != BG_OK) return fail(rc, "bg_wgrad512: cuTensorMapEncodeTiled failed");
+  p.n_seg = 1;
+  p.kblocks[0] = (int32_t)(chunk_k / kblk);
+  p.k_elems_per_block = kblk;
+  p.a_fmt = p.b_fmt = (uint32_t)fmt;
+  p.mn_major = 1;
+  p.chunk_k = chunk_k;
+  p.n_tiles = 2 * n_chunks;
+  p.m = (int64_t)n_chunks * kHidden;
+  for (int i = 0; i < kHidden; ++i) { p.bias[i] = 0.f; p.scale[i] = 1.f; p.shift[i] = 0.f; }
+  p.out = partial; p.ldo = kHidden;
+  return launch_gemm512<2, float, kAddNone, false>(p, stream);
+}
+
 // ------------------------------------------------------------------ K4
 int bg_pool_workspace_bytes(int64_t G, size_t* bytes_host) {
   if (!bytes_host || G < 0) return fail(BG_ERR_INVALID, "bg_pool_workspace_bytes: bad argument");

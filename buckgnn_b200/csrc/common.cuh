@@ -278,6 +278,19 @@ BG_DEVINL uint64_t umma_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major, 128-byte-swizzled operand tile as TMA lays it down from a row-major [K rows, MN cols] matrix: boxes of
+// {128 B of MN, kb rows of K}; a K row is 128 B, 8-row K groups are 1024 B apart (SBO), the next 128 B of MN is the
+// next box, `lbo_bytes` = kb * 128 further (LBO).  (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units, mma_traits_sm100.hpp.)
+BG_DEVINL uint64_t umma_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // instruction descriptor: fp32 accumulate, A/B both K-major; operand format 0 = f16, 1 = bf16, 2 = tf32
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t a_fmt, uint32_t b_fmt, uint32_t m, uint32_t n) {
   return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);

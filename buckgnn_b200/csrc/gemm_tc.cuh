@@ -82,7 +82,11 @@ struct alignas(64) GemmParams {
   int64_t gather_ld;
   float* inv_norm_out;              // [M] f32 or null: 1 / max(|row|, eps) of normalized rows (saved for the backward pass)
   int32_t b_group_tiles;            // 0: one B for all rows; t: row tile i multiplies B rows [(i / t) * 512, +512)
-  int32_t pad_;
+  int32_t mn_major;                 // 1: weight-gradient mode.  seg[0].a / .b map the ROW-MAJOR [n_rows, 512] matrices
+                                    // dz and act; out[(s*512 + o), i] = sum over the nodes of chunk s of dz[n,o] act[n,i]:
+                                    // both operands are MN-major (the reduction runs over matrix rows), so no
+                                    // transposed copies are needed.  Tile t = (chunk t/2, output rows (t%2)*256..+256).
+  int64_t chunk_k;                  // nodes per chunk (mn_major)
   float bias[kHidden];              // epilogue vectors by value -> constant bank, broadcast reads
   float scale[kHidden];             // 1 when there is no BN
   float shift[kHidden];             // 0 when there is no BN
@@ -495,6 +499,31 @@ k_gemm512(const __grid_constant__ GemmParams p) {
         for (int tile = tile0; tile < p.n_tiles; tile += tile_stride) {
           const int32_t row0 = tile * (kTileM * kCg) + (int32_t)rank * kTileM;
           const int32_t brow0 = p.b_group_tiles ? (tile / p.b_group_tiles) * kHidden : 0;   // split-K groups
+          if (kCg == 2 && p.mn_major) {
+            const void* map_a = &p.seg[0].a;
+            const void* map_b = &p.seg[0].b;
+            const int32_t cols_per_box = p.k_elems_per_block == 64 ? 64 : 32;       // 128 B of the MN dimension
+            const int32_t boxes = 128 / cols_per_box;                                 // boxes per 128 MN values
+            const uint32_t box_bytes = (uint32_t)p.k_elems_per_block * 128u;
+            const int32_t a_col0 = (tile & 1) * 256 + (int32_t)rank * 128;
+            const int64_t node_base = (int64_t)(tile >> 1) * p.chunk_k;
+            for (int kb = 0; kb < p.kblocks[0]; ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u, kTagEmpty);
+              const uint32_t sa = stages_u32 + stage * Cfg::kStageBytes;
+              const uint32_t sb = sa + kATileBytes;
+              const int32_t node0 = (int32_t)(node_base + (int64_t)kb * p.k_elems_per_block);
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+              else mbar_arrive_cluster(full_bar(stage), 0);
+              for (int j = 0; j < boxes; ++j)
+                tma_load_2d_cg2(sa + j * box_bytes, map_a, full_bar(stage), a_col0 + j * cols_per_box, node0);
+              for (int h = 0; h < 2; ++h)
+                for (int j = 0; j < boxes; ++j)
+                  tma_load_2d_cg2(sb + h * (Cfg::kBTileBytes / 2) + j * box_bytes, map_b, full_bar(stage),
+                                  h * 256 + (int32_t)rank * 128 + j * cols_per_box, node0);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+            continue;
+          }
           for (int s = 0; s < p.n_seg; ++s) {
             const void* map_a = &p.seg[s].a;
             const void* map_b = &p.seg[s].b;
@@ -528,8 +557,10 @@ k_gemm512(const __grid_constant__ GemmParams p) {
       __syncwarp();
     } else if (warp == 1 && rank == 0) {
       // ================================================================ MMA issuer (leader CTA)
-      const uint32_t idesc = umma_idesc(p.a_fmt, p.b_fmt, kTileM * kCg, 256);
+      const uint32_t idesc = umma_idesc(p.a_fmt, p.b_fmt, kTileM * kCg, 256) | (p.mn_major ? (3u << 15) : 0u);   // a_major, b_major
       const bool tf32 = p.a_fmt == 2;
+      const uint32_t mn_lbo = (uint32_t)p.k_elems_per_block * 128u;       // bytes between 128-byte MN column blocks
+      const uint32_t mn_kstep = tf32 ? 1024u : 2048u;                     // one UMMA K step = 8 / 16 K rows of 128 B
       BG_PROF_DECL
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = tile0; tile < p.n_tiles; tile += tile_stride, ++it) {
@@ -550,10 +581,11 @@ k_gemm512(const __grid_constant__ GemmParams p) {
               const uint32_t sb = sa + kATileBytes;
 #pragma unroll
               for (int k = 0; k < kStageKBytes / 32; ++k) {
-                const uint64_t da = umma_smem_desc(sa + k * 32);
+                const uint64_t da = p.mn_major ? umma_smem_desc_mn(sa + k * mn_kstep, mn_lbo) : umma_smem_desc(sa + k * 32);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                  const uint64_t db = umma_smem_desc(sb + h * (Cfg::kBTileBytes / 2) + k * 32);
+                  const uint64_t db = p.mn_major ? umma_smem_desc_mn(sb + h * (Cfg::kBTileBytes / 2) + k * mn_kstep, mn_lbo)
+                                                 : umma_smem_desc(sb + h * (Cfg::kBTileBytes / 2) + k * 32);
                   const uint32_t acc = (first && k == 0) ? 0u : 1u;
                   if (tf32) umma<kCg, true>(tmem_base + h * 256, da, db, idesc, acc);
                   else umma<kCg, false>(tmem_base + h * 256, da, db, idesc, acc);
@@ -616,6 +648,25 @@ static inline int make_operand_map(CUtensorMap* map, const void* base, int64_t r
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? BG_OK : BG_ERR_CUDA;
+}
+
+// [n_rows, 512] row-major matrix read as an MN-major operand: box = 128 B of columns x `kblk` rows, 128B swizzle,
+// rows beyond n_rows read as zero (the node dimension needs no padding)
+static inline int make_mn_operand_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                      uint32_t fmt, int kblk) {
+  PFN_tensorMapEncodeTiled enc = get_tensor_map_encoder();
+  if (!enc) return BG_ERR_CUDA;
+  const bool tf32 = fmt == 2;
+  const int esz = tf32 ? 4 : 2;
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                      : (fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  cuuint64_t dims[2] = {(cuuint64_t)n_cols, (cuuint64_t)n_rows};     // columns beyond n_cols read as zero too
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)kblk};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? BG_OK : BG_ERR_CUDA;
 }
 

@@ -97,6 +97,17 @@ def weight_grad_512(dz_t: ChunkedTranspose, act_t: ChunkedTranspose, precision: 
     capi.reduce_partials(partial.data_ptr(), s, 512 * 512, out.data_ptr(), accumulate, _stream())
 
 
+def weight_grad_mn(dz: torch.Tensor, act: torch.Tensor, code: int, n_rows: int, out: torch.Tensor, accumulate: bool) -> None:
+    """out[o, i] (+)= sum_n dz[n, o] act[n, i], dz [n, 512] and act [n, <= 512] read in place as MN-major tcgen05
+    operands (bg_wgrad512, 16-bit formats): no transposed copies.  `out` is [512, 512] f32."""
+    chunks, chunk_k = split_k_layout(n_rows)
+    partial = _f32((chunks * 512, 512), out.device)
+    with engine.TIMERS.span("train_wgrad_gemm"):
+        capi.wgrad512(dz.data_ptr(), dz.shape[1], act.data_ptr(), act.shape[1], act.shape[1], code, n_rows, chunks,
+                      chunk_k, partial.data_ptr(), _stream())
+    capi.reduce_partials(partial.data_ptr(), chunks, 512 * 512, out.data_ptr(), accumulate, _stream())
+
+
 def transposed_pack(weight: torch.Tensor, precision: str) -> engine.LinearPack:
     """W^T in operand format: the B operand of dX = dZ W (rows = input features)."""
     w = weight.detach().to(torch.float32).contiguous()
@@ -287,14 +298,18 @@ class SageTrainFunction(torch.autograd.Function):
                 dzs.refresh_split()
             # weight gradients: split-K over nodes on the tensor cores
             with engine.TIMERS.span("train_wgrad"):
-                dz_t = ChunkedTranspose(dz.data, code, n, chunks, chunk_k)
                 dwl, acc_l = gbuf(conv.lin_l.weight)
-                weight_grad_512(dz_t, ChunkedTranspose(agg.data, code, n, chunks, chunk_k), prec, dwl, acc_l)
                 dwr, acc_r = gbuf(conv.lin_r.weight)
-                weight_grad_512(dz_t, ChunkedTranspose(x_in.data, code, n, chunks, chunk_k), prec, dwr, acc_r)
+                if code != capi.BG_F32:          # 16-bit: MN-major operands, read where they lie
+                    weight_grad_mn(dz.data, agg.data, code, n, dwl, acc_l)
+                    weight_grad_mn(dz.data, x_in.data, code, n, dwr, acc_r)
+                else:                            # tf32: node dimension made contiguous first
+                    dz_t = ChunkedTranspose(dz.data, code, n, chunks, chunk_k)
+                    weight_grad_512(dz_t, ChunkedTranspose(agg.data, code, n, chunks, chunk_k), prec, dwl, acc_l)
+                    weight_grad_512(dz_t, ChunkedTranspose(x_in.data, code, n, chunks, chunk_k), prec, dwr, acc_r)
+                    del dz_t
                 dbl, acc_b = gbuf(conv.lin_l.bias)
                 colsum(dz.data, code, n, 512, 512, dbl, accumulate=acc_b)
-                del dz_t
             # input gradient: dx = dz Wr + A^T (dz/deg Wl)  (+ g, added by the next iteration through dy2)
             if id(conv) not in tpacks:
                 tpacks[id(conv)] = (transposed_pack(conv.lin_l.weight, prec), transposed_pack(conv.lin_r.weight, prec))
@@ -318,8 +333,11 @@ class SageTrainFunction(torch.autograd.Function):
             # dW3 = dx0^T h2 (reduction over nodes) on the split-K tensor-core path, h2 padded to 512 columns
             chunks0, chunk_k0 = split_k_layout(n)
             tmp = _f32((512, 512), dev)
-            weight_grad_512(ChunkedTranspose(dx0, code, n, chunks0, chunk_k0),
-                            ChunkedTranspose(sv.h2.data, code, n, chunks0, chunk_k0, pad_rows=512), prec, tmp, False)
+            if code != capi.BG_F32:
+                weight_grad_mn(dx0, sv.h2.data, code, n, tmp, False)         # columns >= 128 of tmp come out 0
+            else:
+                weight_grad_512(ChunkedTranspose(dx0, code, n, chunks0, chunk_k0),
+                                ChunkedTranspose(sv.h2.data, code, n, chunks0, chunk_k0, pad_rows=512), prec, tmp, False)
             dw3e.copy_(tmp[:, :128])
             colsum(dx0, code, n, 512, 512, db3e)
             # dh2 = (dx0 W3) [h2 > 0]: W3^T zero-padded to 512 output rows on the tensor cores, then mask + narrow

@@ -184,6 +184,16 @@ int bg_gemm512(const bg_gemm_segment* segments_host, int32_t n_segments, int64_t
                int a_dtype, int b_dtype, const bg_epilogue* epilogue_host,
                void* out, int out_dtype, int64_t ldo, int cta_group, void* stream);
 
+/* Weight gradients of a Linear with 512 outputs, dW[o, i] = sum_n dz[n, o] * act[n, i] (autograd of lin_l / lin_r,
+ * Models/BuckGNN.py:449): the reduction runs over the ROWS of the row-major dz [n_rows, 512] and act [n_rows, act_cols]
+ * (act_cols <= 512; dW columns beyond it come out 0), i.e. both tcgen05 operands are MN-major -- TMA reads them where
+ * they lie, no transposed copies.  bf16 / f16 only (f32 = tf32 operands: bg_transpose_chunks + bg_gemm512 b_groups).
+ * Split over the nodes: chunk s covers rows [s*chunk_k, (s+1)*chunk_k) (chunk_k a multiple of 64, n_chunks*chunk_k
+ * >= n_rows, rows beyond n_rows read as zero) and writes partial[s] ([512, 512] f32); sum the chunks with
+ * bg_reduce_partials.  One 256 x 512 output tile per CTA pair: n_chunks = 37 fills a B200. */
+int bg_wgrad512(const void* dz, int64_t ld_dz, const void* act, int32_t act_cols, int64_t ld_act, int dtype,
+                int64_t n_rows, int32_t n_chunks, int64_t chunk_k, float* partial, void* stream);
+
 /* ------------------------------------------------------------------ K4: pooling + regression head
  * Replaces `get_pooling_layer` + `decoder(pooled).squeeze()` (Models/BuckGNN.py:246-307, 515-516):
  *    BG_POOL_MEAN                   pooled[g] = sum_{i in g} x[i] / max(count_g, 1)          (:274)

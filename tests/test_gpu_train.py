@@ -360,3 +360,28 @@ def test_fused_eigenvalue_loss_and_mape():
     ml, mm = crit.epoch_means()
     assert abs(ml - float(want_loss)) < 1e-5 and abs(mm - float(want_mape)) < 1e-3
     assert crit.epoch_means() == (0.0, 0.0)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("n", [100, 5000, 70001])
+def test_weight_gradient_mn_major(precision, n):
+    """bg_wgrad512: dW = dz^T act straight from the row-major matrices (MN-major tcgen05 operands)."""
+    torch.manual_seed(4)
+    dt = engine._TORCH[engine.PRECISION_FORMATS[precision][0]]
+    code = engine.PRECISION_FORMATS[precision][0]
+    dz = (torch.randn(n, 512) * 0.1).to(dt)
+    act = torch.randn(n, 512).to(dt)
+    want = dz.double().T @ act.double()
+    out = torch.full((512, 512), 3.0, device=DEV)
+    dzd, actd = dz.to(DEV), act.to(DEV)
+    train.weight_grad_mn(dzd, actd, code, n, out, accumulate=False)
+    tol = 1e-4
+    assert _rel(out.cpu(), want) < tol
+    train.weight_grad_mn(dzd, actd, code, n, out, accumulate=True)
+    assert _rel(out.cpu(), 2 * want) < tol
+    # a narrow second operand (the encoder's [n, 128] hidden layer): columns beyond it are zero
+    narrow = actd[:, :128].contiguous()
+    train.weight_grad_mn(dzd, narrow, code, n, out, accumulate=False)
+    assert _rel(out.cpu()[:, :128], want[:, :128]) < tol and float(out[:, 128:].abs().max()) == 0.0
+    with pytest.raises(capi.BuckGNNError):
+        train.weight_grad_mn(dzd.float(), actd.float(), capi.BG_F32, n, out, accumulate=False)
