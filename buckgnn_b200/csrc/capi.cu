@@ -494,9 +494,7 @@ int bg_wgrad512(const void* dz, int64_t ld_dz, const void* act, int32_t act_cols
                 int32_t n_chunks, int64_t chunk_k, float* partial, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int fmt = umma_format_of(dtype);
-  if (fmt != 0 && fmt != 1)
-    return fail(BG_ERR_UNSUPPORTED, "bg_wgrad512: bf16 / f16 operands only (tf32 MN-major operands need the 32-byte-atom "
-                                    "swizzle; use bg_transpose_chunks + bg_gemm512 for f32)");
+  if (fmt < 0) return fail(BG_ERR_INVALID, "bg_wgrad512: bad dtype");
   if (act_cols <= 0 || act_cols > kHidden || act_cols % 8 != 0) return fail(BG_ERR_INVALID, "bg_wgrad512: act_cols must be a multiple of 8 in (0, 512]");
   const int esz = fmt == 2 ? 4 : 2;
   const int kblk = kStageKBytes / esz;                     // nodes per pipeline stage: 64 (16-bit) / 32 (tf32)

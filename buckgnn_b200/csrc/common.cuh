@@ -282,13 +282,15 @@ BG_DEVINL uint64_t umma_smem_desc(uint32_t smem_addr) {
 // {128 B of MN, kb rows of K}; a K row is 128 B, 8-row K groups are 1024 B apart (SBO), the next 128 B of MN is the
 // next box, `lbo_bytes` = kb * 128 further (LBO).  (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in
 // 16-byte units, mma_traits_sm100.hpp.)
-BG_DEVINL uint64_t umma_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+// 32-bit (tf32) operands use the 32-byte-atom variant of the swizzle (TMA SWIZZLE_128B_ATOM_32B, UMMA layout type
+// SWIZZLE_128B_BASE32B = 1): K groups of 4 rows, 512 B apart.
+BG_DEVINL uint64_t umma_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, bool base32) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((base32 ? 512 : 1024) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(base32 ? 1 : 2) << 61;
   return d;
 }
 // instruction descriptor: fp32 accumulate, A/B both K-major; operand format 0 = f16, 1 = bf16, 2 = tf32

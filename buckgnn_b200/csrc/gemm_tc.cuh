@@ -581,10 +581,10 @@ k_gemm512(const __grid_constant__ GemmParams p) {
               const uint32_t sb = sa + kATileBytes;
 #pragma unroll
               for (int k = 0; k < kStageKBytes / 32; ++k) {
-                const uint64_t da = p.mn_major ? umma_smem_desc_mn(sa + k * mn_kstep, mn_lbo) : umma_smem_desc(sa + k * 32);
+                const uint64_t da = p.mn_major ? umma_smem_desc_mn(sa + k * mn_kstep, mn_lbo, tf32) : umma_smem_desc(sa + k * 32);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                  const uint64_t db = p.mn_major ? umma_smem_desc_mn(sb + h * (Cfg::kBTileBytes / 2) + k * mn_kstep, mn_lbo)
+                  const uint64_t db = p.mn_major ? umma_smem_desc_mn(sb + h * (Cfg::kBTileBytes / 2) + k * mn_kstep, mn_lbo, tf32)
                                                  : umma_smem_desc(sb + h * (Cfg::kBTileBytes / 2) + k * 32);
                   const uint32_t acc = (first && k == 0) ? 0u : 1u;
                   if (tf32) umma<kCg, true>(tmem_base + h * 256, da, db, idesc, acc);
@@ -666,7 +666,8 @@ static inline int make_mn_operand_map(CUtensorMap* map, const void* base, int64_
   cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)kblk};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   tf32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? BG_OK : BG_ERR_CUDA;
 }
 

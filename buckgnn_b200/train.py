@@ -11,7 +11,7 @@ Per layer (Models/BuckGNN.py:447-458, train mode)
               batch statistics of u -> a, shift           bg_bn_batch_stats (+ running stats, momentum)
               y = dropout(relu(a u + shift) + x_prev)     bg_bn_act_forward (counter-based mask)
     backward  dz, dgamma, dbeta                           bg_sage_backward_rows
-              dWl = dz^T agg, dWr = dz^T x                bg_transpose_chunks + bg_gemm512(b_groups) + bg_reduce_partials
+              dWl = dz^T agg, dWr = dz^T x                bg_wgrad512 (MN-major operands, split over nodes) + bg_reduce_partials
               db = colsum(dz)                             bg_colsum
               dagg = (dz / deg) Wl                        bg_gemm512 on the transposed weight
               dx = dz Wr + A^T dagg  (+ g on skip layers) bg_sage_aggregate over the CSR keyed by source + bg_gemm512
@@ -99,7 +99,7 @@ def weight_grad_512(dz_t: ChunkedTranspose, act_t: ChunkedTranspose, precision: 
 
 def weight_grad_mn(dz: torch.Tensor, act: torch.Tensor, code: int, n_rows: int, out: torch.Tensor, accumulate: bool) -> None:
     """out[o, i] (+)= sum_n dz[n, o] act[n, i], dz [n, 512] and act [n, <= 512] read in place as MN-major tcgen05
-    operands (bg_wgrad512, 16-bit formats): no transposed copies.  `out` is [512, 512] f32."""
+    operands (bg_wgrad512): no transposed copies.  `out` is [512, 512] f32."""
     chunks, chunk_k = split_k_layout(n_rows)
     partial = _f32((chunks * 512, 512), out.device)
     with engine.TIMERS.span("train_wgrad_gemm"):
@@ -268,7 +268,6 @@ class SageTrainFunction(torch.autograd.Function):
         # ---- message passing layers, last to first
         idx = sv.idx
         idx_t = engine.build_graph_index(sv.edge_index, None, n, key_row=0) if sv.layers else None   # A^T
-        chunks, chunk_k = split_k_layout(n)
         ws_bytes = capi.train_workspace_bytes(n)
         ws = _ws(ws_bytes, dev)
         tpacks = {}
@@ -300,14 +299,8 @@ class SageTrainFunction(torch.autograd.Function):
             with engine.TIMERS.span("train_wgrad"):
                 dwl, acc_l = gbuf(conv.lin_l.weight)
                 dwr, acc_r = gbuf(conv.lin_r.weight)
-                if code != capi.BG_F32:          # 16-bit: MN-major operands, read where they lie
-                    weight_grad_mn(dz.data, agg.data, code, n, dwl, acc_l)
-                    weight_grad_mn(dz.data, x_in.data, code, n, dwr, acc_r)
-                else:                            # tf32: node dimension made contiguous first
-                    dz_t = ChunkedTranspose(dz.data, code, n, chunks, chunk_k)
-                    weight_grad_512(dz_t, ChunkedTranspose(agg.data, code, n, chunks, chunk_k), prec, dwl, acc_l)
-                    weight_grad_512(dz_t, ChunkedTranspose(x_in.data, code, n, chunks, chunk_k), prec, dwr, acc_r)
-                    del dz_t
+                weight_grad_mn(dz.data, agg.data, code, n, dwl, acc_l)       # MN-major operands, read where they lie
+                weight_grad_mn(dz.data, x_in.data, code, n, dwr, acc_r)
                 dbl, acc_b = gbuf(conv.lin_l.bias)
                 colsum(dz.data, code, n, 512, 512, dbl, accumulate=acc_b)
             # input gradient: dx = dz Wr + A^T (dz/deg Wl)  (+ g, added by the next iteration through dy2)
@@ -330,14 +323,9 @@ class SageTrainFunction(torch.autograd.Function):
             w3 = enc[4].weight.detach().float().contiguous()          # [512, 128]
             w2 = enc[2].weight.detach().float().contiguous()
             dw3e, _ = gbuf(enc[4].weight); db3e, _ = gbuf(enc[4].bias)
-            # dW3 = dx0^T h2 (reduction over nodes) on the split-K tensor-core path, h2 padded to 512 columns
-            chunks0, chunk_k0 = split_k_layout(n)
+            # dW3 = dx0^T h2 (reduction over nodes) on the split-K tensor-core path
             tmp = _f32((512, 512), dev)
-            if code != capi.BG_F32:
-                weight_grad_mn(dx0, sv.h2.data, code, n, tmp, False)         # columns >= 128 of tmp come out 0
-            else:
-                weight_grad_512(ChunkedTranspose(dx0, code, n, chunks0, chunk_k0),
-                                ChunkedTranspose(sv.h2.data, code, n, chunks0, chunk_k0, pad_rows=512), prec, tmp, False)
+            weight_grad_mn(dx0, sv.h2.data, code, n, tmp, False)             # columns >= 128 of tmp come out 0
             dw3e.copy_(tmp[:, :128])
             colsum(dx0, code, n, 512, 512, db3e)
             # dh2 = (dx0 W3) [h2 > 0]: W3^T zero-padded to 512 output rows on the tensor cores, then mask + narrow

@@ -187,7 +187,7 @@ int bg_gemm512(const bg_gemm_segment* segments_host, int32_t n_segments, int64_t
 /* Weight gradients of a Linear with 512 outputs, dW[o, i] = sum_n dz[n, o] * act[n, i] (autograd of lin_l / lin_r,
  * Models/BuckGNN.py:449): the reduction runs over the ROWS of the row-major dz [n_rows, 512] and act [n_rows, act_cols]
  * (act_cols <= 512; dW columns beyond it come out 0), i.e. both tcgen05 operands are MN-major -- TMA reads them where
- * they lie, no transposed copies.  bf16 / f16 only (f32 = tf32 operands: bg_transpose_chunks + bg_gemm512 b_groups).
+ * they lie, no transposed copies (f32 = tf32 operands use the 32-byte-atom swizzle).
  * Split over the nodes: chunk s covers rows [s*chunk_k, (s+1)*chunk_k) (chunk_k a multiple of 64, n_chunks*chunk_k
  * >= n_rows, rows beyond n_rows read as zero) and writes partial[s] ([512, 512] f32); sum the chunks with
  * bg_reduce_partials.  One 256 x 512 output tile per CTA pair: n_chunks = 37 fills a B200. */

@@ -362,7 +362,7 @@ def test_fused_eigenvalue_loss_and_mape():
     assert crit.epoch_means() == (0.0, 0.0)
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "fp16"])
 @pytest.mark.parametrize("n", [100, 5000, 70001])
 def test_weight_gradient_mn_major(precision, n):
     """bg_wgrad512: dW = dz^T act straight from the row-major matrices (MN-major tcgen05 operands)."""
@@ -375,7 +375,7 @@ def test_weight_gradient_mn_major(precision, n):
     out = torch.full((512, 512), 3.0, device=DEV)
     dzd, actd = dz.to(DEV), act.to(DEV)
     train.weight_grad_mn(dzd, actd, code, n, out, accumulate=False)
-    tol = 1e-4
+    tol = 2e-3 if precision == "tf32" else 1e-4
     assert _rel(out.cpu(), want) < tol
     train.weight_grad_mn(dzd, actd, code, n, out, accumulate=True)
     assert _rel(out.cpu(), 2 * want) < tol
@@ -383,5 +383,3 @@ def test_weight_gradient_mn_major(precision, n):
     narrow = actd[:, :128].contiguous()
     train.weight_grad_mn(dzd, narrow, code, n, out, accumulate=False)
     assert _rel(out.cpu()[:, :128], want[:, :128]) < tol and float(out[:, 128:].abs().max()) == 0.0
-    with pytest.raises(capi.BuckGNNError):
-        train.weight_grad_mn(dzd.float(), actd.float(), capi.BG_F32, n, out, accumulate=False)
