@@ -47,6 +47,38 @@ def test_size_queries_and_argument_errors_without_gpu(lib):
         capi.csr_build(None, 10, 10, 7, None, None, None, None, None, None, 0, None)
 
 
+def test_training_and_collate_entry_points_validate_arguments_without_gpu(lib):
+    """Every argument check below happens before the first CUDA call (status -1 / -3 / -4, never a crash)."""
+    assert capi.train_workspace_bytes(1000) > 0
+    assert capi.colsum_workspace_bytes(1000, 512) >= 512 * 4
+    assert capi.sgemm_workspace_bytes(64, 64, 1000) >= 64 * 64 * 4
+    assert capi.hubfold_workspace_bytes(100000, capi.BG_F16, 16, 6000) >= capi.aggregate_workspace_bytes(16)
+    bad = [
+        lambda: capi.bn_batch_stats(None, capi.BG_F32, 0, None, None, 1e-5, 0.1, None, None, None, None, None, None, None, None, 0, None),
+        lambda: capi.bn_act_forward(None, None, None, capi.BG_F32, 10, None, None, 1.5, 0, None),          # dropout_p >= 1
+        lambda: capi.sage_backward_rows(None, None, None, None, None, capi.BG_F32, 0, None, None, None, None, 0.0, 0,
+                                        None, None, False, None, None, None, None, 0, None),
+        lambda: capi.transpose_chunks(1, capi.BG_F32, 100, 500, 500, 1, 128, 1, None),                     # n_cols % 32
+        lambda: capi.transpose_chunks(1, capi.BG_F32, 100, 512, 512, 1, 64, 1, None),                      # chunks too short
+        lambda: capi.wgrad512(16, 512, 16, 512, 512, capi.BG_F16, 100, 1, 100, 16, None),                  # chunk_k % 64
+        lambda: capi.wgrad512(16, 512, 16, 513, 513, capi.BG_F16, 100, 1, 128, 16, None),                  # act_cols > 512
+        lambda: capi.pool_backward(None, 512, None, 0, 0, 10, None, capi.BG_F32, None),                    # G = 0
+        lambda: capi.pool_backward(1, 512, 1, 4, 3, 10, 16, capi.BG_F32, None),                            # concat pooling
+        lambda: capi.sgemm(None, 7, 1, 1, None, capi.BG_F32, 1, 1, 4, 4, 4, None, False, None, capi.BG_F32, 0, 16,
+                           capi.BG_F32, 4, False, None, 0, None),                                          # bad dtype
+        lambda: capi.eigen_loss(None, None, 0, 1.0, 0.0, 1e-8, None, None, None, None),
+        lambda: capi.collate_ptr(None, 3, None, None, None, None, None),
+        lambda: capi.dropout_mask(0, 1.0, 10, 16, None),
+        lambda: capi.mask_narrow(1, capi.BG_F32, 64, None, capi.BG_F32, 0, 10, 128, 16, None),             # ld_in < n_cols
+        lambda: capi.publish_words(None, None, 8, None),
+        lambda: capi.sage_aggregate(16, 16, capi.BG_F16, 10, 16, 16, 16, 0, capi.BG_AGGR_MEAN, 16, 0, None, width=100),
+    ]
+    for i, call in enumerate(bad):
+        with pytest.raises(capi.BuckGNNError) as e:
+            call()
+        assert e.value.status in (-1, -3, -4), (i, e.value.status)
+
+
 @pytest.mark.parametrize("name", ["GraphSage_meanAggr", "GraphSage_sumAggr", "GraphSage_addAggr",
                                   "GraphSage_maxAggr", "GraphSage_addAggr_Shared", "EA_GNN", "EA_GNN_Shared",
                                   "GraphSAGE_MLP"])
