@@ -750,7 +750,8 @@ int bg_pool_backward(const float* dpooled, int64_t ldp, const int32_t* graph_ptr
                      void* dx, int dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (N < 0 || G <= 0 || G >= 0x7fffffffLL || ldp < kHidden) return fail(BG_ERR_INVALID, "bg_pool_backward: bad size");
-  if (pool_mode < BG_POOL_MEAN || pool_mode > BG_POOL_SUPERNODE_ONLY) return fail(BG_ERR_UNSUPPORTED, "bg_pool_backward: pool_mode must be mean, mean_no_super or supernode_only");
+  if (pool_mode < BG_POOL_MEAN || pool_mode > BG_POOL_SUPERNODE_WITH_POOLING) return fail(BG_ERR_INVALID, "bg_pool_backward: bad pool_mode");
+  if (pool_mode == BG_POOL_SUPERNODE_WITH_POOLING && ldp < 2 * kHidden) return fail(BG_ERR_INVALID, "bg_pool_backward: the concatenated pooling needs dpooled [G, 1024]");
   if (N == 0) return BG_OK;
   if (!dpooled || !graph_ptr || !dx || !aligned16(dx)) return fail(BG_ERR_INVALID, "bg_pool_backward: bad pointer");
   const unsigned grid = grid_for(N * 32, 256, sm_count() * 8);

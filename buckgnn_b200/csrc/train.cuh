@@ -341,7 +341,9 @@ k_colsum_partial(const void* __restrict__ in, int dtype, int64_t rows, int cols,
 
 // ------------------------------------------------------------------ global_mean_pool backward
 // dx[r, :] = dpooled[g(r), off:off+512] * w(r);  mean: w = 1/max(cnt,1);  mean_no_super: the graph's last node gets
-// 0 and cnt excludes it;  supernode_only: only the last node, w = 1.  (Models/BuckGNN.py:273-284 in reverse.)
+// 0 and cnt excludes it;  supernode_only: only the last node, w = 1;  supernode_with_pooling (dpooled is [G, 1024] =
+// cat[mean_no_super, super]): real nodes take the first half / (cnt - 1), the last node the second half.
+// (Models/BuckGNN.py:273-293 in reverse.)
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_pool_bwd(const float* __restrict__ dpooled, int64_t ldp, const int32_t* __restrict__ graph_ptr, int G, int mode,
@@ -354,12 +356,14 @@ k_pool_bwd(const float* __restrict__ dpooled, int64_t ldp, const int32_t* __rest
     const int64_t beg = graph_ptr[lo], end = graph_ptr[lo + 1];
     const bool last = (r == end - 1);
     float w;
+    int64_t off = 0;                                  // column offset into dpooled (the concatenated variant)
     if (mode == BG_POOL_MEAN) w = 1.f / (float)max(end - beg, (int64_t)1);
     else if (mode == BG_POOL_MEAN_NO_SUPER) w = last ? 0.f : 1.f / (float)max(end - beg - 1, (int64_t)1);
-    else w = last ? 1.f : 0.f;
+    else if (mode == BG_POOL_SUPERNODE_ONLY) w = last ? 1.f : 0.f;
+    else { w = last ? 1.f : 1.f / (float)max(end - beg - 1, (int64_t)1); off = last ? kHidden : 0; }   // cat[mean_no_super, super]
     float v[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = w * dpooled[(size_t)lo * ldp + RowFrag<T>::col_of(lane, i)];
+    for (int i = 0; i < 16; ++i) v[i] = w * dpooled[(size_t)lo * ldp + off + RowFrag<T>::col_of(lane, i)];
     RowFrag<T>::store(dx + (size_t)r * kHidden, lane, v);
   }
 }

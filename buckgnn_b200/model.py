@@ -223,8 +223,6 @@ class BuckGNN(nn.Module):
                                           f"model_name={self.model_name!r} runs in eval mode only")
             if self.model_name == "GraphSage_maxAggr":
                 raise NotImplementedError("buckgnn_b200: training with max aggregation is not built")
-            if self.pooling_layer not in ("mean", "mean_no_super", "supernode_only"):
-                raise NotImplementedError(f"buckgnn_b200: training with pooling_layer={self.pooling_layer!r} is not built")
         if self.hidden_channels != 512:
             raise NotImplementedError("buckgnn_b200: the tcgen05 path is built for hidden_channels=512")
         if self.model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):

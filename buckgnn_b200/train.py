@@ -208,13 +208,32 @@ class SageTrainFunction(torch.autograd.Function):
             sv.layers.append((conv, bn, cur, agg, u, inv_norm, vec, residual))
             cur = y
         sv.ones, sv.zeros = ones, zeros
-        # ---- pooling + decoder (Models/BuckGNN.py:515-516)
+        # ---- pooling + decoder (Models/BuckGNN.py:246-307, 515-516): the pooled feature comes from bg_pool_head
+        # (its own decoder output is not used here); MLPPooling and the decoder run on bg_sgemm so that their
+        # hidden layers are kept for the backward pass
         dec = model.decoder
         decw = {"w1": dec[0].weight.detach(), "b1": dec[0].bias.detach(), "w2": dec[2].weight.detach(),
                 "b2": dec[2].bias.detach(), "w3": dec[4].weight.detach(), "b3": dec[4].bias.detach()}
         decw = {k: v.float().contiguous() for k, v in decw.items()}
-        pred, pooled = engine.pool_head(cur, idx, decw, model.output_dim, want_pooled=True, pooling=model.pooling_layer)
-        sv.decw, sv.pooled = decw, pooled
+        F32 = capi.BG_F32
+        with engine.TIMERS.span("pool_head"):
+            _, raw = engine.pool_head(cur, idx, decw, model.output_dim, want_pooled=True, pooling=model.pooling_layer)
+            g_count, in_dim = raw.shape
+            sv.mlp = None
+            dec_in = raw
+            if model.pooling_layer in ("mlp", "mlp_no_super"):                     # MLPPooling (:568-581)
+                lin = model.pooling_mpl.mlp[0]
+                wp, bp = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
+                dec_in = _f32((g_count, 512), dev)
+                sgemm(raw, F32, 512, 1, wp, F32, 1, 512, g_count, 512, 512, dec_in, F32, 512, bias=bp, relu=True)
+                sv.mlp = (lin, wp)
+            h1d, h2d = _f32((g_count, 128), dev), _f32((g_count, 64), dev)
+            out_dim = model.output_dim
+            pred = _f32((g_count, out_dim), dev)
+            sgemm(dec_in, F32, in_dim, 1, decw["w1"], F32, 1, in_dim, g_count, 128, in_dim, h1d, F32, 128, bias=decw["b1"], relu=True)
+            sgemm(h1d, F32, 128, 1, decw["w2"], F32, 1, 128, g_count, 64, 128, h2d, F32, 64, bias=decw["b2"], relu=True)
+            sgemm(h2d, F32, 64, 1, decw["w3"], F32, 1, 64, g_count, out_dim, 64, pred, F32, out_dim, bias=decw["b3"])
+        sv.decw, sv.raw, sv.dec_in, sv.h1d, sv.h2d = decw, raw, dec_in, h1d, h2d
         ctx.sv = sv
         ctx.params = params
         return pred
@@ -227,7 +246,8 @@ class SageTrainFunction(torch.autograd.Function):
         s = _stream()
         F32 = capi.BG_F32
         dpred = dpred.detach().to(torch.float32).contiguous()
-        g_count, out_dim = sv.pooled.shape[0], model.output_dim
+        g_count, out_dim = sv.raw.shape[0], model.output_dim
+        in_dim = sv.dec_in.shape[1]
         grads = {}
 
         def gbuf(param):
@@ -237,13 +257,11 @@ class SageTrainFunction(torch.autograd.Function):
                 t = grads[id(param)] = _f32(tuple(param.shape), dev)
             return t, not fresh                      # (buffer, accumulate?)
 
-        # ---- decoder: recompute the two hidden layers, then backward (all [G, <=512]: bg_sgemm)
+        # ---- decoder (+ MLPPooling) backward: all [G, <= 1024], on bg_sgemm
         d = sv.decw
         dec = model.decoder
+        h1d, h2d, dec_in = sv.h1d, sv.h2d, sv.dec_in
         with engine.TIMERS.span("train_head_bwd"):
-            h1d, h2d = _f32((g_count, 128), dev), _f32((g_count, 64), dev)
-            sgemm(sv.pooled, F32, 512, 1, d["w1"], F32, 1, 512, g_count, 128, 512, h1d, F32, 128, bias=d["b1"], relu=True)
-            sgemm(h1d, F32, 128, 1, d["w2"], F32, 1, 128, g_count, 64, 128, h2d, F32, 64, bias=d["b2"], relu=True)
             dw3, _ = gbuf(dec[4].weight); db3, _ = gbuf(dec[4].bias)
             sgemm(dpred, F32, 1, out_dim, h2d, F32, 64, 1, out_dim, 64, g_count, dw3, F32, 64)
             colsum(dpred, F32, g_count, out_dim, out_dim, db3)
@@ -255,13 +273,22 @@ class SageTrainFunction(torch.autograd.Function):
             dh1d = _f32((g_count, 128), dev)
             sgemm(dh2d, F32, 64, 1, d["w2"], F32, 128, 1, g_count, 128, 64, dh1d, F32, 128, mask=h1d, mask_ld=128)
             dw1, _ = gbuf(dec[0].weight); db1, _ = gbuf(dec[0].bias)
-            sgemm(dh1d, F32, 1, 128, sv.pooled, F32, 512, 1, 128, 512, g_count, dw1, F32, 512)
+            sgemm(dh1d, F32, 1, 128, dec_in, F32, in_dim, 1, 128, in_dim, g_count, dw1, F32, in_dim)
             colsum(dh1d, F32, g_count, 128, 128, db1)
-            dpooled = _f32((g_count, 512), dev)
-            sgemm(dh1d, F32, 128, 1, d["w1"], F32, 512, 1, g_count, 512, 128, dpooled, F32, 512)
-            # ---- global_mean_pool backward
+            dpooled = _f32((g_count, in_dim), dev)
+            if sv.mlp is None:
+                sgemm(dh1d, F32, 128, 1, d["w1"], F32, in_dim, 1, g_count, in_dim, 128, dpooled, F32, in_dim)
+            else:                                                   # through relu(Linear(512, 512)) of MLPPooling
+                lin, wp = sv.mlp
+                dpm = _f32((g_count, 512), dev)
+                sgemm(dh1d, F32, 128, 1, d["w1"], F32, 512, 1, g_count, 512, 128, dpm, F32, 512, mask=dec_in, mask_ld=512)
+                dwp, _ = gbuf(lin.weight); dbp, _ = gbuf(lin.bias)
+                sgemm(dpm, F32, 1, 512, sv.raw, F32, 512, 1, 512, 512, g_count, dwp, F32, 512)
+                colsum(dpm, F32, g_count, 512, 512, dbp)
+                sgemm(dpm, F32, 512, 1, wp, F32, 512, 1, g_count, 512, 512, dpooled, F32, 512)
+            # ---- get_pooling_layer backward
             dcur = Activation(n, 512, prec, dev)
-            capi.pool_backward(dpooled.data_ptr(), 512, sv.idx.graph_ptr.data_ptr(), g_count,
+            capi.pool_backward(dpooled.data_ptr(), in_dim, sv.idx.graph_ptr.data_ptr(), g_count,
                                capi.POOL_MODES[model.pooling_layer], n, dcur.data.data_ptr(), code, s)
         dy2: Optional[Activation] = None
 
@@ -367,6 +394,8 @@ def trainable_parameters(model) -> List[torch.nn.Parameter]:
         add(conv.lin_l.weight); add(conv.lin_l.bias); add(conv.lin_r.weight)
         if bn is not None:
             add(bn.weight); add(bn.bias)
+    if model.pooling_layer in ("mlp", "mlp_no_super"):
+        add(model.pooling_mpl.mlp[0].weight); add(model.pooling_mpl.mlp[0].bias)
     for m in (model.decoder[0], model.decoder[2], model.decoder[4]):
         add(m.weight); add(m.bias)
     return ps

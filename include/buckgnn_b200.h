@@ -281,8 +281,8 @@ int bg_reduce_partials(const float* partial, int32_t n_chunks, int64_t n, float*
 int bg_colsum_workspace_bytes(int64_t rows, int32_t cols, size_t* bytes_host);
 int bg_colsum(const void* in, int dtype, int64_t rows, int32_t cols, int64_t ld, float* out, int accumulate,
               void* workspace, size_t workspace_bytes, void* stream);
-/* global_mean_pool backward (Models/BuckGNN.py:273-284): dx[r] = dpooled[graph(r)] * w(r); pool_mode in
- * {BG_POOL_MEAN, BG_POOL_MEAN_NO_SUPER, BG_POOL_SUPERNODE_ONLY}; dpooled [G, >=512] f32 (ld = ldp). */
+/* get_pooling_layer backward (Models/BuckGNN.py:273-293): dx[r] = dpooled[graph(r)] * w(r) for every bg_pool_mode;
+ * dpooled [G, >= 512] f32 (ld = ldp), [G, 1024] for BG_POOL_SUPERNODE_WITH_POOLING. */
 int bg_pool_backward(const float* dpooled, int64_t ldp, const int32_t* graph_ptr, int64_t n_graphs, int pool_mode,
                      int64_t n_nodes, void* dx, int dtype, void* stream);
 /* fp32 GEMM on the CUDA cores for the narrow layers (encoder 16->64->128, decoder 512->128->64->out and their

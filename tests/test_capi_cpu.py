@@ -63,7 +63,7 @@ def test_training_and_collate_entry_points_validate_arguments_without_gpu(lib):
         lambda: capi.wgrad512(16, 512, 16, 512, 512, capi.BG_F16, 100, 1, 100, 16, None),                  # chunk_k % 64
         lambda: capi.wgrad512(16, 512, 16, 513, 513, capi.BG_F16, 100, 1, 128, 16, None),                  # act_cols > 512
         lambda: capi.pool_backward(None, 512, None, 0, 0, 10, None, capi.BG_F32, None),                    # G = 0
-        lambda: capi.pool_backward(1, 512, 1, 4, 3, 10, 16, capi.BG_F32, None),                            # concat pooling
+        lambda: capi.pool_backward(1, 512, 1, 4, 3, 10, 16, capi.BG_F32, None),                            # concat pooling needs ldp 1024
         lambda: capi.sgemm(None, 7, 1, 1, None, capi.BG_F32, 1, 1, 4, 4, 4, None, False, None, capi.BG_F32, 0, 16,
                            capi.BG_F32, 4, False, None, 0, None),                                          # bad dtype
         lambda: capi.eigen_loss(None, None, 0, 1.0, 0.0, 1e-8, None, None, None, None),
