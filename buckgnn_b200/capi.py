@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = (
     "bg_train_workspace_bytes", "bg_bn_batch_stats", "bg_bn_act_forward", "bg_sage_backward_rows",
     "bg_transpose_chunks", "bg_mask_narrow", "bg_reduce_partials", "bg_colsum_workspace_bytes", "bg_colsum", "bg_pool_backward",
     "bg_sgemm_workspace_bytes", "bg_sgemm", "bg_eigen_loss", "bg_dropout_mask", "bg_collate_ptr", "bg_collate",
+    "bg_dropout_residual", "bg_grad_mask", "bg_segment_expand",
 )
 
 
@@ -102,6 +103,9 @@ _SIGNATURES = {
     "bg_sgemm": (C.c_int, [_P, C.c_int, _I64, _I64, _P, C.c_int, _I64, _I64, _I64, _I64, _I64, _P, C.c_int, _P,
                            C.c_int, _I64, _P, C.c_int, _I64, C.c_int, _P, C.c_size_t, _P]),
     "bg_dropout_mask": (C.c_int, [C.c_uint64, C.c_float, _I64, _P, _P]),
+    "bg_dropout_residual": (C.c_int, [_P, _P, _P, C.c_int, _I64, C.c_float, C.c_uint64, _P]),
+    "bg_grad_mask": (C.c_int, [_P, _P, _P, _P, C.c_int, _I64, C.c_float, C.c_uint64, _P]),
+    "bg_segment_expand": (C.c_int, [_P, _P, _I64, C.c_int, _P, C.c_int, _P]),
     "bg_collate_ptr": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
     "bg_collate": (C.c_int, [_P, _I32, _P, _I64, _P, _I32, _P, _P, _I64, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "bg_eigen_loss": (C.c_int, [_P, _P, _I64, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P]),
@@ -331,3 +335,15 @@ def collate(x_all, n_features, ei_all, e_all, ea_all, n_edge_features, y_all, se
 def wgrad512(dz, ld_dz, act, act_cols, ld_act, dtype, n_rows, n_chunks, chunk_k, partial, stream):
     _check(load().bg_wgrad512(dz, ld_dz, act, act_cols, ld_act, dtype, n_rows, n_chunks, chunk_k, partial, stream),
            "bg_wgrad512")
+
+
+def dropout_residual(x, x_prev, y, dtype, n_rows, dropout_p, seed, stream):
+    _check(load().bg_dropout_residual(x, x_prev, y, dtype, n_rows, dropout_p, seed, stream), "bg_dropout_residual")
+
+
+def grad_mask(dy, dy2, act, out, dtype, n_rows, dropout_p, seed, stream):
+    _check(load().bg_grad_mask(dy, dy2, act, out, dtype, n_rows, dropout_p, seed, stream), "bg_grad_mask")
+
+
+def segment_expand(src, rowptr, n_rows, mean, out, dtype, stream):
+    _check(load().bg_segment_expand(src, rowptr, n_rows, int(bool(mean)), out, dtype, stream), "bg_segment_expand")

@@ -800,6 +800,44 @@ int bg_sgemm(const void* a, int a_dtype, int64_t sam, int64_t sak, const void* b
   return BG_OK;
 }
 
+int bg_dropout_residual(const void* x, const void* x_prev, void* y, int dtype, int64_t N, float dropout_p, uint64_t seed, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N < 0 || !(dropout_p >= 0.f && dropout_p < 1.f)) return fail(BG_ERR_INVALID, "bg_dropout_residual: bad size / dropout_p");
+  if (N == 0) return BG_OK;
+  if (!x || !y || !aligned16(x) || !aligned16(y) || (x_prev && !aligned16(x_prev))) return fail(BG_ERR_INVALID, "bg_dropout_residual: bad pointer");
+  const DropArgs d = drop_args(dropout_p, seed);
+  const unsigned grid = grid_for(N * 32, 256, sm_count() * 8);
+  BG_BY_DTYPE(dtype, (k_dropout_residual<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), static_cast<const T*>(x_prev), static_cast<T*>(y), N, d)))
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_grad_mask(const void* dy, const void* dy2, const void* act, void* out, int dtype, int64_t N, float dropout_p,
+                 uint64_t seed, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N < 0 || !(dropout_p >= 0.f && dropout_p < 1.f)) return fail(BG_ERR_INVALID, "bg_grad_mask: bad size / dropout_p");
+  if (N == 0) return BG_OK;
+  if (!dy || !out || !aligned16(dy) || !aligned16(out) || (dy2 && !aligned16(dy2)) || (act && !aligned16(act)))
+    return fail(BG_ERR_INVALID, "bg_grad_mask: bad pointer");
+  const DropArgs d = drop_args(dropout_p, seed);
+  const unsigned grid = grid_for(N * 32, 256, sm_count() * 8);
+  BG_BY_DTYPE(dtype, (k_grad_mask<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(dy), static_cast<const T*>(dy2), static_cast<const T*>(act),
+                                                               static_cast<T*>(out), N, d)))
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_segment_expand(const void* src, const int32_t* rowptr, int64_t n_rows, int mean, void* out, int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_rows < 0) return fail(BG_ERR_INVALID, "bg_segment_expand: bad size");
+  if (n_rows == 0) return BG_OK;
+  if (!src || !rowptr || !out || !aligned16(src) || !aligned16(out)) return fail(BG_ERR_INVALID, "bg_segment_expand: bad pointer");
+  const unsigned grid = grid_for(n_rows * 32, 256, sm_count() * 8);
+  BG_BY_DTYPE(dtype, (k_segment_expand<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(src), rowptr, n_rows, mean, static_cast<T*>(out))))
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
 int bg_collate_ptr(const int64_t* sel, int64_t G, const int64_t* node_ptr, const int64_t* edge_ptr,
                    int64_t* out_node_ptr, int64_t* out_edge_ptr, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -458,6 +458,70 @@ __global__ void k_sgemm_epilogue(const SgemmEpilogue p) {
   }
 }
 
+// ------------------------------------------------------------------ elementwise pieces of the EA-GNN training step
+// (Models/BuckGNN.py:375-387 wrapper and GraphNetBlock :552-566 in train mode)
+// y = dropout(x + x_prev)   -- the wrapper's skip + Dropout on node and edge tensors (no activation in between)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_dropout_residual(const T* __restrict__ x, const T* __restrict__ x_prev, T* __restrict__ y, int64_t N, const DropArgs drop) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < N; r += n_warps) {
+    float v[16];
+    row_load<T>(x + (size_t)r * kHidden, lane, v);
+    if (x_prev) {
+      float t[16];
+      row_load<T>(x_prev + (size_t)r * kHidden, lane, t);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += t[i];
+    }
+    if (drop.thr) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        v[i] = dropout_keep(drop.seed, r, RowFrag<T>::col_of(lane, i), drop.thr) ? v[i] * drop.inv_keep : 0.f;
+    }
+    RowFrag<T>::store(y + (size_t)r * kHidden, lane, v);
+  }
+}
+// out = dropout'(dy + dy2) [act > 0]   (either part optional: thr = 0 -> no dropout, act = null -> no ReLU mask)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_grad_mask(const T* __restrict__ dy, const T* __restrict__ dy2, const T* __restrict__ act, T* __restrict__ out, int64_t N,
+            const DropArgs drop) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < N; r += n_warps) {
+    float g[16];
+    load_upstream<T>(dy, dy2, r, lane, drop, g);
+    if (act) {
+      float a[16];
+      row_load<T>(act + (size_t)r * kHidden, lane, a);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) g[i] = a[i] > 0.f ? g[i] : 0.f;
+    }
+    RowFrag<T>::store(out + (size_t)r * kHidden, lane, g);
+  }
+}
+// scatter_mean backward: every CSR slot of row r receives src[r] / max(count_r, 1)  (count = 1 without `mean`)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_segment_expand(const T* __restrict__ src, const int32_t* __restrict__ rowptr, int64_t n_rows, int mean, T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += n_warps) {
+    const int32_t b = rowptr[r], e = rowptr[r + 1];
+    if (e == b) continue;
+    float v[16];
+    row_load<T>(src + (size_t)r * kHidden, lane, v);
+    if (mean) {
+      const float w = 1.f / (float)(e - b);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] *= w;
+    }
+    for (int32_t s = b; s < e; ++s) RowFrag<T>::store(out + (size_t)s * kHidden, lane, v);
+  }
+}
+
 // ------------------------------------------------------------------ device-side collate
 // PyG's DataLoader collate (Batch.from_data_list) for a dataset that lives in HBM in concatenated form:
 //   store: x_all [sum n, F], ei_all [2, sum e] (node ids LOCAL to their graph), ea_all [sum e, Fe], y_all [G_all],

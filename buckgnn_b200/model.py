@@ -218,9 +218,10 @@ class BuckGNN(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("buckgnn_b200.BuckGNN runs on CUDA (sm_100a) tensors only; there is no CPU path")
         if self.training:
-            if self.model_name not in _SAGE_LISTS and self.model_name != "GraphSage_addAggr_Shared":
-                raise NotImplementedError(f"buckgnn_b200: the training step is built for the GraphSAGE variants; "
-                                          f"model_name={self.model_name!r} runs in eval mode only")
+            if self.model_name not in _SAGE_LISTS and self.model_name not in ("GraphSage_addAggr_Shared", "EA_GNN",
+                                                                               "EA_GNN_Shared"):
+                raise NotImplementedError(f"buckgnn_b200: the training step is built for the GraphSAGE and EA-GNN "
+                                          f"variants; model_name={self.model_name!r} runs in eval mode only")
             if self.model_name == "GraphSage_maxAggr":
                 raise NotImplementedError("buckgnn_b200: training with max aggregation is not built")
         if self.hidden_channels != 512:
@@ -246,7 +247,7 @@ class BuckGNN(nn.Module):
             raise ValueError(f"Unknown pooling layer: {self.pooling_layer}")
         if self.training:       # train-mode BatchNorm / Dropout + autograd through the backward kernels (train.py)
             from . import train
-            return train.forward_train(self, x, edge_index, batch).squeeze(), batch
+            return train.forward_train(self, x, edge_index, batch, edge_attr=edge_attr).squeeze(), batch
         with torch.no_grad():
             if self.model_name in ("EA_GNN", "EA_GNN_Shared"):
                 pred = self._forward_cuda_eagnn(x, edge_index, edge_attr, batch, node_level)

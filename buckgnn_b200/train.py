@@ -121,6 +121,161 @@ class _Saved:
     pass
 
 
+class GradStore:
+    """fp32 gradient buffers by parameter; the second touch of a parameter (shared blocks) accumulates."""
+
+    def __init__(self, device):
+        self.device, self.bufs = device, {}
+
+    def get(self, param):
+        """(buffer, accumulate?) -- the caller overwrites a fresh buffer completely."""
+        t = self.bufs.get(id(param))
+        fresh = t is None
+        if fresh:
+            t = self.bufs[id(param)] = _f32(tuple(param.shape), self.device)
+        return t, not fresh
+
+    def zeros(self, param):
+        """A zero-initialised buffer that column slices are ADDED into."""
+        t = self.bufs.get(id(param))
+        if t is None:
+            t = self.bufs[id(param)] = torch.zeros(tuple(param.shape), dtype=torch.float32, device=self.device)
+        return t
+
+    def for_params(self, params):
+        out: List[Optional[torch.Tensor]] = []
+        for p_ in params:
+            t = self.bufs.get(id(p_))
+            out.append(None if t is None else t.to(p_.dtype))
+        return out
+
+
+# ----------------------------------------------------------------------------- shared pieces: encoders and head
+def encoder_forward_train(enc, inp: torch.Tensor, prec: str, bias3_host: torch.Tensor):
+    """node_encoder / edge_encoder (Models/BuckGNN.py:68-82): the two narrow Linears on bg_sgemm (fp32), the
+    128 -> 512 one on the tensor cores.  Returns (h1 [n,64] f32, h2 [n,128], out [n,512])."""
+    dev, n, f = inp.device, inp.shape[0], inp.shape[1]
+    code = engine.PRECISION_FORMATS[prec][0]
+    F32 = capi.BG_F32
+    w1, b1 = enc[0].weight.detach().float().contiguous(), enc[0].bias.detach().float().contiguous()
+    w2, b2 = enc[2].weight.detach().float().contiguous(), enc[2].bias.detach().float().contiguous()
+    with engine.TIMERS.span("train_encoder"):
+        h1 = _f32((n, 64), dev)
+        sgemm(inp, F32, f, 1, w1, F32, 1, f, n, 64, f, h1, F32, 64, bias=b1, relu=True)
+        h2 = Activation(n, 128, prec, dev)
+        sgemm(h1, F32, 64, 1, w2, F32, 1, 64, n, 128, 64, h2.data, code, 128, bias=b2, relu=True)
+        h2.refresh_split()
+        out = Activation(n, 512, prec, dev)
+        engine.gemm512(engine._segments(h2, engine.pack_linear(enc[4].weight, prec)), n, prec, out,
+                       bias=bias3_host.data_ptr())
+    return h1, h2, out
+
+
+def encoder_backward(enc, inp: torch.Tensor, h1: torch.Tensor, h2: Activation, dout: Activation, prec: str,
+                     grads: GradStore) -> None:
+    """Gradients of the three encoder Linears given d(out) [n, 512]."""
+    dev, n, f = inp.device, inp.shape[0], inp.shape[1]
+    code = engine.PRECISION_FORMATS[prec][0]
+    F32 = capi.BG_F32
+    s = _stream()
+    dx0 = dout.data
+    with engine.TIMERS.span("train_encoder_bwd"):
+        w3 = enc[4].weight.detach().float().contiguous()          # [512, 128]
+        w2 = enc[2].weight.detach().float().contiguous()
+        dw3e, _ = grads.get(enc[4].weight); db3e, _ = grads.get(enc[4].bias)
+        tmp = _f32((512, 512), dev)
+        weight_grad_mn(dx0, h2.data, code, n, tmp, False)             # dW3 = dx0^T h2; columns >= 128 of tmp come out 0
+        dw3e.copy_(tmp[:, :128])
+        colsum(dx0, code, n, 512, 512, db3e)
+        # dh2 = (dx0 W3) [h2 > 0]: W3^T zero-padded to 512 output rows on the tensor cores, then mask + narrow
+        w3t_pad = torch.zeros((512, 512), dtype=torch.float32, device=dev)
+        capi.transpose_chunks(w3.data_ptr(), F32, 512, 128, 128, 1, 512, w3t_pad.data_ptr(), s)
+        full = Activation(n, 512, prec, dev)
+        engine.gemm512(engine._segments(dout, engine.pack_linear(w3t_pad, prec)), n, prec, full)
+        dh2 = _f32((n, 128), dev)
+        capi.mask_narrow(full.data.data_ptr(), code, 512, h2.data.data_ptr(), code, 128, n, 128, dh2.data_ptr(), s)
+        dw2e, _ = grads.get(enc[2].weight); db2e, _ = grads.get(enc[2].bias)
+        sgemm(dh2, F32, 1, 128, h1, F32, 64, 1, 128, 64, n, dw2e, F32, 64)
+        colsum(dh2, F32, n, 128, 128, db2e)
+        dh1 = _f32((n, 64), dev)
+        sgemm(dh2, F32, 128, 1, w2, F32, 64, 1, n, 64, 128, dh1, F32, 64, mask=h1, mask_ld=64)
+        dw1e, _ = grads.get(enc[0].weight); db1e, _ = grads.get(enc[0].bias)
+        sgemm(dh1, F32, 1, 64, inp, F32, f, 1, 64, f, n, dw1e, F32, f)
+        colsum(dh1, F32, n, 64, 64, db1e)
+
+
+def head_forward_train(model, cur: Activation, idx, sv) -> torch.Tensor:
+    """get_pooling_layer + decoder (Models/BuckGNN.py:246-307, 515-516): the pooled feature comes from bg_pool_head
+    (its own decoder output is not used here); MLPPooling and the decoder run on bg_sgemm so that their hidden
+    layers are kept for the backward pass."""
+    dev = cur.data.device
+    dec = model.decoder
+    decw = {"w1": dec[0].weight.detach(), "b1": dec[0].bias.detach(), "w2": dec[2].weight.detach(),
+            "b2": dec[2].bias.detach(), "w3": dec[4].weight.detach(), "b3": dec[4].bias.detach()}
+    decw = {k: v.float().contiguous() for k, v in decw.items()}
+    F32 = capi.BG_F32
+    with engine.TIMERS.span("pool_head"):
+        _, raw = engine.pool_head(cur, idx, decw, model.output_dim, want_pooled=True, pooling=model.pooling_layer)
+        g_count, in_dim = raw.shape
+        sv.mlp = None
+        dec_in = raw
+        if model.pooling_layer in ("mlp", "mlp_no_super"):                     # MLPPooling (:568-581)
+            lin = model.pooling_mpl.mlp[0]
+            wp, bp = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
+            dec_in = _f32((g_count, 512), dev)
+            sgemm(raw, F32, 512, 1, wp, F32, 1, 512, g_count, 512, 512, dec_in, F32, 512, bias=bp, relu=True)
+            sv.mlp = (lin, wp)
+        h1d, h2d = _f32((g_count, 128), dev), _f32((g_count, 64), dev)
+        out_dim = model.output_dim
+        pred = _f32((g_count, out_dim), dev)
+        sgemm(dec_in, F32, in_dim, 1, decw["w1"], F32, 1, in_dim, g_count, 128, in_dim, h1d, F32, 128, bias=decw["b1"], relu=True)
+        sgemm(h1d, F32, 128, 1, decw["w2"], F32, 1, 128, g_count, 64, 128, h2d, F32, 64, bias=decw["b2"], relu=True)
+        sgemm(h2d, F32, 64, 1, decw["w3"], F32, 1, 64, g_count, out_dim, 64, pred, F32, out_dim, bias=decw["b3"])
+    sv.decw, sv.raw, sv.dec_in, sv.h1d, sv.h2d = decw, raw, dec_in, h1d, h2d
+    return pred
+
+
+def head_backward(model, sv, dpred: torch.Tensor, n: int, prec: str, grads: GradStore) -> Activation:
+    """Decoder (+ MLPPooling) and pooling backward: returns d(last layer output) [n, 512]."""
+    dev = dpred.device
+    code = engine.PRECISION_FORMATS[prec][0]
+    F32 = capi.BG_F32
+    g_count, out_dim = sv.raw.shape[0], model.output_dim
+    in_dim = sv.dec_in.shape[1]
+    d, dec = sv.decw, model.decoder
+    h1d, h2d, dec_in = sv.h1d, sv.h2d, sv.dec_in
+    with engine.TIMERS.span("train_head_bwd"):
+        dw3, _ = grads.get(dec[4].weight); db3, _ = grads.get(dec[4].bias)
+        sgemm(dpred, F32, 1, out_dim, h2d, F32, 64, 1, out_dim, 64, g_count, dw3, F32, 64)
+        colsum(dpred, F32, g_count, out_dim, out_dim, db3)
+        dh2d = _f32((g_count, 64), dev)
+        sgemm(dpred, F32, out_dim, 1, d["w3"], F32, 64, 1, g_count, 64, out_dim, dh2d, F32, 64, mask=h2d, mask_ld=64)
+        dw2, _ = grads.get(dec[2].weight); db2, _ = grads.get(dec[2].bias)
+        sgemm(dh2d, F32, 1, 64, h1d, F32, 128, 1, 64, 128, g_count, dw2, F32, 128)
+        colsum(dh2d, F32, g_count, 64, 64, db2)
+        dh1d = _f32((g_count, 128), dev)
+        sgemm(dh2d, F32, 64, 1, d["w2"], F32, 128, 1, g_count, 128, 64, dh1d, F32, 128, mask=h1d, mask_ld=128)
+        dw1, _ = grads.get(dec[0].weight); db1, _ = grads.get(dec[0].bias)
+        sgemm(dh1d, F32, 1, 128, dec_in, F32, in_dim, 1, 128, in_dim, g_count, dw1, F32, in_dim)
+        colsum(dh1d, F32, g_count, 128, 128, db1)
+        dpooled = _f32((g_count, in_dim), dev)
+        if sv.mlp is None:
+            sgemm(dh1d, F32, 128, 1, d["w1"], F32, in_dim, 1, g_count, in_dim, 128, dpooled, F32, in_dim)
+        else:                                                   # through relu(Linear(512, 512)) of MLPPooling
+            lin, wp = sv.mlp
+            dpm = _f32((g_count, 512), dev)
+            sgemm(dh1d, F32, 128, 1, d["w1"], F32, 512, 1, g_count, 512, 128, dpm, F32, 512, mask=dec_in, mask_ld=512)
+            dwp, _ = grads.get(lin.weight); dbp, _ = grads.get(lin.bias)
+            sgemm(dpm, F32, 1, 512, sv.raw, F32, 512, 1, 512, 512, g_count, dwp, F32, 512)
+            colsum(dpm, F32, g_count, 512, 512, dbp)
+            sgemm(dpm, F32, 512, 1, wp, F32, 512, 1, g_count, 512, 512, dpooled, F32, 512)
+        dcur = Activation(n, 512, prec, dev)
+        capi.pool_backward(dpooled.data_ptr(), in_dim, sv.idx.graph_ptr.data_ptr(), g_count,
+                           capi.POOL_MODES[model.pooling_layer], n, dcur.data.data_ptr(), code, _stream())
+    return dcur
+
+
+# ----------------------------------------------------------------------------- GraphSAGE
 class SageTrainFunction(torch.autograd.Function):
     """pred = f(parameters); x / edge_index / batch are data (no gradient)."""
 
@@ -131,7 +286,7 @@ class SageTrainFunction(torch.autograd.Function):
         dev = x.device
         s = _stream()
         x = x.detach().to(torch.float32).contiguous()
-        n, f = x.shape
+        n = x.shape[0]
         convs = model._sage_layers()
         L = len(convs)
         aggr = convs[0][0].aggr
@@ -149,20 +304,8 @@ class SageTrainFunction(torch.autograd.Function):
         bias_of = {id(c): biases[1 + k] for k, c in enumerate(uniq_convs)}
 
         sv = _Saved()
-        sv.model, sv.prec, sv.code, sv.n, sv.f, sv.x, sv.seed, sv.p_drop, sv.aggr = model, prec, code, n, f, x, seed, p_drop, aggr
-        # ---- encoder (Models/BuckGNN.py:68-74, :323)
-        w1, b1 = enc[0].weight.detach().float().contiguous(), enc[0].bias.detach().float().contiguous()
-        w2, b2 = enc[2].weight.detach().float().contiguous(), enc[2].bias.detach().float().contiguous()
-        with engine.TIMERS.span("train_encoder"):
-            h1 = _f32((n, 64), dev)
-            sgemm(x, capi.BG_F32, f, 1, w1, capi.BG_F32, 1, f, n, 64, f, h1, capi.BG_F32, 64, bias=b1, relu=True)
-            h2 = Activation(n, 128, prec, dev)
-            sgemm(h1, capi.BG_F32, 64, 1, w2, capi.BG_F32, 1, 64, n, 128, 64, h2.data, code, 128, bias=b2, relu=True)
-            h2.refresh_split()
-            cur = Activation(n, 512, prec, dev)
-            engine.gemm512(engine._segments(h2, engine.pack_linear(enc[4].weight, prec)), n, prec, cur,
-                           bias=biases[0].data_ptr())
-        sv.h1, sv.h2 = h1, h2
+        sv.model, sv.prec, sv.n, sv.x, sv.seed, sv.p_drop, sv.aggr = model, prec, n, x, seed, p_drop, aggr
+        sv.h1, sv.h2, cur = encoder_forward_train(enc, x, prec, biases[0])          # Models/BuckGNN.py:323
         idx = pending.finish()
         sv.idx = idx
         sv.edge_index = pending.edge_index
@@ -208,32 +351,7 @@ class SageTrainFunction(torch.autograd.Function):
             sv.layers.append((conv, bn, cur, agg, u, inv_norm, vec, residual))
             cur = y
         sv.ones, sv.zeros = ones, zeros
-        # ---- pooling + decoder (Models/BuckGNN.py:246-307, 515-516): the pooled feature comes from bg_pool_head
-        # (its own decoder output is not used here); MLPPooling and the decoder run on bg_sgemm so that their
-        # hidden layers are kept for the backward pass
-        dec = model.decoder
-        decw = {"w1": dec[0].weight.detach(), "b1": dec[0].bias.detach(), "w2": dec[2].weight.detach(),
-                "b2": dec[2].bias.detach(), "w3": dec[4].weight.detach(), "b3": dec[4].bias.detach()}
-        decw = {k: v.float().contiguous() for k, v in decw.items()}
-        F32 = capi.BG_F32
-        with engine.TIMERS.span("pool_head"):
-            _, raw = engine.pool_head(cur, idx, decw, model.output_dim, want_pooled=True, pooling=model.pooling_layer)
-            g_count, in_dim = raw.shape
-            sv.mlp = None
-            dec_in = raw
-            if model.pooling_layer in ("mlp", "mlp_no_super"):                     # MLPPooling (:568-581)
-                lin = model.pooling_mpl.mlp[0]
-                wp, bp = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
-                dec_in = _f32((g_count, 512), dev)
-                sgemm(raw, F32, 512, 1, wp, F32, 1, 512, g_count, 512, 512, dec_in, F32, 512, bias=bp, relu=True)
-                sv.mlp = (lin, wp)
-            h1d, h2d = _f32((g_count, 128), dev), _f32((g_count, 64), dev)
-            out_dim = model.output_dim
-            pred = _f32((g_count, out_dim), dev)
-            sgemm(dec_in, F32, in_dim, 1, decw["w1"], F32, 1, in_dim, g_count, 128, in_dim, h1d, F32, 128, bias=decw["b1"], relu=True)
-            sgemm(h1d, F32, 128, 1, decw["w2"], F32, 1, 128, g_count, 64, 128, h2d, F32, 64, bias=decw["b2"], relu=True)
-            sgemm(h2d, F32, 64, 1, decw["w3"], F32, 1, 64, g_count, out_dim, 64, pred, F32, out_dim, bias=decw["b3"])
-        sv.decw, sv.raw, sv.dec_in, sv.h1d, sv.h2d = decw, raw, dec_in, h1d, h2d
+        pred = head_forward_train(model, cur, idx, sv)
         ctx.sv = sv
         ctx.params = params
         return pred
@@ -241,55 +359,13 @@ class SageTrainFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dpred):
         sv = ctx.sv
-        model, prec, code, n, f = sv.model, sv.prec, sv.code, sv.n, sv.f
+        model, prec, n = sv.model, sv.prec, sv.n
+        code = engine.PRECISION_FORMATS[prec][0]
         dev = sv.x.device
         s = _stream()
-        F32 = capi.BG_F32
         dpred = dpred.detach().to(torch.float32).contiguous()
-        g_count, out_dim = sv.raw.shape[0], model.output_dim
-        in_dim = sv.dec_in.shape[1]
-        grads = {}
-
-        def gbuf(param):
-            t = grads.get(id(param))
-            fresh = t is None
-            if fresh:
-                t = grads[id(param)] = _f32(tuple(param.shape), dev)
-            return t, not fresh                      # (buffer, accumulate?)
-
-        # ---- decoder (+ MLPPooling) backward: all [G, <= 1024], on bg_sgemm
-        d = sv.decw
-        dec = model.decoder
-        h1d, h2d, dec_in = sv.h1d, sv.h2d, sv.dec_in
-        with engine.TIMERS.span("train_head_bwd"):
-            dw3, _ = gbuf(dec[4].weight); db3, _ = gbuf(dec[4].bias)
-            sgemm(dpred, F32, 1, out_dim, h2d, F32, 64, 1, out_dim, 64, g_count, dw3, F32, 64)
-            colsum(dpred, F32, g_count, out_dim, out_dim, db3)
-            dh2d = _f32((g_count, 64), dev)
-            sgemm(dpred, F32, out_dim, 1, d["w3"], F32, 64, 1, g_count, 64, out_dim, dh2d, F32, 64, mask=h2d, mask_ld=64)
-            dw2, _ = gbuf(dec[2].weight); db2, _ = gbuf(dec[2].bias)
-            sgemm(dh2d, F32, 1, 64, h1d, F32, 128, 1, 64, 128, g_count, dw2, F32, 128)
-            colsum(dh2d, F32, g_count, 64, 64, db2)
-            dh1d = _f32((g_count, 128), dev)
-            sgemm(dh2d, F32, 64, 1, d["w2"], F32, 128, 1, g_count, 128, 64, dh1d, F32, 128, mask=h1d, mask_ld=128)
-            dw1, _ = gbuf(dec[0].weight); db1, _ = gbuf(dec[0].bias)
-            sgemm(dh1d, F32, 1, 128, dec_in, F32, in_dim, 1, 128, in_dim, g_count, dw1, F32, in_dim)
-            colsum(dh1d, F32, g_count, 128, 128, db1)
-            dpooled = _f32((g_count, in_dim), dev)
-            if sv.mlp is None:
-                sgemm(dh1d, F32, 128, 1, d["w1"], F32, in_dim, 1, g_count, in_dim, 128, dpooled, F32, in_dim)
-            else:                                                   # through relu(Linear(512, 512)) of MLPPooling
-                lin, wp = sv.mlp
-                dpm = _f32((g_count, 512), dev)
-                sgemm(dh1d, F32, 128, 1, d["w1"], F32, 512, 1, g_count, 512, 128, dpm, F32, 512, mask=dec_in, mask_ld=512)
-                dwp, _ = gbuf(lin.weight); dbp, _ = gbuf(lin.bias)
-                sgemm(dpm, F32, 1, 512, sv.raw, F32, 512, 1, 512, 512, g_count, dwp, F32, 512)
-                colsum(dpm, F32, g_count, 512, 512, dbp)
-                sgemm(dpm, F32, 512, 1, wp, F32, 512, 1, g_count, 512, 512, dpooled, F32, 512)
-            # ---- get_pooling_layer backward
-            dcur = Activation(n, 512, prec, dev)
-            capi.pool_backward(dpooled.data_ptr(), in_dim, sv.idx.graph_ptr.data_ptr(), g_count,
-                               capi.POOL_MODES[model.pooling_layer], n, dcur.data.data_ptr(), code, s)
+        grads = GradStore(dev)
+        dcur = head_backward(model, sv, dpred, n, prec, grads)
         dy2: Optional[Activation] = None
 
         # ---- message passing layers, last to first
@@ -306,7 +382,7 @@ class SageTrainFunction(torch.autograd.Function):
             dzs = Activation(n, 512, prec, dev) if mean else dz
             g = Activation(n, 512, prec, dev) if residual else None
             if bn is not None:
-                dgam, acc_g = gbuf(bn.weight); dbet, _ = gbuf(bn.bias)
+                dgam, acc_g = grads.get(bn.weight); dbet, _ = grads.get(bn.bias)
                 a_vec, shift_vec, mean_vec, invstd_vec = vec[0], vec[1], vec[2], vec[3]
             else:
                 dgam = dbet = mean_vec = invstd_vec = None
@@ -322,13 +398,13 @@ class SageTrainFunction(torch.autograd.Function):
             dz.refresh_split()
             if mean:
                 dzs.refresh_split()
-            # weight gradients: split-K over nodes on the tensor cores
+            # weight gradients: split over nodes on the tensor cores, operands read where they lie (MN-major)
             with engine.TIMERS.span("train_wgrad"):
-                dwl, acc_l = gbuf(conv.lin_l.weight)
-                dwr, acc_r = gbuf(conv.lin_r.weight)
-                weight_grad_mn(dz.data, agg.data, code, n, dwl, acc_l)       # MN-major operands, read where they lie
+                dwl, acc_l = grads.get(conv.lin_l.weight)
+                dwr, acc_r = grads.get(conv.lin_r.weight)
+                weight_grad_mn(dz.data, agg.data, code, n, dwl, acc_l)
                 weight_grad_mn(dz.data, x_in.data, code, n, dwr, acc_r)
-                dbl, acc_b = gbuf(conv.lin_l.bias)
+                dbl, acc_b = grads.get(conv.lin_l.bias)
                 colsum(dz.data, code, n, 512, 512, dbl, accumulate=acc_b)
             # input gradient: dx = dz Wr + A^T (dz/deg Wl)  (+ g, added by the next iteration through dy2)
             if id(conv) not in tpacks:
@@ -344,43 +420,14 @@ class SageTrainFunction(torch.autograd.Function):
                 engine.gemm512(engine._segments(dz, wrt), n, prec, dx, residual=sbuf.data.data_ptr(), ldr=512)
             dcur, dy2 = dx, g
         # ---- encoder backward (dy2 is None here: layer 0 has no skip)
-        enc = model.node_encoder
-        dx0 = dcur.data
-        with engine.TIMERS.span("train_encoder_bwd"):
-            w3 = enc[4].weight.detach().float().contiguous()          # [512, 128]
-            w2 = enc[2].weight.detach().float().contiguous()
-            dw3e, _ = gbuf(enc[4].weight); db3e, _ = gbuf(enc[4].bias)
-            # dW3 = dx0^T h2 (reduction over nodes) on the split-K tensor-core path
-            tmp = _f32((512, 512), dev)
-            weight_grad_mn(dx0, sv.h2.data, code, n, tmp, False)             # columns >= 128 of tmp come out 0
-            dw3e.copy_(tmp[:, :128])
-            colsum(dx0, code, n, 512, 512, db3e)
-            # dh2 = (dx0 W3) [h2 > 0]: W3^T zero-padded to 512 output rows on the tensor cores, then mask + narrow
-            w3t_pad = torch.zeros((512, 512), dtype=torch.float32, device=dev)
-            capi.transpose_chunks(w3.data_ptr(), F32, 512, 128, 128, 1, 512, w3t_pad.data_ptr(), s)
-            full = Activation(n, 512, prec, dev)
-            engine.gemm512(engine._segments(dcur, engine.pack_linear(w3t_pad, prec)), n, prec, full)
-            dh2 = _f32((n, 128), dev)
-            capi.mask_narrow(full.data.data_ptr(), code, 512, sv.h2.data.data_ptr(), code, 128, n, 128, dh2.data_ptr(), s)
-            dw2e, _ = gbuf(enc[2].weight); db2e, _ = gbuf(enc[2].bias)
-            sgemm(dh2, F32, 1, 128, sv.h1, F32, 64, 1, 128, 64, n, dw2e, F32, 64)
-            colsum(dh2, F32, n, 128, 128, db2e)
-            dh1 = _f32((n, 64), dev)
-            sgemm(dh2, F32, 128, 1, w2, F32, 64, 1, n, 64, 128, dh1, F32, 64, mask=sv.h1, mask_ld=64)
-            dw1e, _ = gbuf(enc[0].weight); db1e, _ = gbuf(enc[0].bias)
-            sgemm(dh1, F32, 1, 64, sv.x, F32, f, 1, 64, f, n, dw1e, F32, f)
-            colsum(dh1, F32, n, 64, 64, db1e)
+        encoder_backward(model.node_encoder, sv.x, sv.h1, sv.h2, dcur, prec, grads)
         ctx.sv = None
-        out: List[Optional[torch.Tensor]] = []
-        for p_ in ctx.params:
-            t = grads.get(id(p_))
-            out.append(None if t is None else t.to(p_.dtype))
-        return (None, None, None, None, None, *out)
+        return (None, None, None, None, None, *grads.for_params(ctx.params))
 
 
 def trainable_parameters(model) -> List[torch.nn.Parameter]:
-    """Parameters the GraphSAGE training step produces gradients for (the reference registers more
-    modules than a given `model_name` uses: Models/BuckGNN.py:164,184-187)."""
+    """Parameters the training step produces gradients for (the reference registers more modules than a given
+    `model_name` uses: Models/BuckGNN.py:164,184-187)."""
     ps: List[torch.nn.Parameter] = []
     seen = set()
 
@@ -388,21 +435,33 @@ def trainable_parameters(model) -> List[torch.nn.Parameter]:
         if p is not None and id(p) not in seen:
             seen.add(id(p)); ps.append(p)
 
-    for m in (model.node_encoder[0], model.node_encoder[2], model.node_encoder[4]):
-        add(m.weight); add(m.bias)
+    def add_seq(seq):
+        for m in seq:
+            if isinstance(m, torch.nn.Linear):
+                add(m.weight); add(m.bias)
+
+    add_seq(model.node_encoder)
+    if model.model_name in ("EA_GNN", "EA_GNN_Shared"):
+        add_seq(model.edge_encoder)
+        blocks = [model.shared_gn_block] if model.model_name == "EA_GNN_Shared" else list(model.gn_blocks)
+        for blk in blocks:
+            for seq in (blk.edge_mlp, blk.node_mlp_phi, blk.node_mlp_gamma, blk.node_mlp_beta):
+                add_seq(seq)
     for conv, bn in model._sage_layers():
         add(conv.lin_l.weight); add(conv.lin_l.bias); add(conv.lin_r.weight)
         if bn is not None:
             add(bn.weight); add(bn.bias)
     if model.pooling_layer in ("mlp", "mlp_no_super"):
         add(model.pooling_mpl.mlp[0].weight); add(model.pooling_mpl.mlp[0].bias)
-    for m in (model.decoder[0], model.decoder[2], model.decoder[4]):
-        add(m.weight); add(m.bias)
+    add_seq(model.decoder)
     return ps
 
 
-def forward_train(model, x, edge_index, batch, seed: Optional[int] = None) -> torch.Tensor:
+def forward_train(model, x, edge_index, batch, seed: Optional[int] = None, edge_attr=None) -> torch.Tensor:
     if seed is None:                                    # one draw from torch's generator per step, like nn.Dropout
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     params = trainable_parameters(model)
+    if model.model_name in ("EA_GNN", "EA_GNN_Shared"):
+        from .train_eagnn import EAGNNTrainFunction
+        return EAGNNTrainFunction.apply(model, x, edge_index, edge_attr, batch, seed, *params)
     return SageTrainFunction.apply(model, x, edge_index, batch, seed, *params)

@@ -294,6 +294,18 @@ int bg_sgemm(const void* a, int a_dtype, int64_t sam, int64_t sak, const void* b
              int64_t m, int64_t n, int64_t k, const float* bias, int relu, const void* mask, int mask_dtype,
              int64_t mask_ld, void* out, int out_dtype, int64_t ldo, int accumulate,
              void* workspace, size_t workspace_bytes, void* stream);
+/* Elementwise pieces of the EA-GNN training step ([n_rows, 512] node or edge tensors of `dtype`):
+ * bg_dropout_residual: y = dropout(x + x_prev)  -- the wrapper's skip + Dropout, Models/BuckGNN.py:382-386 (x_prev nullable).
+ * bg_grad_mask:        out = dropout'(dy + dy2) * [act > 0]  (dy2, act nullable; dropout_p = 0: none) -- Dropout and
+ *                      ReLU backward in one pass.
+ * bg_segment_expand:   out[s] = src[r] (/ count_r when mean != 0) for every CSR slot s of row r -- the backward of
+ *                      torch_scatter.scatter_mean(messages, row) (:561) and of the row-gather x[row]. */
+int bg_dropout_residual(const void* x, const void* x_prev, void* y, int dtype, int64_t n_rows, float dropout_p,
+                        uint64_t seed, void* stream);
+int bg_grad_mask(const void* dy, const void* dy2, const void* act, void* out, int dtype, int64_t n_rows, float dropout_p,
+                 uint64_t seed, void* stream);
+int bg_segment_expand(const void* src, const int32_t* rowptr, int64_t n_rows, int mean, void* out, int dtype, void* stream);
+
 /* Device-side collate: PyG `DataLoader` / `Batch.from_data_list` for a dataset kept in HBM in
  * concatenated form -- x_all [sum n, F], ei_all [2, E_all] with node ids LOCAL to their graph (as
  * GraphCreate.py:417-432 emits them), ea_all [E_all, Fe], y_all [G_all], node_ptr / edge_ptr [G_all+1] int64.

@@ -392,3 +392,66 @@ def test_weight_gradient_mn_major(precision, n):
     narrow = actd[:, :128].contiguous()
     train.weight_grad_mn(dzd, narrow, code, n, out, accumulate=False)
     assert _rel(out.cpu()[:, :128], want[:, :128]) < tol and float(out[:, 128:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("model_name,precision,layers,p,pooling", [
+    ("EA_GNN", "tf32", 3, 0.0, "mean"),
+    ("EA_GNN", "tf32", 4, 0.1, "mean"),
+    ("EA_GNN_Shared", "tf32", 3, 0.0, "mean_no_super"),
+    ("EA_GNN", "bf16", 2, 0.0, "mean"),
+])
+def test_eagnn_training_step_gradients_match_oracle(model_name, precision, layers, p, pooling):
+    """loss.backward() through the GraphNetBlock stack (Models/BuckGNN.py:375-387, 528-566) against autograd
+    through the oracle, with the dropout masks and the ReLU masks of our forward (see _MaskedReLU)."""
+    ref, ours = _train_pair(model_name, precision, layers, p, pooling)
+    b = make_batch(4, nx=9, ny=8, stiffened=True)
+    n, ne = b.num_nodes, b.num_edges
+    seed = 31337
+    bd = b.to(DEV)
+    got_raw = train.forward_train(ours, bd.x, bd.edge_index, bd.batch, seed=seed, edge_attr=bd.edge_attr)
+    got = got_raw.squeeze()
+    y = torch.randn(4)
+    loss = F.mse_loss(got, y.to(DEV))
+    saved = got_raw.grad_fn.sv
+    perm = saved.idx.perm[:ne].long().cpu()                  # our edge tensors are in CSR-by-row order
+    inv = torch.empty_like(perm); inv[perm] = torch.arange(ne)
+    on = lambda act, edge: ((act.data.float() > 0).float().cpu()[inv] if edge else (act.data.float() > 0).float().cpu())
+    masks = {"he": [], "hm": [], "g1": [], "t": []}
+    for (_, _, _, he, _, hm, _, g1, _, t, _) in saved.layers:
+        masks["he"].append(on(he, True)); masks["hm"].append(on(hm, True))
+        masks["g1"].append(on(g1, False)); masks["t"].append(on(t, False))
+    head_masks = [(saved.h1d > 0).float().cpu(), (saved.h2d > 0).float().cpu()]
+    loss.backward()
+    blocks = [ref.shared_gn_block] if model_name == "EA_GNN_Shared" else list(ref.gn_blocks)
+    for k, blk in enumerate(blocks):
+        pick = (lambda name: masks[name]) if model_name == "EA_GNN_Shared" else (lambda name: [masks[name][k]])
+        blk.edge_mlp[1] = _MaskedReLU(pick("he")); blk.node_mlp_phi[1] = _MaskedReLU(pick("hm"))
+        blk.node_mlp_gamma[1] = _MaskedReLU(pick("g1")); blk.node_mlp_beta[1] = _MaskedReLU(pick("t"))
+    ref.decoder[1], ref.decoder[3] = _MaskedReLU(head_masks[:1]), _MaskedReLU(head_masks[1:])
+    if p > 0:                                                # x and e dropout masks, in the oracle's call order
+        dm = []
+        for i in range(layers):
+            kx = torch.empty(n, 512, dtype=torch.uint8, device=DEV)
+            ke = torch.empty(ne, 512, dtype=torch.uint8, device=DEV)
+            capi.dropout_mask(train.layer_seed(seed, 2 * i), p, n, kx.data_ptr(), _stream())
+            capi.dropout_mask(train.layer_seed(seed, 2 * i + 1), p, ne, ke.data_ptr(), _stream())
+            dm += [kx.cpu().float(), ke.cpu().float()[inv]]
+        ref.dropout = _MaskedDropout(dm, p)
+    want, _ = ref(b.x, b.edge_index, b.edge_attr, b.batch)
+    F.mse_loss(want, y).backward()
+    assert _rel(got.detach().cpu(), want.detach()) < (3e-2 if precision == "bf16" else 3e-3)
+    tol = {"tf32": 1e-2, "bf16": 1.5e-1}[precision]
+    ref_p, our_p = dict(ref.named_parameters()), dict(ours.named_parameters())
+    bad, checked = [], 0
+    for name, rp in ref_p.items():
+        op = our_p[name]
+        if rp.grad is None:
+            assert op.grad is None, name
+            continue
+        assert op.grad is not None, name
+        err = _rel(op.grad.cpu(), rp.grad)
+        if rp.grad.norm().item() > 1e-12 and not err < tol:
+            bad.append(f"{name}: rel err {err:.3e} >= {tol}")
+        checked += 1
+    assert not bad, "\n".join(bad)
+    assert checked >= 20

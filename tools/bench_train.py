@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--precision", default="tf32")
+    ap.add_argument("--model", default="GraphSage_meanAggr", help="GraphSage_*Aggr | EA_GNN | EA_GNN_Shared")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -38,10 +39,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     capi.device_check()
     torch.manual_seed(0)                                   # same initial weights on every rank
-    model = BuckGNN(16, 5, 512, 6, "mean", model_name="GraphSage_meanAggr", dropout_rate=0.1,
+    model = BuckGNN(16, 5, 512, 6, "mean", model_name=args.model, dropout_rate=0.1,
                     train_precision=args.precision).to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    b = config_batch(3, rank=rank, num_graphs=args.graphs).to(dev)
+    stiff = args.model.startswith("EA_GNN")              # the EA-GNN configs use the stiffened plates (cfg 3)
+    b = config_batch(2 if stiff else 3, rank=rank, num_graphs=args.graphs).to(dev)
     y = b.y.to(dev).abs() + 0.5
     params = train.trainable_parameters(model)
     ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -86,7 +88,7 @@ def main():
     if rank == 0:
         n_grad = sum(p.numel() for p in params)
         print(json.dumps({
-            "config": "cfg4: training step, GraphSage_meanAggr 6x512, dropout 0.1, Adam, batch "
+            "config": f"cfg4: training step, {args.model} 6x512, dropout 0.1, Adam, batch "
                       f"{args.graphs} graphs per GPU, graph-sharded x{world}, gradient all-reduce (NCCL, one flat bucket)",
             "n_gpus": world, "graphs_per_gpu": args.graphs, "nodes_per_gpu": b.num_nodes, "edges_per_gpu": b.num_edges,
             "train_precision": args.precision, "ms_per_step": ms, "graphs_per_s": world * args.graphs / (ms * 1e-3),
