@@ -20,7 +20,7 @@ BG_BF16, BG_F32, BG_F16 = 0, 1, 2
 BG_AGGR_MEAN, BG_AGGR_SUM, BG_AGGR_MAX = 0, 1, 2
 BG_BIG_ROW_THRESHOLD = 64
 BG_MAX_GEMM_SEGMENTS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 AGGR_CODES = {"mean": BG_AGGR_MEAN, "sum": BG_AGGR_SUM, "add": BG_AGGR_SUM, "max": BG_AGGR_MAX}
 
@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = (
     "bg_transpose_chunks", "bg_mask_narrow", "bg_reduce_partials", "bg_colsum_workspace_bytes", "bg_colsum", "bg_pool_backward",
     "bg_sgemm_workspace_bytes", "bg_sgemm", "bg_eigen_loss", "bg_dropout_mask", "bg_collate_ptr", "bg_collate",
     "bg_dropout_residual", "bg_grad_mask", "bg_segment_expand",
+    "bg_sag_workspace_bytes", "bg_sag_select", "bg_sag_connect", "bg_gather_rows", "bg_index_invert", "bg_index_gather",
 )
 
 
@@ -109,6 +110,13 @@ _SIGNATURES = {
     "bg_collate_ptr": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
     "bg_collate": (C.c_int, [_P, _I32, _P, _I64, _P, _I32, _P, _P, _I64, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "bg_eigen_loss": (C.c_int, [_P, _P, _I64, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P]),
+    "bg_sag_workspace_bytes": (C.c_int, [_I64, _I64, _I64, _SZP]),
+    "bg_sag_select": (C.c_int, [_P, C.c_int, _I64, _P, _P, _P, _I32, _P, _P, C.c_float, C.c_float, _P, _I64, C.c_float,
+                                _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "bg_sag_connect": (C.c_int, [_P, _I64, _I64, _P, _I64, _P, _P, _P, C.c_size_t, _P]),
+    "bg_gather_rows": (C.c_int, [_P, C.c_int, _I64, _P, _P, _I64, _P, _I64, _P]),
+    "bg_index_invert": (C.c_int, [_P, _I64, _P, _P]),
+    "bg_index_gather": (C.c_int, [_P, _P, _I64, _P, _P]),
 }
 
 
@@ -347,3 +355,32 @@ def grad_mask(dy, dy2, act, out, dtype, n_rows, dropout_p, seed, stream):
 
 def segment_expand(src, rowptr, n_rows, mean, out, dtype, stream):
     _check(load().bg_segment_expand(src, rowptr, n_rows, int(bool(mean)), out, dtype, stream), "bg_segment_expand")
+
+
+# ----------------------------------------------------------------------------- SAGPooling
+def sag_workspace_bytes(n_nodes: int, n_edges: int, n_graphs: int) -> int:
+    return _query("bg_sag_workspace_bytes", n_nodes, n_edges, n_graphs)
+
+
+def sag_select(x, dtype, n_nodes, rowptr, col, big_rows, n_big, w_l, w_r, bias, sign, graph_ptr, n_graphs, ratio,
+               edge_index, n_edges, score, new_id, perm, batch_out, score_out, new_graph_ptr, info, ws, ws_bytes, stream):
+    _check(load().bg_sag_select(x, dtype, n_nodes, rowptr, col, big_rows, n_big, w_l, w_r, bias, sign, graph_ptr,
+                                n_graphs, ratio, edge_index, n_edges, score, new_id, perm, batch_out, score_out,
+                                new_graph_ptr, info, ws, ws_bytes, stream), "bg_sag_select")
+
+
+def sag_connect(edge_index, n_edges, n_nodes, new_id, n_edges_out, edge_index_out, kept_edge, ws, ws_bytes, stream):
+    _check(load().bg_sag_connect(edge_index, n_edges, n_nodes, new_id, n_edges_out, edge_index_out, kept_edge, ws,
+                                 ws_bytes, stream), "bg_sag_connect")
+
+
+def gather_rows(x, dtype, ldx, row_index, row_scale, n_rows_out, out, ldo, stream):
+    _check(load().bg_gather_rows(x, dtype, ldx, row_index, row_scale, n_rows_out, out, ldo, stream), "bg_gather_rows")
+
+
+def index_invert(perm, n, out, stream):
+    _check(load().bg_index_invert(perm, n, out, stream), "bg_index_invert")
+
+
+def index_gather(table, idx, n, out, stream):
+    _check(load().bg_index_gather(table, idx, n, out, stream), "bg_index_gather")

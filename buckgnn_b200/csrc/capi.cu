@@ -10,6 +10,7 @@
 #include "gemm_tc.cuh"
 #include "pool_head.cuh"
 #include "train.cuh"
+#include "sag_pool.cuh"
 
 namespace bg {
 
@@ -601,6 +602,105 @@ static inline DropArgs drop_args(float p, uint64_t seed) {
   else if ((dtype) == BG_F16) { using T = __half; CALL; }          \
   else if ((dtype) == BG_F32) { using T = float; CALL; }           \
   else return fail(BG_ERR_INVALID, "bad dtype");
+
+// ------------------------------------------------------------------ SAGPooling (GraphSAGE_SAG / EAGNN_SAG)
+int bg_sag_workspace_bytes(int64_t N, int64_t E, int64_t G, size_t* bytes_host) {
+  if (!bytes_host || N < 0 || E < 0 || G < 0) return fail(BG_ERR_INVALID, "bg_sag_workspace_bytes: bad argument");
+  *bytes_host = sag_workspace_layout(nullptr, N, E, G).bytes;
+  return BG_OK;
+}
+
+int bg_sag_select(const void* x, int dtype, int64_t N, const int32_t* rowptr, const int32_t* col,
+                  const int32_t* big_rows, int32_t n_big, const float* w_l, const float* w_r, float bias, float sign,
+                  const int32_t* graph_ptr, int64_t G, float ratio, const int64_t* edge_index, int64_t E,
+                  float* score, int32_t* new_id, int32_t* perm, int64_t* batch_out, float* score_out,
+                  int32_t* new_graph_ptr, int32_t* info, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N < 0 || E < 0 || G < 0 || N >= 0x7fffffffLL || E >= 0x7fffffffLL || G >= 0x7fffffffLL || n_big < 0)
+    return fail(BG_ERR_INVALID, "bg_sag_select: sizes out of range");
+  if (!(ratio > 0.f) || ratio > 1.f) return fail(BG_ERR_INVALID, "bg_sag_select: ratio must be in (0, 1]");
+  if (!info || !new_graph_ptr || !graph_ptr || !workspace) return fail(BG_ERR_INVALID, "bg_sag_select: null pointer");
+  if (N > 0 && (!x || !aligned16(x) || !rowptr || !w_l || !w_r || !score || !new_id || !perm || !batch_out || !score_out))
+    return fail(BG_ERR_INVALID, "bg_sag_select: null or misaligned pointer");
+  if ((E > 0 && (!edge_index || !col)) || (n_big > 0 && !big_rows)) return fail(BG_ERR_INVALID, "bg_sag_select: null pointer");
+  SagWorkspace w = sag_workspace_layout(workspace, N, E, G);
+  if (workspace_bytes < w.bytes) return fail(BG_ERR_WORKSPACE, "bg_sag_select: workspace too small");
+  const int sms = sm_count();
+  BG_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t) * 2, stream));
+  if (N > 0) {
+    const unsigned grid = grid_for(N * 32, kSagWarps * 32, sms * 8);
+    BG_BY_DTYPE(dtype, (k_sag_dots<T><<<grid, kSagWarps * 32, 0, stream>>>(static_cast<const T*>(x), N, w_l, w_r, w.p, w.q)));
+    BG_LAUNCH_OK();
+    k_sag_score<<<grid_for(N * 8, 256, sms * 8), 256, 0, stream>>>(rowptr, col, w.p, w.q, bias, sign, N, score);
+    BG_LAUNCH_OK();
+    if (n_big > 0) {
+      k_sag_score_big<<<(unsigned)n_big, 256, 0, stream>>>(rowptr, col, big_rows, w.p, w.q, bias, sign, score);
+      BG_LAUNCH_OK();
+    }
+  }
+  k_sag_plan<<<1, 1024, 0, stream>>>(graph_ptr, (int32_t)G, ratio, new_graph_ptr, w.tile_ptr, info);
+  BG_LAUNCH_OK();
+  if (N > 0 && G > 0) {
+    const unsigned tiles = (unsigned)(ceil_div64(N, kRankTileI) + G);       // >= sum_g ceil(n_g / tile)
+    k_sag_rank<<<tiles, kRankThreads, 0, stream>>>(score, graph_ptr, (int32_t)G, new_graph_ptr, w.tile_ptr, new_id, perm,
+                                                  batch_out, score_out);
+    BG_LAUNCH_OK();
+  }
+  if (E > 0) {
+    k_sag_edge_count<<<(unsigned)w.n_edge_blocks, 1024, 0, stream>>>(edge_index, E, N, new_id, w.block_sums);
+    BG_LAUNCH_OK();
+    k_sag_scan_sums<<<1, 1024, 0, stream>>>(w.block_sums, w.n_edge_blocks, info + 1);
+    BG_LAUNCH_OK();
+  }
+  return BG_OK;
+}
+
+int bg_sag_connect(const int64_t* edge_index, int64_t E, int64_t N, const int32_t* new_id, int64_t E_out,
+                   int64_t* edge_index_out, int32_t* kept_edge, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N < 0 || E < 0 || E_out < 0 || E_out > E) return fail(BG_ERR_INVALID, "bg_sag_connect: bad size");
+  if (E_out == 0) return BG_OK;
+  if (!edge_index || !new_id || !edge_index_out || !workspace) return fail(BG_ERR_INVALID, "bg_sag_connect: null pointer");
+  SagWorkspace w = sag_workspace_layout(workspace, N, E, 0);       // the block offsets bg_sag_select left behind
+  if (workspace_bytes < w.bytes) return fail(BG_ERR_WORKSPACE, "bg_sag_connect: workspace too small");
+  k_sag_edge_write<<<(unsigned)w.n_edge_blocks, 1024, 0, stream>>>(edge_index, E, N, new_id, w.block_sums, E_out,
+                                                                  edge_index_out, kept_edge);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_gather_rows(const void* x, int dtype, int64_t ldx, const int32_t* row_index, const float* row_scale,
+                   int64_t n_rows_out, void* out, int64_t ldo, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_rows_out < 0 || ldx < kHidden || ldo < kHidden) return fail(BG_ERR_INVALID, "bg_gather_rows: bad size");
+  if (n_rows_out == 0) return BG_OK;
+  if (!x || !out || !row_index || !aligned16(x) || !aligned16(out)) return fail(BG_ERR_INVALID, "bg_gather_rows: null or misaligned pointer");
+  const int esz = (dtype == BG_F32) ? 4 : 2;
+  if ((ldx * esz) % 16 != 0 || (ldo * esz) % 16 != 0) return fail(BG_ERR_INVALID, "bg_gather_rows: rows must be 16-byte aligned");
+  const unsigned grid = grid_for(n_rows_out * 32, kSagWarps * 32, sm_count() * 8);
+  BG_BY_DTYPE(dtype, (k_gather_rows<T><<<grid, kSagWarps * 32, 0, stream>>>(static_cast<const T*>(x), ldx, row_index, row_scale,
+                                                                          n_rows_out, static_cast<T*>(out), ldo)));
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_index_invert(const int32_t* perm, int64_t n, int32_t* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n < 0 || (n > 0 && (!perm || !out))) return fail(BG_ERR_INVALID, "bg_index_invert: bad argument");
+  if (n == 0) return BG_OK;
+  k_index_invert<<<grid_for(n, 256, sm_count() * 16), 256, 0, stream>>>(perm, n, out);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_index_gather(const int32_t* table, const int32_t* idx, int64_t n, int32_t* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n < 0 || (n > 0 && (!table || !idx || !out))) return fail(BG_ERR_INVALID, "bg_index_gather: bad argument");
+  if (n == 0) return BG_OK;
+  k_index_gather<<<grid_for(n, 256, sm_count() * 16), 256, 0, stream>>>(table, idx, n, out);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
 
 int bg_train_workspace_bytes(int64_t N, size_t* bytes_host) {
   if (!bytes_host || N < 0) return fail(BG_ERR_INVALID, "bg_train_workspace_bytes: bad argument");

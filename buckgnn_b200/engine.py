@@ -592,3 +592,93 @@ def gnblock_layer(x: Activation, e: Activation, buf: GNBlockBuffers, idx: GraphI
     if e_next is not None:
         buf.e_alt = e
     return x_next, e_next
+
+
+# ----------------------------------------------------------------------------- SAGPooling (GraphSAGE_SAG / EAGNN_SAG)
+@dataclass
+class SagPoolResult:
+    """What PyG `SAGPooling.forward` returns (Models/BuckGNN.py:365-367, 502-504), plus the index maps."""
+    x: Activation                 # [N', 512] = x[perm] * score[perm]
+    edge_index: torch.Tensor      # [2, E'] int64, relabelled, original edge order
+    batch: torch.Tensor           # [N'] int64
+    perm: torch.Tensor            # [N'] int32: old node id of each kept row
+    score: torch.Tensor           # [N'] f32 = tanh score of the kept rows
+    new_id: torch.Tensor          # [N] int32: new row of an old node, -1 if dropped
+    kept_edge: Optional[torch.Tensor]   # [E'] int32: old edge id of each kept edge
+    n_nodes: int
+    n_edges: int
+    graph_ptr: torch.Tensor       # [G+1] int32 offsets of the pooled graphs
+    all_scores: torch.Tensor      # [N] f32 score of every node
+
+
+def pack_sag_pool(pool) -> Dict[str, object]:
+    gnn = pool.gnn
+    f32 = lambda t: t.detach().float().contiguous().view(-1)
+    return {"w_l": f32(gnn.lin_l.weight), "w_r": f32(gnn.lin_r.weight), "bias": float(gnn.lin_l.bias.detach().float().item()),
+            "ratio": float(pool.ratio)}
+
+
+def sag_pool(x: Activation, csr_by_target: GraphIndex, graph_ptr: torch.Tensor, n_graphs: int,
+             edge_index: torch.Tensor, w: Dict[str, object], sign: float = 1.0, want_kept_edges: bool = False) -> SagPoolResult:
+    """SAGPooling on the device: score GNN + per-graph top-k + row gather + edge filter.  Two result words
+    (N', E') come back to the host through pinned memory -- PyG syncs at the same place (`num_nodes.max().item()`
+    inside `topk`)."""
+    dev = x.data.device
+    n, g = csr_by_target.n_nodes, int(n_graphs)
+    edge_index = edge_index.contiguous()
+    e = edge_index.shape[1]
+    s = _stream()
+    f32 = dict(dtype=torch.float32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    score, score_sel = torch.empty(max(n, 1), **f32), torch.empty(max(n, 1), **f32)
+    new_id, perm = torch.empty(max(n, 1), **i32), torch.empty(max(n, 1), **i32)
+    batch_out = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    new_ptr = torch.empty(g + 1, **i32)
+    info = torch.zeros(2, **i32)
+    ws_bytes = capi.sag_workspace_bytes(n, e, g)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    idx = csr_by_target
+    with TIMERS.span("sag_select"):
+        capi.sag_select(x.data.data_ptr(), x.code, n, idx.rowptr.data_ptr(), idx.col.data_ptr(), idx.big_rows.data_ptr(),
+                        idx.n_big, w["w_l"].data_ptr(), w["w_r"].data_ptr(), w["bias"], float(sign),
+                        graph_ptr.data_ptr(), g, w["ratio"], edge_index.data_ptr(), e,
+                        score.data_ptr(), new_id.data_ptr(), perm.data_ptr(), batch_out.data_ptr(), score_sel.data_ptr(),
+                        new_ptr.data_ptr(), info.data_ptr(), ws.data_ptr(), ws_bytes, s)
+    host = torch.zeros(2, dtype=torch.int32).pin_memory()
+    capi.publish_words(info.data_ptr(), host.data_ptr(), 2, s)
+    done = torch.cuda.Event()
+    done.record()
+    done.synchronize()
+    n2, e2 = host.tolist()
+    x_new = Activation(n2, 512, x.precision, dev)
+    ei_new = torch.empty((2, e2), dtype=torch.int64, device=dev)
+    kept = torch.empty(max(e2, 1), **i32) if want_kept_edges else None
+    with TIMERS.span("sag_connect"):
+        capi.gather_rows(x.data.data_ptr(), x.code, x.data.shape[1], perm.data_ptr(), score.data_ptr(), n2,
+                         x_new.data.data_ptr(), 512, s)
+        x_new.refresh_split()
+        capi.sag_connect(edge_index.data_ptr(), e, n, new_id.data_ptr(), e2, ei_new.data_ptr(), _p(kept),
+                         ws.data_ptr(), ws_bytes, s)
+    return SagPoolResult(x_new, ei_new, batch_out[:n2], perm[:n2], score_sel[:n2], new_id[:n], kept, n2, e2, new_ptr,
+                         score[:n])
+
+
+def regather_edge_rows(e: Activation, idx_old: GraphIndex, idx_new: GraphIndex, kept_edge: torch.Tensor) -> Activation:
+    """Edge features of the kept edges, moved from the old CSR slot order to the new one (EAGNN_SAG:
+    `edge_attr[mask]` of PyG filter_adj, for edge tensors that live in CSR order)."""
+    dev = e.data.device
+    s = _stream()
+    e_old, e_new = idx_old.n_edges, idx_new.n_edges
+    i32 = dict(dtype=torch.int32, device=dev)
+    out = Activation(max(e_new, 1), 512, e.precision, dev)
+    if e_new == 0:
+        return out
+    inv = torch.empty(e_old, **i32)
+    capi.index_invert(idx_old.perm.data_ptr(), e_old, inv.data_ptr(), s)            # old edge id -> old slot
+    orig = torch.empty(e_new, **i32)
+    capi.index_gather(kept_edge.data_ptr(), idx_new.perm.data_ptr(), e_new, orig.data_ptr(), s)   # new slot -> old edge id
+    slot = torch.empty(e_new, **i32)
+    capi.index_gather(inv.data_ptr(), orig.data_ptr(), e_new, slot.data_ptr(), s)   # new slot -> old slot
+    capi.gather_rows(e.data.data_ptr(), e.code, e.data.shape[1], slot.data_ptr(), None, e_new, out.data.data_ptr(), 512, s)
+    out.refresh_split()
+    return out

@@ -79,6 +79,16 @@ class MLPPooling(nn.Module):
         self.mlp = nn.Sequential(nn.Linear(in_channels, hidden_channels), nn.ReLU())
 
 
+class SAGPooling(nn.Module):
+    """Parameter container with PyG `SAGPooling`'s names (`pool.gnn.lin_l.{weight,bias}`, `pool.gnn.lin_r.weight`;
+    reference `:203-208`, `:231-236`): the scoring GNN is `SAGEConv(in_channels, 1, aggr='add')`."""
+
+    def __init__(self, in_channels: int, ratio: float = 0.5, aggr: str = "add"):
+        super().__init__()
+        self.in_channels, self.ratio = in_channels, ratio
+        self.gnn = SAGEConv(in_channels, 1, normalize=False, aggr=aggr)
+
+
 def _output_dim(prediction_type, use_z_coord, use_rotations):
     if prediction_type == "buckling":
         return 1
@@ -100,8 +110,10 @@ class BuckGNN(nn.Module):
                  cache_index: bool = False, fold_encoder: bool = True, train_precision: str = "tf32"):
         super().__init__()
         if precision == "auto":
+            # the SAGPooling variants pick nodes by a discrete top-k on a score: 16-bit activations would pick
+            # different nodes near the threshold than the fp32 reference does, so they default to fp32 storage
             aggr = _SAGE_LISTS[model_name][1] if model_name in _SAGE_LISTS else (
-                "add" if model_name == "GraphSage_addAggr_Shared" else "mean")
+                "add" if model_name in ("GraphSage_addAggr_Shared", "GraphSAGE_SAG", "EAGNN_SAG") else "mean")
             precision = engine.default_precision(aggr)
         if precision not in engine.PRECISIONS:
             raise ValueError(f"precision must be \"auto\" or one of {engine.PRECISIONS}")
@@ -151,13 +163,33 @@ class BuckGNN(nn.Module):
         self.relu = nn.ReLU()
         self.dropout = nn.Dropout(p=dropout_rate)
         self.pooling_mpl = MLPPooling(h, h, h)
+        if model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):                 # reference :190-244 (registered after pooling_mpl)
+            n_before = num_layers // 2
+            n_after = num_layers - n_before
+            sage = model_name == "GraphSAGE_SAG"
+            mk = (lambda: SAGEConv(h, h, normalize=True, aggr="add")) if sage else (lambda: GraphNetBlock(h))
+            setattr(self, "sage_layers_1" if sage else "gnn_layers_1", nn.ModuleList([mk() for _ in range(n_before)]))
+            self.batch_norms_1 = nn.ModuleList([nn.BatchNorm1d(h) for _ in range(n_before)] if sage else [])
+            self.pool = SAGPooling(h, ratio=0.5, aggr="add")
+            setattr(self, "sage_layers_2" if sage else "gnn_layers_2", nn.ModuleList([mk() for _ in range(n_after)]))
+            self.batch_norms_2 = nn.ModuleList([nn.BatchNorm1d(h) for _ in range(n_after)] if sage else [])
+            # PyG >= 2.4 checkpoints carry `pool.select.weight` [1, 1]: SelectTopK multiplies the score by
+            # weight / |weight| before tanh, i.e. by its sign.  Older ones (the formulation restated here) do not.
+            self._sag_sign = 1.0
+            self._register_load_state_dict_pre_hook(self._absorb_select_weight)
         self._packs: Dict[str, object] = {}
         self._pack_sig = None
         self._index_cache = None
 
     # ------------------------------------------------------------------ weight packing
+    def _absorb_select_weight(self, state_dict, prefix, *args):
+        key = prefix + "pool.select.weight"
+        if key in state_dict:
+            w = float(state_dict.pop(key).reshape(-1)[0])
+            self._sag_sign = -1.0 if w < 0 else 1.0
+
     def _signature(self):
-        return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
+        return (self.precision, getattr(self, "_sag_sign", 1.0)) + tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
             tuple((b.data_ptr(), b._version) for b in self.buffers())
 
     def _sage_layers(self):
@@ -166,6 +198,8 @@ class BuckGNN(nn.Module):
             return [(c, bn) for c, bn in zip(convs, self.batch_norms)]
         if self.model_name == "GraphSage_addAggr_Shared":
             return [(self.shared_graphsage_block, None)] * self.num_layers
+        if self.model_name == "GraphSAGE_SAG":
+            return list(zip(self.sage_layers_1, self.batch_norms_1)) + list(zip(self.sage_layers_2, self.batch_norms_2))
         return []
 
     def _packed(self):
@@ -197,6 +231,8 @@ class BuckGNN(nn.Module):
         packs["layers"] = layers
         packs["layer0_folded"] = None
         sl = self._sage_layers()
+        if self.model_name == "GraphSAGE_SAG" and len(self.sage_layers_1) == 0:
+            sl = []                                   # num_layers == 1: the pooling runs on the encoder output itself
         if self.fold_encoder and sl and sl[0][0].aggr != "max":
             conv0, bn0 = sl[0]
             packs["layer0_folded"] = engine.pack_folded_layer0(enc[4], conv0, bn0, conv0.aggr, prec)
@@ -210,6 +246,15 @@ class BuckGNN(nn.Module):
                 packs["gn"] = [shared] * self.num_layers
             else:
                 packs["gn"] = [engine.pack_gnblock(b, prec) for b in self.gn_blocks]
+        if self.model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):
+            packs["sag_pool"] = engine.pack_sag_pool(self.pool)
+        if self.model_name == "EAGNN_SAG":
+            ee = self.edge_encoder
+            packs["edge_enc"] = {"w1": f32(ee[0].weight), "b1": f32(ee[0].bias), "w2": f32(ee[2].weight),
+                                 "b2": f32(ee[2].bias), "b3_host": engine.host_vector(ee[4].bias)}
+            packs["edge_enc_w3"] = engine.pack_linear(ee[4].weight, prec)
+            packs["gn1"] = [engine.pack_gnblock(b, prec) for b in self.gnn_layers_1]
+            packs["gn2"] = [engine.pack_gnblock(b, prec) for b in self.gnn_layers_2]
         self._packs, self._pack_sig = packs, sig
         return packs
 
@@ -226,8 +271,6 @@ class BuckGNN(nn.Module):
                 raise NotImplementedError("buckgnn_b200: training with max aggregation is not built")
         if self.hidden_channels != 512:
             raise NotImplementedError("buckgnn_b200: the tcgen05 path is built for hidden_channels=512")
-        if self.model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):
-            raise NotImplementedError(f"buckgnn_b200: model_name={self.model_name!r} (SAGPooling) is out of scope")
         if self.model_name in ("GraphSage_MLP", "GraphSage_addAggr_woBatchNorm", "GraphSage_sumAggr_woBatchNorm"):
             # the reference constructs the module lists these branches use only under other names
             raise AttributeError(f"'BuckGNN' object has no module list for model_name={self.model_name!r} "
@@ -249,6 +292,14 @@ class BuckGNN(nn.Module):
             from . import train
             return train.forward_train(self, x, edge_index, batch, edge_attr=edge_attr).squeeze(), batch
         with torch.no_grad():
+            if self.model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):
+                if node_level and "super" in self.pooling_layer:
+                    # the reference indexes the POOLED x with the un-pooled is_real_node mask here (:518-521)
+                    raise IndexError("The shape of the mask (is_real_node over all nodes) does not match the pooled node "
+                                     "tensor (same failure as the reference, Models/BuckGNN.py:521 after SAGPooling)")
+                fwd = self._forward_cuda_sag if self.model_name == "GraphSAGE_SAG" else self._forward_cuda_eagnn_sag
+                pred, pooled_batch = fwd(x, edge_index, edge_attr, batch, node_level)
+                return (pred if node_level else pred.squeeze()), pooled_batch      # `batch` was reassigned by self.pool (:365, :502)
             if self.model_name in ("EA_GNN", "EA_GNN_Shared"):
                 pred = self._forward_cuda_eagnn(x, edge_index, edge_attr, batch, node_level)
             else:
@@ -346,3 +397,95 @@ class BuckGNN(nn.Module):
         pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim, pooling=self.pooling_layer,
                                    pre=pre)                                                # reference :515-516
         return pred
+
+    # ------------------------------------------------------------------ SAGPooling variants
+    def _tail(self, cur, idx, packs, node_level, cg):
+        if node_level:
+            return engine.node_head(cur, idx.n_nodes, packs["node_head"], self.output_dim, cg)
+        pre = packs["pool_mlp"] if self.pooling_layer in ("mlp", "mlp_no_super") else None
+        pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim, pooling=self.pooling_layer, pre=pre)
+        return pred
+
+    def _forward_cuda_sag(self, x, edge_index, edge_attr, batch, node_level=False):
+        """`GraphSAGE_SAG` (reference :190-217, :493-511): num_layers // 2 SAGE('add') layers, SAGPooling(0.5),
+        the remaining layers on the pooled graph, every layer after the first with a skip."""
+        packs = self._packed()
+        prec, cg = self.precision, self.cta_group
+        x = x.detach().to(torch.float32).contiguous()
+        n = x.shape[0]
+        pending = engine.begin_graph_index(edge_index, batch, n)
+        layers = packs["layers"]
+        n_before = len(self.sage_layers_1)
+        folded = packs["layer0_folded"] if n_before > 0 else None
+        cur = Activation(n, 512, prec, x.device)
+        if folded is not None:
+            h = engine.encoder_hidden(x, packs["enc"], prec)
+        else:
+            engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg)
+        idx = pending.finish()
+        if n_before > 0:
+            nxt = Activation(n, 512, prec, x.device)
+            agg = Activation(n, 512, prec, x.device)
+            for i in range(n_before):
+                if i == 0 and folded is not None:
+                    engine.sage_layer0_folded(h, nxt, idx, folded, aggr="add", normalize=True, relu=True, cta_group=cg)
+                else:
+                    engine.sage_layer(cur, agg, nxt, idx, layers[i], aggr="add", normalize=True, relu=True,
+                                      residual=(i > 0), cta_group=cg)
+                cur, nxt = nxt, cur
+            del nxt, agg
+        pooled = engine.sag_pool(cur, idx, idx.graph_ptr, idx.n_graphs, edge_index, packs["sag_pool"], sign=self._sag_sign)
+        self.last_pool = pooled          # (perm, score, edge_index, batch) of the last forward, as self.pool returns them
+        idx2 = engine.build_graph_index(pooled.edge_index, pooled.batch, pooled.n_nodes)
+        cur = pooled.x
+        n2 = pooled.n_nodes
+        nxt = Activation(n2, 512, prec, x.device)
+        agg = Activation(n2, 512, prec, x.device)
+        for layer in layers[n_before:]:
+            engine.sage_layer(cur, agg, nxt, idx2, layer, aggr="add", normalize=True, relu=True, residual=True,
+                              cta_group=cg)
+            cur, nxt = nxt, cur
+        return self._tail(cur, idx2, packs, node_level, cg), pooled.batch
+
+    def _forward_cuda_eagnn_sag(self, x, edge_index, edge_attr, batch, node_level=False):
+        """`EAGNN_SAG` (reference :219-244, :354-373): GraphNetBlocks around a SAGPooling; the pooled edge features are
+        the rows of the kept edges."""
+        packs = self._packed()
+        prec, cg = self.precision, self.cta_group
+        x = x.detach().to(torch.float32).contiguous()
+        if not edge_attr.is_cuda:
+            raise RuntimeError("buckgnn_b200: `edge_attr` must be a CUDA tensor")
+        edge_attr = edge_attr.detach().to(torch.float32).contiguous()
+        n = x.shape[0]
+        pending = engine.begin_graph_index(edge_index, batch, n, key_row=0)       # GraphNetBlock direction (:553, :561)
+        pending_t = engine.begin_graph_index(edge_index, None, n, key_row=1)      # SAGEConv direction of the score GNN
+        cur = Activation(n, 512, prec, x.device)
+        engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg)
+        idx = pending.finish()
+        idx_t = pending_t.finish()
+        ne = idx.n_edges
+        e = Activation(max(ne, 1), 512, prec, x.device)
+        if ne > 0:
+            engine.encoder_forward(edge_attr, packs["edge_enc"], packs["edge_enc_w3"], prec, e, cg,
+                                   row_gather=idx.perm[:ne])
+        if packs["gn1"]:
+            ex = engine.edge_extras(idx, prec)
+            buf = engine.GNBlockBuffers(n, ne, prec, x.device)
+            for i, w in enumerate(packs["gn1"]):
+                cur, e_next = engine.gnblock_layer(cur, e, buf, idx, ex, w, skip=(i > 0), need_edges_out=True, cta_group=cg)
+                e = e_next
+        pooled = engine.sag_pool(cur, idx_t, idx.graph_ptr, idx.n_graphs, edge_index, packs["sag_pool"],
+                                 sign=self._sag_sign, want_kept_edges=True)
+        self.last_pool = pooled
+        idx2 = engine.build_graph_index(pooled.edge_index, pooled.batch, pooled.n_nodes, key_row=0)
+        e = engine.regather_edge_rows(e, idx, idx2, pooled.kept_edge)
+        cur = pooled.x
+        n2, ne2 = pooled.n_nodes, idx2.n_edges
+        ex2 = engine.edge_extras(idx2, prec)
+        buf2 = engine.GNBlockBuffers(n2, ne2, prec, x.device)
+        last = len(packs["gn2"]) - 1
+        for i, w in enumerate(packs["gn2"]):
+            cur, e_next = engine.gnblock_layer(cur, e, buf2, idx2, ex2, w, skip=True, need_edges_out=(i < last), cta_group=cg)
+            if e_next is not None:
+                e = e_next
+        return self._tail(cur, idx2, packs, node_level, cg), pooled.batch

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 4
+#define BG_ABI_VERSION 5
 
 typedef enum bg_status {
   BG_OK = 0,
@@ -230,6 +230,38 @@ int bg_pool_head(const void* x, int dtype, int64_t n_nodes, const int32_t* graph
 int bg_expand_rowptr(const int32_t* rowptr, int64_t n_rows, int64_t n_entries, int32_t* row_of, int32_t* iota,
                      void* nonempty, int nonempty_dtype, int as_count, void* stream);
 int bg_add(const void* a, const void* b, const void* c_or_null, void* out, int dtype, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ SAGPooling
+ * Replaces PyG `SAGPooling(hidden, ratio=0.5, GNN=SAGEConv, aggr='add')` of the `GraphSAGE_SAG` / `EAGNN_SAG`
+ * variants (constructed Models/BuckGNN.py:203-208, 231-236; applied :365-367, :502-504):
+ *    s      = tanh(sign * (w_l . sum_{j -> i} x_j + bias + w_r . x_i))      score GNN = SAGEConv(512, 1, aggr='add')
+ *    perm   = for each graph its ceil(ratio * n_g) highest-scoring nodes, descending score, ties by lower node id
+ *    x'     = x[perm] * s[perm];  batch' = batch[perm];  edge_index' = edges whose two endpoints are kept,
+ *             relabelled to the new row ids, original order (PyG `topk` / `filter_adj`).
+ * bg_sag_select (x [N,512] of `dtype`; rowptr/col/big_rows/n_big: bg_csr_build keyed by TARGET, key_row = 1;
+ *   w_l, w_r [512] f32 device = pool.gnn.lin_l.weight / lin_r.weight, bias = pool.gnn.lin_l.bias; sign = +1, or
+ *   the sign of `pool.select.weight` for checkpoints of PyG >= 2.4 whose SelectTopK rescales the score):
+ *    score [N] f32;  new_id [N] int32 = new row of a kept node, -1 for a dropped one;  perm [N'] int32 (buffer of N);
+ *    batch_out [N'] int64;  score_out [N'] f32 = s[perm];  new_graph_ptr [G+1] int32;
+ *    info[0] = N' (kept nodes), info[1] = E' (kept edges) -- read them back (bg_publish_words) before bg_sag_connect.
+ * bg_sag_connect: edge_index_out [2, E'] int64, kept_edge [E'] int32 (nullable) = original edge id of each kept
+ *   edge.  `workspace` must be the buffer bg_sag_select used, untouched in between (it holds the block offsets).
+ * bg_gather_rows: out[r, 0:512] = x[row_index[r], 0:512] * (row_scale ? row_scale[row_index[r]] : 1)  --
+ *   x[perm] * score[perm], and the edge-feature rows of the kept edges for EAGNN_SAG.
+ * bg_index_invert: out[perm[i]] = i;  bg_index_gather: out[i] = table[idx[i]]   (int32 index plumbing). */
+int bg_sag_workspace_bytes(int64_t n_nodes, int64_t n_edges, int64_t n_graphs, size_t* bytes_host);
+int bg_sag_select(const void* x, int dtype, int64_t n_nodes, const int32_t* rowptr, const int32_t* col,
+                  const int32_t* big_rows, int32_t n_big, const float* w_l, const float* w_r, float bias, float sign,
+                  const int32_t* graph_ptr, int64_t n_graphs, float ratio, const int64_t* edge_index, int64_t n_edges,
+                  float* score, int32_t* new_id, int32_t* perm, int64_t* batch_out, float* score_out,
+                  int32_t* new_graph_ptr, int32_t* info, void* workspace, size_t workspace_bytes, void* stream);
+int bg_sag_connect(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, const int32_t* new_id,
+                   int64_t n_edges_out, int64_t* edge_index_out, int32_t* kept_edge,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int bg_gather_rows(const void* x, int dtype, int64_t ldx, const int32_t* row_index, const float* row_scale,
+                   int64_t n_rows_out, void* out, int64_t ldo, void* stream);
+int bg_index_invert(const int32_t* perm, int64_t n, int32_t* out, void* stream);
+int bg_index_gather(const int32_t* table, const int32_t* idx, int64_t n, int32_t* out, void* stream);
 
 /* ------------------------------------------------------------------ training step
  * What `loss.backward()` and train-mode BatchNorm1d / Dropout need around the forward kernels

@@ -21,8 +21,18 @@ Operator semantics restated
   `row = edge_index[0]`).
 * `OracleBuckGNN` <- `Models/BuckGNN.py:9-526`: same constructor, same parameter
   names/shapes/registration order (so a state_dict moves between the two), same
-  forward for the model_name / pooling_layer values that work in the reference
-  (the SAGPooling variants are out of scope).
+  forward for the model_name / pooling_layer values that work in the reference,
+  including the SAGPooling variants `GraphSAGE_SAG` (`:190-217`, `:493-511`) and
+  `EAGNN_SAG` (`:219-244`, `:354-373`).
+* `OracleSAGPooling`, `topk`, `filter_adj` <- PyG `SAGPooling(hidden, ratio=0.5,
+  GNN=SAGEConv, aggr='add')` constructed at `Models/BuckGNN.py:203-208,231-236`,
+  applied at `:365-367,502-504` (PyG < 2.4 formulation, whose state_dict is
+  `pool.gnn.{lin_l.weight,lin_l.bias,lin_r.weight}`):
+  `score = tanh(gnn(x, edge_index).view(-1))`; per graph keep the
+  `ceil(ratio * n_g)` highest scores in descending order (PyG sorts with an
+  unstable sort, so ties are unspecified there; here ties keep the lower node
+  id first); `x = x[perm] * score[perm]`; `batch = batch[perm]`; edges with both
+  endpoints kept survive in their original order with relabelled endpoints.
 
 `dtype=torch.float64` copies of the module give the error-budget reference.
 """
@@ -115,6 +125,54 @@ class OracleGraphNetBlock(nn.Module):
         return x, edge_attr
 
 
+
+def topk(score: torch.Tensor, ratio: float, batch: torch.Tensor) -> torch.Tensor:
+    """PyG `topk(x, ratio, batch)` (torch_geometric.nn.pool.topk_pool / select.topk) for a float ratio:
+    per graph the `ceil(ratio * n_g)` highest-scoring nodes, graphs in order, descending score inside a
+    graph; ties resolved towards the lower node id (stable)."""
+    n = score.shape[0]
+    g = int(batch.max()) + 1 if n > 0 else 0
+    num_nodes = torch.bincount(batch, minlength=g)
+    k = (ratio * num_nodes.to(torch.float)).ceil().to(torch.long)          # as PyG computes it
+    k = torch.minimum(k, num_nodes)
+    order = torch.sort(score, descending=True, stable=True).indices
+    order = order[torch.sort(batch[order], stable=True).indices]            # grouped by graph, descending inside
+    start = torch.cumsum(num_nodes, 0) - num_nodes
+    pos = torch.arange(n) - start[batch[order]]
+    return order[pos < k[batch[order]]]
+
+
+def filter_adj(edge_index: torch.Tensor, edge_attr, perm: torch.Tensor, num_nodes: int):
+    """PyG `filter_adj`: keep the edges whose two endpoints are in `perm`, relabel them to positions in `perm`."""
+    mask = perm.new_full((num_nodes,), -1)
+    mask[perm] = torch.arange(perm.size(0), dtype=perm.dtype)
+    row, col = mask[edge_index[0]], mask[edge_index[1]]
+    keep = (row >= 0) & (col >= 0)
+    if edge_attr is not None:
+        edge_attr = edge_attr[keep]
+    return torch.stack([row[keep], col[keep]], dim=0), edge_attr
+
+
+class OracleSAGPooling(nn.Module):
+    """PyG `SAGPooling(in_channels, ratio, GNN=SAGEConv, aggr=...)`: min_score=None, multiplier=1,
+    nonlinearity=tanh; the scoring GNN is `SAGEConv(in_channels, 1, aggr=aggr)` (normalize=False)."""
+
+    def __init__(self, in_channels: int, ratio: float = 0.5, aggr: str = "add"):
+        super().__init__()
+        self.ratio = ratio
+        self.gnn = OracleSAGEConv(in_channels, 1, normalize=False, aggr=aggr)
+
+    def forward(self, x, edge_index, edge_attr=None, batch=None):
+        if batch is None:
+            batch = edge_index.new_zeros(x.size(0))
+        score = torch.tanh(self.gnn(x, edge_index).view(-1))
+        perm = topk(score, self.ratio, batch)
+        x = x[perm] * score[perm].view(-1, 1)
+        batch = batch[perm]
+        edge_index, edge_attr = filter_adj(edge_index, edge_attr, perm, score.size(0))
+        return x, edge_index, edge_attr, batch, perm, score[perm]
+
+
 class OracleMLPPooling(nn.Module):
     """Reference `MLPPooling` (`Models/BuckGNN.py:568-581`)."""
 
@@ -193,6 +251,18 @@ class OracleBuckGNN(nn.Module):
         self.relu = nn.ReLU()
         self.dropout = nn.Dropout(p=dropout_rate)
         self.pooling_mpl = OracleMLPPooling(h, h, h)
+        if model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):           # Models/BuckGNN.py:190-244
+            n_before = num_layers // 2
+            n_after = num_layers - n_before
+            sage = model_name == "GraphSAGE_SAG"
+            mk = (lambda: OracleSAGEConv(h, h, normalize=True, aggr="add")) if sage else (lambda: OracleGraphNetBlock(h))
+            first = nn.ModuleList([mk() for _ in range(n_before)])
+            setattr(self, "sage_layers_1" if sage else "gnn_layers_1", first)
+            self.batch_norms_1 = nn.ModuleList([nn.BatchNorm1d(h) for _ in range(n_before)] if sage else [])
+            self.pool = OracleSAGPooling(h, ratio=0.5, aggr="add")
+            second = nn.ModuleList([mk() for _ in range(n_after)])
+            setattr(self, "sage_layers_2" if sage else "gnn_layers_2", second)
+            self.batch_norms_2 = nn.ModuleList([nn.BatchNorm1d(h) for _ in range(n_after)] if sage else [])
 
     # -- pooling, `Models/BuckGNN.py:246-307`
     def get_pooling_layer(self, x, edge_index, batch):
@@ -255,6 +325,35 @@ class OracleBuckGNN(nn.Module):
                 if 0 < i < L - 1:
                     x = x + x_prev
                 x = self.dropout(x)
+        elif name == "EAGNN_SAG":                                  # Models/BuckGNN.py:354-373
+            e = self.edge_encoder(edge_attr)
+            for i, conv in enumerate(self.gnn_layers_1):
+                x_prev, e_prev = x, e
+                x, e = conv(x, edge_index, e)
+                x = self.dropout(x)
+                e = self.dropout(e)
+                if i > 0:
+                    x = x + x_prev
+                    e = e + e_prev
+            x, edge_index, e, batch, _, _ = self.pool(x, edge_index, e, batch)
+            for conv in self.gnn_layers_2:
+                x_prev, e_prev = x, e
+                x, e = conv(x, edge_index, e)
+                x = self.dropout(x)
+                e = self.dropout(e)
+                x = x + x_prev
+                e = e + e_prev
+        elif name == "GraphSAGE_SAG":                              # Models/BuckGNN.py:493-511
+            for i, (conv, bn) in enumerate(zip(self.sage_layers_1, self.batch_norms_1)):
+                identity = x
+                x = self.dropout(self.relu(bn(conv(x, edge_index))))
+                if i > 0:
+                    x = x + identity
+            x, edge_index, edge_attr, batch, _, _ = self.pool(x, edge_index, edge_attr, batch)
+            for conv, bn in zip(self.sage_layers_2, self.batch_norms_2):
+                identity = x
+                x = self.dropout(self.relu(bn(conv(x, edge_index))))
+                x = x + identity
         # any other model_name: encoder -> pooling -> decoder only (reference default
         # "GraphSAGE_MLP" matches no branch, Models/BuckGNN.py:12,326-511)
         if self.prediction_type == "buckling":

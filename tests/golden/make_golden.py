@@ -30,7 +30,12 @@ FORWARD_CASES = [  # name, model cfg overrides, batch kwargs
     ("default_mlp", dict(model_name="GraphSAGE_MLP"), dict(num_graphs=3, nx=6, ny=5)),
     ("sage_mean_supernode_only", dict(model_name="GraphSage_meanAggr", num_layers=3, pooling_layer="supernode_only"),
      dict(num_graphs=3, nx=6, ny=5)),
+    # SAGPooling variants: the top-k is discrete, so these cases are chosen (and checked below) to have a clear
+    # score gap at every graph's keep/drop threshold -- tf32 rounding cannot flip the selection
+    ("sage_sag_6x512", dict(model_name="GraphSAGE_SAG"), dict(num_graphs=3, nx=9, ny=7)),
+    ("eagnn_sag_4x512_stiffened", dict(model_name="EAGNN_SAG", num_layers=4), dict(num_graphs=2, nx=7, ny=6, stiffened=True)),
 ]
+MIN_TOPK_GAP = 1e-3
 
 
 def model_cfg(**over):
@@ -63,6 +68,35 @@ def kat():
     return x, ei, batch
 
 
+def sag_kat():
+    """Hand-checkable SAGPooling index work: 2 graphs (5 + 3 nodes), ties inside both.
+    graph 0 keeps ceil(2.5) = 3 of scores [.3, .9, .9, -.2, .5] -> nodes 1, 2 (tie: lower id first), 4;
+    graph 1 keeps ceil(1.5) = 2 of [.1, .7, .7] -> nodes 6, 7."""
+    score = torch.tensor([0.3, 0.9, 0.9, -0.2, 0.5, 0.1, 0.7, 0.7])
+    batch = torch.tensor([0, 0, 0, 0, 0, 1, 1, 1])
+    ei = torch.tensor([[0, 1, 2, 4, 1, 4, 5, 6, 7, 6], [1, 2, 1, 2, 4, 3, 6, 7, 6, 5]])
+    return score, batch, ei
+
+
+def topk_gaps(m, b):
+    """Per graph: score gap between the last kept and the first dropped node of the oracle's SAGPooling."""
+    cap = {}
+
+    def hook(mod, inp, out):
+        cap["score"] = torch.tanh(mod.gnn(inp[0], inp[1]).view(-1))
+        cap["batch"] = inp[3]
+    h = m.pool.register_forward_hook(hook)
+    with torch.no_grad():
+        m(b.x, b.edge_index, b.edge_attr, b.batch)
+    h.remove()
+    gaps = []
+    for g in range(int(cap["batch"].max()) + 1):
+        sg = cap["score"][cap["batch"] == g].sort(descending=True).values
+        k = -(-len(sg) // 2)
+        gaps.append(float(sg[k - 1] - sg[k]) if k < len(sg) else float("inf"))
+    return gaps
+
+
 def main():
     out = {"forward": {}, "operators": {}, "training": {}}
     for name, over, bkw in FORWARD_CASES:
@@ -70,15 +104,24 @@ def main():
         m = seeded_oracle(cfg).eval()
         b = make_batch(**bkw)
         with torch.no_grad():
-            pred, _ = m(b.x, b.edge_index, b.edge_attr, b.batch)
+            pred, bout = m(b.x, b.edge_index, b.edge_attr, b.batch)
         out["forward"][name] = {"cfg": cfg, "batch": bkw, "nodes": b.num_nodes, "edges": b.num_edges,
                                 "state_checksum": state_checksum(m), "pred": pred.double().reshape(-1).tolist()}
+        if hasattr(m, "pool"):
+            gaps = topk_gaps(m, b)
+            assert min(gaps) > MIN_TOPK_GAP, (name, gaps)
+            out["forward"][name].update(pooled_nodes=int(bout.shape[0]), min_topk_gap=min(gaps))
     x, ei, batch = kat()
     ops = out["operators"]
     for aggr in ("mean", "sum", "max"):
         ops[f"aggregate_{aggr}"] = O.aggregate(x, ei, aggr).tolist()
     ops["global_mean_pool"] = O.global_mean_pool(x, batch).tolist()
     ops["scatter_mean_row"] = O.scatter_mean(x[ei[1]], ei[0], 5).tolist()
+    score, sbatch, sei = sag_kat()
+    perm = O.topk(score, 0.5, sbatch)
+    fei, _ = O.filter_adj(sei, None, perm, 8)
+    ops["sag_topk_perm"] = perm.tolist()
+    ops["sag_filter_adj"] = fei.tolist()
     # training step: loss and gradient norms of one step (dropout off), plus BN buffers after it
     cfg = model_cfg(num_layers=3, dropout_rate=0.0)
     m = seeded_oracle(cfg).train()

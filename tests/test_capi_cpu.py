@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(capi.library_path())
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.bg_abi_version() == capi.ABI_VERSION == 4
+    assert lib.bg_abi_version() == capi.ABI_VERSION == 5
 
 
 def test_size_queries_and_argument_errors_without_gpu(lib):
@@ -72,6 +72,17 @@ def test_training_and_collate_entry_points_validate_arguments_without_gpu(lib):
         lambda: capi.mask_narrow(1, capi.BG_F32, 64, None, capi.BG_F32, 0, 10, 128, 16, None),             # ld_in < n_cols
         lambda: capi.publish_words(None, None, 8, None),
         lambda: capi.sage_aggregate(16, 16, capi.BG_F16, 10, 16, 16, 16, 0, capi.BG_AGGR_MEAN, 16, 0, None, width=100),
+        # SAGPooling entry points
+        lambda: capi.sag_workspace_bytes(-1, 0, 0),
+        lambda: capi.sag_select(16, capi.BG_F32, 10, 16, 16, 16, 0, 16, 16, 0.0, 1.0, 16, 1, 1.5, 16, 4, 16, 16, 16, 16, 16, 16, 16, 16,
+                                1 << 20, None),                                                            # ratio > 1
+        lambda: capi.sag_select(16, capi.BG_F32, 10, 16, 16, 16, 0, 16, 16, 0.0, 1.0, 16, 1, 0.5, 16, 4, 16, 16, 16, 16, 16, 16, 16, 16,
+                                8, None),                                                                  # workspace too small
+        lambda: capi.sag_connect(16, 4, 10, 16, 5, 16, None, 16, 1 << 20, None),                           # E' > E
+        lambda: capi.gather_rows(16, capi.BG_F16, 100, 16, None, 4, 16, 512, None),                        # ldx < 512
+        lambda: capi.gather_rows(None, capi.BG_F16, 512, 16, None, 4, 16, 512, None),
+        lambda: capi.index_invert(None, 4, None, None),
+        lambda: capi.index_gather(None, None, 4, None, None),
     ]
     for i, call in enumerate(bad):
         with pytest.raises(capi.BuckGNNError) as e:
@@ -81,7 +92,7 @@ def test_training_and_collate_entry_points_validate_arguments_without_gpu(lib):
 
 @pytest.mark.parametrize("name", ["GraphSage_meanAggr", "GraphSage_sumAggr", "GraphSage_addAggr",
                                   "GraphSage_maxAggr", "GraphSage_addAggr_Shared", "EA_GNN", "EA_GNN_Shared",
-                                  "GraphSAGE_MLP"])
+                                  "GraphSAGE_MLP", "GraphSAGE_SAG", "EAGNN_SAG"])
 @pytest.mark.parametrize("hidden", [128, 512])
 def test_state_dict_layout_matches_oracle_restatement(name, hidden):
     kw = dict(num_node_features=16, num_edge_features=5, hidden_channels=hidden, num_layers=3,
@@ -118,3 +129,23 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(ROOT, d, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_sag_variants_register_the_reference_module_names():
+    """reference :190-244: first-half layers, `pool` (PyG SAGPooling with a SAGEConv(h, 1) scorer), second-half layers,
+    registered after `pooling_mpl`; num_layers // 2 layers come before the pooling."""
+    m = BuckGNN(16, 5, 512, 5, "mean", model_name="GraphSAGE_SAG")
+    keys = list(m.state_dict().keys())
+    assert len(m.sage_layers_1) == 2 and len(m.sage_layers_2) == 3 and len(m.batch_norms_1) == 2 and len(m.batch_norms_2) == 3
+    assert keys.index("pooling_mpl.mlp.0.bias") < keys.index("sage_layers_1.0.lin_l.weight") < keys.index("pool.gnn.lin_l.weight") \
+        < keys.index("sage_layers_2.0.lin_l.weight")
+    assert tuple(m.pool.gnn.lin_l.weight.shape) == (1, 512) and tuple(m.pool.gnn.lin_l.bias.shape) == (1,)
+    assert "pool.gnn.lin_r.bias" not in keys and m.precision == "tf32"
+    e = BuckGNN(16, 5, 512, 4, "mean", model_name="EAGNN_SAG")
+    assert len(e.gnn_layers_1) == 2 and len(e.gnn_layers_2) == 2 and len(e.batch_norms_1) == 0
+    assert "gnn_layers_2.1.node_mlp_beta.2.bias" in e.state_dict()
+    # a PyG >= 2.4 checkpoint carries pool.select.weight: accepted with strict=True, only its sign matters
+    sd = dict(m.state_dict())
+    sd["pool.select.weight"] = torch.tensor([[-2.0]])
+    m.load_state_dict(sd, strict=True)
+    assert m._sag_sign == -1.0

@@ -39,6 +39,11 @@ def test_oracle_reproduces_golden_operators():
         assert mk.O.aggregate(x, ei, aggr).tolist() == ops[f"aggregate_{aggr}"]
     assert mk.O.global_mean_pool(x, batch).tolist() == ops["global_mean_pool"]
     assert mk.O.scatter_mean(x[ei[1]], ei[0], 5).tolist() == ops["scatter_mean_row"]
+    score, sbatch, sei = mk.sag_kat()
+    perm = mk.O.topk(score, 0.5, sbatch)
+    assert perm.tolist() == ops["sag_topk_perm"] == [1, 2, 4, 6, 7]                   # hand-computed (make_golden.sag_kat)
+    fei, _ = mk.O.filter_adj(sei, None, perm, 8)
+    assert fei.tolist() == ops["sag_filter_adj"] == [[0, 1, 2, 0, 3, 4], [1, 0, 1, 2, 4, 3]]
 
 
 def test_oracle_reproduces_golden_training_step():

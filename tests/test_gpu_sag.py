@@ -1,0 +1,224 @@
+"""SAGPooling variants (`GraphSAGE_SAG`, `EAGNN_SAG`) on the B200.
+
+Operator level: the score GNN against the oracle within fp32 rounding, and -- given the SAME scores -- the
+top-k permutation, the pooled batch vector, the filtered / relabelled edge list and the kept-edge ids
+bit-exactly (integer work).  Model level: the forward against the oracle (rtol 1e-3 tf32, 1e-4 fp32-GEMM
+mode) whenever both select the same nodes; the selection is a discrete function of a rounded score, so a
+node within rounding distance of the keep/drop threshold may legitimately differ -- then the test bounds
+how many and how far."""
+import pytest
+import torch
+
+from buckgnn_b200 import capi, engine
+from buckgnn_b200.engine import Activation, build_graph_index
+from buckgnn_b200.model import BuckGNN
+from buckgnn_b200.synth import collate, make_batch, make_plate_graph
+from oracle import buckgnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pool_weights(seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    pool = O.OracleSAGPooling(512, ratio=0.5, aggr="add")
+    with torch.no_grad():
+        for p in pool.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * scale / 512 ** 0.5)
+    return pool
+
+
+def _operator_case(batch, precision, pool, want_kept=True):
+    n = batch.num_nodes
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, 512, generator=g) * 0.5
+    act = Activation(n, 512, precision, DEV)
+    act.data.copy_(x.to(DEV))
+    act.refresh_split()
+    xr = act.data.float().cpu()                       # what the kernels actually read (16-bit modes round x)
+    ei = batch.edge_index.to(DEV)
+    bt = None if batch.batch is None else batch.batch.to(DEV)
+    idx = build_graph_index(ei, bt, n)
+    pack = {"w_l": pool.gnn.lin_l.weight.detach().reshape(-1).to(DEV), "w_r": pool.gnn.lin_r.weight.detach().reshape(-1).to(DEV),
+            "bias": float(pool.gnn.lin_l.bias), "ratio": 0.5}
+    res = engine.sag_pool(act, idx, idx.graph_ptr, idx.n_graphs, ei, pack, want_kept_edges=want_kept)
+    torch.cuda.synchronize()
+    return xr, idx, res
+
+
+def _check_operator(batch, precision, pool, score_atol=2e-5):
+    xr, idx, res = _operator_case(batch, precision, pool)
+    n = batch.num_nodes
+    cpu_batch = batch.batch if batch.batch is not None else torch.zeros(n, dtype=torch.int64)
+    with torch.no_grad():
+        want_score = torch.tanh(pool.gnn(xr, batch.edge_index).view(-1))
+    got_score = res.all_scores.cpu()
+    torch.testing.assert_close(got_score, want_score, rtol=0, atol=score_atol)
+    # integer work, given the device's own scores: bit-exact
+    perm = O.topk(got_score, 0.5, cpu_batch)
+    assert res.n_nodes == perm.numel()
+    assert torch.equal(res.perm.cpu().long(), perm)
+    assert torch.equal(res.batch.cpu(), cpu_batch[perm])
+    assert torch.equal(res.score.cpu(), got_score[perm])
+    new_id = torch.full((n,), -1, dtype=torch.int64)
+    new_id[perm] = torch.arange(perm.numel())
+    assert torch.equal(res.new_id.cpu().long(), new_id)
+    ei_want, _ = O.filter_adj(batch.edge_index, None, perm, n)
+    assert res.n_edges == ei_want.shape[1]
+    assert torch.equal(res.edge_index.cpu(), ei_want)
+    keep = (new_id[batch.edge_index[0]] >= 0) & (new_id[batch.edge_index[1]] >= 0)
+    assert torch.equal(res.kept_edge.cpu().long()[:res.n_edges], torch.nonzero(keep).flatten())
+    counts = torch.bincount(cpu_batch[perm], minlength=idx.n_graphs)
+    assert torch.equal(res.graph_ptr.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.int64), counts.cumsum(0)]))
+    # x' = x[perm] * score[perm]
+    want_x = xr[perm] * got_score[perm].view(-1, 1)
+    tol = dict(rtol=0, atol=1e-6) if precision in ("tf32", "fp32") else dict(rtol=1e-2, atol=1e-3)
+    torch.testing.assert_close(res.x.data.float().cpu(), want_x, **tol)
+    return res
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp16", "bf16"])
+def test_sag_pool_operator_on_plate_batch(precision):
+    """super-node hubs (big rows), several graphs"""
+    _check_operator(make_batch(5, nx=13, ny=11), precision, _pool_weights(1))
+
+
+def test_sag_pool_operator_ragged_graphs():
+    """1-node-wide meshes, odd and even sizes: k = ceil(n / 2) per graph"""
+    b = collate([make_plate_graph(i, nx=nx, ny=ny) for i, (nx, ny) in enumerate([(2, 2), (3, 2), (17, 5), (2, 3), (9, 9)])])
+    res = _check_operator(b, "tf32", _pool_weights(2))
+    sizes = torch.bincount(b.batch)
+    assert torch.equal(torch.bincount(res.batch.cpu()), (sizes + 1) // 2)
+
+
+def test_sag_pool_operator_large_graph_spans_rank_tiles():
+    """one graph above 4 x 1024 nodes: every rank tile sees earlier, own and later score tiles"""
+    b = make_batch(2, nx=70, ny=68)
+    _check_operator(b, "tf32", _pool_weights(3))
+
+
+def test_sag_pool_operator_saturated_scores_tie_break_by_node_id():
+    """large scoring weights drive tanh to exactly +-1 for most nodes: ties resolve to the lower node id"""
+    res = _check_operator(make_batch(3, nx=12, ny=9), "tf32", _pool_weights(4, scale=200.0), score_atol=1e-3)
+    s = res.all_scores.cpu()
+    assert (s.abs() == 1).float().mean() > 0.5
+
+
+def test_sag_pool_operator_single_graph_without_batch_vector():
+    g = make_plate_graph(0, nx=11, ny=7)
+    b = collate([g])
+    b.batch = None
+    res = _check_operator(b, "tf32", _pool_weights(5))
+    assert int(res.batch.max()) == 0
+
+
+def test_gather_rows_and_index_helpers():
+    g = torch.Generator().manual_seed(0)
+    n, m = 1000, 377
+    s = torch.cuda.current_stream().cuda_stream
+    for dt, code in ((torch.float16, capi.BG_F16), (torch.bfloat16, capi.BG_BF16), (torch.float32, capi.BG_F32)):
+        x = torch.randn(n, 512, generator=g).to(dt).to(DEV)
+        idx = torch.randint(0, n, (m,), generator=g).int().to(DEV)
+        out = torch.empty(m, 512, dtype=dt, device=DEV)
+        capi.gather_rows(x.data_ptr(), code, 512, idx.data_ptr(), None, m, out.data_ptr(), 512, s)
+        assert torch.equal(out, x[idx.long()])
+    perm = torch.randperm(n, generator=g).int().to(DEV)
+    inv = torch.empty_like(perm)
+    capi.index_invert(perm.data_ptr(), n, inv.data_ptr(), s)
+    assert torch.equal(inv[perm.long()].cpu(), torch.arange(n, dtype=torch.int32))
+    out = torch.empty(m, dtype=torch.int32, device=DEV)
+    capi.index_gather(perm.data_ptr(), idx.data_ptr(), m, out.data_ptr(), s)
+    assert torch.equal(out, perm[idx.long()])
+
+
+# ----------------------------------------------------------------------------- whole forward
+def _model_pair(name, precision, layers, seed=0, pooling="mean"):
+    torch.manual_seed(seed)
+    cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=layers,
+               pooling_layer=pooling, model_name=name)
+    ref = O.OracleBuckGNN(**cfg).eval()
+    O.randomize_bn_stats(ref, realistic=True)
+    ours = BuckGNN(**cfg, precision=precision)
+    ours.load_state_dict(ref.state_dict())
+    return ref, ours.to(DEV).eval()
+
+
+def _forward_case(ref, ours, b, rtol):
+    cap = {}
+    h = ref.pool.register_forward_hook(lambda mod, inp, out: cap.update(perm=out[4], batch=out[3], ei=out[1]))
+    with torch.no_grad():
+        want, want_batch = ref(b.x, b.edge_index, b.edge_attr, b.batch)
+        bd = b.to(DEV)
+        got, got_batch = ours(bd.x, bd.edge_index, bd.edge_attr, bd.batch)
+    h.remove()
+    got = got.cpu()
+    assert got.shape == want.shape
+    assert torch.equal(got_batch.cpu(), want_batch)            # k per graph is fixed by the graph sizes: bit-exact
+    perm = ours.last_pool.perm.cpu().long()
+    rel = ((got - want).abs() / want.abs().clamp(min=1e-3)).max().item()
+    if torch.equal(perm, cap["perm"]):
+        assert torch.equal(ours.last_pool.edge_index.cpu(), cap["ei"])
+        assert rel < rtol, f"same selection, max rel err {rel:.3e} >= {rtol}"
+    else:                                                       # threshold nodes swapped by score rounding
+        differ = len(set(perm.tolist()) ^ set(cap["perm"].tolist()))
+        assert differ <= max(2, perm.numel() // 50), f"{differ} of {perm.numel()} selected nodes differ"
+        assert rel < 3e-2, f"selection differs in {differ} nodes, max rel err {rel:.3e}"
+    return rel
+
+
+@pytest.mark.parametrize("precision,rtol", [("tf32", 1e-3), ("fp32", 1e-4)])
+@pytest.mark.parametrize("layers", [6, 3])
+def test_graphsage_sag_matches_oracle(precision, rtol, layers):
+    """reference :190-217, :493-511 -- layers // 2 before the pooling, the rest after (3 -> 1 + 2)"""
+    ref, ours = _model_pair("GraphSAGE_SAG", precision, layers)
+    _forward_case(ref, ours, make_batch(3, nx=9, ny=7), rtol)
+
+
+def test_graphsage_sag_larger_meshes_default_precision():
+    ref, ours = _model_pair("GraphSAGE_SAG", "auto", 6, seed=1)
+    assert ours.precision == "tf32"
+    _forward_case(ref, ours, make_batch(4, nx=24, ny=20), 1e-3)
+
+
+@pytest.mark.parametrize("pooling", ["supernode_only", "mean_no_super", "mlp"])
+def test_graphsage_sag_pooling_layers_use_pooled_graph_offsets(pooling):
+    """after SAGPooling the 'super node' of get_pooling_layer is the LAST row of each pooled graph (:256-266)"""
+    ref, ours = _model_pair("GraphSAGE_SAG", "fp32", 4, seed=2, pooling=pooling)
+    _forward_case(ref, ours, make_batch(3, nx=8, ny=6), 1e-4)
+
+
+@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("tf32", 2e-3)])
+def test_eagnn_sag_matches_oracle(precision, rtol):
+    """reference :219-244, :354-373 -- pooled edge features are the rows of the kept edges"""
+    torch.manual_seed(3)
+    cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=4,
+               pooling_layer="mean", model_name="EAGNN_SAG")
+    ref = O.OracleBuckGNN(**cfg).eval()
+    ours = BuckGNN(**cfg, precision=precision)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV).eval()
+    _forward_case(ref, ours, make_batch(2, nx=7, ny=6, stiffened=True), rtol)
+
+
+def test_sag_select_weight_sign_of_newer_pyg_checkpoints():
+    """PyG >= 2.4 stores `pool.select.weight`; a negative one flips the score before tanh"""
+    ref, ours = _model_pair("GraphSAGE_SAG", "fp32", 4)
+    sd = dict(ref.state_dict())
+    sd["pool.select.weight"] = torch.tensor([[-0.7]])
+    ours.load_state_dict(sd)
+    with torch.no_grad():                              # the oracle with negated scoring weights is the same function
+        for p in ref.pool.gnn.parameters():
+            p.neg_()
+    _forward_case(ref, ours, make_batch(2, nx=9, ny=7), 1e-4)
+
+
+def test_sag_variants_are_eval_only_and_node_level_super_mask_fails_like_the_reference():
+    _, ours = _model_pair("GraphSAGE_SAG", "tf32", 4)
+    b = make_batch(2, nx=6, ny=5).to(DEV)
+    ours.train()
+    with pytest.raises(NotImplementedError):
+        ours(b.x, b.edge_index, b.edge_attr, b.batch)
+    torch.manual_seed(0)
+    m = BuckGNN(16, 5, 512, 4, "supernode_only", prediction_type="static_stress", model_name="GraphSAGE_SAG").to(DEV).eval()
+    with pytest.raises(IndexError):
+        m(b.x, b.edge_index, b.edge_attr, b.batch)

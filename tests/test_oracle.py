@@ -9,6 +9,7 @@ import torch.nn.functional as F
 from oracle.buckgnn_oracle import (OracleBuckGNN, OracleGraphNetBlock, OracleSAGEConv, aggregate,
                                    global_mean_pool, randomize_bn_stats, scatter_max, scatter_mean)
 from buckgnn_b200.synth import make_batch
+from oracle import buckgnn_oracle as O
 
 # 5 nodes, 2 graphs: graph 0 = {0,1,2} with hub 2; graph 1 = {3,4}, node 4 isolated (no in-edges)
 EI = torch.tensor([[0, 1, 2, 2, 0, 3],    # src
@@ -188,3 +189,62 @@ def test_unknown_pooling_raises():
     m = OracleBuckGNN(16, 5, 256, 1, "hybrid", model_name="GraphSage_meanAggr").eval()
     with pytest.raises(ValueError, match="Unknown pooling layer"):
         m(b.x, b.edge_index, b.edge_attr, b.batch)
+
+
+# ----------------------------------------------------------------------------- SAGPooling (GraphSAGE_SAG / EAGNN_SAG)
+def test_kat_sag_topk_and_filter_adj_by_hand():
+    """scores [.3,.9,.9,-.2,.5 | .1,.7,.7]: graph 0 keeps ceil(5/2) = 3 -> nodes 1, 2 (tie: lower id first), 4;
+    graph 1 keeps ceil(3/2) = 2 -> nodes 6, 7.  Edges survive iff both ends do, relabelled to positions in perm."""
+    score = torch.tensor([0.3, 0.9, 0.9, -0.2, 0.5, 0.1, 0.7, 0.7])
+    batch = torch.tensor([0, 0, 0, 0, 0, 1, 1, 1])
+    perm = O.topk(score, 0.5, batch)
+    assert perm.tolist() == [1, 2, 4, 6, 7]
+    ei = torch.tensor([[0, 1, 2, 4, 1, 4, 5, 6, 7, 6], [1, 2, 1, 2, 4, 3, 6, 7, 6, 5]])
+    ea = torch.arange(10.0).view(10, 1)
+    fei, fea = O.filter_adj(ei, ea, perm, 8)
+    assert fei.tolist() == [[0, 1, 2, 0, 3, 4], [1, 0, 1, 2, 4, 3]]
+    assert fea.flatten().tolist() == [1.0, 2.0, 3.0, 4.0, 7.0, 8.0]
+
+
+def test_sag_pooling_against_a_per_graph_loop():
+    """independent formulation: loop over graphs, python sort with (-score, id) keys, dict relabelling"""
+    g = torch.Generator().manual_seed(5)
+    sizes = [7, 1, 12, 2]
+    batch = torch.cat([torch.full((s,), i) for i, s in enumerate(sizes)])
+    n = int(batch.numel())
+    x = torch.randn(n, 16, generator=g)
+    src, dst = [], []
+    off = 0
+    for s in sizes:
+        for _ in range(3 * s):
+            a, b = torch.randint(0, s, (2,), generator=g).tolist()
+            src.append(off + a); dst.append(off + b)
+        off += s
+    ei = torch.tensor([src, dst])
+    pool = O.OracleSAGPooling(16, ratio=0.5, aggr="add")
+    with torch.no_grad():
+        x2, ei2, _, b2, perm, sc = pool(x, ei, None, batch)
+        score = torch.tanh(pool.gnn(x, ei).view(-1))
+    want, off = [], 0
+    for s in sizes:
+        ids = sorted(range(off, off + s), key=lambda i: (-float(score[i]), i))[:-(-s // 2)]
+        want += ids
+        off += s
+    assert perm.tolist() == want
+    relabel = {old: new for new, old in enumerate(want)}
+    kept = [(relabel[a], relabel[b]) for a, b in zip(src, dst) if a in relabel and b in relabel]
+    assert ei2.t().tolist() == [list(p) for p in kept]
+    torch.testing.assert_close(x2, x[want] * score[want].view(-1, 1))
+    assert b2.tolist() == batch[want].tolist() and torch.equal(sc, score[want])
+
+
+@pytest.mark.parametrize("name,layers", [("GraphSAGE_SAG", 6), ("GraphSAGE_SAG", 3), ("EAGNN_SAG", 4)])
+def test_sag_variants_forward_shapes_and_pooled_batch(name, layers):
+    torch.manual_seed(0)
+    m = O.OracleBuckGNN(16, 5, 512, layers, "mean", model_name=name).eval()
+    b = make_batch(3, nx=6, ny=5, stiffened=(name == "EAGNN_SAG"))
+    with torch.no_grad():
+        pred, pooled_batch = m(b.x, b.edge_index, b.edge_attr, b.batch)
+    assert pred.shape == (3,) and torch.isfinite(pred).all()
+    sizes = torch.bincount(b.batch)
+    assert torch.equal(torch.bincount(pooled_batch), (sizes + 1) // 2)       # `batch` is reassigned by self.pool (:365, :502)
