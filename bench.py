@@ -326,7 +326,7 @@ def run_b200(args):
         if "sage_update" in kernel_ms:
             ms, calls = kernel_ms["sage_update"]
             a = upd_flops / (ms / calls * 1e-3) / 1e12
-            tr = _traffic_from_profile("k_gemm512<2, __half, 1>") if args.precision == "fp16" else None
+            tr = _traffic_from_profile("k_gemm512<2, __half, 1,") if args.precision == "fp16" else None
             roofs["sage_update"] = {"bound": "tensor", "achieved": a, "peak": tf_peak, "unit": "TFLOP/s",
                                     "frac": a / tf_peak, "traffic": tr and tr["bytes_per_launch"],
                                     "traffic_source": tr and tr["source"], "algorithmic_flops": upd_flops,

@@ -162,7 +162,7 @@ k_sag_plan(const int32_t* __restrict__ graph_ptr, int32_t G, float ratio, int32_
   if (threadIdx.x == 0) { new_ptr[G] = carry_k; tile_ptr[G] = carry_t; info[0] = carry_k; }
 }
 
-// kMode 0: the j tile lies wholly before this CTA's nodes (ties count), 1: wholly after (ties do not), 2: mixed
+// kMode 0: the j range lies wholly before this CTA's nodes (ties count), 1: wholly after (ties do not), 2: overlaps them
 template <int kMode>
 BG_DEVINL void rank_tile(const float* __restrict__ sj, int32_t cnt, int32_t j_base, const float (&si)[kRankPerThread],
                          const int32_t (&ii)[kRankPerThread], int32_t (&rank)[kRankPerThread]) {
@@ -221,9 +221,12 @@ k_sag_rank(const float* __restrict__ score, const int32_t* __restrict__ graph_pt
     __syncthreads();
     for (int32_t j = threadIdx.x; j < cnt; j += kRankThreads) sj[j] = score[jb + j];
     __syncthreads();
-    if (jb + cnt <= i0) rank_tile<0>(sj, cnt, jb, si, ii, rank);
-    else if (jb >= i_end) rank_tile<1>(sj, cnt, jb, si, ii, rank);
-    else rank_tile<2>(sj, cnt, jb, si, ii, rank);
+    // split the staged scores at this CTA's own node range: only the diagonal block needs the index tie-break
+    // (i0 - jb and i_end - jb are multiples of kRankTileI or the end of the graph, so the float4 reads stay aligned)
+    const int32_t a = max(0, min(cnt, i0 - jb)), b = max(0, min(cnt, i_end - jb));
+    if (a > 0) rank_tile<0>(sj, a, jb, si, ii, rank);
+    if (b > a) rank_tile<2>(sj + a, b - a, jb + a, si, ii, rank);
+    if (cnt > b) rank_tile<1>(sj + b, cnt - b, jb + b, si, ii, rank);
   }
   const int32_t k_g = new_ptr[g + 1] - new_ptr[g];
 #pragma unroll

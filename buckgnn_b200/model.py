@@ -110,11 +110,15 @@ class BuckGNN(nn.Module):
                  cache_index: bool = False, fold_encoder: bool = True, train_precision: str = "tf32"):
         super().__init__()
         if precision == "auto":
-            # the SAGPooling variants pick nodes by a discrete top-k on a score: 16-bit activations would pick
-            # different nodes near the threshold than the fp32 reference does, so they default to fp32 storage
             aggr = _SAGE_LISTS[model_name][1] if model_name in _SAGE_LISTS else (
-                "add" if model_name in ("GraphSage_addAggr_Shared", "GraphSAGE_SAG", "EAGNN_SAG") else "mean")
+                "add" if model_name == "GraphSage_addAggr_Shared" else "mean")
             precision = engine.default_precision(aggr)
+            # The SAGPooling variants default to the fp32-GEMM mode: they pick nodes by a discrete top-k on a score and
+            # multiply the survivors by it, which makes the prediction ~10x more sensitive to operand rounding than the
+            # plain variants (emulated tf32 operands in the fp32 oracle: 1.3e-3 .. 6e-3, tests/test_oracle.py), beyond
+            # the 1e-3 parity bar; the 3xTF32 mode stays below 1e-4.  tf32 / fp16 remain available explicitly.
+            if model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):
+                precision = "fp32"
         if precision not in engine.PRECISIONS:
             raise ValueError(f"precision must be \"auto\" or one of {engine.PRECISIONS}")
         if train_precision not in ("tf32", "bf16", "fp16"):

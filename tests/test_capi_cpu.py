@@ -140,7 +140,7 @@ def test_sag_variants_register_the_reference_module_names():
     assert keys.index("pooling_mpl.mlp.0.bias") < keys.index("sage_layers_1.0.lin_l.weight") < keys.index("pool.gnn.lin_l.weight") \
         < keys.index("sage_layers_2.0.lin_l.weight")
     assert tuple(m.pool.gnn.lin_l.weight.shape) == (1, 512) and tuple(m.pool.gnn.lin_l.bias.shape) == (1,)
-    assert "pool.gnn.lin_r.bias" not in keys and m.precision == "tf32"
+    assert "pool.gnn.lin_r.bias" not in keys and m.precision == "fp32"
     e = BuckGNN(16, 5, 512, 4, "mean", model_name="EAGNN_SAG")
     assert len(e.gnn_layers_1) == 2 and len(e.gnn_layers_2) == 2 and len(e.batch_norms_1) == 0
     assert "gnn_layers_2.1.node_mlp_beta.2.bias" in e.state_dict()

@@ -166,7 +166,10 @@ def _forward_case(ref, ours, b, rtol):
     return rel
 
 
-@pytest.mark.parametrize("precision,rtol", [("tf32", 1e-3), ("fp32", 1e-4)])
+# tf32 operands: the SAGPooling variants amplify operand rounding ~10x (the fp32 ORACLE with operands rounded to tf32
+# deviates 1.3e-3 .. 6e-3 from itself, tests/test_oracle.py::test_sag_variants_amplify_operand_rounding), so tf32 is an
+# opt-in fast mode here with its own bound; the default mode of these variants is fp32 (3xTF32), held to 1e-4.
+@pytest.mark.parametrize("precision,rtol", [("tf32", 8e-3), ("fp32", 1e-4)])
 @pytest.mark.parametrize("layers", [6, 3])
 def test_graphsage_sag_matches_oracle(precision, rtol, layers):
     """reference :190-217, :493-511 -- layers // 2 before the pooling, the rest after (3 -> 1 + 2)"""
@@ -176,7 +179,7 @@ def test_graphsage_sag_matches_oracle(precision, rtol, layers):
 
 def test_graphsage_sag_larger_meshes_default_precision():
     ref, ours = _model_pair("GraphSAGE_SAG", "auto", 6, seed=1)
-    assert ours.precision == "tf32"
+    assert ours.precision == "fp32"
     _forward_case(ref, ours, make_batch(4, nx=24, ny=20), 1e-3)
 
 
@@ -187,7 +190,7 @@ def test_graphsage_sag_pooling_layers_use_pooled_graph_offsets(pooling):
     _forward_case(ref, ours, make_batch(3, nx=8, ny=6), 1e-4)
 
 
-@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("tf32", 2e-3)])
+@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("tf32", 8e-3)])
 def test_eagnn_sag_matches_oracle(precision, rtol):
     """reference :219-244, :354-373 -- pooled edge features are the rows of the kept edges"""
     torch.manual_seed(3)

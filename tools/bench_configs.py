@@ -1,6 +1,7 @@
 """Throughput of the other BASELINE.json configs on one B200 (not the headline bench line):
   cfg3  stiffened-plate EA-GNN ("CustomGNN"), batch 128, fp16 operands / fp32 accumulate
   cfg5  GraphSAGE 6x512 on stiffened plates with mesh sizes scaled 1x..8x (hub degree = graph size)
+  sag   the SAGPooling variants: GraphSAGE_SAG on the cfg2 batch (256 plates), EAGNN_SAG on 64 stiffened plates
 Prints one JSON line per case."""
 import json
 import os
@@ -81,6 +82,22 @@ def main():
                               "ms_per_forward": ms, "graphs_per_s": graphs / (ms * 1e-3),
                               "nodes_per_s": b.num_nodes / (ms * 1e-3), "kernel_ms": k}), flush=True)
             del b
+            torch.cuda.empty_cache()
+    if "sag" in which:
+        for name, prec, graphs, kw in (("GraphSAGE_SAG", "fp32", 256, {}), ("GraphSAGE_SAG", "tf32", 256, {}),
+                                       ("GraphSAGE_SAG", "fp16", 256, {}), ("EAGNN_SAG", "fp32", 64, dict(stiffened=True)),
+                                       ("EAGNN_SAG", "tf32", 64, dict(stiffened=True))):
+            cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=6,
+                       pooling_layer="mean", model_name=name)
+            model = seeded_model(cfg, prec)
+            b = make_batch(graphs, **kw).to(DEV)
+            ms, k, _ = timed(model, b)
+            lp = model.last_pool
+            print(json.dumps({"config": f"sag: {name} 6x512 (3 layers, SAGPooling ratio 0.5, 3 layers), batch {graphs}",
+                              "precision": prec, "graphs": graphs, "nodes": b.num_nodes, "edges": b.num_edges,
+                              "pooled_nodes": lp.n_nodes, "pooled_edges": lp.n_edges, "ms_per_forward": ms,
+                              "graphs_per_s": graphs / (ms * 1e-3), "kernel_ms": k}), flush=True)
+            del model, b
             torch.cuda.empty_cache()
 
 
