@@ -641,6 +641,15 @@ int bg_sag_select(const void* x, int dtype, int64_t N, const int32_t* rowptr, co
   k_sag_plan<<<1, 1024, 0, stream>>>(graph_ptr, (int32_t)G, ratio, new_graph_ptr, w.tile_ptr, info);
   BG_LAUNCH_OK();
   if (N > 0 && G > 0) {
+    static bool sort_attr_set = false;
+    const int sort_smem = kSagSortMax * (int)sizeof(unsigned long long);
+    if (!sort_attr_set) {
+      BG_CUDA_OK(cudaFuncSetAttribute(k_sag_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sort_smem));
+      sort_attr_set = true;
+    }
+    k_sag_sort<<<(unsigned)min64(G, sms), 1024, sort_smem, stream>>>(score, graph_ptr, (int32_t)G, new_graph_ptr, new_id, perm,
+                                                                     batch_out, score_out);
+    BG_LAUNCH_OK();
     const unsigned tiles = (unsigned)(ceil_div64(N, kRankTileI) + G);       // >= sum_g ceil(n_g / tile)
     k_sag_rank<<<tiles, kRankThreads, 0, stream>>>(score, graph_ptr, (int32_t)G, new_graph_ptr, w.tile_ptr, new_id, perm,
                                                   batch_out, score_out);

@@ -13,10 +13,13 @@
 //                     and a scalar neighbourhood sum instead of a 512-wide aggregation
 //   k_sag_score(_big) score_i = tanh(sign * (sum_{j -> i} p_j + b + q_i)) over the CSR keyed by target
 //   k_sag_plan        k_g = ceil(ratio * n_g); exclusive scans -> new graph offsets, rank-tile offsets
-//   k_sag_rank        rank_i = #{j in graph(i): s_j > s_i or (s_j == s_i and j < i)} by counting
-//                     (score tiles broadcast from shared memory); node i is kept iff rank_i < k_g
-//                     and lands at row new_ptr[g] + rank_i -- a stable descending top-k with
-//                     no sort, bit-exact vs torch.sort(descending, stable)
+//   k_sag_sort        graphs of up to 16384 nodes: one CTA per graph sorts 64-bit keys (order-preserving score
+//                     bits, descending | local node id) with a bitonic network in shared memory; the first
+//                     k_g entries are the kept nodes in PyG's order.  Equal scores keep the lower node id
+//                     first = torch.sort(descending, stable)
+//   k_sag_rank        larger graphs: rank_i = #{j in graph(i): s_j > s_i or (s_j == s_i and j < i)} by
+//                     counting (score tiles broadcast from shared memory); node i is kept iff
+//                     rank_i < k_g and lands at row new_ptr[g] + rank_i -- the same order without a sort
 //   k_sag_edge_count / k_sag_scan_sums / k_sag_edge_write   order-preserving edge compaction
 //   k_gather_rows     out[r] = x[idx[r]] * scale[idx[r]]   (x[perm] * score[perm]; edge rows)
 #pragma once
@@ -35,6 +38,7 @@ constexpr int kRankPerThread = 4;
 constexpr int kRankTileI = kRankThreads * kRankPerThread;   // nodes ranked by one CTA
 constexpr int kRankTileJ = 2048;                            // scores staged in shared memory per step
 constexpr int kEdgeItemsPerBlock = 4096;                    // 1024 threads x 4 consecutive edges
+constexpr int kSagSortMax = 16384;                          // graphs up to this size sort in shared memory (128 KB of keys)
 
 template <typename T> BG_DEVINL void row_values(const T* row, int lane, float (&v)[16]) {
   RowFrag<T> f;
@@ -191,6 +195,56 @@ BG_DEVINL void rank_tile(const float* __restrict__ sj, int32_t cnt, int32_t j_ba
   }
 }
 
+// ascending order of this key = descending score, ties by ascending local node id.  -0.0 is folded onto +0.0 first
+// (they compare equal as floats, so a stable float sort does not separate them).
+BG_DEVINL unsigned long long sag_sort_key(float s, uint32_t local) {
+  const uint32_t b = __float_as_uint(s + 0.0f);
+  const uint32_t asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)(~asc) << 32) | local;
+}
+
+// one 1024-thread CTA per graph (grid-stride over graphs); graphs above kSagSortMax nodes are left to k_sag_rank
+__global__ void __launch_bounds__(1024)
+k_sag_sort(const float* __restrict__ score, const int32_t* __restrict__ graph_ptr, int32_t G,
+           const int32_t* __restrict__ new_ptr, int32_t* __restrict__ new_id, int32_t* __restrict__ perm,
+           int64_t* __restrict__ batch_out, float* __restrict__ score_out) {
+  extern __shared__ unsigned long long sag_keys[];
+  for (int32_t g = blockIdx.x; g < G; g += gridDim.x) {
+    const int32_t lo = graph_ptr[g], n = graph_ptr[g + 1] - lo;
+    if (n <= 0 || n > kSagSortMax) continue;                       // uniform over the CTA
+    int32_t P = 1;
+    while (P < n) P <<= 1;
+    for (int32_t i = threadIdx.x; i < P; i += 1024)
+      sag_keys[i] = (i < n) ? sag_sort_key(score[lo + i], (uint32_t)i) : ~0ull;
+    __syncthreads();
+    for (int32_t k = 2; k <= P; k <<= 1) {
+      for (int32_t j = k >> 1; j > 0; j >>= 1) {
+        for (int32_t t = threadIdx.x; t < (P >> 1); t += 1024) {
+          const int32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // bit j clear
+          const int32_t l = i | j;
+          const unsigned long long a = sag_keys[i], b = sag_keys[l];
+          if ((a > b) == ((i & k) == 0)) { sag_keys[i] = b; sag_keys[l] = a; }
+        }
+        __syncthreads();
+      }
+    }
+    const int32_t base = new_ptr[g], k_g = new_ptr[g + 1] - base;
+    for (int32_t r = threadIdx.x; r < n; r += 1024) {
+      const int32_t node = lo + (int32_t)(uint32_t)sag_keys[r];
+      if (r < k_g) {
+        const int32_t nid = base + r;
+        new_id[node] = nid;
+        perm[nid] = node;
+        batch_out[nid] = (int64_t)g;
+        score_out[nid] = score[node];
+      } else {
+        new_id[node] = -1;
+      }
+    }
+    __syncthreads();                                                // the keys are reused by the next graph
+  }
+}
+
 __global__ void __launch_bounds__(kRankThreads)
 k_sag_rank(const float* __restrict__ score, const int32_t* __restrict__ graph_ptr, int32_t G,
            const int32_t* __restrict__ new_ptr, const int32_t* __restrict__ tile_ptr,
@@ -206,6 +260,7 @@ k_sag_rank(const float* __restrict__ score, const int32_t* __restrict__ graph_pt
   }
   const int32_t g = lo_g;
   const int32_t lo = graph_ptr[g], hi = graph_ptr[g + 1];
+  if (hi - lo <= kSagSortMax) return;             // sorted in shared memory by k_sag_sort
   const int32_t i0 = lo + (t - tile_ptr[g]) * kRankTileI;
   const int32_t i_end = min(i0 + kRankTileI, hi);
   float si[kRankPerThread];

@@ -68,7 +68,7 @@ def test_cuda_forward_matches_golden(name):
     from buckgnn_b200.model import BuckGNN
     g = GOLD["forward"][name]
     ref = mk.seeded_oracle(g["cfg"])                         # used as a seeded weight container only
-    sag = "SAG" in g["cfg"]["model_name"]                    # SAGPooling variants: their default fp32-GEMM mode
+    sag = g["cfg"]["model_name"] in ("GraphSAGE_SAG", "EAGNN_SAG")                    # SAGPooling variants: their default fp32-GEMM mode
     ours = BuckGNN(**g["cfg"], precision="fp32" if sag else "tf32")
     ours.load_state_dict(ref.state_dict())
     ours = ours.to("cuda:0").eval()

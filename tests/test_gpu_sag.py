@@ -91,10 +91,18 @@ def test_sag_pool_operator_ragged_graphs():
     assert torch.equal(torch.bincount(res.batch.cpu()), (sizes + 1) // 2)
 
 
-def test_sag_pool_operator_large_graph_spans_rank_tiles():
-    """one graph above 4 x 1024 nodes: every rank tile sees earlier, own and later score tiles"""
+def test_sag_pool_operator_mid_size_graphs_sort_in_shared_memory():
+    """4761-node graphs: the bitonic network runs on a padded power of two (8192 keys)"""
     b = make_batch(2, nx=70, ny=68)
     _check_operator(b, "tf32", _pool_weights(3))
+
+
+def test_sag_pool_operator_graph_above_the_sort_limit_is_ranked_by_counting():
+    """one graph above 16384 nodes next to small ones: the counting kernel's tiles see earlier, own and later
+    score ranges; the small graphs go through the shared-memory sort in the same call"""
+    b = collate([make_plate_graph(0, nx=9, ny=7), make_plate_graph(1, nx=131, ny=129), make_plate_graph(2, nx=30, ny=11)])
+    assert int(torch.bincount(b.batch).max()) > 16384
+    _check_operator(b, "tf32", _pool_weights(6))
 
 
 def test_sag_pool_operator_saturated_scores_tie_break_by_node_id():

@@ -83,10 +83,11 @@ def main():
                               "nodes_per_s": b.num_nodes / (ms * 1e-3), "kernel_ms": k}), flush=True)
             del b
             torch.cuda.empty_cache()
-    if "sag" in which:
-        for name, prec, graphs, kw in (("GraphSAGE_SAG", "fp32", 256, {}), ("GraphSAGE_SAG", "tf32", 256, {}),
+    if "sag" in which or "sag1" in which:
+        cases = (("GraphSAGE_SAG", "fp32", 256, {}), ("GraphSAGE_SAG", "tf32", 256, {}),
                                        ("GraphSAGE_SAG", "fp16", 256, {}), ("EAGNN_SAG", "fp32", 64, dict(stiffened=True)),
-                                       ("EAGNN_SAG", "tf32", 64, dict(stiffened=True))):
+                                       ("EAGNN_SAG", "tf32", 64, dict(stiffened=True)))
+        for name, prec, graphs, kw in (cases[:1] if "sag1" in which else cases):
             cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=6,
                        pooling_layer="mean", model_name=name)
             model = seeded_model(cfg, prec)
