@@ -8,10 +8,12 @@ runs, so a B200 forward (about 12 ms for 256 plates) hides the ~5 ms PCIe transf
 """
 from __future__ import annotations
 
-from typing import Iterable, Iterator
+from collections import deque
+from typing import Callable, Iterable, Iterator, Optional
 
 import torch
 
+from . import capi
 from .synth import PlateBatch
 
 
@@ -72,3 +74,71 @@ class DevicePrefetcher:
                 nxt = None
             yield cur
             self.released[cur_k].record(torch.cuda.current_stream(self.device))
+
+
+class PipelinedInference:
+    """The inference loop of `INFERENCE.py:133-150` / `INFERENCE_TIMER.py:229-237` as a three-stage pipeline:
+    while batch i computes, batch i+1 is copied host -> device on a second stream (`DevicePrefetcher`) and the
+    eigenvalues of batch i-1 are already on their way to pinned host memory.  The GPU never waits for the host to
+    read a result before it gets the next batch's kernels, so a step costs max(device time, host enqueue time)
+    instead of their sum.
+
+        for step, pred_host in PipelinedInference(model, pinned_batches, "cuda:0"):
+            ...                                   # pred_host: [G] f32 CPU tensor of batch number `step`
+
+    Results come back `depth` steps late, in order, every batch exactly once (the device-side staging buffers of a
+    batch are recycled two steps later, so only the prediction is handed out).  The read-back goes through
+    `bg_publish_words` (SM stores to pinned memory) rather than a D2H memcpy, which would queue on a copy engine
+    behind the next batch's H2D transfer."""
+
+    def __init__(self, model, batches: Iterable[PlateBatch], device, depth: int = 1,
+                 on_launch: Optional[Callable] = None):
+        self.model, self.batches, self.device, self.depth = model, batches, torch.device(device), max(0, int(depth))
+        self.prefetcher = DevicePrefetcher(batches, self.device)
+        self.on_launch = on_launch            # called as on_launch(step, before: bool) around each forward (timing hooks)
+
+    def _read_back(self, pred: torch.Tensor, host: torch.Tensor) -> torch.cuda.Event:
+        flat = pred.detach().reshape(-1)
+        if flat.dtype != torch.float32:
+            flat = flat.float()
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        n = flat.numel()
+        for off in range(0, n, 256):          # 4-byte words, at most 256 per call
+            capi.publish_words(flat.data_ptr() + 4 * off, host.data_ptr() + 4 * off, min(256, n - off), s)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._keep = flat                     # alive until the next call's kernels are queued behind it
+        return ev
+
+    def __iter__(self) -> Iterator:
+        inflight = deque()
+        pool = {}
+        step = 0
+        with torch.no_grad():
+            for b in self.prefetcher:
+                if self.on_launch:
+                    self.on_launch(step, True)
+                pred, _ = self.model(b.x, b.edge_index, b.edge_attr, b.batch)
+                if self.on_launch:
+                    self.on_launch(step, False)
+                n = max(pred.numel(), 1)
+                bufs = pool.setdefault(n, [])
+                host = bufs.pop() if bufs else torch.empty(n, dtype=torch.float32).pin_memory()
+                ev = self._read_back(pred, host)
+                inflight.append((host, ev, tuple(pred.shape), step, n))
+                step += 1
+                while len(inflight) > self.depth:
+                    yield self._finish(inflight.popleft(), pool)
+            while inflight:
+                yield self._finish(inflight.popleft(), pool)
+
+    @staticmethod
+    def _finish(item, pool):
+        host, ev, shape, step, n = item
+        ev.synchronize()
+        count = 1
+        for d in shape:
+            count *= d
+        result = host[:count].clone().view(shape)     # the pinned buffer goes back to the pool
+        pool[n].append(host)
+        return step, result

@@ -236,3 +236,21 @@ def test_folded_layer0_with_isolated_nodes(name):
     _assert_rel(got, want, 1e-4)
     got2, want2 = _run(ref, ours, b)                                          # no isolated node: gate folded into the bias
     _assert_rel(got2, want2, 1e-4)
+
+
+def test_pipelined_inference_returns_every_batch_in_order():
+    """PipelinedInference (H2D one batch ahead, results one step late) gives the same eigenvalues as plain calls"""
+    from buckgnn_b200.pipeline import PipelinedInference
+    ref, ours = _pair("GraphSage_meanAggr", "fp16", layers=3)
+    hosts = [make_batch(g, nx=8 + g, ny=7, first_index=10 * g).pin_memory() for g in (3, 1, 4, 2, 5)]
+    want = []
+    with torch.no_grad():
+        for h in hosts:
+            d = h.to(DEV)
+            want.append(ours(d.x, d.edge_index, d.edge_attr, d.batch)[0].cpu())
+    for depth in (1, 0, 2):
+        got = list(PipelinedInference(ours, hosts, DEV, depth=depth))
+        assert [s for s, _ in got] == list(range(len(hosts)))
+        for (_, p), w in zip(got, want):
+            assert p.shape == w.shape and not p.is_cuda
+            assert torch.equal(p, w)
