@@ -63,7 +63,7 @@ __global__ void k_split_tf32(const float* __restrict__ src, float* __restrict__ 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float v = src[i];
     const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-    hi[i] = h;
+    if (hi) hi[i] = h;
     lo[i] = v - h;
   }
 }
@@ -1016,7 +1016,7 @@ int bg_cast_f32(const float* src, void* dst, int dst_dtype, int64_t n, void* str
 
 int bg_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (n < 0 || (n > 0 && (!src || !hi || !lo))) return fail(BG_ERR_INVALID, "bg_split_tf32: bad argument");
+  if (n < 0 || (n > 0 && (!src || !lo))) return fail(BG_ERR_INVALID, "bg_split_tf32: bad argument");
   if (n == 0) return BG_OK;
   k_split_tf32<<<grid_for(n, 256, sm_count() * 8), 256, 0, stream>>>(src, hi, lo, n);
   BG_LAUNCH_OK();

@@ -272,12 +272,14 @@ class Activation:
         self.data = torch.empty((n, width), dtype=self.dtype, device=device)
         self.hi = self.lo = None
         if precision == "fp32":
-            self.hi = torch.empty_like(self.data)
+            # tcgen05 kind::tf32 reads the upper 19 bits of an fp32 operand (truncation, verified bit-for-bit by
+            # tools/tf32_trunc_probe.py), so the data itself IS the hi operand; only lo = x - trunc(x) is stored
+            self.hi = self.data
             self.lo = torch.empty_like(self.data)
 
     def refresh_split(self):
         if self.precision == "fp32":
-            capi.split_tf32(self.data.data_ptr(), self.hi.data_ptr(), self.lo.data_ptr(), self.data.numel(), _stream())
+            capi.split_tf32(self.data.data_ptr(), None, self.lo.data_ptr(), self.data.numel(), _stream())
 
 
 def _segments(act: Activation, w: LinearPack):

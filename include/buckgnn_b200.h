@@ -366,7 +366,9 @@ int bg_dropout_mask(uint64_t seed, float dropout_p, int64_t n_rows, uint8_t* kee
  * fp32 -> bf16 / f16 (round to nearest even) cast of a contiguous buffer (weight packing). */
 int bg_cast_f32(const float* src, void* dst, int dst_dtype, int64_t n, void* stream);
 /* hi/lo split for the 3xTF32 "fp32-GEMM" mode: hi = src with the low 13 mantissa bits
- * cleared (exactly representable in tf32), lo = src - hi. */
+ * cleared (exactly representable in tf32), lo = src - hi.  hi may be NULL: tcgen05 kind::tf32 ignores the low 13
+ * mantissa bits of an fp32 operand (verified bit-for-bit on B200, tools/tf32_trunc_probe.py), so `src` itself
+ * serves as the hi operand and only lo needs to be materialised. */
 int bg_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream);
 
 #ifdef __cplusplus

@@ -263,7 +263,12 @@ def test_gemm_3xtf32_is_fp32_accurate():
     out = Activation(m, 512, "fp32", DEV)
     engine.gemm512(engine._segments(act, pack), m, "fp32", out)
     torch.testing.assert_close(out.data.cpu(), want, rtol=2e-5, atol=2e-5)
-    assert torch.equal((act.hi + act.lo).cpu(), a)       # the split is exact
+    trunc = (a.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    assert act.hi is act.data                            # the tensor core truncates: the data is its own hi part
+    assert torch.equal((trunc + act.lo.cpu()), a)        # the split is exact
+    hi, lo = torch.empty_like(act.data), torch.empty_like(act.data)
+    capi.split_tf32(act.data.data_ptr(), hi.data_ptr(), lo.data_ptr(), act.data.numel(), _stream())
+    assert torch.equal(hi.cpu(), trunc) and torch.equal(lo, act.lo)
 
 
 # ----------------------------------------------------------------------------- K4
