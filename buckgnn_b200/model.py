@@ -285,8 +285,8 @@ class BuckGNN(nn.Module):
         node_level = "static" in self.prediction_type or "mode_shape" in self.prediction_type
         if self.prediction_type != "buckling" and not node_level:
             raise ValueError(f"Unknown prediction type: {self.prediction_type}")
-        if node_level and (self.training or self.hidden_channels < 256):
-            raise NotImplementedError("buckgnn_b200: node-level heads run in eval mode with the 3-layer decoder only")
+        if node_level and self.hidden_channels < 256:
+            raise NotImplementedError("buckgnn_b200: node-level heads need the 3-layer decoder (hidden_channels >= 256)")
         if not node_level and self.pooling_layer not in ("mean", "mean_no_super", "supernode_only",
                                                           "supernode_with_pooling", "mlp", "mlp_no_super"):
             if self.pooling_layer == "hybrid":
@@ -294,7 +294,13 @@ class BuckGNN(nn.Module):
             raise ValueError(f"Unknown pooling layer: {self.pooling_layer}")
         if self.training:       # train-mode BatchNorm / Dropout + autograd through the backward kernels (train.py)
             from . import train
-            return train.forward_train(self, x, edge_index, batch, edge_attr=edge_attr).squeeze(), batch
+            pred = train.forward_train(self, x, edge_index, batch, edge_attr=edge_attr)
+            if node_level:                                   # reference :518-524; the row selection is an autograd index
+                if "super" in self.pooling_layer:
+                    is_real_node = x[:, -1] == 0
+                    return pred[is_real_node], (batch[is_real_node] if batch is not None else None)
+                return pred, batch
+            return pred.squeeze(), batch
         with torch.no_grad():
             if self.model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):
                 if node_level and "super" in self.pooling_layer:

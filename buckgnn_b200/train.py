@@ -275,6 +275,59 @@ def head_backward(model, sv, dpred: torch.Tensor, n: int, prec: str, grads: Grad
     return dcur
 
 
+def is_node_level(model) -> bool:
+    return "static" in model.prediction_type or "mode_shape" in model.prediction_type
+
+
+def node_head_forward_train(model, cur: Activation, sv) -> torch.Tensor:
+    """Node-level heads (`static_disp`, `static_stress`, `mode_shape`): `decoder(x)` on every node
+    (Models/BuckGNN.py:518-524; the caller drops the super-node rows).  Three `bg_sgemm` calls whose hidden layers
+    are kept for the backward pass."""
+    dev, n = cur.data.device, cur.data.shape[0]
+    dec = model.decoder
+    if len(dec) != 5:
+        raise NotImplementedError("buckgnn_b200: node-level training needs the 3-layer decoder (hidden_channels >= 256)")
+    decw = {"w1": dec[0].weight.detach(), "b1": dec[0].bias.detach(), "w2": dec[2].weight.detach(),
+            "b2": dec[2].bias.detach(), "w3": dec[4].weight.detach(), "b3": dec[4].bias.detach()}
+    decw = {k: v.float().contiguous() for k, v in decw.items()}
+    F32 = capi.BG_F32
+    out_dim = model.output_dim
+    with engine.TIMERS.span("node_head"):
+        h1d, h2d, pred = _f32((n, 128), dev), _f32((n, 64), dev), _f32((n, out_dim), dev)
+        sgemm(cur.data, cur.code, 512, 1, decw["w1"], F32, 1, 512, n, 128, 512, h1d, F32, 128, bias=decw["b1"], relu=True)
+        sgemm(h1d, F32, 128, 1, decw["w2"], F32, 1, 128, n, 64, 128, h2d, F32, 64, bias=decw["b2"], relu=True)
+        sgemm(h2d, F32, 64, 1, decw["w3"], F32, 1, 64, n, out_dim, 64, pred, F32, out_dim, bias=decw["b3"])
+    sv.decw, sv.dec_in, sv.h1d, sv.h2d, sv.mlp, sv.raw = decw, cur, h1d, h2d, None, None
+    return pred
+
+
+def node_head_backward(model, sv, dpred: torch.Tensor, n: int, prec: str, grads: GradStore) -> Activation:
+    """Backward of `decoder(x)` over all n nodes: returns d(last layer output) [n, 512]."""
+    dev = dpred.device
+    F32 = capi.BG_F32
+    out_dim = model.output_dim
+    d, dec = sv.decw, model.decoder
+    h1d, h2d, x = sv.h1d, sv.h2d, sv.dec_in
+    with engine.TIMERS.span("train_head_bwd"):
+        dw3, _ = grads.get(dec[4].weight); db3, _ = grads.get(dec[4].bias)
+        sgemm(dpred, F32, 1, out_dim, h2d, F32, 64, 1, out_dim, 64, n, dw3, F32, 64)
+        colsum(dpred, F32, n, out_dim, out_dim, db3)
+        dh2d = _f32((n, 64), dev)
+        sgemm(dpred, F32, out_dim, 1, d["w3"], F32, 64, 1, n, 64, out_dim, dh2d, F32, 64, mask=h2d, mask_ld=64)
+        dw2, _ = grads.get(dec[2].weight); db2, _ = grads.get(dec[2].bias)
+        sgemm(dh2d, F32, 1, 64, h1d, F32, 128, 1, 64, 128, n, dw2, F32, 128)
+        colsum(dh2d, F32, n, 64, 64, db2)
+        dh1d = _f32((n, 128), dev)
+        sgemm(dh2d, F32, 64, 1, d["w2"], F32, 128, 1, n, 128, 64, dh1d, F32, 128, mask=h1d, mask_ld=128)
+        dw1, _ = grads.get(dec[0].weight); db1, _ = grads.get(dec[0].bias)
+        sgemm(dh1d, F32, 1, 128, x.data, x.code, 512, 1, 128, 512, n, dw1, F32, 512)
+        colsum(dh1d, F32, n, 128, 128, db1)
+        dcur = Activation(n, 512, prec, dev)
+        sgemm(dh1d, F32, 128, 1, d["w1"], F32, 512, 1, n, 512, 128, dcur.data, dcur.code, 512)
+        dcur.refresh_split()
+    return dcur
+
+
 # ----------------------------------------------------------------------------- GraphSAGE
 class SageTrainFunction(torch.autograd.Function):
     """pred = f(parameters); x / edge_index / batch are data (no gradient)."""
@@ -351,7 +404,8 @@ class SageTrainFunction(torch.autograd.Function):
             sv.layers.append((conv, bn, cur, agg, u, inv_norm, vec, residual))
             cur = y
         sv.ones, sv.zeros = ones, zeros
-        pred = head_forward_train(model, cur, idx, sv)
+        sv.node_level = is_node_level(model)
+        pred = node_head_forward_train(model, cur, sv) if sv.node_level else head_forward_train(model, cur, idx, sv)
         ctx.sv = sv
         ctx.params = params
         return pred
@@ -365,7 +419,7 @@ class SageTrainFunction(torch.autograd.Function):
         s = _stream()
         dpred = dpred.detach().to(torch.float32).contiguous()
         grads = GradStore(dev)
-        dcur = head_backward(model, sv, dpred, n, prec, grads)
+        dcur = (node_head_backward if sv.node_level else head_backward)(model, sv, dpred, n, prec, grads)
         dy2: Optional[Activation] = None
 
         # ---- message passing layers, last to first
@@ -451,7 +505,7 @@ def trainable_parameters(model) -> List[torch.nn.Parameter]:
         add(conv.lin_l.weight); add(conv.lin_l.bias); add(conv.lin_r.weight)
         if bn is not None:
             add(bn.weight); add(bn.bias)
-    if model.pooling_layer in ("mlp", "mlp_no_super"):
+    if model.pooling_layer in ("mlp", "mlp_no_super") and not is_node_level(model):
         add(model.pooling_mpl.mlp[0].weight); add(model.pooling_mpl.mlp[0].bias)
     add_seq(model.decoder)
     return ps

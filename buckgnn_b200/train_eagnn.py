@@ -24,7 +24,8 @@ import torch
 from . import capi, engine
 from .engine import Activation, _stream
 from .train import (GradStore, _Saved, _f32, colsum, encoder_backward, encoder_forward_train, head_backward,
-                    head_forward_train, layer_seed, transposed_pack, weight_grad_mn)
+                    head_forward_train, is_node_level, layer_seed, node_head_backward, node_head_forward_train,
+                    transposed_pack, weight_grad_mn)
 
 _H = 512
 
@@ -151,7 +152,8 @@ class EAGNNTrainFunction(torch.autograd.Function):
             sv.layers.append((blk, cur, e, he, e1, hm, agg, g1, xg, t, skip))
             cur, e = x_next, e_next
         sv.weights = weights
-        pred = head_forward_train(model, cur, idx, sv)
+        sv.node_level = is_node_level(model)
+        pred = node_head_forward_train(model, cur, sv) if sv.node_level else head_forward_train(model, cur, idx, sv)
         ctx.sv = sv
         ctx.params = params
         return pred
@@ -165,7 +167,8 @@ class EAGNNTrainFunction(torch.autograd.Function):
         s = _stream()
         idx, ex = sv.idx, sv.ex
         grads = GradStore(dev)
-        dxn = head_backward(model, sv, dpred.detach().to(torch.float32).contiguous(), n, prec, grads)
+        dxn = (node_head_backward if sv.node_level else head_backward)(
+            model, sv, dpred.detach().to(torch.float32).contiguous(), n, prec, grads)
         den: Optional[Activation] = None                    # the last block's edge output feeds nothing
         G = lambda out, segs, m, **kw: engine.gemm512(segs, m, prec, out, **kw)
         seg = engine._segments

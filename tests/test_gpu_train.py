@@ -455,3 +455,67 @@ def test_eagnn_training_step_gradients_match_oracle(model_name, precision, layer
         checked += 1
     assert not bad, "\n".join(bad)
     assert checked >= 20
+
+
+# ----------------------------------------------------------------------------- node-level heads (static_disp / static_stress / mode_shape)
+@pytest.mark.parametrize("model_name,prediction_type,pooling,layers", [
+    ("GraphSage_meanAggr", "static_disp", "mean", 3),
+    ("GraphSage_meanAggr", "static_stress", "supernode_only", 3),      # decoder(x[is_real_node]): super rows dropped
+    ("EA_GNN", "mode_shape", "mean", 2),
+])
+def test_node_level_head_training_gradients_match_oracle(model_name, prediction_type, pooling, layers):
+    """`decoder(x)` on every node in train mode (Models/BuckGNN.py:518-524) with `loss.backward()`"""
+    torch.manual_seed(0)
+    cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=layers,
+               pooling_layer=pooling, prediction_type=prediction_type, model_name=model_name, dropout_rate=0.0)
+    ref = OracleBuckGNN(**cfg)
+    randomize_bn_stats(ref, realistic=True)
+    ours = BuckGNN(**cfg, train_precision="tf32")
+    ours.load_state_dict(ref.state_dict())
+    ref, ours = ref.train(), ours.to(DEV).train()
+    b = make_batch(3, nx=9, ny=8, stiffened=(model_name == "EA_GNN"))
+    bd = b.to(DEV)
+    got, got_batch = ours(bd.x, bd.edge_index, bd.edge_attr, bd.batch)
+    real = (b.x[:, -1] == 0) if "super" in pooling else torch.ones(b.num_nodes, dtype=torch.bool)
+    assert got.shape == (int(real.sum()), ours.output_dim) and torch.equal(got_batch.cpu(), b.batch[real])
+    y = torch.randn(got.shape, generator=torch.Generator().manual_seed(1))
+    # the oracle with OUR ReLU masks (see _MaskedReLU): message-passing layers and the two decoder ReLUs
+    fn = got.grad_fn
+    while fn is not None and not hasattr(fn, "sv"):
+        fn = fn.next_functions[0][0]
+    saved = fn.sv                                            # read before backward() releases it
+    head_masks = [(saved.h1d > 0).float().cpu()[real], (saved.h2d > 0).float().cpu()[real]]
+    if model_name != "EA_GNN":
+        relu_masks = []
+        for (_, bn, _, _, u, _, vec, _) in saved.layers:
+            v = u.data.float() * (vec[0] if bn is not None else 1.0) + (vec[1] if bn is not None else 0.0)
+            relu_masks.append((v > 0).float().cpu())
+        ref.relu = _MaskedReLU(relu_masks)
+    else:                                                    # our edge tensors are in CSR-by-row order
+        ne = b.num_edges
+        perm = saved.idx.perm[:ne].long().cpu()
+        inv = torch.empty_like(perm); inv[perm] = torch.arange(ne)
+        on = lambda act, edge: ((act.data.float() > 0).float().cpu()[inv] if edge else (act.data.float() > 0).float().cpu())
+        for blk, (_, _, _, he, _, hm, _, g1, _, t, _) in zip(ref.gn_blocks, saved.layers):
+            blk.edge_mlp[1] = _MaskedReLU([on(he, True)]); blk.node_mlp_phi[1] = _MaskedReLU([on(hm, True)])
+            blk.node_mlp_gamma[1] = _MaskedReLU([on(g1, False)]); blk.node_mlp_beta[1] = _MaskedReLU([on(t, False)])
+    ref.decoder[1], ref.decoder[3] = _MaskedReLU(head_masks[:1]), _MaskedReLU(head_masks[1:])
+    F.mse_loss(got, y.to(DEV)).backward()
+    want, _ = ref(b.x, b.edge_index, b.edge_attr, b.batch)
+    F.mse_loss(want, y).backward()
+    assert _rel(got.detach().cpu(), want.detach()) < 5e-3
+    tol = 2e-2 if model_name == "EA_GNN" else GRAD_TOL["tf32"]
+    ref_p, our_p = dict(ref.named_parameters()), dict(ours.named_parameters())
+    checked, bad = 0, []
+    for name, rp in ref_p.items():
+        op = our_p[name]
+        if rp.grad is None:
+            assert op.grad is None, name
+            continue
+        assert op.grad is not None, name
+        err = _rel(op.grad.cpu(), rp.grad)
+        if rp.grad.norm().item() > 1e-12 and not err < tol:
+            bad.append(f"{name}: rel err {err:.3e} >= {tol}")
+        checked += 1
+    assert not bad, "\n".join(bad)
+    assert checked >= 10
