@@ -246,6 +246,22 @@ def run_b200(args):
     kernel_ms = engine.TIMERS.summary()          # per kernel class: total ms, calls
     engine.TIMERS.disable()
 
+    # second figure: the same steps with the CSR cache warm -- `cache_index=True` keeps the
+    # index of an unchanged `edge_index` tensor, as a serving loop over a fixed mesh set would
+    model.cache_index = True
+    for _ in range(2):
+        fwd(resident)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(args.steps):
+        fwd(resident)
+    c1.record()
+    barrier()
+    cached_ms = c0.elapsed_time(c1) / args.steps
+    model.cache_index = False
+    model._index_cache = None
+
     # ---- end to end: every step copies that step's pinned-host inputs H->D (x, edge_index, edge_attr,
     # batch, y, ptr: everything `batch.to(device)` moves) and reads pred back D->H.  The copies of
     # step i+1 run on a second stream while step i computes, and the result of step i reaches the host while
@@ -304,9 +320,9 @@ def run_b200(args):
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([step_ms, e2e_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([step_ms, e2e_ms, cached_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, e2e_ms = t.tolist()
+        step_ms, e2e_ms, cached_ms = t.tolist()
     value = world * G / (step_ms * 1e-3)
     e2e_value = world * G / (e2e_ms * 1e-3)
 
@@ -337,6 +353,21 @@ def run_b200(args):
                                     "kernel": "k_gemm512",
                                     "ms_per_launch": ms / calls, "share_of_step": ms / args.steps / step_ms}
         dominant = max(roofs, key=lambda k: roofs[k]["share_of_step"]) if roofs else None
+        # whole-step fraction: sum over the kernel classes of max(bytes / HBM peak, flops / tensor
+        # peak) divided by the measured step -- algorithmic work only
+        ideal = {
+            "csr_build": (16.0 * E + 8.0 * E + 8.0 * N) / peaks["hbm_gbs"] / 1e6,
+            "encoder_front": (N * 16 * 4 + N * 128 * esz) / peaks["hbm_gbs"] / 1e6,
+            "aggregate128": (2 * N * 128 * esz + 4 * E + 4 * (N + 1)) / peaks["hbm_gbs"] / 1e6,
+            "sage_update0": max(2.0 * N * 320 * 512 * (3 if args.precision == "fp32" else 1) / tf_peak / 1e9,
+                                (N * (320 + 512) * esz) / peaks["hbm_gbs"] / 1e6),
+            "aggregate": (L - 1) * agg_bytes / peaks["hbm_gbs"] / 1e6,
+            "sage_update": (L - 1) * max(upd_flops / tf_peak / 1e9, N * (1024 + 512 + 512) * esz / peaks["hbm_gbs"] / 1e6),
+            "pool_head": N * 512 * esz / peaks["hbm_gbs"] / 1e6,
+        }
+        step_roofline = {"ideal_ms": sum(ideal.values()), "measured_ms": step_ms, "frac": sum(ideal.values()) / step_ms,
+                         "ideal_ms_by_kernel": ideal,
+                         "note": "sum_k max(B_k / measured HBM peak, F_k / measured sustained tensor peak) / step time"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _ = cpu_oracle_throughput(3, 1)
@@ -365,6 +396,9 @@ def run_b200(args):
             "gpu_launches": engine.LAUNCHES_PER_FORWARD(L, folded=model.fold_encoder) * args.steps,
             "roofline": roofs.get(dominant),
             "roofline_all": roofs,
+            "roofline_step": step_roofline,
+            "csr_cache_warm": {"value": world * G / (cached_ms * 1e-3), "unit": "graphs/s", "ms_per_step": cached_ms,
+                               "how": "cache_index=True: the CSR of an unchanged edge_index tensor is reused"},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kernel_ms.items()},
             "peaks": peaks,
             "cpu_baseline": cpu,
