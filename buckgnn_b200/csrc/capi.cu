@@ -631,10 +631,10 @@ int bg_sag_select(const void* x, int dtype, int64_t N, const int32_t* rowptr, co
     const unsigned grid = grid_for(N * 32, kSagWarps * 32, sms * 8);
     BG_BY_DTYPE(dtype, (k_sag_dots<T><<<grid, kSagWarps * 32, 0, stream>>>(static_cast<const T*>(x), N, w_l, w_r, w.p, w.q)));
     BG_LAUNCH_OK();
-    k_sag_score<<<grid_for(N * 8, 256, sms * 8), 256, 0, stream>>>(rowptr, col, w.p, w.q, bias, sign, N, score);
+    k_sag_score<true><<<grid_for(N * 8, 256, sms * 8), 256, 0, stream>>>(rowptr, col, w.p, w.q, bias, sign, N, score);
     BG_LAUNCH_OK();
     if (n_big > 0) {
-      k_sag_score_big<<<(unsigned)n_big, 256, 0, stream>>>(rowptr, col, big_rows, w.p, w.q, bias, sign, score);
+      k_sag_score_big<true><<<(unsigned)n_big, 256, 0, stream>>>(rowptr, col, big_rows, w.p, w.q, bias, sign, score);
       BG_LAUNCH_OK();
     }
   }
@@ -674,6 +674,37 @@ int bg_sag_connect(const int64_t* edge_index, int64_t E, int64_t N, const int32_
   if (workspace_bytes < w.bytes) return fail(BG_ERR_WORKSPACE, "bg_sag_connect: workspace too small");
   k_sag_edge_write<<<(unsigned)w.n_edge_blocks, 1024, 0, stream>>>(edge_index, E, N, new_id, w.block_sums, E_out,
                                                                   edge_index_out, kept_edge);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_sag_pool_backward(const void* dx_pooled, const void* x, int dtype, int64_t N, int64_t N_out, const int32_t* perm,
+                         const int32_t* new_id, const float* score, float sign, const int32_t* rowptr_src,
+                         const int32_t* col_src, const int32_t* big_rows_src, int32_t n_big_src, const float* w_l,
+                         const float* w_r, void* dx, float* t, float* dpre, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N < 0 || N_out < 0 || N_out > N || n_big_src < 0) return fail(BG_ERR_INVALID, "bg_sag_pool_backward: bad size");
+  if (N == 0) return BG_OK;
+  if (!x || !new_id || !score || !rowptr_src || !w_l || !w_r || !dx || !t || !dpre || !aligned16(x) || !aligned16(dx) ||
+      (N_out > 0 && (!dx_pooled || !perm || !aligned16(dx_pooled))) || (n_big_src > 0 && !big_rows_src))
+    return fail(BG_ERR_INVALID, "bg_sag_pool_backward: null or misaligned pointer");
+  const int sms = sm_count();
+  BG_CUDA_OK(cudaMemsetAsync(dpre, 0, sizeof(float) * (size_t)N, stream));
+  if (N_out > 0) {
+    const unsigned grid = grid_for(N_out * 32, kSagWarps * 32, sms * 8);
+    BG_BY_DTYPE(dtype, (k_sag_bwd_rowdot<T><<<grid, kSagWarps * 32, 0, stream>>>(static_cast<const T*>(dx_pooled), static_cast<const T*>(x),
+                                                                               perm, score, sign, N_out, dpre)));
+    BG_LAUNCH_OK();
+  }
+  k_sag_score<false><<<grid_for(N * 8, 256, sms * 8), 256, 0, stream>>>(rowptr_src, col_src, dpre, nullptr, 0.f, 1.f, N, t);
+  BG_LAUNCH_OK();
+  if (n_big_src > 0) {
+    k_sag_score_big<false><<<(unsigned)n_big_src, 256, 0, stream>>>(rowptr_src, col_src, big_rows_src, dpre, nullptr, 0.f, 1.f, t);
+    BG_LAUNCH_OK();
+  }
+  const unsigned grid = grid_for(N * 32, kSagWarps * 32, sms * 8);
+  BG_BY_DTYPE(dtype, (k_sag_bwd_dx<T><<<grid, kSagWarps * 32, 0, stream>>>(static_cast<const T*>(dx_pooled), new_id, score, t, dpre, w_l, w_r,
+                                                                         N, static_cast<T*>(dx))));
   BG_LAUNCH_OK();
   return BG_OK;
 }

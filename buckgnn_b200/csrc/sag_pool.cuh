@@ -87,6 +87,7 @@ k_sag_dots(const T* __restrict__ x, int64_t N, const float* __restrict__ w_l, co
 }
 
 // 8 lanes per row (mesh rows have ~5 neighbours); rows above the big-row threshold are left to k_sag_score_big
+template <bool kTanh>
 __global__ void __launch_bounds__(256)
 k_sag_score(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ p,
             const float* __restrict__ q, float bias, float sign, int64_t N, float* __restrict__ score) {
@@ -106,11 +107,12 @@ k_sag_score(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (small && sub == 0) score[r] = tanhf(sign * ((s + bias) + q[r]));
+    if (small && sub == 0) score[r] = kTanh ? tanhf(sign * ((s + bias) + q[r])) : s;
   }
 }
 
 // one CTA per hub row: strided partial sums, then a fixed-order reduction
+template <bool kTanh>
 __global__ void __launch_bounds__(256)
 k_sag_score_big(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ big_rows,
                 const float* __restrict__ p, const float* __restrict__ q, float bias, float sign,
@@ -127,7 +129,7 @@ k_sag_score_big(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
     float t = red[0];
 #pragma unroll
     for (int w = 1; w < 8; ++w) t += red[w];
-    score[r] = tanhf(sign * ((t + bias) + q[r]));
+    score[r] = kTanh ? tanhf(sign * ((t + bias) + q[r])) : t;
   }
 }
 
@@ -386,6 +388,68 @@ k_gather_rows(const T* __restrict__ x, int64_t ldx, const int32_t* __restrict__ 
       for (int i = 0; i < 16; ++i) v[i] *= s;
     }
     RowFrag<T>::store(out + (size_t)r * ldo, lane, v);
+  }
+}
+
+// ------------------------------------------------------------------ SAGPooling backward (training step)
+// Forward: s = tanh(sign * pre), pre_i = sum_{j -> i} w_l . x_j + b + w_r . x_i;  x'_r = x[perm[r]] * s[perm[r]].
+// Given dx' [N', 512]:
+//   k_sag_bwd_rowdot   ds_r = dx'_r . x[perm[r]];  dpre[perm[r]] = sign * (1 - s^2) * ds_r   (dpre zero elsewhere)
+//   k_sag_score<false> t_j = sum_{i: j -> i} dpre_i  over the CSR keyed by SOURCE
+//   k_sag_bwd_dx       dx_j = [j kept] s_j dx'_{new_id[j]} + w_l t_j + w_r dpre_j
+// and on the host side dw_l = sum_j t_j x_j, dw_r = sum_j dpre_j x_j (bg_sgemm with M = 1), db = sum_j dpre_j (bg_colsum).
+template <typename T>
+__global__ void __launch_bounds__(kSagWarps * 32)
+k_sag_bwd_rowdot(const T* __restrict__ dxp, const T* __restrict__ x, const int32_t* __restrict__ perm,
+                 const float* __restrict__ score, float sign, int64_t n_out, float* __restrict__ dpre) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_out; r += n_warps) {
+    const int32_t j = perm[r];
+    float a[16], b[16];
+    row_values(dxp + (size_t)r * kHidden, lane, a);
+    row_values(x + (size_t)j * kHidden, lane, b);
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d = fmaf(a[i], b[i], d);
+    d = warp_sum(d);
+    if (lane == 0) {
+      const float sj = score[j];
+      dpre[j] = sign * (1.f - sj * sj) * d;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSagWarps * 32)
+k_sag_bwd_dx(const T* __restrict__ dxp, const int32_t* __restrict__ new_id, const float* __restrict__ score,
+             const float* __restrict__ t, const float* __restrict__ dpre, const float* __restrict__ w_l,
+             const float* __restrict__ w_r, int64_t N, T* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  float wl[16], wr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = RowFrag<T>::col_of(lane, i);
+    wl[i] = w_l[c];
+    wr[i] = w_r[c];
+  }
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < N; j += n_warps) {
+    const int32_t nid = new_id[j];
+    float v[16];
+    if (nid >= 0) {
+      row_values(dxp + (size_t)nid * kHidden, lane, v);
+      const float sj = score[j];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] *= sj;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+    const float tj = t[j], dj = dpre[j];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaf(wl[i], tj, fmaf(wr[i], dj, v[i]));
+    RowFrag<T>::store(dx + (size_t)j * kHidden, lane, v);
   }
 }
 

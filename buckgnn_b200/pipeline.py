@@ -58,7 +58,12 @@ class DevicePrefetcher:
         return slot
 
     def __iter__(self) -> Iterator[PlateBatch]:
-        it = iter(self.batches)
+        return self.iterate(self.batches)
+
+    def iterate(self, batches: Iterable[PlateBatch]) -> Iterator[PlateBatch]:
+        """One pass over `batches`; the two device-side staging batches persist between passes (a long-lived
+        loader allocates them once)."""
+        it = iter(batches)
         k = 0
         try:
             nxt = self._stage(next(it), k)
@@ -96,6 +101,7 @@ class PipelinedInference:
         self.model, self.batches, self.device, self.depth = model, batches, torch.device(device), max(0, int(depth))
         self.prefetcher = DevicePrefetcher(batches, self.device)
         self.on_launch = on_launch            # called as on_launch(step, before: bool) around each forward (timing hooks)
+        self._pool = {}                       # pinned result buffers by size
 
     def _read_back(self, pred: torch.Tensor, host: torch.Tensor) -> torch.cuda.Event:
         flat = pred.detach().reshape(-1)
@@ -111,11 +117,16 @@ class PipelinedInference:
         return ev
 
     def __iter__(self) -> Iterator:
+        return self.run(self.batches)
+
+    def run(self, batches: Iterable[PlateBatch]) -> Iterator:
+        """One pass over `batches` (any iterable of pinned host batches).  Staging buffers and the pinned result
+        buffers are kept on the object, so later passes allocate nothing."""
         inflight = deque()
-        pool = {}
+        pool = self._pool
         step = 0
         with torch.no_grad():
-            for b in self.prefetcher:
+            for b in self.prefetcher.iterate(batches):
                 if self.on_launch:
                     self.on_launch(step, True)
                 pred, _ = self.model(b.x, b.edge_index, b.edge_attr, b.batch)

@@ -479,6 +479,163 @@ class SageTrainFunction(torch.autograd.Function):
         return (None, None, None, None, None, *grads.for_params(ctx.params))
 
 
+# ----------------------------------------------------------------------------- GraphSAGE_SAG
+def _sag_layer_forward(conv, bn, cur: Activation, idx, prec: str, bias_host, residual: bool, p_drop: float, seed_i: int,
+                       ws, ws_bytes, ones, zeros):
+    """One layer of the GraphSAGE_SAG loops (Models/BuckGNN.py:494-511): x = dropout(relu(bn(conv(x)))), then
+    `x + identity` -- the skip is added AFTER the dropout here, unlike the plain variants."""
+    dev, n = cur.data.device, cur.data.shape[0]
+    code = cur.code
+    s = _stream()
+    wl, wr = engine.pack_linear(conv.lin_l.weight, prec), engine.pack_linear(conv.lin_r.weight, prec)
+    agg = Activation(n, 512, prec, dev)
+    engine.aggregate(cur, agg, idx, "add")
+    u = Activation(n, 512, prec, dev)
+    inv_norm = _f32((n,), dev)
+    with engine.TIMERS.span("train_update_gemm"):
+        engine.gemm512(engine._segments(agg, wl) + engine._segments(cur, wr), n, prec, u, bias=bias_host.data_ptr(),
+                       normalize=True, inv_norm_out=inv_norm.data_ptr())
+    vec = _f32((4, 512), dev)
+    track = bn.track_running_stats and bn.running_mean is not None
+    momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+    capi.bn_batch_stats(u.data.data_ptr(), code, n, bn.weight.detach().data_ptr(), bn.bias.detach().data_ptr(), float(bn.eps),
+                        momentum, bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
+                        bn.num_batches_tracked.data_ptr() if track else None, vec[0].data_ptr(), vec[1].data_ptr(),
+                        vec[2].data_ptr(), vec[3].data_ptr(), ws.data_ptr(), ws_bytes, s)
+    y = Activation(n, 512, prec, dev)
+    capi.bn_act_forward(u.data.data_ptr(), None, y.data.data_ptr(), code, n, vec[0].data_ptr(), vec[1].data_ptr(), p_drop, seed_i, s)
+    if residual:
+        capi.add(y.data.data_ptr(), cur.data.data_ptr(), None, y.data.data_ptr(), code, y.data.numel(), s)
+    y.refresh_split()
+    return y, (conv, bn, cur, agg, u, inv_norm, vec, residual, seed_i)
+
+
+def _sag_layer_backward(saved, gup: Activation, idx, idx_t, prec: str, p_drop: float, grads: GradStore, ws, ws_bytes) -> Activation:
+    """Backward of `_sag_layer_forward`: `gup` is d loss / d (layer output); returns d loss / d (layer input)."""
+    conv, bn, x_in, agg, u, inv_norm, vec, residual, seed_i = saved
+    dev, n = gup.data.device, gup.data.shape[0]
+    code = gup.code
+    s = _stream()
+    dz = Activation(n, 512, prec, dev)
+    dgam, acc_g = grads.get(bn.weight); dbet, _ = grads.get(bn.bias)
+    capi.sage_backward_rows(u.data.data_ptr(), gup.data.data_ptr(), None, inv_norm.data_ptr(), None, code, n,
+                            vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(), p_drop, seed_i,
+                            dgam.data_ptr(), dbet.data_ptr(), acc_g, dz.data.data_ptr(), None, None, ws.data_ptr(), ws_bytes, s)
+    dz.refresh_split()
+    dwl, acc_l = grads.get(conv.lin_l.weight)
+    dwr, acc_r = grads.get(conv.lin_r.weight)
+    weight_grad_mn(dz.data, agg.data, code, n, dwl, acc_l)
+    weight_grad_mn(dz.data, x_in.data, code, n, dwr, acc_r)
+    dbl, acc_b = grads.get(conv.lin_l.bias)
+    colsum(dz.data, code, n, 512, 512, dbl, accumulate=acc_b)
+    wlt, wrt = transposed_pack(conv.lin_l.weight, prec), transposed_pack(conv.lin_r.weight, prec)
+    dagg = Activation(n, 512, prec, dev)
+    engine.gemm512(engine._segments(dz, wlt), n, prec, dagg)
+    sbuf = Activation(n, 512, prec, dev)
+    engine.aggregate(dagg, sbuf, idx_t, "sum")                      # A^T dagg ('add' aggregation: no degree scaling)
+    dx = Activation(n, 512, prec, dev)
+    engine.gemm512(engine._segments(dz, wrt), n, prec, dx, residual=sbuf.data.data_ptr(), ldr=512)
+    if residual:                                                    # the skip branch carries the undropped gradient
+        capi.add(dx.data.data_ptr(), gup.data.data_ptr(), None, dx.data.data_ptr(), code, dx.data.numel(), s)
+        dx.refresh_split()
+    return dx
+
+
+class SagTrainFunction(torch.autograd.Function):
+    """Training step of `GraphSAGE_SAG` (Models/BuckGNN.py:190-217, 493-511): num_layers // 2 SAGE('add') layers,
+    SAGPooling(0.5) -- differentiable through `x[perm] * score[perm]` and the tanh score GNN, the selection itself is
+    piecewise constant -- then the remaining layers on the pooled graph, pooling and the eigenvalue head."""
+
+    @staticmethod
+    def forward(ctx, model, x, edge_index, batch, seed, *params):
+        prec = model.train_precision
+        dev = x.device
+        x = x.detach().to(torch.float32).contiguous()
+        n = x.shape[0]
+        p_drop = float(model.dropout.p)
+        pending = engine.begin_graph_index(edge_index, batch, n)
+        enc = model.node_encoder
+        convs = model._sage_layers()
+        n_before = len(model.sage_layers_1)
+        biases = torch.stack([enc[4].bias.detach().float()] + [c.lin_l.bias.detach().float() for c, _ in convs]).cpu()
+        sv = _Saved()
+        sv.model, sv.prec, sv.n, sv.x, sv.seed, sv.p_drop = model, prec, n, x, seed, p_drop
+        sv.h1, sv.h2, cur = encoder_forward_train(enc, x, prec, biases[0])
+        idx = pending.finish()
+        sv.idx_full, sv.edge_index = idx, pending.edge_index
+        ws_bytes = capi.train_workspace_bytes(n)
+        ws = _ws(ws_bytes, dev)
+        ones = torch.ones(512, dtype=torch.float32, device=dev)
+        zeros = torch.zeros(512, dtype=torch.float32, device=dev)
+        sv.first, sv.second = [], []
+        for i in range(n_before):
+            conv, bn = convs[i]
+            cur, saved = _sag_layer_forward(conv, bn, cur, idx, prec, biases[1 + i], i > 0, p_drop, layer_seed(seed, i),
+                                            ws, ws_bytes, ones, zeros)
+            sv.first.append(saved)
+        sv.pool_in = cur
+        pack = engine.pack_sag_pool(model.pool)
+        pooled = engine.sag_pool(cur, idx, idx.graph_ptr, idx.n_graphs, edge_index, pack, sign=model._sag_sign)
+        model.last_pool = pooled
+        sv.pooled, sv.pool_pack = pooled, pack
+        idx2 = engine.build_graph_index(pooled.edge_index, pooled.batch, pooled.n_nodes)
+        sv.idx = idx2                                   # head_backward reads sv.idx.graph_ptr
+        cur = pooled.x
+        for k in range(n_before, len(convs)):
+            conv, bn = convs[k]
+            cur, saved = _sag_layer_forward(conv, bn, cur, idx2, prec, biases[1 + k], True, p_drop, layer_seed(seed, k),
+                                            ws, ws_bytes, ones, zeros)
+            sv.second.append(saved)
+        pred = head_forward_train(model, cur, idx2, sv)
+        ctx.sv = sv
+        ctx.params = params
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        sv = ctx.sv
+        model, prec, n = sv.model, sv.prec, sv.n
+        code = engine.PRECISION_FORMATS[prec][0]
+        dev = sv.x.device
+        s = _stream()
+        F32 = capi.BG_F32
+        grads = GradStore(dev)
+        pooled, idx2 = sv.pooled, sv.idx
+        n2 = pooled.n_nodes
+        dcur = head_backward(model, sv, dpred.detach().to(torch.float32).contiguous(), n2, prec, grads)
+        ws_bytes = capi.train_workspace_bytes(n)
+        ws = _ws(ws_bytes, dev)
+        if sv.second:
+            idx2_t = engine.build_graph_index(pooled.edge_index, None, n2, key_row=0)
+            for saved in reversed(sv.second):
+                dcur = _sag_layer_backward(saved, dcur, idx2, idx2_t, prec, sv.p_drop, grads, ws, ws_bytes)
+        # ---- SAGPooling backward
+        idx_t = engine.build_graph_index(sv.edge_index, None, n, key_row=0)
+        xin = sv.pool_in
+        dx = Activation(n, 512, prec, dev)
+        t, dpre = _f32((n,), dev), _f32((n,), dev)
+        pack = sv.pool_pack
+        with engine.TIMERS.span("sag_pool_bwd"):
+            capi.sag_pool_backward(dcur.data.data_ptr(), xin.data.data_ptr(), code, n, n2, pooled.perm.data_ptr(),
+                                   pooled.new_id.data_ptr(), pooled.all_scores.data_ptr(), float(model._sag_sign),
+                                   idx_t.rowptr.data_ptr(), idx_t.col.data_ptr(), idx_t.big_rows.data_ptr(), idx_t.n_big,
+                                   pack["w_l"].data_ptr(), pack["w_r"].data_ptr(), dx.data.data_ptr(), t.data_ptr(),
+                                   dpre.data_ptr(), s)
+            dx.refresh_split()
+            gnn = model.pool.gnn
+            dwl, _ = grads.get(gnn.lin_l.weight); dwr, _ = grads.get(gnn.lin_r.weight); dbl, _ = grads.get(gnn.lin_l.bias)
+            # dw_l = sum_j t_j x_j, dw_r = sum_j dpre_j x_j: [1, n] x [n, 512]
+            sgemm(t, F32, 0, 1, xin.data, code, 512, 1, 1, 512, n, dwl, F32, 512)
+            sgemm(dpre, F32, 0, 1, xin.data, code, 512, 1, 1, 512, n, dwr, F32, 512)
+            colsum(dpre, F32, n, 1, 1, dbl)
+        dcur = dx
+        for saved in reversed(sv.first):
+            dcur = _sag_layer_backward(saved, dcur, sv.idx_full, idx_t, prec, sv.p_drop, grads, ws, ws_bytes)
+        encoder_backward(model.node_encoder, sv.x, sv.h1, sv.h2, dcur, prec, grads)
+        ctx.sv = None
+        return (None, None, None, None, None, *grads.for_params(ctx.params))
+
+
 def trainable_parameters(model) -> List[torch.nn.Parameter]:
     """Parameters the training step produces gradients for (the reference registers more modules than a given
     `model_name` uses: Models/BuckGNN.py:164,184-187)."""
@@ -505,6 +662,9 @@ def trainable_parameters(model) -> List[torch.nn.Parameter]:
         add(conv.lin_l.weight); add(conv.lin_l.bias); add(conv.lin_r.weight)
         if bn is not None:
             add(bn.weight); add(bn.bias)
+    if model.model_name == "GraphSAGE_SAG":
+        gnn = model.pool.gnn
+        add(gnn.lin_l.weight); add(gnn.lin_l.bias); add(gnn.lin_r.weight)
     if model.pooling_layer in ("mlp", "mlp_no_super") and not is_node_level(model):
         add(model.pooling_mpl.mlp[0].weight); add(model.pooling_mpl.mlp[0].bias)
     add_seq(model.decoder)
@@ -518,4 +678,10 @@ def forward_train(model, x, edge_index, batch, seed: Optional[int] = None, edge_
     if model.model_name in ("EA_GNN", "EA_GNN_Shared"):
         from .train_eagnn import EAGNNTrainFunction
         return EAGNNTrainFunction.apply(model, x, edge_index, edge_attr, batch, seed, *params)
+    if model.model_name == "GraphSAGE_SAG":
+        if is_node_level(model):
+            raise NotImplementedError("buckgnn_b200: GraphSAGE_SAG trains with the eigenvalue head only")
+        if batch is None:
+            batch = torch.zeros(x.shape[0], dtype=torch.int64, device=x.device)
+        return SagTrainFunction.apply(model, x, edge_index, batch, seed, *params)
     return SageTrainFunction.apply(model, x, edge_index, batch, seed, *params)

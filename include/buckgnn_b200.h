@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 5
+#define BG_ABI_VERSION 6
 
 typedef enum bg_status {
   BG_OK = 0,
@@ -258,6 +258,19 @@ int bg_sag_select(const void* x, int dtype, int64_t n_nodes, const int32_t* rowp
 int bg_sag_connect(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, const int32_t* new_id,
                    int64_t n_edges_out, int64_t* edge_index_out, int32_t* kept_edge,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of SAGPooling for the training step (autograd of `self.pool`, Models/BuckGNN.py:502-504): given
+ * dx_pooled = d loss / d x' [N', 512], x [N, 512] (the pooling input), perm / new_id / score [N] (= all scores) from
+ * bg_sag_select and the CSR of the un-pooled graph keyed by SOURCE (bg_csr_build key_row = 0, with its big rows):
+ *    dpre_j = sign (1 - s_j^2) (dx'_r . x_j) for j = perm[r], 0 for dropped nodes      (tanh and the row scaling)
+ *    t_j    = sum_{i: j -> i} dpre_i                                                   (the 'add' aggregation, transposed)
+ *    dx_j   = [j kept] s_j dx'_{new_id[j]} + w_l t_j + w_r dpre_j                      [N, 512] of `dtype`
+ * t, dpre [N] f32 are outputs too: the scorer's gradients are dw_l = sum_j t_j x_j, dw_r = sum_j dpre_j x_j
+ * (bg_sgemm with m = 1) and db = sum_j dpre_j (bg_colsum). */
+int bg_sag_pool_backward(const void* dx_pooled, const void* x, int dtype, int64_t n_nodes, int64_t n_nodes_out,
+                         const int32_t* perm, const int32_t* new_id, const float* score, float sign,
+                         const int32_t* rowptr_src, const int32_t* col_src, const int32_t* big_rows_src,
+                         int32_t n_big_src, const float* w_l, const float* w_r, void* dx, float* t, float* dpre,
+                         void* stream);
 int bg_gather_rows(const void* x, int dtype, int64_t ldx, const int32_t* row_index, const float* row_scale,
                    int64_t n_rows_out, void* out, int64_t ldo, void* stream);
 int bg_index_invert(const int32_t* perm, int64_t n, int32_t* out, void* stream);

@@ -223,13 +223,61 @@ def test_sag_select_weight_sign_of_newer_pyg_checkpoints():
     _forward_case(ref, ours, make_batch(2, nx=9, ny=7), 1e-4)
 
 
-def test_sag_variants_are_eval_only_and_node_level_super_mask_fails_like_the_reference():
-    _, ours = _model_pair("GraphSAGE_SAG", "tf32", 4)
+def test_eagnn_sag_is_eval_only_and_node_level_super_mask_fails_like_the_reference():
+    """GraphSAGE_SAG trains (tests/test_gpu_train.py); EAGNN_SAG and the node-level heads of either fail loudly"""
+    torch.manual_seed(0)
+    ours = BuckGNN(16, 5, 512, 4, "mean", model_name="EAGNN_SAG").to(DEV)
     b = make_batch(2, nx=6, ny=5).to(DEV)
     ours.train()
     with pytest.raises(NotImplementedError):
         ours(b.x, b.edge_index, b.edge_attr, b.batch)
+    nl = BuckGNN(16, 5, 512, 4, "mean", prediction_type="static_disp", model_name="GraphSAGE_SAG").to(DEV).train()
+    with pytest.raises(NotImplementedError):
+        nl(b.x, b.edge_index, b.edge_attr, b.batch)
     torch.manual_seed(0)
     m = BuckGNN(16, 5, 512, 4, "supernode_only", prediction_type="static_stress", model_name="GraphSAGE_SAG").to(DEV).eval()
     with pytest.raises(IndexError):
         m(b.x, b.edge_index, b.edge_attr, b.batch)
+
+
+def test_sag_pool_backward_operator_matches_autograd():
+    """bg_sag_pool_backward + the scorer's weight gradients against torch autograd through the oracle's SAGPooling
+    (fp32 storage: agreement to fp32 rounding)."""
+    from buckgnn_b200 import train
+    b = make_batch(4, nx=11, ny=9)
+    n = b.num_nodes
+    pool = _pool_weights(7)
+    xr, idx, res = _operator_case(b, "tf32", pool)
+    n2 = res.n_nodes
+    perm = res.perm.long().cpu()
+    x = xr.clone().requires_grad_(True)
+    score = torch.tanh(pool.gnn(x, b.edge_index).view(-1))
+    xp = x[perm] * score[perm].view(-1, 1)
+    r = torch.randn(n2, 512, generator=torch.Generator().manual_seed(8))
+    (xp * r).sum().backward()
+    # device side
+    s = torch.cuda.current_stream().cuda_stream
+    ei = b.edge_index.to(DEV)
+    idx_t = build_graph_index(ei, None, n, key_row=0)
+    act = Activation(n, 512, "tf32", DEV)
+    act.data.copy_(xr.to(DEV))
+    dxp = Activation(n2, 512, "tf32", DEV)
+    dxp.data.copy_(r.to(DEV))
+    dx = Activation(n, 512, "tf32", DEV)
+    t, dpre = torch.empty(n, device=DEV), torch.empty(n, device=DEV)
+    w_l, w_r = pool.gnn.lin_l.weight.detach().reshape(-1).to(DEV), pool.gnn.lin_r.weight.detach().reshape(-1).to(DEV)
+    capi.sag_pool_backward(dxp.data.data_ptr(), act.data.data_ptr(), act.code, n, n2, res.perm.data_ptr(), res.new_id.data_ptr(),
+                           res.all_scores.data_ptr(), 1.0, idx_t.rowptr.data_ptr(), idx_t.col.data_ptr(),
+                           idx_t.big_rows.data_ptr(), idx_t.n_big, w_l.data_ptr(), w_r.data_ptr(), dx.data.data_ptr(),
+                           t.data_ptr(), dpre.data_ptr(), s)
+    dwl, dwr, db = torch.empty(1, 512, device=DEV), torch.empty(1, 512, device=DEV), torch.empty(1, device=DEV)
+    F32 = capi.BG_F32
+    train.sgemm(t, F32, 0, 1, act.data, act.code, 512, 1, 1, 512, n, dwl, F32, 512)
+    train.sgemm(dpre, F32, 0, 1, act.data, act.code, 512, 1, 1, 512, n, dwr, F32, 512)
+    train.colsum(dpre, F32, n, 1, 1, db)
+    torch.cuda.synchronize()
+    rel = lambda got, want: ((got.double().cpu() - want.double()).norm() / want.double().norm()).item()
+    assert rel(dx.data, x.grad) < 1e-5
+    assert rel(dwl, pool.gnn.lin_l.weight.grad) < 1e-5
+    assert rel(dwr, pool.gnn.lin_r.weight.grad) < 1e-5
+    assert rel(db, pool.gnn.lin_l.bias.grad) < 1e-5
