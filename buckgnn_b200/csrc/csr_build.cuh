@@ -19,7 +19,8 @@
 namespace bg {
 
 constexpr int kScanItemsPerBlock = 4096;   // 1024 threads x 4
-constexpr int kSortSmemElems = 32768;      // hub rows up to this degree sort in shared memory
+constexpr int kSortSmemElems = 57344;      // hub rows up to this degree sort in shared memory (224 KB of the 227 KB a CTA
+                                           // may have; the network skips partners beyond n, so n need not be a power of 2)
 
 // an edge with either endpoint outside [0, N) is dropped and flagged (info bit 0)
 BG_DEVINL bool edge_ok(int64_t k, int64_t o, int64_t N) { return k >= 0 && k < N && o >= 0 && o < N; }

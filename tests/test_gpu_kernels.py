@@ -34,7 +34,7 @@ def _random_multigraph(n, e, seed, hub=None):
 
 
 @pytest.mark.parametrize("key_row", [1, 0])
-@pytest.mark.parametrize("case", ["mesh", "random", "hub", "tiny", "empty_edges", "bighub"])
+@pytest.mark.parametrize("case", ["mesh", "random", "hub", "tiny", "empty_edges", "bighub", "hugehub"])
 def test_csr_build_bit_exact(case, key_row):
     if case == "mesh":
         b = make_batch(5, nx=17, ny=13); ei, n = b.edge_index, b.num_nodes
@@ -46,8 +46,10 @@ def test_csr_build_bit_exact(case, key_row):
         n = 3; ei = torch.tensor([[0, 1, 2, 2], [2, 2, 0, 1]])
     elif case == "empty_edges":
         n = 10; ei = torch.zeros((2, 0), dtype=torch.int64)
-    else:                                     # degree above the shared-memory sort capacity (32768)
+    elif case == "bighub":                    # ~50 k: not a power of two, just below the shared-memory sort capacity (57344)
         n = 200; ei = _random_multigraph(n, 150000, 3, hub=7)
+    else:                                     # ~67 k: above it -> the global-memory network
+        n = 200; ei = _random_multigraph(n, 200000, 4, hub=9)
     idx = build_graph_index(ei.to(DEV), None, n, key_row=key_row)
     rowptr, col, perm = _csr_reference(ei, n, key_row)
     e = ei.shape[1]
