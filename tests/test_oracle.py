@@ -278,3 +278,32 @@ def test_sag_variants_amplify_operand_rounding():
         return float(((a - r).abs() / a.abs().clamp(min=1e-3)).max())
     plain, sag = dev("GraphSage_addAggr"), dev("GraphSAGE_SAG")
     assert plain < 5e-4 < 1e-3 < sag, (plain, sag)
+
+
+def test_sag_topk_is_per_graph_and_order_independent_of_other_graphs():
+    """hypothesis-style property (seeded): the nodes a graph keeps depend on that graph's scores only, and relabelling
+    the graphs of a batch permutes the kept blocks"""
+    g = torch.Generator().manual_seed(11)
+    for trial in range(20):
+        sizes = torch.randint(1, 9, (4,), generator=g).tolist()
+        scores = [torch.randn(s, generator=g).round(decimals=1) for s in sizes]           # rounding creates ties
+        batch = torch.cat([torch.full((s,), i) for i, s in enumerate(sizes)])
+        perm = O.topk(torch.cat(scores), 0.5, batch)
+        off = 0
+        blocks = []
+        for i, s in enumerate(sizes):
+            alone = O.topk(scores[i], 0.5, torch.zeros(s, dtype=torch.long))
+            blocks.append(alone)
+            k = -(-s // 2)
+            mine = perm[(batch[perm] == i)]
+            assert mine.numel() == k and torch.equal(mine - off, alone)
+            assert bool((scores[i][alone][:-1] >= scores[i][alone][1:]).all())             # descending
+            off += s
+        order = torch.randperm(4, generator=g).tolist()
+        batch2 = torch.cat([torch.full((sizes[o],), i) for i, o in enumerate(order)])
+        perm2 = O.topk(torch.cat([scores[o] for o in order]), 0.5, batch2)
+        off2 = 0
+        for i, o in enumerate(order):
+            mine = perm2[(batch2[perm2] == i)]
+            assert torch.equal(mine - off2, blocks[o])
+            off2 += sizes[o]
