@@ -20,7 +20,7 @@ BG_BF16, BG_F32, BG_F16 = 0, 1, 2
 BG_AGGR_MEAN, BG_AGGR_SUM, BG_AGGR_MAX = 0, 1, 2
 BG_BIG_ROW_THRESHOLD = 64
 BG_MAX_GEMM_SEGMENTS = 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 AGGR_CODES = {"mean": BG_AGGR_MEAN, "sum": BG_AGGR_SUM, "add": BG_AGGR_SUM, "max": BG_AGGR_MAX}
 
@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "bg_sgemm_workspace_bytes", "bg_sgemm", "bg_eigen_loss", "bg_dropout_mask", "bg_collate_ptr", "bg_collate",
     "bg_dropout_residual", "bg_grad_mask", "bg_segment_expand",
     "bg_sag_workspace_bytes", "bg_sag_select", "bg_sag_connect", "bg_gather_rows", "bg_index_invert", "bg_index_gather",
-    "bg_sag_pool_backward",
+    "bg_sag_pool_backward", "bg_max_aggregate_backward",
 )
 
 
@@ -118,6 +118,7 @@ _SIGNATURES = {
     "bg_gather_rows": (C.c_int, [_P, C.c_int, _I64, _P, _P, _I64, _P, _I64, _P]),
     "bg_index_invert": (C.c_int, [_P, _I64, _P, _P]),
     "bg_index_gather": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "bg_max_aggregate_backward": (C.c_int, [_P, _P, _P, C.c_int, _I64, _P, _P, _P, _I32, _P, _P, _P, _I32, _P, _P, _P]),
     "bg_sag_pool_backward": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, C.c_float, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
 }
 
@@ -393,3 +394,10 @@ def sag_pool_backward(dx_pooled, x, dtype, n_nodes, n_nodes_out, perm, new_id, s
     _check(load().bg_sag_pool_backward(dx_pooled, x, dtype, n_nodes, n_nodes_out, perm, new_id, score, sign, rowptr_src,
                                        col_src, big_rows_src, n_big_src, w_l, w_r, dx, t, dpre, stream),
            "bg_sag_pool_backward")
+
+
+def max_aggregate_backward(x, agg, dagg, dtype, n_nodes, rowptr_tgt, col_tgt, big_tgt, n_big_tgt, rowptr_src, col_src,
+                           big_src, n_big_src, w_scratch, dx, stream):
+    _check(load().bg_max_aggregate_backward(x, agg, dagg, dtype, n_nodes, rowptr_tgt, col_tgt, big_tgt, n_big_tgt,
+                                            rowptr_src, col_src, big_src, n_big_src, w_scratch, dx, stream),
+           "bg_max_aggregate_backward")

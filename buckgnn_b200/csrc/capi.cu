@@ -11,6 +11,7 @@
 #include "pool_head.cuh"
 #include "train.cuh"
 #include "sag_pool.cuh"
+#include "max_bwd.cuh"
 
 namespace bg {
 
@@ -200,6 +201,23 @@ static void pool_launch(const T* x, const int32_t* graph_ptr, int64_t G, int mod
 }  // namespace bg
 
 using namespace bg;
+
+template <typename T>
+static void launch_max_bwd(const void* x, const void* agg, const void* dagg, int64_t N, const int32_t* rowptr_tgt,
+                           const int32_t* col_tgt, const int32_t* big_tgt, int32_t n_big_tgt, const int32_t* rowptr_src,
+                           const int32_t* col_src, const int32_t* big_src, int32_t n_big_src, void* w_scratch, void* dx,
+                           unsigned grid, cudaStream_t stream) {
+  const T* xp = static_cast<const T*>(x); const T* ap = static_cast<const T*>(agg); const T* dp = static_cast<const T*>(dagg);
+  T* wp = static_cast<T*>(w_scratch); T* op = static_cast<T*>(dx);
+  // pass 1 (by target): w_i = dagg_i / n_i
+  k_max_bwd_rows<T, 0><<<grid, kMaxBwdWarps * 32, 0, stream>>>(ap, xp, nullptr, dp, rowptr_tgt, col_tgt, N, wp);
+  if (n_big_tgt > 0)
+    k_max_bwd_big<T, 0><<<(unsigned)n_big_tgt, kMaxBwdWarps * 32, 0, stream>>>(ap, xp, nullptr, dp, rowptr_tgt, col_tgt, big_tgt, wp);
+  // pass 2 (by source): dx_j = sum_i [agg_i == x_j] w_i
+  k_max_bwd_rows<T, 1><<<grid, kMaxBwdWarps * 32, 0, stream>>>(xp, ap, wp, nullptr, rowptr_src, col_src, N, op);
+  if (n_big_src > 0)
+    k_max_bwd_big<T, 1><<<(unsigned)n_big_src, kMaxBwdWarps * 32, 0, stream>>>(xp, ap, wp, nullptr, rowptr_src, col_src, big_src, op);
+}
 
 extern "C" {
 
@@ -705,6 +723,23 @@ int bg_sag_pool_backward(const void* dx_pooled, const void* x, int dtype, int64_
   const unsigned grid = grid_for(N * 32, kSagWarps * 32, sms * 8);
   BG_BY_DTYPE(dtype, (k_sag_bwd_dx<T><<<grid, kSagWarps * 32, 0, stream>>>(static_cast<const T*>(dx_pooled), new_id, score, t, dpre, w_l, w_r,
                                                                          N, static_cast<T*>(dx))));
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_max_aggregate_backward(const void* x, const void* agg, const void* dagg, int dtype, int64_t N,
+                              const int32_t* rowptr_tgt, const int32_t* col_tgt, const int32_t* big_tgt, int32_t n_big_tgt,
+                              const int32_t* rowptr_src, const int32_t* col_src, const int32_t* big_src, int32_t n_big_src,
+                              void* w_scratch, void* dx, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N < 0 || n_big_tgt < 0 || n_big_src < 0) return fail(BG_ERR_INVALID, "bg_max_aggregate_backward: bad size");
+  if (N == 0) return BG_OK;
+  if (!x || !agg || !dagg || !rowptr_tgt || !rowptr_src || !w_scratch || !dx || !aligned16(x) || !aligned16(agg) ||
+      !aligned16(dagg) || !aligned16(w_scratch) || !aligned16(dx) || (n_big_tgt > 0 && !big_tgt) || (n_big_src > 0 && !big_src))
+    return fail(BG_ERR_INVALID, "bg_max_aggregate_backward: null or misaligned pointer");
+  const unsigned grid = grid_for(N * 32, kMaxBwdWarps * 32, sm_count() * 8);
+  BG_BY_DTYPE(dtype, (launch_max_bwd<T>(x, agg, dagg, N, rowptr_tgt, col_tgt, big_tgt, n_big_tgt, rowptr_src, col_src, big_src,
+                                        n_big_src, w_scratch, dx, grid, stream)));
   BG_LAUNCH_OK();
   return BG_OK;
 }

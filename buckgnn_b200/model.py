@@ -275,8 +275,6 @@ class BuckGNN(nn.Module):
                                                                                "EA_GNN_Shared", "GraphSAGE_SAG"):
                 raise NotImplementedError(f"buckgnn_b200: the training step is built for the GraphSAGE and EA-GNN "
                                           f"variants; model_name={self.model_name!r} runs in eval mode only")
-            if self.model_name == "GraphSage_maxAggr":
-                raise NotImplementedError("buckgnn_b200: training with max aggregation is not built")
         if self.hidden_channels != 512:
             raise NotImplementedError("buckgnn_b200: the tcgen05 path is built for hidden_channels=512")
         if self.model_name in ("GraphSage_MLP", "GraphSage_addAggr_woBatchNorm", "GraphSage_sumAggr_woBatchNorm"):

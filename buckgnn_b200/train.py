@@ -343,8 +343,6 @@ class SageTrainFunction(torch.autograd.Function):
         convs = model._sage_layers()
         L = len(convs)
         aggr = convs[0][0].aggr
-        if aggr == "max":
-            raise NotImplementedError("buckgnn_b200: training with max aggregation is not built")
         p_drop = float(model.dropout.p)
         pending = engine.begin_graph_index(edge_index, batch, n)
         # one read-back for all epilogue bias vectors of the step (they travel as kernel parameters)
@@ -468,7 +466,16 @@ class SageTrainFunction(torch.autograd.Function):
             with engine.TIMERS.span("train_dgrad_gemm"):
                 engine.gemm512(engine._segments(dzs, wlt), n, prec, dagg)
             sbuf = Activation(n, 512, prec, dev)
-            engine.aggregate(dagg, sbuf, idx_t, "sum")
+            if sv.aggr == "max":                     # the gradient goes to the neighbours that attain the maximum
+                wtmp = Activation(n, 512, prec, dev)
+                with engine.TIMERS.span("train_max_bwd"):
+                    capi.max_aggregate_backward(x_in.data.data_ptr(), agg.data.data_ptr(), dagg.data.data_ptr(), code, n,
+                                                idx.rowptr.data_ptr(), idx.col.data_ptr(), idx.big_rows.data_ptr(), idx.n_big,
+                                                idx_t.rowptr.data_ptr(), idx_t.col.data_ptr(), idx_t.big_rows.data_ptr(),
+                                                idx_t.n_big, wtmp.data.data_ptr(), sbuf.data.data_ptr(), s)
+                sbuf.refresh_split()
+            else:
+                engine.aggregate(dagg, sbuf, idx_t, "sum")
             dx = Activation(n, 512, prec, dev)
             with engine.TIMERS.span("train_dgrad_gemm"):
                 engine.gemm512(engine._segments(dz, wrt), n, prec, dx, residual=sbuf.data.data_ptr(), ldr=512)

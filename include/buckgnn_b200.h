@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 6
+#define BG_ABI_VERSION 7
 
 typedef enum bg_status {
   BG_OK = 0,
@@ -350,6 +350,19 @@ int bg_dropout_residual(const void* x, const void* x_prev, void* y, int dtype, i
 int bg_grad_mask(const void* dy, const void* dy2, const void* act, void* out, int dtype, int64_t n_rows, float dropout_p,
                  uint64_t seed, void* stream);
 int bg_segment_expand(const void* src, const int32_t* rowptr, int64_t n_rows, int mean, void* out, int dtype, void* stream);
+
+/* Backward of the 'max' neighbourhood aggregation (autograd of SAGEConv(aggr='max'), Models/BuckGNN.py:171-176, 459-471):
+ * forward agg_i[c] = max_{j -> i} x_j[c] (0 without in-edges).  The gradient is the one autograd gives the reference
+ * when PyG reduces with torch's scatter_reduce_('amax', include_self=False) on a zero-initialised output: dagg_i[c] is
+ * shared evenly by the neighbours attaining the maximum, the zero-initialised element counting as one more sharer
+ * when the maximum is 0:   n_i[c] = [agg_i[c] == 0] + #{j -> i: x_j[c] == agg_i[c]},
+ *                          dx_j[c] = sum_{i: j -> i} [x_j[c] == agg_i[c]] dagg_i[c] / n_i[c].
+ * x, agg, dagg, w_scratch, dx: [N, 512] of `dtype`; CSR keyed by target (bg_csr_build key_row = 1) and by source
+ * (key_row = 0), each with its big-row list.  No atomics: two gather passes. */
+int bg_max_aggregate_backward(const void* x, const void* agg, const void* dagg, int dtype, int64_t n_nodes,
+                              const int32_t* rowptr_tgt, const int32_t* col_tgt, const int32_t* big_rows_tgt, int32_t n_big_tgt,
+                              const int32_t* rowptr_src, const int32_t* col_src, const int32_t* big_rows_src, int32_t n_big_src,
+                              void* w_scratch, void* dx, void* stream);
 
 /* Device-side collate: PyG `DataLoader` / `Batch.from_data_list` for a dataset kept in HBM in
  * concatenated form -- x_all [sum n, F], ei_all [2, E_all] with node ids LOCAL to their graph (as

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(capi.library_path())
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.bg_abi_version() == capi.ABI_VERSION == 6
+    assert lib.bg_abi_version() == capi.ABI_VERSION == 7
 
 
 def test_size_queries_and_argument_errors_without_gpu(lib):
@@ -83,6 +83,8 @@ def test_training_and_collate_entry_points_validate_arguments_without_gpu(lib):
         lambda: capi.gather_rows(None, capi.BG_F16, 512, 16, None, 4, 16, 512, None),
         lambda: capi.index_invert(None, 4, None, None),
         lambda: capi.index_gather(None, None, 4, None, None),
+        lambda: capi.max_aggregate_backward(None, 16, 16, capi.BG_F32, 10, 16, 16, None, 0, 16, 16, None, 0, 16, 16, None),
+        lambda: capi.max_aggregate_backward(16, 16, 16, capi.BG_F32, 10, 16, 16, None, 3, 16, 16, None, 0, 16, 16, None),   # big rows missing
         lambda: capi.sag_pool_backward(16, 16, capi.BG_F32, 10, 11, 16, 16, 16, 1.0, 16, 16, None, 0, 16, 16, 16, 16, 16, None),   # N' > N
         lambda: capi.sag_pool_backward(None, None, capi.BG_F32, 10, 5, 16, 16, 16, 1.0, 16, 16, None, 0, 16, 16, 16, 16, 16, None),
     ]

@@ -250,17 +250,38 @@ def _train_pair(model_name, precision, layers, p, pooling="mean"):
     return ref.train(), ours.to(DEV).train()
 
 
+class _RoutedMax(torch.autograd.Function):
+    """max aggregation whose BACKWARD routes the gradient to the neighbours that attain the maximum in OUR forward
+    (mask [E, 512], share [N, 512] = 1 / number of sharers).  Like the ReLU masks: which neighbour wins a near-tie is
+    a discontinuous function of rounded activations (measured: 1-4 % of the gradient norm in tf32, ~10 % in bf16 with
+    independent winners), while the routing rule itself is checked exactly by
+    test_max_aggregation_backward_matches_autograd."""
+
+    @staticmethod
+    def forward(ctx, src, index, dim_size, mask, share):
+        ctx.save_for_backward(index, mask, share)
+        out = torch.zeros((dim_size, src.shape[1]), dtype=src.dtype)
+        return out.scatter_reduce_(0, index.view(-1, 1).expand_as(src), src, reduce="amax", include_self=False)
+
+    @staticmethod
+    def backward(ctx, grad):
+        index, mask, share = ctx.saved_tensors
+        return mask * (grad * share)[index], None, None, None, None
+
+
 @pytest.mark.parametrize("model_name,precision,layers,p,pooling", [
     ("GraphSage_meanAggr", "tf32", 6, 0.0, "mean"),
     ("GraphSage_meanAggr", "tf32", 4, 0.1, "mean"),
     ("GraphSage_meanAggr", "bf16", 4, 0.0, "mean"),
     ("GraphSage_sumAggr", "tf32", 3, 0.0, "mean_no_super"),
+    ("GraphSage_maxAggr", "tf32", 3, 0.0, "mean"),
+    ("GraphSage_maxAggr", "bf16", 3, 0.1, "mean"),
     ("GraphSage_addAggr_Shared", "tf32", 4, 0.0, "supernode_only"),
     ("GraphSage_meanAggr", "tf32", 3, 0.0, "mlp"),
     ("GraphSage_meanAggr", "tf32", 3, 0.0, "mlp_no_super"),
     ("GraphSage_meanAggr", "tf32", 3, 0.1, "supernode_with_pooling"),
 ])
-def test_training_step_gradients_match_oracle(model_name, precision, layers, p, pooling):
+def test_training_step_gradients_match_oracle(model_name, precision, layers, p, pooling, monkeypatch):
     ref, ours = _train_pair(model_name, precision, layers, p, pooling)
     b = make_batch(5, nx=14, ny=11)
     n = b.num_nodes
@@ -288,6 +309,17 @@ def test_training_step_gradients_match_oracle(model_name, precision, layers, p, 
     # the small heads too: with 5 graphs x 128 hidden units a single flipped decoder unit is ~1 % of every gradient
     head_masks = [(saved.h1d > 0).float().cpu(), (saved.h2d > 0).float().cpu()]
     mlp_mask = (saved.dec_in > 0).float().cpu() if saved.mlp is not None else None
+    if model_name == "GraphSage_maxAggr":                   # the winners of our forward, layer by layer
+        import oracle.buckgnn_oracle as O
+        src_i, dst_i = b.edge_index[0], b.edge_index[1]
+        routes = []
+        for (_, _, x_in, agg, _, _, _, _) in saved.layers:
+            xi, ag = x_in.data.float().cpu(), agg.data.float().cpu()
+            mask = (xi[src_i] == ag[dst_i]).float()
+            sharers = (ag == 0).float().index_add_(0, dst_i, mask)
+            routes.append((mask, 1.0 / sharers.clamp(min=1.0)))
+        it = iter(routes)
+        monkeypatch.setattr(O, "scatter_max", lambda src, index, dim_size: _RoutedMax.apply(src, index, dim_size, *next(it)))
     loss.backward()
     ref.relu = _MaskedReLU(relu_masks)
     ref.decoder[1], ref.decoder[3] = _MaskedReLU(head_masks[:1]), _MaskedReLU(head_masks[1:])
@@ -619,3 +651,35 @@ def test_graphsage_sag_training_step_gradients_match_oracle(layers, p, monkeypat
     assert pred.shape == (4,) and pb.shape[0] == n2
     F.mse_loss(pred, y.to(DEV)).backward()
     opt.step()
+
+
+# ----------------------------------------------------------------------------- max aggregation
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+def test_max_aggregation_backward_matches_autograd(precision):
+    """bg_max_aggregate_backward against torch autograd of the oracle's max aggregation (scatter_reduce amax): ties --
+    frequent after a ReLU -- share the gradient, a maximum of 0 also shares it with the zero-initialised output."""
+    from oracle.buckgnn_oracle import aggregate as oracle_aggregate
+    b = make_batch(3, nx=10, ny=7)
+    n = b.num_nodes
+    g = torch.Generator().manual_seed(9)
+    x0 = torch.relu(torch.randn(n, 512, generator=g)).round(decimals=1)          # many exact ties and zeros
+    act = _act(x0.to(DEV), precision)
+    x = act.data.float().cpu().requires_grad_(True)
+    agg_ref = oracle_aggregate(x, b.edge_index, "max")
+    d0 = torch.randn(n, 512, generator=g)
+    dact = _act(d0.to(DEV), precision)
+    agg_ref.backward(dact.data.float().cpu())
+    ei = b.edge_index.to(DEV)
+    idx = build_graph_index(ei, None, n)
+    idx_t = build_graph_index(ei, None, n, key_row=0)
+    agg = Activation(n, 512, precision, DEV)
+    engine.aggregate(act, agg, idx, "max")
+    assert torch.equal(agg.data.float().cpu(), agg_ref.detach())
+    w, dx = Activation(n, 512, precision, DEV), Activation(n, 512, precision, DEV)
+    capi.max_aggregate_backward(act.data.data_ptr(), agg.data.data_ptr(), dact.data.data_ptr(), act.code, n,
+                                idx.rowptr.data_ptr(), idx.col.data_ptr(), idx.big_rows.data_ptr(), idx.n_big,
+                                idx_t.rowptr.data_ptr(), idx_t.col.data_ptr(), idx_t.big_rows.data_ptr(), idx_t.n_big,
+                                w.data.data_ptr(), dx.data.data_ptr(), _stream())
+    tol = dict(rtol=1e-5, atol=1e-5) if precision == "tf32" else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(dx.data.float().cpu(), x.grad, **tol)
+    assert idx.n_big == 3 and idx_t.n_big == 3                                        # the hub rows went through the CTA path
