@@ -371,7 +371,7 @@ k_sag_edge_write(const int64_t* __restrict__ ei, int64_t E, int64_t N, const int
   }
 }
 
-// out[r, :] = x[idx[r], :] * scale[idx[r]]   (warp per row; scale nullable)
+// out[r, :] = x[idx[r], :] * scale[idx[r]]   (warp per row; scale nullable; idx[r] < 0 gives a zero row)
 template <typename T>
 __global__ void __launch_bounds__(kSagWarps * 32)
 k_gather_rows(const T* __restrict__ x, int64_t ldx, const int32_t* __restrict__ idx, const float* __restrict__ scale,
@@ -381,11 +381,16 @@ k_gather_rows(const T* __restrict__ x, int64_t ldx, const int32_t* __restrict__ 
   for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_out; r += n_warps) {
     const int32_t src = idx[r];
     float v[16];
-    row_values(x + (size_t)src * ldx, lane, v);
-    if (scale) {
-      const float s = scale[src];
+    if (src < 0) {                                   // no source row: zeros (the gradient of a dropped edge)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] *= s;
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    } else {
+      row_values(x + (size_t)src * ldx, lane, v);
+      if (scale) {
+        const float s = scale[src];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= s;
+      }
     }
     RowFrag<T>::store(out + (size_t)r * ldo, lane, v);
   }

@@ -665,22 +665,29 @@ def sag_pool(x: Activation, csr_by_target: GraphIndex, graph_ptr: torch.Tensor, 
                          score[:n])
 
 
-def regather_edge_rows(e: Activation, idx_old: GraphIndex, idx_new: GraphIndex, kept_edge: torch.Tensor) -> Activation:
-    """Edge features of the kept edges, moved from the old CSR slot order to the new one (EAGNN_SAG:
-    `edge_attr[mask]` of PyG filter_adj, for edge tensors that live in CSR order)."""
-    dev = e.data.device
+def edge_slot_map(idx_old: GraphIndex, idx_new: GraphIndex, kept_edge: torch.Tensor) -> torch.Tensor:
+    """[E'] int32: for every CSR slot of the pooled graph, the CSR slot of the same edge in the un-pooled graph."""
+    dev = idx_old.rowptr.device
     s = _stream()
     e_old, e_new = idx_old.n_edges, idx_new.n_edges
     i32 = dict(dtype=torch.int32, device=dev)
-    out = Activation(max(e_new, 1), 512, e.precision, dev)
+    inv = torch.empty(max(e_old, 1), **i32)
+    capi.index_invert(idx_old.perm.data_ptr(), e_old, inv.data_ptr(), s)            # old edge id -> old slot
+    orig = torch.empty(max(e_new, 1), **i32)
+    capi.index_gather(kept_edge.data_ptr(), idx_new.perm.data_ptr(), e_new, orig.data_ptr(), s)   # new slot -> old edge id
+    slot = torch.empty(max(e_new, 1), **i32)
+    capi.index_gather(inv.data_ptr(), orig.data_ptr(), e_new, slot.data_ptr(), s)   # new slot -> old slot
+    return slot
+
+
+def regather_edge_rows(e: Activation, idx_old: GraphIndex, idx_new: GraphIndex, kept_edge: torch.Tensor) -> Activation:
+    """Edge features of the kept edges, moved from the old CSR slot order to the new one (EAGNN_SAG:
+    `edge_attr[mask]` of PyG filter_adj, for edge tensors that live in CSR order)."""
+    e_new = idx_new.n_edges
+    out = Activation(max(e_new, 1), 512, e.precision, e.data.device)
     if e_new == 0:
         return out
-    inv = torch.empty(e_old, **i32)
-    capi.index_invert(idx_old.perm.data_ptr(), e_old, inv.data_ptr(), s)            # old edge id -> old slot
-    orig = torch.empty(e_new, **i32)
-    capi.index_gather(kept_edge.data_ptr(), idx_new.perm.data_ptr(), e_new, orig.data_ptr(), s)   # new slot -> old edge id
-    slot = torch.empty(e_new, **i32)
-    capi.index_gather(inv.data_ptr(), orig.data_ptr(), e_new, slot.data_ptr(), s)   # new slot -> old slot
-    capi.gather_rows(e.data.data_ptr(), e.code, e.data.shape[1], slot.data_ptr(), None, e_new, out.data.data_ptr(), 512, s)
+    slot = edge_slot_map(idx_old, idx_new, kept_edge)
+    capi.gather_rows(e.data.data_ptr(), e.code, e.data.shape[1], slot.data_ptr(), None, e_new, out.data.data_ptr(), 512, _stream())
     out.refresh_split()
     return out

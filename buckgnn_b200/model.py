@@ -272,7 +272,7 @@ class BuckGNN(nn.Module):
             raise RuntimeError("buckgnn_b200.BuckGNN runs on CUDA (sm_100a) tensors only; there is no CPU path")
         if self.training:
             if self.model_name not in _SAGE_LISTS and self.model_name not in ("GraphSage_addAggr_Shared", "EA_GNN",
-                                                                               "EA_GNN_Shared", "GraphSAGE_SAG"):
+                                                                               "EA_GNN_Shared", "GraphSAGE_SAG", "EAGNN_SAG"):
                 raise NotImplementedError(f"buckgnn_b200: the training step is built for the GraphSAGE and EA-GNN "
                                           f"variants; model_name={self.model_name!r} runs in eval mode only")
         if self.hidden_channels != 512:
@@ -297,7 +297,7 @@ class BuckGNN(nn.Module):
         if self.training:       # train-mode BatchNorm / Dropout + autograd through the backward kernels (train.py)
             from . import train
             pred = train.forward_train(self, x, edge_index, batch, edge_attr=edge_attr)
-            if self.model_name == "GraphSAGE_SAG":           # `batch` was reassigned by self.pool (:502)
+            if self.model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):   # `batch` was reassigned by self.pool (:365, :502)
                 return pred.squeeze(), self.last_pool.batch
             if node_level:                                   # reference :518-524; the row selection is an autograd index
                 if "super" in self.pooling_layer:

@@ -659,9 +659,12 @@ def trainable_parameters(model) -> List[torch.nn.Parameter]:
                 add(m.weight); add(m.bias)
 
     add_seq(model.node_encoder)
-    if model.model_name in ("EA_GNN", "EA_GNN_Shared"):
+    if model.model_name in ("EA_GNN", "EA_GNN_Shared", "EAGNN_SAG"):
         add_seq(model.edge_encoder)
-        blocks = [model.shared_gn_block] if model.model_name == "EA_GNN_Shared" else list(model.gn_blocks)
+        if model.model_name == "EAGNN_SAG":
+            blocks = list(model.gnn_layers_1) + list(model.gnn_layers_2)
+        else:
+            blocks = [model.shared_gn_block] if model.model_name == "EA_GNN_Shared" else list(model.gn_blocks)
         for blk in blocks:
             for seq in (blk.edge_mlp, blk.node_mlp_phi, blk.node_mlp_gamma, blk.node_mlp_beta):
                 add_seq(seq)
@@ -669,7 +672,7 @@ def trainable_parameters(model) -> List[torch.nn.Parameter]:
         add(conv.lin_l.weight); add(conv.lin_l.bias); add(conv.lin_r.weight)
         if bn is not None:
             add(bn.weight); add(bn.bias)
-    if model.model_name == "GraphSAGE_SAG":
+    if model.model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):
         gnn = model.pool.gnn
         add(gnn.lin_l.weight); add(gnn.lin_l.bias); add(gnn.lin_r.weight)
     if model.pooling_layer in ("mlp", "mlp_no_super") and not is_node_level(model):
@@ -685,10 +688,13 @@ def forward_train(model, x, edge_index, batch, seed: Optional[int] = None, edge_
     if model.model_name in ("EA_GNN", "EA_GNN_Shared"):
         from .train_eagnn import EAGNNTrainFunction
         return EAGNNTrainFunction.apply(model, x, edge_index, edge_attr, batch, seed, *params)
-    if model.model_name == "GraphSAGE_SAG":
+    if model.model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):
         if is_node_level(model):
-            raise NotImplementedError("buckgnn_b200: GraphSAGE_SAG trains with the eigenvalue head only")
+            raise NotImplementedError("buckgnn_b200: the SAGPooling variants train with the eigenvalue head only")
         if batch is None:
             batch = torch.zeros(x.shape[0], dtype=torch.int64, device=x.device)
+        if model.model_name == "EAGNN_SAG":
+            from .train_eagnn import EAGNNSagTrainFunction
+            return EAGNNSagTrainFunction.apply(model, x, edge_index, edge_attr, batch, seed, *params)
         return SagTrainFunction.apply(model, x, edge_index, batch, seed, *params)
     return SageTrainFunction.apply(model, x, edge_index, batch, seed, *params)

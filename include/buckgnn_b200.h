@@ -247,7 +247,8 @@ int bg_add(const void* a, const void* b, const void* c_or_null, void* out, int d
  * bg_sag_connect: edge_index_out [2, E'] int64, kept_edge [E'] int32 (nullable) = original edge id of each kept
  *   edge.  `workspace` must be the buffer bg_sag_select used, untouched in between (it holds the block offsets).
  * bg_gather_rows: out[r, 0:512] = x[row_index[r], 0:512] * (row_scale ? row_scale[row_index[r]] : 1)  --
- *   x[perm] * score[perm], and the edge-feature rows of the kept edges for EAGNN_SAG.
+ *   x[perm] * score[perm], and the edge-feature rows of the kept edges for EAGNN_SAG.  A negative row_index[r] gives
+ *   a zero row (the training step scatters edge gradients back this way: dropped edges receive none).
  * bg_index_invert: out[perm[i]] = i;  bg_index_gather: out[i] = table[idx[i]]   (int32 index plumbing). */
 int bg_sag_workspace_bytes(int64_t n_nodes, int64_t n_edges, int64_t n_graphs, size_t* bytes_host);
 int bg_sag_select(const void* x, int dtype, int64_t n_nodes, const int32_t* rowptr, const int32_t* col,

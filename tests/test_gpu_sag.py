@@ -223,14 +223,9 @@ def test_sag_select_weight_sign_of_newer_pyg_checkpoints():
     _forward_case(ref, ours, make_batch(2, nx=9, ny=7), 1e-4)
 
 
-def test_eagnn_sag_is_eval_only_and_node_level_super_mask_fails_like_the_reference():
-    """GraphSAGE_SAG trains (tests/test_gpu_train.py); EAGNN_SAG and the node-level heads of either fail loudly"""
-    torch.manual_seed(0)
-    ours = BuckGNN(16, 5, 512, 4, "mean", model_name="EAGNN_SAG").to(DEV)
+def test_sag_node_level_training_and_super_mask_fail_loudly():
+    """both SAGPooling variants train with the eigenvalue head (tests/test_gpu_train.py); node-level heads do not"""
     b = make_batch(2, nx=6, ny=5).to(DEV)
-    ours.train()
-    with pytest.raises(NotImplementedError):
-        ours(b.x, b.edge_index, b.edge_attr, b.batch)
     nl = BuckGNN(16, 5, 512, 4, "mean", prediction_type="static_disp", model_name="GraphSAGE_SAG").to(DEV).train()
     with pytest.raises(NotImplementedError):
         nl(b.x, b.edge_index, b.edge_attr, b.batch)

@@ -683,3 +683,69 @@ def test_max_aggregation_backward_matches_autograd(precision):
     tol = dict(rtol=1e-5, atol=1e-5) if precision == "tf32" else dict(rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(dx.data.float().cpu(), x.grad, **tol)
     assert idx.n_big == 3 and idx_t.n_big == 3                                        # the hub rows went through the CTA path
+
+
+# ----------------------------------------------------------------------------- EAGNN_SAG
+@pytest.mark.parametrize("layers,p", [(4, 0.0), (3, 0.1)])
+def test_eagnn_sag_training_step_gradients_match_oracle(layers, p, monkeypatch):
+    """loss.backward() through GraphNetBlocks -> SAGPooling (node rows scaled by the tanh score, edge rows of the kept
+    edges) -> GraphNetBlocks on the pooled graph (Models/BuckGNN.py:354-373), against autograd through the oracle with
+    our node selection, ReLU masks and dropout masks."""
+    import oracle.buckgnn_oracle as O
+    ref, ours = _train_pair("EAGNN_SAG", "tf32", layers, p)
+    b = make_batch(3, nx=9, ny=8, stiffened=True)
+    n, ne = b.num_nodes, b.num_edges
+    seed = 777
+    bd = b.to(DEV)
+    got_raw = train.forward_train(ours, bd.x, bd.edge_index, bd.batch, seed=seed, edge_attr=bd.edge_attr)
+    got = got_raw.squeeze()
+    saved = got_raw.grad_fn.sv
+    pooled = saved.pooled
+    n2, ne2 = pooled.n_nodes, saved.st2.ne
+    perm = pooled.perm.long().cpu()
+
+    def inverse(p_):
+        inv = torch.empty_like(p_)
+        inv[p_] = torch.arange(p_.numel())
+        return inv
+    inv1 = inverse(saved.st1.idx.perm[:ne].long().cpu())       # edge id -> our CSR slot, un-pooled graph
+    inv2 = inverse(saved.st2.idx.perm[:ne2].long().cpu())      # pooled edge id -> our CSR slot, pooled graph
+    on = lambda act, inv: (act.data.float() > 0).float().cpu() if inv is None else (act.data.float() > 0).float().cpu()[inv]
+    for blocks, layers_saved, inv in ((ref.gnn_layers_1, saved.first, inv1), (ref.gnn_layers_2, saved.second, inv2)):
+        for blk, (_, _, _, he, _, hm, _, g1, _, t, _) in zip(blocks, layers_saved):
+            blk.edge_mlp[1] = _MaskedReLU([on(he, inv)]); blk.node_mlp_phi[1] = _MaskedReLU([on(hm, inv)])
+            blk.node_mlp_gamma[1] = _MaskedReLU([on(g1, None)]); blk.node_mlp_beta[1] = _MaskedReLU([on(t, None)])
+    ref.decoder[1], ref.decoder[3] = _MaskedReLU([(saved.h1d > 0).float().cpu()]), _MaskedReLU([(saved.h2d > 0).float().cpu()])
+    y = torch.randn(3, generator=torch.Generator().manual_seed(5))
+    F.mse_loss(got, y.to(DEV)).backward()
+    if p > 0:
+        n_before = layers // 2
+        dm = []
+        for i in range(layers):
+            rows_x, rows_e, inv = (n, ne, inv1) if i < n_before else (n2, ne2, inv2)
+            kx = torch.empty(rows_x, 512, dtype=torch.uint8, device=DEV)
+            ke = torch.empty(rows_e, 512, dtype=torch.uint8, device=DEV)
+            capi.dropout_mask(train.layer_seed(seed, 2 * i), p, rows_x, kx.data_ptr(), _stream())
+            capi.dropout_mask(train.layer_seed(seed, 2 * i + 1), p, rows_e, ke.data_ptr(), _stream())
+            dm += [kx.cpu().float(), ke.cpu().float()[inv]]
+        ref.dropout = _MaskedDropout(dm, p)
+    monkeypatch.setattr(O, "topk", lambda score, ratio, batch: perm)
+    want, want_batch = ref(b.x, b.edge_index, b.edge_attr, b.batch)
+    F.mse_loss(want, y).backward()
+    assert torch.equal(pooled.batch.cpu(), want_batch)
+    assert _rel(got.detach().cpu(), want.detach()) < 3e-3
+    ref_p, our_p = dict(ref.named_parameters()), dict(ours.named_parameters())
+    checked, bad, seen = 0, [], set()
+    for name, rp in ref_p.items():
+        op = our_p[name]
+        if rp.grad is None:
+            assert op.grad is None, name
+            continue
+        assert op.grad is not None, name
+        err = _rel(op.grad.cpu(), rp.grad)
+        seen.add(name)
+        if rp.grad.norm().item() > 1e-12 and not err < 2e-2:
+            bad.append(f"{name}: rel err {err:.3e} >= 2e-2")
+        checked += 1
+    assert not bad, "\n".join(bad)
+    assert checked >= 40 and {"pool.gnn.lin_l.weight", "pool.gnn.lin_r.weight", "edge_encoder.0.weight"} <= seen
