@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "bg_sgemm_workspace_bytes", "bg_sgemm", "bg_eigen_loss", "bg_dropout_mask", "bg_collate_ptr", "bg_collate",
     "bg_dropout_residual", "bg_grad_mask", "bg_segment_expand",
     "bg_sag_workspace_bytes", "bg_sag_select", "bg_sag_connect", "bg_gather_rows", "bg_index_invert", "bg_index_gather",
-    "bg_sag_pool_backward", "bg_max_aggregate_backward",
+    "bg_sag_pool_backward", "bg_max_aggregate_backward", "bg_max_bwd_workspace_bytes",
 )
 
 
@@ -118,7 +118,8 @@ _SIGNATURES = {
     "bg_gather_rows": (C.c_int, [_P, C.c_int, _I64, _P, _P, _I64, _P, _I64, _P]),
     "bg_index_invert": (C.c_int, [_P, _I64, _P, _P]),
     "bg_index_gather": (C.c_int, [_P, _P, _I64, _P, _P]),
-    "bg_max_aggregate_backward": (C.c_int, [_P, _P, _P, C.c_int, _I64, _P, _P, _P, _I32, _P, _P, _P, _I32, _P, _P, _P]),
+    "bg_max_bwd_workspace_bytes": (C.c_int, [_I32, _I32, _SZP]),
+    "bg_max_aggregate_backward": (C.c_int, [_P, _P, _P, C.c_int, _I64, _P, _P, _P, _I32, _P, _P, _P, _I32, _P, _P, _P, C.c_size_t, _P]),
     "bg_sag_pool_backward": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, C.c_float, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
 }
 
@@ -396,8 +397,12 @@ def sag_pool_backward(dx_pooled, x, dtype, n_nodes, n_nodes_out, perm, new_id, s
            "bg_sag_pool_backward")
 
 
+def max_bwd_workspace_bytes(n_big_tgt: int, n_big_src: int) -> int:
+    return _query("bg_max_bwd_workspace_bytes", n_big_tgt, n_big_src)
+
+
 def max_aggregate_backward(x, agg, dagg, dtype, n_nodes, rowptr_tgt, col_tgt, big_tgt, n_big_tgt, rowptr_src, col_src,
-                           big_src, n_big_src, w_scratch, dx, stream):
+                           big_src, n_big_src, w_scratch, dx, ws, ws_bytes, stream):
     _check(load().bg_max_aggregate_backward(x, agg, dagg, dtype, n_nodes, rowptr_tgt, col_tgt, big_tgt, n_big_tgt,
-                                            rowptr_src, col_src, big_src, n_big_src, w_scratch, dx, stream),
+                                            rowptr_src, col_src, big_src, n_big_src, w_scratch, dx, ws, ws_bytes, stream),
            "bg_max_aggregate_backward")

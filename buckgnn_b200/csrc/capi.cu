@@ -206,17 +206,21 @@ template <typename T>
 static void launch_max_bwd(const void* x, const void* agg, const void* dagg, int64_t N, const int32_t* rowptr_tgt,
                            const int32_t* col_tgt, const int32_t* big_tgt, int32_t n_big_tgt, const int32_t* rowptr_src,
                            const int32_t* col_src, const int32_t* big_src, int32_t n_big_src, void* w_scratch, void* dx,
-                           unsigned grid, cudaStream_t stream) {
+                           float* partial, unsigned grid, cudaStream_t stream) {
   const T* xp = static_cast<const T*>(x); const T* ap = static_cast<const T*>(agg); const T* dp = static_cast<const T*>(dagg);
   T* wp = static_cast<T*>(w_scratch); T* op = static_cast<T*>(dx);
   // pass 1 (by target): w_i = dagg_i / n_i
   k_max_bwd_rows<T, 0><<<grid, kMaxBwdWarps * 32, 0, stream>>>(ap, xp, nullptr, dp, rowptr_tgt, col_tgt, N, wp);
-  if (n_big_tgt > 0)
-    k_max_bwd_big<T, 0><<<(unsigned)n_big_tgt, kMaxBwdWarps * 32, 0, stream>>>(ap, xp, nullptr, dp, rowptr_tgt, col_tgt, big_tgt, wp);
+  if (n_big_tgt > 0) {
+    k_max_bwd_big<T, 0><<<dim3((unsigned)n_big_tgt, kMaxBwdSlices), kMaxBwdBigWarps * 32, 0, stream>>>(ap, xp, nullptr, rowptr_tgt, col_tgt, big_tgt, partial);
+    k_max_bwd_big_finish<T, 0><<<(unsigned)n_big_tgt, 32, 0, stream>>>(ap, dp, big_tgt, partial, wp);
+  }
   // pass 2 (by source): dx_j = sum_i [agg_i == x_j] w_i
   k_max_bwd_rows<T, 1><<<grid, kMaxBwdWarps * 32, 0, stream>>>(xp, ap, wp, nullptr, rowptr_src, col_src, N, op);
-  if (n_big_src > 0)
-    k_max_bwd_big<T, 1><<<(unsigned)n_big_src, kMaxBwdWarps * 32, 0, stream>>>(xp, ap, wp, nullptr, rowptr_src, col_src, big_src, op);
+  if (n_big_src > 0) {
+    k_max_bwd_big<T, 1><<<dim3((unsigned)n_big_src, kMaxBwdSlices), kMaxBwdBigWarps * 32, 0, stream>>>(xp, ap, wp, rowptr_src, col_src, big_src, partial);
+    k_max_bwd_big_finish<T, 1><<<(unsigned)n_big_src, 32, 0, stream>>>(xp, nullptr, big_src, partial, op);
+  }
 }
 
 extern "C" {
@@ -727,19 +731,30 @@ int bg_sag_pool_backward(const void* dx_pooled, const void* x, int dtype, int64_
   return BG_OK;
 }
 
+int bg_max_bwd_workspace_bytes(int32_t n_big_tgt, int32_t n_big_src, size_t* bytes_host) {
+  if (!bytes_host || n_big_tgt < 0 || n_big_src < 0) return fail(BG_ERR_INVALID, "bg_max_bwd_workspace_bytes: bad argument");
+  const int32_t m = n_big_tgt > n_big_src ? n_big_tgt : n_big_src;
+  *bytes_host = (size_t)m * kMaxBwdSlices * kHidden * sizeof(float) + 256;
+  return BG_OK;
+}
+
 int bg_max_aggregate_backward(const void* x, const void* agg, const void* dagg, int dtype, int64_t N,
                               const int32_t* rowptr_tgt, const int32_t* col_tgt, const int32_t* big_tgt, int32_t n_big_tgt,
                               const int32_t* rowptr_src, const int32_t* col_src, const int32_t* big_src, int32_t n_big_src,
-                              void* w_scratch, void* dx, void* stream_) {
+                              void* w_scratch, void* dx, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (N < 0 || n_big_tgt < 0 || n_big_src < 0) return fail(BG_ERR_INVALID, "bg_max_aggregate_backward: bad size");
   if (N == 0) return BG_OK;
   if (!x || !agg || !dagg || !rowptr_tgt || !rowptr_src || !w_scratch || !dx || !aligned16(x) || !aligned16(agg) ||
       !aligned16(dagg) || !aligned16(w_scratch) || !aligned16(dx) || (n_big_tgt > 0 && !big_tgt) || (n_big_src > 0 && !big_src))
     return fail(BG_ERR_INVALID, "bg_max_aggregate_backward: null or misaligned pointer");
+  size_t need = 0;
+  bg_max_bwd_workspace_bytes(n_big_tgt, n_big_src, &need);
+  if ((n_big_tgt > 0 || n_big_src > 0) && (!workspace || workspace_bytes < need))
+    return fail(BG_ERR_WORKSPACE, "bg_max_aggregate_backward: workspace too small");
   const unsigned grid = grid_for(N * 32, kMaxBwdWarps * 32, sm_count() * 8);
   BG_BY_DTYPE(dtype, (launch_max_bwd<T>(x, agg, dagg, N, rowptr_tgt, col_tgt, big_tgt, n_big_tgt, rowptr_src, col_src, big_src,
-                                        n_big_src, w_scratch, dx, grid, stream)));
+                                        n_big_src, w_scratch, dx, static_cast<float*>(workspace), grid, stream)));
   BG_LAUNCH_OK();
   return BG_OK;
 }

@@ -468,11 +468,13 @@ class SageTrainFunction(torch.autograd.Function):
             sbuf = Activation(n, 512, prec, dev)
             if sv.aggr == "max":                     # the gradient goes to the neighbours that attain the maximum
                 wtmp = Activation(n, 512, prec, dev)
+                mb = capi.max_bwd_workspace_bytes(idx.n_big, idx_t.n_big)
+                mws = _ws(mb, dev)
                 with engine.TIMERS.span("train_max_bwd"):
                     capi.max_aggregate_backward(x_in.data.data_ptr(), agg.data.data_ptr(), dagg.data.data_ptr(), code, n,
                                                 idx.rowptr.data_ptr(), idx.col.data_ptr(), idx.big_rows.data_ptr(), idx.n_big,
                                                 idx_t.rowptr.data_ptr(), idx_t.col.data_ptr(), idx_t.big_rows.data_ptr(),
-                                                idx_t.n_big, wtmp.data.data_ptr(), sbuf.data.data_ptr(), s)
+                                                idx_t.n_big, wtmp.data.data_ptr(), sbuf.data.data_ptr(), mws.data_ptr(), mb, s)
                 sbuf.refresh_split()
             else:
                 engine.aggregate(dagg, sbuf, idx_t, "sum")

@@ -359,11 +359,13 @@ int bg_segment_expand(const void* src, const int32_t* rowptr, int64_t n_rows, in
  * when the maximum is 0:   n_i[c] = [agg_i[c] == 0] + #{j -> i: x_j[c] == agg_i[c]},
  *                          dx_j[c] = sum_{i: j -> i} [x_j[c] == agg_i[c]] dagg_i[c] / n_i[c].
  * x, agg, dagg, w_scratch, dx: [N, 512] of `dtype`; CSR keyed by target (bg_csr_build key_row = 1) and by source
- * (key_row = 0), each with its big-row list.  No atomics: two gather passes. */
+ * (key_row = 0), each with its big-row list (hub rows are split over 8 CTAs whose partial sums go through `workspace`,
+ * sized by bg_max_bwd_workspace_bytes).  No atomics: two gather passes, fixed summation order. */
+int bg_max_bwd_workspace_bytes(int32_t n_big_tgt, int32_t n_big_src, size_t* bytes_host);
 int bg_max_aggregate_backward(const void* x, const void* agg, const void* dagg, int dtype, int64_t n_nodes,
                               const int32_t* rowptr_tgt, const int32_t* col_tgt, const int32_t* big_rows_tgt, int32_t n_big_tgt,
                               const int32_t* rowptr_src, const int32_t* col_src, const int32_t* big_rows_src, int32_t n_big_src,
-                              void* w_scratch, void* dx, void* stream);
+                              void* w_scratch, void* dx, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Device-side collate: PyG `DataLoader` / `Batch.from_data_list` for a dataset kept in HBM in
  * concatenated form -- x_all [sum n, F], ei_all [2, E_all] with node ids LOCAL to their graph (as

@@ -83,8 +83,10 @@ def test_training_and_collate_entry_points_validate_arguments_without_gpu(lib):
         lambda: capi.gather_rows(None, capi.BG_F16, 512, 16, None, 4, 16, 512, None),
         lambda: capi.index_invert(None, 4, None, None),
         lambda: capi.index_gather(None, None, 4, None, None),
-        lambda: capi.max_aggregate_backward(None, 16, 16, capi.BG_F32, 10, 16, 16, None, 0, 16, 16, None, 0, 16, 16, None),
-        lambda: capi.max_aggregate_backward(16, 16, 16, capi.BG_F32, 10, 16, 16, None, 3, 16, 16, None, 0, 16, 16, None),   # big rows missing
+        lambda: capi.max_aggregate_backward(None, 16, 16, capi.BG_F32, 10, 16, 16, None, 0, 16, 16, None, 0, 16, 16, None, 0, None),
+        lambda: capi.max_aggregate_backward(16, 16, 16, capi.BG_F32, 10, 16, 16, None, 3, 16, 16, None, 0, 16, 16, 16, 1 << 20, None),   # big rows missing
+        lambda: capi.max_aggregate_backward(16, 16, 16, capi.BG_F32, 10, 16, 16, 16, 3, 16, 16, None, 0, 16, 16, 16, 8, None),           # workspace too small
+        lambda: capi.max_bwd_workspace_bytes(-1, 0),
         lambda: capi.sag_pool_backward(16, 16, capi.BG_F32, 10, 11, 16, 16, 16, 1.0, 16, 16, None, 0, 16, 16, 16, 16, 16, None),   # N' > N
         lambda: capi.sag_pool_backward(None, None, capi.BG_F32, 10, 5, 16, 16, 16, 1.0, 16, 16, None, 0, 16, 16, 16, 16, 16, None),
     ]

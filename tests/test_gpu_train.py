@@ -676,10 +676,12 @@ def test_max_aggregation_backward_matches_autograd(precision):
     engine.aggregate(act, agg, idx, "max")
     assert torch.equal(agg.data.float().cpu(), agg_ref.detach())
     w, dx = Activation(n, 512, precision, DEV), Activation(n, 512, precision, DEV)
+    mb = capi.max_bwd_workspace_bytes(idx.n_big, idx_t.n_big)
+    mws = torch.empty(mb, dtype=torch.uint8, device=DEV)
     capi.max_aggregate_backward(act.data.data_ptr(), agg.data.data_ptr(), dact.data.data_ptr(), act.code, n,
                                 idx.rowptr.data_ptr(), idx.col.data_ptr(), idx.big_rows.data_ptr(), idx.n_big,
                                 idx_t.rowptr.data_ptr(), idx_t.col.data_ptr(), idx_t.big_rows.data_ptr(), idx_t.n_big,
-                                w.data.data_ptr(), dx.data.data_ptr(), _stream())
+                                w.data.data_ptr(), dx.data.data_ptr(), mws.data_ptr(), mb, _stream())
     tol = dict(rtol=1e-5, atol=1e-5) if precision == "tf32" else dict(rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(dx.data.float().cpu(), x.grad, **tol)
     assert idx.n_big == 3 and idx_t.n_big == 3                                        # the hub rows went through the CTA path

@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--precision", default="tf32")
-    ap.add_argument("--model", default="GraphSage_meanAggr", help="GraphSage_*Aggr | EA_GNN | EA_GNN_Shared")
+    ap.add_argument("--model", default="GraphSage_meanAggr", help="GraphSage_*Aggr | GraphSAGE_SAG | EA_GNN | EA_GNN_Shared | EAGNN_SAG")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -42,7 +42,7 @@ def main():
     model = BuckGNN(16, 5, 512, 6, "mean", model_name=args.model, dropout_rate=0.1,
                     train_precision=args.precision).to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    stiff = args.model.startswith("EA_GNN")              # the EA-GNN configs use the stiffened plates (cfg 3)
+    stiff = args.model in ("EA_GNN", "EA_GNN_Shared", "EAGNN_SAG")   # the EA-GNN configs use the stiffened plates (cfg 3)
     b = config_batch(2 if stiff else 3, rank=rank, num_graphs=args.graphs).to(dev)
     y = b.y.to(dev).abs() + 0.5
     params = train.trainable_parameters(model)
