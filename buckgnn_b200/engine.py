@@ -600,17 +600,24 @@ def gnblock_layer(x: Activation, e: Activation, buf: GNBlockBuffers, idx: GraphI
 @dataclass
 class SagPoolResult:
     """What PyG `SAGPooling.forward` returns (Models/BuckGNN.py:365-367, 502-504), plus the index maps."""
-    x: Activation                 # [N', 512] = x[perm] * score[perm]
+    x: Optional[Activation]       # [N', 512] = x[perm] * score[perm]
     edge_index: torch.Tensor      # [2, E'] int64, relabelled, original edge order
     batch: torch.Tensor           # [N'] int64
     perm: torch.Tensor            # [N'] int32: old node id of each kept row
     score: torch.Tensor           # [N'] f32 = tanh score of the kept rows
-    new_id: torch.Tensor          # [N] int32: new row of an old node, -1 if dropped
+    new_id: Optional[torch.Tensor]  # [N] int32: new row of an old node, -1 if dropped
     kept_edge: Optional[torch.Tensor]   # [E'] int32: old edge id of each kept edge
     n_nodes: int
     n_edges: int
     graph_ptr: torch.Tensor       # [G+1] int32 offsets of the pooled graphs
-    all_scores: torch.Tensor      # [N] f32 score of every node
+    all_scores: Optional[torch.Tensor]   # [N] f32 score of every node
+
+
+def pool_summary(res: "SagPoolResult") -> "SagPoolResult":
+    """The index side of a pooling result (what `self.pool` returns besides x): kept on the module for inspection
+    without pinning the [N', 512] feature rows and the per-node scratch vectors in memory between calls."""
+    import dataclasses
+    return dataclasses.replace(res, x=None, new_id=None, all_scores=None)
 
 
 def pack_sag_pool(pool) -> Dict[str, object]:

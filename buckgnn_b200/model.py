@@ -449,7 +449,7 @@ class BuckGNN(nn.Module):
                 cur, nxt = nxt, cur
             del nxt, agg
         pooled = engine.sag_pool(cur, idx, idx.graph_ptr, idx.n_graphs, edge_index, packs["sag_pool"], sign=self._sag_sign)
-        self.last_pool = pooled          # (perm, score, edge_index, batch) of the last forward, as self.pool returns them
+        self.last_pool = engine.pool_summary(pooled)   # perm / score / edge_index / batch of the last pooling, without its feature rows
         idx2 = engine.build_graph_index(pooled.edge_index, pooled.batch, pooled.n_nodes)
         cur = pooled.x
         n2 = pooled.n_nodes
@@ -490,7 +490,7 @@ class BuckGNN(nn.Module):
                 e = e_next
         pooled = engine.sag_pool(cur, idx_t, idx.graph_ptr, idx.n_graphs, edge_index, packs["sag_pool"],
                                  sign=self._sag_sign, want_kept_edges=True)
-        self.last_pool = pooled
+        self.last_pool = engine.pool_summary(pooled)   # perm / score / edge_index / batch of the last pooling, without its feature rows
         idx2 = engine.build_graph_index(pooled.edge_index, pooled.batch, pooled.n_nodes, key_row=0)
         e = engine.regather_edge_rows(e, idx, idx2, pooled.kept_edge)
         cur = pooled.x

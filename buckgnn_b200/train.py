@@ -585,7 +585,7 @@ class SagTrainFunction(torch.autograd.Function):
         sv.pool_in = cur
         pack = engine.pack_sag_pool(model.pool)
         pooled = engine.sag_pool(cur, idx, idx.graph_ptr, idx.n_graphs, edge_index, pack, sign=model._sag_sign)
-        model.last_pool = pooled
+        model.last_pool = engine.pool_summary(pooled)   # perm / score / edge_index / batch of the last pooling, without its feature rows
         sv.pooled, sv.pool_pack = pooled, pack
         idx2 = engine.build_graph_index(pooled.edge_index, pooled.batch, pooled.n_nodes)
         sv.idx = idx2                                   # head_backward reads sv.idx.graph_ptr

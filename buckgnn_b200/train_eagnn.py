@@ -349,7 +349,7 @@ class EAGNNSagTrainFunction(torch.autograd.Function):
         # ---- SAGPooling (:365-367)
         pack = engine.pack_sag_pool(model.pool)
         pooled = engine.sag_pool(cur, idx_t, idx.graph_ptr, idx.n_graphs, edge_index, pack, sign=model._sag_sign, want_kept_edges=True)
-        model.last_pool = pooled
+        model.last_pool = engine.pool_summary(pooled)   # perm / score / edge_index / batch of the last pooling, without its feature rows
         idx2 = engine.build_graph_index(pooled.edge_index, pooled.batch, pooled.n_nodes, key_row=0)
         if idx2.n_edges == 0:
             raise NotImplementedError("buckgnn_b200: EAGNN_SAG training needs at least one edge after the pooling")
