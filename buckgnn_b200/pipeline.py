@@ -30,19 +30,23 @@ class DevicePrefetcher:
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.slots = [None, None]
         self.copied = [torch.cuda.Event(), torch.cuda.Event()]
+        # x / edge_index / batch go first and get their own event: a model that never reads edge_attr (the GraphSAGE
+        # variants) can start on a batch while its edge_attr / y / ptr are still crossing PCIe
+        self.core_copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self.wait_for_all_fields = True
         self.released = [torch.cuda.Event(), torch.cuda.Event()]
         self.copy_events = []          # (start, stop) per staged batch when `time_copies` is set
         self.time_copies = False
 
     def _stage(self, host: PlateBatch, k: int) -> PlateBatch:
         slot = self.slots[k]
-        fields = ("x", "edge_index", "edge_attr", "batch", "y", "ptr")
+        fields = ("edge_index", "batch", "x", "edge_attr", "y", "ptr")
         fits = slot is not None and all(getattr(slot, f).shape == getattr(host, f).shape for f in fields)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.released[k])       # the forward that used this slot is done
             if not fits:
-                slot = PlateBatch(*[torch.empty_like(getattr(host, f), device=self.device) for f in fields],
-                                  host.num_graphs)
+                slot = PlateBatch(*[torch.empty_like(getattr(host, f), device=self.device)
+                                    for f in ("x", "edge_index", "edge_attr", "batch", "y", "ptr")], host.num_graphs)
                 self.slots[k] = slot
             slot.num_graphs = host.num_graphs
             if self.time_copies:
@@ -50,6 +54,8 @@ class DevicePrefetcher:
                 t0.record(self.copy_stream)
             for f in fields:
                 getattr(slot, f).copy_(getattr(host, f), non_blocking=True)
+                if f == "x":
+                    self.core_copied[k].record(self.copy_stream)
             if self.time_copies:
                 t1 = torch.cuda.Event(enable_timing=True)
                 t1.record(self.copy_stream)
@@ -71,7 +77,8 @@ class DevicePrefetcher:
             return
         while nxt is not None:
             cur, cur_k = nxt, k
-            torch.cuda.current_stream(self.device).wait_event(self.copied[cur_k])
+            torch.cuda.current_stream(self.device).wait_event(
+                self.copied[cur_k] if self.wait_for_all_fields else self.core_copied[cur_k])
             k ^= 1
             try:
                 nxt = self._stage(next(it), k)                  # overlaps with the caller's forward on `cur`
@@ -100,6 +107,9 @@ class PipelinedInference:
                  on_launch: Optional[Callable] = None):
         self.model, self.batches, self.device, self.depth = model, batches, torch.device(device), max(0, int(depth))
         self.prefetcher = DevicePrefetcher(batches, self.device)
+        # the GraphSAGE variants never read edge_attr (nor y / ptr): their forward may start once x, edge_index and
+        # batch have arrived; the EA-GNN variants wait for the whole batch
+        self.prefetcher.wait_for_all_fields = getattr(model, "model_name", "") in ("EA_GNN", "EA_GNN_Shared", "EAGNN_SAG")
         self.on_launch = on_launch            # called as on_launch(step, before: bool) around each forward (timing hooks)
         self._pool = {}                       # pinned result buffers by size
 
