@@ -307,3 +307,49 @@ def test_sag_topk_is_per_graph_and_order_independent_of_other_graphs():
             mine = perm2[(batch2[perm2] == i)]
             assert torch.equal(mine - off2, blocks[o])
             off2 += sizes[o]
+
+
+# ----------------------------------------------------------------------------- hypothesis properties
+from hypothesis import given, settings, strategies as st
+
+
+def _random_batch(seed, n_graphs, hidden):
+    g = torch.Generator().manual_seed(seed)
+    sizes = torch.randint(2, 7, (n_graphs,), generator=g).tolist()
+    xs, eis, eas, bs, off = [], [], [], [], 0
+    for gi, s in enumerate(sizes):
+        e = int(torch.randint(s, 3 * s + 1, (1,), generator=g))
+        xs.append(torch.randn(s, 16, generator=g))
+        eis.append(torch.randint(0, s, (2, e), generator=g) + off)
+        eas.append(torch.randn(e, 5, generator=g))
+        bs.append(torch.full((s,), gi))
+        off += s
+    return torch.cat(xs), torch.cat(eis, 1), torch.cat(eas), torch.cat(bs), sizes
+
+
+@settings(max_examples=12, deadline=None)
+@given(seed=st.integers(0, 10_000), name=st.sampled_from(["GraphSage_meanAggr", "GraphSage_maxAggr", "GraphSage_addAggr",
+                                                           "EA_GNN", "GraphSAGE_SAG"]))
+def test_property_edge_order_and_graph_order_do_not_matter(seed, name):
+    """permuting the edge list changes nothing beyond fp rounding; relabelling the graphs permutes the predictions"""
+    torch.manual_seed(seed)
+    m = OracleBuckGNN(16, 5, 64, 3, "mean", model_name=name).double().eval()
+    randomize_bn_stats(m)
+    x, ei, ea, batch, sizes = _random_batch(seed, 3, 64)
+    x, ea = x.double(), ea.double()
+    with torch.no_grad():
+        base, _ = m(x, ei, ea, batch)
+        p = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(seed + 1))
+        shuffled, _ = m(x, ei[:, p], ea[p], batch)
+    torch.testing.assert_close(shuffled, base, rtol=1e-9, atol=1e-12)
+    # move graph 0 to the end
+    n0 = sizes[0]
+    n = x.shape[0]
+    node_perm = torch.cat([torch.arange(n0, n), torch.arange(0, n0)])          # new position -> old node
+    new_of_old = torch.empty(n, dtype=torch.long)
+    new_of_old[node_perm] = torch.arange(n)
+    b2 = batch[node_perm]
+    b2 = torch.where(b2 == 0, torch.tensor(len(sizes) - 1), b2 - 1)
+    with torch.no_grad():
+        moved, _ = m(x[node_perm], new_of_old[ei], ea, b2)
+    torch.testing.assert_close(moved, torch.cat([base[1:], base[:1]]), rtol=1e-9, atol=1e-12)
