@@ -155,3 +155,28 @@ def test_sag_variants_register_the_reference_module_names():
     sd["pool.select.weight"] = torch.tensor([[-2.0]])
     m.load_state_dict(sd, strict=True)
     assert m._sag_sign == -1.0
+
+
+@pytest.mark.parametrize("name,pooling,ptype", [
+    ("GraphSage_meanAggr", "mean", "buckling"), ("GraphSage_maxAggr", "mlp", "buckling"),
+    ("GraphSage_addAggr_Shared", "supernode_with_pooling", "buckling"), ("EA_GNN", "mean", "buckling"),
+    ("EA_GNN_Shared", "mlp_no_super", "buckling"), ("GraphSAGE_SAG", "mean", "buckling"), ("EAGNN_SAG", "mean", "buckling"),
+    ("GraphSage_sumAggr", "mean", "static_disp"), ("EA_GNN", "supernode_only", "mode_shape"),
+])
+def test_trainable_parameters_are_exactly_what_autograd_reaches_in_the_oracle(name, pooling, ptype):
+    """`train.trainable_parameters` (the flat gradient bucket of the all-reduce, and the tensors the training step
+    returns gradients for) must list exactly the parameters `loss.backward()` reaches in the reference forward --
+    the reference registers more modules than a given model_name / pooling_layer uses (Models/BuckGNN.py:164,184-187)."""
+    from buckgnn_b200 import train
+    kw = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=4, pooling_layer=pooling,
+              prediction_type=ptype, model_name=name, dropout_rate=0.0)
+    torch.manual_seed(0)
+    ref = OracleBuckGNN(**kw).train()
+    b = make_batch(2, nx=4, ny=3)
+    out, _ = ref(b.x, b.edge_index, b.edge_attr, b.batch)
+    out.square().sum().backward()
+    reached = {k for k, p in ref.named_parameters() if p.grad is not None}
+    ours = BuckGNN(**kw)
+    ids = {id(p) for p in train.trainable_parameters(ours)}
+    listed = {k for k, p in ours.named_parameters() if id(p) in ids}
+    assert listed == reached, (sorted(listed - reached), sorted(reached - listed))
