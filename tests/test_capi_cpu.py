@@ -180,3 +180,36 @@ def test_trainable_parameters_are_exactly_what_autograd_reaches_in_the_oracle(na
     ids = {id(p) for p in train.trainable_parameters(ours)}
     listed = {k for k, p in ours.named_parameters() if id(p) in ids}
     assert listed == reached, (sorted(listed - reached), sorted(reached - listed))
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """every prototype of include/buckgnn_b200.h has a ctypes signature with the same number of arguments, pointer
+    arguments bound as pointers and 64-bit sizes as int64 (a mismatch would corrupt the call frame silently)"""
+    import ctypes as C
+    header = open(os.path.join(ROOT, "include", "buckgnn_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|const char\*)\s+(bg_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) == len(capi.EXPORTED_SYMBOLS)
+    for name, params in protos:
+        params = " ".join(params.split())
+        args = [] if params in ("", "void") else [a.strip() for a in params.split(",")]
+        _, argtypes = capi._SIGNATURES[name]
+        assert len(argtypes) == len(args), (name, len(argtypes), args)
+        for a, t in zip(args, argtypes):
+            if "*" in a or a.startswith("void*"):
+                assert t in (C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.POINTER(capi.GemmSegment),
+                             C.POINTER(capi.Epilogue)), (name, a, t)
+            elif a.startswith("int64_t"):
+                assert t is C.c_int64, (name, a, t)
+            elif a.startswith("int32_t"):
+                assert t is C.c_int32, (name, a, t)
+            elif a.startswith("size_t"):
+                assert t is C.c_size_t, (name, a, t)
+            elif a.startswith("uint64_t"):
+                assert t is C.c_uint64, (name, a, t)
+            elif a.startswith("float"):
+                assert t is C.c_float, (name, a, t)
+            elif a.startswith("int "):
+                assert t is C.c_int, (name, a, t)
+            else:
+                raise AssertionError(f"unclassified parameter {a!r} of {name}")
