@@ -267,7 +267,14 @@ class BuckGNN(nn.Module):
         return packs
 
     # ------------------------------------------------------------------ forward
+    def _check_model_name(self):
+        if self.model_name in ("GraphSage_MLP", "GraphSage_addAggr_woBatchNorm", "GraphSage_sumAggr_woBatchNorm"):
+            # the reference constructs the module lists these branches use only under other names
+            raise AttributeError(f"'BuckGNN' object has no module list for model_name={self.model_name!r} "
+                                 "(same failure as the reference, Models/BuckGNN.py:404-429,472-492)")
+
     def _check_supported(self, x):
+        self._check_model_name()
         if not x.is_cuda:
             raise RuntimeError("buckgnn_b200.BuckGNN runs on CUDA (sm_100a) tensors only; there is no CPU path")
         if self.training:
@@ -277,10 +284,6 @@ class BuckGNN(nn.Module):
                                           f"variants; model_name={self.model_name!r} runs in eval mode only")
         if self.hidden_channels != 512:
             raise NotImplementedError("buckgnn_b200: the tcgen05 path is built for hidden_channels=512")
-        if self.model_name in ("GraphSage_MLP", "GraphSage_addAggr_woBatchNorm", "GraphSage_sumAggr_woBatchNorm"):
-            # the reference constructs the module lists these branches use only under other names
-            raise AttributeError(f"'BuckGNN' object has no module list for model_name={self.model_name!r} "
-                                 "(same failure as the reference, Models/BuckGNN.py:404-429,472-492)")
 
     def forward(self, x, edge_index, edge_attr, batch=None, mask=None):
         self._check_supported(x)

@@ -1,8 +1,9 @@
 """Pure-torch CPU restatement of `BuckGNN.forward` (reference `Models/BuckGNN.py:311-526`).
 
-TEST INFRASTRUCTURE ONLY -- see `oracle/__init__.py` (parity unpinned: PyG and
-torch_scatter are not installable here, so their operators are restated from their
-published semantics at the reference's call sites).
+TEST INFRASTRUCTURE ONLY -- see `oracle/__init__.py`.  Pinned: `tests/test_reference_source.py`
+runs the reference's own `Models/BuckGNN.py` (unmodified, `oracle/reference_source.py`) against
+this module to 1e-6.  PyG and torch_scatter are not installable here, so THEIR operators stay
+restated from their published semantics at the reference's call sites (below).
 
 Operator semantics restated
 ---------------------------

@@ -1,12 +1,14 @@
-"""Generates tests/golden/*.json from the CPU oracle (oracle/buckgnn_oracle.py).
+"""Generates tests/golden/oracle_golden.json by RUNNING THE REFERENCE'S OWN FILE.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          (in the build container, where /root/reference exists)
 
-PyG / torch_scatter cannot be installed in this environment and the reference ships no golden
-vectors, so these fixtures do not pin the oracle against the reference itself ("parity unpinned",
-DESIGN.md section 3); they FREEZE the oracle -- hand-checked on the known-answer cases of
-tests/test_oracle.py -- so that neither it nor the CUDA path can drift unnoticed.  Inputs are
-regenerated from seeds (buckgnn_b200.synth, torch.manual_seed); outputs are stored.
+The model that produces every stored number is `BuckGNN` from `/root/reference/Models/BuckGNN.py`,
+executed unmodified through `oracle/reference_source.py` (its two third-party imports, torch_geometric
+and torch_scatter -- not installable here -- are shimmed with stand-ins of the same signatures, backed by
+the restated operators of oracle/buckgnn_oracle.py).  The file records the sha256 of the reference source
+it ran.  Inputs are regenerated from seeds (buckgnn_b200.synth, torch.manual_seed); outputs are stored.
+On the GPU box /root/reference is absent: tests read the committed JSON; `seeded_model` there builds the
+oracle twin with the same seed as a WEIGHT CONTAINER (its state_dict checksum is checked against the file).
 """
 import json
 import os
@@ -18,6 +20,7 @@ import torch
 
 from buckgnn_b200.synth import make_batch
 from oracle import buckgnn_oracle as O
+from oracle import reference_source as RS
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -28,6 +31,16 @@ FORWARD_CASES = [  # name, model cfg overrides, batch kwargs
     ("sage_add_shared_4x512", dict(model_name="GraphSage_addAggr_Shared", num_layers=4), dict(num_graphs=2, nx=8, ny=6)),
     ("eagnn_3x512_stiffened", dict(model_name="EA_GNN", num_layers=3), dict(num_graphs=2, nx=7, ny=6, stiffened=True)),
     ("default_mlp", dict(model_name="GraphSAGE_MLP"), dict(num_graphs=3, nx=6, ny=5)),
+    # TRAIN_FINAL.py:55,71 and the constructor default: hidden_channels=128 (2-layer encoder / decoder, :41-65)
+    ("sage_mean_6x128", dict(model_name="GraphSage_meanAggr", hidden_channels=128), dict(num_graphs=3, nx=9, ny=7)),
+    ("sage_add_4x128_mlp_pool", dict(model_name="GraphSage_addAggr", hidden_channels=128, num_layers=4, pooling_layer="mlp"),
+     dict(num_graphs=2, nx=8, ny=6)),
+    ("eagnn_3x128_stiffened", dict(model_name="EA_GNN", hidden_channels=128, num_layers=3), dict(num_graphs=2, nx=7, ny=6, stiffened=True)),
+    ("sage_mean_4x256", dict(model_name="GraphSage_meanAggr", hidden_channels=256, num_layers=4), dict(num_graphs=2, nx=8, ny=6)),
+    # configs[4]'s model on its meshes: stiffened plates with virtual edges + super node
+    ("sage_mean_6x512_stiffened_virtual", dict(model_name="GraphSage_meanAggr"), dict(num_graphs=3, nx=9, ny=8, stiffened=True)),
+    ("sage_mean_6x512_no_super_virtual", dict(model_name="GraphSage_meanAggr"),
+     dict(num_graphs=2, nx=9, ny=8, stiffened=True, super_node=False, virtual_edges=True)),
     ("sage_mean_supernode_only", dict(model_name="GraphSage_meanAggr", num_layers=3, pooling_layer="supernode_only"),
      dict(num_graphs=3, nx=6, ny=5)),
     # SAGPooling variants: the top-k is discrete, so these cases are chosen (and checked below) to have a clear
@@ -45,11 +58,17 @@ def model_cfg(**over):
     return cfg
 
 
-def seeded_oracle(cfg):
+def seeded_model(cfg, reference: bool):
+    """Seeded weights + non-trivial BN statistics.  reference=True: the class from the reference's own file;
+    False: the oracle twin (same constructor order -> same RNG stream -> identical state_dict)."""
     torch.manual_seed(0)
-    m = O.OracleBuckGNN(**cfg)
+    m = (RS.load_reference().BuckGNN if reference else O.OracleBuckGNN)(**cfg)
     O.randomize_bn_stats(m, realistic=True)
     return m
+
+
+def seeded_oracle(cfg):
+    return seeded_model(cfg, reference=False)
 
 
 def state_checksum(m):
@@ -98,10 +117,14 @@ def topk_gaps(m, b):
 
 
 def main():
-    out = {"forward": {}, "operators": {}, "training": {}}
+    if not RS.reference_available():
+        raise SystemExit("make_golden.py needs /root/reference (it runs the reference's own Models/BuckGNN.py)")
+    out = {"generated_from": RS.REFERENCE_FILE, "reference_sha256": RS.reference_sha256(),
+           "generator": "tests/golden/make_golden.py via oracle/reference_source.py (torch_geometric / torch_scatter shimmed)",
+           "forward": {}, "operators": {}, "training": {}}
     for name, over, bkw in FORWARD_CASES:
         cfg = model_cfg(**over)
-        m = seeded_oracle(cfg).eval()
+        m = seeded_model(cfg, reference=True).eval()
         b = make_batch(**bkw)
         with torch.no_grad():
             pred, bout = m(b.x, b.edge_index, b.edge_attr, b.batch)
@@ -124,7 +147,7 @@ def main():
     ops["sag_filter_adj"] = fei.tolist()
     # training step: loss and gradient norms of one step (dropout off), plus BN buffers after it
     cfg = model_cfg(num_layers=3, dropout_rate=0.0)
-    m = seeded_oracle(cfg).train()
+    m = seeded_model(cfg, reference=True).train()
     b = make_batch(num_graphs=3, nx=7, ny=6)
     y = torch.tensor([0.5, -0.25, 1.0])
     pred, _ = m(b.x, b.edge_index, b.edge_attr, b.batch)

@@ -1,6 +1,9 @@
-"""Golden fixtures (tests/golden/oracle_golden.json, written by tests/golden/make_golden.py).
+"""Golden fixtures (tests/golden/oracle_golden.json, written by tests/golden/make_golden.py BY RUNNING THE
+REFERENCE'S OWN `Models/BuckGNN.py` -- see oracle/reference_source.py; the file carries the sha256 of the source
+it ran).
 
-CPU: the oracle reproduces every stored vector (freezes the checker).
+CPU: the oracle reproduces every stored vector (pins the checker to the reference); where /root/reference exists
+     the reference file itself is re-run and must reproduce the committed numbers.
 GPU: the CUDA path reproduces the stored predictions / training-step numbers without the oracle in
 the loop at all -- the weights come from the seed, the expected numbers from the committed file."""
 import importlib.util
@@ -18,6 +21,27 @@ GOLD = json.load(open(os.path.join(HERE, "golden", "oracle_golden.json")))
 _spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
 mk = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(mk)
+
+
+def test_golden_file_is_stamped_with_the_reference_source():
+    assert GOLD["generated_from"] == "/root/reference/Models/BuckGNN.py"
+    assert len(GOLD["reference_sha256"]) == 64
+    if mk.RS.reference_available():
+        assert mk.RS.reference_sha256() == GOLD["reference_sha256"]
+
+
+@pytest.mark.skipif(not mk.RS.reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("name", sorted(GOLD["forward"]))
+def test_reference_file_reproduces_golden_forward(name):
+    """Re-runs the reference's own source on the seeded inputs: the committed fixture is its output."""
+    g = GOLD["forward"][name]
+    m = mk.seeded_model(g["cfg"], reference=True).eval()
+    assert type(m).__module__ == "_reference_Models_BuckGNN"
+    assert mk.state_checksum(m) == pytest.approx(g["state_checksum"], rel=1e-9)
+    b = make_batch(**g["batch"])
+    with torch.no_grad():
+        pred, _ = m(b.x, b.edge_index, b.edge_attr, b.batch)
+    torch.testing.assert_close(pred.double().reshape(-1), torch.tensor(g["pred"], dtype=torch.float64), rtol=1e-5, atol=1e-7)
 
 
 @pytest.mark.parametrize("name", sorted(GOLD["forward"]))
