@@ -109,6 +109,11 @@ class BuckGNN(nn.Module):
                  model_name="GraphSAGE_MLP", *, precision: str = "auto", cta_group: int = 2,
                  cache_index: bool = False, fold_encoder: bool = True, train_precision: str = "tf32"):
         super().__init__()
+        self._ctor_kwargs = dict(num_node_features=num_node_features, num_edge_features=num_edge_features,
+                                 hidden_channels=hidden_channels, num_layers=num_layers, pooling_layer=pooling_layer,
+                                 prediction_type=prediction_type, use_z_coord=use_z_coord, use_rotations=use_rotations,
+                                 dropout_rate=dropout_rate, model_name=model_name, precision=precision, cta_group=cta_group,
+                                 cache_index=cache_index, fold_encoder=fold_encoder, train_precision=train_precision)
         if precision == "auto":
             aggr = _SAGE_LISTS[model_name][1] if model_name in _SAGE_LISTS else (
                 "add" if model_name == "GraphSage_addAggr_Shared" else "mean")
@@ -188,6 +193,8 @@ class BuckGNN(nn.Module):
         self._packs: Dict[str, object] = {}
         self._pack_sig = None
         self._index_cache = None
+        self._wide = None                     # hidden_channels != 512: the zero-padded 512-wide twin (narrow.py), built lazily
+        self._param_inputs = None             # set by narrow.WideTwin around a train-mode forward of the twin
 
     # ------------------------------------------------------------------ weight packing
     def _absorb_select_weight(self, state_dict, prefix, *args):
@@ -277,16 +284,20 @@ class BuckGNN(nn.Module):
         self._check_model_name()
         if not x.is_cuda:
             raise RuntimeError("buckgnn_b200.BuckGNN runs on CUDA (sm_100a) tensors only; there is no CPU path")
-        if self.training:
-            if self.model_name not in _SAGE_LISTS and self.model_name not in ("GraphSage_addAggr_Shared", "EA_GNN",
-                                                                               "EA_GNN_Shared", "GraphSAGE_SAG", "EAGNN_SAG"):
-                raise NotImplementedError(f"buckgnn_b200: the training step is built for the GraphSAGE and EA-GNN "
-                                          f"variants; model_name={self.model_name!r} runs in eval mode only")
-        if self.hidden_channels != 512:
-            raise NotImplementedError("buckgnn_b200: the tcgen05 path is built for hidden_channels=512")
+        if self.hidden_channels > 512:
+            raise NotImplementedError("buckgnn_b200: the tcgen05 path holds one 512-column row per TMEM lane; "
+                                      "hidden_channels > 512 is not built")
 
     def forward(self, x, edge_index, edge_attr, batch=None, mask=None):
         self._check_supported(x)
+        if self.hidden_channels != 512:
+            # TRAIN_FINAL.py:55,71 / the constructor default use 128: runs as the exact zero-padded 512-wide twin.
+            # 129..255 build no encoder in the reference (Models/BuckGNN.py:41,67): the same AttributeError surfaces here.
+            if self._wide is None:
+                self.node_encoder                                    # AttributeError for 129 <= hidden <= 255, as the reference
+                from .narrow import WideTwin
+                self._wide = WideTwin(self, self._ctor_kwargs)
+            return self._wide.forward(x, edge_index, edge_attr, batch)
         node_level = "static" in self.prediction_type or "mode_shape" in self.prediction_type
         if self.prediction_type != "buckling" and not node_level:
             raise ValueError(f"Unknown prediction type: {self.prediction_type}")
@@ -300,6 +311,9 @@ class BuckGNN(nn.Module):
         if self.training:       # train-mode BatchNorm / Dropout + autograd through the backward kernels (train.py)
             from . import train
             pred = train.forward_train(self, x, edge_index, batch, edge_attr=edge_attr)
+            # the train-mode kernels update the BatchNorm running statistics through raw pointers (no version bump):
+            # drop the eval-mode operand cache so the next eval forward folds the new statistics
+            self._pack_sig = None
             if self.model_name in ("GraphSAGE_SAG", "EAGNN_SAG"):   # `batch` was reassigned by self.pool (:365, :502)
                 return pred.squeeze(), self.last_pool.batch
             if node_level:                                   # reference :518-524; the row selection is an autograd index

@@ -342,7 +342,7 @@ class SageTrainFunction(torch.autograd.Function):
         n = x.shape[0]
         convs = model._sage_layers()
         L = len(convs)
-        aggr = convs[0][0].aggr
+        aggr = convs[0][0].aggr if convs else "mean"      # no layers: the default model_name (encoder -> pool -> decoder)
         p_drop = float(model.dropout.p)
         pending = engine.begin_graph_index(edge_index, batch, n)
         # one read-back for all epilogue bias vectors of the step (they travel as kernel parameters)
@@ -687,6 +687,9 @@ def forward_train(model, x, edge_index, batch, seed: Optional[int] = None, edge_
     if seed is None:                                    # one draw from torch's generator per step, like nn.Dropout
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     params = trainable_parameters(model)
+    inputs = getattr(model, "_param_inputs", None)
+    if inputs:          # narrow.WideTwin: the twin's parameters as differentiable embeddings of the narrow model's
+        params = [inputs.get(id(p_), p_) for p_ in params]
     if model.model_name in ("EA_GNN", "EA_GNN_Shared"):
         from .train_eagnn import EAGNNTrainFunction
         return EAGNNTrainFunction.apply(model, x, edge_index, edge_attr, batch, seed, *params)
