@@ -20,7 +20,7 @@ BG_BF16, BG_F32, BG_F16 = 0, 1, 2
 BG_AGGR_MEAN, BG_AGGR_SUM, BG_AGGR_MAX = 0, 1, 2
 BG_BIG_ROW_THRESHOLD = 64
 BG_MAX_GEMM_SEGMENTS = 8
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 AGGR_CODES = {"mean": BG_AGGR_MEAN, "sum": BG_AGGR_SUM, "add": BG_AGGR_SUM, "max": BG_AGGR_MAX}
 
@@ -74,7 +74,7 @@ _SIGNATURES = {
     "bg_batch_info": (C.c_int, [_P, _I64, _P, _P]),
     "bg_publish_words": (C.c_int, [_P, _P, _I32, _P]),
     "bg_graph_ptr_build": (C.c_int, [_P, _I64, _I64, _P, _P]),
-    "bg_encoder_front": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "bg_encoder_front": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P]),
     "bg_expand_rowptr": (C.c_int, [_P, _I64, _I64, _P, _P, _P, C.c_int, C.c_int, _P]),
     "bg_add": (C.c_int, [_P, _P, _P, _P, C.c_int, _I64, _P]),
     "bg_aggregate_workspace_bytes": (C.c_int, [_I32, _SZP]),
@@ -86,7 +86,7 @@ _SIGNATURES = {
     "bg_wgrad512": (C.c_int, [_P, _I64, _P, _I32, _I64, C.c_int, _I64, _I32, _I64, _P, _P]),
     "bg_pool_workspace_bytes": (C.c_int, [_I64, _SZP]),
     "bg_pool_head": (C.c_int, [_P, C.c_int, _I64, _P, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P,
-                               _P, C.c_size_t, _P]),
+                               _P, C.c_size_t, _P, _P]),
     "bg_cast_f32": (C.c_int, [_P, _P, C.c_int, _I64, _P]),
     "bg_split_tf32": (C.c_int, [_P, _P, _P, _I64, _P]),
     "bg_train_workspace_bytes": (C.c_int, [_I64, _SZP]),
@@ -207,8 +207,8 @@ def graph_ptr_build(batch, n_nodes, n_graphs, graph_ptr, stream):
     _check(load().bg_graph_ptr_build(batch, n_nodes, n_graphs, graph_ptr, stream), "bg_graph_ptr_build")
 
 
-def encoder_front(x, n_nodes, n_features, w1, b1, w2, b2, out, out_dtype, stream, row_gather=None):
-    _check(load().bg_encoder_front(x, n_nodes, n_features, w1, b1, w2, b2, row_gather, out, out_dtype, stream),
+def encoder_front(x, n_nodes, n_features, w1, b1, w2, b2, out, out_dtype, stream, row_gather=None, nonfinite=None):
+    _check(load().bg_encoder_front(x, n_nodes, n_features, w1, b1, w2, b2, row_gather, out, out_dtype, nonfinite, stream),
            "bg_encoder_front")
 
 
@@ -251,9 +251,9 @@ POOL_MODES = {"mean": 0, "mlp": 0, "mean_no_super": 1, "mlp_no_super": 1, "super
 
 
 def pool_head(x, dtype, n_nodes, graph_ptr, n_graphs, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim,
-              pred, pooled_out, ws, ws_bytes, stream):
+              pred, pooled_out, ws, ws_bytes, stream, nonfinite=None):
     _check(load().bg_pool_head(x, dtype, n_nodes, graph_ptr, n_graphs, pool_mode, pre_w, pre_b, w1, b1, w2, b2,
-                               w3, b3, out_dim, pred, pooled_out, ws, ws_bytes, stream), "bg_pool_head")
+                               w3, b3, out_dim, pred, pooled_out, ws, ws_bytes, nonfinite, stream), "bg_pool_head")
 
 
 def cast_f32(src, dst, dst_dtype, n, stream):

@@ -81,7 +81,12 @@ __global__ void k_expand_rowptr(const int32_t* __restrict__ rowptr, int64_t n_ro
     if (row_of)
       for (int32_t i = b + lane; i < e; i += 32) { row_of[i] = (int32_t)r; iota[i] = i; }
     if (nonempty) {
-      const float v0 = (lane == 0 && e > b) ? (as_count ? (float)(e - b) : 1.f) : 0.f;
+      // as_count: the row's degree as three base-256 digits in columns 0..2 (weights 1, 256, 65536 on the host side):
+      // every digit is exact in bf16 / fp16 / tf32 operands, a plain count above 256 / 2048 would be rounded
+      const int32_t deg = e - b;
+      float v0 = 0.f;
+      if (as_count) { if (lane < 3) v0 = (float)((deg >> (8 * lane)) & (lane == 2 ? 0x7fff : 0xff)); }
+      else if (lane == 0 && deg > 0) v0 = 1.f;
       if constexpr (sizeof(T) == 2) { nonempty[r * 64 + lane] = Pack16<T>::one(v0); nonempty[r * 64 + 32 + lane] = Pack16<T>::one(0.f); }
       else { nonempty[r * 64 + lane] = v0; nonempty[r * 64 + 32 + lane] = 0.f; }
     }
@@ -188,14 +193,15 @@ static int aggregate_dispatch(const T* x, T* out, int64_t N, const int32_t* rowp
 template <typename T>
 static void pool_launch(const T* x, const int32_t* graph_ptr, int64_t G, int mode, const float* pre_w, const float* pre_b,
                         const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
-                        const float* b3, int out_dim, float* pred, float* pooled_out, float* partial, cudaStream_t stream) {
+                        const float* b3, int out_dim, float* pred, float* pooled_out, float* partial, const int32_t* nonfinite,
+                        cudaStream_t stream) {
   if (mode != BG_POOL_SUPERNODE_ONLY) {
     dim3 grid((unsigned)G, kPoolSlices);
     const int exclude_last = (mode == BG_POOL_MEAN_NO_SUPER || mode == BG_POOL_SUPERNODE_WITH_POOLING) ? 1 : 0;
     k_pool_partial<T><<<grid, kPoolWarps * 32, 0, stream>>>(x, graph_ptr, partial, exclude_last);
   }
   k_pool_head<T><<<(unsigned)G, 128, 0, stream>>>(x, partial, graph_ptr, mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3,
-                                                   out_dim, pred, pooled_out);
+                                                   out_dim, pred, pooled_out, nonfinite);
 }
 
 }  // namespace bg
@@ -337,7 +343,8 @@ int bg_publish_words(const int32_t* src, int32_t* dst_host_mapped, int32_t n, vo
 
 // ------------------------------------------------------------------ K5 front
 int bg_encoder_front(const float* x, int64_t N, int32_t F, const float* w1, const float* b1,
-                     const float* w2, const float* b2, const int32_t* row_gather, void* out, int out_dtype, void* stream_) {
+                     const float* w2, const float* b2, const int32_t* row_gather, void* out, int out_dtype,
+                     int32_t* nonfinite_flag, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (N < 0 || F <= 0 || F > kEncMaxF) return fail(BG_ERR_UNSUPPORTED, "bg_encoder_front: need 0 < n_features <= 32");
   if (N == 0) return BG_OK;
@@ -356,7 +363,7 @@ int bg_encoder_front(const float* x, int64_t N, int32_t F, const float* w1, cons
     static bool set = false;                                                                                   \
     if (!set) { BG_CUDA_OK(cudaFuncSetAttribute(k_encoder_front_mma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem)); set = true; } \
     const unsigned mgrid = (unsigned)min64(ceil_div64(N, 16 * kEncMmaWarps), (int64_t)sm_count() * 2);        \
-    k_encoder_front_mma<T><<<mgrid, kEncMmaWarps * 32, msmem, stream>>>(x, N, F, w1, b1, w2, b2, row_gather, static_cast<T*>(out)); \
+    k_encoder_front_mma<T><<<mgrid, kEncMmaWarps * 32, msmem, stream>>>(x, N, F, w1, b1, w2, b2, row_gather, static_cast<T*>(out), nonfinite_flag); \
   }
   if (out_dtype == BG_BF16) BG_ENC_MMA_CASE(__nv_bfloat16)
   else if (out_dtype == BG_F16) BG_ENC_MMA_CASE(__half)
@@ -555,7 +562,8 @@ int bg_pool_workspace_bytes(int64_t G, size_t* bytes_host) {
 int bg_pool_head(const void* x, int dtype, int64_t N, const int32_t* graph_ptr, int64_t G, int pool_mode,
                  const float* pre_w, const float* pre_b,
                  const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
-                 int32_t out_dim, float* pred, float* pooled_out, void* workspace, size_t workspace_bytes, void* stream_) {
+                 int32_t out_dim, float* pred, float* pooled_out, void* workspace, size_t workspace_bytes,
+                 const int32_t* nonfinite_flag, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (G < 0 || N < 0 || G > 65535LL * 1024) return fail(BG_ERR_INVALID, "bg_pool_head: bad size");
   if (G == 0) return BG_OK;
@@ -570,11 +578,11 @@ int bg_pool_head(const void* x, int dtype, int64_t N, const int32_t* graph_ptr, 
   if (!workspace || workspace_bytes < need) return fail(BG_ERR_WORKSPACE, "bg_pool_head: workspace too small");
   float* partial = static_cast<float*>(workspace);
   if (dtype == BG_BF16)
-    pool_launch(static_cast<const __nv_bfloat16*>(x), graph_ptr, G, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, partial, stream);
+    pool_launch(static_cast<const __nv_bfloat16*>(x), graph_ptr, G, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, partial, nonfinite_flag, stream);
   else if (dtype == BG_F16)
-    pool_launch(static_cast<const __half*>(x), graph_ptr, G, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, partial, stream);
+    pool_launch(static_cast<const __half*>(x), graph_ptr, G, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, partial, nonfinite_flag, stream);
   else if (dtype == BG_F32)
-    pool_launch(static_cast<const float*>(x), graph_ptr, G, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, partial, stream);
+    pool_launch(static_cast<const float*>(x), graph_ptr, G, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, partial, nonfinite_flag, stream);
   else
     return fail(BG_ERR_INVALID, "bg_pool_head: bad dtype");
   BG_LAUNCH_OK();

@@ -298,4 +298,7 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t a_fmt, uint32_t b_fmt
   return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+template <typename T> struct is_bf16 { static constexpr bool value = false; };
+template <> struct is_bf16<__nv_bfloat16> { static constexpr bool value = true; };
+
 }  // namespace bg

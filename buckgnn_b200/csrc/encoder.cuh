@@ -153,8 +153,13 @@ __global__ void __launch_bounds__(kEncMmaWarps * 32)
 k_encoder_front_mma(const float* __restrict__ x, int64_t N, int F,
                     const float* __restrict__ w1, const float* __restrict__ b1,
                     const float* __restrict__ w2, const float* __restrict__ b2,
-                    const int32_t* __restrict__ row_gather, TOut* __restrict__ out) {
+                    const int32_t* __restrict__ row_gather, TOut* __restrict__ out, int32_t* __restrict__ nonfinite) {
   static_assert(sizeof(TOut) == 2, "16-bit outputs only");
+  // h is stored BEFORE any normalisation: a checkpoint with large encoder activations would overflow the fp16 range
+  // silently (inf -> NaN in the L2-normalize -> 0 after ReLU's fmaxf).  Values the output format cannot hold raise
+  // *nonfinite instead; bg_pool_head turns the flag into NaN predictions (no host sync involved).
+  const float limit = is_bf16<TOut>::value ? 3.3e38f : 65504.f;
+  bool bad = false;
   extern __shared__ __align__(16) unsigned char enc_smem_raw[];
   EncoderMmaSmem& s = *reinterpret_cast<EncoderMmaSmem*>(enc_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -227,6 +232,8 @@ k_encoder_front_mma(const float* __restrict__ x, int64_t N, int F,
         mma_16816(cb, a2[kk], *reinterpret_cast<const uint32_t*>(&s.w2[8 * j + 8 + g][k0]),
                   *reinterpret_cast<const uint32_t*>(&s.w2[8 * j + 8 + g][k0 + 8]));
       }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bad |= !(ca[e] <= limit) | !(cb[e] <= limit);          // NaN compares false
       *reinterpret_cast<uint32_t*>(&stage[g][8 * j + 2 * tig]) = Pack16<TOut>::pack(fmaxf(ca[0], 0.f), fmaxf(ca[1], 0.f));
       *reinterpret_cast<uint32_t*>(&stage[g + 8][8 * j + 2 * tig]) = Pack16<TOut>::pack(fmaxf(ca[2], 0.f), fmaxf(ca[3], 0.f));
       *reinterpret_cast<uint32_t*>(&stage[g][8 * j + 8 + 2 * tig]) = Pack16<TOut>::pack(fmaxf(cb[0], 0.f), fmaxf(cb[1], 0.f));
@@ -241,6 +248,7 @@ k_encoder_front_mma(const float* __restrict__ x, int64_t N, int F,
     }
     __syncwarp();
   }
+  if (bad && nonfinite != nullptr) atomicOr(nonfinite, 1);
 }
 
 }  // namespace bg

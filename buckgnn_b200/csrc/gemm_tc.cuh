@@ -126,8 +126,6 @@ BG_DEVINL void sts_v4(uint32_t addr, uint4 v) {
 template <int kRegs> BG_DEVINL void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs> BG_DEVINL void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
-template <typename T> struct is_bf16 { static constexpr bool value = false; };
-template <> struct is_bf16<__nv_bfloat16> { static constexpr bool value = true; };
 
 struct EpiCtx {
   uint32_t tmem_base, stage_u32;    // stage_u32: this warp's 4 KB staging tile

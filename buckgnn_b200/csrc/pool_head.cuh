@@ -74,7 +74,7 @@ k_pool_head(const T* __restrict__ x, const float* __restrict__ partial, const in
             const float* __restrict__ w1, const float* __restrict__ b1,
             const float* __restrict__ w2, const float* __restrict__ b2,
             const float* __restrict__ w3, const float* __restrict__ b3, int out_dim,
-            float* __restrict__ pred, float* __restrict__ pooled_out) {
+            float* __restrict__ pred, float* __restrict__ pooled_out, const int32_t* __restrict__ nonfinite) {
   __shared__ float feat[2 * kHidden];
   __shared__ float tmp[kHidden];
   __shared__ float h1[128];
@@ -138,7 +138,9 @@ k_pool_head(const T* __restrict__ x, const float* __restrict__ partial, const in
     const float* wr = w3 + (size_t)t * 64;
     float a = 0.f;
     for (int k = 0; k < 64; ++k) a = fmaf(__ldg(wr + k), h2[k], a);
-    pred[(size_t)g * out_dim + t] = a + b3[t];
+    // an upstream kernel met values its 16-bit storage format cannot hold (bg_encoder_front): fail loudly
+    const bool poisoned = nonfinite != nullptr && *nonfinite != 0;
+    pred[(size_t)g * out_dim + t] = poisoned ? __int_as_float(0x7fc00000) : a + b3[t];
   }
 }
 

@@ -199,8 +199,12 @@ BG_DEVINL void rank_tile(const float* __restrict__ sj, int32_t cnt, int32_t j_ba
 
 // ascending order of this key = descending score, ties by ascending local node id.  -0.0 is folded onto +0.0 first
 // (they compare equal as floats, so a stable float sort does not separate them).
+// a NaN score (non-finite activations upstream) ranks as -inf, so both paths still produce a valid permutation: the
+// counting rank would otherwise give every NaN rank 0 (all comparisons false) and leave perm slots unwritten
+BG_DEVINL float sag_rank_value(float s) { return (s != s) ? -CUDART_INF_F : s; }
+
 BG_DEVINL unsigned long long sag_sort_key(float s, uint32_t local) {
-  const uint32_t b = __float_as_uint(s + 0.0f);
+  const uint32_t b = __float_as_uint(sag_rank_value(s) + 0.0f);
   const uint32_t asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
   return ((unsigned long long)(~asc) << 32) | local;
 }
@@ -270,13 +274,13 @@ k_sag_rank(const float* __restrict__ score, const int32_t* __restrict__ graph_pt
 #pragma unroll
   for (int k = 0; k < kRankPerThread; ++k) {
     ii[k] = i0 + (int32_t)threadIdx.x + k * kRankThreads;
-    si[k] = (ii[k] < hi) ? score[ii[k]] : CUDART_INF_F;
+    si[k] = (ii[k] < hi) ? sag_rank_value(score[ii[k]]) : CUDART_INF_F;
     rank[k] = 0;
   }
   for (int32_t jb = lo; jb < hi; jb += kRankTileJ) {
     const int32_t cnt = min(kRankTileJ, hi - jb);
     __syncthreads();
-    for (int32_t j = threadIdx.x; j < cnt; j += kRankThreads) sj[j] = score[jb + j];
+    for (int32_t j = threadIdx.x; j < cnt; j += kRankThreads) sj[j] = sag_rank_value(score[jb + j]);
     __syncthreads();
     // split the staged scores at this CTA's own node range: only the diagonal block needs the index tie-break
     // (i0 - jb and i_end - jb are multiples of kRankTileI or the end of the graph, so the float4 reads stay aligned)
@@ -294,7 +298,7 @@ k_sag_rank(const float* __restrict__ score, const int32_t* __restrict__ graph_pt
       new_id[ii[k]] = nid;
       perm[nid] = ii[k];
       batch_out[nid] = (int64_t)g;
-      score_out[nid] = si[k];
+      score_out[nid] = score[ii[k]];
     } else {
       new_id[ii[k]] = -1;
     }

@@ -323,15 +323,16 @@ def aggregate(x: Activation, out: Activation, idx: GraphIndex, aggr: str, fold_h
 
 
 def encoder_hidden(x: torch.Tensor, enc_w: Dict[str, torch.Tensor], precision: str,
-                   row_gather: Optional[torch.Tensor] = None) -> "Activation":
-    """First two Linear+ReLU of an encoder -> [n,128] activation (K5 front)."""
+                   row_gather: Optional[torch.Tensor] = None, nonfinite: Optional[torch.Tensor] = None) -> "Activation":
+    """First two Linear+ReLU of an encoder -> [n,128] activation (K5 front).  `nonfinite` (int32 [1], device) is
+    raised when the 16-bit storage format cannot hold a value of the (un-normalised) hidden layer."""
     f = x.shape[1]
     n = x.shape[0] if row_gather is None else row_gather.shape[0]
     h = Activation(n, 128, precision, x.device)
     with TIMERS.span("encoder_front"):
         capi.encoder_front(x.data_ptr(), n, f, enc_w["w1"].data_ptr(), enc_w["b1"].data_ptr(),
                            enc_w["w2"].data_ptr(), enc_w["b2"].data_ptr(), h.data.data_ptr(), h.code, _stream(),
-                           row_gather=_p(row_gather))
+                           row_gather=_p(row_gather), nonfinite=_p(nonfinite))
     h.refresh_split()
     return h
 
@@ -361,6 +362,11 @@ def pack_folded_layer0(enc_last: torch.nn.Linear, conv, bn, aggr: str, precision
     Wl, bl, Wr = d64(conv.lin_l.weight), d64(conv.lin_l.bias), d64(conv.lin_r.weight)
     lp = lambda w: pack_linear(w.to(torch.float32).to(dev), precision)
     gate = torch.cat([(Wl @ b3)[:, None], torch.zeros(512, 63, dtype=torch.float64)], 1)
+    if aggr in ("sum", "add"):
+        # the A operand carries deg_i as three base-256 digits (bg_expand_rowptr as_count): a super node's degree
+        # (thousands) is not exact in 8 / 11 significant bits, its digits are
+        gate[:, 1] = gate[:, 0] * 256.0
+        gate[:, 2] = gate[:, 0] * 65536.0
     scale, shift = fold_batchnorm(bn) if bn is not None else (None, None)
     return FoldedLayer0Pack(lp(Wl @ W3), lp(Wr @ W3), lp(gate), (Wr @ b3 + bl).to(torch.float32).contiguous(),
                             scale, shift, aggr in ("sum", "add"),
@@ -381,6 +387,7 @@ def sage_layer0_folded(h: "Activation", out: "Activation", idx: GraphIndex, w: F
         capi.expand_rowptr(idx.rowptr.data_ptr(), n, idx.n_edges, None, None, ind.data.data_ptr(), ind.code, _stream(),
                            as_count=w.as_count)
         ind.refresh_split()
+        # indicator / degree digits are exact in tf32 (lo part 0): of the 3xTF32 products only hi*w_hi + hi*w_lo remain
         segs = segs + _segments(ind, w.wgate)[:2]
     with TIMERS.span("sage_update0"):
         gemm512(segs, n, h.precision, out, cta_group=cta_group, bias=bias.data_ptr(), bn_scale=_p(w.bn_scale),
@@ -388,10 +395,11 @@ def sage_layer0_folded(h: "Activation", out: "Activation", idx: GraphIndex, w: F
 
 
 def encoder_forward(x: torch.Tensor, enc_w: Dict[str, torch.Tensor], w3: LinearPack, precision: str,
-                    out: Activation, cta_group: int, row_gather: Optional[torch.Tensor] = None) -> None:
+                    out: Activation, cta_group: int, row_gather: Optional[torch.Tensor] = None,
+                    nonfinite: Optional[torch.Tensor] = None) -> None:
     """node_encoder / edge_encoder (Models/BuckGNN.py:68-82): two fp32 CUDA-core layers, then 128->512 on
     tcgen05.  `row_gather` [n] int32 reads input row row_gather[i] for output row i."""
-    h = encoder_hidden(x, enc_w, precision, row_gather)
+    h = encoder_hidden(x, enc_w, precision, row_gather, nonfinite)
     n = h.data.shape[0]
     with TIMERS.span("encoder_gemm"):
         gemm512(_segments(h, w3), n, precision, out, cta_group=cta_group, bias=enc_w["b3_host"].data_ptr())
@@ -410,7 +418,8 @@ def sage_layer(x: Activation, agg: Activation, out: Activation, idx: GraphIndex,
 
 
 def pool_head(x: Activation, idx: GraphIndex, dec: Dict[str, torch.Tensor], out_dim: int,
-              want_pooled: bool = False, pooling: str = "mean", pre: Optional[Dict[str, torch.Tensor]] = None):
+              want_pooled: bool = False, pooling: str = "mean", pre: Optional[Dict[str, torch.Tensor]] = None,
+              nonfinite: Optional[torch.Tensor] = None):
     """get_pooling_layer + decoder (Models/BuckGNN.py:246-307, 515-516)."""
     dev = x.data.device
     g = idx.n_graphs
@@ -425,7 +434,7 @@ def pool_head(x: Activation, idx: GraphIndex, dec: Dict[str, torch.Tensor], out_
                        _p(pre["w"]) if pre else None, _p(pre["b"]) if pre else None,
                        dec["w1"].data_ptr(), dec["b1"].data_ptr(), dec["w2"].data_ptr(), dec["b2"].data_ptr(),
                        dec["w3"].data_ptr(), dec["b3"].data_ptr(), out_dim, pred.data_ptr(), _p(pooled),
-                       ws.data_ptr(), ws_bytes, _stream())
+                       ws.data_ptr(), ws_bytes, _stream(), nonfinite=_p(nonfinite))
     return pred, pooled
 
 

@@ -342,22 +342,45 @@ class BuckGNN(nn.Module):
             return pred, batch
         return pred.squeeze(), batch
 
+    def _new_nonfinite_flag(self, device):
+        """Device word the 16-bit kernels raise when a value does not fit their storage format (bg_encoder_front);
+        bg_pool_head turns it into NaN predictions.  Kept on the module for `check_finite()`."""
+        self._nonfinite = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._nonfinite
+
+    def check_finite(self) -> None:
+        """Raises FloatingPointError if the last eval-mode forward met activations its 16-bit storage format cannot
+        hold (synchronises; the forward itself reports the condition as NaN predictions without a sync)."""
+        target = self._wide.twin if self._wide is not None else self
+        flag = getattr(target, "_nonfinite", None)
+        if flag is not None and int(flag.item()) != 0:
+            raise FloatingPointError(f"buckgnn_b200: activations left the range of precision={target.precision!r} storage "
+                                     "(encoder hidden layer); run this checkpoint with precision='tf32' or 'fp32'")
+
     def _begin_graph_index(self, edge_index, batch, n):
-        """Returns an object with .finish() -> GraphIndex (cached index when cache_index is on)."""
+        """Returns an object with .finish() -> GraphIndex (cached index when cache_index is on).
+
+        `cache_index=True` reuses the CSR while the caller passes THE SAME tensor objects, unmodified: the key is the
+        identity of `edge_index` / `batch` (held through weak references, so a recycled id or a recycled allocator
+        address cannot alias a dead tensor) plus their version counters.  A new tensor with equal contents rebuilds."""
         if self.cache_index:
-            key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape),
-                   None if batch is None else (batch.data_ptr(), batch._version), n)
-            if self._index_cache is not None and self._index_cache[0] == key:
-                cached = self._index_cache[1]
+            import weakref
+            c = self._index_cache
+            if (c is not None and c["ei"]() is edge_index and c["ei_v"] == edge_index._version and c["n"] == n
+                    and ((batch is None and c["b"] is None) or
+                         (batch is not None and c["b"] is not None and c["b"]() is batch and c["b_v"] == batch._version))):
+                cached = c["idx"]
                 return type("Cached", (), {"finish": staticmethod(lambda: cached)})
             pending = engine.begin_graph_index(edge_index, batch, n)
             outer = self
+            entry = {"ei": weakref.ref(edge_index), "ei_v": edge_index._version, "n": n,
+                     "b": None if batch is None else weakref.ref(batch), "b_v": None if batch is None else batch._version}
 
             class _Fill:
                 @staticmethod
                 def finish():
                     idx = pending.finish()
-                    outer._index_cache = (key, idx)
+                    outer._index_cache = dict(entry, idx=idx)
                     return idx
             return _Fill
         return engine.begin_graph_index(edge_index, batch, n)
@@ -374,14 +397,15 @@ class BuckGNN(nn.Module):
         # GraphNetBlock aggregates on row = edge_index[0] (:553,561) -> CSR keyed by row 0
         pending = engine.begin_graph_index(edge_index, batch, n, key_row=0)
         cur = Activation(n, 512, prec, x.device)
-        engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg)                 # :323
+        flag = self._new_nonfinite_flag(x.device)
+        engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg, nonfinite=flag)  # :323
         idx = pending.finish()
         ne = idx.n_edges
         ex = engine.edge_extras(idx, prec)
         e = Activation(max(ne, 1), 512, prec, x.device)
         if ne > 0:                                   # edge_encoder on edge_attr in CSR order (:327, :376)
             engine.encoder_forward(edge_attr, packs["edge_enc"], packs["edge_enc_w3"], prec, e, cg,
-                                   row_gather=idx.perm[:ne])
+                                   row_gather=idx.perm[:ne], nonfinite=flag)
         buf = engine.GNBlockBuffers(n, ne, prec, x.device)
         L = self.num_layers
         for i, w in enumerate(packs["gn"]):
@@ -392,7 +416,8 @@ class BuckGNN(nn.Module):
         if node_level:
             return engine.node_head(cur, n, packs["node_head"], self.output_dim, cg)
         pre = packs["pool_mlp"] if self.pooling_layer in ("mlp", "mlp_no_super") else None
-        pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim, pooling=self.pooling_layer, pre=pre)
+        pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim, pooling=self.pooling_layer, pre=pre,
+                                   nonfinite=flag)
         return pred
 
     def _forward_cuda(self, x, edge_index, batch, node_level=False):
@@ -404,10 +429,11 @@ class BuckGNN(nn.Module):
         cur = Activation(n, 512, prec, x.device)
         layers = packs["layers"]
         folded = packs["layer0_folded"]
+        flag = self._new_nonfinite_flag(x.device)
         if folded is not None:
-            h = engine.encoder_hidden(x, packs["enc"], prec)          # reference :323, first two Linears
+            h = engine.encoder_hidden(x, packs["enc"], prec, nonfinite=flag)          # reference :323, first two Linears
         else:
-            engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg)      # reference :323
+            engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg, nonfinite=flag)      # reference :323
         idx = pending.finish()                                        # host sync hidden behind the encoder
         if layers:
             nxt = Activation(n, 512, prec, x.device)
@@ -426,7 +452,7 @@ class BuckGNN(nn.Module):
             return engine.node_head(cur, n, packs["node_head"], self.output_dim, cg)     # reference :518-524
         pre = packs["pool_mlp"] if self.pooling_layer in ("mlp", "mlp_no_super") else None
         pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim, pooling=self.pooling_layer,
-                                   pre=pre)                                                # reference :515-516
+                                   pre=pre, nonfinite=flag)                                # reference :515-516
         return pred
 
     # ------------------------------------------------------------------ SAGPooling variants

@@ -122,7 +122,7 @@ class PipelinedInference:
         for off in range(0, n, 256):          # 4-byte words, at most 256 per call
             capi.publish_words(flat.data_ptr() + 4 * off, host.data_ptr() + 4 * off, min(256, n - off), s)
         ev = torch.cuda.Event()
-        ev.record()
+        ev.record(torch.cuda.current_stream(self.device))     # the stream the publish kernels were queued on
         self._keep = flat                     # alive until the next call's kernels are queued behind it
         return ev
 

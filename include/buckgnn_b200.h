@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 7
+#define BG_ABI_VERSION 8
 
 typedef enum bg_status {
   BG_OK = 0,
@@ -108,10 +108,12 @@ int bg_graph_ptr_build(const int64_t* batch, int64_t n_nodes, int64_t n_graphs, 
  *    h = relu(relu(x W1^T + b1) W2^T + b2),  x [N,F] f32 -> h [N,128] (out_dtype)
  * W1 [64,F], W2 [128,64] f32 row-major (out,in) as in nn.Linear.  F <= 32.
  * row_gather (optional, DEVICE [N] int32): output row i is computed from input row row_gather[i]
- * (the edge encoder reads `edge_attr` through the CSR permutation this way). */
+ * (the edge encoder reads `edge_attr` through the CSR permutation this way).
+ * nonfinite_flag (optional, DEVICE int32): OR-ed with 1 when a 16-bit output cannot hold a value of h (fp16: above
+ * 65504, or NaN) -- h is the one activation stored before any normalisation; pass the same word to bg_pool_head. */
 int bg_encoder_front(const float* x, int64_t n_nodes, int32_t n_features,
                      const float* w1, const float* b1, const float* w2, const float* b2,
-                     const int32_t* row_gather, void* out, int out_dtype, void* stream);
+                     const int32_t* row_gather, void* out, int out_dtype, int32_t* nonfinite_flag, void* stream);
 
 /* ------------------------------------------------------------------ K2: neighbourhood aggregation
  * Replaces `x[src]` gather + `scatter_add_` + divide inside SAGEConv.propagate:
@@ -204,7 +206,9 @@ int bg_wgrad512(const void* dz, int64_t ld_dz, const void* act, int32_t act_cols
  * allowed with the two mean modes only.  Then decoder Linear(in,128) ReLU Linear(128,64) ReLU
  * Linear(64,out_dim), in = 1024 for SUPERNODE_WITH_POOLING else 512; all weights f32, nn.Linear layout.
  * x [N,512] of `dtype`; pred [G,out_dim] f32; pooled_out [G,in] f32 optional (NULL to skip).
- * workspace from bg_pool_workspace_bytes(G). */
+ * workspace from bg_pool_workspace_bytes(G).
+ * nonfinite_flag (optional, DEVICE int32): when the word is non-zero at kernel time every prediction is written as
+ * NaN (an upstream kernel overflowed its 16-bit storage: fail loudly, without a host sync). */
 typedef enum bg_pool_mode {
   BG_POOL_MEAN = 0, BG_POOL_MEAN_NO_SUPER = 1, BG_POOL_SUPERNODE_ONLY = 2, BG_POOL_SUPERNODE_WITH_POOLING = 3
 } bg_pool_mode;
@@ -214,15 +218,16 @@ int bg_pool_head(const void* x, int dtype, int64_t n_nodes, const int32_t* graph
                  const float* w1, const float* b1, const float* w2, const float* b2,
                  const float* w3, const float* b3, int32_t out_dim,
                  float* pred, float* pooled_out,
-                 void* workspace, size_t workspace_bytes, void* stream);
+                 void* workspace, size_t workspace_bytes, const int32_t* nonfinite_flag, void* stream);
 
 /* ------------------------------------------------------------------ EA-GNN helpers
  * bg_expand_rowptr: row_of[i] = r with rowptr[r] <= i < rowptr[r+1], iota[i] = i   (i < E)
  *   (row ids of the CSR slots, and the identity "col" that turns bg_sage_aggregate into the
  *   segmented mean torch_scatter.scatter_mean(messages, row) needs once edges are in CSR order);
  *   row_of / iota may be NULL.
- *   nonempty (optional, [n_rows, 64] of nonempty_dtype): column 0 = 1 for rows with >= 1 entry (or the
- *   entry count when as_count != 0), rest 0 --
+ *   nonempty (optional, [n_rows, 64] of nonempty_dtype): column 0 = 1 for rows with >= 1 entry, rest 0;
+ *   with as_count != 0 columns 0..2 hold the row's entry count as base-256 digits (count = c0 + 256 c1 + 65536 c2:
+ *   each digit is exact in bf16 / fp16 / tf32, a super node's degree is not) --
  *   a K = 64 GEMM segment that applies a bias only to rows whose scatter_mean segment is non-empty
  *   (what remains of phi's second-layer bias after that Linear is folded through the mean).
  * bg_add: out = a + b (+ c) elementwise over n values of `dtype`, fp32 math (skip connections

@@ -106,13 +106,21 @@ def test_cached_index_reuses_csr():
     b = make_batch(2, nx=9, ny=8).to(DEV)
     with torch.no_grad():
         p1, _ = ours(b.x, b.edge_index, b.edge_attr, b.batch)
-        first = ours._index_cache[1]
+        first = ours._index_cache["idx"]
         p2, _ = ours(b.x, b.edge_index, b.edge_attr, b.batch)
-        assert ours._index_cache[1] is first
+        assert ours._index_cache["idx"] is first
         b.edge_index.add_(0)                      # version bump -> rebuilt
         p3, _ = ours(b.x, b.edge_index, b.edge_attr, b.batch)
-        assert ours._index_cache[1] is not first
+        second = ours._index_cache["idx"]
+        assert second is not first
+        # a DIFFERENT tensor object of the same shape (what a loader loop produces, possibly at a recycled address)
+        # must never be served the previous CSR: the key is the tensor's identity, not its address
+        other = make_batch(2, nx=9, ny=8, first_index=7).to(DEV)
+        p4, _ = ours(other.x, other.edge_index, other.edge_attr, other.batch)
+        assert ours._index_cache["idx"] is not second
+        want4, _ = ref(*(t.cpu() for t in (other.x, other.edge_index, other.edge_attr, other.batch)))
     assert torch.equal(p1, p2) and torch.equal(p1, p3)
+    _assert_rel(p4.cpu(), want4, 1e-3)
 
 
 def test_single_graph_batch_none_gives_0dim():
