@@ -405,7 +405,7 @@ class SageTrainFunction(torch.autograd.Function):
         sv.node_level = is_node_level(model)
         pred = node_head_forward_train(model, cur, sv) if sv.node_level else head_forward_train(model, cur, idx, sv)
         ctx.sv = sv
-        ctx.params = params
+        ctx.params = trainable_parameters(model)      # the module's own parameters key the GradStore (the inputs may be embeddings, narrow.py)
         return pred
 
     @staticmethod
@@ -597,7 +597,7 @@ class SagTrainFunction(torch.autograd.Function):
             sv.second.append(saved)
         pred = head_forward_train(model, cur, idx2, sv)
         ctx.sv = sv
-        ctx.params = params
+        ctx.params = trainable_parameters(model)      # the module's own parameters key the GradStore (the inputs may be embeddings, narrow.py)
         return pred
 
     @staticmethod

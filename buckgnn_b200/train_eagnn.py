@@ -25,7 +25,7 @@ from . import capi, engine
 from .engine import Activation, _stream
 from .train import (GradStore, _Saved, _f32, colsum, encoder_backward, encoder_forward_train, head_backward,
                     head_forward_train, is_node_level, layer_seed, node_head_backward, node_head_forward_train,
-                    transposed_pack, weight_grad_mn)
+                    trainable_parameters, transposed_pack, weight_grad_mn)
 
 _H = 512
 
@@ -287,7 +287,7 @@ class EAGNNTrainFunction(torch.autograd.Function):
         sv.node_level = is_node_level(model)
         pred = node_head_forward_train(model, cur, sv) if sv.node_level else head_forward_train(model, cur, idx, sv)
         ctx.sv = sv
-        ctx.params = params
+        ctx.params = trainable_parameters(model)      # the module's own parameters key the GradStore (the inputs may be embeddings, narrow.py)
         return pred
 
     @staticmethod
@@ -368,7 +368,7 @@ class EAGNNSagTrainFunction(torch.autograd.Function):
         sv.idx = idx2                                   # head_backward reads sv.idx.graph_ptr
         pred = head_forward_train(model, cur, idx2, sv)
         ctx.sv = sv
-        ctx.params = params
+        ctx.params = trainable_parameters(model)      # the module's own parameters key the GradStore (the inputs may be embeddings, narrow.py)
         return pred
 
     @staticmethod
