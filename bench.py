@@ -184,6 +184,105 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def modes_section(args, dev, resident, world, G, barrier):
+    """The other operand modes on the same workload (north_star: rtol 1e-4 in an fp32-GEMM mode): graphs/s over a few steps."""
+    import torch
+    import torch.distributed as dist
+    from buckgnn_b200.model import BuckGNN
+    ref = _oracle_model()
+    out = {}
+    for mode in ("tf32", "fp32"):
+        m = BuckGNN(**MODEL_CFG, precision=mode, cta_group=args.cta_group)
+        m.load_state_dict(ref.state_dict())
+        m = m.to(dev).eval()
+        with torch.no_grad():
+            for _ in range(2):
+                m(resident.x, resident.edge_index, resident.edge_attr, resident.batch)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = max(2, min(args.steps, 5))
+            e0.record()
+            for _ in range(n):
+                m(resident.x, resident.edge_index, resident.edge_attr, resident.batch)
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        out[mode] = {"graphs_per_s": world * G / (ms * 1e-3), "ms_per_step": ms, "steps": n,
+                     "what": "fp32 storage, tf32 operands" if mode == "tf32" else "fp32-GEMM mode (3xTF32 split operands)"}
+        del m
+    return out
+
+
+def train_section(args, dev, world, rank, barrier):
+    """BASELINE.json configs[3]: TRAIN_FINAL-style training step, GraphSage_meanAggr 6x512, 16 graphs per GPU, dropout
+    0.1, relative-error loss, Adam; graph-sharded, gradients all-reduced (mean) over NCCL bucket by bucket under the
+    backward pass (dist.GradSync).  `allreduce_exposed_ms` = step time with the collectives - step time without them."""
+    import torch
+    import torch.distributed as dist
+    from buckgnn_b200.loss import EigenvalueRelativeLoss
+    from buckgnn_b200.model import BuckGNN
+    from buckgnn_b200.synth import config_batch
+    torch.manual_seed(0)                                    # same initial weights on every rank
+    cfg = dict(MODEL_CFG, dropout_rate=0.1)
+    model = BuckGNN(**cfg, train_precision=args.train_precision).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    b = config_batch(3, rank=rank, num_graphs=16).to(dev)
+    y = b.y.abs() + 0.5
+    crit = EigenvalueRelativeLoss(scale=1.0, center=0.0)
+    sync = model.enable_gradient_sync() if world > 1 else None
+    steps = max(3, min(args.steps, 20))
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        pred, _ = model(b.x, b.edge_index, b.edge_attr, b.batch)
+        loss = crit(pred, y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timed(n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            last = step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, float(last.detach())
+
+    for _ in range(3):
+        first = step()
+    ms, loss_last = timed(steps)
+    out = {"config": f"BASELINE.json configs[3]: training step GraphSage_meanAggr 6x512, 16 graphs per GPU, dropout 0.1, Adam, "
+                     f"graph-sharded x{world}", "train_precision": args.train_precision, "ms_per_step": ms, "steps": steps,
+           "graphs_per_s": world * 16 / (ms * 1e-3), "nodes_per_gpu": b.num_nodes, "loss_first": float(first.detach()),
+           "loss_last": loss_last}
+    if sync is not None:
+        sync.time_collectives = True                        # one instrumented step: device time of every collective
+        step()
+        torch.cuda.synchronize()
+        out["allreduce_ms"] = sum(a.elapsed_time(c) for a, c in sync.events)
+        out["allreduce_buckets"] = len(sync.events)
+        out["allreduce_elements"] = int(sync.flat.numel())
+        sync.time_collectives = False
+        model._grad_sync = None                             # the same steps without any collective (ranks diverge: timing only)
+        step()
+        ms_local, _ = timed(steps)
+        out["ms_per_step_without_allreduce"] = ms_local
+        out["allreduce_exposed_ms"] = ms - ms_local
+        out["allreduce"] = "per-layer buckets of one flat fp32 buffer, ncclAllReduce(avg) on a second stream under the backward"
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -266,9 +365,14 @@ def run_b200(args):
     # batch, y, ptr: everything `batch.to(device)` moves) and reads pred back D->H.  The copies of
     # step i+1 run on a second stream while step i computes, and the result of step i reaches the host while
     # step i+1 computes (buckgnn_b200.pipeline.PipelinedInference); every result is on the host inside the clock.
-    from buckgnn_b200.pipeline import PipelinedInference
-    h2d = sum(t.numel() * t.element_size() for t in (host.x, host.edge_index, host.edge_attr, host.batch,
-                                                      host.y, host.ptr))
+    from buckgnn_b200.pipeline import PipelinedInference, WireBatch
+    h2d_full = sum(t.numel() * t.element_size() for t in (host.x, host.edge_index, host.edge_attr, host.batch,
+                                                           host.y, host.ptr))
+    # GraphSAGE never reads edge_attr / y / ptr, and the super node's hub pairs (1/3 of edge_index) follow from the node
+    # offsets: the loader hands the pipeline the compact wire format (x, explicit edges as int32, three offset vectors)
+    # and bg_expand_wire rebuilds the exact PyG tensors on the device (tests/test_gpu_kernels.py)
+    wire = WireBatch.from_batch(host).pin_memory()
+    h2d = wire.nbytes()
     copy_ms, fwd_dev_ms, stamps = [], [], []
     # the loop object is created once (as an inference service would): its two device-side staging batches and its
     # pinned result buffers are set up by the warm-up pass, not inside the timed region
@@ -287,7 +391,7 @@ def run_b200(args):
         pipe.prefetcher.copy_events = []
         seen = 0
         stamps[:] = [time.perf_counter()]
-        for step, pred_host in pipe.run(host for _ in range(n)):   # pred_host: this step's eigenvalues, on the host
+        for step, pred_host in pipe.run(wire for _ in range(n)):   # pred_host: this step's eigenvalues, on the host
             outs = pred_host
             seen += 1
             stamps.append(time.perf_counter())
@@ -324,6 +428,11 @@ def run_b200(args):
     resident_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     del store
     barrier()
+
+    modes = None if args.no_extras else modes_section(args, dev, resident, world, G, barrier)
+    del resident
+    torch.cuda.empty_cache()
+    train_info = None if args.no_extras else train_section(args, dev, world, rank, barrier)
 
     # ---- max over ranks
     if world > 1:
@@ -391,13 +500,17 @@ def run_b200(args):
                        "parallelism": f"graph-sharded x{world}, no data-path collective",
                        "parity_rel_err_vs_oracle_sample": rel_err},
             "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "h2d_bytes_full_pyg_batch": h2d_full,
+                    "wire_format": "x f32 + explicit edges int32 + node/edge offsets; hub pairs, batch vector and int64 "
+                                   "widening rebuilt on the device (bg_expand_wire); edge_attr / y / ptr are never read by "
+                                   "GraphSAGE and stay on the host",
                     "d2h_bytes_per_step": int(out.numel() * out.element_size()),
                     "ms_per_step_without_h2d": sync_only_ms,
                     "ms_per_step_device_collate": resident_ms,      # DeviceGraphStore.batch() + forward + pred.cpu()
                     "h2d_copy_ms_overlapped": sorted(copy_ms)[len(copy_ms) // 2] if copy_ms else None,
                     "forward_device_ms_under_copy": sorted(fwd_dev_ms)[len(fwd_dev_ms) // 2] if fwd_dev_ms else None,
                     "result_arrival_intervals_ms": [round((b_ - a_) * 1e3, 3) for a_, b_ in zip(stamps, stamps[1:])],
-                    "how": "buckgnn_b200.pipeline.PipelinedInference: pinned host batch -> H2D of step i+1 on a copy stream "
+                    "how": "buckgnn_b200.pipeline.PipelinedInference: pinned host batch (wire format) -> H2D of step i+1 on a copy stream "
                            "during step i -> model(...) -> eigenvalues of every step read back to pinned host memory "
                            "(one step late, so the GPU never waits for the host); host wall clock over the timed "
                            "steps, all K results on the host before the clock stops"},
@@ -408,6 +521,8 @@ def run_b200(args):
             "csr_cache_warm": {"value": world * G / (cached_ms * 1e-3), "unit": "graphs/s", "ms_per_step": cached_ms,
                                "how": "cache_index=True: the CSR of an unchanged edge_index tensor is reused"},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kernel_ms.items()},
+            "modes": modes,
+            "train": train_info,
             "peaks": peaks,
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
@@ -427,6 +542,8 @@ def main():
     ap.add_argument("--cta-group", type=int, default=2)
     ap.add_argument("--graphs", type=int, default=GRAPHS_PER_RANK)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the tf32 / fp32 modes and the training-step section")
+    ap.add_argument("--train-precision", default="tf32")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "bg_expand_rowptr", "bg_add",
     "bg_train_workspace_bytes", "bg_bn_batch_stats", "bg_bn_act_forward", "bg_sage_backward_rows",
     "bg_transpose_chunks", "bg_mask_narrow", "bg_reduce_partials", "bg_colsum_workspace_bytes", "bg_colsum", "bg_pool_backward",
-    "bg_sgemm_workspace_bytes", "bg_sgemm", "bg_eigen_loss", "bg_dropout_mask", "bg_collate_ptr", "bg_collate",
+    "bg_sgemm_workspace_bytes", "bg_sgemm", "bg_eigen_loss", "bg_dropout_mask", "bg_collate_ptr", "bg_collate", "bg_expand_wire",
     "bg_dropout_residual", "bg_grad_mask", "bg_segment_expand",
     "bg_sag_workspace_bytes", "bg_sag_select", "bg_sag_connect", "bg_gather_rows", "bg_index_invert", "bg_index_gather",
     "bg_sag_pool_backward", "bg_max_aggregate_backward", "bg_max_bwd_workspace_bytes",
@@ -109,6 +109,7 @@ _SIGNATURES = {
     "bg_grad_mask": (C.c_int, [_P, _P, _P, _P, C.c_int, _I64, C.c_float, C.c_uint64, _P]),
     "bg_segment_expand": (C.c_int, [_P, _P, _I64, C.c_int, _P, C.c_int, _P]),
     "bg_collate_ptr": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
+    "bg_expand_wire": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _I64, _P, _P, _P]),
     "bg_collate": (C.c_int, [_P, _I32, _P, _I64, _P, _I32, _P, _P, _I64, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "bg_eigen_loss": (C.c_int, [_P, _P, _I64, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P]),
     "bg_sag_workspace_bytes": (C.c_int, [_I64, _I64, _I64, _SZP]),
@@ -342,6 +343,11 @@ def collate(x_all, n_features, ei_all, e_all, ea_all, n_edge_features, y_all, se
     _check(load().bg_collate(x_all, n_features, ei_all, e_all, ea_all, n_edge_features, y_all, sel, n_graphs, node_ptr,
                              edge_ptr, out_node_ptr, out_edge_ptr, n_out, e_out, x, edge_index, edge_attr, batch, y,
                              stream), "bg_collate")
+
+
+def expand_wire(wire_edges, e_wire, node_ptr, wire_ptr, full_ptr, n_graphs, e_full, edge_index, batch, stream):
+    _check(load().bg_expand_wire(wire_edges, e_wire, node_ptr, wire_ptr, full_ptr, n_graphs, e_full, edge_index, batch,
+                                 stream), "bg_expand_wire")
 
 
 def wgrad512(dz, ld_dz, act, act_cols, ld_act, dtype, n_rows, n_chunks, chunk_k, partial, stream):

@@ -110,6 +110,33 @@ __global__ void k_publish_words(const int32_t* __restrict__ src, volatile int32_
   __threadfence_system();
 }
 
+
+// Compact wire format of an inference batch -> the PyG layout `BuckGNN.forward` takes (pipeline.py: WireBatch).
+// One CTA per graph (grid-stride): its explicit edges int32 -> int64, then -- for graphs whose super node is implicit --
+// the hub pairs (s, i), (i, s) for i = first node .. s-1 in order, exactly where `create_super_node`
+// (reference Dataset_Preparation/VirtualEdgeCreate.py:106-111) appends them; and the `batch` id of its nodes.
+__global__ void __launch_bounds__(256)
+k_expand_wire(const int32_t* __restrict__ wire_edges, int64_t E_wire, const int64_t* __restrict__ node_ptr,
+              const int64_t* __restrict__ wire_ptr, const int64_t* __restrict__ full_ptr, int64_t G, int64_t E_full,
+              int64_t* __restrict__ edge_index, int64_t* __restrict__ batch) {
+  for (int64_t g = blockIdx.x; g < G; g += gridDim.x) {
+    const int64_t n0 = node_ptr[g], n1 = node_ptr[g + 1];
+    const int64_t w0 = wire_ptr[g], w1 = wire_ptr[g + 1];
+    const int64_t f0 = full_ptr[g], f1 = full_ptr[g + 1];
+    for (int64_t i = threadIdx.x; i < w1 - w0; i += blockDim.x) {
+      edge_index[f0 + i] = (int64_t)wire_edges[w0 + i];
+      edge_index[E_full + f0 + i] = (int64_t)wire_edges[E_wire + w0 + i];
+    }
+    const int64_t hub_pairs = ((f1 - f0) - (w1 - w0)) / 2;          // 0, or n_g - 1: an implicit super node
+    const int64_t s = n1 - 1, base = f0 + (w1 - w0);
+    for (int64_t i = threadIdx.x; i < hub_pairs; i += blockDim.x) {
+      edge_index[base + 2 * i] = s;              edge_index[E_full + base + 2 * i] = n0 + i;
+      edge_index[base + 2 * i + 1] = n0 + i;     edge_index[E_full + base + 2 * i + 1] = s;
+    }
+    for (int64_t i = n0 + threadIdx.x; i < n1; i += blockDim.x) batch[i] = g;
+  }
+}
+
 static inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
   int64_t b = ceil_div64(n > 0 ? n : 1, threads);
@@ -1069,6 +1096,19 @@ int bg_collate(const float* x_all, int32_t F, const int64_t* ei_all, int64_t E_a
     k_collate_y<<<(unsigned)ceil_div64(G, 256), 256, 0, stream>>>(y_all, sel, G, y);
     BG_LAUNCH_OK();
   }
+  return BG_OK;
+}
+
+int bg_expand_wire(const int32_t* wire_edges, int64_t E_wire, const int64_t* node_ptr, const int64_t* wire_ptr,
+                   const int64_t* full_ptr, int64_t G, int64_t E_full, int64_t* edge_index, int64_t* batch, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (G < 0 || E_wire < 0 || E_full < E_wire || (G > 0 && (!node_ptr || !wire_ptr || !full_ptr || !batch)) ||
+      (E_full > 0 && !edge_index) || (E_wire > 0 && !wire_edges))
+    return fail(BG_ERR_INVALID, "bg_expand_wire: bad argument");
+  if (G == 0) return BG_OK;
+  k_expand_wire<<<(unsigned)min64(G, (int64_t)sm_count() * 8), 256, 0, stream>>>(wire_edges, E_wire, node_ptr, wire_ptr, full_ptr, G,
+                                                                               E_full, edge_index, batch);
+  BG_LAUNCH_OK();
   return BG_OK;
 }
 

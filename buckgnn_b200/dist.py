@@ -87,3 +87,92 @@ def allreduce_gradients(params, group=None, average: bool = True) -> int:
         g.copy_(flat[off:off + n].view_as(g).to(g.dtype))
         off += n
     return off
+
+
+class GradSync:
+    """Bucketed gradient all-reduce that overlaps the backward pass (BASELINE.json configs[3]).
+
+    All gradients of the parameters a model trains live in ONE pre-allocated fp32 buffer, laid out in
+    `train.trainable_parameters(model)` order; the backward kernels write straight into its slices (no `torch.cat`,
+    no copy back).  As soon as the backward has finished the gradients of a group of parameters -- the head, then
+    layer L-1 ... layer 0, then the encoder -- `launch()` records an event on the compute stream and starts the
+    all-reduce (mean) of that group's slice on a communication stream, so it runs under the backward kernels of the
+    earlier layers; `finish()` makes the compute stream wait for the collectives at the end of the backward (only the
+    last, smallest bucket is exposed).  Per-rank BatchNorm statistics stay local.
+
+    Install with `model.enable_gradient_sync()`; `allreduce_gradients` afterwards is not needed.  Works on gloo
+    (CPU tensors, no streams) for the world-size-2 tests."""
+
+    def __init__(self, params, device, group=None):
+        self.group = group
+        self.params = list(params)
+        self.offsets, off = {}, 0
+        for p in self.params:
+            self.offsets[id(p)] = (off, p.numel(), tuple(p.shape))
+            off += (p.numel() + 3) // 4 * 4                      # 16-byte aligned slices
+        self.flat = torch.zeros(max(off, 1), dtype=torch.float32, device=device)
+        self.cuda = self.flat.is_cuda
+        self.comm_stream = torch.cuda.Stream(device=device) if self.cuda else None
+        self.works, self.launched = [], set()
+        self.events = []          # (start, end) CUDA events of every collective of the last step (timing)
+        self.time_collectives = False
+
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def view(self, param):
+        o = self.offsets.get(id(param))
+        if o is None:
+            return None
+        off, n, shape = o
+        return self.flat[off:off + n].view(shape)
+
+    def begin_step(self) -> None:
+        self.works, self.launched, self.events = [], set(), []
+
+    def launch(self, params) -> None:
+        """The gradients of `params` are final: all-reduce their slice(s), contiguous runs merged."""
+        spans = []
+        for p in params:
+            o = self.offsets.get(id(p))
+            if o is None or id(p) in self.launched:
+                continue
+            self.launched.add(id(p))
+            spans.append((o[0], o[0] + (o[1] + 3) // 4 * 4))
+        if not spans or self.world() == 1:
+            return
+        spans.sort()
+        merged = [list(spans[0])]
+        for a, b in spans[1:]:
+            if a == merged[-1][1]:
+                merged[-1][1] = b
+            else:
+                merged.append([a, b])
+        avg = dist.ReduceOp.AVG if self.cuda else dist.ReduceOp.SUM      # gloo has no AVG
+        if self.cuda:
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ready)
+                for a, b in merged:
+                    if self.time_collectives:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                    self.works.append(dist.all_reduce(self.flat[a:b], op=avg, group=self.group, async_op=True))
+                    if self.time_collectives:
+                        self.works[-1].wait()                         # comm stream waits (not the host, not compute)
+                        e1.record()
+                        self.events.append((e0, e1))
+        else:
+            for a, b in merged:
+                dist.all_reduce(self.flat[a:b], op=avg, group=self.group)
+                self.flat[a:b] /= self.world()
+
+    def finish(self) -> None:
+        """End of the backward: everything not launched yet goes now, then the compute stream waits for all of it."""
+        self.launch(self.params)
+        if self.cuda:
+            for w in self.works:
+                w.wait()                                              # current (compute) stream waits for the collective
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.works = []

@@ -348,6 +348,18 @@ class BuckGNN(nn.Module):
         self._nonfinite = torch.zeros(1, dtype=torch.int32, device=device)
         return self._nonfinite
 
+    def enable_gradient_sync(self, group=None):
+        """Multi-GPU training (BASELINE.json configs[3]): all-reduce (mean) the gradients of this model's trainable
+        parameters over `group`, bucketed per layer and overlapped with the backward pass (dist.GradSync).  Call once
+        after `.to(device)`, on every rank; `loss.backward()` then leaves the REDUCED gradients in `.grad`."""
+        if self.hidden_channels != 512:
+            raise NotImplementedError("buckgnn_b200: overlapped gradient sync is built for hidden_channels=512; "
+                                      "use dist.allreduce_gradients(model.parameters()) after backward() instead")
+        from . import train
+        from .dist import GradSync
+        self._grad_sync = GradSync(train.trainable_parameters(self), next(self.parameters()).device, group)
+        return self._grad_sync
+
     def check_finite(self) -> None:
         """Raises FloatingPointError if the last eval-mode forward met activations its 16-bit storage format cannot
         hold (synchronises; the forward itself reports the condition as NaN predictions without a sync)."""

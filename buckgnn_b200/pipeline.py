@@ -13,8 +13,93 @@ from typing import Callable, Iterable, Iterator, Optional
 
 import torch
 
+from dataclasses import dataclass
+
 from . import capi
 from .synth import PlateBatch
+
+
+@dataclass
+class WireBatch:
+    """Host-side wire format of an inference batch for models that never read `edge_attr` (every GraphSAGE variant):
+    what has to cross PCIe, and nothing else.
+
+    * `x` [N, F] f32 -- as in the PyG batch;
+    * `edges` [2, E_wire] int32 -- the explicit edges only, global node ids (a batch has < 2^31 nodes).  The super
+      node's hub pairs (s, i), (i, s) -- a third of all directed edges -- are implicit: `create_super_node` appends
+      them after a graph's mesh edges in a fixed order (reference Dataset_Preparation/VirtualEdgeCreate.py:106-111), so
+      the device rebuilds them from the node offsets;
+    * `node_ptr`, `wire_ptr`, `full_ptr` [G+1] int64 -- node offsets, offsets into `edges`, offsets into the full
+      PyG `edge_index`; the `batch` vector is rebuilt from `node_ptr`.
+    `edge_attr`, `y` and `ptr` stay on the host.  `bg_expand_wire` turns this into the exact tensors
+    `batch.to(device)` would have produced (tests/test_gpu_kernels.py), 98 MB instead of 294 MB for 256 plates."""
+    x: torch.Tensor
+    edges: torch.Tensor
+    node_ptr: torch.Tensor
+    wire_ptr: torch.Tensor
+    full_ptr: torch.Tensor
+    num_graphs: int
+    num_nodes: int
+    num_edges: int            # of the full PyG edge_index
+    edge_features: int
+
+    FIELDS = ("x", "edges", "node_ptr", "wire_ptr", "full_ptr")
+
+    @staticmethod
+    def from_batch(b: PlateBatch) -> "WireBatch":
+        """Host-side (loader) conversion.  A graph's trailing edges are dropped from the wire only if they are EXACTLY
+        the hub pairs of its last node in the reference's order; any other graph ships all its edges."""
+        ei = b.edge_index
+        g = b.num_graphs
+        node_ptr = b.ptr.to(torch.int64)
+        E = ei.shape[1]
+        # edges are grouped by graph (PyG collate): graph of an edge = graph of its source node
+        eg = b.batch[ei[0]] if E > 0 else torch.zeros(0, dtype=torch.int64)
+        counts = torch.bincount(eg, minlength=g)
+        full_ptr = torch.zeros(g + 1, dtype=torch.int64)
+        full_ptr[1:] = torch.cumsum(counts, 0)
+        keep = torch.ones(E, dtype=torch.bool)
+        for k in range(g):
+            n0, n1 = int(node_ptr[k]), int(node_ptr[k + 1])
+            f0, f1 = int(full_ptr[k]), int(full_ptr[k + 1])
+            m = n1 - n0 - 1                                    # hub pairs if the last node is a super node
+            if m <= 0 or f1 - f0 < 2 * m:
+                continue
+            tail = ei[:, f1 - 2 * m:f1]
+            s = n1 - 1
+            others = torch.arange(n0, s)
+            if (torch.equal(tail[0, 0::2], torch.full((m,), s)) and torch.equal(tail[1, 0::2], others) and
+                    torch.equal(tail[0, 1::2], others) and torch.equal(tail[1, 1::2], torch.full((m,), s))):
+                keep[f1 - 2 * m:f1] = False
+        edges = ei[:, keep].to(torch.int32).contiguous()
+        wire_counts = torch.bincount(eg[keep], minlength=g)
+        wire_ptr = torch.zeros(g + 1, dtype=torch.int64)
+        wire_ptr[1:] = torch.cumsum(wire_counts, 0)
+        return WireBatch(b.x.to(torch.float32).contiguous(), edges, node_ptr.contiguous(), wire_ptr, full_ptr, g,
+                         b.num_nodes, E, b.edge_attr.shape[1])
+
+    def pin_memory(self) -> "WireBatch":
+        return WireBatch(*[getattr(self, f).pin_memory() for f in self.FIELDS], self.num_graphs, self.num_nodes,
+                         self.num_edges, self.edge_features)
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self.FIELDS)
+
+    def expand(self, device, out: Optional[PlateBatch] = None, stream=None) -> PlateBatch:
+        """Device-resident wire tensors (self must live on `device`) -> PyG-layout batch (edge_attr: a 0-row
+        placeholder of the right width, `y` / `ptr` as given by node_ptr)."""
+        dev = torch.device(device)
+        if out is None or out.edge_index.shape[1] != self.num_edges or out.batch.shape[0] != self.num_nodes:
+            out = PlateBatch(self.x, torch.empty((2, self.num_edges), dtype=torch.int64, device=dev),
+                             torch.empty((0, self.edge_features), dtype=torch.float32, device=dev),
+                             torch.empty(self.num_nodes, dtype=torch.int64, device=dev),
+                             torch.empty(0, dtype=torch.float32, device=dev), self.node_ptr, self.num_graphs)
+        out.x, out.ptr, out.num_graphs = self.x, self.node_ptr, self.num_graphs
+        s = (stream or torch.cuda.current_stream(dev)).cuda_stream
+        capi.expand_wire(self.edges.data_ptr(), self.edges.shape[1], self.node_ptr.data_ptr(), self.wire_ptr.data_ptr(),
+                         self.full_ptr.data_ptr(), self.num_graphs, self.num_edges, out.edge_index.data_ptr(),
+                         out.batch.data_ptr(), s)
+        return out
 
 
 class DevicePrefetcher:
@@ -38,8 +123,40 @@ class DevicePrefetcher:
         self.copy_events = []          # (start, stop) per staged batch when `time_copies` is set
         self.time_copies = False
 
-    def _stage(self, host: PlateBatch, k: int) -> PlateBatch:
+    def _stage_wire(self, host: "WireBatch", k: int) -> PlateBatch:
+        """WireBatch: copy its five tensors, then rebuild edge_index / batch on the copy stream (bg_expand_wire)."""
         slot = self.slots[k]
+        fits = (isinstance(slot, tuple) and all(getattr(slot[0], f).shape == getattr(host, f).shape for f in WireBatch.FIELDS)
+                and slot[1].edge_index.shape[1] == host.num_edges)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.released[k])
+            if not fits:
+                wire = WireBatch(*[torch.empty_like(getattr(host, f), device=self.device) for f in WireBatch.FIELDS],
+                                 host.num_graphs, host.num_nodes, host.num_edges, host.edge_features)
+                slot = (wire, None)
+            wire, full = slot
+            wire.num_graphs, wire.num_nodes, wire.num_edges = host.num_graphs, host.num_nodes, host.num_edges
+            if self.time_copies:
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record(self.copy_stream)
+            for f in WireBatch.FIELDS:
+                getattr(wire, f).copy_(getattr(host, f), non_blocking=True)
+            if self.time_copies:
+                t1 = torch.cuda.Event(enable_timing=True)
+                t1.record(self.copy_stream)
+                self.copy_events.append((t0, t1))
+            full = wire.expand(self.device, full, stream=self.copy_stream)
+            self.slots[k] = (wire, full)
+            self.core_copied[k].record(self.copy_stream)
+            self.copied[k].record(self.copy_stream)
+        return full
+
+    def _stage(self, host, k: int) -> PlateBatch:
+        if isinstance(host, WireBatch):
+            return self._stage_wire(host, k)
+        slot = self.slots[k]
+        if isinstance(slot, tuple):
+            slot = None
         fields = ("edge_index", "batch", "x", "edge_attr", "y", "ptr")
         fits = slot is not None and all(getattr(slot, f).shape == getattr(host, f).shape for f in fields)
         with torch.cuda.stream(self.copy_stream):

@@ -124,28 +124,57 @@ class _Saved:
 class GradStore:
     """fp32 gradient buffers by parameter; the second touch of a parameter (shared blocks) accumulates."""
 
-    def __init__(self, device):
-        self.device, self.bufs = device, {}
+    def __init__(self, device, sync=None):
+        """`sync` (dist.GradSync): gradients are written into slices of its flat all-reduce buffer and handed to the
+        collective group by group (`done`), overlapping the rest of the backward."""
+        self.device, self.bufs, self.sync = device, {}, sync
+        if sync is not None:
+            sync.begin_step()
+
+    def _new(self, param):
+        if self.sync is not None:
+            v = self.sync.view(param)
+            if v is not None:
+                return v
+        return _f32(tuple(param.shape), self.device)
 
     def get(self, param):
         """(buffer, accumulate?) -- the caller overwrites a fresh buffer completely."""
         t = self.bufs.get(id(param))
         fresh = t is None
         if fresh:
-            t = self.bufs[id(param)] = _f32(tuple(param.shape), self.device)
+            t = self.bufs[id(param)] = self._new(param)
         return t, not fresh
 
     def zeros(self, param):
         """A zero-initialised buffer that column slices are ADDED into."""
         t = self.bufs.get(id(param))
         if t is None:
-            t = self.bufs[id(param)] = torch.zeros(tuple(param.shape), dtype=torch.float32, device=self.device)
+            t = self.bufs[id(param)] = self._new(param)
+            t.zero_()
         return t
+
+    def done(self, params) -> None:
+        """The gradients of `params` are final (no later layer of the backward adds to them)."""
+        if self.sync is not None:
+            self.sync.launch([p_ for p_ in params if p_ is not None and id(p_) in self.bufs])
+
+    def finish(self) -> None:
+        if self.sync is not None:
+            self.sync.finish()
 
     def for_params(self, params):
         out: List[Optional[torch.Tensor]] = []
+        snap = None
+        if self.sync is not None:
+            # autograd may adopt a returned gradient as `.grad` without copying; the flat all-reduce buffer is reused by
+            # the next step, so hand out slices of a per-step snapshot instead (one copy kernel for all parameters)
+            snap = self.sync.flat.clone()
         for p_ in params:
             t = self.bufs.get(id(p_))
+            if t is not None and snap is not None and self.sync.view(p_) is not None:
+                off, n, shape = self.sync.offsets[id(p_)]
+                t = snap[off:off + n].view(shape)
             out.append(None if t is None else t.to(p_.dtype))
         return out
 
@@ -416,8 +445,12 @@ class SageTrainFunction(torch.autograd.Function):
         dev = sv.x.device
         s = _stream()
         dpred = dpred.detach().to(torch.float32).contiguous()
-        grads = GradStore(dev)
+        grads = GradStore(dev, getattr(model, "_grad_sync", None))
         dcur = (node_head_backward if sv.node_level else head_backward)(model, sv, dpred, n, prec, grads)
+        grads.done(_head_params(model))                      # decoder (+ MLPPooling): their all-reduce starts now
+        first_use = {}
+        for j, (c_, _b, *_rest) in enumerate(sv.layers):
+            first_use.setdefault(id(c_), j)                  # a shared block is final after its first (last visited) layer
         dy2: Optional[Activation] = None
 
         # ---- message passing layers, last to first
@@ -481,9 +514,13 @@ class SageTrainFunction(torch.autograd.Function):
             dx = Activation(n, 512, prec, dev)
             with engine.TIMERS.span("train_dgrad_gemm"):
                 engine.gemm512(engine._segments(dz, wrt), n, prec, dx, residual=sbuf.data.data_ptr(), ldr=512)
+            if first_use[id(conv)] == i:
+                grads.done([conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight] +
+                           ([bn.weight, bn.bias] if bn is not None else []))
             dcur, dy2 = dx, g
         # ---- encoder backward (dy2 is None here: layer 0 has no skip)
         encoder_backward(model.node_encoder, sv.x, sv.h1, sv.h2, dcur, prec, grads)
+        grads.finish()
         ctx.sv = None
         return (None, None, None, None, None, *grads.for_params(ctx.params))
 
@@ -608,7 +645,7 @@ class SagTrainFunction(torch.autograd.Function):
         dev = sv.x.device
         s = _stream()
         F32 = capi.BG_F32
-        grads = GradStore(dev)
+        grads = GradStore(dev, getattr(model, "_grad_sync", None))
         pooled, idx2 = sv.pooled, sv.idx
         n2 = pooled.n_nodes
         dcur = head_backward(model, sv, dpred.detach().to(torch.float32).contiguous(), n2, prec, grads)
@@ -641,8 +678,19 @@ class SagTrainFunction(torch.autograd.Function):
         for saved in reversed(sv.first):
             dcur = _sag_layer_backward(saved, dcur, sv.idx_full, idx_t, prec, sv.p_drop, grads, ws, ws_bytes)
         encoder_backward(model.node_encoder, sv.x, sv.h1, sv.h2, dcur, prec, grads)
+        grads.finish()
         ctx.sv = None
         return (None, None, None, None, None, *grads.for_params(ctx.params))
+
+
+def _head_params(model):
+    ps = []
+    if model.pooling_layer in ("mlp", "mlp_no_super") and not is_node_level(model):
+        ps += [model.pooling_mpl.mlp[0].weight, model.pooling_mpl.mlp[0].bias]
+    for m in model.decoder:
+        if isinstance(m, torch.nn.Linear):
+            ps += [m.weight, m.bias]
+    return ps
 
 
 def trainable_parameters(model) -> List[torch.nn.Parameter]:

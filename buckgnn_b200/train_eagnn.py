@@ -295,7 +295,7 @@ class EAGNNTrainFunction(torch.autograd.Function):
         sv = ctx.sv
         model, prec, n = sv.model, sv.prec, sv.n
         dev = sv.x.device
-        grads = GradStore(dev)
+        grads = GradStore(dev, getattr(model, "_grad_sync", None))
         st = sv.stage
         st.grads = grads
         dxn = (node_head_backward if sv.node_level else head_backward)(
@@ -306,6 +306,7 @@ class EAGNNTrainFunction(torch.autograd.Function):
             dxn, den = _block_backward(st, saved, sv.weights[id(saved[0])], dxn, den, sv.p_drop, sv.seed, i, False)
         encoder_backward(model.node_encoder, sv.x, sv.h1, sv.h2, dxn, prec, grads)
         encoder_backward(model.edge_encoder, sv.ea, sv.eh1, sv.eh2, den, prec, grads)
+        grads.finish()
         ctx.sv = None
         return (None, None, None, None, None, None, *grads.for_params(ctx.params))
 
@@ -378,7 +379,7 @@ class EAGNNSagTrainFunction(torch.autograd.Function):
         dev = sv.x.device
         s = _stream()
         F32 = capi.BG_F32
-        grads = GradStore(dev)
+        grads = GradStore(dev, getattr(model, "_grad_sync", None))
         st1, st2 = sv.st1, sv.st2
         st1.grads = st2.grads = grads
         code = st1.code
@@ -424,5 +425,6 @@ class EAGNNSagTrainFunction(torch.autograd.Function):
         encoder_backward(model.node_encoder, sv.x, sv.h1, sv.h2, dxn, prec, grads)
         if den is not None:
             encoder_backward(model.edge_encoder, sv.ea, sv.eh1, sv.eh2, den, prec, grads)
+        grads.finish()
         ctx.sv = None
         return (None, None, None, None, None, None, *grads.for_params(ctx.params))

@@ -379,6 +379,16 @@ int bg_max_aggregate_backward(const void* x, const void* agg, const void* dagg, 
  * bg_collate (after the host has read n_out = out_node_ptr[G], e_out = out_edge_ptr[G] and allocated):
  *   x [n_out, F], edge_index [2, e_out] (+ the slot's node offset), edge_attr [e_out, Fe], batch [n_out], y [G].
  * An 80 k-graph inference set (~90 GB) fits the 180 GB of a B200: no host collate, no PCIe traffic per batch. */
+/* bg_expand_wire: the compact host->device wire format of an inference batch (buckgnn_b200/pipeline.py: WireBatch) ->
+ * the PyG tensors `BuckGNN.forward(x, edge_index, edge_attr, batch)` takes (INFERENCE.py:135-136).  wire_edges
+ * [2, E_wire] int32 holds every graph's explicit edges (global node ids, graph g at wire_ptr[g]..wire_ptr[g+1]); a graph
+ * with full_ptr[g+1] - full_ptr[g] > its explicit count has an IMPLICIT super node = its last node: the hub pairs
+ * (s, i), (i, s), i ascending, are appended after its explicit edges, the order `create_super_node` emits
+ * (Dataset_Preparation/VirtualEdgeCreate.py:106-111).  Writes edge_index [2, E_full] int64 and batch [N] int64.
+ * node_ptr / wire_ptr / full_ptr: DEVICE [G+1] int64. */
+int bg_expand_wire(const int32_t* wire_edges, int64_t e_wire, const int64_t* node_ptr, const int64_t* wire_ptr,
+                   const int64_t* full_ptr, int64_t n_graphs, int64_t e_full, int64_t* edge_index, int64_t* batch,
+                   void* stream);
 int bg_collate_ptr(const int64_t* sel, int64_t n_graphs, const int64_t* node_ptr, const int64_t* edge_ptr,
                    int64_t* out_node_ptr, int64_t* out_edge_ptr, void* stream);
 int bg_collate(const float* x_all, int32_t n_features, const int64_t* ei_all, int64_t e_all, const float* ea_all,

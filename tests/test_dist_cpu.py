@@ -108,3 +108,56 @@ def test_gradient_allreduce_world_size_2_matches_single_process():
         assert n == want.numel()
         assert unused == ["batch_norm", "edge_encoder", "pooling_mpl", "sage_mlps"]   # never touched by this model_name
         assert torch.allclose(torch.tensor(flat, dtype=torch.float64), want, rtol=1e-9, atol=1e-12)
+
+
+def _sync_worker(rank, world, port, q):
+    """dist.GradSync on gloo: gradients written into the flat buffer group by group, every group all-reduced (mean) as
+    soon as it is declared done, shared parameters only once, the result handed out as per-step snapshots."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from buckgnn_b200.dist import GradSync
+    from buckgnn_b200.train import GradStore
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in ((3, 5), (7,), (4, 4), (2, 3))]
+    sync = GradSync(params, "cpu")
+    out = []
+    for step in range(2):
+        store = GradStore("cpu", sync)
+        g0, acc0 = store.get(params[0])
+        g0.copy_(torch.full((3, 5), float(rank + 1 + step)))
+        store.done([params[0]])                                   # first group goes while the "backward" continues
+        g2, _ = store.get(params[2])
+        g2.copy_(torch.arange(16.).view(4, 4) * (rank + 1))
+        z = store.zeros(params[3])
+        z[:, 1:] += float(10 * (rank + 1))
+        store.done([params[2], params[0]])                        # params[0] again: must not be reduced twice
+        store.finish()                                            # params[3] was never declared done: reduced here
+        res = store.for_params(params)
+        assert res[1] is None and not acc0                        # params[1] got no gradient this step
+        out.append([None if t is None else t.tolist() for t in res])
+        assert res[0].data_ptr() != sync.view(params[0]).data_ptr()   # a snapshot, not the reused buffer
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_sync_buckets_world_size_2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = dict(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert got[0] == got[1]                                       # both ranks hold the same (mean) gradients
+    for step in range(2):
+        g0, g1, g2, g3 = got[0][step]
+        assert g1 is None
+        assert torch.allclose(torch.tensor(g0), torch.full((3, 5), 1.5 + step))
+        assert torch.allclose(torch.tensor(g2), torch.arange(16.).view(4, 4) * 1.5)
+        want3 = torch.zeros(2, 3)
+        want3[:, 1:] = 15.0
+        assert torch.allclose(torch.tensor(g3), want3)

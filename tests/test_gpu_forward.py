@@ -265,3 +265,10 @@ def test_pipelined_inference_returns_every_batch_in_order():
         for (_, p), w in zip(got, want):
             assert p.shape == w.shape and not p.is_cuda
             assert torch.equal(p, w)
+    # the compact wire format (no edge_attr / y / ptr, int32 explicit edges, implicit hub pairs) gives the same numbers
+    from buckgnn_b200.pipeline import WireBatch
+    wires = [WireBatch.from_batch(h).pin_memory() for h in hosts]
+    assert sum(w.nbytes() for w in wires) < 0.45 * sum(sum(t.numel() * t.element_size() for t in (h.x, h.edge_index, h.edge_attr, h.batch, h.y, h.ptr)) for h in hosts)
+    got = list(PipelinedInference(ours, wires, DEV, depth=1))
+    for (_, p), w in zip(got, want):
+        assert torch.equal(p, w)

@@ -323,3 +323,38 @@ def test_device_collate_is_bit_exact():
     want = collate([graphs[int(i)] for i in sel])
     assert torch.equal(got.edge_index.cpu(), want.edge_index) and torch.equal(got.ptr.cpu(), want.ptr)
     assert torch.equal(got.batch.cpu(), want.batch) and torch.equal(got.x.cpu(), want.x)
+
+
+# ----------------------------------------------------------------------------- wire format (pipeline.WireBatch)
+@pytest.mark.parametrize("case", ["super_node", "stiffened_virtual", "no_super", "shuffled", "single_graph"])
+def test_wire_format_expands_to_the_exact_pyg_batch(case):
+    """bg_expand_wire: explicit int32 edges + implicit hub pairs + node offsets -> the int64 edge_index and batch vector
+    `batch.to(device)` would have delivered, bit for bit; graphs whose trailing edges are not the reference's hub pairs
+    ship every edge explicitly."""
+    from buckgnn_b200.pipeline import WireBatch
+    from buckgnn_b200.synth import PlateBatch
+    if case == "super_node":
+        b = make_batch(5, nx=9, ny=7)
+    elif case == "stiffened_virtual":
+        b = make_batch(3, nx=8, ny=6, stiffened=True)
+    elif case == "no_super":
+        b = make_batch(3, nx=8, ny=6, stiffened=True, super_node=False, virtual_edges=True)
+    elif case == "single_graph":
+        b = make_batch(1, nx=10, ny=4)
+    else:                                                    # edges of every graph in random order: nothing is implicit
+        b = make_batch(3, nx=8, ny=6)
+        g = torch.Generator().manual_seed(0)
+        eg = b.batch[b.edge_index[0]]
+        order = torch.cat([torch.nonzero(eg == k).flatten()[torch.randperm(int((eg == k).sum()), generator=g)] for k in range(3)])
+        b = PlateBatch(b.x, b.edge_index[:, order].contiguous(), b.edge_attr[order], b.batch, b.y, b.ptr, b.num_graphs)
+    w = WireBatch.from_batch(b)
+    if case in ("super_node", "stiffened_virtual", "single_graph"):
+        assert w.edges.shape[1] == b.num_edges - 2 * (b.num_nodes - b.num_graphs)      # hub pairs are implicit
+    else:
+        assert w.edges.shape[1] == b.num_edges
+    dev_w = WireBatch(*[getattr(w, f).to(DEV) for f in WireBatch.FIELDS], w.num_graphs, w.num_nodes, w.num_edges, w.edge_features)
+    full = dev_w.expand(DEV)
+    torch.cuda.synchronize()
+    assert torch.equal(full.edge_index.cpu(), b.edge_index)
+    assert torch.equal(full.batch.cpu(), b.batch)
+    assert full.edge_attr.shape == (0, 5) and full.x.data_ptr() == dev_w.x.data_ptr()

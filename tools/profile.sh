@@ -2,7 +2,7 @@
 # ncu evidence for the bench command (run under gpurun, 1 GPU). Outputs under gpurun_out/ -- summaries are made on the
 # box and the raw reports are dropped when they would not fit gpurun's 64 MiB return limit.
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"
