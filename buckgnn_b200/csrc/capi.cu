@@ -316,7 +316,7 @@ int bg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int key_row,
   if (hub_of_row && N > 0) BG_CUDA_OK(cudaMemsetAsync(hub_of_row, 0xff, sizeof(int32_t) * (size_t)N, stream));
   if (N == 0) return BG_OK;
   if (E > 0) {
-    k_csr_hist<<<grid_for(E, 256, sms * 16), 256, 0, stream>>>(key, other, E, N, w.deg, info);
+    k_csr_hist<<<grid_for(E, 256, sms * 16), 256, 0, stream>>>(key, E, N, w.deg, info);
     BG_LAUNCH_OK();
   }
   k_scan_block_sums<<<w.n_scan_blocks, 1024, 0, stream>>>(w.deg, N, w.block_sums);
@@ -326,9 +326,9 @@ int bg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int key_row,
   k_scan_apply<<<w.n_scan_blocks, 1024, 0, stream>>>(w.deg, N, w.block_sums, rowptr, w.cursor, big_rows, info, max_big);
   BG_LAUNCH_OK();
   if (E > 0) {
-    k_csr_fill<<<grid_for(E, 256, sms * 16), 256, 0, stream>>>(key, other, E, N, w.cursor, perm);
+    k_csr_fill<<<grid_for(E, 256, sms * 16), 256, 0, stream>>>(key, E, N, w.cursor, perm);
     BG_LAUNCH_OK();
-    k_csr_sort_small<<<(unsigned)ceil_div64(N, 256), 256, 0, stream>>>(rowptr, N, other, perm, col);
+    k_csr_sort_small<<<(unsigned)ceil_div64(N, 256), 256, 0, stream>>>(rowptr, N, other, perm, col, info);
     BG_LAUNCH_OK();
     static bool attr_set = false;
     const int sort_smem = kSortSmemElems * (int)sizeof(int32_t);
@@ -336,7 +336,7 @@ int bg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int key_row,
       BG_CUDA_OK(cudaFuncSetAttribute(k_csr_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, sort_smem));
       attr_set = true;
     }
-    k_csr_sort_big<<<sms, 1024, sort_smem, stream>>>(rowptr, big_rows, info, max_big, other, perm, col, hub_lo, hub_of_row);
+    k_csr_sort_big<<<sms, 1024, sort_smem, stream>>>(rowptr, big_rows, info, max_big, other, N, perm, col, hub_lo, hub_of_row);
     BG_LAUNCH_OK();
   }
   return BG_OK;

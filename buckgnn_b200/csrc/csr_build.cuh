@@ -22,16 +22,23 @@ constexpr int kScanItemsPerBlock = 4096;   // 1024 threads x 4
 constexpr int kSortSmemElems = 57344;      // hub rows up to this degree sort in shared memory (224 KB of the 227 KB a CTA
                                            // may have; the network skips partners beyond n, so n need not be a power of 2)
 
-// an edge with either endpoint outside [0, N) is dropped and flagged (info bit 0)
-BG_DEVINL bool edge_ok(int64_t k, int64_t o, int64_t N) { return k >= 0 && k < N && o >= 0 && o < N; }
+// An edge whose KEY endpoint lies outside [0, N) is dropped and flagged (info bit 0) by the histogram and the fill; the
+// OTHER endpoint is only read where `col` is written (the sort kernels), which flag it there and store 0 -- the host
+// raises on the flag before any kernel dereferences `col` (engine.PendingGraphIndex.finish).  Histogram and fill thus
+// read 8 instead of 16 bytes per edge.
+BG_DEVINL bool key_ok(int64_t k, int64_t N) { return k >= 0 && k < N; }
+BG_DEVINL int32_t checked_col(int64_t o, int64_t N, int32_t* __restrict__ info) {
+  if (o < 0 || o >= N) { atomicOr(&info[0], 1); return 0; }
+  return (int32_t)o;
+}
 
-__global__ void k_csr_hist(const int64_t* __restrict__ key, const int64_t* __restrict__ other, int64_t E, int64_t N,
+__global__ void k_csr_hist(const int64_t* __restrict__ key, int64_t E, int64_t N,
                            int32_t* __restrict__ deg, int32_t* __restrict__ info) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   bool bad = false;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
     int64_t k = key[e];
-    if (!edge_ok(k, other[e], N)) { bad = true; continue; }
+    if (!key_ok(k, N)) { bad = true; continue; }
     atomicAdd(&deg[k], 1);
   }
   if (bad) atomicOr(&info[0], 1);
@@ -124,12 +131,12 @@ __global__ void __launch_bounds__(1024) k_scan_apply(const int32_t* __restrict__
   }
 }
 
-__global__ void k_csr_fill(const int64_t* __restrict__ key, const int64_t* __restrict__ other, int64_t E, int64_t N,
+__global__ void k_csr_fill(const int64_t* __restrict__ key, int64_t E, int64_t N,
                            int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
     int64_t k = key[e];
-    if (!edge_ok(k, other[e], N)) continue;
+    if (!key_ok(k, N)) continue;
     int32_t pos = atomicAdd(&cursor[k], 1);
     perm[pos] = (int32_t)e;
   }
@@ -138,7 +145,7 @@ __global__ void k_csr_fill(const int64_t* __restrict__ key, const int64_t* __res
 // one thread per small row: insertion sort of its edge ids, then col = other[perm]
 __global__ void k_csr_sort_small(const int32_t* __restrict__ rowptr, int64_t N,
                                  const int64_t* __restrict__ other, int32_t* __restrict__ perm,
-                                 int32_t* __restrict__ col) {
+                                 int32_t* __restrict__ col, int32_t* __restrict__ info) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= N) return;
   const int32_t s = rowptr[r], e = rowptr[r + 1];
@@ -150,7 +157,7 @@ __global__ void k_csr_sort_small(const int32_t* __restrict__ rowptr, int64_t N,
     while (j >= s && perm[j] > v) { perm[j + 1] = perm[j]; --j; }
     perm[j + 1] = v;
   }
-  for (int32_t i = s; i < e; ++i) col[i] = (int32_t)other[perm[i]];
+  for (int32_t i = s; i < e; ++i) col[i] = checked_col(other[perm[i]], N, info);
 }
 
 // ascending-only bitonic network over n (<= P = pow2) keys; partners beyond n act as +inf
@@ -192,11 +199,54 @@ BG_DEVINL void mark_range_hub(int32_t b, const int32_t* __restrict__ colseg, int
   }
 }
 
-// one CTA per hub row (grid-stride over the list): bitonic sort of its edge ids
+// Sorts the n DISTINCT edge ids of a hub row with a bitmap: the ids of a hub's in-edges span a short interval of the edge
+// list (the reference appends a graph's hub pairs (s, i), (i, s) in one block, VirtualEdgeCreate.py:106-111: span = 2n - 1),
+// so "set bit id - min; rank = number of lower set bits" orders them in O(n + span / 32) instead of the bitonic
+// network's O(n log^2 n).  `bits` holds span bits (span <= 32 * kSortSmemElems), `red` 64 words of scratch.
+// Returns false (nothing written) when the span does not fit.
+BG_DEVINL bool bitmap_sort_row(int32_t* __restrict__ seg, int32_t n, uint32_t* __restrict__ bits, int32_t* __restrict__ red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  int32_t lo = 0x7fffffff, hi = -1;
+  for (int32_t i = threadIdx.x; i < n; i += blockDim.x) { const int32_t v = seg[i]; lo = min(lo, v); hi = max(hi, v); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if (lane == 0) { red[warp] = lo; red[32 + warp] = hi; }
+  __syncthreads();
+  lo = red[0]; hi = red[32];
+  for (int w = 1; w < n_warps; ++w) { lo = min(lo, red[w]); hi = max(hi, red[32 + w]); }
+  __syncthreads();
+  const int64_t span = (int64_t)hi - lo + 1;
+  const int32_t words = (int32_t)((span + 31) >> 5);
+  if (span > (int64_t)32 * (kSortSmemElems - 64)) return false;                        // uniform over the CTA
+  for (int32_t w = threadIdx.x; w < words; w += blockDim.x) bits[w] = 0u;
+  __syncthreads();
+  for (int32_t i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t d = (uint32_t)(seg[i] - lo); atomicOr(&bits[d >> 5], 1u << (d & 31)); }
+  __syncthreads();
+  // exclusive prefix of the per-word popcounts: each thread owns a contiguous run of words
+  const int32_t per = (words + (int32_t)blockDim.x - 1) / (int32_t)blockDim.x;
+  const int32_t w0 = min(words, (int32_t)threadIdx.x * per), w1 = min(words, w0 + per);
+  int32_t mine = 0;
+  for (int32_t w = w0; w < w1; ++w) mine += __popc(bits[w]);
+  int32_t total;
+  int32_t run = block_exclusive_scan(mine, red, total);
+  __syncthreads();                                                               // every element of seg has been read
+  for (int32_t w = w0; w < w1; ++w) {
+    uint32_t b = bits[w];
+    while (b) {
+      const int bit = __ffs(b) - 1;
+      b &= b - 1;
+      seg[run++] = lo + (w << 5) + bit;
+    }
+  }
+  __syncthreads();
+  return true;
+}
+
+// one CTA per hub row (grid-stride over the list): bitmap sort of its edge ids (bitonic network as the fallback)
 __global__ void __launch_bounds__(1024) k_csr_sort_big(const int32_t* __restrict__ rowptr,
                                                        const int32_t* __restrict__ big_rows,
                                                        int32_t* __restrict__ info, int32_t max_big,
-                                                       const int64_t* __restrict__ other,
+                                                       const int64_t* __restrict__ other, int64_t N,
                                                        int32_t* __restrict__ perm, int32_t* __restrict__ col,
                                                        int32_t* __restrict__ hub_lo, int32_t* __restrict__ hub_of_row) {
   extern __shared__ int32_t sbuf[];
@@ -206,19 +256,22 @@ __global__ void __launch_bounds__(1024) k_csr_sort_big(const int32_t* __restrict
     const int32_t s = rowptr[r], n = rowptr[r + 1] - s;
     int32_t P = 1;
     while (P < n) P <<= 1;
-    if (n <= kSortSmemElems) {
+    if (bitmap_sort_row(perm + s, n, reinterpret_cast<uint32_t*>(sbuf) + 64, sbuf)) {
+      for (int32_t i = threadIdx.x; i < n; i += blockDim.x) col[s + i] = checked_col(other[perm[s + i]], N, info);
+      __syncthreads();
+    } else if (n <= kSortSmemElems) {
       for (int32_t i = threadIdx.x; i < n; i += blockDim.x) sbuf[i] = perm[s + i];
       __syncthreads();
       bitonic_ascending(sbuf, n, P);
       for (int32_t i = threadIdx.x; i < n; i += blockDim.x) {
         int32_t p = sbuf[i];
         perm[s + i] = p;
-        col[s + i] = (int32_t)other[p];
+        col[s + i] = checked_col(other[p], N, info);
       }
       __syncthreads();
     } else {
       bitonic_ascending(perm + s, n, P);   // global-memory fallback for giant rows
-      for (int32_t i = threadIdx.x; i < n; i += blockDim.x) col[s + i] = (int32_t)other[perm[s + i]];
+      for (int32_t i = threadIdx.x; i < n; i += blockDim.x) col[s + i] = checked_col(other[perm[s + i]], N, info);
       __syncthreads();
     }
     if (hub_of_row) mark_range_hub(b, col + s, n, hub_lo, hub_of_row, info);

@@ -110,6 +110,12 @@ __device__ unsigned long long g_gemm_prof[296 * 8];
 #define BG_PROF_STORE(slot, v)
 #endif
 
+#ifndef BG_GEMM_P1_WIDE
+#define BG_GEMM_P1_WIDE 0          // 1: pass 1 of the epilogue reads TMEM 32 columns per load.  Measured SLOWER (r02:
+                                   // pass 1 4.9k -> 8.1k cycles per tile, spills): the drain runs at the TMEM read rate
+                                   // (~57 B/cycle/SM: 256 KB in 4.5k cycles), not at load latency, so wider loads cannot help
+#endif
+
 enum : uint32_t { kTagEmpty = 1, kTagFull = 2, kTagTmemEmpty = 3, kTagTmemFull = 4 };
 
 BG_DEVINL void named_bar_sync(uint32_t id, uint32_t threads) {
@@ -221,7 +227,9 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
         }
       }
     };
+#if !BG_GEMM_P1_WIDE
     fetch(0);                                                   // in flight while we wait for the MMAs
+#endif
 
     BG_PROF_T0();
     mbar_wait(cx.tmem_full_bar, it & 1u, kTagTmemFull);
@@ -230,40 +238,59 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
     BG_PROF_T0();
 
     // ---- pass 1: row sum of squares of (acc + bias); 16-bit output also stashes the row.
-    // TMEM loads are double-buffered (16 columns each) so their latency hides behind the math.
+    // This is the one part of the epilogue the next tile's MMAs cannot overlap (the 128 x 512 fp32 accumulator is
+    // all of TMEM), so it is kept short: TMEM loads are double-buffered, BG_GEMM_P1_WIDE columns each.
     [[maybe_unused]] uint32_t stash[kOut16 ? 128 : 1];
     float ss = 0.f;
     if (kOut16 || p.normalize) {
-      uint32_t ra[16], rb[16];
-      auto consume = [&](const uint32_t (&r)[16], int c16) {    // c16: index of the 16-column block
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 b = bias4[c16 * 4 + i];
-          const float v0 = __uint_as_float(r[4 * i]) + b.x, v1 = __uint_as_float(r[4 * i + 1]) + b.y;
-          const float v2 = __uint_as_float(r[4 * i + 2]) + b.z, v3 = __uint_as_float(r[4 * i + 3]) + b.w;
-          ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
-          if constexpr (kOut16) {
-            stash[c16 * 8 + 2 * i] = Pack16<TOut>::pack(v0, v1);
-            stash[c16 * 8 + 2 * i + 1] = Pack16<TOut>::pack(v2, v3);
-          }
+      auto consume4 = [&](const uint32_t* r, int c4) {          // c4: index of the 4-column group
+        const float4 b = bias4[c4];
+        const float v0 = __uint_as_float(r[0]) + b.x, v1 = __uint_as_float(r[1]) + b.y;
+        const float v2 = __uint_as_float(r[2]) + b.z, v3 = __uint_as_float(r[3]) + b.w;
+        ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
+        if constexpr (kOut16) {
+          stash[2 * c4] = Pack16<TOut>::pack(v0, v1);
+          stash[2 * c4 + 1] = Pack16<TOut>::pack(v2, v3);
         }
       };
+#if BG_GEMM_P1_WIDE
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(taddr, ra);
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) consume4(ra + 4 * i, c * 8 + i);
+        tmem_ld_wait();
+        if (c + 2 < 8) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) consume4(rb + 4 * i, (c + 1) * 8 + i);
+      }
+#else
+      uint32_t ra[16], rb[16];
       tmem_ld_32x16(taddr, ra);
 #pragma unroll
       for (int c = 0; c < 16; c += 2) {
         tmem_ld_wait();
         tmem_ld_32x16(taddr + (c + 1) * 16, rb);
-        consume(ra, c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) consume4(ra + 4 * i, c * 4 + i);
         tmem_ld_wait();
         if (c + 2 < 16) tmem_ld_32x16(taddr + (c + 2) * 16, ra);
-        consume(rb, c + 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) consume4(rb + 4 * i, (c + 1) * 4 + i);
       }
+#endif
     }
     if constexpr (kOut16) {                                     // accumulator fully read: release TMEM now
       tc_fence_before();
       if (kCg == 1 || cx.rank == 0) mbar_arrive(cx.tmem_empty_bar);
       else mbar_arrive_cluster(cx.tmem_empty_bar, 0);
     }
+#if BG_GEMM_P1_WIDE
+    fetch(0);                                                   // (after pass 1: its 32 registers are the second TMEM buffer there)
+#endif
     float inv = 1.f;
     if (p.normalize) {                                          // exchange through the (idle) staging tiles
       cx.my_tile[lane] = ss;

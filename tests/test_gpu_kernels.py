@@ -34,7 +34,7 @@ def _random_multigraph(n, e, seed, hub=None):
 
 
 @pytest.mark.parametrize("key_row", [1, 0])
-@pytest.mark.parametrize("case", ["mesh", "random", "hub", "tiny", "empty_edges", "bighub", "hugehub"])
+@pytest.mark.parametrize("case", ["mesh", "random", "hub", "tiny", "empty_edges", "bighub", "hugehub", "sparsehub", "sparsehugehub"])
 def test_csr_build_bit_exact(case, key_row):
     if case == "mesh":
         b = make_batch(5, nx=17, ny=13); ei, n = b.edge_index, b.num_nodes
@@ -48,8 +48,14 @@ def test_csr_build_bit_exact(case, key_row):
         n = 10; ei = torch.zeros((2, 0), dtype=torch.int64)
     elif case == "bighub":                    # ~50 k: not a power of two, just below the shared-memory sort capacity (57344)
         n = 200; ei = _random_multigraph(n, 150000, 3, hub=7)
-    else:                                     # ~67 k: above it -> the global-memory network
+    elif case == "hugehub":                   # ~67 k entries within 200 k edge ids: still the bitmap sort
         n = 200; ei = _random_multigraph(n, 200000, 4, hub=9)
+    elif case == "sparsehub":                 # hub entries spread over 2.4 M edge ids (> 32 * 57 k bits): bitonic network in smem
+        n = 4000; ei = _random_multigraph(n, 2400000, 5)
+        ei[1, ::64] = 77
+    else:                                     # ... and more entries than shared memory holds: the global-memory network
+        n = 4000; ei = _random_multigraph(n, 2400000, 6)
+        ei[1, ::30] = 78
     idx = build_graph_index(ei.to(DEV), None, n, key_row=key_row)
     rowptr, col, perm = _csr_reference(ei, n, key_row)
     e = ei.shape[1]
