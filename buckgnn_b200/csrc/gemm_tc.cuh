@@ -116,6 +116,20 @@ __device__ unsigned long long g_gemm_prof[296 * 8];
                                    // (~57 B/cycle/SM: 256 KB in 4.5k cycles), not at load latency, so wider loads cannot help
 #endif
 
+// Epilogue global I/O experiments (r02, tools/gemm_bench.py, K = 1024 fp16 with skip rows; baseline 1.085 ms per launch):
+// the MMA phase of a tile is shared-memory-bandwidth bound (operand reads 64 B/cycle + TMA fill ~39 B/cycle of the SM's
+// 128 B/cycle) and the previous tile's pass 2 runs beside it, so moving the epilogue's global I/O off the staging tile
+// looked attractive.  It is not: BG_EPI_DIRECT_LOAD (a thread reads the skip / gathered pieces of its OWN row, eight
+// 16-byte loads per 128-byte line) 1.74 ms; plus BG_EPI_DIRECT_STORE (16-byte stores of its own row) 1.91 ms, and the
+// K = 128 encoder GEMM 0.30 -> 0.61 ms.  32 distinct lines per warp instruction cost far more in L1/L2 transactions than
+// the STS + LDS round trip through the warp's swizzled tile.  Both stay off.
+#ifndef BG_EPI_DIRECT_LOAD
+#define BG_EPI_DIRECT_LOAD 0
+#endif
+#ifndef BG_EPI_DIRECT_STORE
+#define BG_EPI_DIRECT_STORE 0
+#endif
+
 enum : uint32_t { kTagEmpty = 1, kTagFull = 2, kTagTmemEmpty = 3, kTagTmemFull = 4 };
 
 BG_DEVINL void named_bar_sync(uint32_t id, uint32_t threads) {
@@ -213,6 +227,44 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
       add_base = reinterpret_cast<const char*>(p.residual) + (size_t)(warp_row0 + r4) * p.ldr * esz + (size_t)cb * esz + piece * 16;
     if constexpr (kAdd == kAddGather)
       add_base = reinterpret_cast<const char*>(p.gather[0]) + (size_t)cb * esz + piece * 16;
+    // this thread's own row: piece j (16 bytes) of 128-byte chunk ch of the addend (skip row, or gathered row(s))
+    [[maybe_unused]] const bool row_ok = m_row < p.m;
+    [[maybe_unused]] const char* own0 = nullptr;
+    [[maybe_unused]] const char* own1 = nullptr;
+    if constexpr (kAdd == kAddResidual)
+      own0 = reinterpret_cast<const char*>(p.residual) + (size_t)(row_ok ? m_row : 0) * p.ldr * esz + (size_t)cb * esz;
+    if constexpr (kAdd == kAddGather) {
+      own0 = reinterpret_cast<const char*>(p.gather[0]) + (size_t)gi0 * p.gather_ld * esz + (size_t)cb * esz;
+      own1 = reinterpret_cast<const char*>(p.gather[1]) + (size_t)gi1 * p.gather_ld * esz + (size_t)cb * esz;
+    }
+    auto load_piece = [&](int ch, int j) -> uint4 {
+      if constexpr (kAdd == kAddResidual) {
+        return row_ok ? ldg_nc_v4(own0 + ch * 128 + j * 16) : make_uint4(0u, 0u, 0u, 0u);
+      } else if constexpr (kAdd == kAddGather) {
+        uint4 a = ldg_v4(own0 + ch * 128 + j * 16);
+        if (p.n_gather > 1) {
+          const uint4 b = ldg_v4(own1 + ch * 128 + j * 16);
+          if constexpr (kOut16) {
+            a.x = Pack16<TOut>::hadd2(a.x, b.x); a.y = Pack16<TOut>::hadd2(a.y, b.y);
+            a.z = Pack16<TOut>::hadd2(a.z, b.z); a.w = Pack16<TOut>::hadd2(a.w, b.w);
+          } else {
+            a.x = __float_as_uint(__uint_as_float(a.x) + __uint_as_float(b.x)); a.y = __float_as_uint(__uint_as_float(a.y) + __uint_as_float(b.y));
+            a.z = __float_as_uint(__uint_as_float(a.z) + __uint_as_float(b.z)); a.w = __float_as_uint(__uint_as_float(a.w) + __uint_as_float(b.w));
+          }
+        }
+        return a;
+      } else {
+        return make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+#if BG_EPI_DIRECT_LOAD
+    auto fetch = [&](int ch) {
+      if constexpr (kAdd != kAddNone) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pre[j] = load_piece(ch, j);
+      }
+    };
+#else
     auto fetch = [&](int ch) {
       if constexpr (kAdd == kAddResidual) {
 #pragma unroll
@@ -227,6 +279,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
         }
       }
     };
+#endif
 #if !BG_GEMM_P1_WIDE
     fetch(0);                                                   // in flight while we wait for the MMAs
 #endif
@@ -307,6 +360,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
     char* out_base = reinterpret_cast<char*>(p.out) + (size_t)(warp_row0 + r4) * out_row_bytes + (size_t)cb * esz + piece * 16;
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
+#if !BG_EPI_DIRECT_LOAD
       if constexpr (kAdd != kAddNone) {
         if constexpr (kAdd == kAddGather) {
           if (p.n_gather > 1) {                                 // second gathered matrix, summed on the way in
@@ -332,6 +386,25 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
         __syncwarp();
         if (ch + 1 < kChunks) fetch(ch + 1);                    // next chunk's addends fly during the math below
       }
+#endif
+      // addend piece j of this chunk for the thread's row; in direct mode the register is refilled with the next chunk's
+      // piece at once (prefetch one chunk ahead without a second register set)
+      auto addend = [&](int j, uint32_t addr) -> uint4 {
+#if BG_EPI_DIRECT_LOAD
+        const uint4 a = pre[j];
+        if (ch + 1 < kChunks) pre[j] = load_piece(ch + 1, j);
+        return a;
+#else
+        return lds_v4(addr);
+#endif
+      };
+      auto emit = [&](int j, uint32_t addr, uint4 o) {
+#if BG_EPI_DIRECT_STORE
+        if (row_ok) stg_v4(reinterpret_cast<char*>(p.out) + (size_t)m_row * out_row_bytes + (size_t)cb * esz + ch * 128 + j * 16, o);
+#else
+        sts_v4(addr, o);
+#endif
+      };
       [[maybe_unused]] uint32_t r[32];
       if constexpr (!kOut16) {
         tmem_ld_32x32(taddr + ch * 32, r);
@@ -348,7 +421,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
           const uint32_t addr = my_row + (((uint32_t)j ^ my_sw) << 4);
           uint32_t o[4] = {stash[ch * 32 + j * 4], stash[ch * 32 + j * 4 + 1], stash[ch * 32 + j * 4 + 2], stash[ch * 32 + j * 4 + 3]};
           if constexpr (kAdd != kAddNone) {
-            const uint4 ad = lds_v4(addr);
+            const uint4 ad = addend(j, addr);
             const uint32_t au[4] = {ad.x, ad.y, ad.z, ad.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -360,7 +433,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = Pack16<TOut>::relu2(o[e]);
           }
-          sts_v4(addr, make_uint4(o[0], o[1], o[2], o[3]));
+          emit(j, addr, make_uint4(o[0], o[1], o[2], o[3]));
         }
       } else if constexpr (kPacked) {
         // fp16 output: the stash already holds the row as fp16 pairs, so normalize / BN / ReLU / addends run as
@@ -373,7 +446,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
         for (int j = 0; j < 8; ++j) {
           const uint32_t addr = my_row + (((uint32_t)j ^ my_sw) << 4);
           [[maybe_unused]] uint4 ad;
-          if constexpr (kAdd != kAddNone) ad = lds_v4(addr);
+          if constexpr (kAdd != kAddNone) ad = addend(j, addr);
           const uint32_t au[4] = {kAdd != kAddNone ? ad.x : 0u, kAdd != kAddNone ? ad.y : 0u,
                                   kAdd != kAddNone ? ad.z : 0u, kAdd != kAddNone ? ad.w : 0u};
           const uint2 sca = sc2[2 * j], scb = sc2[2 * j + 1], sha = sh2[2 * j], shb = sh2[2 * j + 1];
@@ -389,7 +462,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
             if constexpr (kAdd == kAddResidual) v = __hadd2(v, *reinterpret_cast<const __half2*>(&au[e]));
             o[e] = *reinterpret_cast<const uint32_t*>(&v);
           }
-          sts_v4(addr, make_uint4(o[0], o[1], o[2], o[3]));
+          emit(j, addr, make_uint4(o[0], o[1], o[2], o[3]));
         }
       } else {
 #pragma unroll
@@ -409,7 +482,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
           v[2] = __uint_as_float(r[j * 4 + 2]) + b.z; v[3] = __uint_as_float(r[j * 4 + 3]) + b.w;
         }
         [[maybe_unused]] uint4 ad;
-        if constexpr (kAdd != kAddNone) ad = lds_v4(addr);
+        if constexpr (kAdd != kAddNone) ad = addend(j, addr);
         if constexpr (kAdd == kAddGather) {                     // gathered addends enter before the activation
           const uint32_t au[4] = {ad.x, ad.y, ad.z, ad.w};
           if constexpr (kOut16) {
@@ -448,9 +521,10 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
         } else {
           o.x = __float_as_uint(v[0]); o.y = __float_as_uint(v[1]); o.z = __float_as_uint(v[2]); o.w = __float_as_uint(v[3]);
         }
-        sts_v4(addr, o);
+        emit(j, addr, o);
       }
       }
+#if !BG_EPI_DIRECT_STORE
       __syncwarp();
       // coalesced store: 4 rows x 128 B per instruction
 #pragma unroll
@@ -459,6 +533,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
         if (t * 4 + r4 < rows_here) stg_v4(out_base + (size_t)t * 4 * out_row_bytes + ch * 128, o);
       }
       __syncwarp();
+#endif
     }
     BG_PROF_ADD(_pacc_c);
   }
