@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "csr_build.cuh"
 #include "aggregate.cuh"
+#include "aggregate_window.cuh"
 #include "encoder.cuh"
 #include "gemm_tc.cuh"
 #include "pool_head.cuh"
@@ -176,6 +177,38 @@ static int aggregate_dispatch(const T* x, T* out, int64_t N, const int32_t* rowp
   }
   const unsigned grid = agg_grid<T>(N);
   const int64_t band = ceil_div64(N, grid);
+  if constexpr (sizeof(T) == 2) {
+    // 16-bit rows, opt-in (BG_AGG_WINDOW=1 in the environment): the band's rows staged once through a shared-memory ring
+    // (aggregate_window.cuh).  Bit-identical results, but measured SLOWER than the L1/L2-gather kernels below (r02, cfg 2:
+    // 0.59 vs 0.42 ms; stiffened degree-11 meshes 0.49 vs 0.41 ms per launch): the +-84-row window takes 21 of the ring's 27
+    // slots, the 48 KB left in flight ahead of the gather front cannot cover HBM latency at 44 GB/s per SM.
+    static const bool use_window = [] { const char* e = getenv("BG_AGG_WINDOW"); return e && e[0] == '1'; }();
+    if (use_window) {
+      const bool fold = hr.hub_lo && n_big > 0 && aggr != BG_AGGR_MAX;
+      const HubFold hf = fold ? HubFold{hr.hub_of_row, hr.hub_lo, hr.partial, (int32_t)hub_parts(band, hr.max_degree)}
+                              : HubFold{nullptr, nullptr, nullptr, 0};
+#define BG_AGGW_LAUNCH(A, F)                                                                                          \
+  {                                                                                                                   \
+    static bool set = false;                                                                                          \
+    if (!set) { BG_CUDA_OK(cudaFuncSetAttribute(k_aggregate_window<T, A, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmemBytes)); set = true; } \
+    k_aggregate_window<T, A, F><<<grid, kWinThreads, kWinSmemBytes, stream>>>(x, out, N, band, rowptr, col, hf);      \
+  }
+      if (fold) {
+        if (aggr == BG_AGGR_MEAN) { BG_AGGW_LAUNCH(BG_AGGR_MEAN, true); k_hub_finalize<T, BG_AGGR_MEAN><<<(unsigned)n_big, 128, 0, stream>>>(out, N, band, rowptr, big_rows, hf); }
+        else if (aggr == BG_AGGR_SUM) { BG_AGGW_LAUNCH(BG_AGGR_SUM, true); k_hub_finalize<T, BG_AGGR_SUM><<<(unsigned)n_big, 128, 0, stream>>>(out, N, band, rowptr, big_rows, hf); }
+        else return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad aggr");
+      } else {
+        const unsigned hub_grid_w = (unsigned)n_big * kHubSlices;
+        if (aggr == BG_AGGR_MEAN) { BG_AGGW_LAUNCH(BG_AGGR_MEAN, false); if (n_big > 0) k_aggregate_hubs<T, BG_AGGR_MEAN><<<hub_grid_w, kAggWarpsPerBlock * 32, 0, stream>>>(x, out, rowptr, col, big_rows, n_big, partial, ticket); }
+        else if (aggr == BG_AGGR_SUM) { BG_AGGW_LAUNCH(BG_AGGR_SUM, false); if (n_big > 0) k_aggregate_hubs<T, BG_AGGR_SUM><<<hub_grid_w, kAggWarpsPerBlock * 32, 0, stream>>>(x, out, rowptr, col, big_rows, n_big, partial, ticket); }
+        else if (aggr == BG_AGGR_MAX) { BG_AGGW_LAUNCH(BG_AGGR_MAX, false); if (n_big > 0) k_aggregate_hubs<T, BG_AGGR_MAX><<<hub_grid_w, kAggWarpsPerBlock * 32, 0, stream>>>(x, out, rowptr, col, big_rows, n_big, partial, ticket); }
+        else return fail(BG_ERR_INVALID, "bg_sage_aggregate: bad aggr");
+      }
+#undef BG_AGGW_LAUNCH
+      BG_LAUNCH_OK();
+      return BG_OK;
+    }
+  }
   if (hr.hub_lo && n_big > 0) {                    // range hubs folded into the row pass
     constexpr int kThreads = agg_fold_threads<T>();
     HubFold hf{hr.hub_of_row, hr.hub_lo, hr.partial, (int32_t)hub_parts(band, hr.max_degree)};
