@@ -20,13 +20,13 @@ BG_BF16, BG_F32, BG_F16 = 0, 1, 2
 BG_AGGR_MEAN, BG_AGGR_SUM, BG_AGGR_MAX = 0, 1, 2
 BG_BIG_ROW_THRESHOLD = 64
 BG_MAX_GEMM_SEGMENTS = 8
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 AGGR_CODES = {"mean": BG_AGGR_MEAN, "sum": BG_AGGR_SUM, "add": BG_AGGR_SUM, "max": BG_AGGR_MAX}
 
 # every symbol include/buckgnn_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
-    "bg_abi_version", "bg_last_error", "bg_device_check", "bg_watchdog_info_host",
+    "bg_abi_version", "bg_last_error", "bg_device_check", "bg_watchdog_info_host", "bg_set_sm_partition",
     "bg_csr_max_big_rows", "bg_csr_workspace_bytes", "bg_csr_build",
     "bg_batch_info", "bg_graph_ptr_build", "bg_publish_words", "bg_encoder_front",
     "bg_aggregate_workspace_bytes", "bg_hubfold_workspace_bytes", "bg_sage_aggregate", "bg_gemm512",
@@ -68,6 +68,7 @@ _SIGNATURES = {
     "bg_last_error": (C.c_char_p, []),
     "bg_device_check": (C.c_int, []),
     "bg_watchdog_info_host": (C.c_int, [C.POINTER(C.c_uint32)]),
+    "bg_set_sm_partition": (C.c_int, [C.c_int, C.c_int]),
     "bg_csr_max_big_rows": (_I64, [_I64]),
     "bg_csr_workspace_bytes": (C.c_int, [_I64, _I64, _SZP]),
     "bg_csr_build": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),

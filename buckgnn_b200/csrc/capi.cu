@@ -40,6 +40,11 @@ int sm_count() {
   return cached;
 }
 
+// SM partition for co-running kernels (bg_set_sm_partition): 0 = the whole device
+static int g_gemm_sm_limit = 0, g_agg_sm_limit = 0;
+int gemm_sm_count() { const int n = sm_count(); return (g_gemm_sm_limit > 0 && g_gemm_sm_limit < n) ? g_gemm_sm_limit : n; }
+static int agg_sm_count() { const int n = sm_count(); return (g_agg_sm_limit > 0 && g_agg_sm_limit < n) ? g_agg_sm_limit : n; }
+
 PFN_tensorMapEncodeTiled get_tensor_map_encoder() {
   static PFN_tensorMapEncodeTiled fn = nullptr;
   if (!fn) {
@@ -147,7 +152,7 @@ static inline unsigned grid_for(int64_t n, int threads, int max_blocks) {
 struct HubRangeArgs { const int32_t* hub_lo; const int32_t* hub_of_row; int32_t max_degree; float* partial; };
 
 template <typename T> static inline unsigned agg_grid(int64_t N) {
-  return (unsigned)min64(ceil_div64(N, agg_row_threads<T>() / 32), (int64_t)sm_count());
+  return (unsigned)min64(ceil_div64(N, agg_row_threads<T>() / 32), (int64_t)agg_sm_count());
 }
 static inline int64_t hub_parts(int64_t band, int32_t max_degree) { return ceil_div64(max_degree > 0 ? max_degree : 1, band) + 1; }
 
@@ -310,6 +315,13 @@ int bg_gemm_prof_host(unsigned long long* out, int n) {
   return BG_OK;
 }
 #endif
+
+int bg_set_sm_partition(int gemm_sms, int agg_sms) {
+  if (gemm_sms < 0 || agg_sms < 0 || gemm_sms == 1) return fail(BG_ERR_INVALID, "bg_set_sm_partition: bad SM count");
+  g_gemm_sm_limit = gemm_sms;
+  g_agg_sm_limit = agg_sms;
+  return BG_OK;
+}
 
 int bg_watchdog_info_host(uint32_t* out4_host) {
   if (!out4_host) return fail(BG_ERR_INVALID, "null output");

@@ -58,6 +58,15 @@ BG_DEVINL uint4 ldg_nc_v4(const void* p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+// ptxas reorders ordinary loads freely (under register pressure it SINKS a prefetch to its first use, exposing the
+// whole DRAM latency), but it keeps .volatile operations of a thread in program order: a volatile load issued ahead of
+// volatile shared-memory stores stays ahead of them.
+BG_DEVINL uint4 ldg_volatile_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
 // cached variant: gathers re-touch neighbouring rows, let L1 keep them
 BG_DEVINL uint4 ldg_v4(const void* p) {
   uint4 r;
@@ -80,6 +89,16 @@ BG_DEVINL uint32_t pack_f16(float a, float b) {
   __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// sm_100 packed fp32 pairs (FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per instruction, each rounded exactly like
+// the scalar instruction).  A pair lives in an aligned 64-bit register pair; pack / unpack are register renames.
+BG_DEVINL uint64_t f2_pack(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+BG_DEVINL void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+BG_DEVINL uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+BG_DEVINL uint64_t f2_mul(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+BG_DEVINL uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+
 // 16-bit storage formats: unpack a pair / pack a pair / scalar convert / fp32 += 16-bit pair.
 // add2 uses sm_100's mixed-precision add (add.rn.f32.{f16,bf16} -> one FHADD per element, the
 // 16-bit half selected for free), so fp32 accumulation of 16-bit rows needs no conversions.
@@ -90,6 +109,13 @@ template <> struct Pack16<__nv_bfloat16> {
   static BG_DEVINL void add2(float& a0, float& a1, uint32_t u) {
     asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\t"
         "add.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t}" : "+f"(a0), "+f"(a1) : "r"(u));
+  }
+  // out-of-place: fp32(low / high 16-bit half of u) + b  (b may come straight from a uniform register)
+  static BG_DEVINL float add_lo(uint32_t u, float b) {
+    float r; asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, lo, %2;\n\t}" : "=f"(r) : "r"(u), "f"(b)); return r;
+  }
+  static BG_DEVINL float add_hi(uint32_t u, float b) {
+    float r; asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, hi, %2;\n\t}" : "=f"(r) : "r"(u), "f"(b)); return r;
   }
   static BG_DEVINL uint32_t pack(float a, float b) { return pack_bf16(a, b); }
   static BG_DEVINL __nv_bfloat16 one(float a) { return __float2bfloat16_rn(a); }
@@ -108,6 +134,12 @@ template <> struct Pack16<__half> {
   static BG_DEVINL void add2(float& a0, float& a1, uint32_t u) {
     asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\t"
         "add.rn.f32.f16 %0, lo, %0;\n\tadd.rn.f32.f16 %1, hi, %1;\n\t}" : "+f"(a0), "+f"(a1) : "r"(u));
+  }
+  static BG_DEVINL float add_lo(uint32_t u, float b) {
+    float r; asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.f16 %0, lo, %2;\n\t}" : "=f"(r) : "r"(u), "f"(b)); return r;
+  }
+  static BG_DEVINL float add_hi(uint32_t u, float b) {
+    float r; asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.f16 %0, hi, %2;\n\t}" : "=f"(r) : "r"(u), "f"(b)); return r;
   }
   static BG_DEVINL uint32_t pack(float a, float b) { return pack_f16(a, b); }
   static BG_DEVINL __half one(float a) { return __float2half_rn(a); }

@@ -119,15 +119,15 @@ __device__ unsigned long long g_gemm_prof[296 * 8];
 // Epilogue global I/O experiments (r02, tools/gemm_bench.py, K = 1024 fp16 with skip rows; baseline 1.085 ms per launch):
 // the MMA phase of a tile is shared-memory-bandwidth bound (operand reads 64 B/cycle + TMA fill ~39 B/cycle of the SM's
 // 128 B/cycle) and the previous tile's pass 2 runs beside it, so moving the epilogue's global I/O off the staging tile
-// looked attractive.  It is not: BG_EPI_DIRECT_LOAD (a thread reads the skip / gathered pieces of its OWN row, eight
-// 16-byte loads per 128-byte line) 1.74 ms; plus BG_EPI_DIRECT_STORE (16-byte stores of its own row) 1.91 ms, and the
-// K = 128 encoder GEMM 0.30 -> 0.61 ms.  32 distinct lines per warp instruction cost far more in L1/L2 transactions than
-// the STS + LDS round trip through the warp's swizzled tile.  Both stay off.
-#ifndef BG_EPI_DIRECT_LOAD
-#define BG_EPI_DIRECT_LOAD 0
-#endif
-#ifndef BG_EPI_DIRECT_STORE
-#define BG_EPI_DIRECT_STORE 0
+// looked attractive.  With one ROW per thread it is not: a thread reading the skip pieces of its own row (eight 16-byte
+// loads per 128-byte line) 1.74 ms; plus 16-byte stores of its own row 1.91 ms, and the K = 128 encoder GEMM 0.30 ->
+// 0.61 ms.  32 distinct lines per warp instruction cost far more in L1/L2 transactions than the STS + LDS round trip
+// through the warp's swizzled tile (code removed; git 1543111).  What does pay: skip rows never enter shared memory at
+// all -- they are added to the coalesced output pieces on their way out (kSkipAtStore below).
+// 1 (default): pass 2 of the normalize / BN epilogue on packed fp32 pairs with the ReLU and the skip add on the packed
+// 16-bit result.  0: the scalar fp32 sequence (skip rows added in fp32 before the one rounding).
+#ifndef BG_EPI_F32X2
+#define BG_EPI_F32X2 1
 #endif
 
 enum : uint32_t { kTagEmpty = 1, kTagFull = 2, kTagTmemEmpty = 3, kTagTmemFull = 4 };
@@ -137,11 +137,11 @@ BG_DEVINL void named_bar_sync(uint32_t id, uint32_t threads) {
 }
 BG_DEVINL uint4 lds_v4(uint32_t addr) {
   uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
   return r;
 }
 BG_DEVINL void sts_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 template <int kRegs> BG_DEVINL void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs> BG_DEVINL void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
@@ -191,16 +191,28 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
   constexpr bool kPacked = false;
 #endif
   constexpr bool kPlainPacked = kPlain && kOut16;
+  constexpr bool kF32x2 = kOut16 && !kPlain && !kPacked && kAdd != kAddGather && BG_EPI_F32X2;
+  // skip rows are added to the packed 16-bit activation AFTER the transpose through the staging tile, in the coalesced
+  // layout they were loaded in: 256 KB less shared-memory traffic per tile (the MMA phase is shared-memory-bound)
+  constexpr bool kSkipAtStore = kAdd == kAddResidual && (kPlainPacked || kF32x2);
   constexpr int kChunkCols = 128 / (int)sizeof(TOut);           // columns per 128-byte row chunk: 64 / 32
   constexpr int kChunks = 256 / kChunkCols;                     // 4 / 8
   constexpr int kPer = 16 / (int)sizeof(TOut);                  // 8 or 4 columns per 16-byte piece
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (warp index through a shuffle: the compiler then KNOWS it is warp-uniform, so g-indexed reads of the per-column
+  // vectors become uniform-datapath constant loads feeding FFMA2 / FADD2 directly instead of per-thread indexed LDCs,
+  // which were half of pass 2's time -- r02 probe -DBG_EPI_NO_CONST)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int q = warp & 3;                                       // TMEM lane quarter this warp may read
   const int cb = g * 256;
   const uint32_t taddr = cx.tmem_base + ((uint32_t)(q * 32) << 16) + cb;
+#ifdef BG_EPI_NO_CONST                                          // timing probe (wrong results): per-column vectors as immediates
+  struct FakeVec { float a; BG_DEVINL float4 operator[](int) const { return make_float4(a, a + 0.25f, a + 0.5f, a + 0.75f); } };
+  const FakeVec bias4{0.5f}, scale4{2.f}, shift4{1.f};
+#else
   const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cb);
   const float4* scale4 = reinterpret_cast<const float4*>(p.scale + cb);
   const float4* shift4 = reinterpret_cast<const float4*>(p.shift + cb);
+#endif
   // per-thread view of the staging tile (own row = lane) and cooperative view (8 lanes per row, 4 rows per pass;
   // the swizzle of row 4t + r4 only depends on the parity of t)
   const uint32_t my_row = cx.stage_u32 + (uint32_t)lane * 128u;
@@ -227,49 +239,12 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
       add_base = reinterpret_cast<const char*>(p.residual) + (size_t)(warp_row0 + r4) * p.ldr * esz + (size_t)cb * esz + piece * 16;
     if constexpr (kAdd == kAddGather)
       add_base = reinterpret_cast<const char*>(p.gather[0]) + (size_t)cb * esz + piece * 16;
-    // this thread's own row: piece j (16 bytes) of 128-byte chunk ch of the addend (skip row, or gathered row(s))
-    [[maybe_unused]] const bool row_ok = m_row < p.m;
-    [[maybe_unused]] const char* own0 = nullptr;
-    [[maybe_unused]] const char* own1 = nullptr;
-    if constexpr (kAdd == kAddResidual)
-      own0 = reinterpret_cast<const char*>(p.residual) + (size_t)(row_ok ? m_row : 0) * p.ldr * esz + (size_t)cb * esz;
-    if constexpr (kAdd == kAddGather) {
-      own0 = reinterpret_cast<const char*>(p.gather[0]) + (size_t)gi0 * p.gather_ld * esz + (size_t)cb * esz;
-      own1 = reinterpret_cast<const char*>(p.gather[1]) + (size_t)gi1 * p.gather_ld * esz + (size_t)cb * esz;
-    }
-    auto load_piece = [&](int ch, int j) -> uint4 {
-      if constexpr (kAdd == kAddResidual) {
-        return row_ok ? ldg_nc_v4(own0 + ch * 128 + j * 16) : make_uint4(0u, 0u, 0u, 0u);
-      } else if constexpr (kAdd == kAddGather) {
-        uint4 a = ldg_v4(own0 + ch * 128 + j * 16);
-        if (p.n_gather > 1) {
-          const uint4 b = ldg_v4(own1 + ch * 128 + j * 16);
-          if constexpr (kOut16) {
-            a.x = Pack16<TOut>::hadd2(a.x, b.x); a.y = Pack16<TOut>::hadd2(a.y, b.y);
-            a.z = Pack16<TOut>::hadd2(a.z, b.z); a.w = Pack16<TOut>::hadd2(a.w, b.w);
-          } else {
-            a.x = __float_as_uint(__uint_as_float(a.x) + __uint_as_float(b.x)); a.y = __float_as_uint(__uint_as_float(a.y) + __uint_as_float(b.y));
-            a.z = __float_as_uint(__uint_as_float(a.z) + __uint_as_float(b.z)); a.w = __float_as_uint(__uint_as_float(a.w) + __uint_as_float(b.w));
-          }
-        }
-        return a;
-      } else {
-        return make_uint4(0u, 0u, 0u, 0u);
-      }
-    };
-#if BG_EPI_DIRECT_LOAD
-    auto fetch = [&](int ch) {
-      if constexpr (kAdd != kAddNone) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pre[j] = load_piece(ch, j);
-      }
-    };
-#else
     auto fetch = [&](int ch) {
       if constexpr (kAdd == kAddResidual) {
 #pragma unroll
         for (int t = 0; t < 8; ++t)
-          pre[t] = (t * 4 + r4 < rows_here) ? ldg_nc_v4(add_base + (size_t)t * 4 * p.ldr * esz + ch * 128)
+          pre[t] = (t * 4 + r4 < rows_here) ? (kSkipAtStore ? ldg_volatile_v4(add_base + (size_t)t * 4 * p.ldr * esz + ch * 128)
+                                                            : ldg_nc_v4(add_base + (size_t)t * 4 * p.ldr * esz + ch * 128))
                                             : make_uint4(0u, 0u, 0u, 0u);
       } else if constexpr (kAdd == kAddGather) {
 #pragma unroll
@@ -279,10 +254,11 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
         }
       }
     };
-#endif
-#if !BG_GEMM_P1_WIDE
-    fetch(0);                                                   // in flight while we wait for the MMAs
-#endif
+    // first addend chunk: skip rows that join at the store are first needed after chunk 0's math, so their loads are
+    // issued after pass 1 and the row-norm exchange (32 fewer live registers in pass 1; and a CTA barrier waits for
+    // volatile loads in flight).  Staged addends are needed at once: in flight while we wait for the MMAs.
+    constexpr bool kFetchLate = kSkipAtStore || BG_GEMM_P1_WIDE;
+    if constexpr (!kFetchLate) fetch(0);
 
     BG_PROF_T0();
     mbar_wait(cx.tmem_full_bar, it & 1u, kTagTmemFull);
@@ -290,18 +266,38 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
     tc_fence_after();
     BG_PROF_T0();
 
-    // ---- pass 1: row sum of squares of (acc + bias); 16-bit output also stashes the row.
-    // This is the one part of the epilogue the next tile's MMAs cannot overlap (the 128 x 512 fp32 accumulator is
-    // all of TMEM), so it is kept short: TMEM loads are double-buffered, BG_GEMM_P1_WIDE columns each.
+    // ---- pass 1: drain the accumulator.  This is the one part of the epilogue the next tile's MMAs cannot overlap
+    // (the 128 x 512 fp32 accumulator is all of TMEM), and it is issue-bound, not TMEM-bound: the bare drain takes
+    // ~0.7k cycles per tile, every instruction per column pair adds ~1k (r02 probe, -DBG_P1_DRAIN_ONLY: 0.93 ms per
+    // SAGE update against 1.04 ms with bias + sum of squares + pack in here).  So the normalize / BN epilogue
+    // (kDeferBias) only PACKS the raw accumulator here; the bias is added when the stash is unpacked (one mixed-precision
+    // add per column either way) and the row's sum of squares is taken from the stash after TMEM is released.
+    // Plain epilogues (no normalize) add the bias here and never need the sum.
+    constexpr bool kDeferBias = kF32x2;
     [[maybe_unused]] uint32_t stash[kOut16 ? 128 : 1];
     float ss = 0.f;
+    uint64_t ss_a = 0ull, ss_b = 0ull;                          // four independent partial sums of squares (two packed pairs)
     if (kOut16 || p.normalize) {
       auto consume4 = [&](const uint32_t* r, int c4) {          // c4: index of the 4-column group
+#ifdef BG_P1_DRAIN_ONLY                                         // timing probe (wrong results): TMEM -> registers only
+        if constexpr (kOut16) { stash[2 * c4] = r[0] ^ r[1]; stash[2 * c4 + 1] = r[2] ^ r[3]; return; }
+#endif
+        if constexpr (kDeferBias) {
+          stash[2 * c4] = Pack16<TOut>::pack(__uint_as_float(r[0]), __uint_as_float(r[1]));
+          stash[2 * c4 + 1] = Pack16<TOut>::pack(__uint_as_float(r[2]), __uint_as_float(r[3]));
+          return;
+        }
+        // packed fp32 pairs (FADD2 / FFMA2); the sum of squares is four independent chains
         const float4 b = bias4[c4];
-        const float v0 = __uint_as_float(r[0]) + b.x, v1 = __uint_as_float(r[1]) + b.y;
-        const float v2 = __uint_as_float(r[2]) + b.z, v3 = __uint_as_float(r[3]) + b.w;
-        ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
+        const uint64_t v01 = f2_add(f2_pack(__uint_as_float(r[0]), __uint_as_float(r[1])), f2_pack(b.x, b.y));
+        const uint64_t v23 = f2_add(f2_pack(__uint_as_float(r[2]), __uint_as_float(r[3])), f2_pack(b.z, b.w));
+        if constexpr (!kPlain) {
+          ss_a = f2_fma(v01, v01, ss_a);
+          ss_b = f2_fma(v23, v23, ss_b);
+        }
         if constexpr (kOut16) {
+          float v0, v1, v2, v3;
+          f2_unpack(v01, v0, v1); f2_unpack(v23, v2, v3);
           stash[2 * c4] = Pack16<TOut>::pack(v0, v1);
           stash[2 * c4 + 1] = Pack16<TOut>::pack(v2, v3);
         }
@@ -341,9 +337,28 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
       if (kCg == 1 || cx.rank == 0) mbar_arrive(cx.tmem_empty_bar);
       else mbar_arrive_cluster(cx.tmem_empty_bar, 0);
     }
-#if BG_GEMM_P1_WIDE
-    fetch(0);                                                   // (after pass 1: its 32 registers are the second TMEM buffer there)
-#endif
+    if constexpr (kDeferBias) {
+      if (p.normalize) {                                        // sum of squares of (stash + bias), beside the next tile's MMAs
+        uint64_t ss_c = 0ull, ss_d = 0ull;
+#pragma unroll
+        for (int c4 = 0; c4 < 64; c4 += 2) {
+          const float4 b0 = bias4[c4], b1 = bias4[c4 + 1];
+          using P = Pack16<TOut>;
+          const uint64_t p0 = f2_pack(P::add_lo(stash[2 * c4], b0.x), P::add_hi(stash[2 * c4], b0.y));
+          const uint64_t p1 = f2_pack(P::add_lo(stash[2 * c4 + 1], b0.z), P::add_hi(stash[2 * c4 + 1], b0.w));
+          const uint64_t p2 = f2_pack(P::add_lo(stash[2 * c4 + 2], b1.x), P::add_hi(stash[2 * c4 + 2], b1.y));
+          const uint64_t p3 = f2_pack(P::add_lo(stash[2 * c4 + 3], b1.z), P::add_hi(stash[2 * c4 + 3], b1.w));
+          ss_a = f2_fma(p0, p0, ss_a); ss_b = f2_fma(p1, p1, ss_b);
+          ss_c = f2_fma(p2, p2, ss_c); ss_d = f2_fma(p3, p3, ss_d);
+        }
+        ss_a = f2_add(ss_a, ss_c); ss_b = f2_add(ss_b, ss_d);
+      }
+    }
+    {
+      float s0, s1, s2, s3;
+      f2_unpack(ss_a, s0, s1); f2_unpack(ss_b, s2, s3);
+      ss = (s0 + s1) + (s2 + s3);
+    }
     float inv = 1.f;
     if (p.normalize) {                                          // exchange through the (idle) staging tiles
       cx.my_tile[lane] = ss;
@@ -353,6 +368,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
       if (p.inv_norm_out != nullptr && g == 0 && m_row < p.m) p.inv_norm_out[m_row] = inv;
     }
     [[maybe_unused]] const __half2 inv2 = __float2half2_rn(inv);
+    if constexpr (kFetchLate) fetch(0);
     BG_PROF_ADD(_pacc_b);
     BG_PROF_T0();
 
@@ -360,8 +376,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
     char* out_base = reinterpret_cast<char*>(p.out) + (size_t)(warp_row0 + r4) * out_row_bytes + (size_t)cb * esz + piece * 16;
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
-#if !BG_EPI_DIRECT_LOAD
-      if constexpr (kAdd != kAddNone) {
+      if constexpr (kAdd != kAddNone && !kSkipAtStore) {
         if constexpr (kAdd == kAddGather) {
           if (p.n_gather > 1) {                                 // second gathered matrix, summed on the way in
             const char* g1_base = reinterpret_cast<const char*>(p.gather[1]) + (size_t)cb * esz + piece * 16 + ch * 128;
@@ -386,25 +401,9 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
         __syncwarp();
         if (ch + 1 < kChunks) fetch(ch + 1);                    // next chunk's addends fly during the math below
       }
-#endif
-      // addend piece j of this chunk for the thread's row; in direct mode the register is refilled with the next chunk's
-      // piece at once (prefetch one chunk ahead without a second register set)
-      auto addend = [&](int j, uint32_t addr) -> uint4 {
-#if BG_EPI_DIRECT_LOAD
-        const uint4 a = pre[j];
-        if (ch + 1 < kChunks) pre[j] = load_piece(ch + 1, j);
-        return a;
-#else
-        return lds_v4(addr);
-#endif
-      };
-      auto emit = [&](int j, uint32_t addr, uint4 o) {
-#if BG_EPI_DIRECT_STORE
-        if (row_ok) stg_v4(reinterpret_cast<char*>(p.out) + (size_t)m_row * out_row_bytes + (size_t)cb * esz + ch * 128 + j * 16, o);
-#else
-        sts_v4(addr, o);
-#endif
-      };
+      // addend piece j of this chunk for the thread's own row (staged above)
+      auto addend = [&](int j, uint32_t addr) -> uint4 { return lds_v4(addr); };
+      auto emit = [&](int j, uint32_t addr, uint4 o) { sts_v4(addr, o); };
       [[maybe_unused]] uint32_t r[32];
       if constexpr (!kOut16) {
         tmem_ld_32x32(taddr + ch * 32, r);
@@ -420,7 +419,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
         for (int j = 0; j < 8; ++j) {
           const uint32_t addr = my_row + (((uint32_t)j ^ my_sw) << 4);
           uint32_t o[4] = {stash[ch * 32 + j * 4], stash[ch * 32 + j * 4 + 1], stash[ch * 32 + j * 4 + 2], stash[ch * 32 + j * 4 + 3]};
-          if constexpr (kAdd != kAddNone) {
+          if constexpr (kAdd != kAddNone && !kSkipAtStore) {
             const uint4 ad = addend(j, addr);
             const uint32_t au[4] = {ad.x, ad.y, ad.z, ad.w};
 #pragma unroll
@@ -463,6 +462,37 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
             o[e] = *reinterpret_cast<const uint32_t*>(&v);
           }
           emit(j, addr, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+      } else if constexpr (kF32x2) {
+        // SAGE update, 16-bit output: per column pair  stash + bias (2) . FMUL2 (x 1/|row|) . FFMA2 (BN scale, shift) .
+        // pack (1) . packed ReLU (1) . packed skip add (1)  = 7 instructions instead of 11.  ReLU commutes with the
+        // rounding to 16 bits (both monotonic, 0 is exact); the skip row is added to the ROUNDED activation, one more
+        // round-to-nearest of the stored value than the fp32 add had (|error| <= 2^-12 of the activation, unbiased).
+        const uint64_t inv_pair = f2_pack(inv, inv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = my_row + (((uint32_t)j ^ my_sw) << 4);
+          uint32_t o[4];
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const float4 sc = scale4[(ch * kChunkCols + j * kPer) / 4 + e2];
+            const float4 sh = shift4[(ch * kChunkCols + j * kPer) / 4 + e2];
+            const float4 bb = bias4[(ch * kChunkCols + j * kPer) / 4 + e2];
+            using P = Pack16<TOut>;                                           // stash + bias: one mixed-precision add per column
+            const uint32_t u0 = stash[ch * 32 + j * 4 + 2 * e2], u1 = stash[ch * 32 + j * 4 + 2 * e2 + 1];
+            uint64_t t0 = f2_mul(f2_pack(P::add_lo(u0, bb.x), P::add_hi(u0, bb.y)), inv_pair);
+            uint64_t t1 = f2_mul(f2_pack(P::add_lo(u1, bb.z), P::add_hi(u1, bb.w)), inv_pair);
+            t0 = f2_fma(t0, f2_pack(sc.x, sc.y), f2_pack(sh.x, sh.y));
+            t1 = f2_fma(t1, f2_pack(sc.z, sc.w), f2_pack(sh.z, sh.w));
+            float a0, a1, b0, b1;
+            f2_unpack(t0, a0, a1); f2_unpack(t1, b0, b1);
+            o[2 * e2] = Pack16<TOut>::pack(a0, a1);
+            o[2 * e2 + 1] = Pack16<TOut>::pack(b0, b1);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (p.relu) o[e] = Pack16<TOut>::relu2(o[e]);
+          emit(j, addr, make_uint4(o[0], o[1], o[2], o[3]));                // (the skip row joins at the coalesced store)
         }
       } else {
 #pragma unroll
@@ -524,16 +554,21 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
         emit(j, addr, o);
       }
       }
-#if !BG_EPI_DIRECT_STORE
       __syncwarp();
       // coalesced store: 4 rows x 128 B per instruction
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
-        const uint4 o = lds_v4(((t & 1) ? coop_odd : coop_even) + (uint32_t)(t >> 1) * 1024u);
+        uint4 o = lds_v4(((t & 1) ? coop_odd : coop_even) + (uint32_t)(t >> 1) * 1024u);
+        if constexpr (kSkipAtStore) {                           // skip rows: global -> registers -> global, never staged
+          o.x = Pack16<TOut>::hadd2(o.x, pre[t].x); o.y = Pack16<TOut>::hadd2(o.y, pre[t].y);
+          o.z = Pack16<TOut>::hadd2(o.z, pre[t].z); o.w = Pack16<TOut>::hadd2(o.w, pre[t].w);
+        }
         if (t * 4 + r4 < rows_here) stg_v4(out_base + (size_t)t * 4 * out_row_bytes + ch * 128, o);
       }
       __syncwarp();
-#endif
+      if constexpr (kSkipAtStore) {                             // (after the warp barrier: it waits for loads in flight)
+        if (ch + 1 < kChunks) fetch(ch + 1);                    // in flight during the next chunk's math
+      }
     }
     BG_PROF_ADD(_pacc_c);
   }
@@ -563,7 +598,7 @@ k_gemm512(const __grid_constant__ GemmParams p) {
   const uint32_t tmem_full_bar = bars_u32 + 8u * (2 * kStages);
   const uint32_t tmem_empty_bar = bars_u32 + 8u * (2 * kStages + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);    // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const uint32_t rank = (kCg == 2) ? cluster_ctarank() : 0u;
   const int tile0 = (kCg == 2) ? (blockIdx.x >> 1) : blockIdx.x;
@@ -728,6 +763,7 @@ typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, 
                                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_tensorMapEncodeTiled get_tensor_map_encoder();
+int gemm_sm_count();
 
 // [rows, k] row-major matrix, box = 128 rows x 128 bytes of K, 128B swizzle, zero fill out of bounds
 // (the same geometry serves the operand tiles and the epilogue's out / residual staging tiles)
@@ -780,7 +816,7 @@ static int launch_gemm512(const GemmParams& p, cudaStream_t stream) {
     BG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int sms = sm_count();
+  const int sms = gemm_sm_count();
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   if (kCg == 1) {

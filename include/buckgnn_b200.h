@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 8
+#define BG_ABI_VERSION 9
 
 typedef enum bg_status {
   BG_OK = 0,
@@ -54,6 +54,10 @@ const char* bg_last_error(void);
 int bg_device_check(void);
 /* info about the last barrier watchdog trip (debugging aid): 4 words copied to host */
 int bg_watchdog_info_host(uint32_t* out4_host);
+/* SM partition for kernels that are meant to run side by side on two streams: bg_gemm512 launches at most
+ * `gemm_sms` CTAs (rounded down to CTA pairs) and bg_sage_aggregate at most `agg_sms`; 0 = the whole device.
+ * Process-wide, takes effect at the next launch. */
+int bg_set_sm_partition(int gemm_sms, int agg_sms);
 
 /* ------------------------------------------------------------------ K1: CSR build
  * Replaces the implicit gather/scatter indexing inside PyG's
