@@ -147,6 +147,43 @@ def test_forward_full_size_properties(graphs, batch, pair):
     assert ((got - want).abs() / want.abs().clamp(min=1e-3)).max().item() < 1e-3
 
 
+def _sample_against_oracle(model_name, precision, graphs, sample, rtol, layers=6):
+    """full batch on the device; the oracle on a few graphs of the SAME batch (graphs are independent)"""
+    torch.manual_seed(1)
+    cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=layers,
+               pooling_layer="mean", model_name=model_name)
+    ref = OracleBuckGNN(**cfg).eval()
+    randomize_bn_stats(ref, realistic=True)
+    ours = BuckGNN(**cfg, precision=precision)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV).eval()
+    b = collate(graphs).to(DEV)
+    with torch.no_grad():
+        full, _ = ours(b.x, b.edge_index, b.edge_attr, b.batch)
+        sb = collate([graphs[i] for i in sample])
+        want, _ = ref(sb.x, sb.edge_index, sb.edge_attr, sb.batch)
+    assert full.shape == (len(graphs),) and bool(torch.isfinite(full).all())
+    got = full[sample].cpu()
+    rel = ((got - want).abs() / want.abs().clamp(min=1e-3)).max().item()
+    assert rel < rtol, f"{model_name} {precision}: max rel err {rel:.3e} >= {rtol}"
+
+
+def test_eagnn_configs2_size_sample_matches_oracle():
+    """BASELINE.json configs[2]: EA_GNN 6x512 on 128 stiffened plates with virtual edges (~0.5 M nodes, ~5.6 M edges);
+    two graphs of the batch against the fp32 oracle at rtol 1e-3 in the mode tools/bench_configs.py cfg3 reports."""
+    graphs = [make_plate_graph(i, stiffened=True) for i in range(128)]
+    assert sum(g.num_nodes for g in graphs) > 400_000
+    _sample_against_oracle("EA_GNN", "fp16", graphs, [0, 127], 1e-3)
+
+
+def test_meanaggr_configs4_mixed_mesh_scales_sample_matches_oracle():
+    """BASELINE.json configs[4]'s model and data: GraphSage_meanAggr on stiffened plates with virtual edges, mesh node
+    counts x1 .. x8 mixed in one batch (hub rows of 3 k .. 46 k entries; non-range hubs take the generic hub kernel)."""
+    scales = [1.0, 2 ** 0.5, 2.0, 2 ** 1.5]
+    graphs = [make_plate_graph(i, stiffened=True, scale=scales[i % 4]) for i in range(24)]
+    _sample_against_oracle("GraphSage_meanAggr", "fp16", graphs, [0, 1, 2], 1e-3)
+
+
 def test_sag_pool_full_size_invariants(batch):
     n, e = batch.num_nodes, batch.num_edges
     idx = build_graph_index(batch.edge_index, batch.batch, n)
