@@ -17,6 +17,7 @@
 //    writes the row -- no warp ever walks a 4k-32k neighbour list alone, and the
 //    result does not depend on scheduling.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace bg {
@@ -523,6 +524,14 @@ BG_DEVINL void narrow_accumulate(float (&acc)[Narrow<T>::kVals], const uint4& q)
   }
 }
 
+// the 16 bytes that leave an accumulator unchanged: zeros for sum / mean, -inf for max
+template <typename T, int kAggr> BG_DEVINL uint4 narrow_neutral() {
+  if constexpr (kAggr != BG_AGGR_MAX) return make_uint4(0u, 0u, 0u, 0u);
+  else if constexpr (sizeof(T) == 4) return make_uint4(0xff800000u, 0xff800000u, 0xff800000u, 0xff800000u);
+  else if constexpr (is_bf16<T>::value) return make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+  else return make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
+}
+
 template <typename T> BG_DEVINL uint4 narrow_pack(const float (&v)[Narrow<T>::kVals]) {
   uint4 o;
   if constexpr (sizeof(T) == 2) {
@@ -558,73 +567,82 @@ BG_DEVINL void narrow_gather(const T* __restrict__ x, const int32_t* __restrict_
   }
 }
 
-// neighbours my[0..cnt) (one per sub-warp lane, cnt <= kLanes), 4 rows in flight, tail issued as one group
-template <typename T, int kAggr>
-BG_DEVINL void narrow_gather_indexed(const T* __restrict__ x, int32_t my, int32_t cnt, int sl, uint32_t mask,
-                                     float (&acc)[Narrow<T>::kVals]) {
-  constexpr int kLanes = Narrow<T>::kLanes;
-  const char* xb = reinterpret_cast<const char*>(x) + (size_t)sl * 16;
-  constexpr size_t kRowBytes = 128 * sizeof(T);
-  int32_t j = 0;
-  for (; j + 4 <= cnt; j += 4) {
-    const uint4 q0 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j, kLanes) * kRowBytes);
-    const uint4 q1 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 1, kLanes) * kRowBytes);
-    const uint4 q2 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 2, kLanes) * kRowBytes);
-    const uint4 q3 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 3, kLanes) * kRowBytes);
-    narrow_accumulate<T, kAggr>(acc, q0); narrow_accumulate<T, kAggr>(acc, q1);
-    narrow_accumulate<T, kAggr>(acc, q2); narrow_accumulate<T, kAggr>(acc, q3);
-  }
-  const int32_t rem = cnt - j;
-  if (rem == 3) {
-    const uint4 q0 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j, kLanes) * kRowBytes);
-    const uint4 q1 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 1, kLanes) * kRowBytes);
-    const uint4 q2 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 2, kLanes) * kRowBytes);
-    narrow_accumulate<T, kAggr>(acc, q0); narrow_accumulate<T, kAggr>(acc, q1); narrow_accumulate<T, kAggr>(acc, q2);
-  } else if (rem == 2) {
-    const uint4 q0 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j, kLanes) * kRowBytes);
-    const uint4 q1 = ldg_v4(xb + (size_t)__shfl_sync(mask, my, j + 1, kLanes) * kRowBytes);
-    narrow_accumulate<T, kAggr>(acc, q0); narrow_accumulate<T, kAggr>(acc, q1);
-  } else if (rem == 1) {
-    narrow_accumulate<T, kAggr>(acc, ldg_v4(xb + (size_t)__shfl_sync(mask, my, j, kLanes) * kRowBytes));
-  }
-}
-
 // Same band walk and two-deep index pipeline as k_aggregate_rows, one SUB-warp (16 or 32 lanes) per row.
+// Control flow is WARP-UNIFORM: the two sub-warps of a 16-bit warp walk rows r0 and r0 + 1 in lock step (trip counts are
+// the maximum over the two), so every shuffle uses the full-warp mask with width = kLanes.  (Round 1 gave each sub-warp
+// its own mask and trip counts: a shuffle with a run-time mask compiles to a MATCH / WARPSYNC / ENDCOLLECTIVE sequence
+// and the sub-warps executed one after the other -- ncu: 267 warp instructions per row, issue slots 74 % busy at 19 % of
+// the DRAM peak.)  Up to 8 neighbours are in flight per row; slots past a row's degree are predicated off.
 template <typename T, int kAggr>
 __global__ void __launch_bounds__(1024, 1)
 k_aggregate_rows128(const T* __restrict__ x, T* __restrict__ out, int64_t N,
                     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col) {
   using NW = Narrow<T>;
+  constexpr int kLanes = NW::kLanes;
+  constexpr uint32_t kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / NW::kLanes, sl = lane % NW::kLanes;
-  const uint32_t mask = (NW::kLanes == 32) ? 0xffffffffu : (0xffffu << (16 * sub));
+  const int sub = lane / kLanes, sl = lane % kLanes;
   const int64_t band = (N + gridDim.x - 1) / gridDim.x;
   const int64_t r_beg = (int64_t)blockIdx.x * band;
   const int64_t r_end = min(N, r_beg + band);
   constexpr int kStride = 32 * NW::kRowsPerWarp;               // rows per CTA iteration (32 warps)
-  int64_t r = r_beg + warp * NW::kRowsPerWarp + sub;
-  int32_t beg = 0, end = 0, my = 0, nbeg = 0, nend = 0;
-  if (r < r_end) {
-    beg = rowptr[r]; end = rowptr[r + 1];
-    my = (sl < end - beg) ? col[beg + sl] : 0;
-  }
-  if (r + kStride < r_end) { nbeg = rowptr[r + kStride]; nend = rowptr[r + kStride + 1]; }
-  // the two sub-warps of a warp may run out of rows at different iterations: shuffles use per-sub-warp masks
-  for (; r < r_end; r += kStride) {
+  const char* xb = reinterpret_cast<const char*>(x) + (size_t)sl * 16;
+  constexpr size_t kRowBytes = 128 * sizeof(T);
+  auto offsets = [&](int64_t row, int32_t& b, int32_t& e) {
+    b = 0; e = 0;
+    if (row < r_end) { b = rowptr[row]; e = rowptr[row + 1]; }
+  };
+  int64_t r0 = r_beg + warp * NW::kRowsPerWarp;                // warp-uniform; this sub-warp's row is r0 + sub
+  int32_t beg, end, nbeg, nend;
+  offsets(r0 + sub, beg, end);
+  int32_t my = (sl < end - beg) ? col[beg + sl] : 0;
+  offsets(r0 + sub + kStride, nbeg, nend);
+  for (; r0 < r_end; r0 += kStride) {
+    const int64_t r = r0 + sub;
     const int32_t nmy = (sl < nend - nbeg) ? col[nbeg + sl] : 0;
-    int32_t n2beg = 0, n2end = 0;
-    if (r + 2 * kStride < r_end) { n2beg = rowptr[r + 2 * kStride]; n2end = rowptr[r + 2 * kStride + 1]; }
+    int32_t n2beg, n2end;
+    offsets(r + 2 * kStride, n2beg, n2end);
     const int32_t deg = end - beg;
-    if (deg <= kBigRowThreshold) {
-      float acc[NW::kVals];
+    const int32_t cnt = (deg <= kBigRowThreshold) ? min(deg, kLanes) : 0;     // hub rows: k_aggregate_hubs128
+    int32_t wcnt = cnt;
+    if constexpr (kLanes == 16) wcnt = max(wcnt, __shfl_xor_sync(kFull, cnt, 16));
+    float acc[NW::kVals];
 #pragma unroll
-      for (int i = 0; i < NW::kVals; ++i) acc[i] = agg_init<kAggr>();
-      narrow_gather_indexed<T, kAggr>(x, my, min(deg, NW::kLanes), sl, mask, acc);
-      if (deg > NW::kLanes) narrow_gather<T, kAggr>(x, col, beg + NW::kLanes, end, sl, mask, acc);
+    for (int i = 0; i < NW::kVals; ++i) acc[i] = agg_init<kAggr>();
+    for (int32_t base = 0; base < wcnt; base += 8) {           // uniform trip count
+      // kN neighbour slots, all loads in flight before the first add; a slot past this row's degree loads nothing and
+      // adds the neutral element (no per-lane branches).  Two unrolled bodies: 5 slots (plain quad meshes: 4 mesh
+      // neighbours + the super node) and 8.
+      auto round = [&](auto kN) {
+        constexpr int n = decltype(kN)::value;
+        uint4 q[n];
+#pragma unroll
+        for (int k = 0; k < n; ++k) {
+          const int32_t nb = __shfl_sync(kFull, my, (base + k) & (kLanes - 1), kLanes);
+          q[k] = narrow_neutral<T, kAggr>();
+          if (base + k < cnt) q[k] = ldg_v4(xb + (size_t)nb * kRowBytes);
+        }
+#pragma unroll
+        for (int k = 0; k < n; ++k) narrow_accumulate<T, kAggr>(acc, q[k]);
+      };
+      if (wcnt - base <= 5) round(std::integral_constant<int, 5>{});
+      else round(std::integral_constant<int, 8>{});
+    }
+    if (deg <= kBigRowThreshold && r < r_end) {
+      if (deg > kLanes) {                                      // rare: more neighbours than index lanes (sub-warp masks)
+        const uint32_t mask = (kLanes == 32) ? kFull : (0xffffu << (16 * sub));
+        narrow_gather<T, kAggr>(x, col, beg + kLanes, end, sl, mask, acc);
+      }
       if constexpr (kAggr == BG_AGGR_MEAN) {
         const float d = (float)max(deg, 1);
+        if constexpr (sizeof(T) == 4) {                        // fp32 rows: true division, as `sum / count` does
 #pragma unroll
-        for (int i = 0; i < NW::kVals; ++i) acc[i] = acc[i] / d;
+          for (int i = 0; i < NW::kVals; ++i) acc[i] = acc[i] / d;
+        } else {                                               // 16-bit rows: the 1-ulp difference is below the output rounding
+          const float rd = 1.f / d;
+#pragma unroll
+          for (int i = 0; i < NW::kVals; ++i) acc[i] *= rd;
+        }
       } else if constexpr (kAggr == BG_AGGR_MAX) {
         if (deg == 0) {
 #pragma unroll
