@@ -213,18 +213,39 @@ struct HubFold {
   float* partial;              // [n_big][parts][kStream][512] f32, lane-major
   int32_t parts;               // band slots per hub
 };
-#ifndef BG_AGG_STREAM_WARPS
-#define BG_AGG_STREAM_WARPS 2
-#endif
 #ifndef BG_AGG_STREAM_LEAD
 #define BG_AGG_STREAM_LEAD 96                // rows the hub stream may run ahead of the gather front
 #endif
 static_assert(BG_AGG_STREAM_LEAD >= 0, "a negative lead can starve the stream warps");
-constexpr int kStreamChunk = 8;              // rows per bulk copy
-constexpr int kStreamRing = 3;               // bulk copies in flight per stream warp
 constexpr int kStreamLead = BG_AGG_STREAM_LEAD;
+constexpr int kMaxStreamWarps = 2;           // bound used by the workspace size (bg_hubfold_workspace_bytes)
+// Stream geometry per storage type (r02 sweep, tools/gpu_r4b.sh on cfg 2, ms per launch): what matters is the bytes per
+// bulk copy and in flight, not the row count.  16-bit rows: ONE stream warp, 16-row (16 KB) copies, 3 in flight
+// 0.409 ms (two warps x 8 rows x 3: 0.422; 4-row copies 0.50; one warp x 8 rows x 6: 0.54; three warps 0.45).
+// fp32 rows: one warp, 4-row (8 KB) copies, 6 in flight 1.03 ms (two warps x 8 rows x 3: 1.13; 16-row copies x 3: 1.45).
+// A smaller ring would let the L1 window grow by a carve-out step (64 -> 32 KB), but every ring below ~48 KB lost more
+// on the stream than the L1 gained.  -DBG_AGG_STREAM_WARPS / _CHUNK / _RING override all types (experiments).
+template <typename T> struct StreamGeom {
+#if defined(BG_AGG_STREAM_WARPS) || defined(BG_AGG_STREAM_CHUNK) || defined(BG_AGG_STREAM_RING)
+#ifndef BG_AGG_STREAM_WARPS
+#define BG_AGG_STREAM_WARPS 2
+#endif
+#ifndef BG_AGG_STREAM_CHUNK
+#define BG_AGG_STREAM_CHUNK 8
+#endif
+#ifndef BG_AGG_STREAM_RING
+#define BG_AGG_STREAM_RING 3
+#endif
+  static constexpr int kWarps = BG_AGG_STREAM_WARPS, kChunk = BG_AGG_STREAM_CHUNK, kRing = BG_AGG_STREAM_RING;
+#else
+  static constexpr int kWarps = 1;
+  static constexpr int kChunk = sizeof(T) == 2 ? 16 : 4;   // rows per bulk copy (multiple of 4)
+  static constexpr int kRing = sizeof(T) == 2 ? 3 : 6;     // bulk copies in flight per stream warp
+#endif
+  static_assert(kChunk % 4 == 0 && kChunk <= 32 && kWarps <= kMaxStreamWarps, "stream geometry");
+};
 template <typename T> constexpr int agg_fold_smem() {
-  return 1024 + BG_AGG_STREAM_WARPS * kStreamRing * kStreamChunk * kHidden * (int)sizeof(T);
+  return 1024 + StreamGeom<T>::kWarps * StreamGeom<T>::kRing * StreamGeom<T>::kChunk * kHidden * (int)sizeof(T);
 }
 #ifndef BG_AGG_PF
 #define BG_AGG_PF 0                          // 0: no prefetch (default), 1: prefetch.global.L2, 2: prefetch.global.L1 -- both slower
@@ -238,7 +259,8 @@ template <typename T, int kAggr, bool kFold, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1)
 k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N, int64_t band,
                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const HubFold hf) {
-  constexpr int kStream = kFold ? BG_AGG_STREAM_WARPS : 0;
+  constexpr int kStream = kFold ? StreamGeom<T>::kWarps : 0;
+  constexpr int kStreamChunk = StreamGeom<T>::kChunk, kStreamRing = StreamGeom<T>::kRing;
   constexpr int kWarps = kThreads / 32 - kStream;            // gather warps
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t r_beg = (int64_t)blockIdx.x * band;
@@ -404,7 +426,7 @@ template <typename T, int kAggr>
 __global__ void __launch_bounds__(128)
 k_hub_finalize(T* __restrict__ out, int64_t N, int64_t band, const int32_t* __restrict__ rowptr,
                const int32_t* __restrict__ big_rows, const HubFold hf) {
-  constexpr int kStream = BG_AGG_STREAM_WARPS;
+  constexpr int kStream = StreamGeom<T>::kWarps, kStreamChunk = StreamGeom<T>::kChunk;
   const int32_t b = blockIdx.x;
   const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t r = big_rows[b];

@@ -64,7 +64,9 @@ __global__ void __launch_bounds__(kWinThreads, 1)
 k_aggregate_window(const T* __restrict__ x, T* __restrict__ out, int64_t N, int64_t band,
                    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const HubFold hf) {
   static_assert(sizeof(T) == 2, "16-bit rows only (a 216-row window of fp32 rows does not fit shared memory)");
-  constexpr int kHubWarps = kFold ? BG_AGG_STREAM_WARPS : 0;
+  constexpr int kHubWarps = kFold ? StreamGeom<T>::kWarps : 0;
+  // k_hub_finalize assumes chunk q of a band belongs to hub warp q % kWarps with StreamGeom's chunk size
+  static_assert(StreamGeom<T>::kWarps == 1 || StreamGeom<T>::kChunk == kWinChunk, "window / finalize chunk ownership");
   constexpr int kConsumers = kWinThreads / 32 - 1;               // every warp but the producer
   constexpr int kGather = kConsumers - kHubWarps;
   extern __shared__ __align__(1024) unsigned char win_smem[];

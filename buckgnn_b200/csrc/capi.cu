@@ -221,7 +221,13 @@ static int aggregate_dispatch(const T* x, T* out, int64_t N, const int32_t* rowp
 #define BG_AGGF_CASE(A)                                                                                              \
   case A: {                                                                                                          \
     static bool set = false;                                                                                         \
-    if (!set) { BG_CUDA_OK(cudaFuncSetAttribute(k_aggregate_rows<T, A, true, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; } \
+    if (!set) {                                                                                                      \
+      BG_CUDA_OK(cudaFuncSetAttribute(k_aggregate_rows<T, A, true, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      /* the gathers live on the L1 window: ask for the smallest shared-memory carve-out that holds the stream ring */ \
+      BG_CUDA_OK(cudaFuncSetAttribute(k_aggregate_rows<T, A, true, kThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                      (smem + 1024) * 100 / (228 * 1024) + 1));                                      \
+      set = true;                                                                                                    \
+    }                                                                                                                \
     k_aggregate_rows<T, A, true, kThreads><<<grid, kThreads, smem, stream>>>(x, out, N, band, rowptr, col, hf);      \
     k_hub_finalize<T, A><<<(unsigned)n_big, 128, 0, stream>>>(out, N, band, rowptr, big_rows, hf);                   \
   } break;
@@ -460,7 +466,7 @@ int bg_aggregate_workspace_bytes(int32_t n_big, size_t* bytes_host) {
 static size_t hubfold_bytes(int64_t N, int dtype, int32_t n_big, int32_t max_degree) {
   const unsigned grid = dtype == BG_F32 ? agg_grid<float>(N) : agg_grid<__half>(N);
   const int64_t band = ceil_div64(N > 0 ? N : 1, grid);
-  return (size_t)n_big * (size_t)hub_parts(band, max_degree) * BG_AGG_STREAM_WARPS * kHidden * sizeof(float) + 256;
+  return (size_t)n_big * (size_t)hub_parts(band, max_degree) * kMaxStreamWarps * kHidden * sizeof(float) + 256;
 }
 int bg_hubfold_workspace_bytes(int64_t N, int dtype, int32_t n_big, int32_t max_degree, size_t* bytes_host) {
   if (!bytes_host || n_big < 0 || N < 0 || max_degree < 0) return fail(BG_ERR_INVALID, "bg_hubfold_workspace_bytes: bad argument");

@@ -198,6 +198,9 @@ BG_DEVINL void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef BG_WAIT_SLEEP                     // experiment: back off between polls (idle-warp power); tag 2/3 = the MMA warp's waits
+    if (tag != 2u && tag != 3u) __nanosleep(BG_WAIT_SLEEP);
+#endif
     if ((++spins & 1023u) == 0 && clock64() - t0 > (1ll << 31)) watchdog_trip(tag, bar, parity);
   }
 }

@@ -676,12 +676,26 @@ k_gemm512(const __grid_constant__ GemmParams p) {
                 for (int j = 0; j < Cfg::kBRows / 128; ++j)
                   tma_load_2d(sb + j * 16384, map_b, full_bar(stage), k0, brow0 + j * 128);
               } else {
-                if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+                // timing probes (wrong results): -DBG_PROBE_NO_B / -DBG_PROBE_NO_A load the weight / activation stages
+                // of a CTA's FIRST tile only -- what the kernel would cost if that operand's L2 (and HBM) traffic were free
+#ifdef BG_PROBE_NO_B
+                const bool load_b = tile == tile0;
+#else
+                constexpr bool load_b = true;
+#endif
+#ifdef BG_PROBE_NO_A
+                const bool load_a = tile == tile0;
+#else
+                constexpr bool load_a = true;
+#endif
+                if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * ((load_a ? kATileBytes : 0) + (load_b ? Cfg::kBTileBytes : 0)));
                 else mbar_arrive_cluster(full_bar(stage), 0);
-                tma_load_2d_cg2(sa, map_a, full_bar(stage), k0, row0);
+                if (load_a) tma_load_2d_cg2(sa, map_a, full_bar(stage), k0, row0);
+                if (load_b) {
 #pragma unroll
-                for (int j = 0; j < Cfg::kBRows / 128; ++j)      // N half j: weight rows j*256 + rank*128
-                  tma_load_2d_cg2(sb + j * 16384, map_b, full_bar(stage), k0, brow0 + j * 256 + (int32_t)rank * 128);
+                  for (int j = 0; j < Cfg::kBRows / 128; ++j)      // N half j: weight rows j*256 + rank*128
+                    tma_load_2d_cg2(sb + j * 16384, map_b, full_bar(stage), k0, brow0 + j * 256 + (int32_t)rank * 128);
+                }
               }
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }

@@ -35,6 +35,26 @@ def partition_graphs(costs: Sequence[int], world_size: int) -> List[List[int]]:
     return [sorted(p) for p in parts]
 
 
+def batches_by_node_budget(indices: Sequence[int], num_nodes: Sequence[int], node_budget: int) -> List[List[int]]:
+    """Cut a rank's shard (graph indices, in order) into batches of at most `node_budget` nodes -- the inference
+    loop of configs[4], whose meshes differ 8x in size, batches by memory footprint where `INFERENCE.py:94`
+    batches by graph count.  A graph larger than the budget forms a batch of its own; order is kept; every
+    index appears exactly once."""
+    out: List[List[int]] = []
+    cur: List[int] = []
+    load = 0
+    for i in indices:
+        n = int(num_nodes[i])
+        if cur and load + n > node_budget:
+            out.append(cur)
+            cur, load = [], 0
+        cur.append(i)
+        load += n
+    if cur:
+        out.append(cur)
+    return out
+
+
 def sharded_predict(graphs: Sequence[PlateGraph], forward: Callable, device, group=None) -> torch.Tensor:
     """Run `forward(batch) -> pred [G_local]` on this rank's shard of `graphs` and return the
     predictions of ALL graphs, in the original order, on every rank."""

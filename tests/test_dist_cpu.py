@@ -161,3 +161,14 @@ def test_grad_sync_buckets_world_size_2():
         want3 = torch.zeros(2, 3)
         want3[:, 1:] = 15.0
         assert torch.allclose(torch.tensor(g3), want3)
+
+
+def test_batches_by_node_budget_keeps_order_and_covers_every_graph():
+    from buckgnn_b200.dist import batches_by_node_budget
+    nodes = [4000, 8000, 16000, 32000, 4000, 4000, 50000, 1000]
+    idx = [0, 2, 3, 4, 6, 7]
+    out = batches_by_node_budget(idx, nodes, 40000)
+    assert [i for b in out for i in b] == idx                       # order kept, nothing lost or repeated
+    assert out == [[0, 2], [3, 4], [6], [7]]                        # a graph above the budget rides alone
+    assert all(sum(nodes[i] for i in b) <= 40000 or len(b) == 1 for b in out)
+    assert batches_by_node_budget([], nodes, 10) == []

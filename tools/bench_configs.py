@@ -35,7 +35,7 @@ def timed(model, b, steps=5, warmup=2):
     return ms, k, pred
 
 
-def seeded_model(cfg, precision, **kw):
+def seeded_model(cfg, precision, device=None, **kw):
     """Seeded weights with BatchNorm running statistics of a trained network's magnitude (parity of these
     configurations against the oracle is tests/test_gpu_forward.py's job, not this tool's)."""
     torch.manual_seed(0)
@@ -49,7 +49,7 @@ def seeded_model(cfg, precision, **kw):
                 mod.running_var.copy_((torch.rand(c, generator=g) + 0.5) / c)
                 mod.weight.copy_(torch.rand(c, generator=g) + 0.5)
                 mod.bias.copy_(torch.randn(c, generator=g) * 0.1)
-    return m.to(DEV).eval()
+    return m.to(device or DEV).eval()
 
 
 def main():
