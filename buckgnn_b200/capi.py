@@ -20,7 +20,7 @@ BG_BF16, BG_F32, BG_F16 = 0, 1, 2
 BG_AGGR_MEAN, BG_AGGR_SUM, BG_AGGR_MAX = 0, 1, 2
 BG_BIG_ROW_THRESHOLD = 64
 BG_MAX_GEMM_SEGMENTS = 8
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 AGGR_CODES = {"mean": BG_AGGR_MEAN, "sum": BG_AGGR_SUM, "add": BG_AGGR_SUM, "max": BG_AGGR_MAX}
 
@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     "bg_csr_max_big_rows", "bg_csr_workspace_bytes", "bg_csr_build",
     "bg_batch_info", "bg_graph_ptr_build", "bg_publish_words", "bg_encoder_front",
     "bg_aggregate_workspace_bytes", "bg_hubfold_workspace_bytes", "bg_sage_aggregate", "bg_gemm512",
-    "bg_wgrad512", "bg_pool_workspace_bytes", "bg_pool_head", "bg_cast_f32", "bg_split_tf32",
+    "bg_wgrad512", "bg_pool_workspace_bytes", "bg_pool_head", "bg_pool_block_flags", "bg_pool_head_blocks", "bg_cast_f32", "bg_split_tf32",
     "bg_expand_rowptr", "bg_add",
     "bg_train_workspace_bytes", "bg_bn_batch_stats", "bg_bn_act_forward", "bg_sage_backward_rows",
     "bg_transpose_chunks", "bg_mask_narrow", "bg_reduce_partials", "bg_colsum_workspace_bytes", "bg_colsum", "bg_pool_backward",
@@ -56,7 +56,8 @@ class Epilogue(C.Structure):
     _fields_ = [("bias_host", C.c_void_p), ("bn_scale_host", C.c_void_p), ("bn_shift_host", C.c_void_p),
                 ("residual", C.c_void_p), ("ldr", C.c_int64), ("normalize", C.c_int32), ("relu", C.c_int32),
                 ("gather", C.c_void_p * 2),
-                ("gather_idx", C.c_void_p * 2), ("gather_ld", C.c_int64), ("inv_norm_out", C.c_void_p)]
+                ("gather_idx", C.c_void_p * 2), ("gather_ld", C.c_int64), ("inv_norm_out", C.c_void_p),
+                ("pool_block_sums", C.c_void_p), ("pool_block_keep", C.c_void_p)]
 
 
 _lib = None
@@ -88,6 +89,9 @@ _SIGNATURES = {
     "bg_pool_workspace_bytes": (C.c_int, [_I64, _SZP]),
     "bg_pool_head": (C.c_int, [_P, C.c_int, _I64, _P, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P,
                                _P, C.c_size_t, _P, _P]),
+    "bg_pool_block_flags": (C.c_int, [_P, _I64, _I64, _P, _P]),
+    "bg_pool_head_blocks": (C.c_int, [_P, C.c_int, _I64, _P, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P,
+                                      _P, _P, _P, C.c_size_t, _P, _P]),
     "bg_cast_f32": (C.c_int, [_P, _P, C.c_int, _I64, _P]),
     "bg_split_tf32": (C.c_int, [_P, _P, _P, _I64, _P]),
     "bg_train_workspace_bytes": (C.c_int, [_I64, _SZP]),
@@ -235,15 +239,16 @@ def sage_aggregate(x, out, dtype, n_nodes, rowptr, col, big_rows, n_big, aggr, w
 
 def gemm512(segments, m, a_dtype, b_dtype, out, out_dtype, ldo, stream, *, bias=None, bn_scale=None,
             bn_shift=None, residual=None, ldr=0, normalize=False, relu=False, cta_group=2,
-            gather=(), gather_ld=512, inv_norm_out=None, b_groups=0):
+            gather=(), gather_ld=512, inv_norm_out=None, b_groups=0, pool_block_sums=None, pool_block_keep=None):
     """segments: list of (a_ptr, lda, b_ptr, ldb, k); bias / bn_scale / bn_shift are HOST pointers;
-    gather: up to two (matrix_ptr, index_ptr) pairs of gathered pre-activation addends."""
+    gather: up to two (matrix_ptr, index_ptr) pairs of gathered pre-activation addends;
+    pool_block_sums / pool_block_keep: the pool-fused epilogue of the last layer (see the header)."""
     n = len(segments)
     arr = (GemmSegment * n)(*[GemmSegment(a, lda, b, ldb, k, b_groups) for (a, lda, b, ldb, k) in segments])
     gm = (C.c_void_p * 2)(*([g[0] for g in gather] + [None] * (2 - len(gather))))
     gi = (C.c_void_p * 2)(*([g[1] for g in gather] + [None] * (2 - len(gather))))
     epi = Epilogue(bias, bn_scale, bn_shift, residual, ldr, int(bool(normalize)), int(bool(relu)),
-                   gm, gi, gather_ld, inv_norm_out)
+                   gm, gi, gather_ld, inv_norm_out, pool_block_sums, pool_block_keep)
     _check(load().bg_gemm512(arr, n, m, a_dtype, b_dtype, C.byref(epi), out, out_dtype, ldo, cta_group, stream),
            "bg_gemm512")
 
@@ -256,6 +261,17 @@ def pool_head(x, dtype, n_nodes, graph_ptr, n_graphs, pool_mode, pre_w, pre_b, w
               pred, pooled_out, ws, ws_bytes, stream, nonfinite=None):
     _check(load().bg_pool_head(x, dtype, n_nodes, graph_ptr, n_graphs, pool_mode, pre_w, pre_b, w1, b1, w2, b2,
                                w3, b3, out_dim, pred, pooled_out, ws, ws_bytes, nonfinite, stream), "bg_pool_head")
+
+
+def pool_block_flags(graph_ptr, n_graphs, n_nodes, keep, stream):
+    _check(load().bg_pool_block_flags(graph_ptr, n_graphs, n_nodes, keep, stream), "bg_pool_block_flags")
+
+
+def pool_head_blocks(x, dtype, n_nodes, graph_ptr, n_graphs, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim,
+                     pred, pooled_out, block_sums, keep, ws, ws_bytes, stream, nonfinite=None):
+    _check(load().bg_pool_head_blocks(x, dtype, n_nodes, graph_ptr, n_graphs, pool_mode, pre_w, pre_b, w1, b1, w2, b2,
+                                      w3, b3, out_dim, pred, pooled_out, block_sums, keep, ws, ws_bytes, nonfinite,
+                                      stream), "bg_pool_head_blocks")
 
 
 def cast_f32(src, dst, dst_dtype, n, stream):

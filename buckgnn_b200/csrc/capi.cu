@@ -576,6 +576,13 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
     p.residual = epi->residual; p.ldr = epi->ldr;
     if (epi->inv_norm_out && !epi->normalize) return fail(BG_ERR_INVALID, "bg_gemm512: inv_norm_out needs normalize");
     p.inv_norm_out = epi->inv_norm_out;
+    if ((epi->pool_block_sums != nullptr) != (epi->pool_block_keep != nullptr))
+      return fail(BG_ERR_INVALID, "bg_gemm512: pool_block_sums and pool_block_keep go together");
+    if (epi->pool_block_sums) {
+      if (!epi->normalize || out_dtype == BG_F32 || epi->residual || p.n_gather > 0 || !aligned16(epi->pool_block_sums))
+        return fail(BG_ERR_UNSUPPORTED, "bg_gemm512: the pool-fused epilogue needs normalize, a 16-bit output and no addends");
+      p.pool_sums = epi->pool_block_sums; p.pool_keep = epi->pool_block_keep;
+    }
   }
   for (int i = 0; i < kHidden / 2; ++i) {
     const __half2 sc = __floats2half2_rn(p.scale[2 * i], p.scale[2 * i + 1]);
@@ -591,6 +598,9 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
    : out_dtype == BG_F16 ? launch_gemm512<2, __half, ADD, PLAIN>(p, stream)                    \
                          : launch_gemm512<2, float, ADD, false>(p, stream))
 #define BG_GEMM_OUT(ADD) (plain ? BG_GEMM_OUT2(ADD, true) : BG_GEMM_OUT2(ADD, false))
+  if (p.pool_sums)
+    return out_dtype == BG_BF16 ? launch_gemm512<2, __nv_bfloat16, kAddNone, false, true>(p, stream)
+                                : launch_gemm512<2, __half, kAddNone, false, true>(p, stream);
   if (p.n_gather > 0) return BG_GEMM_OUT(kAddGather);
   if (p.residual) return BG_GEMM_OUT(kAddResidual);
   return BG_GEMM_OUT(kAddNone);
@@ -663,6 +673,51 @@ int bg_pool_head(const void* x, int dtype, int64_t N, const int32_t* graph_ptr, 
     pool_launch(static_cast<const float*>(x), graph_ptr, G, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, partial, nonfinite_flag, stream);
   else
     return fail(BG_ERR_INVALID, "bg_pool_head: bad dtype");
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_pool_block_flags(const int32_t* graph_ptr, int64_t G, int64_t N, uint8_t* keep, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (G < 0 || N < 0 || !graph_ptr || (N > 0 && !keep)) return fail(BG_ERR_INVALID, "bg_pool_block_flags: bad argument");
+  if (N == 0) return BG_OK;
+  BG_CUDA_OK(cudaMemsetAsync(keep, 0, (size_t)ceil_div64(N, 32), stream));
+  k_pool_block_flags<<<(unsigned)ceil_div64(G + 1, 256), 256, 0, stream>>>(graph_ptr, G, N, keep);
+  BG_LAUNCH_OK();
+  return BG_OK;
+}
+
+int bg_pool_head_blocks(const void* x, int dtype, int64_t N, const int32_t* graph_ptr, int64_t G, int pool_mode,
+                        const float* pre_w, const float* pre_b,
+                        const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
+                        int32_t out_dim, float* pred, float* pooled_out, const float* block_sums, const uint8_t* keep,
+                        void* workspace, size_t workspace_bytes, const int32_t* nonfinite_flag, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (G < 0 || N < 0 || G > 65535LL * 1024) return fail(BG_ERR_INVALID, "bg_pool_head_blocks: bad size");
+  if (G == 0) return BG_OK;
+  if (out_dim < 1 || out_dim > 64) return fail(BG_ERR_UNSUPPORTED, "bg_pool_head_blocks: out_dim must be in [1,64]");
+  if (pool_mode < BG_POOL_MEAN || pool_mode > BG_POOL_SUPERNODE_WITH_POOLING) return fail(BG_ERR_INVALID, "bg_pool_head_blocks: bad pool_mode");
+  if ((pre_w != nullptr) != (pre_b != nullptr) || (pre_w && pool_mode > BG_POOL_MEAN_NO_SUPER) || (pre_w && !aligned16(pre_w)))
+    return fail(BG_ERR_INVALID, "bg_pool_head_blocks: pooling MLP needs both pre_w and pre_b and a mean pooling mode");
+  if (!graph_ptr || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !pred || !aligned16(w1) ||
+      (N > 0 && (!x || !aligned16(x) || !block_sums || !aligned16(block_sums) || !keep)))
+    return fail(BG_ERR_INVALID, "bg_pool_head_blocks: bad pointer");
+  if (dtype != BG_BF16 && dtype != BG_F16) return fail(BG_ERR_UNSUPPORTED, "bg_pool_head_blocks: 16-bit rows only");
+  size_t need = 0;
+  bg_pool_workspace_bytes(G, &need);
+  if (!workspace || workspace_bytes < need) return fail(BG_ERR_WORKSPACE, "bg_pool_head_blocks: workspace too small");
+  float* partial = static_cast<float*>(workspace);
+  const int exclude_last = (pool_mode == BG_POOL_MEAN_NO_SUPER || pool_mode == BG_POOL_SUPERNODE_WITH_POOLING) ? 1 : 0;
+  dim3 grid((unsigned)G, kPoolSlices);
+  if (dtype == BG_BF16) {
+    const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+    if (pool_mode != BG_POOL_SUPERNODE_ONLY) k_pool_partial_blocks<__nv_bfloat16><<<grid, 256, 0, stream>>>(xp, block_sums, keep, graph_ptr, partial, exclude_last);
+    k_pool_head<__nv_bfloat16><<<(unsigned)G, 128, 0, stream>>>(xp, partial, graph_ptr, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, nonfinite_flag);
+  } else {
+    const __half* xp = static_cast<const __half*>(x);
+    if (pool_mode != BG_POOL_SUPERNODE_ONLY) k_pool_partial_blocks<__half><<<grid, 256, 0, stream>>>(xp, block_sums, keep, graph_ptr, partial, exclude_last);
+    k_pool_head<__half><<<(unsigned)G, 128, 0, stream>>>(xp, partial, graph_ptr, pool_mode, pre_w, pre_b, w1, b1, w2, b2, w3, b3, out_dim, pred, pooled_out, nonfinite_flag);
+  }
   BG_LAUNCH_OK();
   return BG_OK;
 }

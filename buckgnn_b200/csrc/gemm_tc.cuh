@@ -81,6 +81,8 @@ struct alignas(64) GemmParams {
   const int32_t* gidx[2];           // [M] row index into gather[k]
   int64_t gather_ld;
   float* inv_norm_out;              // [M] f32 or null: 1 / max(|row|, eps) of normalized rows (saved for the backward pass)
+  float* pool_sums;                 // kPool: [ceil(M/32), 512] f32 column sums of every 32-row block of the OUTPUT rows
+  const uint8_t* pool_keep;         // kPool: [ceil(M/32)] only blocks with a non-zero flag are also stored to `out`
   int32_t b_group_tiles;            // 0: one B for all rows; t: row tile i multiplies B rows [(i / t) * 512, +512)
   int32_t mn_major;                 // 1: weight-gradient mode.  seg[0].a / .b map the ROW-MAJOR [n_rows, 512] matrices
                                     // dz and act; out[(s*512 + o), i] = sum over the nodes of chunk s of dz[n,o] act[n,i]:
@@ -178,8 +180,16 @@ enum : int { kAddNone = 0, kAddResidual = 1, kAddGather = 2 };
 // input-gradient GEMMs).  With a 16-bit output, pass 2 then is "stash (+ gathered rows) -> ReLU (+ skip rows)" on
 // packed pairs: HADD2 / HMNMX2 round exactly like the fp32 path does (the sum of two 16-bit values is exact in
 // fp32, so both round the exact sum once), at ~1.5 instead of ~6.5 instructions per column.
-template <int kCg, typename TOut, int kAdd, bool kPlain>
+// kPool (last GraphSAGE layer of a graph-level model, 16-bit output, normalize epilogue, no addends): the layer's
+// output is only read by the pooling layer (Models/BuckGNN.py:515), which is linear in the rows, so the epilogue sums
+// the rows it produces instead of storing them -- per 32-row block (one warp's rows) and column, fp32, fixed order --
+// and writes [M/32, 512] sums (6 % of the bytes).  Blocks holding the first or last row of a graph (pool_keep) are
+// stored as well: bg_pool_head_blocks takes those rows from `out`, so graph boundaries inside a block, super-node
+// pooling variants and graphs smaller than a block all stay exact.  Saves the 1 GB write here and the 1 GB read of
+// the pooling pass (cfg 2).
+template <int kCg, typename TOut, int kAdd, bool kPlain, bool kPool = false>
 BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g) {
+  static_assert(!kPool || (sizeof(TOut) == 2 && kAdd == kAddNone && !kPlain), "pool-fused epilogue: 16-bit normalize epilogue only");
   constexpr bool kOut16 = sizeof(TOut) == 2;
   // -DBG_GEMM_PACKED_EPILOGUE: pass 2 of fp16 outputs as packed half2 math also WITH normalize / BN.  Measured
   // (r01): SAGE update 1.04 -> 1.00 ms, but the prediction error vs the fp32 oracle rises from 6e-5 to 2.8e-4
@@ -228,6 +238,8 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
     const int64_t warp_row0 = (int64_t)tile * (kTileM * kCg) + (int64_t)cx.rank * kTileM + q * 32;
     const int64_t m_row = warp_row0 + lane;
     const int rows_here = (int)min((int64_t)32, p.m - warp_row0);                 // <= 0: nothing to store
+    [[maybe_unused]] bool keep_rows = true;
+    if constexpr (kPool) keep_rows = rows_here > 0 && p.pool_keep[warp_row0 >> 5] != 0;   // warp-uniform
     [[maybe_unused]] int32_t gi0 = 0, gi1 = 0;
     if constexpr (kAdd == kAddGather) {
       if (m_row < p.m) { gi0 = p.gidx[0][m_row]; if (p.n_gather > 1) gi1 = p.gidx[1][m_row]; }
@@ -556,6 +568,11 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
       }
       __syncwarp();
       // coalesced store: 4 rows x 128 B per instruction
+      [[maybe_unused]] float cs[8];                             // kPool: this lane's 8 columns summed over its 8 rows
+      if constexpr (kPool) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+      }
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         uint4 o = lds_v4(((t & 1) ? coop_odd : coop_even) + (uint32_t)(t >> 1) * 1024u);
@@ -563,7 +580,28 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
           o.x = Pack16<TOut>::hadd2(o.x, pre[t].x); o.y = Pack16<TOut>::hadd2(o.y, pre[t].y);
           o.z = Pack16<TOut>::hadd2(o.z, pre[t].z); o.w = Pack16<TOut>::hadd2(o.w, pre[t].w);
         }
-        if (t * 4 + r4 < rows_here) stg_v4(out_base + (size_t)t * 4 * out_row_bytes + ch * 128, o);
+        if constexpr (kPool) {
+          if (t * 4 + r4 < rows_here) {                         // one mixed-precision add per column (the stored value)
+            using P = Pack16<TOut>;
+            cs[0] = P::add_lo(o.x, cs[0]); cs[1] = P::add_hi(o.x, cs[1]); cs[2] = P::add_lo(o.y, cs[2]); cs[3] = P::add_hi(o.y, cs[3]);
+            cs[4] = P::add_lo(o.z, cs[4]); cs[5] = P::add_hi(o.z, cs[5]); cs[6] = P::add_lo(o.w, cs[6]); cs[7] = P::add_hi(o.w, cs[7]);
+            if (keep_rows) stg_v4(out_base + (size_t)t * 4 * out_row_bytes + ch * 128, o);
+          }
+        } else {
+          if (t * 4 + r4 < rows_here) stg_v4(out_base + (size_t)t * 4 * out_row_bytes + ch * 128, o);
+        }
+      }
+      if constexpr (kPool) {                                    // rows 4t + r4: add the four r4 groups, lanes 0..7 write
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
+          cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+        }
+        if (r4 == 0 && rows_here > 0) {
+          float4* dst = reinterpret_cast<float4*>(p.pool_sums + (size_t)(warp_row0 >> 5) * kHidden + cb + ch * kChunkCols + piece * kPer);
+          dst[0] = make_float4(cs[0], cs[1], cs[2], cs[3]);
+          dst[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
+        }
       }
       __syncwarp();
       if constexpr (kSkipAtStore) {                             // (after the warp barrier: it waits for loads in flight)
@@ -579,7 +617,7 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
 #endif
 }
 
-template <int kCg, typename TOut, int kAdd, bool kPlain>
+template <int kCg, typename TOut, int kAdd, bool kPlain, bool kPool = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm512(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<kCg>;
@@ -762,7 +800,7 @@ k_gemm512(const __grid_constant__ GemmParams p) {
                     reinterpret_cast<float*>(epi_gen + ew * kEpiStageBytes),
                     reinterpret_cast<const float*>(epi_gen + (ew ^ 4) * kEpiStageBytes),
                     tmem_full_bar, tmem_empty_bar, rank, tile0, tile_stride};
-    epilogue_warp<kCg, TOut, kAdd, kPlain>(p, cx, ew >> 2);
+    epilogue_warp<kCg, TOut, kAdd, kPlain, kPool>(p, cx, ew >> 2);
   }
 
   // ---- teardown
@@ -821,10 +859,10 @@ static inline int make_mn_operand_map(CUtensorMap* map, const void* base, int64_
   return r == CUDA_SUCCESS ? BG_OK : BG_ERR_CUDA;
 }
 
-template <int kCg, typename TOut, int kAdd, bool kPlain>
+template <int kCg, typename TOut, int kAdd, bool kPlain, bool kPool = false>
 static int launch_gemm512(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<kCg>;
-  auto kern = k_gemm512<kCg, TOut, kAdd, kPlain>;
+  auto kern = k_gemm512<kCg, TOut, kAdd, kPlain, kPool>;
   static bool attr_set = false;
   if (!attr_set) {
     BG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

@@ -61,6 +61,47 @@ k_pool_partial(const T* __restrict__ x, const int32_t* __restrict__ graph_ptr, f
   }
 }
 
+// ---- pooling over the 32-row block sums a pool-fused bg_gemm512 epilogue wrote (gemm_tc.cuh, kPool)
+// keep[b] = 1 for every 32-row block that holds the first or the last row of a graph: those blocks are read row by
+// row from x (the GEMM stored them), every other block lies wholly inside one graph and contributes its block sum.
+__global__ void k_pool_block_flags(const int32_t* __restrict__ graph_ptr, int64_t G, int64_t N, uint8_t* __restrict__ keep) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > G) return;
+  const int64_t p = graph_ptr[i];
+  if (p < N) keep[p >> 5] = 1;
+  if (p > 0) keep[(p - 1) >> 5] = 1;
+}
+
+// grid (G, kPoolSlices), 256 threads = 2 columns each; same partial[g][slice][512] layout as k_pool_partial
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_pool_partial_blocks(const T* __restrict__ x, const float* __restrict__ block_sums, const uint8_t* __restrict__ keep,
+                      const int32_t* __restrict__ graph_ptr, float* __restrict__ partial, int exclude_last) {
+  static_assert(sizeof(T) == 2, "block sums come from the 16-bit pool-fused epilogue");
+  const int g = blockIdx.x, slice = blockIdx.y, t = threadIdx.x;
+  const int32_t beg = graph_ptr[g], cnt = max(graph_ptr[g + 1] - beg - (exclude_last ? 1 : 0), 0);
+  const int32_t end = beg + cnt;
+  float a0 = 0.f, a1 = 0.f;
+  if (cnt > 0) {
+    const int32_t b0 = beg >> 5, nb = ((end - 1) >> 5) - b0 + 1;
+    const int32_t s_b = b0 + (int32_t)((int64_t)nb * slice / kPoolSlices);
+    const int32_t e_b = b0 + (int32_t)((int64_t)nb * (slice + 1) / kPoolSlices);
+    for (int32_t b = s_b; b < e_b; ++b) {
+      if (!keep[b]) {                                 // no graph starts or ends in this block: all 32 rows are ours
+        const float2 v = __ldg(reinterpret_cast<const float2*>(block_sums + (size_t)b * kHidden) + t);
+        a0 += v.x; a1 += v.y;
+      } else {
+        const int32_t r0 = max(beg, b << 5), r1 = min(end, (b << 5) + 32);
+        for (int32_t r = r0; r < r1; ++r) {
+          const uint32_t u = *(reinterpret_cast<const uint32_t*>(x + (size_t)r * kHidden) + t);
+          a0 = Pack16<T>::add_lo(u, a0); a1 = Pack16<T>::add_hi(u, a1);
+        }
+      }
+    }
+  }
+  reinterpret_cast<float2*>(partial + ((size_t)g * kPoolSlices + slice) * kHidden)[t] = make_float2(a0, a1);
+}
+
 template <typename T> BG_DEVINL float load_as_float(const T* p) {
   if constexpr (sizeof(T) == 4) return *p; else return (float)*p;
 }

@@ -97,14 +97,15 @@ class _KernelTimers:
 TIMERS = _KernelTimers()
 
 
-def LAUNCHES_PER_FORWARD(num_layers: int, folded: bool = True) -> int:
+def LAUNCHES_PER_FORWARD(num_layers: int, folded: bool = True, fused_pool: bool = False) -> int:
     """Kernels of ours launched by one GraphSAGE forward: CSR build 7 (hist, 3 scan, fill,
     2 sorts) + batch_info + publish_words + graph_ptr + encoder front 1 (+ encoder GEMM when layer 0 is not folded;
-    + row indicator when it is) + per layer (aggregate rows + hubs + GEMM) + pool 2.
+    + row indicator when it is) + per layer (aggregate rows + hubs + GEMM) + pool 2 (+ the block-flag kernel of a pool-fused last layer).
     (memsets and the 16-byte info read-back are not counted.)"""
+    extra = 1 if fused_pool else 0      # bg_pool_block_flags
     if folded:                          # (the row-indicator kernel is skipped when no node is isolated)
-        return 7 + 3 + 1 + 3 * num_layers + 2
-    return 7 + 3 + 2 + 3 * num_layers + 2
+        return 7 + 3 + 1 + 3 * num_layers + 2 + extra
+    return 7 + 3 + 2 + 3 * num_layers + 2 + extra
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -405,22 +406,48 @@ def encoder_forward(x: torch.Tensor, enc_w: Dict[str, torch.Tensor], w3: LinearP
         gemm512(_segments(h, w3), n, precision, out, cta_group=cta_group, bias=enc_w["b3_host"].data_ptr())
 
 
+@dataclass
+class PoolBlocks:
+    """What a pool-fused last layer hands to `pool_head`: fp32 column sums of every 32-row block of the layer's
+    output, and the flags of the blocks whose rows were stored as well (first / last row of a graph)."""
+    sums: torch.Tensor       # [ceil(N/32), 512] f32
+    keep: torch.Tensor       # [ceil(N/32)] uint8
+
+
+def new_pool_blocks(idx: GraphIndex, device) -> PoolBlocks:
+    nb = (idx.n_nodes + 31) // 32
+    keep = torch.empty(max(nb, 1), dtype=torch.uint8, device=device)
+    capi.pool_block_flags(idx.graph_ptr.data_ptr(), idx.n_graphs, idx.n_nodes, keep.data_ptr(), _stream())
+    return PoolBlocks(torch.empty((max(nb, 1), 512), dtype=torch.float32, device=device), keep)
+
+
+def can_fuse_pool(precision: str, normalize: bool, residual: bool) -> bool:
+    """The pool-fused epilogue exists for the 16-bit normalize epilogue without addends (the last SAGE layer)."""
+    return PRECISION_FORMATS[precision][0] != capi.BG_F32 and normalize and not residual
+
+
 def sage_layer(x: Activation, agg: Activation, out: Activation, idx: GraphIndex, layer: SageLayerPack, *,
-               aggr: str, normalize: bool, relu: bool, residual: bool, cta_group: int) -> None:
-    """One reference layer iteration (Models/BuckGNN.py:447-457) = aggregate + fused update GEMM."""
+               aggr: str, normalize: bool, relu: bool, residual: bool, cta_group: int,
+               pool_blocks: Optional[PoolBlocks] = None) -> None:
+    """One reference layer iteration (Models/BuckGNN.py:447-457) = aggregate + fused update GEMM.
+    `pool_blocks` (last layer of a graph-level model): the epilogue sums the output rows per 32-row block for
+    `pool_head` instead of storing them (only the blocks at graph boundaries are stored)."""
     aggregate(x, agg, idx, aggr)
     segs = _segments(agg, layer.lin_l) + _segments(x, layer.lin_r)
-    with TIMERS.span("sage_update"):
+    pool = {} if pool_blocks is None else dict(pool_block_sums=pool_blocks.sums.data_ptr(),
+                                               pool_block_keep=pool_blocks.keep.data_ptr())
+    with TIMERS.span("sage_update" if pool_blocks is None else "sage_update_pool"):
         gemm512(segs, idx.n_nodes, x.precision, out, cta_group=cta_group,
                 bias=layer.bias.data_ptr(), bn_scale=_p(layer.bn_scale), bn_shift=_p(layer.bn_shift),
                 residual=x.data.data_ptr() if residual else None, ldr=x.data.shape[1],
-                normalize=normalize, relu=relu)
+                normalize=normalize, relu=relu, **pool)
 
 
 def pool_head(x: Activation, idx: GraphIndex, dec: Dict[str, torch.Tensor], out_dim: int,
               want_pooled: bool = False, pooling: str = "mean", pre: Optional[Dict[str, torch.Tensor]] = None,
-              nonfinite: Optional[torch.Tensor] = None):
-    """get_pooling_layer + decoder (Models/BuckGNN.py:246-307, 515-516)."""
+              nonfinite: Optional[torch.Tensor] = None, blocks: Optional[PoolBlocks] = None):
+    """get_pooling_layer + decoder (Models/BuckGNN.py:246-307, 515-516).  With `blocks` (pool-fused last layer)
+    x holds valid rows only in the flagged blocks and the rest comes from the block sums."""
     dev = x.data.device
     g = idx.n_graphs
     mode = capi.POOL_MODES[pooling]
@@ -430,11 +457,19 @@ def pool_head(x: Activation, idx: GraphIndex, dec: Dict[str, torch.Tensor], out_
     ws_bytes = capi.pool_workspace_bytes(g)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with TIMERS.span("pool_head"):
-        capi.pool_head(x.data.data_ptr(), x.code, idx.n_nodes, idx.graph_ptr.data_ptr(), g, mode,
-                       _p(pre["w"]) if pre else None, _p(pre["b"]) if pre else None,
-                       dec["w1"].data_ptr(), dec["b1"].data_ptr(), dec["w2"].data_ptr(), dec["b2"].data_ptr(),
-                       dec["w3"].data_ptr(), dec["b3"].data_ptr(), out_dim, pred.data_ptr(), _p(pooled),
-                       ws.data_ptr(), ws_bytes, _stream(), nonfinite=_p(nonfinite))
+        if blocks is not None:
+            capi.pool_head_blocks(x.data.data_ptr(), x.code, idx.n_nodes, idx.graph_ptr.data_ptr(), g, mode,
+                                  _p(pre["w"]) if pre else None, _p(pre["b"]) if pre else None,
+                                  dec["w1"].data_ptr(), dec["b1"].data_ptr(), dec["w2"].data_ptr(), dec["b2"].data_ptr(),
+                                  dec["w3"].data_ptr(), dec["b3"].data_ptr(), out_dim, pred.data_ptr(), _p(pooled),
+                                  blocks.sums.data_ptr(), blocks.keep.data_ptr(), ws.data_ptr(), ws_bytes, _stream(),
+                                  nonfinite=_p(nonfinite))
+        else:
+            capi.pool_head(x.data.data_ptr(), x.code, idx.n_nodes, idx.graph_ptr.data_ptr(), g, mode,
+                           _p(pre["w"]) if pre else None, _p(pre["b"]) if pre else None,
+                           dec["w1"].data_ptr(), dec["b1"].data_ptr(), dec["w2"].data_ptr(), dec["b2"].data_ptr(),
+                           dec["w3"].data_ptr(), dec["b3"].data_ptr(), out_dim, pred.data_ptr(), _p(pooled),
+                           ws.data_ptr(), ws_bytes, _stream(), nonfinite=_p(nonfinite))
     return pred, pooled
 
 

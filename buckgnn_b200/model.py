@@ -107,13 +107,15 @@ class BuckGNN(nn.Module):
                  num_layers=6, pooling_layer="mean", prediction_type="buckling",
                  use_z_coord=False, use_rotations=False, dropout_rate=0.1,
                  model_name="GraphSAGE_MLP", *, precision: str = "auto", cta_group: int = 2,
-                 cache_index: bool = False, fold_encoder: bool = True, train_precision: str = "tf32"):
+                 cache_index: bool = False, fold_encoder: bool = True, train_precision: str = "tf32",
+                 fuse_pool: bool = True):
         super().__init__()
         self._ctor_kwargs = dict(num_node_features=num_node_features, num_edge_features=num_edge_features,
                                  hidden_channels=hidden_channels, num_layers=num_layers, pooling_layer=pooling_layer,
                                  prediction_type=prediction_type, use_z_coord=use_z_coord, use_rotations=use_rotations,
                                  dropout_rate=dropout_rate, model_name=model_name, precision=precision, cta_group=cta_group,
-                                 cache_index=cache_index, fold_encoder=fold_encoder, train_precision=train_precision)
+                                 cache_index=cache_index, fold_encoder=fold_encoder, train_precision=train_precision,
+                                 fuse_pool=fuse_pool)
         if precision == "auto":
             aggr = _SAGE_LISTS[model_name][1] if model_name in _SAGE_LISTS else (
                 "add" if model_name == "GraphSage_addAggr_Shared" else "mean")
@@ -142,6 +144,7 @@ class BuckGNN(nn.Module):
         self.cta_group = cta_group
         self.cache_index = cache_index
         self.fold_encoder = fold_encoder      # fold node_encoder[4] into SAGE layer 0 (mean / sum / add aggregation)
+        self.fuse_pool = fuse_pool            # last SAGE layer's epilogue sums its rows for the pooling layer (16-bit modes)
         self.output_dim = output_dim = _output_dim(prediction_type, use_z_coord, use_rotations)
         h = hidden_channels
         cat_dec = pooling_layer == "supernode_with_pooling" and prediction_type == "buckling"
@@ -447,6 +450,7 @@ class BuckGNN(nn.Module):
         else:
             engine.encoder_forward(x, packs["enc"], packs["enc_w3"], prec, cur, cg, nonfinite=flag)      # reference :323
         idx = pending.finish()                                        # host sync hidden behind the encoder
+        blocks = None
         if layers:
             nxt = Activation(n, 512, prec, x.device)
             agg = Activation(n, 512, prec, x.device)
@@ -457,14 +461,20 @@ class BuckGNN(nn.Module):
                     engine.sage_layer0_folded(h, nxt, idx, folded, aggr=aggr, normalize=True, relu=True,
                                               cta_group=cg)
                 else:
+                    residual = 0 < i < L - 1
+                    # the last layer's rows are only read by the pooling layer (:515), which is linear in them:
+                    # its epilogue sums them per 32-row block instead of storing them (16-bit modes)
+                    if (i == L - 1 and not node_level and self.fuse_pool
+                            and engine.can_fuse_pool(prec, True, residual)):
+                        blocks = engine.new_pool_blocks(idx, x.device)
                     engine.sage_layer(cur, agg, nxt, idx, layer, aggr=aggr, normalize=True, relu=True,
-                                      residual=(0 < i < L - 1), cta_group=cg)
+                                      residual=residual, cta_group=cg, pool_blocks=blocks)
                 cur, nxt = nxt, cur
         if node_level:
             return engine.node_head(cur, n, packs["node_head"], self.output_dim, cg)     # reference :518-524
         pre = packs["pool_mlp"] if self.pooling_layer in ("mlp", "mlp_no_super") else None
         pred, _ = engine.pool_head(cur, idx, packs["dec"], self.output_dim, pooling=self.pooling_layer,
-                                   pre=pre, nonfinite=flag)                                # reference :515-516
+                                   pre=pre, nonfinite=flag, blocks=blocks)                 # reference :515-516
         return pred
 
     # ------------------------------------------------------------------ SAGPooling variants

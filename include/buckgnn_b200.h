@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 9
+#define BG_ABI_VERSION 10
 
 typedef enum bg_status {
   BG_OK = 0,
@@ -184,6 +184,13 @@ typedef struct bg_epilogue {
   int64_t gather_ld;
   float* inv_norm_out;         /* DEVICE [M] f32 or NULL: with normalize, 1 / max(||v||_2, 1e-12) per row (the   */
                                /* training forward saves it for the backward of F.normalize)                     */
+  float* pool_block_sums;      /* DEVICE [ceil(M/32), 512] f32 or NULL.  Pool-fused epilogue for the LAST layer  */
+                               /* of a graph-level model, whose output only feeds global_mean_pool               */
+                               /* (Models/BuckGNN.py:515): the column sums of every 32-row block of the output   */
+                               /* rows (the rounded values a store would have written; fp32, fixed order) are    */
+                               /* written here, and only the blocks flagged in pool_block_keep are stored to     */
+                               /* `out`.  Needs normalize, a 16-bit out_dtype, no residual / gathered addends.   */
+  const uint8_t* pool_block_keep; /* DEVICE [ceil(M/32)] from bg_pool_block_flags; required with pool_block_sums */
 } bg_epilogue;
 
 int bg_gemm512(const bg_gemm_segment* segments_host, int32_t n_segments, int64_t m,
@@ -223,6 +230,19 @@ int bg_pool_head(const void* x, int dtype, int64_t n_nodes, const int32_t* graph
                  const float* w3, const float* b3, int32_t out_dim,
                  float* pred, float* pooled_out,
                  void* workspace, size_t workspace_bytes, const int32_t* nonfinite_flag, void* stream);
+
+/* Pooling over the block sums of a pool-fused bg_gemm512 (bg_epilogue.pool_block_sums): same result and arguments
+ * as bg_pool_head, but x holds valid rows only in the blocks flagged by bg_pool_block_flags -- keep[b] = 1 for every
+ * 32-row block [32b, 32b+32) that contains the first or the last row of a graph (so every other block lies inside one
+ * graph, and the super node's row -- the graph's last -- is always stored).  16-bit x only.  The row sums are added in
+ * a different (fixed) order than bg_pool_head's, so predictions agree to fp32 rounding, not bit for bit. */
+int bg_pool_block_flags(const int32_t* graph_ptr, int64_t n_graphs, int64_t n_nodes, uint8_t* keep, void* stream);
+int bg_pool_head_blocks(const void* x, int dtype, int64_t n_nodes, const int32_t* graph_ptr, int64_t n_graphs,
+                        int pool_mode, const float* pre_w, const float* pre_b,
+                        const float* w1, const float* b1, const float* w2, const float* b2,
+                        const float* w3, const float* b3, int32_t out_dim,
+                        float* pred, float* pooled_out, const float* block_sums, const uint8_t* keep,
+                        void* workspace, size_t workspace_bytes, const int32_t* nonfinite_flag, void* stream);
 
 /* ------------------------------------------------------------------ EA-GNN helpers
  * bg_expand_rowptr: row_of[i] = r with rowptr[r] <= i < rowptr[r+1], iota[i] = i   (i < E)
