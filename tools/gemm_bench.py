@@ -11,7 +11,7 @@ from buckgnn_b200.engine import Activation
 DEV = "cuda:0"
 
 
-def case(name, m, ks, precision, normalize, residual, iters=20):
+def case(name, m, ks, precision, normalize, residual, iters=20, pool=False):
     dt = engine._TORCH[engine.PRECISION_FORMATS[precision][0]]
     g = torch.Generator().manual_seed(0)
     As = [(torch.randn(m, k, generator=g) / k ** 0.5).to(dt).to(DEV) for k in ks]
@@ -21,10 +21,16 @@ def case(name, m, ks, precision, normalize, residual, iters=20):
     res = torch.randn(m, 512, generator=g).to(dt).to(DEV) if residual else None
     out = Activation(m, 512, precision, DEV)
     segs = [(a.data_ptr(), k, b.data_ptr(), k, k) for a, b, k in zip(As, Bs, ks)]
+    extra = {}
+    if pool:                                   # pool-fused epilogue: block sums instead of rows (1 block in 125 is kept)
+        nb = (m + 31) // 32
+        sums = torch.empty(nb, 512, dtype=torch.float32, device=DEV)
+        keep = (torch.arange(nb) % 125 == 0).to(torch.uint8).to(DEV)
+        extra = dict(pool_block_sums=sums.data_ptr(), pool_block_keep=keep.data_ptr())
     def run():
         engine.gemm512(segs, m, precision, out, bias=bias.data_ptr(), bn_scale=scale.data_ptr() if normalize else None,
                        bn_shift=shift.data_ptr() if normalize else None, residual=engine._p(res), ldr=512,
-                       normalize=normalize, relu=normalize)
+                       normalize=normalize, relu=normalize, **extra)
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -56,6 +62,7 @@ if __name__ == "__main__":
     M = 1030398
     case("sage update, full epilogue + skip", M, [512, 512], "fp16", True, True)
     case("sage update, full epilogue", M, [512, 512], "fp16", True, False)
+    case("sage update, pool-fused epilogue", M, [512, 512], "fp16", True, False, pool=True)
     case("sage update, bias only", M, [512, 512], "fp16", False, False)
     case("encoder 128->512, bias only", M, [128], "fp16", False, False)
     case("sage update bf16 + skip", M, [512, 512], "bf16", True, True)
