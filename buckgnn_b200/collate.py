@@ -32,22 +32,30 @@ class DeviceGraphStore:
         self.edge_attr = torch.cat([g.edge_attr for g in graphs], 0).to(torch.float32).contiguous().to(dev)
         self.y = torch.cat([g.y.reshape(-1)[:1] for g in graphs], 0).to(torch.float32).contiguous().to(dev)
         self.node_ptr, self.edge_ptr = node_ptr.to(dev), edge_ptr.to(dev)
+        self._n_host, self._e_host = n, e            # per-graph sizes on the host: a CPU `indices` needs no read-back
         self.device = dev
 
     def bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.x, self.edge_index, self.edge_attr, self.y))
 
     def batch(self, indices: torch.Tensor) -> PlateBatch:
-        """PyG-layout batch of the graphs `indices` (int64, on the device), in that order."""
+        """PyG-layout batch of the graphs `indices` (int64), in that order.  With `indices` on the HOST the batch's
+        node / edge totals come from the host-side size table and nothing is read back from the device (the loop
+        never waits for the previous forward); with device indices one 16-byte read-back supplies them."""
         dev = self.device
-        sel = indices.to(device=dev, dtype=torch.int64).contiguous()
+        host_idx = indices if not indices.is_cuda else None
+        sel = indices.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
         g = sel.numel()
         s = _stream()
         i64 = dict(dtype=torch.int64, device=dev)
         out_np, out_ep = torch.empty(g + 1, **i64), torch.empty(g + 1, **i64)
         capi.collate_ptr(sel.data_ptr(), g, self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(), out_np.data_ptr(),
                          out_ep.data_ptr(), s)
-        n_out, e_out = (int(v) for v in torch.stack([out_np[g], out_ep[g]]).tolist())     # one small read-back
+        if host_idx is not None:
+            hi = host_idx.to(torch.int64)
+            n_out, e_out = int(self._n_host[hi].sum()), int(self._e_host[hi].sum())
+        else:
+            n_out, e_out = (int(v) for v in torch.stack([out_np[g], out_ep[g]]).tolist())     # one small read-back
         f, fe = self.x.shape[1], self.edge_attr.shape[1]
         x = torch.empty((n_out, f), dtype=torch.float32, device=dev)
         ei = torch.empty((2, e_out), **i64)

@@ -319,10 +319,11 @@ def test_device_collate_is_bit_exact():
     store = DeviceGraphStore(graphs, DEV)
     for sel in ([0, 1, 2, 3, 4, 5, 6, 7, 8], [7, 2, 2, 5], [3]):
         want = collate([graphs[i] for i in sel])
-        got = store.batch(torch.tensor(sel))
-        assert got.num_graphs == len(sel)
-        for f in ("x", "edge_index", "edge_attr", "batch", "y", "ptr"):
-            assert torch.equal(getattr(got, f).cpu(), getattr(want, f)), f
+        for idx in (torch.tensor(sel), torch.tensor(sel, device=DEV)):     # host indices (no read-back) / device indices
+            got = store.batch(idx)
+            assert got.num_graphs == len(sel)
+            for f in ("x", "edge_index", "edge_attr", "batch", "y", "ptr"):
+                assert torch.equal(getattr(got, f).cpu(), getattr(want, f)), f
     # 1500 graphs: more than one scan block of bg_collate_ptr
     sel = torch.arange(1500) % 9
     got = store.batch(sel)

@@ -62,7 +62,7 @@ def main():
     loads = [sum(costs[j] for j in p) for p in parts]
     mine = parts[rank]
     batches = batches_by_node_budget(mine, [nodes[m] for m in member], args.node_budget)
-    sels = [torch.tensor([member[j] for j in b], dtype=torch.int64, device=dev) for b in batches]
+    sels = [torch.tensor([member[j] for j in b], dtype=torch.int64).pin_memory() for b in batches]      # host indices: no read-back
 
     cfg = dict(num_node_features=16, num_edge_features=5, hidden_channels=512, num_layers=6,
                pooling_layer="mean", model_name="GraphSage_meanAggr")
