@@ -6,6 +6,7 @@ run() { name=$1; shift; echo "=== $name"; timeout 900 "$@" > gpurun_out/$name.lo
 run t_all python -m pytest tests -q -x -m gpu
 run smoke python __graft_entry__.py --smoke
 TAILN=2 run bench python bench.py --steps 10 --warmup 3
+TAILN=2 run bench25 python bench.py --steps 25 --warmup 5 --no-cpu-baseline
 TAILN=2 run bench_ref python bench.py --impl reference --steps 3 --warmup 1
 TAILN=2 run bench_tf32 python bench.py --steps 5 --warmup 3 --precision tf32 --no-cpu-baseline
 TAILN=2 run bench_fp32 python bench.py --steps 5 --warmup 3 --precision fp32 --no-cpu-baseline
@@ -13,6 +14,9 @@ TAILN=2 run bench_train python tools/bench_train.py --steps 10 --warmup 3
 TAILN=2 run bench_train_bf16 python tools/bench_train.py --steps 10 --warmup 3 --precision bf16
 TAILN=4 run bench_configs python tools/bench_configs.py
 TAILN=6 run bench_sag python tools/bench_configs.py sag
+TAILN=2 run sweep1 python tools/bench_sweep.py --graphs 10000
+TAILN=12 run gemm_bench python tools/gemm_bench.py
+TAILN=5 run agg_bench python tools/agg_bench.py
 if [ "$1" != "noprof" ]; then
   bash tools/profile.sh
   # launch list of training steps (cfg 4): two steps after three warm-up steps, skipping the warm-up launches
