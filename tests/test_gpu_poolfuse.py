@@ -126,3 +126,20 @@ def test_fused_pool_is_the_default_and_is_skipped_where_it_cannot_apply():
     names = set(TIMERS.summary())
     TIMERS.disable()
     assert "sage_update_pool" not in names
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_fused_pool_random_ragged_batches(seed):
+    """random graph sizes from 2 to ~700 nodes (many boundaries per 32-row block, blocks shared by three graphs,
+    boundaries on multiples of 32): fused == unfused for the mean and the super-node variants"""
+    g = torch.Generator().manual_seed(seed)
+    dims = [(int(a), int(b)) for a, b in torch.randint(1, 27, (40, 2), generator=g).tolist()]
+    dims += [(31, 1), (1, 1), (15, 2), (3, 5)]                          # 33-, 3-, 33- and 17-node graphs (+ super node)
+    b = collate([make_plate_graph(i, nx=nx + 1, ny=ny + 1) for i, (nx, ny) in enumerate(dims)]).to(DEV)
+    for pooling in ("mean", "supernode_with_pooling", "mean_no_super"):
+        _, fused, unfused = _pair(pooling, layers=2)
+        with torch.no_grad():
+            a, _ = fused(b.x, b.edge_index, b.edge_attr, b.batch)
+            u, _ = unfused(b.x, b.edge_index, b.edge_attr, b.batch)
+        assert a.shape == u.shape == (len(dims),)
+        assert _rel(a.cpu(), u.cpu()) < 2e-6, pooling
