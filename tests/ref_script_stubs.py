@@ -166,7 +166,7 @@ def cpu_forward_through_oracle(model_cls):
         assert edge_attr.dim() == 2 and edge_attr.shape[0] == edge_index.shape[1]
         assert batch is None or (batch.dtype == torch.int64 and batch.shape[0] == x.shape[0])
         kw = {k: v for k, v in self._ctor_kwargs.items()
-              if k not in ("precision", "cta_group", "cache_index", "fold_encoder", "train_precision")}
+              if k not in ("precision", "cta_group", "cache_index", "fold_encoder", "train_precision", "fuse_pool")}
         twin = O.OracleBuckGNN(**kw).train(self.training)
         state = dict(self.named_parameters())
         state.update(dict(self.named_buffers()))
