@@ -958,7 +958,7 @@ int bg_bn_batch_stats(const void* u, int dtype, int64_t N, const float* gamma, c
                                                                           nullptr, nullptr, nodrop, partial)))
   BG_LAUNCH_OK();
   BnVectors out{a_out, shift_out, mean_out, invstd_out};
-  k_bn_fwd_finalize<<<1, kHidden, 0, stream>>>(partial, grid, N, gamma, beta, eps, momentum, running_mean, running_var,
+  k_bn_fwd_finalize<<<kFinalizeCtas, kHidden, 0, stream>>>(partial, grid, N, gamma, beta, eps, momentum, running_mean, running_var,
                                                reinterpret_cast<long long*>(num_batches_tracked), out);
   BG_LAUNCH_OK();
   return BG_OK;
@@ -1005,7 +1005,7 @@ int bg_sage_backward_rows(const void* u, const void* dy, const void* dy2, const 
                                                                             static_cast<const T*>(dy2), N, a, shift, d, partial)))
     BG_LAUNCH_OK();
     BnVectors v{const_cast<float*>(a), const_cast<float*>(shift), const_cast<float*>(mean), const_cast<float*>(invstd)};
-    k_bn_bwd_finalize<<<1, kHidden, 0, stream>>>(partial, grid, N, v, dgamma, dbeta, accumulate, k0, k1);
+    k_bn_bwd_finalize<<<kFinalizeCtas, kHidden, 0, stream>>>(partial, grid, N, v, dgamma, dbeta, accumulate, k0, k1);
     BG_LAUNCH_OK();
   } else {
     BG_CUDA_OK(cudaMemsetAsync(k0, 0, 2 * kHidden * sizeof(float), stream));

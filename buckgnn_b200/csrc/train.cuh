@@ -132,37 +132,52 @@ struct BnVectors {          // [512] f32 each, device
   float* invstd;
 };
 
-// column c of the [n_parts][2][512] partials, summed in fp64 in a fixed order: eight interleaved chains (the loads of
-// one chain of ~300 would each wait for the previous add: 40 us per finalize kernel), combined at the end
-BG_DEVINL void sum_partials(const float* __restrict__ partial, int n_parts, int c, double& s1, double& s2) {
-  double a1[8], a2[8];
+// Finalize kernels: kFinalizeCtas CTAs x 512 threads.  CTA b owns columns [64 b, 64 b + 64); thread (g, cl) sums the
+// partial slots p = g, g + 8, ... of column 64 b + cl in fp64 (four interleaved chains), the eight groups are added in
+// a fixed order through shared memory, and the threads of group 0 finish their column.  (Round 1 ran ONE CTA of 512
+// threads, each walking all ~300 slots of its column: 34 us per launch, 12 launches per training step -- the
+// dependent L2 round trips, not the arithmetic, were the cost.)
+constexpr int kFinalizeCtas = kHidden / 64;
+BG_DEVINL bool sum_partials(const float* __restrict__ partial, int n_parts, int& c, double& s1, double& s2) {
+  __shared__ double sh1[8][64], sh2[8][64];
+  const int cl = threadIdx.x & 63, g = threadIdx.x >> 6;
+  c = blockIdx.x * 64 + cl;
+  double a1[4], a2[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) a1[k] = a2[k] = 0.0;
-  int p = 0;
-  for (; p + 8 <= n_parts; p += 8) {
+  for (int k = 0; k < 4; ++k) a1[k] = a2[k] = 0.0;
+  int p = g;
+  for (; p + 24 < n_parts; p += 32) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      a1[k] += (double)partial[(size_t)(p + k) * 2 * kHidden + c];
-      a2[k] += (double)partial[(size_t)(p + k) * 2 * kHidden + kHidden + c];
+    for (int k = 0; k < 4; ++k) {
+      a1[k] += (double)partial[(size_t)(p + 8 * k) * 2 * kHidden + c];
+      a2[k] += (double)partial[(size_t)(p + 8 * k) * 2 * kHidden + kHidden + c];
     }
   }
-  for (int k = 0; p < n_parts; ++p, ++k) {
-    a1[k] += (double)partial[(size_t)p * 2 * kHidden + c];
-    a2[k] += (double)partial[(size_t)p * 2 * kHidden + kHidden + c];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (p + 8 * k < n_parts) {
+      a1[k] += (double)partial[(size_t)(p + 8 * k) * 2 * kHidden + c];
+      a2[k] += (double)partial[(size_t)(p + 8 * k) * 2 * kHidden + kHidden + c];
+    }
   }
-  s1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
-  s2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + ((a2[4] + a2[5]) + (a2[6] + a2[7]));
+  sh1[g][cl] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+  sh2[g][cl] = (a2[0] + a2[1]) + (a2[2] + a2[3]);
+  __syncthreads();
+  if (g != 0) return false;
+  s1 = ((sh1[0][cl] + sh1[1][cl]) + (sh1[2][cl] + sh1[3][cl])) + ((sh1[4][cl] + sh1[5][cl]) + (sh1[6][cl] + sh1[7][cl]));
+  s2 = ((sh2[0][cl] + sh2[1][cl]) + (sh2[2][cl] + sh2[3][cl])) + ((sh2[4][cl] + sh2[5][cl]) + (sh2[6][cl] + sh2[7][cl]));
+  return true;
 }
 
-// 1 CTA x 512 threads.  Batch mean / biased variance -> a, shift, mean, invstd; running statistics updated
-// as torch.nn.BatchNorm1d does in train mode (momentum, unbiased variance) -- Models/BuckGNN.py:163,451.
+// Batch mean / biased variance -> a, shift, mean, invstd; running statistics updated as torch.nn.BatchNorm1d does in
+// train mode (momentum, unbiased variance) -- Models/BuckGNN.py:163,451.
 __global__ void __launch_bounds__(kHidden)
 k_bn_fwd_finalize(const float* __restrict__ partial, int n_parts, int64_t N, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
                   float* __restrict__ running_var, long long* __restrict__ num_batches_tracked, BnVectors out) {
-  const int c = threadIdx.x;
+  int c;
   double s1, s2;
-  sum_partials(partial, n_parts, c, s1, s2);
+  if (!sum_partials(partial, n_parts, c, s1, s2)) return;
   const double mean = s1 / (double)N;
   double var = s2 / (double)N - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -186,9 +201,9 @@ __global__ void __launch_bounds__(kHidden)
 k_bn_bwd_finalize(const float* __restrict__ partial, int n_parts, int64_t N, const BnVectors bn,
                   float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                   float* __restrict__ k0, float* __restrict__ k1) {
-  const int c = threadIdx.x;
+  int c;
   double s1, s2;
-  sum_partials(partial, n_parts, c, s1, s2);
+  if (!sum_partials(partial, n_parts, c, s1, s2)) return;
   const double mean = bn.mean[c], invstd = bn.invstd[c], av = bn.a[c];
   const double dg = invstd * (s2 - mean * s1);
   if (accumulate) { dgamma[c] += (float)dg; dbeta[c] += (float)s1; }
