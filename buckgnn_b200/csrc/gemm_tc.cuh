@@ -817,6 +817,9 @@ typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, 
 PFN_tensorMapEncodeTiled get_tensor_map_encoder();
 int gemm_sm_count();
 
+#ifndef BG_TMA_L2_PROMOTION
+#define BG_TMA_L2_PROMOTION 3      // CU_TENSOR_MAP_L2_PROMOTION_L2_256B (0 none, 1 64 B, 2 128 B): an operand box is 128 B of
+#endif                             // each of 128 rows; the next K block reads the adjacent 128 B of the same rows
 // [rows, k] row-major matrix, box = 128 rows x 128 bytes of K, 128B swizzle, zero fill out of bounds
 // (the same geometry serves the operand tiles and the epilogue's out / residual staging tiles)
 // fmt: UMMA operand format (0 f16, 1 bf16, 2 tf32/f32)
@@ -834,7 +837,7 @@ static inline int make_operand_map(CUtensorMap* map, const void* base, int64_t r
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(map, dt, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)BG_TMA_L2_PROMOTION,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? BG_OK : BG_ERR_CUDA;
 }
