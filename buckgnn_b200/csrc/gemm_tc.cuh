@@ -591,16 +591,19 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
           if (t * 4 + r4 < rows_here) stg_v4(out_base + (size_t)t * 4 * out_row_bytes + ch * 128, o);
         }
       }
-      if constexpr (kPool) {                                    // rows 4t + r4: add the four r4 groups, lanes 0..7 write
+      if constexpr (kPool) {                                    // rows 4t + r4: add the four lane groups (butterfly)
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
           cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
         }
-        if (r4 == 0 && rows_here > 0) {
+        // every lane now holds the block's sums of its 8 columns; lane groups 0 and 1 store the two halves in ONE
+        // instruction, so every 32-byte sector is written whole.  (In the forward this launch is ~0.09 ms slower than
+        // the unfused last layer -- 64 mixed adds + 16 shuffles + 16 adds per chunk and warp -- against 0.15 ms saved
+        // in the pooling pass: profiles/r02_pool_fused_probe.txt)
+        if (r4 < 2 && rows_here > 0) {
           float4* dst = reinterpret_cast<float4*>(p.pool_sums + (size_t)(warp_row0 >> 5) * kHidden + cb + ch * kChunkCols + piece * kPer);
-          dst[0] = make_float4(cs[0], cs[1], cs[2], cs[3]);
-          dst[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
+          dst[r4] = r4 == 0 ? make_float4(cs[0], cs[1], cs[2], cs[3]) : make_float4(cs[4], cs[5], cs[6], cs[7]);
         }
       }
       __syncwarp();
