@@ -15,6 +15,7 @@ The CSR (bg_csr_build) and graph offsets (bg_graph_ptr_build) are rebuilt from t
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -53,10 +54,14 @@ def _stream() -> int:
 
 class _KernelTimers:
     """Optional CUDA-event brackets around each kernel class, recorded on the launching
-    stream (bench.py turns them on for its timed region; off by default = zero cost)."""
+    stream (bench.py turns them on for its timed region; off by default = zero cost).
+    With BUCKGNN_NVTX=1 in the environment (or `TIMERS.nvtx = True`) every span also opens an NVTX range
+    of the same name, so an `ncu --nvtx --nvtx-include "sage_update/"` capture or a timeline groups the
+    launches by what they do (tools/profile.sh)."""
 
     def __init__(self):
         self.enabled = False
+        self.nvtx = os.environ.get("BUCKGNN_NVTX", "0") not in ("", "0")
         self.spans = []
 
     def enable(self):
@@ -70,6 +75,9 @@ class _KernelTimers:
             self.owner, self.name = owner, name
 
         def __enter__(self):
+            self.pushed = self.owner.nvtx
+            if self.pushed:
+                torch.cuda.nvtx.range_push(self.name)
             if self.owner.enabled:
                 self.e0 = torch.cuda.Event(enable_timing=True)
                 self.e1 = torch.cuda.Event(enable_timing=True)
@@ -80,6 +88,8 @@ class _KernelTimers:
             if self.owner.enabled:
                 self.e1.record()
                 self.owner.spans.append((self.name, self.e0, self.e1))
+            if self.pushed:
+                torch.cuda.nvtx.range_pop()
 
     def span(self, name):
         return self._Span(self, name)

@@ -59,7 +59,10 @@ class WireBatch:
         full_ptr = torch.zeros(g + 1, dtype=torch.int64)
         full_ptr[1:] = torch.cumsum(counts, 0)
         keep = torch.ones(E, dtype=torch.bool)
-        for k in range(g):
+        # the per-graph edge offsets above mean something only if the edge list IS grouped by graph; a batch built any
+        # other way ships every edge (wire_ptr == full_ptr: bg_expand_wire is then a plain widening copy)
+        grouped = E == 0 or bool((eg[1:] >= eg[:-1]).all())
+        for k in range(g if grouped else 0):
             n0, n1 = int(node_ptr[k]), int(node_ptr[k + 1])
             f0, f1 = int(full_ptr[k]), int(full_ptr[k + 1])
             m = n1 - n0 - 1                                    # hub pairs if the last node is a super node

@@ -333,7 +333,7 @@ def test_device_collate_is_bit_exact():
 
 
 # ----------------------------------------------------------------------------- wire format (pipeline.WireBatch)
-@pytest.mark.parametrize("case", ["super_node", "stiffened_virtual", "no_super", "shuffled", "single_graph"])
+@pytest.mark.parametrize("case", ["super_node", "stiffened_virtual", "no_super", "shuffled", "single_graph", "interleaved"])
 def test_wire_format_expands_to_the_exact_pyg_batch(case):
     """bg_expand_wire: explicit int32 edges + implicit hub pairs + node offsets -> the int64 edge_index and batch vector
     `batch.to(device)` would have delivered, bit for bit; graphs whose trailing edges are not the reference's hub pairs
@@ -348,6 +348,10 @@ def test_wire_format_expands_to_the_exact_pyg_batch(case):
         b = make_batch(3, nx=8, ny=6, stiffened=True, super_node=False, virtual_edges=True)
     elif case == "single_graph":
         b = make_batch(1, nx=10, ny=4)
+    elif case == "interleaved":                              # edge list NOT grouped by graph: everything ships, as is
+        b = make_batch(3, nx=8, ny=6)
+        order = torch.randperm(b.num_edges, generator=torch.Generator().manual_seed(1))
+        b = PlateBatch(b.x, b.edge_index[:, order].contiguous(), b.edge_attr[order], b.batch, b.y, b.ptr, b.num_graphs)
     else:                                                    # edges of every graph in random order: nothing is implicit
         b = make_batch(3, nx=8, ny=6)
         g = torch.Generator().manual_seed(0)

@@ -59,3 +59,45 @@ def test_stiffened_density():
     # ~4n mesh edges (sides + diagonals) + 13.33% virtual + n hub, directed x2  => ~11n
     assert 10.5 * n < g.num_edges < 11.5 * n
     assert (g.edge_attr[:, 0] == 1.0).sum() >= 20        # active stiffener edges (directed)
+
+
+def _expand_wire_host(w):
+    """What bg_expand_wire does on the device (capi.cu k_expand_wire), as a host loop: the spec of the wire format."""
+    ei = torch.empty((2, w.num_edges), dtype=torch.int64)
+    batch = torch.empty(w.num_nodes, dtype=torch.int64)
+    for g in range(w.num_graphs):
+        n0, n1 = int(w.node_ptr[g]), int(w.node_ptr[g + 1])
+        w0, w1 = int(w.wire_ptr[g]), int(w.wire_ptr[g + 1])
+        f0, f1 = int(w.full_ptr[g]), int(w.full_ptr[g + 1])
+        ei[:, f0:f0 + (w1 - w0)] = w.edges[:, w0:w1].to(torch.int64)
+        pairs = ((f1 - f0) - (w1 - w0)) // 2
+        s, base = n1 - 1, f0 + (w1 - w0)
+        others = torch.arange(n0, n0 + pairs)
+        ei[0, base:base + 2 * pairs:2], ei[1, base:base + 2 * pairs:2] = s, others
+        ei[0, base + 1:base + 2 * pairs:2], ei[1, base + 1:base + 2 * pairs:2] = others, s
+        batch[n0:n1] = g
+    return ei, batch
+
+
+def test_wire_format_host_conversion_round_trips():
+    """pipeline.WireBatch.from_batch (loader side): hub pairs leave the wire only where they are exactly the
+    reference's block; an edge list that is not grouped by graph ships every edge unchanged."""
+    from buckgnn_b200.pipeline import WireBatch
+    from buckgnn_b200.synth import PlateBatch
+    b = make_batch(4, nx=7, ny=5)
+    w = WireBatch.from_batch(b)
+    assert w.edges.shape[1] == b.num_edges - 2 * (b.num_nodes - b.num_graphs)
+    ei, batch = _expand_wire_host(w)
+    assert torch.equal(ei, b.edge_index) and torch.equal(batch, b.batch)
+    order = torch.randperm(b.num_edges, generator=torch.Generator().manual_seed(3))
+    mixed = PlateBatch(b.x, b.edge_index[:, order].contiguous(), b.edge_attr[order], b.batch, b.y, b.ptr, b.num_graphs)
+    w = WireBatch.from_batch(mixed)
+    assert w.edges.shape[1] == b.num_edges and torch.equal(w.wire_ptr, w.full_ptr)
+    ei, batch = _expand_wire_host(w)
+    assert torch.equal(ei, mixed.edge_index) and torch.equal(batch, b.batch)
+    # no super node at all
+    plain = make_batch(2, nx=6, ny=4, super_node=False)
+    w = WireBatch.from_batch(plain)
+    assert w.edges.shape[1] == plain.num_edges
+    ei, _ = _expand_wire_host(w)
+    assert torch.equal(ei, plain.edge_index)
