@@ -192,6 +192,76 @@ BG_DEVINL void gather_indexed(const T* __restrict__ x, int32_t my, int32_t cnt, 
   }
 }
 
+// Max aggregation over 16-bit rows stays PACKED: the maximum of 16-bit values is one of them, so HMNMX2 on the raw pairs
+// gives bit for bit what converting every value to fp32, FMNMX and rounding back gave -- at 8 instead of 32 instructions
+// per neighbour row and lane, with 8 instead of 16 accumulator registers and no conversion at the store.
+template <typename T> struct PackedMax {
+  uint4 m[2];
+  BG_DEVINL void init() {
+    m[0] = m[1] = make_uint4(Pack16<T>::kNegInf2, Pack16<T>::kNegInf2, Pack16<T>::kNegInf2, Pack16<T>::kNegInf2);
+  }
+  BG_DEVINL void take(const RowFrag<T>& f) {
+    using P = Pack16<T>;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      m[j].x = P::hmax2(m[j].x, f.q[j].x); m[j].y = P::hmax2(m[j].y, f.q[j].y);
+      m[j].z = P::hmax2(m[j].z, f.q[j].z); m[j].w = P::hmax2(m[j].w, f.q[j].w);
+    }
+  }
+  BG_DEVINL void store(T* row, int lane, int32_t deg) const {      // a row without neighbours aggregates to 0, not -inf
+    uint4* p = reinterpret_cast<uint4*>(row);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    stg_v4(p + lane, deg == 0 ? z : m[0]);
+    stg_v4(p + 32 + lane, deg == 0 ? z : m[1]);
+  }
+};
+
+// neighbours col[beg..end) (any count), 4 rows in flight
+template <typename T>
+BG_DEVINL void gather_range_max16(const T* __restrict__ x, const int32_t* __restrict__ col, int32_t beg, int32_t end,
+                                  int lane, PackedMax<T>& acc) {
+  for (int32_t base = beg; base < end; base += 32) {
+    const int32_t cnt = min(32, end - base);
+    const int32_t my = (lane < cnt) ? col[base + lane] : 0;
+    int32_t j = 0;
+    for (; j + 4 <= cnt; j += 4) {
+      RowFrag<T> f0, f1, f2, f3;
+      f0.load(x + (size_t)__shfl_sync(0xffffffffu, my, j) * kHidden, lane);
+      f1.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 1) * kHidden, lane);
+      f2.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 2) * kHidden, lane);
+      f3.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 3) * kHidden, lane);
+      acc.take(f0); acc.take(f1); acc.take(f2); acc.take(f3);
+    }
+    for (; j < cnt; ++j) {
+      RowFrag<T> f;
+      f.load(x + (size_t)__shfl_sync(0xffffffffu, my, j) * kHidden, lane);
+      acc.take(f);
+    }
+  }
+}
+
+// the first <= 32 neighbours, whose indices sit in `my` (same grouping as gather_indexed)
+template <typename T>
+BG_DEVINL void gather_indexed_max16(const T* __restrict__ x, int32_t my, int32_t cnt, int lane, PackedMax<T>& acc) {
+  int32_t j = 0;
+  for (; j + 4 <= cnt; j += 4) {
+    RowFrag<T> f0, f1, f2, f3;
+    f0.load(x + (size_t)__shfl_sync(0xffffffffu, my, j) * kHidden, lane);
+    f1.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 1) * kHidden, lane);
+    f2.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 2) * kHidden, lane);
+    f3.load(x + (size_t)__shfl_sync(0xffffffffu, my, j + 3) * kHidden, lane);
+    acc.take(f0); acc.take(f1); acc.take(f2); acc.take(f3);
+  }
+  const int32_t rem = cnt - j;
+  if (rem > 0) {                                   // the last 1-3 rows issued together (slots past the end re-read row j)
+    RowFrag<T> f0, f1, f2;
+    f0.load(x + (size_t)__shfl_sync(0xffffffffu, my, j) * kHidden, lane);
+    f1.load(x + (size_t)__shfl_sync(0xffffffffu, my, rem > 1 ? j + 1 : j) * kHidden, lane);
+    f2.load(x + (size_t)__shfl_sync(0xffffffffu, my, rem > 2 ? j + 2 : j) * kHidden, lane);
+    acc.take(f0); acc.take(f1); acc.take(f2);      // max is idempotent: a repeated row changes nothing
+  }
+}
+
 // One persistent CTA per SM owns a CONTIGUOUS band of rows and walks it in order, one warp per row.
 // Mesh neighbours of row i are i+-1 and i+-nx, so the band's reuse window (~2*nx+32 rows of 1 KB)
 // stays in the SM's L1: a source row is fetched from L2 once and hit ~3 more times.
@@ -404,13 +474,21 @@ k_aggregate_rows(const T* __restrict__ x, T* __restrict__ out, int64_t N, int64_
     if (r + 3 * kWarps < r_end) { n3beg = rowptr[r + 3 * kWarps]; n3end = rowptr[r + 3 * kWarps + 1]; }
     const int32_t deg = end - beg;
     if (deg <= kBigRowThreshold) {                          // hub rows: k_aggregate_hubs / k_hub_finalize
-      float acc[16];
+      if constexpr (kAggr == BG_AGGR_MAX && sizeof(T) == 2) {
+        PackedMax<T> pm;
+        pm.init();
+        gather_indexed_max16<T>(x, my, min(deg, 32), lane, pm);
+        if (deg > 32) gather_range_max16<T>(x, col, beg + 32, end, lane, pm);
+        pm.store(out + (size_t)r * kHidden, lane, deg);
+      } else {
+        float acc[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = agg_init<kAggr>();
-      gather_indexed<T, kAggr>(x, my, min(deg, 32), lane, acc);
-      if (deg > 32) gather_range<T, kAggr>(x, col, beg + 32, end, lane, acc);
-      agg_finalize<kAggr, sizeof(T) == 4>(acc, deg);
-      RowFrag<T>::store(out + (size_t)r * kHidden, lane, acc);
+        for (int i = 0; i < 16; ++i) acc[i] = agg_init<kAggr>();
+        gather_indexed<T, kAggr>(x, my, min(deg, 32), lane, acc);
+        if (deg > 32) gather_range<T, kAggr>(x, col, beg + 32, end, lane, acc);
+        agg_finalize<kAggr, sizeof(T) == 4>(acc, deg);
+        RowFrag<T>::store(out + (size_t)r * kHidden, lane, acc);
+      }
     }
     beg = nbeg; end = nend; my = nmy; nbeg = n2beg; nend = n2end; nmy = n2my; n2beg = n3beg; n2end = n3end;
   }

@@ -127,6 +127,11 @@ template <> struct Pack16<__nv_bfloat16> {
     __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), __floats2bfloat162_rn(0.f, 0.f));
     return *reinterpret_cast<uint32_t*>(&r);
   }
+  static BG_DEVINL uint32_t hmax2(uint32_t a, uint32_t b) {            // packed max (exact: the result is one of the inputs)
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static constexpr uint32_t kNegInf2 = 0xff80ff80u;
 };
 template <> struct Pack16<__half> {
   static BG_DEVINL float lo(uint32_t u) { return __low2float(*reinterpret_cast<const __half2*>(&u)); }
@@ -151,6 +156,11 @@ template <> struct Pack16<__half> {
     __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), __floats2half2_rn(0.f, 0.f));
     return *reinterpret_cast<uint32_t*>(&r);
   }
+  static BG_DEVINL uint32_t hmax2(uint32_t a, uint32_t b) {
+    __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static constexpr uint32_t kNegInf2 = 0xfc00fc00u;
 };
 
 // ------------------------------------------------------------------ watchdog

@@ -168,6 +168,33 @@ def test_aggregate_matches_oracle(aggr, precision, fold):
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16", "tf32"])
 @pytest.mark.parametrize("aggr", ["mean", "sum", "max"])
+def test_aggregate_medium_degrees(aggr, precision):
+    """rows of degree 20..64 (more neighbours than one index fetch holds, still below the hub threshold) and a few hubs
+    with scattered neighbours, on a random multigraph; max over 16-bit rows is exact (packed HMNMX2 path)"""
+    n, e = 600, 24000
+    g = torch.Generator().manual_seed(11)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei[1, ::50] = 17                                       # one hub of ~480 + its random share
+    x = torch.randn(n, 512, generator=g)
+    x = x.to(engine._TORCH[engine.PRECISION_FORMATS[precision][0]]).float()
+    want = O.aggregate(x.double(), ei, aggr).float()
+    idx = build_graph_index(ei.to(DEV), None, n)
+    deg = idx.rowptr.cpu()[1:] - idx.rowptr.cpu()[:-1]
+    assert int(((deg > 32) & (deg <= capi.BG_BIG_ROW_THRESHOLD)).sum()) > 100 and idx.n_big >= 1
+    xa, oa = Activation(n, 512, precision, DEV), Activation(n, 512, precision, DEV)
+    xa.data.copy_(x)
+    engine.aggregate(xa, oa, idx, aggr)
+    got = oa.data.float().cpu()
+    if aggr == "max":
+        assert torch.equal(got, want)                      # the maximum of representable values is representable
+    elif precision == "tf32":
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-4)
+    else:
+        torch.testing.assert_close(got, want, rtol=8e-3 if precision == "bf16" else 1e-3, atol=0.2 if aggr == "sum" else 2e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16", "tf32"])
+@pytest.mark.parametrize("aggr", ["mean", "sum", "max"])
 def test_aggregate_128_columns(aggr, precision):
     torch.manual_seed(7)
     b = make_batch(3, nx=19, ny=15)
