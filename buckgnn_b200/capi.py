@@ -20,7 +20,7 @@ BG_BF16, BG_F32, BG_F16 = 0, 1, 2
 BG_AGGR_MEAN, BG_AGGR_SUM, BG_AGGR_MAX = 0, 1, 2
 BG_BIG_ROW_THRESHOLD = 64
 BG_MAX_GEMM_SEGMENTS = 8
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 AGGR_CODES = {"mean": BG_AGGR_MEAN, "sum": BG_AGGR_SUM, "add": BG_AGGR_SUM, "max": BG_AGGR_MAX}
 
@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "bg_csr_max_big_rows", "bg_csr_workspace_bytes", "bg_csr_build",
     "bg_batch_info", "bg_graph_ptr_build", "bg_publish_words", "bg_encoder_front",
     "bg_aggregate_workspace_bytes", "bg_hubfold_workspace_bytes", "bg_sage_aggregate", "bg_gemm512",
+    "bg_sage_fused512", "bg_sage_aggregate_hubs",
     "bg_wgrad512", "bg_pool_workspace_bytes", "bg_pool_head", "bg_pool_block_flags", "bg_pool_head_blocks", "bg_cast_f32", "bg_split_tf32",
     "bg_expand_rowptr", "bg_add",
     "bg_train_workspace_bytes", "bg_bn_batch_stats", "bg_bn_act_forward", "bg_sage_backward_rows",
@@ -60,6 +61,11 @@ class Epilogue(C.Structure):
                 ("pool_block_sums", C.c_void_p), ("pool_block_keep", C.c_void_p)]
 
 
+class FusedAggregate(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ldx", C.c_int64), ("rowptr", C.c_void_p), ("col", C.c_void_p),
+                ("aggr", C.c_int32), ("n_big", C.c_int32), ("hub_agg", C.c_void_p), ("big_rows", C.c_void_p)]
+
+
 _lib = None
 _lock = threading.Lock()
 _P, _I64, _I32, _SZP = C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_size_t)
@@ -85,6 +91,9 @@ _SIGNATURES = {
                                     C.c_size_t, _P]),
     "bg_gemm512": (C.c_int, [C.POINTER(GemmSegment), _I32, _I64, C.c_int, C.c_int, C.POINTER(Epilogue), _P,
                              C.c_int, _I64, C.c_int, _P]),
+    "bg_sage_fused512": (C.c_int, [C.POINTER(GemmSegment), _I32, _I64, C.c_int, C.c_int, C.POINTER(Epilogue),
+                                   C.POINTER(FusedAggregate), _P, C.c_int, _I64, _P]),
+    "bg_sage_aggregate_hubs": (C.c_int, [_P, C.c_int, _P, _P, _P, _I32, C.c_int, _P, _P, C.c_size_t, _P]),
     "bg_wgrad512": (C.c_int, [_P, _I64, _P, _I32, _I64, C.c_int, _I64, _I32, _I64, _P, _P]),
     "bg_pool_workspace_bytes": (C.c_int, [_I64, _SZP]),
     "bg_pool_head": (C.c_int, [_P, C.c_int, _I64, _P, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P,
@@ -251,6 +260,26 @@ def gemm512(segments, m, a_dtype, b_dtype, out, out_dtype, ldo, stream, *, bias=
                    gm, gi, gather_ld, inv_norm_out, pool_block_sums, pool_block_keep)
     _check(load().bg_gemm512(arr, n, m, a_dtype, b_dtype, C.byref(epi), out, out_dtype, ldo, cta_group, stream),
            "bg_gemm512")
+
+
+def sage_fused512(segments, m, a_dtype, b_dtype, out, out_dtype, ldo, stream, *, x, ldx, rowptr, col, aggr, hub_agg=None,
+                  big_rows=None, n_big=0, bias=None, bn_scale=None, bn_shift=None, residual=None, ldr=0, relu=False,
+                  pool_block_sums=None, pool_block_keep=None):
+    """The fused SAGE layer: bg_gemm512 whose first segment's A operand (the neighbourhood aggregate of `x`) is gathered
+    inside the kernel.  segments[0] = (None, 0, lin_l_ptr, ldb, 512), segments[1:] as in gemm512."""
+    n = len(segments)
+    arr = (GemmSegment * n)(*[GemmSegment(a, lda, b, ldb, k, 0) for (a, lda, b, ldb, k) in segments])
+    none2 = (C.c_void_p * 2)(None, None)
+    epi = Epilogue(bias, bn_scale, bn_shift, residual, ldr, 1, int(bool(relu)), none2, (C.c_void_p * 2)(None, None), 512,
+                   None, pool_block_sums, pool_block_keep)
+    fa = FusedAggregate(x, ldx, rowptr, col, aggr, n_big, hub_agg, big_rows)
+    _check(load().bg_sage_fused512(arr, n, m, a_dtype, b_dtype, C.byref(epi), C.byref(fa), out, out_dtype, ldo, stream),
+           "bg_sage_fused512")
+
+
+def sage_aggregate_hubs(x, dtype, rowptr, col, big_rows, n_big, aggr, hub_out, ws, ws_bytes, stream):
+    _check(load().bg_sage_aggregate_hubs(x, dtype, rowptr, col, big_rows, n_big, aggr, hub_out, ws, ws_bytes, stream),
+           "bg_sage_aggregate_hubs")
 
 
 POOL_MODES = {"mean": 0, "mlp": 0, "mean_no_super": 1, "mlp_no_super": 1, "supernode_only": 2,

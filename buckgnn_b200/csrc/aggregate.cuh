@@ -542,7 +542,9 @@ k_hub_finalize(T* __restrict__ out, int64_t N, int64_t band, const int32_t* __re
 }
 
 // grid = n_big * kHubSlices CTAs of 8 warps; partial [n_big][kHubSlices][512] f32; ticket [n_big] (zeroed)
-template <typename T, int kAggr>
+// kCompact: the aggregate of hub b goes to row b of `out` ([n_big, 512], the fused SAGE layer's side buffer) instead of
+// row big_rows[b] of the [N, 512] aggregate matrix
+template <typename T, int kAggr, bool kCompact = false>
 __global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
 k_aggregate_hubs(const T* __restrict__ x, T* __restrict__ out,
                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -582,7 +584,7 @@ k_aggregate_hubs(const T* __restrict__ x, T* __restrict__ out,
   if (!is_last) return;
   __threadfence();
   const float* hp = partial + (size_t)hub * kHubSlices * kHidden;
-  T* orow = out + (size_t)r * kHidden;
+  T* orow = out + (size_t)(kCompact ? hub : r) * kHidden;
   for (int c = threadIdx.x; c < kHidden; c += blockDim.x) {
     float v = __ldcg(hp + c);
     for (int s = 1; s < kHubSlices; ++s) v = agg_op<kAggr>(v, __ldcg(hp + (size_t)s * kHidden + c));

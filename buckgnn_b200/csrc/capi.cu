@@ -516,8 +516,9 @@ int bg_sage_aggregate(const void* x, void* out, int dtype, int64_t N, int32_t wi
 // ------------------------------------------------------------------ K3
 static inline int umma_format_of(int dtype) { return dtype == BG_F16 ? 0 : (dtype == BG_BF16 ? 1 : (dtype == BG_F32 ? 2 : -1)); }
 
-int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtype, int b_dtype,
-               const bg_epilogue* epi, void* out, int out_dtype, int64_t ldo, int cta_group, void* stream_) {
+static int gemm512_impl(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtype, int b_dtype,
+                        const bg_epilogue* epi, const bg_fused_aggregate* fuse, void* out, int out_dtype, int64_t ldo,
+                        int cta_group, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!segs || n_seg < 1 || n_seg > BG_MAX_GEMM_SEGMENTS) return fail(BG_ERR_INVALID, "bg_gemm512: bad segment count");
   if (m < 0 || m >= 0x7fffffffLL) return fail(BG_ERR_INVALID, "bg_gemm512: bad m");
@@ -535,13 +536,14 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < n_seg; ++s) {
     const bg_gemm_segment& g = segs[s];
-    if (!g.a || !g.b || g.k <= 0 || g.k % kblk != 0) return fail(BG_ERR_UNSUPPORTED, "bg_gemm512: k must be a positive multiple of 64 (16-bit) / 32 (tf32)");
-    if (!aligned16(g.a) || !aligned16(g.b) || (g.lda * esz) % 16 != 0 || (g.ldb * esz) % 16 != 0 || g.lda < g.k || g.ldb < g.k)
+    const bool gathered = fuse != nullptr && s == 0;      // the A operand of this segment is produced inside the kernel
+    if ((!g.a && !gathered) || !g.b || g.k <= 0 || g.k % kblk != 0) return fail(BG_ERR_UNSUPPORTED, "bg_gemm512: k must be a positive multiple of 64 (16-bit) / 32 (tf32)");
+    if ((!gathered && (!aligned16(g.a) || (g.lda * esz) % 16 != 0 || g.lda < g.k)) || !aligned16(g.b) || (g.ldb * esz) % 16 != 0 || g.ldb < g.k)
       return fail(BG_ERR_INVALID, "bg_gemm512: operand alignment / leading dimension");
     const int groups = g.b_groups > 1 ? g.b_groups : 1;
     if (groups != (segs[0].b_groups > 1 ? segs[0].b_groups : 1)) return fail(BG_ERR_INVALID, "bg_gemm512: segments disagree on b_groups");
     if (groups > 1 && m != (int64_t)groups * kHidden) return fail(BG_ERR_INVALID, "bg_gemm512: b_groups needs m == b_groups * 512");
-    int rc = make_operand_map(&p.seg[s].a, g.a, m, g.k, g.lda, (uint32_t)a_fmt);
+    int rc = gathered ? BG_OK : make_operand_map(&p.seg[s].a, g.a, m, g.k, g.lda, (uint32_t)a_fmt);
     if (rc == BG_OK) rc = make_operand_map(&p.seg[s].b, g.b, (int64_t)groups * kHidden, g.k, g.ldb, (uint32_t)b_fmt);
     if (rc != BG_OK) return fail(rc, "bg_gemm512: cuTensorMapEncodeTiled failed");
     p.kblocks[s] = g.k / kblk;
@@ -591,6 +593,28 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
     memcpy(&p.shift_h2[i], &sh, 4);
   }
   p.out = out; p.ldo = ldo;
+  if (fuse) {
+    // fused SAGE layer: segment 0 = (aggregate of fuse->x, lin_l), K = 512, gathered in the kernel; 16-bit activations,
+    // the normalize epilogue (with or without skip rows, or pool-fused)
+    if (tf32 || out_dtype == BG_F32) return fail(BG_ERR_UNSUPPORTED, "bg_sage_fused512: 16-bit activations only");
+    if (segs[0].k != kHidden || (segs[0].b_groups > 1)) return fail(BG_ERR_UNSUPPORTED, "bg_sage_fused512: segment 0 must be K = 512, one weight group");
+    if (!fuse->x || !fuse->rowptr || (!fuse->col && m > 0) || !aligned16(fuse->x) || (fuse->ldx * esz) % 16 != 0 || fuse->ldx < kHidden)
+      return fail(BG_ERR_INVALID, "bg_sage_fused512: bad x / CSR");
+    if (fuse->aggr != BG_AGGR_MEAN && fuse->aggr != BG_AGGR_SUM) return fail(BG_ERR_UNSUPPORTED, "bg_sage_fused512: mean / sum aggregation only");
+    if (fuse->n_big < 0 || (fuse->n_big > 0 && (!fuse->hub_agg || !fuse->big_rows || !aligned16(fuse->hub_agg))))
+      return fail(BG_ERR_INVALID, "bg_sage_fused512: hub rows need hub_agg and big_rows");
+    if (p.n_gather > 0 || !p.normalize) return fail(BG_ERR_UNSUPPORTED, "bg_sage_fused512: the SAGE update epilogue (normalize) only");
+    p.fuse_x = fuse->x; p.fuse_ldx = fuse->ldx; p.fuse_rowptr = fuse->rowptr; p.fuse_col = fuse->col;
+    p.fuse_hub_agg = fuse->hub_agg; p.fuse_big_rows = fuse->big_rows; p.fuse_n_big = fuse->n_big;
+    p.fuse_mean = fuse->aggr == BG_AGGR_MEAN ? 1 : 0;
+#define BG_FUSED_OUT(ADD, POOL)                                                                        \
+  (out_dtype == BG_BF16 ? launch_gemm512<2, __nv_bfloat16, ADD, false, POOL, true>(p, stream)           \
+                        : launch_gemm512<2, __half, ADD, false, POOL, true>(p, stream))
+    if (p.pool_sums) return BG_FUSED_OUT(kAddNone, true);
+    if (p.residual) return BG_FUSED_OUT(kAddResidual, false);
+    return BG_FUSED_OUT(kAddNone, false);
+#undef BG_FUSED_OUT
+  }
   // "plain" epilogue: no normalize, no BatchNorm vectors -> the packed 16-bit pass 2 (exactly equivalent rounding)
   const bool plain = !p.normalize && !(epi && epi->bn_scale_host) && out_dtype != BG_F32;
 #define BG_GEMM_OUT2(ADD, PLAIN)                                                               \
@@ -606,6 +630,42 @@ int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtyp
   return BG_GEMM_OUT(kAddNone);
 #undef BG_GEMM_OUT2
 #undef BG_GEMM_OUT
+}
+
+int bg_gemm512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtype, int b_dtype,
+               const bg_epilogue* epi, void* out, int out_dtype, int64_t ldo, int cta_group, void* stream_) {
+  return gemm512_impl(segs, n_seg, m, a_dtype, b_dtype, epi, nullptr, out, out_dtype, ldo, cta_group, stream_);
+}
+
+int bg_sage_fused512(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, int a_dtype, int b_dtype,
+                     const bg_epilogue* epi, const bg_fused_aggregate* fuse, void* out, int out_dtype, int64_t ldo,
+                     void* stream_) {
+  if (!fuse) return fail(BG_ERR_INVALID, "bg_sage_fused512: fused aggregate description missing");
+  if (n_seg < 2) return fail(BG_ERR_INVALID, "bg_sage_fused512: needs the (aggregate, lin_l) and (x, lin_r) segments");
+  return gemm512_impl(segs, n_seg, m, a_dtype, b_dtype, epi, fuse, out, out_dtype, ldo, 2, stream_);
+}
+
+int bg_sage_aggregate_hubs(const void* x, int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* big_rows,
+                           int32_t n_big, int aggr, void* hub_out, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_big < 0) return fail(BG_ERR_INVALID, "bg_sage_aggregate_hubs: bad n_big");
+  if (n_big == 0) return BG_OK;
+  if (!x || !rowptr || !col || !big_rows || !hub_out || !aligned16(x) || !aligned16(hub_out))
+    return fail(BG_ERR_INVALID, "bg_sage_aggregate_hubs: bad pointer");
+  if (!workspace || workspace_bytes < generic_hub_bytes(n_big)) return fail(BG_ERR_WORKSPACE, "bg_sage_aggregate_hubs: workspace too small");
+  float* partial = static_cast<float*>(workspace);
+  int32_t* ticket = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + (size_t)n_big * kHubSlices * kHidden * sizeof(float));
+  BG_CUDA_OK(cudaMemsetAsync(ticket, 0, sizeof(int32_t) * (size_t)n_big, stream));
+  const unsigned grid = (unsigned)n_big * kHubSlices;
+#define BG_HUBS_CASE(T, A) k_aggregate_hubs<T, A, true><<<grid, kAggWarpsPerBlock * 32, 0, stream>>>(                 \
+      static_cast<const T*>(x), static_cast<T*>(hub_out), rowptr, col, big_rows, n_big, partial, ticket)
+  if (aggr != BG_AGGR_MEAN && aggr != BG_AGGR_SUM) return fail(BG_ERR_UNSUPPORTED, "bg_sage_aggregate_hubs: mean / sum only");
+  if (dtype == BG_F16) { if (aggr == BG_AGGR_MEAN) BG_HUBS_CASE(__half, BG_AGGR_MEAN); else BG_HUBS_CASE(__half, BG_AGGR_SUM); }
+  else if (dtype == BG_BF16) { if (aggr == BG_AGGR_MEAN) BG_HUBS_CASE(__nv_bfloat16, BG_AGGR_MEAN); else BG_HUBS_CASE(__nv_bfloat16, BG_AGGR_SUM); }
+  else return fail(BG_ERR_UNSUPPORTED, "bg_sage_aggregate_hubs: 16-bit rows only");
+#undef BG_HUBS_CASE
+  BG_LAUNCH_OK();
+  return BG_OK;
 }
 
 int bg_wgrad512(const void* dz, int64_t ld_dz, const void* act, int32_t act_cols, int64_t ld_act, int dtype, int64_t n_rows,

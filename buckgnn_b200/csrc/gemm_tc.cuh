@@ -42,6 +42,8 @@ constexpr int kTileM = 128;                       // rows per CTA
 constexpr int kStageKBytes = 128;                 // one 128B swizzle row of K per stage
 constexpr int kATileBytes = kTileM * kStageKBytes;        // 16 KB
 constexpr int kGemmThreads = 384;                 // 12 warps
+constexpr int kGatherWarps = 4;                   // kFuse: warps 12-15 (one warpgroup: setmaxnreg is per warpgroup) gather the aggregate operand
+constexpr int kGemmThreadsFused = 512;            // 16 warps
 constexpr int kEpiFirstWarp = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiStageBytes = 32 * 128;          // per-warp staging tile: 32 rows x 128 B
@@ -89,6 +91,16 @@ struct alignas(64) GemmParams {
                                     // both operands are MN-major (the reduction runs over matrix rows), so no
                                     // transposed copies are needed.  Tile t = (chunk t/2, output rows (t%2)*256..+256).
   int64_t chunk_k;                  // nodes per chunk (mn_major)
+  // kFuse (fused SAGE layer): segment 0's A operand -- the neighbourhood aggregate of the rows of `fuse_x` -- is not
+  // read from memory but PRODUCED inside the kernel by gather warps (see fused_gather below); seg[0].a is unused
+  const void* fuse_x;               // [*, 512] 16-bit rows of the layer input (the same matrix seg[1].a maps), ld = fuse_ldx
+  int64_t fuse_ldx;
+  const int32_t* fuse_rowptr;       // CSR by destination row (bg_csr_build)
+  const int32_t* fuse_col;
+  const void* fuse_hub_agg;         // [n_big, 512] aggregates of the hub rows (degree > kBigRowThreshold), slot = index in big_rows
+  const int32_t* fuse_big_rows;
+  int32_t fuse_n_big;
+  int32_t fuse_mean;                // 1: mean, 0: sum
   float bias[kHidden];              // epilogue vectors by value -> constant bank, broadcast reads
   float scale[kHidden];             // 1 when there is no BN
   float shift[kHidden];             // 0 when there is no BN
@@ -620,9 +632,135 @@ BG_DEVINL void epilogue_warp(const GemmParams& p, const EpiCtx& cx, const int g)
 #endif
 }
 
-template <int kCg, typename TOut, int kAdd, bool kPlain, bool kPool = false>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// ---------------------------------------------------------------------------------------------------------------
+// kFuse: the fused SAGE layer (north_star; reference Models/BuckGNN.py:449-457 = SAGEConv.propagate + lin_l / lin_r).
+// The aggregate operand never exists in global memory.  Four gather warps per CTA build the [128 rows x 64 columns]
+// K block of mean_j x[j] for the CTA's rows straight into the A half of the pipeline stage the MMA will read, in the
+// 128-byte-swizzled K-major layout TMA would have produced: 8 lanes per row (one 16-byte chunk each, 4 rows per warp
+// pass), up to 8 neighbour rows in flight per lane, fp32 accumulation in CSR order, the same reciprocal multiply and
+// rounding as k_aggregate_rows -- so the operand is bit-identical to the unfused one.  The weight half of the stage
+// still arrives by TMA; a stage's "full" barrier counts the producer and the gather warps of both CTAs of the pair.
+// Neighbour rows come from L2 (the x tiles of the ~74 row tiles in flight were just read by the pairs next door);
+// hub rows (the super node) are copied from a small side buffer filled by k_aggregate_hubs beforehand.
+BG_DEVINL void mbar_arrive_cluster_release(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 r;\n\t"
+      "mapa.shared::cluster.u32 r, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [r];\n\t}" ::"r"(bar), "r"(cta) : "memory");
+}
+
+template <int kCg, typename T, int kStages, int kStageBytes>
+BG_DEVINL void fused_gather(const GemmParams& p, const int gw, const uint32_t stages_u32, const uint32_t bars_u32,
+                            const uint32_t rank, const int tile0, const int tile_stride) {
+  constexpr uint32_t kFull = 0xffffffffu;
+  constexpr int kPasses = (32 + kGatherWarps - 1) / kGatherWarps;       // 4-row passes of one warp per K block
+  const int lane = threadIdx.x & 31;
+  const int grp = lane >> 3, c = lane & 7;
+  const char* xb = reinterpret_cast<const char*>(p.fuse_x) + c * 16;
+  const char* hb = reinterpret_cast<const char*>(p.fuse_hub_agg) + c * 16;
+  const size_t row_bytes = (size_t)p.fuse_ldx * sizeof(T);
+  const int nkb = p.kblocks[0];
+  int per_tile = 0;
+  for (int s = 0; s < p.n_seg; ++s) per_tile += p.kblocks[s];
+  uint32_t cnt0 = 0;                                                    // pipeline slot of this tile's first K block
+  for (int tile = tile0; tile < p.n_tiles; tile += tile_stride, cnt0 += (uint32_t)per_tile) {
+    const int64_t row0 = (int64_t)tile * (kTileM * kCg) + (int64_t)rank * kTileM;
+    // per pass: offsets, degree and the first 8 neighbour ids of this lane group's row (lane c holds neighbour c);
+    // a hub row keeps its slot in the side buffer instead
+    int32_t beg[kPasses], deg[kPasses], nb[kPasses];
+#pragma unroll
+    for (int i = 0; i < kPasses; ++i) {
+      const int pass = gw + i * kGatherWarps;
+      const int64_t r = row0 + 4 * pass + grp;
+      int32_t b = 0, e = 0;
+      if (pass < 32 && r < p.m) { b = p.fuse_rowptr[r]; e = p.fuse_rowptr[r + 1]; }
+      const int32_t d = e - b;
+      const bool is_hub = d > kBigRowThreshold;
+      int32_t v = (!is_hub && c < d) ? p.fuse_col[b + c] : 0;
+      if (__any_sync(kFull, is_hub)) {                                  // rare: find the row in big_rows (8 lanes per probe)
+        for (int32_t k = 0; k < p.fuse_n_big; k += 8) {
+          const bool hit = is_hub && k + c < p.fuse_n_big && p.fuse_big_rows[k + c] == (int32_t)r;
+          const uint32_t bits = (__ballot_sync(kFull, hit) >> (grp * 8)) & 0xffu;
+          if (bits) v = k + __ffs(bits) - 1;
+        }
+      }
+      beg[i] = b; deg[i] = d; nb[i] = v;
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+      const uint32_t cnt = cnt0 + (uint32_t)kb;
+      const uint32_t stage = cnt % kStages, parity = (cnt / kStages) & 1u;
+      mbar_wait(bars_u32 + 8u * (kStages + stage), parity ^ 1u, kTagEmpty);          // the MMAs that read this slot retired
+      const uint32_t sa = stages_u32 + stage * kStageBytes;
+      const size_t koff = (size_t)kb * kStageKBytes;
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i) {
+        const int pass = gw + i * kGatherWarps;
+        if (pass >= 32) break;                                          // warp-uniform
+        const int R = 4 * pass + grp;
+        const int32_t d = deg[i];
+        const bool is_hub = d > kBigRowThreshold;
+        const int32_t dn = is_hub ? 0 : d;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        auto add = [&](const uint4& q) {
+          Pack16<T>::add2(acc[0], acc[1], q.x); Pack16<T>::add2(acc[2], acc[3], q.y);
+          Pack16<T>::add2(acc[4], acc[5], q.z); Pack16<T>::add2(acc[6], acc[7], q.w);
+        };
+        {
+          uint4 q[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int32_t n = __shfl_sync(kFull, nb[i], (lane & 24) + j);
+            q[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (j < dn) q[j] = ldg_v4(xb + (size_t)n * row_bytes + koff);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) add(q[j]);
+        }
+        int32_t wmax = dn;                                              // more than 8 neighbours somewhere in the warp?
+        wmax = max(wmax, __shfl_xor_sync(kFull, wmax, 8));
+        wmax = max(wmax, __shfl_xor_sync(kFull, wmax, 16));
+        for (int32_t base = 8; base < wmax; base += 8) {
+          const int32_t idx = (base + c < dn) ? p.fuse_col[beg[i] + base + c] : 0;
+          uint4 q[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int32_t n = __shfl_sync(kFull, idx, (lane & 24) + j);
+            q[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (base + j < dn) q[j] = ldg_v4(xb + (size_t)n * row_bytes + koff);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) add(q[j]);
+        }
+        uint4 o;
+        if (is_hub) {
+          o = ldg_v4(hb + (size_t)nb[i] * (kHidden * sizeof(T)) + koff);
+        } else {
+          if (p.fuse_mean) {
+            const float rd = 1.f / (float)max(d, 1);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] *= rd;
+          }
+          o.x = Pack16<T>::pack(acc[0], acc[1]); o.y = Pack16<T>::pack(acc[2], acc[3]);
+          o.z = Pack16<T>::pack(acc[4], acc[5]); o.w = Pack16<T>::pack(acc[6], acc[7]);
+        }
+        sts_v4(sa + (uint32_t)R * 128u + (((uint32_t)c ^ ((uint32_t)R & 7u)) << 4), o);
+      }
+      fence_proxy_async_smem();                                         // generic-proxy stores -> visible to the tensor core's reads
+      named_bar_sync(2, kGatherWarps * 32);
+      if (gw == 0 && lane == 0) {
+        if (kCg == 1 || rank == 0) mbar_arrive(bars_u32 + 8u * stage);
+        else mbar_arrive_cluster_release(bars_u32 + 8u * stage, 0);
+      }
+    }
+  }
+}
+
+template <int kCg, typename TOut, int kAdd, bool kPlain, bool kPool = false, bool kFuse = false>
+__global__ void __launch_bounds__(kFuse ? kGemmThreadsFused : kGemmThreads, 1)
 k_gemm512(const __grid_constant__ GemmParams p) {
+  static_assert(!kFuse || (sizeof(TOut) == 2 && kCg == 2), "fused SAGE layer: 16-bit activations, CTA pairs");
   using Cfg = GemmCfg<kCg>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t gemm_smem_raw[];
@@ -647,12 +785,13 @@ k_gemm512(const __grid_constant__ GemmParams p) {
 
   // ---- one-time setup
   if (warp == 0 && elect_one()) {
-    for (int s = 0; s < p.n_seg; ++s) { tma_prefetch_desc(&p.seg[s].a); tma_prefetch_desc(&p.seg[s].b); }
+    for (int s = 0; s < p.n_seg; ++s) { if (!(kFuse && s == 0)) tma_prefetch_desc(&p.seg[s].a); tma_prefetch_desc(&p.seg[s].b); }
   }
   if (kCg == 2) cluster_sync();                // both CTAs resident before the paired TMEM alloc
   if (warp == 1) {
     if (elect_one()) {
-      for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), kCg); mbar_init(empty_bar(s), 1); }
+      // (kFuse: a stage is full when the producer AND the gather warps of both CTAs have delivered)
+      for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), kFuse ? 2 * kCg : kCg); mbar_init(empty_bar(s), 1); }
       mbar_init(tmem_full_bar, 1);
       mbar_init(tmem_empty_bar, kCg * 256);
       fence_mbar_init();
@@ -665,7 +804,15 @@ k_gemm512(const __grid_constant__ GemmParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  if (warp < kEpiFirstWarp) {
+  if (kFuse && warp >= kEpiFirstWarp + kEpiWarps) {
+    // ================================================================ gather warps 12..15 (fused SAGE layer)
+    // register budget per warpgroup (setmaxnreg acts on whole warpgroups): 128 * (40 + 192 + 192 + 88) = 65536
+    if constexpr (kFuse) {
+      setmaxnreg_dec<88>();
+      fused_gather<kCg, TOut, kStages, Cfg::kStageBytes>(p, warp - (kEpiFirstWarp + kEpiWarps), stages_u32, bars_u32, rank,
+                                                         tile0, tile_stride);
+    }
+  } else if (warp < kEpiFirstWarp) {
     setmaxnreg_dec<40>();
     if (warp == 0) {
       // ================================================================ TMA producer
@@ -729,9 +876,14 @@ k_gemm512(const __grid_constant__ GemmParams p) {
 #else
                 constexpr bool load_a = true;
 #endif
-                if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * ((load_a ? kATileBytes : 0) + (load_b ? Cfg::kBTileBytes : 0)));
+                const bool gathered = kFuse && s == 0;                  // this stage's A half comes from the gather warps
+                if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * ((load_a && !gathered ? kATileBytes : 0) + (load_b ? Cfg::kBTileBytes : 0)));
                 else mbar_arrive_cluster(full_bar(stage), 0);
-                if (load_a) tma_load_2d_cg2(sa, map_a, full_bar(stage), k0, row0);
+                if (kFuse && !gathered) {                               // no gather arrival on this stage: the producer stands in
+                  if (rank == 0) mbar_arrive(full_bar(stage));
+                  else mbar_arrive_cluster(full_bar(stage), 0);
+                }
+                if (load_a && !gathered) tma_load_2d_cg2(sa, map_a, full_bar(stage), k0, row0);
                 if (load_b) {
 #pragma unroll
                   for (int j = 0; j < Cfg::kBRows / 128; ++j)      // N half j: weight rows j*256 + rank*128
@@ -795,9 +947,9 @@ k_gemm512(const __grid_constant__ GemmParams p) {
 #endif
       __syncwarp();
     }
-  } else {
+  } else if (warp < kEpiFirstWarp + kEpiWarps) {
     // ================================================================ epilogue warps 4..11
-    setmaxnreg_inc<232>();
+    if constexpr (kFuse) setmaxnreg_inc<192>(); else setmaxnreg_inc<232>();
     const int ew = warp - kEpiFirstWarp;
     const EpiCtx cx{tmem_base, epi_u32 + (uint32_t)ew * kEpiStageBytes,
                     reinterpret_cast<float*>(epi_gen + ew * kEpiStageBytes),
@@ -805,6 +957,7 @@ k_gemm512(const __grid_constant__ GemmParams p) {
                     tmem_full_bar, tmem_empty_bar, rank, tile0, tile_stride};
     epilogue_warp<kCg, TOut, kAdd, kPlain, kPool>(p, cx, ew >> 2);
   }
+  static_assert(kEpiFirstWarp + kEpiWarps + kGatherWarps == kGemmThreadsFused / 32, "fused warp roles");
 
   // ---- teardown
   tc_fence_before();
@@ -865,10 +1018,10 @@ static inline int make_mn_operand_map(CUtensorMap* map, const void* base, int64_
   return r == CUDA_SUCCESS ? BG_OK : BG_ERR_CUDA;
 }
 
-template <int kCg, typename TOut, int kAdd, bool kPlain, bool kPool = false>
+template <int kCg, typename TOut, int kAdd, bool kPlain, bool kPool = false, bool kFuse = false>
 static int launch_gemm512(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<kCg>;
-  auto kern = k_gemm512<kCg, TOut, kAdd, kPlain, kPool>;
+  auto kern = k_gemm512<kCg, TOut, kAdd, kPlain, kPool, kFuse>;
   static bool attr_set = false;
   if (!attr_set) {
     BG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -887,7 +1040,7 @@ static int launch_gemm512(const GemmParams& p, cudaStream_t stream) {
     cfg.numAttrs = 1;
   }
   cfg.attrs = attr;
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(kFuse ? kGemmThreadsFused : kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   BG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));

@@ -436,12 +436,51 @@ def can_fuse_pool(precision: str, normalize: bool, residual: bool) -> bool:
     return PRECISION_FORMATS[precision][0] != capi.BG_F32 and normalize and not residual
 
 
+# The fused SAGE layer (bg_sage_fused512: the aggregate operand is gathered inside the GEMM kernel and never written to
+# global memory).  Opt-in: BUCKGNN_FUSE_AGGREGATE=1 in the environment, or `model.fuse_aggregate = True`.
+FUSE_AGGREGATE_DEFAULT = os.environ.get("BUCKGNN_FUSE_AGGREGATE", "0") not in ("", "0")
+
+
+def can_fuse_aggregate(precision: str, aggr: str, normalize: bool) -> bool:
+    return precision in ("fp16", "bf16") and aggr in ("mean", "sum", "add") and normalize
+
+
+def sage_layer_fused(x: Activation, out: Activation, idx: GraphIndex, layer: SageLayerPack, *, aggr: str, relu: bool,
+                     residual: bool, pool_blocks: Optional[PoolBlocks] = None) -> None:
+    """One reference layer iteration (Models/BuckGNN.py:447-457) as ONE kernel (+ the hub rows' aggregates, one small
+    launch over the few super-node rows): mean / sum aggregation, lin_l / lin_r, F.normalize, BatchNorm, ReLU, skip."""
+    dev = x.data.device
+    hub_agg = None
+    if idx.n_big > 0:
+        hub_agg = torch.empty((idx.n_big, 512), dtype=x.data.dtype, device=dev)
+        ws_bytes = capi.aggregate_workspace_bytes(idx.n_big)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with TIMERS.span("aggregate_hubs"):
+            capi.sage_aggregate_hubs(x.data.data_ptr(), x.code, idx.rowptr.data_ptr(), idx.col.data_ptr(),
+                                     idx.big_rows.data_ptr(), idx.n_big, capi.AGGR_CODES[aggr], hub_agg.data_ptr(),
+                                     ws.data_ptr(), ws_bytes, _stream())
+    k = layer.lin_l.k
+    segs = [(None, 0, layer.lin_l.parts[0].data_ptr(), k, k)] + _segments(x, layer.lin_r)
+    pool = {} if pool_blocks is None else dict(pool_block_sums=pool_blocks.sums.data_ptr(),
+                                               pool_block_keep=pool_blocks.keep.data_ptr())
+    a_code, b_code = PRECISION_FORMATS[x.precision]
+    with TIMERS.span("sage_fused" if pool_blocks is None else "sage_fused_pool"):
+        capi.sage_fused512(segs, idx.n_nodes, a_code, b_code, out.data.data_ptr(), out.code, out.data.shape[1], _stream(),
+                           x=x.data.data_ptr(), ldx=x.data.shape[1], rowptr=idx.rowptr.data_ptr(), col=idx.col.data_ptr(),
+                           aggr=capi.AGGR_CODES[aggr], hub_agg=_p(hub_agg), big_rows=idx.big_rows.data_ptr(), n_big=idx.n_big,
+                           bias=layer.bias.data_ptr(), bn_scale=_p(layer.bn_scale), bn_shift=_p(layer.bn_shift),
+                           residual=x.data.data_ptr() if residual else None, ldr=x.data.shape[1], relu=relu, **pool)
+    out.refresh_split()
+
+
 def sage_layer(x: Activation, agg: Activation, out: Activation, idx: GraphIndex, layer: SageLayerPack, *,
                aggr: str, normalize: bool, relu: bool, residual: bool, cta_group: int,
-               pool_blocks: Optional[PoolBlocks] = None) -> None:
+               pool_blocks: Optional[PoolBlocks] = None, fuse_aggregate: bool = False) -> None:
     """One reference layer iteration (Models/BuckGNN.py:447-457) = aggregate + fused update GEMM.
     `pool_blocks` (last layer of a graph-level model): the epilogue sums the output rows per 32-row block for
     `pool_head` instead of storing them (only the blocks at graph boundaries are stored)."""
+    if fuse_aggregate and can_fuse_aggregate(x.precision, aggr, normalize):
+        return sage_layer_fused(x, out, idx, layer, aggr=aggr, relu=relu, residual=residual, pool_blocks=pool_blocks)
     aggregate(x, agg, idx, aggr)
     segs = _segments(agg, layer.lin_l) + _segments(x, layer.lin_r)
     pool = {} if pool_blocks is None else dict(pool_block_sums=pool_blocks.sums.data_ptr(),

@@ -145,6 +145,7 @@ class BuckGNN(nn.Module):
         self.cache_index = cache_index
         self.fold_encoder = fold_encoder      # fold node_encoder[4] into SAGE layer 0 (mean / sum / add aggregation)
         self.fuse_pool = fuse_pool            # last SAGE layer's epilogue sums its rows for the pooling layer (16-bit modes)
+        self.fuse_aggregate = engine.FUSE_AGGREGATE_DEFAULT    # the aggregate operand gathered inside the update GEMM (opt-in)
         self.output_dim = output_dim = _output_dim(prediction_type, use_z_coord, use_rotations)
         h = hidden_channels
         cat_dec = pooling_layer == "supernode_with_pooling" and prediction_type == "buckling"
@@ -468,7 +469,8 @@ class BuckGNN(nn.Module):
                             and engine.can_fuse_pool(prec, True, residual)):
                         blocks = engine.new_pool_blocks(idx, x.device)
                     engine.sage_layer(cur, agg, nxt, idx, layer, aggr=aggr, normalize=True, relu=True,
-                                      residual=residual, cta_group=cg, pool_blocks=blocks)
+                                      residual=residual, cta_group=cg, pool_blocks=blocks,
+                                      fuse_aggregate=self.fuse_aggregate)
                 cur, nxt = nxt, cur
         if node_level:
             return engine.node_head(cur, n, packs["node_head"], self.output_dim, cg)     # reference :518-524

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BG_ABI_VERSION 10
+#define BG_ABI_VERSION 11
 
 typedef enum bg_status {
   BG_OK = 0,
@@ -196,6 +196,33 @@ typedef struct bg_epilogue {
 int bg_gemm512(const bg_gemm_segment* segments_host, int32_t n_segments, int64_t m,
                int a_dtype, int b_dtype, const bg_epilogue* epilogue_host,
                void* out, int out_dtype, int64_t ldo, int cta_group, void* stream);
+
+/* The fused SAGE layer (reference: SAGEConv.propagate + lin_l / lin_r + F.normalize + BatchNorm1d + ReLU + skip,
+ * Models/BuckGNN.py:449-457, in ONE kernel): bg_gemm512 whose segment 0 is (aggregate_of(x), lin_l.weight) with K = 512
+ * -- segment 0's `a` is ignored: four gather warps per CTA build the aggregate rows of the CTA's 128 nodes straight into
+ * the shared-memory operand tile the tensor core reads (fp32 accumulation in CSR order, the same rounding as
+ * bg_sage_aggregate: the operand is bit-identical), so the [N,512] aggregate matrix never exists in global memory.
+ * Segment 1.. as in bg_gemm512 (the root rows: (x, lin_r.weight)).  16-bit activations; the epilogue must normalize
+ * (skip rows and the pool-fused variant allowed, no gathered addends).  Rows whose degree exceeds
+ * BG_BIG_ROW_THRESHOLD take their aggregate from hub_agg (bg_sage_aggregate_hubs). */
+typedef struct bg_fused_aggregate {
+  const void* x; int64_t ldx;     /* DEVICE [N,512] rows of a_dtype: the layer input */
+  const int32_t* rowptr;          /* CSR by target (bg_csr_build, key_row = 1) */
+  const int32_t* col;
+  int32_t aggr;                   /* BG_AGGR_MEAN or BG_AGGR_SUM */
+  int32_t n_big;
+  const void* hub_agg;            /* DEVICE [n_big, 512] of a_dtype, row b = aggregate of node big_rows[b]; NULL iff n_big == 0 */
+  const int32_t* big_rows;
+} bg_fused_aggregate;
+
+int bg_sage_fused512(const bg_gemm_segment* segments_host, int32_t n_segments, int64_t m,
+                     int a_dtype, int b_dtype, const bg_epilogue* epilogue_host, const bg_fused_aggregate* fused_host,
+                     void* out, int out_dtype, int64_t ldo, void* stream);
+
+/* Aggregates of the hub rows only, compact: hub_out[b, :] = reduce over the neighbours of node big_rows[b] (mean / sum,
+ * 16-bit rows).  workspace: bg_aggregate_workspace_bytes(n_big). */
+int bg_sage_aggregate_hubs(const void* x, int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* big_rows,
+                           int32_t n_big, int aggr, void* hub_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Weight gradients of a Linear with 512 outputs, dW[o, i] = sum_n dz[n, o] * act[n, i] (autograd of lin_l / lin_r,
  * Models/BuckGNN.py:449): the reduction runs over the ROWS of the row-major dz [n_rows, 512] and act [n_rows, act_cols]

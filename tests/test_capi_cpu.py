@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(capi.library_path())
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.bg_abi_version() == capi.ABI_VERSION == 10
+    assert lib.bg_abi_version() == capi.ABI_VERSION == 11
 
 
 def test_size_queries_and_argument_errors_without_gpu(lib):
