@@ -754,6 +754,14 @@ BG_DEVINL void fused_gather(const GemmParams& p, const int gw, const uint32_t st
         else mbar_arrive_cluster_release(bars_u32 + 8u * stage, 0);
       }
     }
+    // The other segments' slots are filled by the producer alone, but their "empty" phases are observed here too, one
+    // by one: a parity wait can only tell the current phase from the previous one, so a warp that skipped the two uses
+    // a slot has between this tile's aggregate K blocks and the next tile's would take the phase of the FIRST skipped
+    // use for the one it is waiting for and overwrite a tile the tensor core has not read yet.
+    for (int kb = nkb; kb < per_tile; ++kb) {
+      const uint32_t cnt = cnt0 + (uint32_t)kb;
+      mbar_wait(bars_u32 + 8u * (kStages + cnt % kStages), ((cnt / kStages) & 1u) ^ 1u, kTagEmpty);
+    }
   }
 }
 

@@ -198,7 +198,7 @@ def test_ctypes_signatures_match_the_header_prototypes():
         for a, t in zip(args, argtypes):
             if "*" in a or a.startswith("void*"):
                 assert t in (C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.POINTER(capi.GemmSegment),
-                             C.POINTER(capi.Epilogue)), (name, a, t)
+                             C.POINTER(capi.Epilogue), C.POINTER(capi.FusedAggregate)), (name, a, t)
             elif a.startswith("int64_t"):
                 assert t is C.c_int64, (name, a, t)
             elif a.startswith("int32_t"):

@@ -96,3 +96,25 @@ def test_fused_layer_rejects_what_it_cannot_do():
     assert not engine.can_fuse_aggregate("tf32", "mean", True) and not engine.can_fuse_aggregate("fp16", "max", True)
     with pytest.raises(capi.BuckGNNError):
         engine.sage_layer_fused(x, out, idx, layer, aggr="mean", relu=True, residual=False)
+
+
+def test_fused_layer_with_several_tiles_per_cta_and_repeated_launches():
+    """193 row tiles on 74 CTA pairs: every pair walks 2-3 tiles, so the gather warps cross tile boundaries of the
+    4-slot operand ring (the round-2 bug: a parity wait that skipped the slots filled by the producer alone took the
+    wrong phase for its own and overwrote tiles the tensor core had not read -- only when the gathers were FAST, i.e.
+    from the second launch on, with the rows in L2)."""
+    b = make_batch(12, nx=64, ny=64)
+    n = b.num_nodes
+    _, ours = _pair("GraphSage_meanAggr", "fp16", layers=2)
+    layer = ours._packed()["layers"][1]
+    idx = build_graph_index(b.edge_index.to(DEV), b.batch.to(DEV), n)
+    x, agg, out_a = (Activation(n, 512, "fp16", DEV) for _ in range(3))
+    x.data.copy_(torch.randn(n, 512, device=DEV).abs())
+    engine.aggregate(x, agg, idx, "mean", fold_hubs=False)
+    segs = engine._segments(agg, layer.lin_l) + engine._segments(x, layer.lin_r)
+    engine.gemm512(segs, n, "fp16", out_a, bias=layer.bias.data_ptr(), bn_scale=engine._p(layer.bn_scale),
+                   bn_shift=engine._p(layer.bn_shift), residual=x.data.data_ptr(), ldr=512, normalize=True, relu=True)
+    for _ in range(6):
+        out_b = Activation(n, 512, "fp16", DEV)
+        engine.sage_layer_fused(x, out_b, idx, layer, aggr="mean", relu=True, residual=True)
+        assert torch.equal(out_a.data, out_b.data)
