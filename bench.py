@@ -214,6 +214,34 @@ def modes_section(args, dev, resident, world, G, barrier):
         out[mode] = {"graphs_per_s": world * G / (ms * 1e-3), "ms_per_step": ms, "steps": n,
                      "what": "fp32 storage, tf32 operands" if mode == "tf32" else "fp32-GEMM mode (3xTF32 split operands)"}
         del m
+    # the fused SAGE layer (bg_sage_fused512: aggregate operand gathered inside the update GEMM), headline precision
+    m = BuckGNN(**MODEL_CFG, precision=args.precision, cta_group=args.cta_group)
+    m.load_state_dict(ref.state_dict())
+    m = m.to(dev).eval()
+    if __import__("buckgnn_b200.engine", fromlist=["x"]).can_fuse_aggregate(m.precision, "mean", True):
+        with torch.no_grad():
+            plain, _ = m(resident.x, resident.edge_index, resident.edge_attr, resident.batch)
+            m.fuse_aggregate = True
+            fused, _ = m(resident.x, resident.edge_index, resident.edge_attr, resident.batch)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 2
+            e0.record()
+            for _ in range(n):
+                m(resident.x, resident.edge_index, resident.edge_attr, resident.batch)
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1) / n
+        dev_rel = ((fused.float() - plain.float()).abs() / plain.float().abs().clamp(min=1e-3)).max().item()
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        out["fused_sage_layer"] = {"graphs_per_s": world * G / (ms * 1e-3), "ms_per_step": ms, "steps": n,
+                                   "max_rel_dev_from_default_path": dev_rel,
+                                   "what": "opt-in: every SAGE layer as one kernel, the aggregate never written to HBM "
+                                           "(bit-identical operand; slower: gather-latency-bound, DESIGN.md section 5)"}
+    del m
     return out
 
 
