@@ -177,6 +177,15 @@ def test_narrow_hidden_stays_inside_its_tensors(hidden):
     assert _rel(got, want) < 1e-2
 
 
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_fused_sage_layer_stays_inside_its_tensors(precision):
+    """bg_sage_fused512 + bg_sage_aggregate_hubs (model.fuse_aggregate): side buffer, workspace and output rows"""
+    ref, ours = _pair("GraphSage_meanAggr", precision, layers=4)
+    ours.fuse_aggregate = True
+    got, want = _guarded_forward(ref, ours, _ragged())
+    assert _rel(got, want) < 1e-2
+
+
 def test_single_tiny_graph_and_batch_none():
     ref, ours = _pair("GraphSage_meanAggr", "fp16")
     got, want = _guarded_forward(ref, ours, make_batch(1, nx=2, ny=2), batch_none=True)
