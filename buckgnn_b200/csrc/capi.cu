@@ -598,8 +598,8 @@ static int gemm512_impl(const bg_gemm_segment* segs, int32_t n_seg, int64_t m, i
     // the normalize epilogue (with or without skip rows, or pool-fused)
     if (tf32 || out_dtype == BG_F32) return fail(BG_ERR_UNSUPPORTED, "bg_sage_fused512: 16-bit activations only");
     if (segs[0].k != kHidden || (segs[0].b_groups > 1)) return fail(BG_ERR_UNSUPPORTED, "bg_sage_fused512: segment 0 must be K = 512, one weight group");
-    if (!fuse->x || !fuse->rowptr || (!fuse->col && m > 0) || !aligned16(fuse->x) || (fuse->ldx * esz) % 16 != 0 || fuse->ldx < kHidden)
-      return fail(BG_ERR_INVALID, "bg_sage_fused512: bad x / CSR");
+    if (!fuse->x || !fuse->rowptr || (!fuse->col && m > 0) || !aligned16(fuse->x) || fuse->ldx != kHidden)
+      return fail(BG_ERR_INVALID, "bg_sage_fused512: bad x / CSR (rows of x must be contiguous: ldx == 512)");
     if (fuse->aggr != BG_AGGR_MEAN && fuse->aggr != BG_AGGR_SUM) return fail(BG_ERR_UNSUPPORTED, "bg_sage_fused512: mean / sum aggregation only");
     if (fuse->n_big < 0 || (fuse->n_big > 0 && (!fuse->hub_agg || !fuse->big_rows || !aligned16(fuse->hub_agg))))
       return fail(BG_ERR_INVALID, "bg_sage_fused512: hub rows need hub_agg and big_rows");

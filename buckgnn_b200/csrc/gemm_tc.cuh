@@ -653,89 +653,85 @@ template <int kCg, typename T, int kStages, int kStageBytes>
 BG_DEVINL void fused_gather(const GemmParams& p, const int gw, const uint32_t stages_u32, const uint32_t bars_u32,
                             const uint32_t rank, const int tile0, const int tile_stride) {
   constexpr uint32_t kFull = 0xffffffffu;
-  constexpr int kPasses = (32 + kGatherWarps - 1) / kGatherWarps;       // 4-row passes of one warp per K block
+  constexpr uint32_t kRowBytes = kHidden * (uint32_t)sizeof(T);          // rows of fuse_x are contiguous (ldx == 512)
   const int lane = threadIdx.x & 31;
   const int grp = lane >> 3, c = lane & 7;
   const char* xb = reinterpret_cast<const char*>(p.fuse_x) + c * 16;
   const char* hb = reinterpret_cast<const char*>(p.fuse_hub_agg) + c * 16;
-  const size_t row_bytes = (size_t)p.fuse_ldx * sizeof(T);
   const int nkb = p.kblocks[0];
   int per_tile = 0;
   for (int s = 0; s < p.n_seg; ++s) per_tile += p.kblocks[s];
+  // offsets, degree and first neighbour id (lane c holds neighbour c) of this lane group's row in pass `pass`;
+  // a hub row gets its slot in the side buffer instead.  (Re-read for every K block: the 3 KB of indices of a tile
+  // stay in L1, and per-tile register arrays for all passes would have to be unrolled -- the first version's 9 k
+  // instructions of gather code evicted the epilogue from the instruction cache.)
+  auto row_info = [&](int64_t row0, int pass, int32_t& b, int32_t& d, int32_t& v) {
+    const int64_t r = row0 + 4 * pass + grp;
+    b = 0;
+    int32_t e = 0;
+    if (pass < 32 && r < p.m) { b = p.fuse_rowptr[r]; e = p.fuse_rowptr[r + 1]; }
+    d = e - b;
+    const bool is_hub = d > kBigRowThreshold;
+    v = (!is_hub && c < d) ? p.fuse_col[b + c] : 0;
+    if (__any_sync(kFull, is_hub)) {                                    // rare: find the row in big_rows (8 lanes per probe)
+      for (int32_t k = 0; k < p.fuse_n_big; k += 8) {
+        const bool hit = is_hub && k + c < p.fuse_n_big && p.fuse_big_rows[k + c] == (int32_t)r;
+        const uint32_t bits = (__ballot_sync(kFull, hit) >> (grp * 8)) & 0xffu;
+        if (bits) v = k + __ffs(bits) - 1;
+      }
+    }
+  };
   uint32_t cnt0 = 0;                                                    // pipeline slot of this tile's first K block
   for (int tile = tile0; tile < p.n_tiles; tile += tile_stride, cnt0 += (uint32_t)per_tile) {
     const int64_t row0 = (int64_t)tile * (kTileM * kCg) + (int64_t)rank * kTileM;
-    // per pass: offsets, degree and the first 8 neighbour ids of this lane group's row (lane c holds neighbour c);
-    // a hub row keeps its slot in the side buffer instead
-    int32_t beg[kPasses], deg[kPasses], nb[kPasses];
-#pragma unroll
-    for (int i = 0; i < kPasses; ++i) {
-      const int pass = gw + i * kGatherWarps;
-      const int64_t r = row0 + 4 * pass + grp;
-      int32_t b = 0, e = 0;
-      if (pass < 32 && r < p.m) { b = p.fuse_rowptr[r]; e = p.fuse_rowptr[r + 1]; }
-      const int32_t d = e - b;
-      const bool is_hub = d > kBigRowThreshold;
-      int32_t v = (!is_hub && c < d) ? p.fuse_col[b + c] : 0;
-      if (__any_sync(kFull, is_hub)) {                                  // rare: find the row in big_rows (8 lanes per probe)
-        for (int32_t k = 0; k < p.fuse_n_big; k += 8) {
-          const bool hit = is_hub && k + c < p.fuse_n_big && p.fuse_big_rows[k + c] == (int32_t)r;
-          const uint32_t bits = (__ballot_sync(kFull, hit) >> (grp * 8)) & 0xffu;
-          if (bits) v = k + __ffs(bits) - 1;
-        }
-      }
-      beg[i] = b; deg[i] = d; nb[i] = v;
-    }
     for (int kb = 0; kb < nkb; ++kb) {
       const uint32_t cnt = cnt0 + (uint32_t)kb;
       const uint32_t stage = cnt % kStages, parity = (cnt / kStages) & 1u;
+      int32_t b_n, d_n, v_n;
+      row_info(row0, gw, b_n, d_n, v_n);                                // (before the wait: overlaps it)
       mbar_wait(bars_u32 + 8u * (kStages + stage), parity ^ 1u, kTagEmpty);          // the MMAs that read this slot retired
       const uint32_t sa = stages_u32 + stage * kStageBytes;
-      const size_t koff = (size_t)kb * kStageKBytes;
-#pragma unroll
-      for (int i = 0; i < kPasses; ++i) {
-        const int pass = gw + i * kGatherWarps;
-        if (pass >= 32) break;                                          // warp-uniform
+      const uint32_t koff = (uint32_t)kb * kStageKBytes;
+#pragma unroll 1
+      for (int pass = gw; pass < 32; pass += kGatherWarps) {
+        const int32_t beg = b_n, d = d_n, nb = v_n;
         const int R = 4 * pass + grp;
-        const int32_t d = deg[i];
         const bool is_hub = d > kBigRowThreshold;
         const int32_t dn = is_hub ? 0 : d;
+        uint4 q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t n = (uint32_t)__shfl_sync(kFull, nb, (lane & 24) + j);
+          q[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (j < dn) q[j] = ldg_v4(xb + ((size_t)n * kRowBytes + koff));
+        }
+        row_info(row0, pass + kGatherWarps, b_n, d_n, v_n);             // next pass's indices fly with this pass's rows
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        auto add = [&](const uint4& q) {
-          Pack16<T>::add2(acc[0], acc[1], q.x); Pack16<T>::add2(acc[2], acc[3], q.y);
-          Pack16<T>::add2(acc[4], acc[5], q.z); Pack16<T>::add2(acc[6], acc[7], q.w);
+        auto add = [&](const uint4& qq) {
+          Pack16<T>::add2(acc[0], acc[1], qq.x); Pack16<T>::add2(acc[2], acc[3], qq.y);
+          Pack16<T>::add2(acc[4], acc[5], qq.z); Pack16<T>::add2(acc[6], acc[7], qq.w);
         };
-        {
-          uint4 q[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int32_t n = __shfl_sync(kFull, nb[i], (lane & 24) + j);
-            q[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (j < dn) q[j] = ldg_v4(xb + (size_t)n * row_bytes + koff);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) add(q[j]);
-        }
+        for (int j = 0; j < 8; ++j) add(q[j]);
         int32_t wmax = dn;                                              // more than 8 neighbours somewhere in the warp?
         wmax = max(wmax, __shfl_xor_sync(kFull, wmax, 8));
         wmax = max(wmax, __shfl_xor_sync(kFull, wmax, 16));
         for (int32_t base = 8; base < wmax; base += 8) {
-          const int32_t idx = (base + c < dn) ? p.fuse_col[beg[i] + base + c] : 0;
-          uint4 q[8];
+          const int32_t idx = (base + c < dn) ? p.fuse_col[beg + base + c] : 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int32_t n = __shfl_sync(kFull, idx, (lane & 24) + j);
+            const uint32_t n = (uint32_t)__shfl_sync(kFull, idx, (lane & 24) + j);
             q[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (base + j < dn) q[j] = ldg_v4(xb + (size_t)n * row_bytes + koff);
+            if (base + j < dn) q[j] = ldg_v4(xb + ((size_t)n * kRowBytes + koff));
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) add(q[j]);
         }
         uint4 o;
         if (is_hub) {
-          o = ldg_v4(hb + (size_t)nb[i] * (kHidden * sizeof(T)) + koff);
+          o = ldg_v4(hb + ((size_t)(uint32_t)nb * kRowBytes + koff));
         } else {
           if (p.fuse_mean) {
             const float rd = 1.f / (float)max(d, 1);
