@@ -247,8 +247,8 @@ def modes_section(args, dev, resident, world, G, barrier):
 
 def train_section(args, dev, world, rank, barrier):
     """BASELINE.json configs[3]: TRAIN_FINAL-style training step, GraphSage_meanAggr 6x512, 16 graphs per GPU, dropout
-    0.1, relative-error loss, Adam; graph-sharded, gradients all-reduced (mean) over NCCL bucket by bucket under the
-    backward pass (dist.GradSync).  `allreduce_exposed_ms` = step time with the collectives - step time without them."""
+    0.1, relative-error loss, Adam; graph-sharded, gradients all-reduced (mean) over NCCL from one flat buffer
+    (dist.GradSync: buckets of >= 8 M elements can start under the backward pass; this model's 3.3 M go in one collective).  `allreduce_exposed_ms` = step time with the collectives - step time without them."""
     import torch
     import torch.distributed as dist
     from buckgnn_b200.loss import EigenvalueRelativeLoss
@@ -307,7 +307,8 @@ def train_section(args, dev, world, rank, barrier):
         ms_local, _ = timed(steps)
         out["ms_per_step_without_allreduce"] = ms_local
         out["allreduce_exposed_ms"] = ms - ms_local
-        out["allreduce"] = "per-layer buckets of one flat fp32 buffer, ncclAllReduce(avg) on a second stream under the backward"
+        out["allreduce"] = ("one flat fp32 gradient buffer the backward kernels write into; ncclAllReduce(avg) on a second stream in "
+                            "buckets of >= 8 M elements (latency-bound collectives: one for this model; dist.GradSync)")
     return out
 
 

@@ -7,6 +7,7 @@ communication is one small all_gather of the per-graph predictions.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Sequence
 
 import torch
@@ -110,7 +111,7 @@ def allreduce_gradients(params, group=None, average: bool = True) -> int:
 
 
 class GradSync:
-    """Bucketed gradient all-reduce that overlaps the backward pass (BASELINE.json configs[3]).
+    """Bucketed gradient all-reduce that can overlap the backward pass (BASELINE.json configs[3]).
 
     All gradients of the parameters a model trains live in ONE pre-allocated fp32 buffer, laid out in
     `train.trainable_parameters(model)` order; the backward kernels write straight into its slices (no `torch.cat`,
@@ -135,10 +136,14 @@ class GradSync:
         self.comm_stream = torch.cuda.Stream(device=device) if self.cuda else None
         self.works, self.launched = [], set()
         self.pending, self.pending_elems = [], 0
-        # collectives of ~1 M elements: at 0.5 M per SAGE layer that is one per two layers -- each collective costs the
-        # host ~50 us of launch work and the 16-graph training step is partly host-bound (measured: 8 buckets exposed
-        # 0.46 ms at 2 GPUs, profiles/r02_*)
-        self.min_bucket_elems = 1 << 20
+        # Bucket size (elements).  Round 2, 8 GPUs (tools/train_bucket_probe.py, profiles/r02_train_bucket_probe_8gpu.jsonl):
+        # an NCCL all-reduce over NVSwitch costs ~0.1 ms whether it carries 0.8 M or 3.3 M elements (latency-bound, NVLS),
+        # and every collective is a point where the ranks wait for the slowest one -- four 1 M-element buckets took
+        # 0.54-0.66 ms of collective time with 0.15-0.31 ms exposed, two buckets 0.28 / 0.12-0.13 ms, ONE bucket at the end
+        # of the backward 0.10-0.13 / 0.02-0.11 ms (step 8.42-8.43 ms against 8.44-8.64 ms).  So buckets are large: the
+        # 3.3 M gradients of the GraphSAGE models go in one collective, a model with more than 8 M trainable elements
+        # (EA-GNN) still overlaps its first buckets with the backward.  BUCKGNN_GRAD_BUCKET_ELEMS overrides.
+        self.min_bucket_elems = int(os.environ.get("BUCKGNN_GRAD_BUCKET_ELEMS", 1 << 23))
         self.events = []          # (start, end) CUDA events of every collective of the last step (timing)
         self.time_collectives = False
 
