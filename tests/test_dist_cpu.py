@@ -122,6 +122,7 @@ def _sync_worker(rank, world, port, q):
     sync = GradSync(params, "cpu")
     out = []
     for step in range(2):
+        sync.min_bucket_elems = 1 if step == 0 else 1 << 23       # every group its own collective / one collective at finish
         store = GradStore("cpu", sync)
         g0, acc0 = store.get(params[0])
         g0.copy_(torch.full((3, 5), float(rank + 1 + step)))
