@@ -107,6 +107,28 @@ def test_cuda_forward_matches_golden(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sage_mean_6x512", "sage_sum_4x512", "sage_mean_6x512_stiffened_virtual",
+                                  "sage_mean_6x512_no_super_virtual", "sage_mean_supernode_only"])
+def test_cuda_fused_sage_layer_matches_golden(name):
+    """The fused SAGE layer (bg_sage_fused512, fp16 operands) against the numbers generated from the reference's own
+    Models/BuckGNN.py -- with hub rows, without any (no super node: n_big = 0), degree-11 stiffened meshes, and the
+    super-node-only pooling that reads exactly the hub rows' outputs."""
+    from buckgnn_b200.model import BuckGNN
+    g = GOLD["forward"][name]
+    ref = mk.seeded_oracle(g["cfg"])
+    ours = BuckGNN(**g["cfg"], precision="fp16")
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to("cuda:0").eval()
+    ours.fuse_aggregate = True
+    b = make_batch(**g["batch"]).to("cuda:0")
+    with torch.no_grad():
+        pred, _ = ours(b.x, b.edge_index, b.edge_attr, b.batch)
+    want = torch.tensor(g["pred"], dtype=torch.float64)
+    rel = ((pred.double().cpu().reshape(-1) - want).abs() / want.abs().clamp(min=1e-3)).max().item()
+    assert rel < 1e-3, rel
+
+
+@pytest.mark.gpu
 def test_cuda_training_step_matches_golden():
     from buckgnn_b200.model import BuckGNN
     g = GOLD["training"]["sage_mean_3x512_step"]
