@@ -213,3 +213,25 @@ def test_ctypes_signatures_match_the_header_prototypes():
                 assert t is C.c_int, (name, a, t)
             else:
                 raise AssertionError(f"unclassified parameter {a!r} of {name}")
+
+
+def test_gemm_register_budget_by_warpgroup():
+    """setmaxnreg acts on whole warpgroups (4 warps) and `inc` BLOCKS until the CTA's register pool has room: a budget
+    above 64 K registers, or two different values inside one warpgroup, hangs the kernel with no watchdog able to
+    see it (round 2: the first fused-layer build).  Static check of the numbers in gemm_tc.cuh."""
+    import re
+    src = open(os.path.join(ROOT, "buckgnn_b200", "csrc", "gemm_tc.cuh")).read()
+    dec_producer = int(re.search(r"else if \(warp < kEpiFirstWarp\) \{\s*setmaxnreg_dec<(\d+)>", src).group(1))
+    dec_gather = int(re.search(r"if constexpr \(kFuse\) \{\s*setmaxnreg_dec<(\d+)>", src).group(1))
+    inc_fused, inc_plain = map(int, re.search(r"if constexpr \(kFuse\) setmaxnreg_inc<(\d+)>\(\); else setmaxnreg_inc<(\d+)>\(\);", src).groups())
+    threads_plain = int(re.search(r"constexpr int kGemmThreads = (\d+);", src).group(1))
+    threads_fused = int(re.search(r"constexpr int kGemmThreadsFused = (\d+);", src).group(1))
+    gather_warps = int(re.search(r"constexpr int kGatherWarps = (\d+);", src).group(1))
+    for v in (dec_producer, dec_gather, inc_fused, inc_plain):
+        assert 24 <= v <= 256 and v % 8 == 0
+    assert gather_warps == 4                                               # exactly one warpgroup
+    # plain kernel: warpgroup 0 (producer, MMA issuer, two idle warps) + two epilogue warpgroups
+    assert threads_plain == 3 * 128 and 128 * (dec_producer + 2 * inc_plain) <= 65536
+    # fused kernel: + the gather warpgroup; launch allocation = 65536 / 512 registers per thread
+    assert threads_fused == 4 * 128 and 128 * (dec_producer + 2 * inc_fused + dec_gather) <= 65536
+    assert dec_producer <= 65536 // threads_fused and dec_gather <= 65536 // threads_fused <= inc_fused
