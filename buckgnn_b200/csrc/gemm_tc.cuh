@@ -750,13 +750,21 @@ BG_DEVINL void fused_gather(const GemmParams& p, const int gw, const uint32_t st
         else mbar_arrive_cluster_release(bars_u32 + 8u * stage, 0);
       }
     }
-    // The other segments' slots are filled by the producer alone, but their "empty" phases are observed here too, one
-    // by one: a parity wait can only tell the current phase from the previous one, so a warp that skipped the two uses
-    // a slot has between this tile's aggregate K blocks and the next tile's would take the phase of the FIRST skipped
-    // use for the one it is waiting for and overwrite a tile the tensor core has not read yet.
+    // The other segments' slots are filled by the producer alone, but the gather warps take part in every use of
+    // every slot all the same -- wait for `empty`, meet, one of them arrives on `full`: a parity wait can only tell the
+    // barrier's current phase from the previous one, so an agent that skips uses can take the phase of a skipped use for
+    // its own (round 2, first build: fast gathers overwrote tiles the tensor core had not read), and one that merely
+    // watches them without being waited for can fall two phases behind and wait forever.  With its arrival required
+    // for every phase, neither can happen under any scheduling (host model: tests/test_ring_protocol_cpu.py).
     for (int kb = nkb; kb < per_tile; ++kb) {
       const uint32_t cnt = cnt0 + (uint32_t)kb;
-      mbar_wait(bars_u32 + 8u * (kStages + cnt % kStages), ((cnt / kStages) & 1u) ^ 1u, kTagEmpty);
+      const uint32_t stage = cnt % kStages;
+      mbar_wait(bars_u32 + 8u * (kStages + stage), ((cnt / kStages) & 1u) ^ 1u, kTagEmpty);
+      named_bar_sync(2, kGatherWarps * 32);
+      if (gw == 0 && lane == 0) {
+        if (kCg == 1 || rank == 0) mbar_arrive(bars_u32 + 8u * stage);
+        else mbar_arrive_cluster_release(bars_u32 + 8u * stage, 0);
+      }
     }
   }
 }
@@ -794,7 +802,8 @@ k_gemm512(const __grid_constant__ GemmParams p) {
   if (kCg == 2) cluster_sync();                // both CTAs resident before the paired TMEM alloc
   if (warp == 1) {
     if (elect_one()) {
-      // (kFuse: a stage is full when the producer AND the gather warps of both CTAs have delivered)
+      // (kFuse: a stage is full when the producer AND the gather warps of both CTAs have delivered -- the gather warps
+      //  arrive on every use of every slot, also where they have nothing to write: see fused_gather)
       for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), kFuse ? 2 * kCg : kCg); mbar_init(empty_bar(s), 1); }
       mbar_init(tmem_full_bar, 1);
       mbar_init(tmem_empty_bar, kCg * 256);
@@ -883,10 +892,6 @@ k_gemm512(const __grid_constant__ GemmParams p) {
                 const bool gathered = kFuse && s == 0;                  // this stage's A half comes from the gather warps
                 if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * ((load_a && !gathered ? kATileBytes : 0) + (load_b ? Cfg::kBTileBytes : 0)));
                 else mbar_arrive_cluster(full_bar(stage), 0);
-                if (kFuse && !gathered) {                               // no gather arrival on this stage: the producer stands in
-                  if (rank == 0) mbar_arrive(full_bar(stage));
-                  else mbar_arrive_cluster(full_bar(stage), 0);
-                }
                 if (load_a && !gathered) tma_load_2d_cg2(sa, map_a, full_bar(stage), k0, row0);
                 if (load_b) {
 #pragma unroll
